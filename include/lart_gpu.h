@@ -1,0 +1,277 @@
+/* lart_gpu.h — C ABI of the B200-native Cartesian photon-transport engine.
+ *
+ * This is the drop-in boundary for ONE path of LaRT v2.00: the Cartesian-grid
+ * Monte-Carlo photon loop.  Every entry point below is what a Fortran
+ * ISO_C_BINDING interface block (shim/lart_gpu_shim.f90) binds;
+ * each cites the reference interface it replaces (paths relative to the
+ * reference tree, file:line).
+ *
+ *   - plain C, `extern "C"`, POD structs with explicit int32/int64/double
+ *     members and raw pointers; no C++/torch types cross this boundary;
+ *   - every function returns int: 0 = OK, non-zero = error; the message is
+ *     retrievable through lart_gpu_last_error() (reference convention: print,
+ *     then MPI_ABORT — src/setup.f90:132-135; the shim does the abort);
+ *   - all arrays are Fortran column-major, x fastest, exactly as grid_type
+ *     holds them (src/define.f90:131-148); indices in the API are 1-based as
+ *     in the reference, conversion to 0-based happens inside the library;
+ *   - the library never frees or reallocates host memory; device memory is
+ *     owned by the opaque handle;
+ *   - tallies come back as raw, un-normalised weighted sums that are ADDED
+ *     into caller-owned buffers (normalisation stays with the host,
+ *     src/output_sum_rect.f90:151-487).
+ *
+ * Called from one host thread per process (the reference is not re-entrant
+ * either: global par/observer/RNG state, src/define.f90:729-737).
+ */
+#ifndef LART_GPU_H
+#define LART_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LART_MAX_OBSERVERS 181 /* src/define.f90:77 */
+
+/* par%spectral_type (src/generate_photon.f90:243-300) */
+enum {
+  LART_SPEC_MONO = 0,      /* any other string: x = xfreq0                 */
+  LART_SPEC_VOIGT = 1,     /* 'voigt'   : x0 + rand_voigt(a_cell)           */
+  LART_SPEC_VOIGT0 = 2,    /* 'voigt0'  : x0 + rand_voigt(a0)*Dfreq0/Dfreq  */
+  LART_SPEC_CONTINUUM = 3, /* 'continuum': uniform in [xfreq_min,xfreq_max] */
+  LART_SPEC_GAUSSIAN = 4   /* 'gaussian': x0 + gauss*sigma_x (ref. units)   */
+};
+
+/* par%source_geometry (src/generate_photon.f90:33-132) */
+enum {
+  LART_SRC_POINT = 0,         /* default: (xs,ys,zs)_point                  */
+  LART_SRC_UNIFORM = 1,       /* 'uniform': uniform in the box              */
+  LART_SRC_UNIFORM_SPHERE = 2 /* 'uniform_sphere'/'sphere': r<source_rmax   */
+};
+
+/* grid_type scalars + arrays — src/define.f90:117-148; built by
+ * src/grid_mod_car.f90:73-209,273-284,487-538,786-803. */
+typedef struct lart_grid {
+  int32_t nx, ny, nz;
+  int32_t nxfreq;
+  double xmin, ymin, zmin;
+  double xmax, ymax, zmax;
+  double dx, dy, dz;
+  double Dfreq_ref;            /* grid%Dfreq_ref   (grid_mod_car.f90:245)   */
+  double xfreq_min, xfreq_max; /* grid%xfreq_min/max (:1496-1498)           */
+  double dxfreq;               /* grid%dxfreq                               */
+  double xcrit, xcrit2;        /* grid%xcrit(2): global core-skip (:1186-1219) */
+  double rmax;                 /* par%rmax (<=0: none); used by allph records  */
+  const double *xface;         /* (nx+1)  xface(i) = (i-1)*dx + xmin        */
+  const double *yface;         /* (ny+1)                                    */
+  const double *zface;         /* (nz+1)                                    */
+  const double *rhokap;        /* (nx,ny,nz) dtau = rhokap*H(x,a)*ds        */
+  const double *voigt_a;       /* (nx,ny,nz)                                */
+  const double *Dfreq;         /* (nx,ny,nz)                                */
+  const double *vfx, *vfy, *vfz; /* (nx,ny,nz) bulk velocity / v_th(cell)   */
+  const double *rhokapD;       /* (nx,ny,nz) dust extinction, or NULL if DGR==0 */
+} lart_grid;
+
+/* the members of params_type the path reads — src/define.f90:209-544 */
+typedef struct lart_params {
+  int64_t nphotons;  /* par%nphotons: photon ids run 1..nphotons            */
+  uint64_t seed;     /* Philox key; replaces par%iseed (random_mt.f90:889-956) */
+  double xfreq0;
+  double xs_point, ys_point, zs_point;
+  double source_rmax;
+  double DGR, albedo, hgg;
+  double voigt_a0, Dfreq0;   /* 'voigt0' emission                           */
+  double gaussian_sigma_x;   /* 'gaussian': sigma in reference Doppler units */
+  double mu_min, dmu;        /* Jmu binning (setup.f90:375-382)             */
+  int32_t nmu;
+  int32_t spectral_type;     /* LART_SPEC_*                                 */
+  int32_t source_geometry;   /* LART_SRC_*                                  */
+  int32_t comoving_source;
+  int32_t recoil;
+  int32_t core_skip, core_skip_global;
+  int32_t use_stokes;
+  int32_t use_reduced_wgt;
+  int32_t save_Jin, save_Jabs, save_Jmu;
+  int32_t save_peeloff, save_peeloff_2D, save_peeloff_3D, save_direc0;
+  int32_t save_all_photons;
+  int32_t xy_periodic;       /* with nx==ny==1 binds the _zonly ray tracers
+                                (setup.f90:957-965); other periodic modes are
+                                rejected with an error                      */
+  int32_t nobs;
+} lart_params;
+
+/* line_type members — src/define.f90:639-656; values from
+ * src/line_mod.f90:1241-1270 (host owns the numbers, incl. the g_recoil0 quirk) */
+typedef struct lart_line {
+  int32_t line_type; /* only 1 (singlet, Ly-alpha without fine structure)  */
+  int32_t pad_;
+  double E1, E2, E3;
+  double g_recoil0;
+  double DnuHK_Hz;
+} lart_line;
+
+/* observer_type members — src/define.f90:547-560; rmatrix is the Fortran
+ * (3,3) array in memory order, i.e. rmatrix[(r-1) + 3*(c-1)] = rmatrix(r,c). */
+typedef struct lart_observer {
+  double x, y, z;
+  double rmatrix[9];
+  double dxim, dyim;
+  int32_t nxim, nyim;
+} lart_observer;
+
+/* scattering_matrix_type — src/define.f90:616-625 (dust + Stokes only) */
+typedef struct lart_scatt_mat {
+  int32_t nPDF;
+  int32_t pad_;
+  const double *coss, *S11, *S12, *S33, *S34; /* (nPDF), S* already normalised */
+  const double *phase_PDF;                   /* (nPDF-1) alias probabilities   */
+  const int32_t *alias;                      /* (nPDF-1) 1-based, 0 = none     */
+} lart_scatt_mat;
+
+typedef struct lart_config {
+  lart_grid grid;
+  lart_params par;
+  lart_line line;
+  lart_scatt_mat scatt_mat;        /* nPDF = 0 when unused                  */
+  const lart_observer *observers;  /* par.nobs entries                      */
+  int32_t device;                  /* CUDA device ordinal                   */
+  int32_t pool_slots;              /* photons in flight; 0 = auto           */
+  int32_t quantum;                 /* scattering events per slot per launch; 0 = auto */
+  int32_t flags;                   /* LART_FLAG_*                           */
+} lart_config;
+
+enum {
+  LART_FLAG_SOA_GRID = 1,   /* walk the six SoA arrays instead of packed cell records */
+  LART_FLAG_NO_WARP_AGG = 2 /* plain atomics for peel tallies (ablation)      */
+};
+
+/* per-observer output cubes (src/define.f90:561-600); frequency fastest:
+ * cube(ixf,ix,iy) at [(ixf-1) + nxfreq*((ix-1) + nxim*(iy-1))]. NULL = skip. */
+typedef struct lart_observer_out {
+  double *scatt, *direc, *direc0, *I, *Q, *U, *V;                      /* 3-D */
+  double *scatt_2D, *direc_2D, *direc0_2D, *I_2D, *Q_2D, *U_2D, *V_2D; /* 2-D */
+} lart_observer_out;
+
+/* allph record — src/define.f90:602-613; written by photon id (1-based, slot id-1) */
+typedef struct lart_allph_out {
+  double *rp0, *rp, *xfreq1, *xfreq2, *nscatt_gas, *nscatt_dust, *I, *Q, *U, *V;
+} lart_allph_out;
+
+/* work counters: the units the roofline is computed from */
+typedef struct lart_counters {
+  double n_photons_done;
+  double n_scatter;     /* resonance + dust scattering events (unweighted)  */
+  double n_cellsteps;   /* DDA cell steps, all ray kinds                    */
+  double n_peel;        /* peel-off rays traced                             */
+  double n_rng;         /* uniforms drawn                                   */
+  double n_reject_iter; /* iterations of the rejection loops                */
+} lart_counters;
+
+typedef struct lart_tallies {
+  double *Jout, *Jin, *Jabs; /* (nxfreq) — grid%Jout/Jin/Jabs             */
+  double *Jmu;               /* (nxfreq,nmu)                               */
+  lart_observer_out *obs;    /* par.nobs entries (or NULL)                 */
+  lart_allph_out allph;      /* all NULL unless save_all_photons           */
+  double nscatt_gas, nscatt_dust; /* par%nscatt_* : weighted sums, ADDED   */
+  lart_counters counters;    /* ADDED                                      */
+} lart_tallies;
+
+typedef struct lart_gpu_ctx *lart_gpu_handle;
+
+/* ---- whole-path drop-in: one more implementation of run_sim ------------- */
+
+/* Upload grid/par/line/observers, allocate photon pool and zeroed tallies.
+ * Replaces nothing by itself; precedes the call that replaces
+ * `call run_simulation(grid)` (src/main.f90:42, interface src/define.f90:832-838). */
+int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out);
+
+/* Run photons id = first_id, first_id+stride, ... (count of them) to completion:
+ * generate_photon + forced first scattering + {raytrace_to_tau, scattering,
+ * peeling}* — replaces the body of run_equal_number
+ * (src/run_simulation_mod.f90:150-202; partition rule :150). */
+int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride);
+
+/* Bounded-work variant of the same loop (used for benchmarking heavy-tailed
+ * cases): begin() queues the photon ids, each step() launches ONE pass of the
+ * persistent kernel in which every pool slot processes at most `quantum`
+ * scattering events (finished photons are refilled from the queue);
+ * *in_flight returns photons still alive or queued. */
+int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride);
+int lart_gpu_step(lart_gpu_handle h, int32_t quantum, int64_t *in_flight);
+int lart_gpu_sync(lart_gpu_handle h);
+
+/* Add the device tallies into host buffers — the data half of output_reduce
+ * (src/output_sum_rect.f90:7-149; src/memory_mod_mpi.f90:366-458). */
+int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out);
+int lart_gpu_reset_tallies(lart_gpu_handle h);
+int lart_gpu_destroy(lart_gpu_handle h);
+
+/* Contiguous FP64 device buffer holding every reducible tally (Jout|Jin|Jabs|
+ * Jmu|cubes|images|scalars|counters): ONE sum-reduce over it replaces the
+ * reference's per-array MPI_REDUCE (src/memory_mod_mpi.f90:380-390,441-453).
+ * The allph buffer is slot-per-photon-id (disjoint across ranks; also summed). */
+int lart_gpu_tally_buffer(lart_gpu_handle h, void **dev_ptr, int64_t *n_doubles);
+int lart_gpu_allph_buffer(lart_gpu_handle h, void **dev_ptr, int64_t *n_doubles);
+/* CUDA stream (cudaStream_t) the engine launches on, for event timing. */
+int lart_gpu_stream(lart_gpu_handle h, void **stream);
+/* event-timed duration of the transport kernels since create/reset, ms */
+int lart_gpu_kernel_ms(lart_gpu_handle h, double *ms, int64_t *launches);
+
+const char *lart_gpu_last_error(void);
+
+/* ---- unit-level batched equivalents of the finer plugin points ----------
+ * (src/define.f90:741-784,820-876): arrays of photons instead of one photon.
+ * All pointers are HOST pointers; n elements each. */
+
+/* calc_voigt -> voigt_seon2 (src/line_mod.f90:38-47, src/voigt_mod.f90:541-733) */
+int lart_gpu_voigt_batch(int64_t n, const double *x, const double *a, double *H);
+
+/* raytrace_to_edge (src/raytrace_car.f90:410-508; _zonly :1138-1234).
+ * icell/jcell/kcell are 1-based inputs.  Optional trace: for ray r the first
+ * min(nsteps,trace_cap) visited cells, linear 0-based index, into
+ * trace_cells[r*trace_cap + s] (NULL = no trace). */
+int lart_gpu_raytrace_edge_batch(lart_gpu_handle h, int64_t n,
+                                 const double *x, const double *y, const double *z,
+                                 const double *kx, const double *ky, const double *kz,
+                                 const double *xfreq,
+                                 const int32_t *icell, const int32_t *jcell, const int32_t *kcell,
+                                 double *tau, int32_t *nsteps,
+                                 int32_t trace_cap, int32_t *trace_cells);
+
+/* raytrace_to_tau (src/raytrace_car.f90:1425-1648; _zonly :2519-2675), without
+ * the Jout tally: returns the updated photon (position, cell, frequency,
+ * inside flag, and on escape the lab-frame xfreq_ref). In-place on x..kcell. */
+int lart_gpu_raytrace_tau_batch(lart_gpu_handle h, int64_t n,
+                                double *x, double *y, double *z,
+                                const double *kx, const double *ky, const double *kz,
+                                double *xfreq,
+                                int32_t *icell, int32_t *jcell, int32_t *kcell,
+                                const double *tau_in,
+                                int32_t *inside, double *xfreq_ref, int32_t *nsteps);
+
+/* Random variates on the path, one Philox stream per element (key = seed,
+ * stream id = ids[i], starting at draw 0):
+ *   kind 0: rand_number                (src/random_mt.f90:579-630 mapping)
+ *   kind 1: rand_gauss                 (:964-988)
+ *   kind 2: rand_resonance_vz(p0,p1)   (:2562-2696)  p0 = x, p1 = a
+ *   kind 3: rand_resonance(p0)         (:2974-2993)  p0 = E1
+ *   kind 4: rand_henyey_greenstein(p0) (:3022-3042)  p0 = g
+ *   kind 5: rand_voigt(p0)             (:3075-3083)  p0 = a
+ * ndraw variates per element, out[i*ndraw + j]. */
+int lart_gpu_sample_batch(int32_t kind, uint64_t seed, int64_t n, const int64_t *ids,
+                          const double *p0, const double *p1, int32_t ndraw, double *out);
+
+/* car_xcrit_local (src/grid_mod_car.f90:1598-1629) */
+int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n,
+                         const double *x, const double *y, const double *z,
+                         const int32_t *icell, const int32_t *jcell, const int32_t *kcell,
+                         double *xcrit);
+
+/* library/ABI version: major*10000 + minor*100 + patch */
+int lart_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LART_GPU_H */

@@ -1,0 +1,1412 @@
+// lart_oracle.cpp — CPU ORACLE (test infrastructure, NOT product code).
+//
+// A scalar, one-photon-at-a-time FP64 restatement of the reference's Cartesian
+// photon loop (LaRT v2.00), written to be read side by side with the Fortran.
+// Every function cites the reference file:line it follows (paths relative to
+// the reference tree).  It exists so that the CUDA path has something to be
+// checked against: only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.  The product
+// (lart_b200/) never links, imports or falls back to it.
+//
+// PARITY PINNING.  The reference ships no unit-level golden vectors and cannot
+// be compiled here (no Fortran/MPI toolchain), so at function level this oracle
+// is "parity unpinned": it is pinned only (a) by construction against the cited
+// lines, (b) by the whole-run known answers the reference's logs hold
+// (<N_scatt> = 1.7898e3 / 2.8225e4, voigt_a, N(HI)_pole — tests/test_oracle_pins.py),
+// (c) by independent mathematics (Harris functions, scipy wofz, Neufeld/Dijkstra
+// analytic spectra, Philox and MT19937-64 known-answer vectors).
+//
+// The struct layouts come from the product's public header include/lart_gpu.h
+// (POD declarations only) so both sides consume identical host arrays.
+//
+// Build: see oracle/Makefile (g++ -O3 -ffp-contract=off; no FMA contraction so
+// the DDA arithmetic is plain IEEE, matching the kernel's __dadd_rn/__dmul_rn).
+
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/lart_gpu.h"
+#include "voigt_tables.inc"
+
+namespace {
+
+constexpr double kPi = 3.141592653589793238462643383279502884197;      // define.f90:45
+constexpr double kTwoPi = 6.283185307179586476925286766559005768394;   // define.f90:46
+constexpr double kFourPi = 12.56637061435917295385057353311801153679;  // define.f90:47
+constexpr double kHalfPi = kPi / 2.0;
+constexpr double kRad2Deg = 180.0 / kPi;                               // define.f90:57
+constexpr double kHugest = DBL_MAX;                                    // define.f90:38
+constexpr double kTauHuge = 745.2;                                     // raytrace_car.f90:432
+
+// ---------------------------------------------------------------------------
+// Uniform generators.  Both map a 64-bit word w to ((w>>12)+0.5)*2^-52, an
+// OPEN interval (0,1) — random_mt.f90:628-629.
+// ---------------------------------------------------------------------------
+inline double word_to_open01(uint64_t w) {
+  return (static_cast<double>(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+// MT19937-64 — random_mt.f90:579-630 (generation + tempering), :486-498 (init_mt).
+struct Mt64 {
+  static constexpr int N = 312, M = 156;
+  uint64_t mt[N];
+  int mti = N + 1;
+  void init(int64_t seed) {
+    mt[0] = static_cast<uint64_t>(seed);
+    for (int i = 1; i < N; ++i)
+      mt[i] = 6364136223846793005ULL * (mt[i - 1] ^ (mt[i - 1] >> 62)) + static_cast<uint64_t>(i);
+    mti = N;
+  }
+  uint64_t next() {
+    static const uint64_t mag01[2] = {0ULL, 0xB5026F5AA96619E9ULL};
+    const uint64_t UM = 0xFFFFFFFF80000000ULL, LM = 0x7FFFFFFFULL;
+    if (mti >= N) {
+      if (mti == N + 1) init(5489);
+      int i;
+      for (i = 0; i < N - M; ++i) {
+        uint64_t x = (mt[i] & UM) | (mt[i + 1] & LM);
+        mt[i] = mt[i + M] ^ (x >> 1) ^ mag01[x & 1ULL];
+      }
+      for (; i < N - 1; ++i) {
+        uint64_t x = (mt[i] & UM) | (mt[i + 1] & LM);
+        mt[i] = mt[i + (M - N)] ^ (x >> 1) ^ mag01[x & 1ULL];
+      }
+      uint64_t x = (mt[N - 1] & UM) | (mt[0] & LM);
+      mt[N - 1] = mt[M - 1] ^ (x >> 1) ^ mag01[x & 1ULL];
+      mti = 0;
+    }
+    uint64_t x = mt[mti++];
+    x ^= (x >> 29) & 0x5555555555555555ULL;
+    x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+    x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+    x ^= (x >> 43);
+    return x;
+  }
+};
+
+// Philox4x32-10 (Salmon et al. 2011, Random123).  Not in the reference: it is
+// the counter-based generator the north star prescribes for the device; the
+// oracle carries it so GPU and oracle can be compared photon by photon.
+//   key     = (seed_lo, seed_hi)
+//   counter = (id_lo, id_hi, block_lo, block_hi)
+// One block yields two uniforms: word0 = c0 | c1<<32, word1 = c2 | c3<<32.
+inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c[0];
+    uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c[2];
+    uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = static_cast<uint32_t>(p1);
+    uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = static_cast<uint32_t>(p0);
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+struct Counters {
+  double n_photons_done = 0, n_scatter = 0, n_cellsteps = 0, n_peel = 0, n_rng = 0, n_reject_iter = 0;
+};
+
+// rand_number() + rand_gauss() state.  MT mode keeps the Marsaglia spare across
+// photons like the Fortran `save` variable (random_mt.f90:968-987); Philox mode
+// restarts stream and spare for every photon.
+struct Rng {
+  int mode = 0;  // 0 = MT19937-64, 1 = Philox
+  Mt64 mt;
+  uint64_t seed = 0, stream = 0, ndraw = 0;
+  uint64_t spare_word = 0;
+  bool gauss_stored = false;
+  double gset = 0.0;
+  Counters *cnt = nullptr;
+
+  void start_stream(uint64_t id) {
+    if (mode == 1) {
+      stream = id;
+      ndraw = 0;
+      gauss_stored = false;
+    }
+  }
+  double uniform() {
+    if (cnt) cnt->n_rng += 1;
+    if (mode == 0) return word_to_open01(mt.next());
+    uint64_t w;
+    if ((ndraw & 1ULL) == 0) {
+      uint64_t blk = ndraw >> 1;
+      uint32_t c[4] = {static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32),
+                       static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32)};
+      philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+      w = static_cast<uint64_t>(c[0]) | (static_cast<uint64_t>(c[1]) << 32);
+      spare_word = static_cast<uint64_t>(c[2]) | (static_cast<uint64_t>(c[3]) << 32);
+    } else {
+      w = spare_word;
+    }
+    ++ndraw;
+    return word_to_open01(w);
+  }
+  // rand_gauss1 — random_mt.f90:964-988 (Marsaglia polar, returns v2*f, stores v1*f)
+  double gauss() {
+    if (gauss_stored) {
+      gauss_stored = false;
+      return gset;
+    }
+    double v1, v2, rsq;
+    for (;;) {
+      v1 = 2.0 * uniform() - 1.0;
+      v2 = 2.0 * uniform() - 1.0;
+      rsq = v1 * v1 + v2 * v2;
+      if (cnt) cnt->n_reject_iter += 1;
+      if (rsq > 0.0 && rsq < 1.0) break;
+    }
+    rsq = std::sqrt(-2.0 * std::log(rsq) / rsq);
+    gset = v1 * rsq;
+    gauss_stored = true;
+    return v2 * rsq;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// voigt_seon2 — voigt_mod.f90:541-733.  Tables are 0-based here: h(k) -> H[k-1].
+// ---------------------------------------------------------------------------
+double voigt_seon2(double vin, double a) {
+  const double one_sqrtPI = 0.56418958354775628695;
+  double v = (vin < 0.0) ? -vin : vin;  // :686-690 (no abs())
+  if (v < 1.0) {                        // :691-700
+    double vv = v * 20.0;
+    int k1 = static_cast<int>(vv) + 1, k2 = k1 + 1;
+    double y1 = ORACLE_H0[k1 - 1] + a * (ORACLE_H1[k1 - 1] + a * ORACLE_H2[k1 - 1]);
+    double y2 = ORACLE_H0[k2 - 1] + a * (ORACLE_H1[k2 - 1] + a * ORACLE_H2[k2 - 1]);
+    return y1 + (y2 - y1) * (vv - static_cast<double>(k1 - 1));
+  } else if (v < 5.0) {                 // :701-717
+    double vv = v * 20.0;
+    int k1 = static_cast<int>(vv), k2 = k1 + 1, k3 = k1 + 2;
+    double y1 = ORACLE_H0[k1 - 1] + a * (ORACLE_H1[k1 - 1] + a * (ORACLE_H2[k1 - 1] + a * ORACLE_H3[k1 - 1]));
+    double y2 = ORACLE_H0[k2 - 1] + a * (ORACLE_H1[k2 - 1] + a * (ORACLE_H2[k2 - 1] + a * ORACLE_H3[k2 - 1]));
+    double y3 = ORACLE_H0[k3 - 1] + a * (ORACLE_H1[k3 - 1] + a * (ORACLE_H2[k3 - 1] + a * ORACLE_H3[k3 - 1]));
+    double u1 = static_cast<double>(k1 - 1), u2 = static_cast<double>(k2 - 1), u3 = static_cast<double>(k3 - 1);
+    return 0.5 * y1 * (vv - u2) * (vv - u3) - y2 * (vv - u1) * (vv - u3) + 0.5 * y3 * (vv - u1) * (vv - u2);
+  } else if (v < 10.0) {                // :718-726
+    double vv = v * 20.0;
+    int k1 = static_cast<int>(vv) + 1, k2 = k1 + 1;
+    double a2 = a * a;
+    double y1 = a * (ORACLE_H1[k1 - 1] + a2 * ORACLE_H3[k1 - 1]);
+    double y2 = a * (ORACLE_H1[k2 - 1] + a2 * ORACLE_H3[k2 - 1]);
+    return y1 + (y2 - y1) * (vv - static_cast<double>(k1 - 1));
+  }
+  double v2 = 1.0 / (v * v);            // :727-731
+  return one_sqrtPI * a * v2 * (1.0 + ((1.5 - a * a) + 3.75 * v2) * v2);
+}
+
+// ---------------------------------------------------------------------------
+// photon_type — define.f90:80-111 (the members this path touches)
+// ---------------------------------------------------------------------------
+struct Photon {
+  int64_t id = 0;
+  double nscatt_gas = 0, nscatt_dust = 0;
+  double x = 0, y = 0, z = 0;
+  double kx = 0, ky = 0, kz = 1;
+  double mx = 0, my = 0, mz = 0, nx = 0, ny = 0, nz = 0;
+  int icell = 1, jcell = 1, kcell = 1;  // 1-based like the reference
+  double xfreq = 0, xfreq_ref = 0, wgt = 1;
+  bool inside = true;
+  double I = 1, Q = 0, U = 0, V = 0;
+  double E1 = 1, E2 = 0, E3 = 1;
+};
+
+// Read-only view of one run's inputs with Fortran-style 1-based accessors.
+struct World {
+  const lart_grid *g;
+  const lart_params *par;
+  const lart_line *line;
+  const lart_scatt_mat *sm;
+  const lart_observer *obs;
+  bool zonly;
+  inline size_t idx(int i, int j, int k) const {
+    return static_cast<size_t>(i - 1) + static_cast<size_t>(g->nx) * (static_cast<size_t>(j - 1) + static_cast<size_t>(g->ny) * static_cast<size_t>(k - 1));
+  }
+  inline double rhokap(int i, int j, int k) const { return g->rhokap[idx(i, j, k)]; }
+  inline double rhokapD(int i, int j, int k) const { return g->rhokapD[idx(i, j, k)]; }
+  inline double voigt_a(int i, int j, int k) const { return g->voigt_a[idx(i, j, k)]; }
+  inline double Dfreq(int i, int j, int k) const { return g->Dfreq[idx(i, j, k)]; }
+  inline double vdotk(int i, int j, int k, double kx, double ky, double kz) const {
+    size_t c = idx(i, j, k);
+    return g->vfx[c] * kx + g->vfy[c] * ky + g->vfz[c] * kz;
+  }
+  inline double xface(int i) const { return g->xface[i - 1]; }
+  inline double yface(int j) const { return g->yface[j - 1]; }
+  inline double zface(int k) const { return g->zface[k - 1]; }
+  // calc_voigt1 — line_mod.f90:38-47 (signed x is passed through)
+  inline double calc_voigt(double xfreq, int i, int j, int k) const { return voigt_seon2(xfreq, voigt_a(i, j, k)); }
+  inline bool dust() const { return par->DGR > 0.0; }
+};
+
+// Tally sinks.  Small histograms are thread-private; the big cubes are shared
+// between threads and updated with an atomic add (the reference keeps one
+// private copy per MPI rank and reduces — memory_mod_mpi.f90:276-292,366-458 —
+// which is the same sum).
+inline void atomic_add(double *p, double v) {
+  if (v == 0.0) return;  // adding an exact zero never changes a sum
+  std::atomic_ref<double> r(*p);
+  double old = r.load(std::memory_order_relaxed);
+  while (!r.compare_exchange_weak(old, old + v, std::memory_order_relaxed)) {
+  }
+}
+
+struct Tally {
+  std::vector<double> Jout, Jin, Jabs, Jmu;
+  double nscatt_gas = 0, nscatt_dust = 0;
+  Counters cnt;
+  lart_tallies *shared;  // cubes + allph written straight into the caller's buffers
+};
+
+// ---------------------------------------------------------------------------
+// setup_traversal_car — raytrace_car.f90:12-87.  Returns true when the photon
+// is already leaving the grid.  `zonly_eq` selects the `== zp` test of the
+// z-only to_tau variant (raytrace_car.f90:2560) instead of `<= zp` (:31,:1185).
+// ---------------------------------------------------------------------------
+struct Trav {
+  int istep, jstep, kstep;
+  double tx, ty, tz, delx, dely, delz;
+};
+
+inline bool axis_setup(double k, double p, int &cell, int n, const double *face, double d, int &step, double &t, double &del, bool eq_test) {
+  if (k > 0.0) {
+    if (cell > n) {
+      double f = face[cell - 1];
+      if (eq_test ? (f == p) : (f <= p)) return true;
+    }
+    step = 1;
+    t = (face[cell] - p) / k;
+    del = d / k;
+  } else if (k < 0.0) {
+    if (face[cell - 1] == p) {
+      if (cell > 1) cell -= 1;
+      else return true;
+    }
+    step = -1;
+    t = (face[cell - 1] - p) / k;
+    del = -d / k;
+  } else {
+    step = 0;
+    t = kHugest;
+    del = kHugest;
+  }
+  return false;
+}
+
+inline bool setup_traversal(const World &w, double xp, double yp, double zp, double kx, double ky, double kz,
+                            int &ic, int &jc, int &kc, Trav &t, bool zonly_eq) {
+  const lart_grid &g = *w.g;
+  if (w.zonly) {
+    // raytrace_car.f90:1184-1204 / :2559-2583 — only the z axis is walked
+    t.istep = t.jstep = 0;
+    t.tx = t.ty = kHugest;
+    t.delx = t.dely = kHugest;
+    return axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, zonly_eq);
+  }
+  if (axis_setup(kx, xp, ic, g.nx, g.xface, g.dx, t.istep, t.tx, t.delx, false)) return true;
+  if (axis_setup(ky, yp, jc, g.ny, g.yface, g.dy, t.jstep, t.ty, t.dely, false)) return true;
+  if (axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, false)) return true;
+  return false;
+}
+
+// minloc([tx,ty,tz],dim=1) — first minimum wins (raytrace_car.f90:476,1506)
+inline int minloc3(double tx, double ty, double tz) {
+  if (tx <= ty && tx <= tz) return 1;
+  if (ty <= tz) return 2;
+  return 3;
+}
+
+// ---------------------------------------------------------------------------
+// raytrace_to_edge_car — raytrace_car.f90:410-508; _zonly :1138-1234.
+// Optional trace of visited cells (0-based linear index) for parity tests.
+// ---------------------------------------------------------------------------
+double raytrace_to_edge(const World &w, const Photon &p0, Counters *cnt, int *nsteps_out = nullptr,
+                        int trace_cap = 0, int32_t *trace = nullptr) {
+  const lart_grid &g = *w.g;
+  double xp = p0.x, yp = p0.y, zp = p0.z, kx = p0.kx, ky = p0.ky, kz = p0.kz;
+  int ic = p0.icell, jc = p0.jcell, kc = p0.kcell;
+  double tau = 0.0, d = 0.0;
+  int nsteps = 0;
+  Trav t;
+  if (setup_traversal(w, xp, yp, zp, kx, ky, kz, ic, jc, kc, t, false)) {
+    if (nsteps_out) *nsteps_out = 0;
+    return tau;
+  }
+  int io = ic, jo = jc, ko = kc;
+  double u1 = w.vdotk(io, jo, ko, kx, ky, kz);
+  double xfreq = p0.xfreq;
+  for (;;) {
+    double rhokap = w.rhokap(ic, jc, kc) * w.calc_voigt(xfreq, ic, jc, kc);
+    if (w.dust()) rhokap += w.rhokapD(ic, jc, kc);
+    if (trace && nsteps < trace_cap) trace[nsteps] = static_cast<int32_t>(w.idx(ic, jc, kc));
+    ++nsteps;
+    int m = w.zonly ? 3 : minloc3(t.tx, t.ty, t.tz);
+    if (m == 1) {
+      tau += (t.tx - d) * rhokap;
+      d = t.tx;
+      ic += t.istep;
+      if (ic < 1 || ic > g.nx) break;
+      t.tx += t.delx;
+    } else if (m == 2) {
+      tau += (t.ty - d) * rhokap;
+      d = t.ty;
+      jc += t.jstep;
+      if (jc < 1 || jc > g.ny) break;
+      t.ty += t.dely;
+    } else {
+      tau += (t.tz - d) * rhokap;
+      d = t.tz;
+      kc += t.kstep;
+      if (kc < 1 || kc > g.nz) break;
+      t.tz += t.delz;
+    }
+    if (tau >= kTauHuge) break;
+    double u2 = w.vdotk(ic, jc, kc, kx, ky, kz);
+    xfreq = (xfreq + u1) * w.Dfreq(io, jo, ko) / w.Dfreq(ic, jc, kc) - u2;
+    io = ic; jo = jc; ko = kc;
+    u1 = u2;
+  }
+  if (cnt) cnt->n_cellsteps += nsteps;
+  if (nsteps_out) *nsteps_out = nsteps;
+  return tau;
+}
+
+// add_to_Jmu — raytrace_car.f90:4049-4064
+inline int jmu_bin(const lart_params &par, double kz) {
+  double mu = kz;
+  if (false) mu = std::fabs(mu);  // xyz_symmetry is out of scope on this path
+  int imu = static_cast<int>(std::floor((mu - par.mu_min) / par.dmu)) + 1;
+  if (imu < 1) imu = 1;
+  if (imu > par.nmu) imu = par.nmu;
+  return imu;
+}
+
+// ---------------------------------------------------------------------------
+// raytrace_to_tau_car — raytrace_car.f90:1425-1648; _zonly :2519-2675.
+// `tl` may be null (unit-level batch calls: no Jout tally).
+// ---------------------------------------------------------------------------
+void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Counters *cnt, int *nsteps_out = nullptr) {
+  const lart_grid &g = *w.g;
+  double xp = ph.x, yp = ph.y, zp = ph.z, kx = ph.kx, ky = ph.ky, kz = ph.kz;
+  int ic = ph.icell, jc = ph.jcell, kc = ph.kcell;
+  int nsteps = 0;
+  Trav t;
+  if (setup_traversal(w, xp, yp, zp, kx, ky, kz, ic, jc, kc, t, true)) {
+    ph.inside = false;  // :1469-1472 — returns before any tally
+    if (nsteps_out) *nsteps_out = 0;
+    return;
+  }
+  double tau = 0.0, d = 0.0;
+  int io = ic, jo = jc, ko = kc;
+  double u1 = w.vdotk(io, jo, ko, kx, ky, kz);
+  while (ph.inside) {
+    double rhokap = w.rhokap(ic, jc, kc) * w.calc_voigt(ph.xfreq, ic, jc, kc);
+    if (w.dust()) rhokap += w.rhokapD(ic, jc, kc);
+    ++nsteps;
+    int m = w.zonly ? 3 : minloc3(t.tx, t.ty, t.tz);
+    double tnext = (m == 1) ? t.tx : (m == 2) ? t.ty : t.tz;
+    double del = tnext - d;
+    tau += del * rhokap;
+    d = tnext;
+    if (tau >= tau_in) {  // :1513-1524
+      if (rhokap > 0.0) {
+        double d_overshoot = (tau - tau_in) / rhokap;
+        d = d - d_overshoot;
+      }
+      xp = xp + d * kx;
+      yp = yp + d * ky;
+      zp = zp + d * kz;
+      break;
+    }
+    if (m == 1) {
+      ic += t.istep;
+      if (ic < 1 || ic > g.nx) { ph.inside = false; break; }
+      t.tx += t.delx;
+    } else if (m == 2) {
+      jc += t.jstep;
+      if (jc < 1 || jc > g.ny) { ph.inside = false; break; }
+      t.ty += t.dely;
+    } else {
+      kc += t.kstep;
+      if (kc < 1 || kc > g.nz) { ph.inside = false; break; }
+      t.tz += t.delz;
+    }
+    double u2 = w.vdotk(ic, jc, kc, kx, ky, kz);
+    ph.xfreq = (ph.xfreq + u1) * w.Dfreq(io, jo, ko) / w.Dfreq(ic, jc, kc) - u2;  // :1586-1589
+    io = ic; jo = jc; ko = kc;
+    u1 = u2;
+  }
+  if (!ph.inside) {  // :1598-1602
+    ic = io; jc = jo; kc = ko;
+    // :1613-1623 — fluid frame -> lab frame, reference Doppler units, Jout bin
+    double ue = w.vdotk(ic, jc, kc, kx, ky, kz);
+    ph.xfreq = ph.xfreq + ue;
+    ph.xfreq_ref = ph.xfreq * (w.Dfreq(ic, jc, kc) / g.Dfreq_ref);
+    if (tl) {
+      int ix = static_cast<int>(std::floor((ph.xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
+      if (ix >= 1 && ix <= g.nxfreq) {
+        tl->Jout[ix - 1] += ph.wgt;
+        if (w.par->save_Jmu) tl->Jmu[(ix - 1) + static_cast<size_t>(g.nxfreq) * (jmu_bin(*w.par, ph.kz) - 1)] += ph.wgt;
+      }
+    }
+  }
+  ph.x = xp; ph.y = yp; ph.z = zp;
+  if (!w.zonly) { ph.icell = ic; ph.jcell = jc; }
+  ph.kcell = kc;
+  if (cnt) cnt->n_cellsteps += nsteps;
+  if (nsteps_out) *nsteps_out = nsteps;
+}
+
+// ---------------------------------------------------------------------------
+// Samplers
+// ---------------------------------------------------------------------------
+// rand_resonance_vz_seon — random_mt.f90:2562-2696
+double rand_resonance_vz(Rng &r, double x0in, double a) {
+  const double x0_crit = 1.0;
+  const double xc = 1.0 + std::sqrt(2.0);
+  const double two_over_PI = 2.0 / kPi;
+  double x0 = std::fabs(x0in);
+  double vz;
+  Counters *cnt = r.cnt;
+  if (x0 <= x0_crit) {  // :2579-2585
+    for (;;) {
+      vz = x0 + a * std::tan(kPi * (r.uniform() - 0.5));
+      if (cnt) cnt->n_reject_iter += 1;
+      if (r.uniform() <= std::exp(-vz * vz)) break;
+    }
+    if (x0in < 0.0) vz = -vz;
+    return vz;
+  }
+  double x0sq = x0 * x0, api = a * kPi;
+  double beta0 = std::exp(-x0sq / 2.0);
+  double h0_two = beta0 / a, h0 = h0_two / 2.0;
+  double beta, Cb, pb, t1, t2, delt;
+  auto trial = [&](double b, double c) -> bool {
+    beta = b;
+    Cb = c;
+    pb = std::sqrt(-2.0 * std::log(beta));
+    t2 = std::atan((pb - x0) / a);
+    t1 = std::atan((-pb - x0) / a);
+    delt = t2 - t1;
+    if (cnt) cnt->n_reject_iter += 1;
+    return r.uniform() * Cb < (beta / api) * delt;
+  };
+  if (x0 < xc) {  // :2605-2635
+    double dbeta = std::sqrt(two_over_PI * a * (1.0 - beta0) * beta0 * x0);
+    double beta1 = beta0 + dbeta, one_b1 = 1.0 - beta1;
+    double pb1 = std::sqrt(-2.0 * std::log(beta1));
+    double h1 = two_over_PI * beta1 * pb1 / (x0sq - pb1 * pb1);
+    double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * h1, Stot = S0 + S1 + S2;
+    for (;;) {
+      double rs = r.uniform();
+      bool ok;
+      if (rs < S0 / Stot) { double b = beta0 * std::sqrt(r.uniform()); ok = trial(b, b / a); }
+      else if (rs < 1.0 - S2 / Stot) ok = trial(beta0 + dbeta * r.uniform(), h0);
+      else ok = trial(beta1 + one_b1 * r.uniform(), h1);
+      if (ok) break;
+    }
+  } else {
+    double h2 = 0.3861 / (x0sq - 1.373);
+    if (h0_two < h2) {  // :2638-2647
+      for (;;) if (trial(r.uniform(), h2)) break;
+    } else if (h0 < h2) {  // :2648-2666
+      double S0 = beta0 * h0, one_b0 = 1.0 - beta0, S1 = one_b0 * h2, Stot = S0 + S1;
+      for (;;) {
+        bool ok;
+        if (r.uniform() < S0 / Stot) { double b = beta0 * std::sqrt(r.uniform()); ok = trial(b, b / a); }
+        else ok = trial(beta0 + one_b0 * r.uniform(), h2);
+        if (ok) break;
+      }
+    } else {  // :2667-2690
+      double dbeta = std::sqrt(two_over_PI * a * (1.0 - beta0) * beta0 * x0);
+      double beta1 = beta0 + dbeta, one_b1 = 1.0 - beta1;
+      double pb1 = std::sqrt(-2.0 * std::log(beta1));
+      double h1 = two_over_PI * beta1 * pb1 / (x0sq - pb1 * pb1);
+      double hmax = (h1 > h2) ? h1 : h2;
+      double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * hmax, Stot = S0 + S1 + S2;
+      for (;;) {
+        double rs = r.uniform();
+        bool ok;
+        if (rs < S0 / Stot) { double b = beta0 * std::sqrt(r.uniform()); ok = trial(b, b / a); }
+        else if (rs < 1.0 - S2 / Stot) ok = trial(beta0 + dbeta * r.uniform(), h0);
+        else ok = trial(beta1 + one_b1 * r.uniform(), hmax);
+        if (ok) break;
+      }
+    }
+  }
+  vz = x0 + a * std::tan(delt * r.uniform() + t1);  // :2693
+  if (x0in < 0.0) vz = -vz;
+  return vz;
+}
+
+// rand_resonance — random_mt.f90:2974-2993 (x**(1/3) is a pow in the Fortran)
+double rand_resonance(Rng &r, double E1) {
+  const double one_over_three = 1.0 / 3.0;
+  if (E1 > 0.0) {
+    double p2 = std::sqrt((4.0 - E1) / (3.0 * E1));
+    double Q = (4.0 * r.uniform() - 2.0) / (E1 * (p2 * p2 * p2));
+    double W = std::pow(Q + std::sqrt(Q * Q + 1.0), one_over_three);
+    return p2 * (W - 1.0 / W);
+  } else if (E1 < 0.0) {
+    double p2 = std::sqrt(std::fabs((4.0 - E1) / (3.0 * E1)));
+    double Q = (4.0 * r.uniform() - 2.0) / (E1 * (p2 * p2 * p2));
+    return 2.0 * p2 * std::cos((std::acos(Q) + kFourPi) / 3.0);
+  }
+  return 2.0 * r.uniform() - 1.0;
+}
+
+// rand_henyey_greenstein — random_mt.f90:3022-3042
+double rand_hg(Rng &r, double g) {
+  double x = r.uniform();
+  if (g == 0.0) return 2.0 * x - 1.0;
+  double g2 = g * g, twog = 2.0 * g;
+  double q = (1.0 - g2) / (1.0 - g + twog * x);
+  return ((1.0 + g2) - q * q) / twog;
+}
+
+// rand_voigt — random_mt.f90:3062-3083
+double rand_voigt(Rng &r, double a) {
+  double c = std::tan(kPi * r.uniform() - kHalfPi);
+  return a * c + r.gauss() * (1.0 / std::sqrt(2.0));
+}
+
+// rand_alias_linear64 — random_mt.f90:2196-2216 (arrays 1-based in the Fortran)
+double rand_alias_linear(Rng &r, const lart_scatt_mat &sm) {
+  int n = sm.nPDF - 1;
+  int k = static_cast<int>(std::floor(n * r.uniform())) + 1;
+  int idx = (r.uniform() < sm.phase_PDF[k - 1]) ? k : sm.alias[k - 1];
+  double p0 = sm.S11[idx - 1], p1 = sm.S11[idx];
+  double x0 = sm.coss[idx - 1], x1 = sm.coss[idx];
+  return (std::sqrt(p0 * p0 + (p1 * p1 - p0 * p0) * r.uniform()) - p0) * (x1 - x0) / (p1 - p0) + x0;
+}
+
+// interp_eq — mathlib.f90:71-106 (integer conversion truncates toward zero)
+double interp_eq(const double *x, const double *y, int n, double xnew) {
+  double dx = x[1] - x[0];
+  int i = static_cast<int>((xnew - x[0]) / dx + 1.0);
+  if (i <= 0) return y[0];
+  if (i >= n) return y[n - 1];
+  return y[i - 1] + (y[i] - y[i - 1]) * (xnew - x[i - 1]) / dx;
+}
+
+// car_xcrit_local — grid_mod_car.f90:1598-1629
+void car_xcrit_local(const World &w, int i, int j, int k, double x, double y, double z, double &xc, double &xc2) {
+  const lart_grid &g = *w.g;
+  if (w.par->core_skip_global) {
+    xc = g.xcrit;
+    xc2 = g.xcrit2;
+    return;
+  }
+  xc = 0.0;
+  xc2 = 0.0;
+  if (i < 1 || j < 1 || k < 1) return;
+  double dlx = std::fmin(x - w.xface(i), w.xface(i + 1) - x);
+  double dly = std::fmin(y - w.yface(j), w.yface(j + 1) - y);
+  double dlz = std::fmin(z - w.zface(k), w.zface(k + 1) - z);
+  double dl = std::fmin(dlx, std::fmin(dly, dlz));
+  if (dl <= 0.0) return;
+  double atau = w.voigt_a(i, j, k) * w.rhokap(i, j, k) * dl;
+  if (atau > 1.0) {
+    xc = std::pow(atau, 1.0 / 3.0) / 5.0;
+    xc2 = xc * xc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Peel-off (outside observer, TAN image) — peelingoff_rect.f90
+// ---------------------------------------------------------------------------
+struct PeelGeom {
+  Photon pobs;
+  double r2;
+  int ix, iy;
+  bool in_image;
+};
+
+// common head of every peeling routine: :44-61 / :326-357 / :595-627
+inline PeelGeom peel_geometry(const Photon &ph, const lart_observer &ob) {
+  PeelGeom pg;
+  pg.pobs = ph;
+  Photon &po = pg.pobs;
+  po.kx = ob.x - ph.x;
+  po.ky = ob.y - ph.y;
+  po.kz = ob.z - ph.z;
+  pg.r2 = po.kx * po.kx + po.ky * po.ky + po.kz * po.kz;
+  double r = std::sqrt(pg.r2);
+  po.kx /= r; po.ky /= r; po.kz /= r;
+  const double *R = ob.rmatrix;  // R[(row-1)+3*(col-1)]
+  double kx = R[0] * po.kx + R[3] * po.ky + R[6] * po.kz;
+  double ky = R[1] * po.kx + R[4] * po.ky + R[7] * po.kz;
+  double kz = R[2] * po.kx + R[5] * po.ky + R[8] * po.kz;
+  pg.ix = static_cast<int>(std::floor(std::atan2(-kx, kz) * kRad2Deg / ob.dxim + ob.nxim / 2.0)) + 1;
+  pg.iy = static_cast<int>(std::floor(std::atan2(-ky, kz) * kRad2Deg / ob.dyim + ob.nyim / 2.0)) + 1;
+  pg.in_image = pg.ix >= 1 && pg.ix <= ob.nxim && pg.iy >= 1 && pg.iy <= ob.nyim;
+  return pg;
+}
+
+inline size_t pix2(const lart_observer &ob, int ix, int iy) { return static_cast<size_t>(ix - 1) + static_cast<size_t>(ob.nxim) * (iy - 1); }
+inline size_t pix3(const World &w, const lart_observer &ob, int ixf, int ix, int iy) {
+  return static_cast<size_t>(ixf - 1) + static_cast<size_t>(w.g->nxfreq) * pix2(ob, ix, iy);
+}
+inline void add_to(double *arr, size_t i, double v) { if (arr) atomic_add(arr + i, v); }
+
+// peeling_direct_outside — peelingoff_rect.f90:24-129
+void peeling_direct(const World &w, const Photon &ph, Tally &tl) {
+  const lart_params &par = *w.par;
+  const lart_grid &g = *w.g;
+  for (int i = 0; i < par.nobs; ++i) {
+    const lart_observer &ob = w.obs[i];
+    lart_observer_out &oo = tl.shared->obs[i];
+    PeelGeom pg = peel_geometry(ph, ob);
+    Photon &po = pg.pobs;
+    double xfreq_ref;
+    if (!par.comoving_source) {  // :70-80
+      double u1 = w.vdotk(ph.icell, ph.jcell, ph.kcell, ph.kx, ph.ky, ph.kz);
+      xfreq_ref = ph.xfreq + u1;
+      double u2 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+      po.xfreq = xfreq_ref - u2;
+    } else {  // :81-87
+      double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+      xfreq_ref = ph.xfreq + u1;
+    }
+    xfreq_ref = xfreq_ref * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
+    int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
+    if (!pg.in_image) continue;
+    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    tl.cnt.n_peel += 1;
+    double wgt0 = 1.0 / (kFourPi * pg.r2) * ph.wgt;
+    double wgt = std::exp(-tau) * wgt0;
+    if (par.save_peeloff_2D) {
+      size_t q = pix2(ob, pg.ix, pg.iy);
+      add_to(oo.direc_2D, q, wgt);
+      if (par.use_stokes) add_to(oo.I_2D, q, wgt);
+      if (par.save_direc0) add_to(oo.direc0_2D, q, wgt0);
+    }
+    if (par.save_peeloff_3D && ixf >= 1 && ixf <= g.nxfreq) {
+      size_t q = pix3(w, ob, ixf, pg.ix, pg.iy);
+      add_to(oo.direc, q, wgt);
+      if (par.use_stokes) add_to(oo.I, q, wgt);
+      if (par.save_direc0) add_to(oo.direc0, q, wgt0);
+    }
+  }
+}
+
+// shared tail of the two Stokes peels: rotate to the detector and deposit
+// (peelingoff_rect.f90:428-479 and :243-296)
+inline void deposit_stokes(const World &w, const lart_observer &ob, lart_observer_out &oo, const Photon &po, const PeelGeom &pg,
+                           int ixf, double wgt, double Iobs, double Qobs, double Uobs, double Vobs) {
+  const double *R = ob.rmatrix;
+  double cosg = -(R[0] * po.nx + R[3] * po.ny + R[6] * po.nz);
+  double sing = R[1] * po.nx + R[4] * po.ny + R[7] * po.nz;
+  double cos2g = 2.0 * cosg * cosg - 1.0, sin2g = 2.0 * cosg * sing;
+  double Idet = Iobs, Qdet = cos2g * Qobs + sin2g * Uobs, Udet = -sin2g * Qobs + cos2g * Uobs, Vdet = Vobs;
+  if (w.par->save_peeloff_2D) {
+    size_t q = pix2(ob, pg.ix, pg.iy);
+    add_to(oo.scatt_2D, q, wgt * Idet);
+    add_to(oo.I_2D, q, wgt * Idet);
+    add_to(oo.Q_2D, q, wgt * Qdet);
+    add_to(oo.U_2D, q, wgt * Udet);
+    add_to(oo.V_2D, q, wgt * Vdet);
+  }
+  if (w.par->save_peeloff_3D && ixf >= 1 && ixf <= w.g->nxfreq) {
+    size_t q = pix3(w, ob, ixf, pg.ix, pg.iy);
+    add_to(oo.scatt, q, wgt * Idet);
+    add_to(oo.I, q, wgt * Idet);
+    add_to(oo.Q, q, wgt * Qdet);
+    add_to(oo.U, q, wgt * Udet);
+    add_to(oo.V, q, wgt * Vdet);
+  }
+}
+
+// azimuth of the observer direction in the photon's (m,n) frame and the new
+// reference normal (:364-380 / :208-224)
+inline void stokes_azimuth(const Photon &ph, Photon &po, double cost, double &sint, double &cosp, double &sinp, double &cos2p, double &sin2p) {
+  sint = std::sqrt(1.0 - cost * cost);
+  if (sint == 0.0) {
+    cosp = 1.0; sinp = 0.0; cos2p = 1.0; sin2p = 0.0;
+  } else {
+    cosp = (po.kx * ph.mx + po.ky * ph.my + po.kz * ph.mz) / sint;
+    sinp = (po.kx * ph.nx + po.ky * ph.ny + po.kz * ph.nz) / sint;
+    cos2p = 2.0 * cosp * cosp - 1.0;
+    sin2p = 2.0 * cosp * sinp;
+  }
+  po.nx = -sinp * ph.mx + cosp * ph.nx;
+  po.ny = -sinp * ph.my + cosp * ph.ny;
+  po.nz = -sinp * ph.mz + cosp * ph.nz;
+}
+
+// peeling_resonance_stokes_outside — peelingoff_rect.f90:303-482
+void peeling_resonance_stokes(const World &w, const Photon &ph, Tally &tl, double xfreq_atom, const double vel_atom[3]) {
+  const lart_params &par = *w.par;
+  const lart_grid &g = *w.g;
+  for (int i = 0; i < par.nobs; ++i) {
+    const lart_observer &ob = w.obs[i];
+    PeelGeom pg = peel_geometry(ph, ob);
+    if (!pg.in_image) continue;
+    Photon &po = pg.pobs;
+    double cost = ph.kx * po.kx + ph.ky * po.ky + ph.kz * po.kz;
+    double sint, cosp, sinp, cos2p, sin2p;
+    stokes_azimuth(ph, po, cost, sint, cosp, sinp, cos2p, sin2p);
+    double cost2 = cost * cost;
+    double S22 = 0.75 * ph.E1 * (cost2 + 1.0);
+    double S11 = S22 + ph.E2;
+    double S12 = 0.75 * ph.E1 * (cost2 - 1.0);
+    double S33 = 1.5 * ph.E1 * cost;
+    double S44 = 1.5 * ph.E3 * cost;
+    double xfreq = xfreq_atom + (vel_atom[0] * cosp + vel_atom[1] * sinp) * sint + vel_atom[2] * cost;  // :392
+    double Dcell = w.Dfreq(ph.icell, ph.jcell, ph.kcell);
+    if (par.recoil) xfreq -= (w.line->g_recoil0 / Dcell) * (1.0 - cost);
+    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double xfreq_ref = (xfreq + u1) * (Dcell / g.Dfreq_ref);
+    int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
+    double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+    double Iobs = (S11 + S12 * Q0) / kFourPi, Qobs = (S12 + S22 * Q0) / kFourPi;
+    double Uobs = (S33 * U0) / kFourPi, Vobs = (S44 * ph.V) / kFourPi;
+    po.xfreq = xfreq;
+    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    tl.cnt.n_peel += 1;
+    double wgt = 1.0 / pg.r2 * std::exp(-tau) * ph.wgt;
+    deposit_stokes(w, ob, tl.shared->obs[i], po, pg, ixf, wgt, Iobs, Qobs, Uobs, Vobs);
+  }
+}
+
+// peeling_resonance_nostokes_outside — peelingoff_rect.f90:576-690
+void peeling_resonance_nostokes(const World &w, const Photon &ph, Tally &tl, double xfreq_atom, const double vel_atom[3]) {
+  const lart_params &par = *w.par;
+  const lart_grid &g = *w.g;
+  for (int i = 0; i < par.nobs; ++i) {
+    const lart_observer &ob = w.obs[i];
+    lart_observer_out &oo = tl.shared->obs[i];
+    PeelGeom pg = peel_geometry(ph, ob);
+    if (!pg.in_image) continue;
+    Photon &po = pg.pobs;
+    double cost = ph.kx * po.kx + ph.ky * po.ky + ph.kz * po.kz;
+    double cost2 = cost * cost;
+    double sint = std::sqrt(1.0 - cost2);
+    double rho1 = std::sqrt(1.0 - ph.kz * ph.kz) * sint;
+    double cosp, sinp;
+    if (rho1 == 0.0) { cosp = 1.0; sinp = 0.0; }
+    else {
+      double rho = 1.0 / rho1;
+      cosp = rho * (cost * ph.kz - po.kz);
+      sinp = rho * (ph.kx * po.ky - po.kx * ph.ky);
+    }
+    double xfreq = xfreq_atom + (vel_atom[0] * cosp + vel_atom[1] * sinp) * sint + vel_atom[2] * cost;
+    double Dcell = w.Dfreq(ph.icell, ph.jcell, ph.kcell);
+    if (par.recoil) xfreq -= (w.line->g_recoil0 / Dcell) * (1.0 - cost);
+    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double xfreq_ref = (xfreq + u1) * (Dcell / g.Dfreq_ref);
+    int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
+    po.xfreq = xfreq;
+    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    tl.cnt.n_peel += 1;
+    double peel = 0.75 * ph.E1 * (cost2 + 1.0) + ph.E2;
+    double wgt = peel / (kFourPi * pg.r2) * std::exp(-tau) * ph.wgt;
+    if (par.save_peeloff_2D) add_to(oo.scatt_2D, pix2(ob, pg.ix, pg.iy), wgt);
+    if (par.save_peeloff_3D && ixf >= 1 && ixf <= g.nxfreq) add_to(oo.scatt, pix3(w, ob, ixf, pg.ix, pg.iy), wgt);
+  }
+}
+
+// peeling_dust_stokes_outside — peelingoff_rect.f90:131-299
+void peeling_dust_stokes(const World &w, const Photon &ph, Tally &tl) {
+  const lart_params &par = *w.par;
+  const lart_grid &g = *w.g;
+  const lart_scatt_mat &sm = *w.sm;
+  for (int i = 0; i < par.nobs; ++i) {
+    const lart_observer &ob = w.obs[i];
+    PeelGeom pg = peel_geometry(ph, ob);
+    Photon &po = pg.pobs;
+    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double xfreq_ref = (ph.xfreq + u1) * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
+    int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
+    if (!pg.in_image) continue;
+    double cost = ph.kx * po.kx + ph.ky * po.ky + ph.kz * po.kz;
+    double sint, cosp, sinp, cos2p, sin2p;
+    stokes_azimuth(ph, po, cost, sint, cosp, sinp, cos2p, sin2p);
+    double S11 = interp_eq(sm.coss, sm.S11, sm.nPDF, cost);
+    double S12 = interp_eq(sm.coss, sm.S12, sm.nPDF, cost);
+    double S33 = interp_eq(sm.coss, sm.S33, sm.nPDF, cost);
+    double S34 = interp_eq(sm.coss, sm.S34, sm.nPDF, cost);
+    double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+    double Iobs = (S11 * ph.I + S12 * Q0) / kTwoPi, Qobs = (S12 * ph.I + S11 * Q0) / kTwoPi;
+    double Uobs = (S33 * U0 + S34 * ph.V) / kTwoPi, Vobs = (-S34 * U0 + S33 * ph.V) / kTwoPi;
+    double tau = raytrace_to_edge(w, po, &tl.cnt);  // pobs%xfreq = photon%xfreq (:195-197)
+    tl.cnt.n_peel += 1;
+    double wgt = 1.0 / pg.r2 * std::exp(-tau) * ph.wgt;
+    deposit_stokes(w, ob, tl.shared->obs[i], po, pg, ixf, wgt, Iobs, Qobs, Uobs, Vobs);
+  }
+}
+
+// peeling_dust_nostokes_outside — peelingoff_rect.f90:484-574
+void peeling_dust_nostokes(const World &w, const Photon &ph, Tally &tl) {
+  const lart_params &par = *w.par;
+  const lart_grid &g = *w.g;
+  for (int i = 0; i < par.nobs; ++i) {
+    const lart_observer &ob = w.obs[i];
+    lart_observer_out &oo = tl.shared->obs[i];
+    PeelGeom pg = peel_geometry(ph, ob);
+    if (!pg.in_image) continue;
+    Photon &po = pg.pobs;
+    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double xfreq_ref = (ph.xfreq + u1) * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
+    int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
+    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    tl.cnt.n_peel += 1;
+    double cosa = ph.kx * po.kx + ph.ky * po.ky + ph.kz * po.kz;
+    double hg = par.hgg;
+    double peel = (1.0 - hg * hg) / std::pow((1.0 + hg * hg) - 2.0 * hg * cosa, 1.5) / kFourPi;
+    double wgt = peel / pg.r2 * std::exp(-tau) * ph.wgt;
+    if (par.save_peeloff_2D) add_to(oo.scatt_2D, pix2(ob, pg.ix, pg.iy), wgt);
+    if (par.save_peeloff_3D && ixf >= 1 && ixf <= g.nxfreq) add_to(oo.scatt, pix3(w, ob, ixf, pg.ix, pg.iy), wgt);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Scattering — scattering_car.f90
+// ---------------------------------------------------------------------------
+// do_resonance1 — line_mod.f90:108-139
+inline void do_resonance1(const World &w, Photon &ph, Rng &r, double &uz, double &xfreq_atom, double &cost, double &sint) {
+  uz = rand_resonance_vz(r, ph.xfreq, w.voigt_a(ph.icell, ph.jcell, ph.kcell));
+  xfreq_atom = ph.xfreq - uz;
+  ph.E1 = w.line->E1; ph.E2 = w.line->E2; ph.E3 = w.line->E3;
+  cost = rand_resonance(r, ph.E1);
+  sint = std::sqrt(1.0 - cost * cost);
+}
+
+// rotate the (m,n,k) triad — scattering_car.f90:470-484 / :314-328
+inline void rotate_triad(Photon &ph, double cost, double sint, double cosp, double sinp) {
+  double px = cosp * ph.mx + sinp * ph.nx, py = cosp * ph.my + sinp * ph.ny, pz = cosp * ph.mz + sinp * ph.nz;
+  ph.nx = cosp * ph.nx - sinp * ph.mx;
+  ph.ny = cosp * ph.ny - sinp * ph.my;
+  ph.nz = cosp * ph.nz - sinp * ph.mz;
+  ph.mx = cost * px - sint * ph.kx;
+  ph.my = cost * py - sint * ph.ky;
+  ph.mz = cost * pz - sint * ph.kz;
+  ph.kx = sint * px + cost * ph.kx;
+  ph.ky = sint * py + cost * ph.ky;
+  ph.kz = sint * pz + cost * ph.kz;
+}
+
+// new direction without a triad — scattering_car.f90:795-809 / :568-582
+inline void rotate_k(Photon &ph, double cost, double sint, double cosp, double sinp) {
+  if (std::fabs(ph.kz) >= 0.99999999999) {
+    ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
+  } else {
+    double kx1 = ph.kx, ky1 = ph.ky, kz1 = ph.kz;
+    double kr = std::sqrt(kx1 * kx1 + ky1 * ky1);
+    ph.kx = cost * kx1 + sint * (kz1 * kx1 * cosp - ky1 * sinp) / kr;
+    ph.ky = cost * ky1 + sint * (kz1 * ky1 * cosp + kx1 * sinp) / kr;
+    ph.kz = cost * kz1 - sint * cosp * kr;
+  }
+}
+
+// azimuth by rejection — scattering_car.f90:364-371 / :280-287
+inline double sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11) {
+  double phi;
+  for (;;) {
+    phi = kTwoPi * r.uniform();
+    double phi1 = 2.0 * phi;
+    double Prand = (1.0 + std::fabs(S12overS11) * std::sqrt(ph.Q * ph.Q + ph.U * ph.U)) * r.uniform();
+    double Pcomp = 1.0 + S12overS11 * (ph.Q * std::cos(phi1) + ph.U * std::sin(phi1));
+    if (r.cnt) r.cnt->n_reject_iter += 1;
+    if (Prand <= Pcomp) break;
+  }
+  return phi;
+}
+
+// scatter_resonance_stokes — scattering_car.f90:331-486
+void scatter_resonance_stokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
+  const lart_params &par = *w.par;
+  ph.nscatt_gas += ph.wgt;
+  double uz, xfreq_atom, cost, sint;
+  do_resonance1(w, ph, r, uz, xfreq_atom, cost, sint);
+  double cost2 = cost * cost;
+  double S22 = 0.75 * ph.E1 * (cost2 + 1.0), S11 = S22 + ph.E2, S12 = 0.75 * ph.E1 * (cost2 - 1.0);
+  double S33 = 1.5 * ph.E1 * cost, S44 = 1.5 * ph.E3 * cost;
+  double phi = sample_phi_stokes(r, ph, S12 / S11);
+  double cosp = std::cos(phi), sinp = std::sin(phi);
+  double xc = 0.0, xc2 = 0.0;
+  if (par.core_skip) car_xcrit_local(w, ph.icell, ph.jcell, ph.kcell, ph.x, ph.y, ph.z, xc, xc2);
+  double ux, uy;
+  if (par.core_skip && std::fabs(ph.xfreq) < xc) {  // :397-401
+    double phi2 = kTwoPi * r.uniform();
+    double uxy = std::sqrt(xc2 - std::log(r.uniform()));
+    ux = uxy * std::cos(phi2);
+    uy = uxy * std::sin(phi2);
+  } else {  // :413-414
+    const double one_over_sqrt2 = 1.0 / std::sqrt(2.0);
+    ux = r.gauss() * one_over_sqrt2;
+    uy = r.gauss() * one_over_sqrt2;
+  }
+  ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
+  if (par.recoil) ph.xfreq -= (w.line->g_recoil0 / w.Dfreq(ph.icell, ph.jcell, ph.kcell)) * (1.0 - cost);
+  if (par.save_peeloff) {
+    double va[3] = {ux, uy, uz};
+    peeling_resonance_stokes(w, ph, tl, xfreq_atom, va);
+  }
+  double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
+  double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+  double I1 = S11 + S12 * Q0, Q1 = S12 + S22 * Q0, U1 = S33 * U0, V1 = S44 * ph.V;
+  ph.I = 1.0; ph.Q = Q1 / I1; ph.U = U1 / I1; ph.V = V1 / I1;
+  rotate_triad(ph, cost, sint, cosp, sinp);
+}
+
+// scatter_resonance_nostokes — scattering_car.f90:660-827
+void scatter_resonance_nostokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
+  const lart_params &par = *w.par;
+  ph.nscatt_gas += ph.wgt;
+  double uz, xfreq_atom, cost, sint;
+  do_resonance1(w, ph, r, uz, xfreq_atom, cost, sint);
+  double phi = kTwoPi * r.uniform();
+  double cosp = std::cos(phi), sinp = std::sin(phi);
+  double xc = 0.0, xc2 = 0.0;
+  if (par.core_skip) car_xcrit_local(w, ph.icell, ph.jcell, ph.kcell, ph.x, ph.y, ph.z, xc, xc2);
+  double phi2 = kTwoPi * r.uniform();
+  double uxy = (par.core_skip && std::fabs(ph.xfreq) < xc) ? std::sqrt(xc2 - std::log(r.uniform())) : std::sqrt(-std::log(r.uniform()));
+  double ux = uxy * std::cos(phi2), uy = uxy * std::sin(phi2);
+  ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
+  if (par.recoil) ph.xfreq -= (w.line->g_recoil0 / w.Dfreq(ph.icell, ph.jcell, ph.kcell)) * (1.0 - cost);
+  if (par.save_peeloff) {
+    double va[3] = {ux, uy, uz};
+    peeling_resonance_nostokes(w, ph, tl, xfreq_atom, va);
+  }
+  rotate_k(ph, cost, sint, cosp, sinp);
+}
+
+// dust absorption / weight reduction shared by both dust routines —
+// scattering_car.f90:219-264 / :506-555.  Returns false when the photon died.
+inline bool dust_absorb(const World &w, Photon &ph, Rng &r, Tally &tl) {
+  const lart_params &par = *w.par;
+  const lart_grid &g = *w.g;
+  auto lab_bin = [&](double &xref) {
+    double uu1 = w.vdotk(ph.icell, ph.jcell, ph.kcell, ph.kx, ph.ky, ph.kz);
+    xref = (ph.xfreq + uu1) * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
+    return static_cast<int>(std::floor((xref - g.xfreq_min) / g.dxfreq)) + 1;
+  };
+  double xref = 0.0;
+  if (!par.use_reduced_wgt) {
+    if (r.uniform() > par.albedo) {
+      if (par.save_Jabs) {
+        int ix = lab_bin(xref);
+        if (ix >= 1 && ix <= g.nxfreq) tl.Jabs[ix - 1] += ph.wgt;
+      }
+      ph.inside = false;
+      if (par.save_all_photons) {
+        if (!par.save_Jabs) lab_bin(xref);
+        ph.xfreq_ref = xref;
+        ph.wgt = 0.0;
+      }
+      return false;
+    }
+  } else {
+    if (par.save_Jabs) {
+      int ix = lab_bin(xref);
+      if (ix >= 1 && ix <= g.nxfreq) tl.Jabs[ix - 1] += ph.wgt * (1.0 - par.albedo);
+    }
+    ph.wgt = ph.wgt * par.albedo;
+  }
+  return true;
+}
+
+// scatter_dust_stokes — scattering_car.f90:201-329
+void scatter_dust_stokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
+  const lart_scatt_mat &sm = *w.sm;
+  ph.nscatt_dust += ph.wgt;
+  if (!dust_absorb(w, ph, r, tl)) return;
+  if (w.par->save_peeloff) peeling_dust_stokes(w, ph, tl);
+  double cost = rand_alias_linear(r, sm);
+  double sint = std::sqrt(1.0 - cost * cost);
+  double S11 = interp_eq(sm.coss, sm.S11, sm.nPDF, cost), S12 = interp_eq(sm.coss, sm.S12, sm.nPDF, cost);
+  double S33 = interp_eq(sm.coss, sm.S33, sm.nPDF, cost), S34 = interp_eq(sm.coss, sm.S34, sm.nPDF, cost);
+  double phi = sample_phi_stokes(r, ph, S12 / S11);
+  double cosp = std::cos(phi), sinp = std::sin(phi);
+  double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
+  double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+  double I1 = S11 + S12 * Q0, Q1 = S12 + S11 * Q0, U1 = S33 * U0 + S34 * ph.V, V1 = -S34 * U0 + S33 * ph.V;
+  ph.I = 1.0; ph.Q = Q1 / I1; ph.U = U1 / I1; ph.V = V1 / I1;
+  rotate_triad(ph, cost, sint, cosp, sinp);
+}
+
+// scatter_dust_nostokes — scattering_car.f90:488-584
+void scatter_dust_nostokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
+  ph.nscatt_dust += ph.wgt;
+  if (!dust_absorb(w, ph, r, tl)) return;
+  if (w.par->save_peeloff) peeling_dust_nostokes(w, ph, tl);
+  double cost = rand_hg(r, w.par->hgg);
+  double sint = std::sqrt(1.0 - cost * cost);
+  double phi = kTwoPi * r.uniform();
+  rotate_k(ph, cost, sint, std::cos(phi), std::sin(phi));
+}
+
+// scattering — scattering_car.f90:14-120 (Cartesian, no H2/AMR/clump branches)
+void scattering(const World &w, Photon &ph, Rng &r, Tally &tl) {
+  tl.cnt.n_scatter += 1;
+  bool to_dust = false;
+  if (w.dust()) {
+    int i = ph.icell, j = ph.jcell, k = ph.kcell;
+    double p_dust = w.rhokapD(i, j, k) / (w.rhokap(i, j, k) * w.calc_voigt(ph.xfreq, i, j, k) + w.rhokapD(i, j, k));
+    to_dust = r.uniform() <= p_dust;
+  }
+  if (to_dust) {
+    if (w.par->use_stokes) scatter_dust_stokes(w, ph, r, tl);
+    else scatter_dust_nostokes(w, ph, r, tl);
+  } else {
+    if (w.par->use_stokes) scatter_resonance_stokes(w, ph, r, tl);
+    else scatter_resonance_nostokes(w, ph, r, tl);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// generate_photon + setup_isotropic_injection — generate_photon.f90:3-339, 342-408
+// ---------------------------------------------------------------------------
+void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
+  const lart_params &par = *w.par;
+  const lart_grid &g = *w.g;
+  switch (par.source_geometry) {
+    case LART_SRC_UNIFORM_SPHERE: {  // :34-42
+      double rp = std::pow(r.uniform(), 1.0 / 3.0) * par.source_rmax;
+      double cost = 2.0 * r.uniform() - 1.0, sint = std::sqrt(1.0 - cost * cost), phi = kTwoPi * r.uniform();
+      ph.x = rp * sint * std::cos(phi); ph.y = rp * sint * std::sin(phi); ph.z = rp * cost;
+      break;
+    }
+    case LART_SRC_UNIFORM:  // :50-54
+      ph.x = (g.xmax - g.xmin) * r.uniform() + g.xmin;
+      ph.y = (g.ymax - g.ymin) * r.uniform() + g.ymin;
+      ph.z = (g.zmax - g.zmin) * r.uniform() + g.zmin;
+      break;
+    default:  // :126-131
+      ph.x = par.xs_point; ph.y = par.ys_point; ph.z = par.zs_point;
+  }
+  // setup_isotropic_injection :342-408
+  ph.wgt = 1.0;
+  double cost = 2.0 * r.uniform() - 1.0;
+  double sint = std::sqrt(1.0 - cost * cost);
+  double phi = kTwoPi * r.uniform();
+  double cosp = std::cos(phi), sinp = std::sin(phi);
+  ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
+  ph.icell = static_cast<int>(std::floor((ph.x - g.xmin) / g.dx)) + 1;
+  ph.jcell = static_cast<int>(std::floor((ph.y - g.ymin) / g.dy)) + 1;
+  ph.kcell = static_cast<int>(std::floor((ph.z - g.zmin) / g.dz)) + 1;
+  if (ph.kx < 0.0 && ph.icell == g.nx + 1) ph.icell = g.nx;
+  if (ph.ky < 0.0 && ph.jcell == g.ny + 1) ph.jcell = g.ny;
+  if (ph.kz < 0.0 && ph.kcell == g.nz + 1) ph.kcell = g.nz;
+  if (ph.kx > 0.0 && ph.icell < 1) ph.icell = 1;
+  if (ph.ky > 0.0 && ph.jcell < 1) ph.jcell = 1;
+  if (ph.kz > 0.0 && ph.kcell < 1) ph.kcell = 1;
+  if (par.use_stokes) {
+    ph.mx = cost * cosp; ph.my = cost * sinp; ph.mz = -sint;
+    ph.nx = -sinp; ph.ny = cosp; ph.nz = 0.0;
+    ph.I = 1.0; ph.Q = 0.0; ph.U = 0.0; ph.V = 0.0;
+  }
+  // :134-157
+  ph.nscatt_gas = 0.0; ph.nscatt_dust = 0.0; ph.inside = true;
+  ph.xfreq = par.xfreq0;
+  double Dloc = w.Dfreq(ph.icell, ph.jcell, ph.kcell), aloc = w.voigt_a(ph.icell, ph.jcell, ph.kcell);
+  // :243-300
+  switch (par.spectral_type) {
+    case LART_SPEC_CONTINUUM:
+      ph.xfreq = r.uniform() * (g.xfreq_max - g.xfreq_min) + g.xfreq_min;
+      ph.xfreq = ph.xfreq / (Dloc / g.Dfreq_ref);
+      break;
+    case LART_SPEC_VOIGT0:
+      ph.xfreq = ph.xfreq + rand_voigt(r, par.voigt_a0) * par.Dfreq0 / Dloc;
+      break;
+    case LART_SPEC_VOIGT:
+      ph.xfreq = ph.xfreq + rand_voigt(r, aloc);
+      break;
+    case LART_SPEC_GAUSSIAN:
+      ph.xfreq = ph.xfreq + r.gauss() * par.gaussian_sigma_x;
+      ph.xfreq = ph.xfreq / (Dloc / g.Dfreq_ref);
+      break;
+    default:
+      break;
+  }
+  double u1 = w.vdotk(ph.icell, ph.jcell, ph.kcell, ph.kx, ph.ky, ph.kz);
+  if (!par.comoving_source) ph.xfreq = ph.xfreq - u1;  // :303-306
+  if (par.save_Jin) {                                  // :309-322
+    double xlab = (ph.xfreq + u1) * (Dloc / g.Dfreq_ref);
+    int ix = static_cast<int>(std::floor((xlab - g.xfreq_min) / g.dxfreq)) + 1;
+    if (ix >= 1 && ix <= g.nxfreq) tl.Jin[ix - 1] += ph.wgt;
+  }
+  if (par.save_peeloff) peeling_direct(w, ph, tl);  // :334-336
+}
+
+// impact radius of the photon's line w.r.t. the origin — run_simulation_mod.f90:302-330
+inline double impact_radius(const World &w, const Photon &ph, double &mx, double &my, double &mz) {
+  double rmax = w.g->rmax;
+  double xp = ph.x, yp = ph.y, zp = ph.z;
+  if (rmax > 0.0) {
+    double rr = ph.x * ph.x + ph.y * ph.y + ph.z * ph.z, dist = 0.0;
+    if (rr > rmax * rmax) {
+      double rk = ph.x * ph.kx + ph.y * ph.ky + ph.z * ph.kz;
+      double det = rk * rk - (rr - rmax * rmax);
+      dist = (det < 0.0) ? 0.0 : -rk + std::sqrt(std::fmax(0.0, det));
+    }
+    xp = ph.x + dist * ph.kx; yp = ph.y + dist * ph.ky; zp = ph.z + dist * ph.kz;
+  }
+  double rk = xp * ph.kx + yp * ph.ky + zp * ph.kz;
+  mx = xp - rk * ph.kx; my = yp - rk * ph.ky; mz = zp - rk * ph.kz;
+  return std::sqrt(mx * mx + my * my + mz * mz);
+}
+
+// make_all_initial_photons / make_all_photons — run_simulation_mod.f90:249-358
+void record_initial(const World &w, const Photon &ph, lart_allph_out &ap) {
+  if (ap.xfreq1) ap.xfreq1[ph.id - 1] = ph.xfreq;
+  if (w.par->source_geometry != LART_SRC_POINT && ap.rp0) {
+    double mx, my, mz;
+    ap.rp0[ph.id - 1] = impact_radius(w, ph, mx, my, mz);
+  }
+}
+void record_final(const World &w, const Photon &ph, lart_allph_out &ap) {
+  double mx, my, mz;
+  double mm = impact_radius(w, ph, mx, my, mz);
+  size_t s = static_cast<size_t>(ph.id - 1);
+  if (ap.rp) ap.rp[s] = mm;
+  if (ap.xfreq2) ap.xfreq2[s] = ph.xfreq_ref;
+  if (ap.nscatt_gas) ap.nscatt_gas[s] = ph.nscatt_gas;
+  if (ap.nscatt_dust) ap.nscatt_dust[s] = ph.nscatt_dust;
+  if (w.par->use_stokes) {
+    double cos2p = 1.0, sin2p = 0.0;
+    if (mm > 0.0) {
+      mx /= mm; my /= mm; mz /= mm;
+      double cosp = mx * ph.mx + my * ph.my + mz * ph.mz, sinp = mx * ph.nx + my * ph.ny + mz * ph.nz;
+      cos2p = 2.0 * cosp * cosp - 1.0;
+      sin2p = 2.0 * sinp * cosp;
+    }
+    if (ap.I) ap.I[s] = ph.wgt;
+    if (ap.Q) ap.Q[s] = (cos2p * ph.Q + sin2p * ph.U) * ph.wgt;
+    if (ap.U) ap.U[s] = (-sin2p * ph.Q + cos2p * ph.U) * ph.wgt;
+    if (ap.V) ap.V[s] = ph.V * ph.wgt;
+  }
+}
+
+// add_escaped_fraction_to_Jout — run_simulation_mod.f90:208-247
+void add_escaped_fraction(const World &w, const Photon &ph, double tau0, Tally &tl) {
+  const lart_grid &g = *w.g;
+  double wgt_esc = ph.wgt * std::exp(-tau0);
+  double u1 = w.vdotk(ph.icell, ph.jcell, ph.kcell, ph.kx, ph.ky, ph.kz);
+  double xref = (ph.xfreq + u1) * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
+  int ix = static_cast<int>(std::floor((xref - g.xfreq_min) / g.dxfreq)) + 1;
+  if (ix >= 1 && ix <= g.nxfreq) {
+    tl.Jout[ix - 1] += wgt_esc;
+    if (w.par->save_Jmu) tl.Jmu[(ix - 1) + static_cast<size_t>(g.nxfreq) * (jmu_bin(*w.par, ph.kz) - 1)] += wgt_esc;
+  }
+}
+
+// one photon, start to finish — run_simulation_mod.f90:155-196
+// max_events > 0 abandons the photon after that many scatterings (bounded
+// CPU-baseline samples only; never used for parity).
+void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_events) {
+  Photon ph;
+  ph.id = id;
+  r.start_stream(static_cast<uint64_t>(id));
+  generate_photon(w, ph, r, tl);
+  if (w.par->save_all_photons) record_initial(w, ph, tl.shared->allph);
+  bool first = true;
+  int64_t nev = 0;
+  while (ph.inside) {
+    double tau;
+    if (first) {  // :163-177 forced first scattering
+      double tau0 = raytrace_to_edge(w, ph, &tl.cnt);
+      add_escaped_fraction(w, ph, tau0, tl);
+      double wgt1 = 1.0 - std::exp(-tau0);
+      ph.wgt = ph.wgt * wgt1;
+      tau = (tau0 > 0.0) ? -std::log(1.0 - r.uniform() * wgt1) : kHugest;
+      first = false;
+    } else {
+      tau = -std::log(r.uniform());
+    }
+    raytrace_to_tau(w, ph, tau, &tl, &tl.cnt);
+    if (ph.inside) {
+      scattering(w, ph, r, tl);
+      if (max_events > 0 && ++nev >= max_events) break;
+    }
+  }
+  tl.nscatt_gas += ph.nscatt_gas;
+  tl.nscatt_dust += ph.nscatt_dust;
+  tl.cnt.n_photons_done += 1;
+  if (w.par->save_all_photons && !(max_events > 0 && ph.inside)) record_final(w, ph, tl.shared->allph);
+}
+
+std::string g_err;
+
+World make_world(const lart_config *cfg) {
+  World w;
+  w.g = &cfg->grid;
+  w.par = &cfg->par;
+  w.line = &cfg->line;
+  w.sm = &cfg->scatt_mat;
+  w.obs = cfg->observers;
+  w.zonly = cfg->par.xy_periodic && cfg->grid.nx == 1 && cfg->grid.ny == 1;  // setup.f90:957-965
+  return w;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C interface (ctypes) — mirrors the batched entry points of include/lart_gpu.h
+// ===========================================================================
+extern "C" {
+
+const char *oracle_last_error(void) { return g_err.c_str(); }
+
+int oracle_voigt(int64_t n, const double *x, const double *a, double *H) {
+  for (int64_t i = 0; i < n; ++i) H[i] = voigt_seon2(x[i], a[i]);
+  return 0;
+}
+
+int oracle_raytrace_edge(const lart_config *cfg, int64_t n, const double *x, const double *y, const double *z,
+                         const double *kx, const double *ky, const double *kz, const double *xfreq,
+                         const int32_t *ic, const int32_t *jc, const int32_t *kc, double *tau, int32_t *nsteps,
+                         int32_t trace_cap, int32_t *trace) {
+  World w = make_world(cfg);
+  for (int64_t i = 0; i < n; ++i) {
+    Photon p;
+    p.x = x[i]; p.y = y[i]; p.z = z[i]; p.kx = kx[i]; p.ky = ky[i]; p.kz = kz[i];
+    p.xfreq = xfreq[i]; p.icell = ic[i]; p.jcell = jc[i]; p.kcell = kc[i];
+    int ns = 0;
+    tau[i] = raytrace_to_edge(w, p, nullptr, &ns, trace_cap, trace ? trace + i * static_cast<int64_t>(trace_cap) : nullptr);
+    if (nsteps) nsteps[i] = ns;
+  }
+  return 0;
+}
+
+int oracle_raytrace_tau(const lart_config *cfg, int64_t n, double *x, double *y, double *z, const double *kx,
+                        const double *ky, const double *kz, double *xfreq, int32_t *ic, int32_t *jc, int32_t *kc,
+                        const double *tau_in, int32_t *inside, double *xfreq_ref, int32_t *nsteps) {
+  World w = make_world(cfg);
+  for (int64_t i = 0; i < n; ++i) {
+    Photon p;
+    p.x = x[i]; p.y = y[i]; p.z = z[i]; p.kx = kx[i]; p.ky = ky[i]; p.kz = kz[i];
+    p.xfreq = xfreq[i]; p.icell = ic[i]; p.jcell = jc[i]; p.kcell = kc[i];
+    p.inside = true;
+    int ns = 0;
+    raytrace_to_tau(w, p, tau_in[i], nullptr, nullptr, &ns);
+    x[i] = p.x; y[i] = p.y; z[i] = p.z; xfreq[i] = p.xfreq;
+    ic[i] = p.icell; jc[i] = p.jcell; kc[i] = p.kcell;
+    inside[i] = p.inside ? 1 : 0;
+    if (xfreq_ref) xfreq_ref[i] = p.inside ? 0.0 : p.xfreq_ref;
+    if (nsteps) nsteps[i] = ns;
+  }
+  return 0;
+}
+
+int oracle_xcrit(const lart_config *cfg, int64_t n, const double *x, const double *y, const double *z,
+                 const int32_t *ic, const int32_t *jc, const int32_t *kc, double *xcrit) {
+  World w = make_world(cfg);
+  for (int64_t i = 0; i < n; ++i) {
+    double a, b;
+    car_xcrit_local(w, ic[i], jc[i], kc[i], x[i], y[i], z[i], a, b);
+    xcrit[i] = a;
+  }
+  return 0;
+}
+
+// kinds as in lart_gpu_sample_batch.  rng_mode 1: Philox stream ids[i];
+// rng_mode 0: one MT19937-64 stream seeded with `seed`, elements in order.
+int oracle_sample(int32_t kind, int32_t rng_mode, uint64_t seed, int64_t n, const int64_t *ids, const double *p0,
+                  const double *p1, int32_t ndraw, double *out) {
+  Rng r;
+  r.mode = rng_mode;
+  r.seed = seed;
+  if (rng_mode == 0) r.mt.init(static_cast<int64_t>(seed));
+  for (int64_t i = 0; i < n; ++i) {
+    if (rng_mode == 1) r.start_stream(static_cast<uint64_t>(ids ? ids[i] : i));
+    for (int j = 0; j < ndraw; ++j) {
+      double v;
+      switch (kind) {
+        case 0: v = r.uniform(); break;
+        case 1: v = r.gauss(); break;
+        case 2: v = rand_resonance_vz(r, p0[i], p1[i]); break;
+        case 3: v = rand_resonance(r, p0[i]); break;
+        case 4: v = rand_hg(r, p0[i]); break;
+        case 5: v = rand_voigt(r, p0[i]); break;
+        default: g_err = "oracle_sample: unknown kind"; return 1;
+      }
+      out[i * static_cast<int64_t>(ndraw) + j] = v;
+    }
+  }
+  return 0;
+}
+
+// raw generator words for known-answer tests
+int oracle_philox_block(uint64_t seed, uint64_t stream, uint64_t block, uint32_t out[4]) {
+  uint32_t c[4] = {static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32), static_cast<uint32_t>(block), static_cast<uint32_t>(block >> 32)};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+  return 0;
+}
+int oracle_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  philox4x32_10(c, key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+  return 0;
+}
+int oracle_mt64_words(int64_t seed, int64_t n, uint64_t *out) {
+  Mt64 m;
+  m.init(seed);
+  for (int64_t i = 0; i < n; ++i) out[i] = m.next();
+  return 0;
+}
+
+// Whole run: photons id = first_id + t*stride ... dealt to `nthreads` threads
+// the way run_equal_number deals them to ranks (run_simulation_mod.f90:150).
+// rng_mode 0 = MT19937-64 seeded seed + 9999*thread (random_mt.f90:941-953);
+// rng_mode 1 = Philox keyed (seed, photon id) — thread-count independent.
+int oracle_run(const lart_config *cfg, int32_t rng_mode, int32_t nthreads, int64_t first_id, int64_t count, int64_t stride,
+               int64_t max_events_per_photon, lart_tallies *out) {
+  if (cfg->line.line_type != 1) { g_err = "oracle_run: only line_type 1"; return 1; }
+  if (cfg->par.xy_periodic && !(cfg->grid.nx == 1 && cfg->grid.ny == 1)) { g_err = "oracle_run: xy_periodic needs nx=ny=1"; return 1; }
+  if (cfg->par.nobs > 0 && (!out->obs || !cfg->observers)) { g_err = "oracle_run: observers/outputs missing"; return 1; }
+  World w = make_world(cfg);
+  if (nthreads < 1) nthreads = 1;
+  const int nxf = cfg->grid.nxfreq;
+  std::vector<Tally> tls(nthreads);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) {
+    Tally &tl = tls[t];
+    tl.Jout.assign(nxf, 0.0);
+    tl.Jin.assign(nxf, 0.0);
+    tl.Jabs.assign(nxf, 0.0);
+    tl.Jmu.assign(static_cast<size_t>(nxf) * (cfg->par.save_Jmu ? cfg->par.nmu : 0), 0.0);
+    tl.shared = out;
+    th.emplace_back([&, t]() {
+      Rng r;
+      r.mode = rng_mode;
+      r.seed = cfg->par.seed;
+      r.cnt = &tls[t].cnt;
+      if (rng_mode == 0) r.mt.init(static_cast<int64_t>(cfg->par.seed) + 9999 * t);
+      for (int64_t q = t; q < count; q += nthreads) run_photon(w, first_id + q * stride, r, tls[t], max_events_per_photon);
+    });
+  }
+  for (auto &x : th) x.join();
+  for (int t = 0; t < nthreads; ++t) {  // reduce_mem — memory_mod_mpi.f90:366-458
+    Tally &tl = tls[t];
+    for (int i = 0; i < nxf; ++i) {
+      if (out->Jout) out->Jout[i] += tl.Jout[i];
+      if (out->Jin) out->Jin[i] += tl.Jin[i];
+      if (out->Jabs) out->Jabs[i] += tl.Jabs[i];
+    }
+    if (out->Jmu) for (size_t i = 0; i < tl.Jmu.size(); ++i) out->Jmu[i] += tl.Jmu[i];
+    out->nscatt_gas += tl.nscatt_gas;
+    out->nscatt_dust += tl.nscatt_dust;
+    out->counters.n_photons_done += tl.cnt.n_photons_done;
+    out->counters.n_scatter += tl.cnt.n_scatter;
+    out->counters.n_cellsteps += tl.cnt.n_cellsteps;
+    out->counters.n_peel += tl.cnt.n_peel;
+    out->counters.n_rng += tl.cnt.n_rng;
+    out->counters.n_reject_iter += tl.cnt.n_reject_iter;
+  }
+  return 0;
+}
+
+int oracle_hardware_threads(void) { return static_cast<int>(std::thread::hardware_concurrency()); }
+
+}  // extern "C"

@@ -137,14 +137,20 @@ typedef struct lart_config {
   const lart_observer *observers;  /* par.nobs entries                      */
   int32_t device;                  /* CUDA device ordinal                   */
   int32_t pool_slots;              /* photons in flight; 0 = auto           */
-  int32_t quantum;                 /* scattering events per slot per launch; 0 = auto */
+  int32_t quantum;                 /* scattering events per slot per lart_gpu_step; 0 = auto */
   int32_t flags;                   /* LART_FLAG_*                           */
 } lart_config;
 
 enum {
   LART_FLAG_SOA_GRID = 1,   /* walk the six SoA arrays instead of packed cell records */
-  LART_FLAG_NO_WARP_AGG = 2 /* plain atomics for peel tallies (ablation)      */
+  LART_FLAG_NO_WARP_AGG = 2, /* plain atomics for peel tallies (ablation)      */
+  LART_FLAG_MONOLITHIC = 4,  /* one thread per photon slot, no stage compaction
+                                (the "before" arm of the warp-efficiency evidence) */
+  LART_FLAG_STAGE_TIMING = 8 /* CUDA-event timing of every stage kernel (bench/roofline) */
 };
+
+/* stage kernels of one wave, in launch order (index into lart_gpu_stage_ms) */
+enum { LART_STAGE_EMIT = 0, LART_STAGE_TRACE = 1, LART_STAGE_SCATTER = 2, LART_STAGE_PEEL = 3, LART_STAGE_COUNT = 4 };
 
 /* per-observer output cubes (src/define.f90:561-600); frequency fastest:
  * cube(ixf,ix,iy) at [(ixf-1) + nxfreq*((ix-1) + nxim*(iy-1))]. NULL = skip. */
@@ -193,9 +199,9 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out);
 int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride);
 
 /* Bounded-work variant of the same loop (used for benchmarking heavy-tailed
- * cases): begin() queues the photon ids, each step() launches ONE pass of the
- * persistent kernel in which every pool slot processes at most `quantum`
- * scattering events (finished photons are refilled from the queue);
+ * cases): begin() queues the photon ids, each step() advances every pool slot by
+ * at most `quantum` scattering events (`quantum` waves of the emit/trace/scatter/
+ * peel stage kernels; finished photons are refilled from the queue);
  * *in_flight returns photons still alive or queued. */
 int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride);
 int lart_gpu_step(lart_gpu_handle h, int32_t quantum, int64_t *in_flight);
@@ -217,6 +223,15 @@ int lart_gpu_allph_buffer(lart_gpu_handle h, void **dev_ptr, int64_t *n_doubles)
 int lart_gpu_stream(lart_gpu_handle h, void **stream);
 /* event-timed duration of the transport kernels since create/reset, ms */
 int lart_gpu_kernel_ms(lart_gpu_handle h, double *ms, int64_t *launches);
+
+/* with LART_FLAG_STAGE_TIMING: summed CUDA-event duration (ms) and launch count of
+ * each stage kernel since create/reset (monolithic driver: everything in TRACE) */
+int lart_gpu_stage_ms(lart_gpu_handle h, double ms[LART_STAGE_COUNT], int64_t launches[LART_STAGE_COUNT]);
+/* photon slots in flight (after auto-sizing) */
+int lart_gpu_pool_slots(lart_gpu_handle h, int64_t *slots);
+/* FP64 FMA throughput of `device` measured with a register-resident DFMA loop,
+ * TFLOP/s (2 flops per FMA): the issue-rate denominator of the FP64 roofline. */
+int lart_gpu_measure_fp64(int32_t device, double *tflops);
 
 const char *lart_gpu_last_error(void);
 

@@ -1,0 +1,1025 @@
+// lart_device.cuh — device-side physics of the Cartesian photon loop (sm_100a).
+//
+// Building blocks shared by every kernel in lart_engine.cu: Philox4x32-10 stream
+// per photon, voigt_seon2, the DDA cell walk, the random variates, scattering,
+// emission and the peel-off descriptors.  Each block cites the reference lines it
+// reproduces (paths relative to the reference tree).  All arithmetic is FP64 as in
+// the reference (define.f90:25); the deterministic pieces (Voigt, DDA) use explicit
+// round-to-nearest intrinsics so that no FMA contraction can change a bit relative
+// to the plain IEEE evaluation order of the Fortran expressions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lart {
+
+#define LART_DEV __device__ __forceinline__
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+
+constexpr double kPi = 3.141592653589793238462643383279502884197;
+constexpr double kTwoPi = 6.283185307179586476925286766559005768394;
+constexpr double kFourPi = 12.56637061435917295385057353311801153679;
+constexpr double kHalfPi = kPi / 2.0;
+constexpr double kRad2Deg = 180.0 / kPi;
+constexpr double kHugest = 1.7976931348623157e308;  // huge(1d0), define.f90:38
+constexpr double kTauHuge = 745.2;                  // raytrace_car.f90:432
+
+// One grid cell, packed so that a DDA step touches two 32-byte sectors instead of
+// six (SoA).  Built on the device from the host's SoA arrays at create time.
+struct __align__(64) Cell {
+  double rhokap, voigt_a, Dfreq, vfx, vfy, vfz, rhokapD, pad;
+};
+
+struct DevObserver {
+  double x, y, z;
+  double R[9];  // Fortran order: R[(r-1)+3*(c-1)]
+  double dxim, dyim;
+  int nxim, nyim;
+};
+
+// offsets (in doubles) inside the contiguous tally buffer; -1 = not saved
+struct TallyLayout {
+  long long Jout, Jin, Jabs, Jmu;
+  long long obs_base, obs_stride;  // observer k starts at obs_base + k*obs_stride
+  long long cube[7];               // scatt, direc, direc0, I, Q, U, V   (within an observer block)
+  long long img[7];                // the same, 2-D
+  long long scalars;               // nscatt_gas, nscatt_dust
+  long long counters;              // 6 work counters
+  long long total;
+};
+enum { T_SCATT = 0, T_DIREC = 1, T_DIREC0 = 2, T_I = 3, T_Q = 4, T_U = 5, T_V = 6 };
+enum { C_PHOTONS = 0, C_SCATTER = 1, C_CELLSTEPS = 2, C_PEEL = 3, C_RNG = 4, C_REJECT = 5 };
+
+// Everything a kernel needs, passed by value as a __grid_constant__ parameter.
+struct DevParams {
+  // grid
+  int nx, ny, nz, nxfreq;
+  double dx, dy, dz;
+  double xmin, ymin, zmin, xmax, ymax, zmax;
+  double Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax;
+  const double *xface, *yface, *zface;
+  const Cell *cells;                                            // packed records (default walk)
+  const double *rhokap, *voigt_a, *Dfreq, *vfx, *vfy, *vfz, *rhokapD;  // SoA (ablation / batch API)
+  const double *voigt_tab;  // [202][4] interleaved h0,h1,h2,h3
+  // par / line
+  unsigned long long seed;
+  double xfreq0, xs, ys, zs, source_rmax, albedo, hgg, voigt_a0, Dfreq0, gaussian_sigma_x, mu_min, dmu;
+  double E1, E2, E3, g_recoil0;
+  int nmu, spectral_type, source_geometry;
+  int zonly, dust, soa, comoving_source, recoil, core_skip, core_skip_global, use_stokes, use_reduced_wgt;
+  int save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D, save_direc0, save_all_photons;
+  int warp_agg;
+  int nobs;
+  const DevObserver *obs;
+  // dust scattering matrix
+  int nPDF;
+  const double *sm_coss, *sm_S11, *sm_S12, *sm_S33, *sm_S34, *sm_pdf;
+  const int *sm_alias;
+  // outputs
+  double *tally;
+  TallyLayout lay;
+  double *allph[10];  // rp0, rp, xfreq1, xfreq2, nscatt_gas, nscatt_dust, I, Q, U, V (NULL = off)
+  long long nphotons;
+};
+enum { A_RP0 = 0, A_RP, A_XFREQ1, A_XFREQ2, A_NSG, A_NSD, A_I, A_Q, A_U, A_V };
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), key = seed, counter = (photon id, block).
+// One block gives two 64-bit words; each word maps to the reference's open
+// interval (0,1): ((w>>12)+0.5)*2^-52 — random_mt.f90:628-629.
+// ---------------------------------------------------------------------------
+LART_DEV void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+struct Counters {
+  unsigned long long scatter = 0, cellsteps = 0, peel = 0, rng = 0, reject = 0, photons = 0;
+};
+
+struct Rng {
+  unsigned long long seed, stream, ndraw, spare;
+  unsigned long long nrng;  // uniforms drawn through this object (work counter)
+  bool gauss_stored;
+  double gset;
+  LART_DEV void start(unsigned long long seed_, unsigned long long id, unsigned long long ndraw_ = 0) {
+    seed = seed_; stream = id; ndraw = ndraw_; gauss_stored = false; gset = 0.0; nrng = 0; spare = 0;
+    if (ndraw & 1ULL) {  // resume in the middle of a block: regenerate the second word
+      uint32_t c0, c1, c2, c3;
+      block(ndraw >> 1, c0, c1, c2, c3);
+      spare = (unsigned long long)c2 | ((unsigned long long)c3 << 32);
+    }
+  }
+  LART_DEV void block(unsigned long long blk, uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3) const {
+    c0 = (uint32_t)stream; c1 = (uint32_t)(stream >> 32); c2 = (uint32_t)blk; c3 = (uint32_t)(blk >> 32);
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  }
+  LART_DEV double uniform() {
+    unsigned long long w;
+    if ((ndraw & 1ULL) == 0) {
+      uint32_t c0, c1, c2, c3;
+      block(ndraw >> 1, c0, c1, c2, c3);
+      w = (unsigned long long)c0 | ((unsigned long long)c1 << 32);
+      spare = (unsigned long long)c2 | ((unsigned long long)c3 << 32);
+    } else {
+      w = spare;
+    }
+    ++ndraw;
+    ++nrng;
+    return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+  }
+  // rand_gauss1 — random_mt.f90:964-988 (Marsaglia polar; the spare deviate is kept
+  // per photon stream, never shared between photons)
+  LART_DEV double gauss(unsigned long long &nreject) {
+    if (gauss_stored) { gauss_stored = false; return gset; }
+    double v1, v2, rsq;
+    for (;;) {
+      v1 = 2.0 * uniform() - 1.0;
+      v2 = 2.0 * uniform() - 1.0;
+      rsq = v1 * v1 + v2 * v2;
+      ++nreject;
+      if (rsq > 0.0 && rsq < 1.0) break;
+    }
+    rsq = sqrt(-2.0 * log(rsq) / rsq);
+    gset = v1 * rsq;
+    gauss_stored = true;
+    return v2 * rsq;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// voigt_seon2 — voigt_mod.f90:541-733.  tab[k*4 + {0,1,2,3}] = h0,h1,h2,h3 at node k
+// (0-based; h0/h2 are zero beyond node 100 and unused there).
+// ---------------------------------------------------------------------------
+LART_DEV double voigt_seon2(const double *__restrict__ tab, double vin, double a) {
+  const double one_sqrtPI = 0.56418958354775628695;
+  double v = (vin < 0.0) ? -vin : vin;
+  if (v < 1.0) {  // :691-700
+    double vv = DMUL(v, 20.0);
+    int k1 = (int)vv;  // 0-based node
+    const double *t1 = tab + 4 * k1, *t2 = t1 + 4;
+    double y1 = DADD(t1[0], DMUL(a, DADD(t1[1], DMUL(a, t1[2]))));
+    double y2 = DADD(t2[0], DMUL(a, DADD(t2[1], DMUL(a, t2[2]))));
+    return DADD(y1, DMUL(DSUB(y2, y1), DSUB(vv, (double)k1)));
+  } else if (v < 5.0) {  // :701-717
+    double vv = DMUL(v, 20.0);
+    int k1 = (int)vv - 1;  // 0-based node of the first of three
+    const double *t1 = tab + 4 * k1, *t2 = t1 + 4, *t3 = t1 + 8;
+    double y1 = DADD(t1[0], DMUL(a, DADD(t1[1], DMUL(a, DADD(t1[2], DMUL(a, t1[3]))))));
+    double y2 = DADD(t2[0], DMUL(a, DADD(t2[1], DMUL(a, DADD(t2[2], DMUL(a, t2[3]))))));
+    double y3 = DADD(t3[0], DMUL(a, DADD(t3[1], DMUL(a, DADD(t3[2], DMUL(a, t3[3]))))));
+    double u1 = (double)k1, u2 = (double)(k1 + 1), u3 = (double)(k1 + 2);
+    double d1 = DSUB(vv, u1), d2 = DSUB(vv, u2), d3 = DSUB(vv, u3);
+    double A = DMUL(DMUL(DMUL(0.5, y1), d2), d3);
+    double B = DMUL(DMUL(y2, d1), d3);
+    double Cc = DMUL(DMUL(DMUL(0.5, y3), d1), d2);
+    return DADD(DSUB(A, B), Cc);
+  } else if (v < 10.0) {  // :718-726
+    double vv = DMUL(v, 20.0);
+    int k1 = (int)vv;
+    const double *t1 = tab + 4 * k1, *t2 = t1 + 4;
+    double a2 = DMUL(a, a);
+    double y1 = DMUL(a, DADD(t1[1], DMUL(a2, t1[3])));
+    double y2 = DMUL(a, DADD(t2[1], DMUL(a2, t2[3])));
+    return DADD(y1, DMUL(DSUB(y2, y1), DSUB(vv, (double)k1)));
+  }
+  double v2 = 1.0 / DMUL(v, v);  // :727-731
+  double inner = DADD(DSUB(1.5, DMUL(a, a)), DMUL(3.75, v2));
+  return DMUL(DMUL(DMUL(one_sqrtPI, a), v2), DADD(1.0, DMUL(inner, v2)));
+}
+
+// ---------------------------------------------------------------------------
+// grid access (0-based linear index; x fastest as in grid_type)
+// ---------------------------------------------------------------------------
+struct CellData {
+  double rhokap, voigt_a, Dfreq, vfx, vfy, vfz, rhokapD;
+};
+LART_DEV size_t cell_index(const DevParams &P, int ic, int jc, int kc) {  // 1-based in
+  return (size_t)(ic - 1) + (size_t)P.nx * ((size_t)(jc - 1) + (size_t)P.ny * (size_t)(kc - 1));
+}
+LART_DEV void load_cell(const DevParams &P, size_t c, CellData &o) {
+  if (!P.soa) {
+    const double2 *q = reinterpret_cast<const double2 *>(P.cells + c);
+    double2 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2), e = __ldg(q + 3);
+    o.rhokap = a.x; o.voigt_a = a.y; o.Dfreq = b.x; o.vfx = b.y; o.vfy = d.x; o.vfz = d.y; o.rhokapD = e.x;
+  } else {
+    o.rhokap = __ldg(P.rhokap + c); o.voigt_a = __ldg(P.voigt_a + c); o.Dfreq = __ldg(P.Dfreq + c);
+    o.vfx = __ldg(P.vfx + c); o.vfy = __ldg(P.vfy + c); o.vfz = __ldg(P.vfz + c);
+    o.rhokapD = P.dust ? __ldg(P.rhokapD + c) : 0.0;
+  }
+}
+LART_DEV double vdotk(const CellData &c, double kx, double ky, double kz) {
+  return DADD(DADD(DMUL(c.vfx, kx), DMUL(c.vfy, ky)), DMUL(c.vfz, kz));
+}
+
+// ---------------------------------------------------------------------------
+// DDA — setup_traversal_car (raytrace_car.f90:12-87) and the step shared by
+// raytrace_to_edge_car (:410-508, _zonly :1138-1234) and raytrace_to_tau_car
+// (:1425-1648, _zonly :2519-2675).
+// ---------------------------------------------------------------------------
+struct Ray {
+  double x0, y0, z0, kx, ky, kz;    // start point and direction (fixed)
+  double tx, ty, tz, delx, dely, delz;
+  double d, tau, xfreq, u1;
+  CellData cell;                    // record of the current cell (ic,jc,kc)
+  int ic, jc, kc;                   // 1-based
+  int istep, jstep, kstep;
+  int nsteps;
+};
+
+LART_DEV bool axis_setup(double k, double p, int &cell, int n, const double *face, double d, int &step, double &t,
+                         double &del, bool eq_test) {
+  if (k > 0.0) {
+    if (cell > n) {
+      double f = __ldg(face + cell - 1);
+      if (eq_test ? (f == p) : (f <= p)) return true;
+    }
+    step = 1;
+    t = DSUB(__ldg(face + cell), p) / k;
+    del = d / k;
+  } else if (k < 0.0) {
+    if (__ldg(face + cell - 1) == p) {
+      if (cell > 1) cell -= 1; else return true;
+    }
+    step = -1;
+    t = DSUB(__ldg(face + cell - 1), p) / k;
+    del = -d / k;
+  } else {
+    step = 0; t = kHugest; del = kHugest;
+  }
+  return false;
+}
+
+// returns true when the photon is already leaving the grid (no step is taken)
+LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
+                        int ic, int jc, int kc, double xfreq, bool zonly_eq) {
+  r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
+  r.ic = ic; r.jc = jc; r.kc = kc;
+  r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0;
+  if (P.zonly) {
+    r.istep = r.jstep = 0; r.tx = r.ty = kHugest; r.delx = r.dely = kHugest;
+    if (axis_setup(kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, zonly_eq)) return true;
+  } else {
+    if (axis_setup(kx, x, r.ic, P.nx, P.xface, P.dx, r.istep, r.tx, r.delx, false)) return true;
+    if (axis_setup(ky, y, r.jc, P.ny, P.yface, P.dy, r.jstep, r.ty, r.dely, false)) return true;
+    if (axis_setup(kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, false)) return true;
+  }
+  load_cell(P, cell_index(P, r.ic, r.jc, r.kc), r.cell);
+  r.u1 = vdotk(r.cell, kx, ky, kz);
+  return false;
+}
+
+// opacity of the current cell at the ray's current frequency (:1488-1494)
+LART_DEV double ray_opacity(const DevParams &P, const double *vtab, const Ray &r) {
+  double k = DMUL(r.cell.rhokap, voigt_seon2(vtab, r.xfreq, r.cell.voigt_a));
+  if (P.dust) k = DADD(k, r.cell.rhokapD);
+  return k;
+}
+
+// minloc([tx,ty,tz]) — first minimum wins (:476,:1506); z-only walks z
+LART_DEV int ray_axis(const DevParams &P, const Ray &r) {
+  if (P.zonly) return 3;
+  if (r.tx <= r.ty && r.tx <= r.tz) return 1;
+  if (r.ty <= r.tz) return 2;
+  return 3;
+}
+
+// Move the index along `axis`; false when the ray left the grid.  On success loads
+// the new cell and shifts the frequency into its frame (:1586-1589 / :485-494).
+LART_DEV bool ray_advance(const DevParams &P, Ray &r, int axis) {
+  if (axis == 1) {
+    r.ic += r.istep;
+    if (r.ic < 1 || r.ic > P.nx) { r.ic -= r.istep; return false; }
+    r.tx = DADD(r.tx, r.delx);
+  } else if (axis == 2) {
+    r.jc += r.jstep;
+    if (r.jc < 1 || r.jc > P.ny) { r.jc -= r.jstep; return false; }
+    r.ty = DADD(r.ty, r.dely);
+  } else {
+    r.kc += r.kstep;
+    if (r.kc < 1 || r.kc > P.nz) { r.kc -= r.kstep; return false; }
+    r.tz = DADD(r.tz, r.delz);
+  }
+  return true;
+}
+LART_DEV void ray_shift(const DevParams &P, Ray &r) {
+  double Dold = r.cell.Dfreq;
+  load_cell(P, cell_index(P, r.ic, r.jc, r.kc), r.cell);
+  double u2 = vdotk(r.cell, r.kx, r.ky, r.kz);
+  r.xfreq = DSUB(DMUL(DADD(r.xfreq, r.u1), Dold) / r.cell.Dfreq, u2);
+  r.u1 = u2;
+}
+
+// One cell step of raytrace_to_edge.  Returns true when the walk is finished.
+LART_DEV bool edge_step(const DevParams &P, const double *vtab, Ray &r) {
+  double kap = ray_opacity(P, vtab, r);
+  ++r.nsteps;
+  int ax = ray_axis(P, r);
+  double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
+  r.tau = DADD(r.tau, DMUL(DSUB(tn, r.d), kap));
+  r.d = tn;
+  if (!ray_advance(P, r, ax)) return true;
+  if (r.tau >= kTauHuge) return true;
+  ray_shift(P, r);
+  return false;
+}
+
+// One cell step of raytrace_to_tau.  status: 0 = keep walking, 1 = reached tau_in
+// (position in xp,yp,zp), 2 = left the grid.
+LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau_in, double &xp, double &yp, double &zp) {
+  double kap = ray_opacity(P, vtab, r);
+  ++r.nsteps;
+  int ax = ray_axis(P, r);
+  double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
+  r.tau = DADD(r.tau, DMUL(DSUB(tn, r.d), kap));
+  r.d = tn;
+  if (r.tau >= tau_in) {  // :1513-1524
+    if (kap > 0.0) r.d = DSUB(r.d, DSUB(r.tau, tau_in) / kap);
+    xp = DADD(r.x0, DMUL(r.d, r.kx));
+    yp = DADD(r.y0, DMUL(r.d, r.ky));
+    zp = DADD(r.z0, DMUL(r.d, r.kz));
+    return 1;
+  }
+  if (!ray_advance(P, r, ax)) return 2;
+  ray_shift(P, r);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// photon_type — define.f90:80-111 (I == 1 always; E1,E2,E3 are line constants)
+// ---------------------------------------------------------------------------
+enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8 };
+struct Photon {
+  long long id;
+  double x, y, z, kx, ky, kz, mx, my, mz, nx, ny, nz;
+  double xfreq, xfreq_ref, wgt, Q, U, V, nsg, nsd;
+  int ic, jc, kc;
+  int flags;
+};
+
+// ---------------------------------------------------------------------------
+// random variates
+// ---------------------------------------------------------------------------
+// rand_resonance_vz_seon — random_mt.f90:2562-2696
+LART_DEV double rand_resonance_vz(Rng &r, double x0in, double a, unsigned long long &nrej) {
+  const double xc = 1.0 + 1.4142135623730951;
+  const double two_over_PI = 2.0 / kPi;
+  double x0 = fabs(x0in), vz;
+  if (x0 <= 1.0) {  // :2579-2585
+    for (;;) {
+      vz = x0 + a * tan(kPi * (r.uniform() - 0.5));
+      ++nrej;
+      if (r.uniform() <= exp(-vz * vz)) break;
+    }
+    return (x0in < 0.0) ? -vz : vz;
+  }
+  double x0sq = x0 * x0, api = a * kPi;
+  double beta0 = exp(-x0sq / 2.0);
+  double h0_two = beta0 / a, h0 = h0_two / 2.0;
+  // region table: up to three pieces of the piecewise-constant majorant in beta
+  //   piece 0: beta = beta0*sqrt(xi),        C = beta/a
+  //   piece 1: beta = lo1 + w1*xi,            C = c1
+  //   piece 2: beta = lo2 + w2*xi,            C = c2
+  double p0 = 0.0, p01 = 0.0;  // cumulative selection thresholds
+  double lo1 = 0.0, w1 = 0.0, c1 = 0.0, lo2 = 0.0, w2 = 0.0, c2 = 0.0;
+  int mode;  // 0: single piece (lo1,w1,c1); 1: pieces 0+1; 2: pieces 0+1+2
+  double h2 = 0.3861 / (x0sq - 1.373);
+  if (x0 < xc || !(h0 < h2)) {  // :2605-2635 and :2667-2690
+    double dbeta = sqrt(two_over_PI * a * (1.0 - beta0) * beta0 * x0);
+    double beta1 = beta0 + dbeta, one_b1 = 1.0 - beta1;
+    double pb1 = sqrt(-2.0 * log(beta1));
+    double h1 = two_over_PI * beta1 * pb1 / (x0sq - pb1 * pb1);
+    double hm = (x0 < xc) ? h1 : ((h1 > h2) ? h1 : h2);
+    double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * hm, Stot = S0 + S1 + S2;
+    mode = 2; p0 = S0 / Stot; p01 = 1.0 - S2 / Stot;
+    lo1 = beta0; w1 = dbeta; c1 = h0; lo2 = beta1; w2 = one_b1; c2 = hm;
+  } else if (h0_two < h2) {  // :2638-2647
+    mode = 0; lo1 = 0.0; w1 = 1.0; c1 = h2;
+  } else {  // :2648-2666
+    double S0 = beta0 * h0, one_b0 = 1.0 - beta0, S1 = one_b0 * h2, Stot = S0 + S1;
+    mode = 1; p0 = S0 / Stot; lo1 = beta0; w1 = one_b0; c1 = h2;
+  }
+  double t1, delt;
+  for (;;) {
+    double beta, Cb;
+    if (mode == 0) {
+      beta = lo1 + w1 * r.uniform(); Cb = c1;
+    } else {
+      double rs = r.uniform();
+      if (rs < p0) { beta = beta0 * sqrt(r.uniform()); Cb = beta / a; }
+      else if (mode == 1 || rs < p01) { beta = lo1 + w1 * r.uniform(); Cb = c1; }
+      else { beta = lo2 + w2 * r.uniform(); Cb = c2; }
+    }
+    double pb = sqrt(-2.0 * log(beta));
+    double t2 = atan((pb - x0) / a);
+    t1 = atan((-pb - x0) / a);
+    delt = t2 - t1;
+    ++nrej;
+    if (r.uniform() * Cb < (beta / api) * delt) break;
+  }
+  vz = x0 + a * tan(delt * r.uniform() + t1);  // :2693
+  return (x0in < 0.0) ? -vz : vz;
+}
+
+// rand_resonance — random_mt.f90:2974-2993
+LART_DEV double rand_resonance(Rng &r, double E1) {
+  if (E1 > 0.0) {
+    double p2 = sqrt((4.0 - E1) / (3.0 * E1));
+    double Q = (4.0 * r.uniform() - 2.0) / (E1 * (p2 * p2 * p2));
+    double W = cbrt(Q + sqrt(Q * Q + 1.0));
+    return p2 * (W - 1.0 / W);
+  } else if (E1 < 0.0) {
+    double p2 = sqrt(fabs((4.0 - E1) / (3.0 * E1)));
+    double Q = (4.0 * r.uniform() - 2.0) / (E1 * (p2 * p2 * p2));
+    return 2.0 * p2 * cos((acos(Q) + kFourPi) / 3.0);
+  }
+  return 2.0 * r.uniform() - 1.0;
+}
+
+// rand_henyey_greenstein — random_mt.f90:3022-3042
+LART_DEV double rand_hg(Rng &r, double g) {
+  double x = r.uniform();
+  if (g == 0.0) return 2.0 * x - 1.0;
+  double g2 = g * g, twog = 2.0 * g;
+  double q = (1.0 - g2) / (1.0 - g + twog * x);
+  return ((1.0 + g2) - q * q) / twog;
+}
+
+// rand_voigt — random_mt.f90:3062-3083
+LART_DEV double rand_voigt(Rng &r, double a, unsigned long long &nrej) {
+  double c = tan(kPi * r.uniform() - kHalfPi);
+  return a * c + r.gauss(nrej) * (1.0 / 1.4142135623730951);
+}
+
+// rand_alias_linear64 — random_mt.f90:2196-2216
+LART_DEV double rand_alias_linear(Rng &r, const DevParams &P) {
+  int n = P.nPDF - 1;
+  int k = (int)floor(n * r.uniform()) + 1;
+  int idx = (r.uniform() < P.sm_pdf[k - 1]) ? k : P.sm_alias[k - 1];
+  double p0 = P.sm_S11[idx - 1], p1 = P.sm_S11[idx];
+  double x0 = P.sm_coss[idx - 1], x1 = P.sm_coss[idx];
+  return (sqrt(p0 * p0 + (p1 * p1 - p0 * p0) * r.uniform()) - p0) * (x1 - x0) / (p1 - p0) + x0;
+}
+
+// interp_eq — mathlib.f90:71-106
+LART_DEV double interp_eq(const double *x, const double *y, int n, double xnew) {
+  double dx = x[1] - x[0];
+  int i = (int)((xnew - x[0]) / dx + 1.0);
+  if (i <= 0) return y[0];
+  if (i >= n) return y[n - 1];
+  return y[i - 1] + (y[i] - y[i - 1]) * (xnew - x[i - 1]) / dx;
+}
+
+// car_xcrit_local — grid_mod_car.f90:1598-1629
+LART_DEV void car_xcrit_local(const DevParams &P, int i, int j, int k, double x, double y, double z, double voigt_a,
+                              double rhokap, double &xc, double &xc2) {
+  if (P.core_skip_global) { xc = P.xcrit; xc2 = P.xcrit2; return; }
+  xc = 0.0; xc2 = 0.0;
+  if (i < 1 || j < 1 || k < 1) return;
+  double dlx = fmin(x - __ldg(P.xface + i - 1), __ldg(P.xface + i) - x);
+  double dly = fmin(y - __ldg(P.yface + j - 1), __ldg(P.yface + j) - y);
+  double dlz = fmin(z - __ldg(P.zface + k - 1), __ldg(P.zface + k) - z);
+  double dl = fmin(dlx, fmin(dly, dlz));
+  if (dl <= 0.0) return;
+  double atau = voigt_a * rhokap * dl;
+  if (atau > 1.0) { xc = cbrt(atau) / 5.0; xc2 = xc * xc; }
+}
+
+// ---------------------------------------------------------------------------
+// tallies
+// ---------------------------------------------------------------------------
+LART_DEV void tally_add(double *p, double v) {
+  if (v != 0.0) atomicAdd(p, v);
+}
+LART_DEV int freq_bin(const DevParams &P, double xref) {  // 1-based; may be out of range
+  return (int)floor((xref - P.xfreq_min) / P.dxfreq) + 1;
+}
+LART_DEV int jmu_bin(const DevParams &P, double kz) {  // add_to_Jmu — raytrace_car.f90:4049-4064
+  int imu = (int)floor((kz - P.mu_min) / P.dmu) + 1;
+  return imu < 1 ? 1 : (imu > P.nmu ? P.nmu : imu);
+}
+LART_DEV void tally_Jout(const DevParams &P, double xref, double kz, double w) {
+  int ix = freq_bin(P, xref);
+  if (ix >= 1 && ix <= P.nxfreq) {
+    tally_add(P.tally + P.lay.Jout + ix - 1, w);
+    if (P.save_Jmu) tally_add(P.tally + P.lay.Jmu + (ix - 1) + (long long)P.nxfreq * (jmu_bin(P, kz) - 1), w);
+  }
+}
+
+// A peel-off ray waiting for its optical depth: everything the deposit needs.
+enum { PEEL_DIRECT = 0, PEEL_STOKES = 1, PEEL_NOSTOKES = 2 };
+struct PeelRay {
+  double x, y, z, kx, ky, kz, xfreq;
+  double wa, wb;           // weight factors around exp(-tau): wgt = wa*exp(-tau)*wb
+  double sI, sQ, sU, sV;   // detector-frame Stokes per unit weight (Stokes kinds)
+  int ic, jc, kc;
+  int obs, pix, ixf, kind;  // pix = (ix-1)+nxim*(iy-1); ixf 1-based or 0 when outside the cube
+};
+
+// common head of every peeling routine (peelingoff_rect.f90:44-61 / :326-357 / :595-627)
+LART_DEV bool peel_geometry(const DevObserver &ob, const Photon &ph, PeelRay &pr, double &r2) {
+  double kx = ob.x - ph.x, ky = ob.y - ph.y, kz = ob.z - ph.z;
+  r2 = kx * kx + ky * ky + kz * kz;
+  double r = sqrt(r2);
+  kx /= r; ky /= r; kz /= r;
+  pr.x = ph.x; pr.y = ph.y; pr.z = ph.z; pr.kx = kx; pr.ky = ky; pr.kz = kz;
+  pr.ic = ph.ic; pr.jc = ph.jc; pr.kc = ph.kc;
+  const double *R = ob.R;
+  double ox = R[0] * kx + R[3] * ky + R[6] * kz;
+  double oy = R[1] * kx + R[4] * ky + R[7] * kz;
+  double oz = R[2] * kx + R[5] * ky + R[8] * kz;
+  int ix = (int)floor(atan2(-ox, oz) * kRad2Deg / ob.dxim + ob.nxim / 2.0) + 1;
+  int iy = (int)floor(atan2(-oy, oz) * kRad2Deg / ob.dyim + ob.nyim / 2.0) + 1;
+  pr.pix = (ix - 1) + ob.nxim * (iy - 1);
+  return ix >= 1 && ix <= ob.nxim && iy >= 1 && iy <= ob.nyim;
+}
+
+// rotate Stokes to the detector axes (peelingoff_rect.f90:428-445)
+LART_DEV void to_detector(const DevObserver &ob, double nx, double ny, double nz, double Qobs, double Uobs, double &Qdet,
+                          double &Udet) {
+  const double *R = ob.R;
+  double cosg = -(R[0] * nx + R[3] * ny + R[6] * nz);
+  double sing = R[1] * nx + R[4] * ny + R[7] * nz;
+  double cos2g = 2.0 * cosg * cosg - 1.0, sin2g = 2.0 * cosg * sing;
+  Qdet = cos2g * Qobs + sin2g * Uobs;
+  Udet = -sin2g * Qobs + cos2g * Uobs;
+}
+
+// observer azimuth in the photon's (m,n) frame and the new normal (:364-380)
+LART_DEV void stokes_azimuth(const Photon &ph, const PeelRay &pr, double cost, double &sint, double &cosp, double &sinp,
+                             double &nx, double &ny, double &nz) {
+  sint = sqrt(1.0 - cost * cost);
+  if (sint == 0.0) { cosp = 1.0; sinp = 0.0; }
+  else {
+    cosp = (pr.kx * ph.mx + pr.ky * ph.my + pr.kz * ph.mz) / sint;
+    sinp = (pr.kx * ph.nx + pr.ky * ph.ny + pr.kz * ph.nz) / sint;
+  }
+  nx = -sinp * ph.mx + cosp * ph.nx;
+  ny = -sinp * ph.my + cosp * ph.ny;
+  nz = -sinp * ph.mz + cosp * ph.nz;
+}
+
+// peeling_direct_outside — peelingoff_rect.f90:24-129.  cs = photon's cell record.
+LART_DEV bool peel_direct_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph, const CellData &cs,
+                                  PeelRay &pr) {
+  double r2;
+  bool in_image = peel_geometry(ob, ph, pr, r2);
+  double xref;
+  pr.xfreq = ph.xfreq;
+  if (!P.comoving_source) {  // :70-80
+    double u1 = vdotk(cs, ph.kx, ph.ky, ph.kz);
+    xref = ph.xfreq + u1;
+    pr.xfreq = xref - vdotk(cs, pr.kx, pr.ky, pr.kz);
+  } else {  // :81-87
+    xref = ph.xfreq + vdotk(cs, pr.kx, pr.ky, pr.kz);
+  }
+  xref = xref * (cs.Dfreq / P.Dfreq_ref);
+  int ixf = freq_bin(P, xref);
+  pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
+  pr.obs = iobs; pr.kind = PEEL_DIRECT;
+  pr.wa = 1.0 / (kFourPi * r2) * ph.wgt;  // wgt0
+  pr.wb = 1.0;
+  pr.sI = pr.sQ = pr.sU = pr.sV = 0.0;
+  return in_image;
+}
+
+// peeling_resonance_stokes_outside — peelingoff_rect.f90:303-482
+LART_DEV bool peel_resonance_stokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+                                            const CellData &cs, double xfreq_atom, double ux, double uy, double uz,
+                                            PeelRay &pr) {
+  double r2;
+  if (!peel_geometry(ob, ph, pr, r2)) return false;
+  double cost = ph.kx * pr.kx + ph.ky * pr.ky + ph.kz * pr.kz;
+  double sint, cosp, sinp, nx, ny, nz;
+  stokes_azimuth(ph, pr, cost, sint, cosp, sinp, nx, ny, nz);
+  double cos2p = 1.0, sin2p = 0.0;
+  if (sint != 0.0) { cos2p = 2.0 * cosp * cosp - 1.0; sin2p = 2.0 * cosp * sinp; }
+  double cost2 = cost * cost;
+  double S22 = 0.75 * P.E1 * (cost2 + 1.0), S11 = S22 + P.E2, S12 = 0.75 * P.E1 * (cost2 - 1.0);
+  double S33 = 1.5 * P.E1 * cost, S44 = 1.5 * P.E3 * cost;
+  double xfreq = xfreq_atom + (ux * cosp + uy * sinp) * sint + uz * cost;  // :392
+  if (P.recoil) xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
+  double u1 = vdotk(cs, pr.kx, pr.ky, pr.kz);
+  double xref = (xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
+  int ixf = freq_bin(P, xref);
+  double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+  double Iobs = (S11 + S12 * Q0) / kFourPi, Qobs = (S12 + S22 * Q0) / kFourPi;
+  double Uobs = (S33 * U0) / kFourPi, Vobs = (S44 * ph.V) / kFourPi;
+  pr.xfreq = xfreq;
+  pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
+  pr.obs = iobs; pr.kind = PEEL_STOKES;
+  pr.wa = 1.0 / r2; pr.wb = ph.wgt;
+  pr.sI = Iobs; pr.sV = Vobs;
+  to_detector(ob, nx, ny, nz, Qobs, Uobs, pr.sQ, pr.sU);
+  return true;
+}
+
+// peeling_resonance_nostokes_outside — peelingoff_rect.f90:576-690
+LART_DEV bool peel_resonance_nostokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+                                              const CellData &cs, double xfreq_atom, double ux, double uy, double uz,
+                                              PeelRay &pr) {
+  double r2;
+  if (!peel_geometry(ob, ph, pr, r2)) return false;
+  double cost = ph.kx * pr.kx + ph.ky * pr.ky + ph.kz * pr.kz;
+  double cost2 = cost * cost;
+  double sint = sqrt(1.0 - cost2);
+  double rho1 = sqrt(1.0 - ph.kz * ph.kz) * sint;
+  double cosp = 1.0, sinp = 0.0;
+  if (rho1 != 0.0) {
+    double rho = 1.0 / rho1;
+    cosp = rho * (cost * ph.kz - pr.kz);
+    sinp = rho * (ph.kx * pr.ky - pr.kx * ph.ky);
+  }
+  double xfreq = xfreq_atom + (ux * cosp + uy * sinp) * sint + uz * cost;
+  if (P.recoil) xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
+  double u1 = vdotk(cs, pr.kx, pr.ky, pr.kz);
+  double xref = (xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
+  int ixf = freq_bin(P, xref);
+  pr.xfreq = xfreq;
+  pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
+  pr.obs = iobs; pr.kind = PEEL_NOSTOKES;
+  double peel = 0.75 * P.E1 * (cost2 + 1.0) + P.E2;
+  pr.wa = peel / (kFourPi * r2); pr.wb = ph.wgt;
+  pr.sI = pr.sQ = pr.sU = pr.sV = 0.0;
+  return true;
+}
+
+// peeling_dust_stokes_outside — peelingoff_rect.f90:131-299
+LART_DEV bool peel_dust_stokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+                                       const CellData &cs, PeelRay &pr) {
+  double r2;
+  if (!peel_geometry(ob, ph, pr, r2)) return false;
+  double u1 = vdotk(cs, pr.kx, pr.ky, pr.kz);
+  double xref = (ph.xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
+  int ixf = freq_bin(P, xref);
+  double cost = ph.kx * pr.kx + ph.ky * pr.ky + ph.kz * pr.kz;
+  double sint, cosp, sinp, nx, ny, nz;
+  stokes_azimuth(ph, pr, cost, sint, cosp, sinp, nx, ny, nz);
+  double cos2p = 1.0, sin2p = 0.0;
+  if (sint != 0.0) { cos2p = 2.0 * cosp * cosp - 1.0; sin2p = 2.0 * cosp * sinp; }
+  double S11 = interp_eq(P.sm_coss, P.sm_S11, P.nPDF, cost), S12 = interp_eq(P.sm_coss, P.sm_S12, P.nPDF, cost);
+  double S33 = interp_eq(P.sm_coss, P.sm_S33, P.nPDF, cost), S34 = interp_eq(P.sm_coss, P.sm_S34, P.nPDF, cost);
+  double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+  double Iobs = (S11 + S12 * Q0) / kTwoPi, Qobs = (S12 + S11 * Q0) / kTwoPi;
+  double Uobs = (S33 * U0 + S34 * ph.V) / kTwoPi, Vobs = (-S34 * U0 + S33 * ph.V) / kTwoPi;
+  pr.xfreq = ph.xfreq;
+  pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
+  pr.obs = iobs; pr.kind = PEEL_STOKES;
+  pr.wa = 1.0 / r2; pr.wb = ph.wgt;
+  pr.sI = Iobs; pr.sV = Vobs;
+  to_detector(ob, nx, ny, nz, Qobs, Uobs, pr.sQ, pr.sU);
+  return true;
+}
+
+// peeling_dust_nostokes_outside — peelingoff_rect.f90:484-574
+LART_DEV bool peel_dust_nostokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+                                         const CellData &cs, PeelRay &pr) {
+  double r2;
+  if (!peel_geometry(ob, ph, pr, r2)) return false;
+  double u1 = vdotk(cs, pr.kx, pr.ky, pr.kz);
+  double xref = (ph.xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
+  int ixf = freq_bin(P, xref);
+  double cosa = ph.kx * pr.kx + ph.ky * pr.ky + ph.kz * pr.kz;
+  double hg = P.hgg;
+  double base = (1.0 + hg * hg) - 2.0 * hg * cosa;
+  double peel = (1.0 - hg * hg) / (base * sqrt(base)) / kFourPi;
+  pr.xfreq = ph.xfreq;
+  pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
+  pr.obs = iobs; pr.kind = PEEL_NOSTOKES;
+  pr.wa = peel / r2; pr.wb = ph.wgt;
+  pr.sI = pr.sQ = pr.sU = pr.sV = 0.0;
+  return true;
+}
+
+// Deposit one finished peel ray (peelingoff_rect.f90:96-126, :451-479, :674-687).
+// `lanes` = mask of converged lanes calling together; with warp aggregation lanes
+// that hit the same (observer, pixel, frequency bin) are summed in registers first
+// and one lane issues the atomics.
+LART_DEV void peel_deposit(const DevParams &P, const PeelRay &pr, double tau, unsigned lanes) {
+  double e = exp(-tau);
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  int nv;
+  if (pr.kind == PEEL_DIRECT) { v[0] = e * pr.wa; v[1] = pr.wa; nv = 2; }
+  else if (pr.kind == PEEL_STOKES) {
+    double w = pr.wa * e * pr.wb;
+    v[0] = w * pr.sI; v[1] = w * pr.sQ; v[2] = w * pr.sU; v[3] = w * pr.sV; nv = 4;
+  } else { v[0] = pr.wa * e * pr.wb; nv = 1; }
+  bool leader = true;
+  if (P.warp_agg) {
+    unsigned long long key = ((unsigned long long)(unsigned)pr.kind << 60) ^ ((unsigned long long)(unsigned)pr.obs << 44) ^
+                             ((unsigned long long)(unsigned)pr.pix << 12) ^ (unsigned long long)(unsigned)pr.ixf;
+    unsigned grp = __match_any_sync(lanes, key);
+    int lane = threadIdx.x & 31;
+    int lead = __ffs(grp) - 1;
+    leader = lane == lead;
+    unsigned rest = leader ? (grp & ~(1u << lead)) : 0u;  // lanes whose values the leader still has to add
+    int maxpop = __reduce_max_sync(lanes, (unsigned)__popc(rest));
+    for (int it = 0; it < maxpop; ++it) {
+      bool take = rest != 0u;
+      int src = take ? (__ffs(rest) - 1) : lane;
+      rest &= rest - 1u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double o = __shfl_sync(lanes, v[q], src);
+        if (take && q < nv) v[q] += o;
+      }
+    }
+  }
+  if (!leader) return;
+  double *base = P.tally + P.lay.obs_base + (long long)pr.obs * P.lay.obs_stride;
+  const TallyLayout &L = P.lay;
+  long long q3 = (long long)(pr.ixf - 1) + (long long)P.nxfreq * pr.pix;
+  bool c3 = P.save_peeloff_3D && pr.ixf > 0, c2 = P.save_peeloff_2D;
+  if (pr.kind == PEEL_DIRECT) {
+    if (c2) {
+      tally_add(base + L.img[T_DIREC] + pr.pix, v[0]);
+      if (P.use_stokes) tally_add(base + L.img[T_I] + pr.pix, v[0]);
+      if (P.save_direc0) tally_add(base + L.img[T_DIREC0] + pr.pix, v[1]);
+    }
+    if (c3) {
+      tally_add(base + L.cube[T_DIREC] + q3, v[0]);
+      if (P.use_stokes) tally_add(base + L.cube[T_I] + q3, v[0]);
+      if (P.save_direc0) tally_add(base + L.cube[T_DIREC0] + q3, v[1]);
+    }
+  } else if (pr.kind == PEEL_STOKES) {
+    if (c2) {
+      tally_add(base + L.img[T_SCATT] + pr.pix, v[0]); tally_add(base + L.img[T_I] + pr.pix, v[0]);
+      tally_add(base + L.img[T_Q] + pr.pix, v[1]); tally_add(base + L.img[T_U] + pr.pix, v[2]);
+      tally_add(base + L.img[T_V] + pr.pix, v[3]);
+    }
+    if (c3) {
+      tally_add(base + L.cube[T_SCATT] + q3, v[0]); tally_add(base + L.cube[T_I] + q3, v[0]);
+      tally_add(base + L.cube[T_Q] + q3, v[1]); tally_add(base + L.cube[T_U] + q3, v[2]);
+      tally_add(base + L.cube[T_V] + q3, v[3]);
+    }
+  } else {
+    if (c2) tally_add(base + L.img[T_SCATT] + pr.pix, v[0]);
+    if (c3) tally_add(base + L.cube[T_SCATT] + q3, v[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// scattering — scattering_car.f90
+// ---------------------------------------------------------------------------
+// rotate the (m,n,k) triad — scattering_car.f90:470-484 / :314-328
+LART_DEV void rotate_triad(Photon &ph, double cost, double sint, double cosp, double sinp) {
+  double px = cosp * ph.mx + sinp * ph.nx, py = cosp * ph.my + sinp * ph.ny, pz = cosp * ph.mz + sinp * ph.nz;
+  ph.nx = cosp * ph.nx - sinp * ph.mx;
+  ph.ny = cosp * ph.ny - sinp * ph.my;
+  ph.nz = cosp * ph.nz - sinp * ph.mz;
+  ph.mx = cost * px - sint * ph.kx;
+  ph.my = cost * py - sint * ph.ky;
+  ph.mz = cost * pz - sint * ph.kz;
+  ph.kx = sint * px + cost * ph.kx;
+  ph.ky = sint * py + cost * ph.ky;
+  ph.kz = sint * pz + cost * ph.kz;
+}
+// new direction without a triad — scattering_car.f90:795-809 / :568-582
+LART_DEV void rotate_k(Photon &ph, double cost, double sint, double cosp, double sinp) {
+  if (fabs(ph.kz) >= 0.99999999999) {
+    ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
+  } else {
+    double kx1 = ph.kx, ky1 = ph.ky, kz1 = ph.kz;
+    double kr = sqrt(kx1 * kx1 + ky1 * ky1);
+    ph.kx = cost * kx1 + sint * (kz1 * kx1 * cosp - ky1 * sinp) / kr;
+    ph.ky = cost * ky1 + sint * (kz1 * ky1 * cosp + kx1 * sinp) / kr;
+    ph.kz = cost * kz1 - sint * cosp * kr;
+  }
+}
+// azimuth by rejection — scattering_car.f90:364-371 / :280-287
+LART_DEV double sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11, unsigned long long &nrej) {
+  double phi;
+  double env = 1.0 + fabs(S12overS11) * sqrt(ph.Q * ph.Q + ph.U * ph.U);
+  for (;;) {
+    phi = kTwoPi * r.uniform();
+    double s2, c2;
+    sincos(2.0 * phi, &s2, &c2);
+    double Prand = env * r.uniform();
+    double Pcomp = 1.0 + S12overS11 * (ph.Q * c2 + ph.U * s2);
+    ++nrej;
+    if (Prand <= Pcomp) break;
+  }
+  return phi;
+}
+
+// Outcome of one scattering event: what the peel stage needs.
+struct ScatterOut {
+  int peel_kind;  // -1 none, else PEEL_STOKES / PEEL_NOSTOKES with the fields below (resonance) or dust
+  bool dust;
+  double xfreq_atom, ux, uy, uz;
+};
+
+// scatter_resonance_stokes (:331-486) / _nostokes (:660-827).  The peel-off call
+// sits between the frequency update and the Stokes/triad update in the reference
+// (:446 / :788): `peel` is invoked at exactly that point.
+template <class PeelFn>
+LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, PeelFn &&peel) {
+  ph.nsg += ph.wgt;
+  // do_resonance1 — line_mod.f90:108-139
+  double uz = rand_resonance_vz(r, ph.xfreq, cs.voigt_a, cnt.reject);
+  double xfreq_atom = ph.xfreq - uz;
+  double cost = rand_resonance(r, P.E1);
+  double sint = sqrt(1.0 - cost * cost);
+  double cost2 = cost * cost;
+  double S22 = 0.75 * P.E1 * (cost2 + 1.0), S11 = S22 + P.E2, S12 = 0.75 * P.E1 * (cost2 - 1.0);
+  double S33 = 1.5 * P.E1 * cost, S44 = 1.5 * P.E3 * cost;
+  double phi = P.use_stokes ? sample_phi_stokes(r, ph, S12 / S11, cnt.reject) : kTwoPi * r.uniform();
+  double cosp, sinp;
+  sincos(phi, &sinp, &cosp);
+  double xc = 0.0, xc2 = 0.0;
+  if (P.core_skip) car_xcrit_local(P, ph.ic, ph.jc, ph.kc, ph.x, ph.y, ph.z, cs.voigt_a, cs.rhokap, xc, xc2);
+  bool skip = P.core_skip && fabs(ph.xfreq) < xc;
+  double ux, uy;
+  if (P.use_stokes && !skip) {  // :413-414
+    const double one_over_sqrt2 = 1.0 / 1.4142135623730951;
+    ux = r.gauss(cnt.reject) * one_over_sqrt2;
+    uy = r.gauss(cnt.reject) * one_over_sqrt2;
+  } else {  // :397-401 / :749-752
+    double phi2 = kTwoPi * r.uniform();
+    double uxy = skip ? sqrt(xc2 - log(r.uniform())) : sqrt(-log(r.uniform()));
+    double s2, c2;
+    sincos(phi2, &s2, &c2);
+    ux = uxy * c2; uy = uxy * s2;
+  }
+  ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
+  if (P.recoil) ph.xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
+  if (P.save_peeloff) peel(xfreq_atom, ux, uy, uz);
+  if (P.use_stokes) {
+    double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
+    double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+    double I1 = S11 + S12 * Q0, Q1 = S12 + S22 * Q0, U1 = S33 * U0, V1 = S44 * ph.V;
+    ph.Q = Q1 / I1; ph.U = U1 / I1; ph.V = V1 / I1;
+    rotate_triad(ph, cost, sint, cosp, sinp);
+  } else {
+    rotate_k(ph, cost, sint, cosp, sinp);
+  }
+}
+
+// dust absorption / weight reduction — scattering_car.f90:219-264 / :506-555
+LART_DEV bool dust_absorb(const DevParams &P, Photon &ph, Rng &r, const CellData &cs) {
+  double xref = (ph.xfreq + vdotk(cs, ph.kx, ph.ky, ph.kz)) * (cs.Dfreq / P.Dfreq_ref);
+  int ix = freq_bin(P, xref);
+  bool inb = ix >= 1 && ix <= P.nxfreq;
+  if (!P.use_reduced_wgt) {
+    if (r.uniform() > P.albedo) {
+      if (P.save_Jabs && inb) tally_add(P.tally + P.lay.Jabs + ix - 1, ph.wgt);
+      ph.flags &= ~PH_ALIVE;
+      if (P.save_all_photons) { ph.xfreq_ref = xref; ph.wgt = 0.0; }
+      return false;
+    }
+  } else {
+    if (P.save_Jabs && inb) tally_add(P.tally + P.lay.Jabs + ix - 1, ph.wgt * (1.0 - P.albedo));
+    ph.wgt = ph.wgt * P.albedo;
+  }
+  return true;
+}
+
+// scatter_dust_stokes (:201-329) / _nostokes (:488-584); `peel` is invoked where
+// the reference calls peeling_dust_* (after absorption, before the new direction).
+template <class PeelFn>
+LART_DEV void scatter_dust(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, PeelFn &&peel) {
+  ph.nsd += ph.wgt;
+  if (!dust_absorb(P, ph, r, cs)) return;
+  if (P.save_peeloff) peel();
+  if (P.use_stokes) {
+    double cost = rand_alias_linear(r, P);
+    double sint = sqrt(1.0 - cost * cost);
+    double S11 = interp_eq(P.sm_coss, P.sm_S11, P.nPDF, cost), S12 = interp_eq(P.sm_coss, P.sm_S12, P.nPDF, cost);
+    double S33 = interp_eq(P.sm_coss, P.sm_S33, P.nPDF, cost), S34 = interp_eq(P.sm_coss, P.sm_S34, P.nPDF, cost);
+    double phi = sample_phi_stokes(r, ph, S12 / S11, cnt.reject);
+    double cosp, sinp;
+    sincos(phi, &sinp, &cosp);
+    double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
+    double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+    double I1 = S11 + S12 * Q0, Q1 = S12 + S11 * Q0, U1 = S33 * U0 + S34 * ph.V, V1 = -S34 * U0 + S33 * ph.V;
+    ph.Q = Q1 / I1; ph.U = U1 / I1; ph.V = V1 / I1;
+    rotate_triad(ph, cost, sint, cosp, sinp);
+  } else {
+    double cost = rand_hg(r, P.hgg);
+    double sint = sqrt(1.0 - cost * cost);
+    double phi = kTwoPi * r.uniform();
+    double cosp, sinp;
+    sincos(phi, &sinp, &cosp);
+    rotate_k(ph, cost, sint, cosp, sinp);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// generate_photon + setup_isotropic_injection — generate_photon.f90:3-339, 342-408
+// (everything up to, not including, the direct peel-off call at :334-336)
+// ---------------------------------------------------------------------------
+LART_DEV void generate_photon(const DevParams &P, Photon &ph, Rng &r, Counters &cnt, CellData &cs) {
+  if (P.source_geometry == 2) {  // uniform_sphere :34-42
+    double rp = cbrt(r.uniform()) * P.source_rmax;
+    double cost = 2.0 * r.uniform() - 1.0, sint = sqrt(1.0 - cost * cost), phi = kTwoPi * r.uniform();
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    ph.x = rp * sint * cp; ph.y = rp * sint * sp; ph.z = rp * cost;
+  } else if (P.source_geometry == 1) {  // uniform :50-54
+    ph.x = (P.xmax - P.xmin) * r.uniform() + P.xmin;
+    ph.y = (P.ymax - P.ymin) * r.uniform() + P.ymin;
+    ph.z = (P.zmax - P.zmin) * r.uniform() + P.zmin;
+  } else {  // point :126-131
+    ph.x = P.xs; ph.y = P.ys; ph.z = P.zs;
+  }
+  ph.wgt = 1.0;
+  double cost = 2.0 * r.uniform() - 1.0;
+  double sint = sqrt(1.0 - cost * cost);
+  double phi = kTwoPi * r.uniform();
+  double cosp, sinp;
+  sincos(phi, &sinp, &cosp);
+  ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
+  ph.ic = (int)floor((ph.x - P.xmin) / P.dx) + 1;
+  ph.jc = (int)floor((ph.y - P.ymin) / P.dy) + 1;
+  ph.kc = (int)floor((ph.z - P.zmin) / P.dz) + 1;
+  if (ph.kx < 0.0 && ph.ic == P.nx + 1) ph.ic = P.nx;
+  if (ph.ky < 0.0 && ph.jc == P.ny + 1) ph.jc = P.ny;
+  if (ph.kz < 0.0 && ph.kc == P.nz + 1) ph.kc = P.nz;
+  if (ph.kx > 0.0 && ph.ic < 1) ph.ic = 1;
+  if (ph.ky > 0.0 && ph.jc < 1) ph.jc = 1;
+  if (ph.kz > 0.0 && ph.kc < 1) ph.kc = 1;
+  ph.mx = cost * cosp; ph.my = cost * sinp; ph.mz = -sint;
+  ph.nx = -sinp; ph.ny = cosp; ph.nz = 0.0;
+  ph.Q = 0.0; ph.U = 0.0; ph.V = 0.0;
+  ph.nsg = 0.0; ph.nsd = 0.0; ph.xfreq_ref = 0.0;
+  ph.flags = PH_ALIVE | PH_FIRST;
+  ph.xfreq = P.xfreq0;
+  // a source placed on the upper boundary with k>0 keeps index n+1 in the reference and
+  // reads out of bounds there; clamp the READ only (the photon leaves at its first trace)
+  int ci = min(max(ph.ic, 1), P.nx), cj = min(max(ph.jc, 1), P.ny), ck = min(max(ph.kc, 1), P.nz);
+  load_cell(P, cell_index(P, ci, cj, ck), cs);
+  switch (P.spectral_type) {  // :243-300
+    case 3: ph.xfreq = r.uniform() * (P.xfreq_max - P.xfreq_min) + P.xfreq_min; ph.xfreq = ph.xfreq / (cs.Dfreq / P.Dfreq_ref); break;
+    case 2: ph.xfreq = ph.xfreq + rand_voigt(r, P.voigt_a0, cnt.reject) * P.Dfreq0 / cs.Dfreq; break;
+    case 1: ph.xfreq = ph.xfreq + rand_voigt(r, cs.voigt_a, cnt.reject); break;
+    case 4: ph.xfreq = ph.xfreq + r.gauss(cnt.reject) * P.gaussian_sigma_x; ph.xfreq = ph.xfreq / (cs.Dfreq / P.Dfreq_ref); break;
+    default: break;
+  }
+  double u1 = vdotk(cs, ph.kx, ph.ky, ph.kz);
+  if (!P.comoving_source) ph.xfreq = ph.xfreq - u1;  // :303-306
+  if (P.save_Jin) {  // :309-322
+    double xlab = (ph.xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
+    int ix = freq_bin(P, xlab);
+    if (ix >= 1 && ix <= P.nxfreq) tally_add(P.tally + P.lay.Jin + ix - 1, ph.wgt);
+  }
+}
+
+// impact radius of the photon's line about the origin — run_simulation_mod.f90:302-330
+LART_DEV double impact_radius(const DevParams &P, const Photon &ph, double &mx, double &my, double &mz) {
+  double xp = ph.x, yp = ph.y, zp = ph.z;
+  if (P.rmax > 0.0) {
+    double rr = ph.x * ph.x + ph.y * ph.y + ph.z * ph.z, dist = 0.0;
+    if (rr > P.rmax * P.rmax) {
+      double rk = ph.x * ph.kx + ph.y * ph.ky + ph.z * ph.kz;
+      double det = rk * rk - (rr - P.rmax * P.rmax);
+      dist = (det < 0.0) ? 0.0 : -rk + sqrt(fmax(0.0, det));
+    }
+    xp = ph.x + dist * ph.kx; yp = ph.y + dist * ph.ky; zp = ph.z + dist * ph.kz;
+  }
+  double rk = xp * ph.kx + yp * ph.ky + zp * ph.kz;
+  mx = xp - rk * ph.kx; my = yp - rk * ph.ky; mz = zp - rk * ph.kz;
+  return sqrt(mx * mx + my * my + mz * mz);
+}
+// make_all_initial_photons / make_all_photons — run_simulation_mod.f90:249-358
+LART_DEV void record_initial(const DevParams &P, const Photon &ph) {
+  size_t s = (size_t)(ph.id - 1);
+  if (ph.id < 1 || ph.id > P.nphotons) return;
+  if (P.allph[A_XFREQ1]) P.allph[A_XFREQ1][s] = ph.xfreq;
+  if (P.source_geometry != 0 && P.allph[A_RP0]) {
+    double mx, my, mz;
+    P.allph[A_RP0][s] = impact_radius(P, ph, mx, my, mz);
+  }
+}
+LART_DEV void record_final(const DevParams &P, const Photon &ph) {
+  if (ph.id < 1 || ph.id > P.nphotons) return;
+  size_t s = (size_t)(ph.id - 1);
+  double mx, my, mz;
+  double mm = impact_radius(P, ph, mx, my, mz);
+  if (P.allph[A_RP]) P.allph[A_RP][s] = mm;
+  if (P.allph[A_XFREQ2]) P.allph[A_XFREQ2][s] = ph.xfreq_ref;
+  if (P.allph[A_NSG]) P.allph[A_NSG][s] = ph.nsg;
+  if (P.allph[A_NSD]) P.allph[A_NSD][s] = ph.nsd;
+  if (P.use_stokes) {
+    double cos2p = 1.0, sin2p = 0.0;
+    if (mm > 0.0) {
+      mx /= mm; my /= mm; mz /= mm;
+      double cosp = mx * ph.mx + my * ph.my + mz * ph.mz, sinp = mx * ph.nx + my * ph.ny + mz * ph.nz;
+      cos2p = 2.0 * cosp * cosp - 1.0; sin2p = 2.0 * sinp * cosp;
+    }
+    if (P.allph[A_I]) P.allph[A_I][s] = ph.wgt;
+    if (P.allph[A_Q]) P.allph[A_Q][s] = (cos2p * ph.Q + sin2p * ph.U) * ph.wgt;
+    if (P.allph[A_U]) P.allph[A_U][s] = (-sin2p * ph.Q + cos2p * ph.U) * ph.wgt;
+    if (P.allph[A_V]) P.allph[A_V][s] = ph.V * ph.wgt;
+  }
+}
+
+}  // namespace lart

@@ -1,0 +1,1328 @@
+// lart_engine.cu — the CUDA engine behind include/lart_gpu.h (sm_100a).
+//
+// Two drivers of the same device physics (lart_device.cuh):
+//
+//  * WAVEFRONT (default).  The photon pool is SoA in HBM; one "wave" advances every
+//    live photon by one scattering through four stage kernels whose work lists are
+//    stream-compacted on the device:
+//       emit    dead slots pull photon ids from the job queue (generate_photon +
+//               peeling_direct ray descriptors)
+//       trace   raytrace_to_tau for every live photon (forced first scattering
+//               included); escapes are tallied and retire their slot, the rest are
+//               appended to the scatter list
+//       scatter frequency redistribution + phase function + Stokes update; one
+//               peel-ray descriptor per observer is appended to the ray queue
+//       peel    raytrace_to_edge for every queued ray, exp(-tau) deposit with
+//               warp-aggregated atomics
+//    trace and peel are persistent kernels with per-lane refill: a lane whose ray
+//    ended pulls the next work item while its neighbours keep stepping, so a warp
+//    always executes the same DDA step body.
+//  * MONOLITHIC (LART_FLAG_MONOLITHIC).  One thread owns one photon slot and runs
+//    trace -> scatter -> peel back to back for `quantum` events.  Kept as the
+//    "before compaction" baseline for the warp-efficiency evidence, and as a second
+//    implementation the parity tests cross-check.
+//
+// Photon physics is independent of the scheduling: every photon has its own Philox
+// stream (seed, photon id) and its draw counter travels with the photon, so both
+// drivers — and the CPU oracle in Philox mode — produce the same photon histories.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lart_gpu.h"
+#include "lart_device.cuh"
+#include "voigt_tables.cuh"
+
+
+using namespace lart;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string &msg) {
+  g_err = msg;
+  return 1;
+}
+#define CUDA_OK(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+constexpr int kVoigtTabN = 202 * 4;
+constexpr int kBlock = 256;
+
+// ------------------------------- photon pool -------------------------------
+enum {
+  F_X, F_Y, F_Z, F_KX, F_KY, F_KZ, F_MX, F_MY, F_MZ, F_NX, F_NY, F_NZ,
+  F_XFREQ, F_XREF, F_WGT, F_Q, F_U, F_V, F_NSG, F_NSD, F_GSET, F_COUNT
+};
+struct Pool {
+  double *f;                   // [F_COUNT][S]
+  long long *id;               // [S]
+  unsigned long long *ndraw;   // [S]
+  int *ic, *jc, *kc, *flags;   // [S]
+  int S;
+};
+struct Job {  // photon ids = first_id + j*stride, j in [0,count)
+  unsigned long long next, count, done;
+  long long first_id, stride;
+};
+struct Queues {
+  PeelRay *rays;      // [ray_cap]: S*nobs slot rays, then the direct rays of this wave's emits
+  unsigned int *n_direct, *head_trace, *head_peel;
+  unsigned int direct_base, ray_cap;
+};
+
+__device__ __forceinline__ void load_trace_part(const Pool &pl, int s, Photon &ph) {
+  const double *f = pl.f;
+  size_t S = pl.S;
+  ph.x = f[F_X * S + s]; ph.y = f[F_Y * S + s]; ph.z = f[F_Z * S + s];
+  ph.kx = f[F_KX * S + s]; ph.ky = f[F_KY * S + s]; ph.kz = f[F_KZ * S + s];
+  ph.xfreq = f[F_XFREQ * S + s]; ph.wgt = f[F_WGT * S + s];
+  ph.id = pl.id[s]; ph.ic = pl.ic[s]; ph.jc = pl.jc[s]; ph.kc = pl.kc[s]; ph.flags = pl.flags[s];
+}
+__device__ __forceinline__ void load_rest(const Pool &pl, int s, Photon &ph) {
+  const double *f = pl.f;
+  size_t S = pl.S;
+  ph.mx = f[F_MX * S + s]; ph.my = f[F_MY * S + s]; ph.mz = f[F_MZ * S + s];
+  ph.nx = f[F_NX * S + s]; ph.ny = f[F_NY * S + s]; ph.nz = f[F_NZ * S + s];
+  ph.xfreq_ref = f[F_XREF * S + s]; ph.Q = f[F_Q * S + s]; ph.U = f[F_U * S + s]; ph.V = f[F_V * S + s];
+  ph.nsg = f[F_NSG * S + s]; ph.nsd = f[F_NSD * S + s];
+}
+__device__ __forceinline__ void store_trace_part(const Pool &pl, int s, const Photon &ph) {
+  double *f = pl.f;
+  size_t S = pl.S;
+  f[F_X * S + s] = ph.x; f[F_Y * S + s] = ph.y; f[F_Z * S + s] = ph.z;
+  f[F_XFREQ * S + s] = ph.xfreq; f[F_WGT * S + s] = ph.wgt;
+  pl.ic[s] = ph.ic; pl.jc[s] = ph.jc; pl.kc[s] = ph.kc; pl.flags[s] = ph.flags;
+}
+__device__ __forceinline__ void store_all(const Pool &pl, int s, const Photon &ph) {
+  double *f = pl.f;
+  size_t S = pl.S;
+  store_trace_part(pl, s, ph);
+  f[F_KX * S + s] = ph.kx; f[F_KY * S + s] = ph.ky; f[F_KZ * S + s] = ph.kz;
+  f[F_MX * S + s] = ph.mx; f[F_MY * S + s] = ph.my; f[F_MZ * S + s] = ph.mz;
+  f[F_NX * S + s] = ph.nx; f[F_NY * S + s] = ph.ny; f[F_NZ * S + s] = ph.nz;
+  f[F_XREF * S + s] = ph.xfreq_ref; f[F_Q * S + s] = ph.Q; f[F_U * S + s] = ph.U; f[F_V * S + s] = ph.V;
+  f[F_NSG * S + s] = ph.nsg; f[F_NSD * S + s] = ph.nsd;
+  pl.id[s] = ph.id;
+}
+__device__ __forceinline__ void load_rng(const DevParams &P, const Pool &pl, int s, long long id, int flags, Rng &r) {
+  r.start(P.seed, (unsigned long long)id, pl.ndraw[s]);
+  if (flags & PH_GAUSS) { r.gauss_stored = true; r.gset = pl.f[(size_t)F_GSET * pl.S + s]; }
+}
+__device__ __forceinline__ void store_rng(const Pool &pl, int s, const Rng &r, int &flags) {
+  pl.ndraw[s] = r.ndraw;
+  if (r.gauss_stored) { flags |= PH_GAUSS; pl.f[(size_t)F_GSET * pl.S + s] = r.gset; }
+  else flags &= ~PH_GAUSS;
+}
+
+__device__ __forceinline__ void load_vtab(const DevParams &P, double *vtab) {
+  for (int i = threadIdx.x; i < kVoigtTabN; i += blockDim.x) vtab[i] = P.voigt_tab[i];
+  __syncthreads();
+}
+
+// warp-reduce the work counters and add them to the tally buffer (as doubles)
+__device__ void flush_counters(const DevParams &P, Counters &c, unsigned long long nrng) {
+  c.rng += nrng;
+  unsigned long long v[6] = {c.photons, c.scatter, c.cellsteps, c.peel, c.rng, c.reject};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    unsigned long long x = v[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(P.tally + P.lay.counters + q, (double)x);
+  }
+}
+
+// full walks (monolithic driver, batch API)
+__device__ __forceinline__ double walk_edge(const DevParams &P, const double *vtab, double x, double y, double z,
+                                            double kx, double ky, double kz, int ic, int jc, int kc, double xfreq,
+                                            int &nsteps, int trace_cap = 0, int *trace = nullptr) {
+  Ray r;
+  nsteps = 0;
+  if (ray_setup(P, r, x, y, z, kx, ky, kz, ic, jc, kc, xfreq, false)) return 0.0;
+  for (;;) {
+    if (trace && r.nsteps < trace_cap) trace[r.nsteps] = (int)cell_index(P, r.ic, r.jc, r.kc);
+    if (edge_step(P, vtab, r)) break;
+  }
+  nsteps = r.nsteps;
+  return r.tau;
+}
+
+// raytrace_to_tau on a photon; returns the number of cell steps.  On escape the
+// photon is flagged dead and carries the lab-frame xfreq_ref (raytrace_car.f90:1598-1623);
+// the Jout tally is the caller's.
+__device__ __forceinline__ int finish_escape(const DevParams &P, Photon &ph, const Ray &r) {
+  ph.flags &= ~PH_ALIVE;
+  ph.xfreq = DADD(r.xfreq, r.u1);
+  ph.xfreq_ref = DMUL(ph.xfreq, r.cell.Dfreq / P.Dfreq_ref);
+  ph.x = r.x0; ph.y = r.y0; ph.z = r.z0;
+  if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
+  ph.kc = r.kc;
+  return r.nsteps;
+}
+__device__ __forceinline__ int walk_tau(const DevParams &P, const double *vtab, Photon &ph, double tau_in, CellData &cs) {
+  Ray r;
+  if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
+    ph.flags &= ~PH_ALIVE;  // raytrace_car.f90:1469-1472: returns before any update
+    return -1;
+  }
+  for (;;) {
+    double xp, yp, zp;
+    int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
+    if (st == 1) {
+      ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
+      if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
+      ph.kc = r.kc;
+      cs = r.cell;
+      return r.nsteps;
+    }
+    if (st == 2) return finish_escape(P, ph, r);
+  }
+}
+
+// photon left the system: Jout (if it was walked), allph record, per-run sums
+__device__ __forceinline__ void retire_photon(const DevParams &P, const Photon &ph, bool tally_jout, Job *job, Counters &cnt) {
+  if (tally_jout) tally_Jout(P, ph.xfreq_ref, ph.kz, ph.wgt);
+  if (ph.nsg != 0.0) atomicAdd(P.tally + P.lay.scalars + 0, ph.nsg);
+  if (ph.nsd != 0.0) atomicAdd(P.tally + P.lay.scalars + 1, ph.nsd);
+  if (P.save_all_photons) record_final(P, ph);
+  atomicAdd(&job->done, 1ULL);
+  cnt.photons += 1;
+}
+
+// add_escaped_fraction_to_Jout + weight/tau of the forced first scattering —
+// run_simulation_mod.f90:163-177, 208-247.  cs = record of the photon's cell.
+__device__ __forceinline__ double forced_first(const DevParams &P, Photon &ph, Rng &rng, const CellData &cs, double tau0) {
+  double wgt_esc = ph.wgt * exp(-tau0);
+  double xref = (ph.xfreq + vdotk(cs, ph.kx, ph.ky, ph.kz)) * (cs.Dfreq / P.Dfreq_ref);
+  tally_Jout(P, xref, ph.kz, wgt_esc);
+  double wgt1 = 1.0 - exp(-tau0);
+  ph.wgt = ph.wgt * wgt1;
+  ph.flags &= ~PH_FIRST;
+  return (tau0 > 0.0) ? -log(1.0 - rng.uniform() * wgt1) : kHugest;
+}
+
+__device__ __forceinline__ void clamp_cell_for_read(const DevParams &P, const Photon &ph, int &ci, int &cj, int &ck) {
+  ci = min(max(ph.ic, 1), P.nx); cj = min(max(ph.jc, 1), P.ny); ck = min(max(ph.kc, 1), P.nz);
+}
+
+// ------------------------------ monolithic driver ---------------------------
+__global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevParams P, Pool pl, Job *job, int quantum) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  Counters cnt;
+  unsigned long long nrng = 0;
+  if (s < pl.S) {
+    Photon ph;
+    Rng rng;
+    ph.flags = pl.flags[s];
+    bool rng_valid = false, touched = false;
+    if (ph.flags & PH_ALIVE) {
+      load_trace_part(pl, s, ph);
+      load_rest(pl, s, ph);
+      load_rng(P, pl, s, ph.id, ph.flags, rng);
+      rng_valid = true;
+    }
+    for (int ev = 0; ev < quantum; ++ev) {
+      CellData cs;
+      if (!(ph.flags & PH_ALIVE)) {
+        if (job->next >= job->count) break;
+        unsigned long long j = atomicAdd(&job->next, 1ULL);
+        if (j >= job->count) break;
+        touched = true;
+        ph.id = job->first_id + (long long)j * job->stride;
+        if (rng_valid) nrng += rng.nrng;  // draws of the previous photon in this slot
+        rng.start(P.seed, (unsigned long long)ph.id);
+        rng_valid = true;
+        generate_photon(P, ph, rng, cnt, cs);
+        if (P.save_all_photons) record_initial(P, ph);
+        if (P.save_peeloff) {  // peeling_direct — generate_photon.f90:334-336
+          for (int i = 0; i < P.nobs; ++i) {
+            PeelRay pr;
+            if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
+            int ns;
+            double tau = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns);
+            cnt.cellsteps += ns; cnt.peel += 1;
+            peel_deposit(P, pr, tau, __activemask());
+          }
+        }
+      }
+      touched = true;
+      double tau;
+      if (ph.flags & PH_FIRST) {
+        int ci, cj, ck, ns;
+        clamp_cell_for_read(P, ph, ci, cj, ck);
+        load_cell(P, cell_index(P, ci, cj, ck), cs);
+        double tau0 = walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, ns);
+        cnt.cellsteps += ns;
+        tau = forced_first(P, ph, rng, cs, tau0);
+      } else {
+        tau = -log(rng.uniform());
+      }
+      int ns = walk_tau(P, vtab, ph, tau, cs);
+      if (ns > 0) cnt.cellsteps += ns;
+      if (!(ph.flags & PH_ALIVE)) {
+        retire_photon(P, ph, ns >= 0, job, cnt);
+        continue;
+      }
+      // scattering — scattering_car.f90:14-120
+      cnt.scatter += 1;
+      bool to_dust = false;
+      if (P.dust) {
+        double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
+        to_dust = rng.uniform() <= pd;
+      }
+      auto trace_and_deposit = [&](PeelRay &pr) {
+        int ns2;
+        double t = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns2);
+        cnt.cellsteps += ns2; cnt.peel += 1;
+        peel_deposit(P, pr, t, __activemask());
+      };
+      if (to_dust) {
+        scatter_dust(P, ph, rng, cs, cnt, [&]() {
+          for (int i = 0; i < P.nobs; ++i) {
+            PeelRay pr;
+            bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[i], i, ph, cs, pr)
+                                   : peel_dust_nostokes_prepare(P, P.obs[i], i, ph, cs, pr);
+            if (ok) trace_and_deposit(pr);
+          }
+        });
+        if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
+      } else {
+        scatter_resonance(P, ph, rng, cs, cnt, [&](double xa, double ux, double uy, double uz) {
+          for (int i = 0; i < P.nobs; ++i) {
+            PeelRay pr;
+            bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[i], i, ph, cs, xa, ux, uy, uz, pr)
+                                   : peel_resonance_nostokes_prepare(P, P.obs[i], i, ph, cs, xa, ux, uy, uz, pr);
+            if (ok) trace_and_deposit(pr);
+          }
+        });
+      }
+    }
+    if (touched) {
+      int fl = ph.flags;
+      if (fl & PH_ALIVE) store_rng(pl, s, rng, fl);
+      ph.flags = fl;
+      store_all(pl, s, ph);
+    }
+    if (rng_valid) nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// ------------------------------ wavefront driver ----------------------------
+// Work items are pool slots (trace, scatter) and ray-queue entries (peel); the ray
+// of slot s toward observer k lives at rays[s*nobs + k] (kind = -1: no ray this
+// wave), direct-peel rays of freshly emitted photons are appended behind them.
+constexpr int kRefillMin = 8;  // refill a warp when at least this many lanes are idle
+
+// warp-aggregated reservation from a converged point: lanes with `want` get
+// consecutive indices (one atomic per warp)
+__device__ __forceinline__ unsigned reserve(unsigned int *ctr, bool want) {
+  unsigned m = __ballot_sync(0xffffffffu, want);
+  int lane = threadIdx.x & 31;
+  unsigned base = 0;
+  if (m) {
+    int lead = __ffs(m) - 1;
+    if (lane == lead) base = atomicAdd(ctr, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, lead);
+  }
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// stage 1: refill dead slots from the job queue
+__global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+  Counters cnt;
+  unsigned long long nrng = 0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < pl.S; s += gridDim.x * blockDim.x) {
+    if (pl.flags[s] & PH_ALIVE) continue;
+    if (job->next >= job->count) continue;
+    unsigned long long j = atomicAdd(&job->next, 1ULL);
+    if (j >= job->count) continue;
+    Photon ph;
+    Rng rng;
+    CellData cs;
+    ph.id = job->first_id + (long long)j * job->stride;
+    rng.start(P.seed, (unsigned long long)ph.id);
+    generate_photon(P, ph, rng, cnt, cs);
+    if (P.save_all_photons) record_initial(P, ph);
+    if (P.save_peeloff) {
+      for (int i = 0; i < P.nobs; ++i) {
+        PeelRay pr;
+        if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
+        unsigned at = q.direct_base + atomicAdd(q.n_direct, 1u);
+        if (at < q.ray_cap) q.rays[at] = pr;
+      }
+    }
+    int fl = ph.flags;
+    store_rng(pl, s, rng, fl);
+    ph.flags = fl;
+    store_all(pl, s, ph);
+    nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// stage 2: raytrace_to_tau for every live photon, per-lane refill
+__global__ void __launch_bounds__(kBlock) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  const unsigned FULL = 0xffffffffu;
+  Counters cnt;
+  unsigned long long nrng = 0;
+  Ray r;
+  Photon ph;
+  Rng rng;
+  double tau_in = 0.0;
+  int slot = -1, mode = 0;  // mode 0: forced-first edge walk, 1: tau walk
+  bool have = false, exhausted = false;
+  CellData cs0;  // start cell of a first-flight photon
+  for (;;) {
+    // ---- refill idle lanes (converged point)
+    bool need = !have && !exhausted;
+    unsigned nm = __ballot_sync(FULL, need), hm = __ballot_sync(FULL, have);
+    if (nm && (__popc(nm) >= kRefillMin || !hm)) {
+      unsigned idx = reserve(q.head_trace, need);
+      if (need) {
+        if (idx >= (unsigned)pl.S) exhausted = true;
+        else if (pl.flags[idx] & PH_ALIVE) {
+          slot = (int)idx;
+          load_trace_part(pl, slot, ph);
+          load_rng(P, pl, slot, ph.id, ph.flags, rng);
+          bool leaving;
+          if (ph.flags & PH_FIRST) {
+            int ci, cj, ck;
+            clamp_cell_for_read(P, ph, ci, cj, ck);
+            load_cell(P, cell_index(P, ci, cj, ck), cs0);
+            mode = 0;
+            leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, false);
+            if (leaving) {  // tau0 = 0 (raytrace_to_edge returns at once)
+              tau_in = forced_first(P, ph, rng, cs0, 0.0);
+              mode = 1;
+            }
+          } else {
+            tau_in = -log(rng.uniform());
+            mode = 1;
+            leaving = true;
+          }
+          if (mode == 1 && leaving)
+            leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true);
+          if (leaving) {  // dead without tally (raytrace_car.f90:1469-1472)
+            ph.flags &= ~PH_ALIVE;
+            load_rest(pl, slot, ph);
+            retire_photon(P, ph, false, job, cnt);
+            pl.flags[slot] = ph.flags;
+            nrng += rng.nrng;
+          } else {
+            have = true;
+          }
+        }
+      }
+    }
+    if (!__any_sync(FULL, have)) {
+      if (!__any_sync(FULL, !exhausted)) break;
+      continue;
+    }
+    // ---- one cell step for every lane that has a ray
+    if (have) {
+      if (mode == 0) {
+        if (edge_step(P, vtab, r)) {
+          cnt.cellsteps += r.nsteps;
+          tau_in = forced_first(P, ph, rng, cs0, r.tau);
+          mode = 1;
+          if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
+            ph.flags &= ~PH_ALIVE;
+            load_rest(pl, slot, ph);
+            retire_photon(P, ph, false, job, cnt);
+            store_trace_part(pl, slot, ph);
+            nrng += rng.nrng;
+            have = false;
+          }
+        }
+      } else {
+        double xp, yp, zp;
+        int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
+        if (st == 1) {
+          ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
+          if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
+          ph.kc = r.kc;
+          ph.flags |= PH_SCATTER;
+          cnt.cellsteps += r.nsteps;
+          store_trace_part(pl, slot, ph);
+          pl.ndraw[slot] = rng.ndraw;
+          nrng += rng.nrng;
+          have = false;
+        } else if (st == 2) {
+          cnt.cellsteps += finish_escape(P, ph, r);
+          load_rest(pl, slot, ph);
+          retire_photon(P, ph, true, job, cnt);
+          store_trace_part(pl, slot, ph);
+          nrng += rng.nrng;
+          have = false;
+        }
+      }
+    }
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// stage 3: scattering for every photon flagged by the trace stage; writes the
+// peel-ray descriptors of its slot
+__global__ void __launch_bounds__(kBlock) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+  __shared__ double vtab[kVoigtTabN];
+  if (P.dust) load_vtab(P, vtab);
+  Counters cnt;
+  unsigned long long nrng = 0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < pl.S; s += gridDim.x * blockDim.x) {
+    int fl0 = pl.flags[s];
+    PeelRay *myrays = q.rays + (size_t)s * P.nobs;
+    if (!(fl0 & PH_SCATTER)) {
+      for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+      continue;
+    }
+    Photon ph;
+    Rng rng;
+    load_trace_part(pl, s, ph);
+    load_rest(pl, s, ph);
+    ph.flags &= ~PH_SCATTER;
+    load_rng(P, pl, s, ph.id, ph.flags, rng);
+    CellData cs;
+    load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
+    cnt.scatter += 1;
+    bool to_dust = false;
+    if (P.dust) {
+      double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
+      to_dust = rng.uniform() <= pd;
+    }
+    bool peeled = false;
+    if (to_dust) {
+      scatter_dust(P, ph, rng, cs, cnt, [&]() {
+        peeled = true;
+        for (int k = 0; k < P.nobs; ++k) {
+          PeelRay pr;
+          bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[k], k, ph, cs, pr)
+                                 : peel_dust_nostokes_prepare(P, P.obs[k], k, ph, cs, pr);
+          if (ok) myrays[k] = pr; else myrays[k].kind = -1;
+        }
+      });
+      if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
+    } else {
+      scatter_resonance(P, ph, rng, cs, cnt, [&](double xa, double ux, double uy, double uz) {
+        peeled = true;
+        for (int k = 0; k < P.nobs; ++k) {
+          PeelRay pr;
+          bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr)
+                                 : peel_resonance_nostokes_prepare(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr);
+          if (ok) myrays[k] = pr; else myrays[k].kind = -1;
+        }
+      });
+    }
+    if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+    int fl = ph.flags;
+    store_rng(pl, s, rng, fl);
+    ph.flags = fl;
+    store_all(pl, s, ph);
+    nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// stage 4: raytrace_to_edge for every queued peel ray, per-lane refill, deposit
+__global__ void __launch_bounds__(kBlock) k_wf_peel(const __grid_constant__ DevParams P, Queues q) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  const unsigned FULL = 0xffffffffu;
+  Counters cnt;
+  const unsigned n = min(q.direct_base + *q.n_direct, q.ray_cap);
+  Ray r;
+  unsigned mine = 0;
+  bool have = false, exhausted = false;
+  for (;;) {
+    bool zero_tau = false;
+    bool need = !have && !exhausted;
+    unsigned nm = __ballot_sync(FULL, need), hm = __ballot_sync(FULL, have);
+    if (nm && (__popc(nm) >= kRefillMin || !hm)) {
+      unsigned idx = reserve(q.head_peel, need);
+      if (need) {
+        if (idx >= n) exhausted = true;
+        else if (q.rays[idx].kind >= 0) {
+          mine = idx;
+          const PeelRay &pr = q.rays[idx];
+          cnt.peel += 1;
+          if (ray_setup(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
+          else have = true;
+        }
+      }
+    }
+    bool fin = zero_tau;
+    if (have && edge_step(P, vtab, r)) { fin = true; have = false; cnt.cellsteps += r.nsteps; }
+    unsigned fm = __ballot_sync(FULL, fin);
+    if (fin) peel_deposit(P, q.rays[mine], zero_tau ? 0.0 : r.tau, fm);
+    if (!__any_sync(FULL, have || !exhausted)) break;
+  }
+  flush_counters(P, cnt, 0);
+}
+
+__global__ void k_wf_reset(Queues q) {
+  *q.n_direct = 0; *q.head_trace = 0; *q.head_peel = 0;
+}
+
+// ------------------------------ set-up kernels ------------------------------
+__global__ void k_pack_cells(DevParams P, Cell *cells, size_t n) {
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+    Cell o;
+    o.rhokap = P.rhokap[c]; o.voigt_a = P.voigt_a[c]; o.Dfreq = P.Dfreq[c];
+    o.vfx = P.vfx[c]; o.vfy = P.vfy[c]; o.vfz = P.vfz[c];
+    o.rhokapD = P.dust ? P.rhokapD[c] : 0.0; o.pad = 0.0;
+    cells[c] = o;
+  }
+}
+__global__ void k_build_vtab(double *tab) {
+  for (int k = threadIdx.x; k < 202; k += blockDim.x) {
+    tab[4 * k + 0] = k < 101 ? c_voigt_h0[k] : 0.0;
+    tab[4 * k + 1] = c_voigt_h1[k];
+    tab[4 * k + 2] = k < 101 ? c_voigt_h2[k] : 0.0;
+    tab[4 * k + 3] = c_voigt_h3[k];
+  }
+}
+
+// ------------------------------ batch kernels -------------------------------
+__global__ void k_voigt_batch(const double *tab, long long n, const double *x, const double *a, double *H) {
+  __shared__ double vtab[kVoigtTabN];
+  for (int i = threadIdx.x; i < kVoigtTabN; i += blockDim.x) vtab[i] = tab[i];
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    H[i] = voigt_seon2(vtab, x[i], a[i]);
+}
+__global__ void k_edge_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
+                             const double *z, const double *kx, const double *ky, const double *kz, const double *xfreq,
+                             const int *ic, const int *jc, const int *kc, double *tau, int *nsteps, int trace_cap, int *trace) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int ns;
+    tau[i] = walk_edge(P, vtab, x[i], y[i], z[i], kx[i], ky[i], kz[i], ic[i], jc[i], kc[i], xfreq[i], ns, trace_cap,
+                       trace ? trace + i * trace_cap : nullptr);
+    if (nsteps) nsteps[i] = ns;
+  }
+}
+__global__ void k_tau_batch(const __grid_constant__ DevParams P, long long n, double *x, double *y, double *z,
+                            const double *kx, const double *ky, const double *kz, double *xfreq, int *ic, int *jc, int *kc,
+                            const double *tau_in, int *inside, double *xfreq_ref, int *nsteps) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    Photon ph;
+    ph.x = x[i]; ph.y = y[i]; ph.z = z[i]; ph.kx = kx[i]; ph.ky = ky[i]; ph.kz = kz[i];
+    ph.xfreq = xfreq[i]; ph.ic = ic[i]; ph.jc = jc[i]; ph.kc = kc[i]; ph.flags = PH_ALIVE; ph.xfreq_ref = 0.0;
+    CellData cs;
+    int ns = walk_tau(P, vtab, ph, tau_in[i], cs);
+    x[i] = ph.x; y[i] = ph.y; z[i] = ph.z; xfreq[i] = ph.xfreq; ic[i] = ph.ic; jc[i] = ph.jc; kc[i] = ph.kc;
+    inside[i] = (ph.flags & PH_ALIVE) ? 1 : 0;
+    if (xfreq_ref) xfreq_ref[i] = (ph.flags & PH_ALIVE) ? 0.0 : ph.xfreq_ref;
+    if (nsteps) nsteps[i] = ns < 0 ? 0 : ns;
+  }
+}
+__global__ void k_xcrit_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
+                              const double *z, const int *ic, const int *jc, const int *kc, double *out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double xc = 0.0, xc2 = 0.0;
+    if (P.core_skip_global) { xc = P.xcrit; }
+    else if (ic[i] >= 1 && jc[i] >= 1 && kc[i] >= 1) {
+      CellData cs;
+      load_cell(P, cell_index(P, ic[i], jc[i], kc[i]), cs);
+      car_xcrit_local(P, ic[i], jc[i], kc[i], x[i], y[i], z[i], cs.voigt_a, cs.rhokap, xc, xc2);
+    }
+    out[i] = xc;
+  }
+}
+__global__ void k_sample_batch(int kind, unsigned long long seed, long long n, const long long *ids, const double *p0,
+                               const double *p1, int ndraw, double *out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    Rng r;
+    r.start(seed, (unsigned long long)(ids ? ids[i] : i));
+    unsigned long long nrej = 0;
+    for (int j = 0; j < ndraw; ++j) {
+      double v;
+      switch (kind) {
+        case 0: v = r.uniform(); break;
+        case 1: v = r.gauss(nrej); break;
+        case 2: v = rand_resonance_vz(r, p0[i], p1[i], nrej); break;
+        case 3: v = rand_resonance(r, p0[i]); break;
+        case 4: v = rand_hg(r, p0[i]); break;
+        default: v = rand_voigt(r, p0[i], nrej); break;
+      }
+      out[i * ndraw + j] = v;
+    }
+  }
+}
+
+// register-resident DFMA loop: 16 independent chains per thread
+__global__ void k_dfma_peak(double *out, int iters, double a, double b) {
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = threadIdx.x * 1e-3 + q;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = fma(v[q], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) s += v[q];
+  if (s == 12345.678) *out = s;
+}
+
+// shared per-device Voigt table for the handle-less batch entry points
+std::mutex g_tab_mu;
+double *g_tab[64] = {nullptr};
+int device_vtab(int dev, double **out) {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  if (dev < 0 || dev >= 64) return fail("bad device ordinal");
+  if (!g_tab[dev]) {
+    CUDA_OK(cudaMalloc(&g_tab[dev], sizeof(double) * kVoigtTabN));
+    k_build_vtab<<<1, 256>>>(g_tab[dev]);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+  }
+  *out = g_tab[dev];
+  return 0;
+}
+
+template <class T>
+int upload(T **dst, const T *src, size_t n) {
+  *dst = nullptr;
+  if (!src || n == 0) return 0;
+  CUDA_OK(cudaMalloc(dst, n * sizeof(T)));
+  CUDA_OK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace
+
+struct lart_gpu_ctx {
+  int device = 0;
+  DevParams P{};
+  Pool pool{};
+  Queues q{};
+  Job *job = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<void *> owned;  // every device allocation
+  double *allph_buf = nullptr;
+  long long allph_n = 0;
+  int allph_slot[10];
+  int quantum = 0, flags = 0, nsm = 148, nobs = 0, nxim = 0, nyim = 0;
+  long long count = 0;
+  double kernel_ms = 0.0;
+  long long launches = 0;
+  bool begun = false;
+  std::vector<double> stage;  // host staging for fetch
+  std::vector<cudaEvent_t> tev;  // stage-timing events of one step
+  double stage_ms[LART_STAGE_COUNT] = {0, 0, 0, 0};
+  long long stage_n[LART_STAGE_COUNT] = {0, 0, 0, 0};
+};
+
+namespace {
+template <class T>
+int dalloc(lart_gpu_ctx *h, T **p, size_t n, bool zero = true) {
+  CUDA_OK(cudaMalloc(p, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CUDA_OK(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  h->owned.push_back(*p);
+  return 0;
+}
+template <class T>
+int dupload(lart_gpu_ctx *h, const T **dst, const T *src, size_t n) {
+  T *p = nullptr;
+  if (int rc = upload(&p, src, n)) return rc;
+  if (p) h->owned.push_back(p);
+  *dst = p;
+  return 0;
+}
+
+int validate(const lart_config *c) {
+  const lart_grid &g = c->grid;
+  const lart_params &p = c->par;
+  if (g.nx < 1 || g.ny < 1 || g.nz < 1 || g.nxfreq < 1) return fail("lart_gpu_create: grid dimensions must be >= 1");
+  if (!g.xface || !g.yface || !g.zface || !g.rhokap || !g.voigt_a || !g.Dfreq || !g.vfx || !g.vfy || !g.vfz)
+    return fail("lart_gpu_create: NULL grid array");
+  if (c->line.line_type != 1) return fail("lart_gpu_create: only line_type 1 (Ly-alpha singlet) is on the GPU path");
+  if (p.xy_periodic && !(g.nx == 1 && g.ny == 1))
+    return fail("lart_gpu_create: xy_periodic is supported only for the nx=ny=1 slab (setup.f90:957-965)");
+  if (p.DGR > 0.0 && !g.rhokapD) return fail("lart_gpu_create: DGR > 0 but rhokapD is NULL");
+  if (p.DGR > 0.0 && p.use_stokes && c->scatt_mat.nPDF < 2) return fail("lart_gpu_create: dust + Stokes needs scatt_mat");
+  if (p.nobs < 0 || p.nobs > LART_MAX_OBSERVERS) return fail("lart_gpu_create: nobs out of range");
+  if (p.save_peeloff && p.nobs > 0 && !c->observers) return fail("lart_gpu_create: observers is NULL");
+  if (p.save_Jmu && (p.nmu < 1 || !(p.dmu > 0.0))) return fail("lart_gpu_create: save_Jmu needs nmu >= 1 and dmu > 0");
+  if (!(g.dxfreq > 0.0)) return fail("lart_gpu_create: dxfreq must be > 0");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+const char *lart_gpu_last_error(void) { return g_err.c_str(); }
+int lart_gpu_version(void) { return 100; }
+
+int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
+  if (!cfg || !out) return fail("lart_gpu_create: NULL argument");
+  *out = nullptr;
+  if (int rc = validate(cfg)) return rc;
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("lart_gpu_create: no such CUDA device");
+  CUDA_OK(cudaSetDevice(cfg->device));
+  lart_gpu_ctx *h = new lart_gpu_ctx();
+  h->device = cfg->device;
+  auto bail = [&](int rc) { lart_gpu_destroy(h); return rc; };
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  h->nsm = prop.multiProcessorCount;
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&h->ev0));
+  CUDA_OK(cudaEventCreate(&h->ev1));
+  const lart_grid &g = cfg->grid;
+  const lart_params &p = cfg->par;
+  DevParams &P = h->P;
+  P.nx = g.nx; P.ny = g.ny; P.nz = g.nz; P.nxfreq = g.nxfreq;
+  P.dx = g.dx; P.dy = g.dy; P.dz = g.dz;
+  P.xmin = g.xmin; P.ymin = g.ymin; P.zmin = g.zmin; P.xmax = g.xmax; P.ymax = g.ymax; P.zmax = g.zmax;
+  P.Dfreq_ref = g.Dfreq_ref; P.xfreq_min = g.xfreq_min; P.xfreq_max = g.xfreq_max; P.dxfreq = g.dxfreq;
+  P.xcrit = g.xcrit; P.xcrit2 = g.xcrit2; P.rmax = g.rmax;
+  const size_t nc = (size_t)g.nx * g.ny * g.nz;
+  P.dust = p.DGR > 0.0 ? 1 : 0;
+  int rc = 0;
+  rc = rc ? rc : dupload(h, &P.xface, g.xface, g.nx + 1);
+  rc = rc ? rc : dupload(h, &P.yface, g.yface, g.ny + 1);
+  rc = rc ? rc : dupload(h, &P.zface, g.zface, g.nz + 1);
+  rc = rc ? rc : dupload(h, &P.rhokap, g.rhokap, nc);
+  rc = rc ? rc : dupload(h, &P.voigt_a, g.voigt_a, nc);
+  rc = rc ? rc : dupload(h, &P.Dfreq, g.Dfreq, nc);
+  rc = rc ? rc : dupload(h, &P.vfx, g.vfx, nc);
+  rc = rc ? rc : dupload(h, &P.vfy, g.vfy, nc);
+  rc = rc ? rc : dupload(h, &P.vfz, g.vfz, nc);
+  if (!rc && P.dust) rc = dupload(h, &P.rhokapD, g.rhokapD, nc);
+  if (rc) return bail(rc);
+  double *vt = nullptr;
+  if ((rc = dalloc(h, &vt, kVoigtTabN))) return bail(rc);
+  k_build_vtab<<<1, 256, 0, h->stream>>>(vt);
+  P.voigt_tab = vt;
+  P.soa = (cfg->flags & LART_FLAG_SOA_GRID) ? 1 : 0;
+  P.warp_agg = (cfg->flags & LART_FLAG_NO_WARP_AGG) ? 0 : 1;
+  if (!P.soa) {
+    Cell *cells = nullptr;
+    if ((rc = dalloc(h, &cells, nc, false))) return bail(rc);
+    k_pack_cells<<<h->nsm * 8, 256, 0, h->stream>>>(P, cells, nc);
+    P.cells = cells;
+  }
+  P.seed = p.seed; P.xfreq0 = p.xfreq0; P.xs = p.xs_point; P.ys = p.ys_point; P.zs = p.zs_point;
+  P.source_rmax = p.source_rmax; P.albedo = p.albedo; P.hgg = p.hgg; P.voigt_a0 = p.voigt_a0; P.Dfreq0 = p.Dfreq0;
+  P.gaussian_sigma_x = p.gaussian_sigma_x; P.mu_min = p.mu_min; P.dmu = p.dmu; P.nmu = p.nmu;
+  P.E1 = cfg->line.E1; P.E2 = cfg->line.E2; P.E3 = cfg->line.E3; P.g_recoil0 = cfg->line.g_recoil0;
+  P.spectral_type = p.spectral_type; P.source_geometry = p.source_geometry;
+  P.zonly = (p.xy_periodic && g.nx == 1 && g.ny == 1) ? 1 : 0;
+  P.comoving_source = p.comoving_source; P.recoil = p.recoil; P.core_skip = p.core_skip; P.core_skip_global = p.core_skip_global;
+  P.use_stokes = p.use_stokes; P.use_reduced_wgt = p.use_reduced_wgt;
+  P.save_Jin = p.save_Jin; P.save_Jabs = (p.save_Jabs && P.dust) ? 1 : 0; P.save_Jmu = p.save_Jmu;
+  P.nobs = (p.save_peeloff && (p.save_peeloff_2D || p.save_peeloff_3D)) ? p.nobs : 0;
+  P.save_peeloff = P.nobs > 0 ? 1 : 0;
+  P.save_peeloff_2D = P.save_peeloff && p.save_peeloff_2D; P.save_peeloff_3D = P.save_peeloff && p.save_peeloff_3D;
+  P.save_direc0 = p.save_direc0; P.save_all_photons = p.save_all_photons; P.nphotons = p.nphotons;
+  h->nobs = P.nobs;
+  if (P.nobs > 0) {
+    std::vector<DevObserver> ob(P.nobs);
+    for (int i = 0; i < P.nobs; ++i) {
+      const lart_observer &o = cfg->observers[i];
+      if (o.nxim != cfg->observers[0].nxim || o.nyim != cfg->observers[0].nyim || o.nxim < 1 || o.nyim < 1)
+        return bail(fail("lart_gpu_create: observers must share one positive image size (par%nxim, par%nyim)"));
+      ob[i].x = o.x; ob[i].y = o.y; ob[i].z = o.z;
+      for (int k = 0; k < 9; ++k) ob[i].R[k] = o.rmatrix[k];
+      ob[i].dxim = o.dxim; ob[i].dyim = o.dyim; ob[i].nxim = o.nxim; ob[i].nyim = o.nyim;
+    }
+    h->nxim = ob[0].nxim; h->nyim = ob[0].nyim;
+    if ((rc = dupload(h, &P.obs, ob.data(), ob.size()))) return bail(rc);
+  }
+  const lart_scatt_mat &sm = cfg->scatt_mat;
+  P.nPDF = (P.dust && P.use_stokes) ? sm.nPDF : 0;
+  if (P.nPDF > 0) {
+    rc = rc ? rc : dupload(h, &P.sm_coss, sm.coss, sm.nPDF);
+    rc = rc ? rc : dupload(h, &P.sm_S11, sm.S11, sm.nPDF);
+    rc = rc ? rc : dupload(h, &P.sm_S12, sm.S12, sm.nPDF);
+    rc = rc ? rc : dupload(h, &P.sm_S33, sm.S33, sm.nPDF);
+    rc = rc ? rc : dupload(h, &P.sm_S34, sm.S34, sm.nPDF);
+    rc = rc ? rc : dupload(h, &P.sm_pdf, sm.phase_PDF, sm.nPDF - 1);
+    rc = rc ? rc : dupload(h, &P.sm_alias, sm.alias, sm.nPDF - 1);
+    if (rc) return bail(rc);
+  }
+  // ---- tally layout: Jout|Jin|Jabs|Jmu|observer blocks|scalars|counters
+  TallyLayout &L = P.lay;
+  long long off = 0;
+  auto take = [&](bool on, long long n) { long long o = on ? off : -1; if (on) off += n; return o; };
+  L.Jout = take(true, g.nxfreq);
+  L.Jin = take(P.save_Jin, g.nxfreq);
+  L.Jabs = take(P.save_Jabs, g.nxfreq);
+  L.Jmu = take(P.save_Jmu, (long long)g.nxfreq * p.nmu);
+  L.obs_base = off;
+  {
+    long long n2 = (long long)h->nxim * h->nyim, n3 = n2 * g.nxfreq, o = 0;
+    bool on[7] = {true, true, P.save_direc0 != 0, P.use_stokes != 0, P.use_stokes != 0, P.use_stokes != 0, P.use_stokes != 0};
+    for (int k = 0; k < 7; ++k) { L.cube[k] = (P.save_peeloff_3D && on[k]) ? o : -1; if (L.cube[k] >= 0) o += n3; }
+    for (int k = 0; k < 7; ++k) { L.img[k] = (P.save_peeloff_2D && on[k]) ? o : -1; if (L.img[k] >= 0) o += n2; }
+    L.obs_stride = o;
+    off += o * P.nobs;
+  }
+  L.scalars = take(true, 2);
+  L.counters = take(true, 6);
+  L.total = off;
+  if ((rc = dalloc(h, &P.tally, (size_t)L.total))) return bail(rc);
+  // ---- allph: one slot per photon id
+  for (int k = 0; k < 10; ++k) { P.allph[k] = nullptr; h->allph_slot[k] = -1; }
+  if (P.save_all_photons && p.nphotons > 0) {
+    bool on[10] = {p.source_geometry != LART_SRC_POINT, true, true, true, true, true,
+                   P.use_stokes != 0, P.use_stokes != 0, P.use_stokes != 0, P.use_stokes != 0};
+    int n = 0;
+    for (int k = 0; k < 10; ++k) if (on[k]) h->allph_slot[k] = n++;
+    h->allph_n = (long long)n * p.nphotons;
+    if ((rc = dalloc(h, &h->allph_buf, (size_t)h->allph_n))) return bail(rc);
+    for (int k = 0; k < 10; ++k) if (on[k]) P.allph[k] = h->allph_buf + (long long)h->allph_slot[k] * p.nphotons;
+  }
+  // ---- photon pool
+  h->flags = cfg->flags;
+  const bool mono = (cfg->flags & LART_FLAG_MONOLITHIC) != 0;
+  int S = cfg->pool_slots;
+  if (S <= 0) S = mono ? h->nsm * 2048 : h->nsm * 8192;
+  {
+    // keep the ray queue below ~3 GB when many observers are configured
+    long long per_slot = (long long)sizeof(PeelRay) * std::max(1, P.nobs);
+    long long cap = (3LL << 30) / per_slot;
+    if (S > cap) S = (int)std::max<long long>(cap, 1024);
+  }
+  S = std::max(32, (S + 31) / 32 * 32);
+  h->pool.S = S;
+  rc = rc ? rc : dalloc(h, &h->pool.f, (size_t)F_COUNT * S);
+  rc = rc ? rc : dalloc(h, &h->pool.id, S);
+  rc = rc ? rc : dalloc(h, &h->pool.ndraw, S);
+  rc = rc ? rc : dalloc(h, &h->pool.ic, S);
+  rc = rc ? rc : dalloc(h, &h->pool.jc, S);
+  rc = rc ? rc : dalloc(h, &h->pool.kc, S);
+  rc = rc ? rc : dalloc(h, &h->pool.flags, S);
+  rc = rc ? rc : dalloc(h, &h->job, 1);
+  if (!mono) {
+    h->q.direct_base = (unsigned)((long long)S * P.nobs);
+    h->q.ray_cap = (unsigned)std::min<long long>((long long)S * P.nobs * 2, 0x7fffffffLL);
+    rc = rc ? rc : dalloc(h, &h->q.rays, h->q.ray_cap, true);
+    unsigned int *ctr = nullptr;
+    rc = rc ? rc : dalloc(h, &ctr, 4);
+    h->q.n_direct = ctr; h->q.head_trace = ctr + 1; h->q.head_peel = ctr + 2;
+  }
+  if (rc) return bail(rc);
+  h->quantum = cfg->quantum > 0 ? cfg->quantum : (mono ? 32 : 8);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  *out = h;
+  return 0;
+}
+
+int lart_gpu_destroy(lart_gpu_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void *p : h->owned) cudaFree(p);
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride) {
+  if (!h) return fail("lart_gpu_begin: NULL handle");
+  if (count < 0 || stride < 1) return fail("lart_gpu_begin: count must be >= 0 and stride >= 1");
+  CUDA_OK(cudaSetDevice(h->device));
+  Job j{0ULL, (unsigned long long)count, 0ULL, (long long)first_id, (long long)stride};
+  CUDA_OK(cudaMemcpyAsync(h->job, &j, sizeof(Job), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemsetAsync(h->pool.flags, 0, sizeof(int) * h->pool.S, h->stream));  // abandon unfinished photons
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->count = count;
+  h->begun = true;
+  return 0;
+}
+
+int lart_gpu_step(lart_gpu_handle h, int32_t quantum, int64_t *in_flight) {
+  if (!h) return fail("lart_gpu_step: NULL handle");
+  if (!h->begun) return fail("lart_gpu_step: call lart_gpu_begin first");
+  CUDA_OK(cudaSetDevice(h->device));
+  const int qn = quantum > 0 ? quantum : h->quantum;
+  const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
+  const bool timing = (h->flags & LART_FLAG_STAGE_TIMING) != 0;
+  size_t ne = 0;
+  auto mark = [&]() -> int {  // one event between consecutive stage kernels
+    if (!timing) return 0;
+    if (ne == h->tev.size()) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreate(&e));
+      h->tev.push_back(e);
+    }
+    CUDA_OK(cudaEventRecord(h->tev[ne++], h->stream));
+    return 0;
+  };
+  CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  if (mono) {
+    if (int rc = mark()) return rc;
+    k_mono<<<(h->pool.S + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
+    if (int rc = mark()) return rc;
+    h->launches += 1;
+  } else {
+    const int gemit = std::min((h->pool.S + kBlock - 1) / kBlock, h->nsm * 8);
+    const int gwalk = std::min((h->pool.S + kBlock - 1) / kBlock, h->nsm * 4);
+    const int gscat = std::min((h->pool.S + kBlock - 1) / kBlock, h->nsm * 8);
+    for (int w = 0; w < qn; ++w) {
+      k_wf_reset<<<1, 1, 0, h->stream>>>(h->q);
+      if (int rc = mark()) return rc;
+      k_wf_emit<<<gemit, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, h->q);
+      if (int rc = mark()) return rc;
+      k_wf_trace<<<gwalk, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, h->q);
+      if (int rc = mark()) return rc;
+      k_wf_scatter<<<gscat, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, h->q);
+      if (int rc = mark()) return rc;
+      k_wf_peel<<<gwalk, kBlock, 0, h->stream>>>(h->P, h->q);
+      if (int rc = mark()) return rc;
+      h->launches += 5;
+    }
+  }
+  CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  Job j;
+  CUDA_OK(cudaMemcpyAsync(&j, h->job, sizeof(Job), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->kernel_ms += ms;
+  if (timing) {
+    if (mono) {
+      float t = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&t, h->tev[0], h->tev[1]));
+      h->stage_ms[LART_STAGE_TRACE] += t;
+      h->stage_n[LART_STAGE_TRACE] += 1;
+    } else {
+      for (int w = 0; w < qn; ++w)
+        for (int k = 0; k < LART_STAGE_COUNT; ++k) {
+          float t = 0.f;
+          CUDA_OK(cudaEventElapsedTime(&t, h->tev[5 * w + k], h->tev[5 * w + k + 1]));
+          h->stage_ms[k] += t;
+          h->stage_n[k] += 1;
+        }
+    }
+  }
+  if (in_flight) *in_flight = (int64_t)h->count - (int64_t)j.done;
+  return 0;
+}
+
+int lart_gpu_sync(lart_gpu_handle h) {
+  if (!h) return fail("lart_gpu_sync: NULL handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride) {
+  if (int rc = lart_gpu_begin(h, first_id, count, stride)) return rc;
+  int64_t left = count;
+  while (left > 0)
+    if (int rc = lart_gpu_step(h, 0, &left)) return rc;
+  return 0;
+}
+
+int lart_gpu_reset_tallies(lart_gpu_handle h) {
+  if (!h) return fail("lart_gpu_reset_tallies: NULL handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaMemsetAsync(h->P.tally, 0, sizeof(double) * h->P.lay.total, h->stream));
+  if (h->allph_buf) CUDA_OK(cudaMemsetAsync(h->allph_buf, 0, sizeof(double) * h->allph_n, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->kernel_ms = 0.0;
+  h->launches = 0;
+  for (int k = 0; k < LART_STAGE_COUNT; ++k) { h->stage_ms[k] = 0.0; h->stage_n[k] = 0; }
+  return 0;
+}
+
+int lart_gpu_tally_buffer(lart_gpu_handle h, void **dev_ptr, int64_t *n_doubles) {
+  if (!h || !dev_ptr || !n_doubles) return fail("lart_gpu_tally_buffer: NULL argument");
+  *dev_ptr = h->P.tally;
+  *n_doubles = h->P.lay.total;
+  return 0;
+}
+int lart_gpu_allph_buffer(lart_gpu_handle h, void **dev_ptr, int64_t *n_doubles) {
+  if (!h || !dev_ptr || !n_doubles) return fail("lart_gpu_allph_buffer: NULL argument");
+  *dev_ptr = h->allph_buf;
+  *n_doubles = h->allph_n;
+  return 0;
+}
+int lart_gpu_stream(lart_gpu_handle h, void **stream) {
+  if (!h || !stream) return fail("lart_gpu_stream: NULL argument");
+  *stream = (void *)h->stream;
+  return 0;
+}
+int lart_gpu_kernel_ms(lart_gpu_handle h, double *ms, int64_t *launches) {
+  if (!h) return fail("lart_gpu_kernel_ms: NULL handle");
+  if (ms) *ms = h->kernel_ms;
+  if (launches) *launches = h->launches;
+  return 0;
+}
+
+int lart_gpu_stage_ms(lart_gpu_handle h, double ms[LART_STAGE_COUNT], int64_t launches[LART_STAGE_COUNT]) {
+  if (!h) return fail("lart_gpu_stage_ms: NULL handle");
+  for (int k = 0; k < LART_STAGE_COUNT; ++k) {
+    if (ms) ms[k] = h->stage_ms[k];
+    if (launches) launches[k] = h->stage_n[k];
+  }
+  return 0;
+}
+int lart_gpu_pool_slots(lart_gpu_handle h, int64_t *slots) {
+  if (!h || !slots) return fail("lart_gpu_pool_slots: NULL argument");
+  *slots = h->pool.S;
+  return 0;
+}
+
+int lart_gpu_measure_fp64(int32_t device, double *tflops) {
+  if (!tflops) return fail("lart_gpu_measure_fp64: NULL argument");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  double *out = nullptr;
+  CUDA_OK(cudaMalloc(&out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_OK(cudaEventRecord(e0));
+    k_dfma_peak<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    CUDA_OK(cudaEventRecord(e1));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 16.0 * (double)iters * blocks * threads;  // 16 independent FMA chains per thread
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  CUDA_OK(cudaGetLastError());
+  *tflops = best;
+  return 0;
+}
+
+int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out) {
+  if (!h || !out) return fail("lart_gpu_fetch: NULL argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  const DevParams &P = h->P;
+  const TallyLayout &L = P.lay;
+  if (P.nobs > 0 && !out->obs) return fail("lart_gpu_fetch: out->obs is NULL but observers are configured");
+  h->stage.resize((size_t)L.total);
+  CUDA_OK(cudaMemcpyAsync(h->stage.data(), P.tally, sizeof(double) * L.total, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  const double *b = h->stage.data();
+  auto add = [&](double *dst, long long off, long long n) {
+    if (!dst || off < 0) return;
+    const double *s = b + off;
+    for (long long i = 0; i < n; ++i) dst[i] += s[i];
+  };
+  add(out->Jout, L.Jout, P.nxfreq);
+  add(out->Jin, L.Jin, P.nxfreq);
+  add(out->Jabs, L.Jabs, P.nxfreq);
+  add(out->Jmu, L.Jmu, (long long)P.nxfreq * P.nmu);
+  const long long n2 = (long long)h->nxim * h->nyim, n3 = n2 * P.nxfreq;
+  for (int k = 0; k < P.nobs; ++k) {
+    lart_observer_out &o = out->obs[k];
+    const long long base = L.obs_base + (long long)k * L.obs_stride;
+    double *c3[7] = {o.scatt, o.direc, o.direc0, o.I, o.Q, o.U, o.V};
+    double *c2[7] = {o.scatt_2D, o.direc_2D, o.direc0_2D, o.I_2D, o.Q_2D, o.U_2D, o.V_2D};
+    for (int q = 0; q < 7; ++q) {
+      if (L.cube[q] >= 0) add(c3[q], base + L.cube[q], n3);
+      if (L.img[q] >= 0) add(c2[q], base + L.img[q], n2);
+    }
+  }
+  out->nscatt_gas += b[L.scalars + 0];
+  out->nscatt_dust += b[L.scalars + 1];
+  const double *c = b + L.counters;
+  out->counters.n_photons_done += c[C_PHOTONS]; out->counters.n_scatter += c[C_SCATTER];
+  out->counters.n_cellsteps += c[C_CELLSTEPS]; out->counters.n_peel += c[C_PEEL];
+  out->counters.n_rng += c[C_RNG]; out->counters.n_reject_iter += c[C_REJECT];
+  if (h->allph_buf) {
+    std::vector<double> a((size_t)h->allph_n);
+    CUDA_OK(cudaMemcpy(a.data(), h->allph_buf, sizeof(double) * h->allph_n, cudaMemcpyDeviceToHost));
+    double *dst[10] = {out->allph.rp0, out->allph.rp, out->allph.xfreq1, out->allph.xfreq2, out->allph.nscatt_gas,
+                       out->allph.nscatt_dust, out->allph.I, out->allph.Q, out->allph.U, out->allph.V};
+    for (int k = 0; k < 10; ++k)
+      if (h->allph_slot[k] >= 0 && dst[k]) {
+        const double *s = a.data() + (long long)h->allph_slot[k] * P.nphotons;
+        for (long long i = 0; i < P.nphotons; ++i) dst[k][i] += s[i];
+      }
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------- batched plugin points -------------------------
+namespace {
+struct Scratch {  // device copies of host arrays for one batch call
+  std::vector<void *> p;
+  ~Scratch() { for (void *q : p) cudaFree(q); }
+  template <class T>
+  int in(T **d, const T *hsrc, size_t n) {
+    *d = nullptr;
+    if (!hsrc) return 0;
+    CUDA_OK(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
+    p.push_back(*d);
+    CUDA_OK(cudaMemcpy(*d, hsrc, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+  }
+  template <class T>
+  int outbuf(T **d, size_t n) {
+    CUDA_OK(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
+    p.push_back(*d);
+    return 0;
+  }
+};
+inline int grid_for(long long n, int nsm) { return (int)std::max<long long>(1, std::min<long long>((n + kBlock - 1) / kBlock, nsm * 8LL)); }
+#define D2H(dst, src, n) CUDA_OK(cudaMemcpy((dst), (src), (n) * sizeof(*(dst)), cudaMemcpyDeviceToHost))
+}  // namespace
+
+extern "C" {
+
+int lart_gpu_voigt_batch(int64_t n, const double *x, const double *a, double *H) {
+  if (n < 0 || (n > 0 && (!x || !a || !H))) return fail("lart_gpu_voigt_batch: bad argument");
+  if (n == 0) return 0;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  double *tab;
+  if (int rc = device_vtab(dev, &tab)) return rc;
+  Scratch s;
+  double *dx, *da, *dH;
+  if (int rc = s.in(&dx, x, n)) return rc;
+  if (int rc = s.in(&da, a, n)) return rc;
+  if (int rc = s.outbuf(&dH, n)) return rc;
+  k_voigt_batch<<<grid_for(n, 148), kBlock>>>(tab, n, dx, da, dH);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  D2H(H, dH, n);
+  return 0;
+}
+
+int lart_gpu_raytrace_edge_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z,
+                                 const double *kx, const double *ky, const double *kz, const double *xfreq,
+                                 const int32_t *icell, const int32_t *jcell, const int32_t *kcell, double *tau,
+                                 int32_t *nsteps, int32_t trace_cap, int32_t *trace_cells) {
+  if (!h) return fail("lart_gpu_raytrace_edge_batch: NULL handle");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !kx || !ky || !kz || !xfreq || !icell || !jcell || !kcell || !tau)))
+    return fail("lart_gpu_raytrace_edge_batch: bad argument");
+  if (n == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz, *dkx, *dky, *dkz, *dxf, *dtau;
+  int *dic, *djc, *dkc, *dns, *dtr = nullptr;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, x, n); rc = rc ? rc : s.in(&dy, y, n); rc = rc ? rc : s.in(&dz, z, n);
+  rc = rc ? rc : s.in(&dkx, kx, n); rc = rc ? rc : s.in(&dky, ky, n); rc = rc ? rc : s.in(&dkz, kz, n);
+  rc = rc ? rc : s.in(&dxf, xfreq, n);
+  rc = rc ? rc : s.in(&dic, icell, n); rc = rc ? rc : s.in(&djc, jcell, n); rc = rc ? rc : s.in(&dkc, kcell, n);
+  rc = rc ? rc : s.outbuf(&dtau, n); rc = rc ? rc : s.outbuf(&dns, n);
+  if (!rc && trace_cells && trace_cap > 0) {
+    rc = s.outbuf(&dtr, (size_t)n * trace_cap);
+    if (!rc) CUDA_OK(cudaMemset(dtr, 0xff, sizeof(int) * (size_t)n * trace_cap));
+  }
+  if (rc) return rc;
+  k_edge_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dkx, dky, dkz, dxf, dic, djc, dkc, dtau, dns,
+                                                             dtr ? trace_cap : 0, dtr);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  D2H(tau, dtau, n);
+  if (nsteps) D2H(nsteps, dns, n);
+  if (dtr) D2H(trace_cells, dtr, (size_t)n * trace_cap);
+  return 0;
+}
+
+int lart_gpu_raytrace_tau_batch(lart_gpu_handle h, int64_t n, double *x, double *y, double *z, const double *kx,
+                                const double *ky, const double *kz, double *xfreq, int32_t *icell, int32_t *jcell,
+                                int32_t *kcell, const double *tau_in, int32_t *inside, double *xfreq_ref, int32_t *nsteps) {
+  if (!h) return fail("lart_gpu_raytrace_tau_batch: NULL handle");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !kx || !ky || !kz || !xfreq || !icell || !jcell || !kcell || !tau_in || !inside)))
+    return fail("lart_gpu_raytrace_tau_batch: bad argument");
+  if (n == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz, *dkx, *dky, *dkz, *dxf, *dti, *dxr;
+  int *dic, *djc, *dkc, *dins, *dns;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, (const double *)x, n); rc = rc ? rc : s.in(&dy, (const double *)y, n); rc = rc ? rc : s.in(&dz, (const double *)z, n);
+  rc = rc ? rc : s.in(&dkx, kx, n); rc = rc ? rc : s.in(&dky, ky, n); rc = rc ? rc : s.in(&dkz, kz, n);
+  rc = rc ? rc : s.in(&dxf, (const double *)xfreq, n); rc = rc ? rc : s.in(&dti, tau_in, n);
+  rc = rc ? rc : s.in(&dic, (const int *)icell, n); rc = rc ? rc : s.in(&djc, (const int *)jcell, n); rc = rc ? rc : s.in(&dkc, (const int *)kcell, n);
+  rc = rc ? rc : s.outbuf(&dins, n); rc = rc ? rc : s.outbuf(&dxr, n); rc = rc ? rc : s.outbuf(&dns, n);
+  if (rc) return rc;
+  k_tau_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dkx, dky, dkz, dxf, dic, djc, dkc, dti, dins, dxr, dns);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  D2H(x, dx, n); D2H(y, dy, n); D2H(z, dz, n); D2H(xfreq, dxf, n);
+  D2H(icell, dic, n); D2H(jcell, djc, n); D2H(kcell, dkc, n); D2H(inside, dins, n);
+  if (xfreq_ref) D2H(xfreq_ref, dxr, n);
+  if (nsteps) D2H(nsteps, dns, n);
+  return 0;
+}
+
+int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z,
+                         const int32_t *icell, const int32_t *jcell, const int32_t *kcell, double *xcrit) {
+  if (!h) return fail("lart_gpu_xcrit_batch: NULL handle");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !icell || !jcell || !kcell || !xcrit))) return fail("lart_gpu_xcrit_batch: bad argument");
+  if (n == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz, *dout;
+  int *dic, *djc, *dkc;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, x, n); rc = rc ? rc : s.in(&dy, y, n); rc = rc ? rc : s.in(&dz, z, n);
+  rc = rc ? rc : s.in(&dic, icell, n); rc = rc ? rc : s.in(&djc, jcell, n); rc = rc ? rc : s.in(&dkc, kcell, n);
+  rc = rc ? rc : s.outbuf(&dout, n);
+  if (rc) return rc;
+  k_xcrit_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dic, djc, dkc, dout);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  D2H(xcrit, dout, n);
+  return 0;
+}
+
+int lart_gpu_sample_batch(int32_t kind, uint64_t seed, int64_t n, const int64_t *ids, const double *p0, const double *p1,
+                          int32_t ndraw, double *out) {
+  if (kind < 0 || kind > 5) return fail("lart_gpu_sample_batch: unknown kind");
+  if (n < 0 || ndraw < 1 || (n > 0 && !out)) return fail("lart_gpu_sample_batch: bad argument");
+  if ((kind >= 2) && n > 0 && !p0) return fail("lart_gpu_sample_batch: p0 required");
+  if (kind == 2 && n > 0 && !p1) return fail("lart_gpu_sample_batch: p1 required");
+  if (n == 0) return 0;
+  Scratch s;
+  long long *dids;
+  double *dp0, *dp1, *dout;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dids, (const long long *)ids, n);
+  rc = rc ? rc : s.in(&dp0, p0, n); rc = rc ? rc : s.in(&dp1, p1, n);
+  rc = rc ? rc : s.outbuf(&dout, (size_t)n * ndraw);
+  if (rc) return rc;
+  k_sample_batch<<<grid_for(n, 148), kBlock>>>(kind, seed, n, dids, dp0, dp1, ndraw, dout);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  D2H(out, dout, (size_t)n * ndraw);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+"""Host-side mirror of LaRT's driver sequence for the Cartesian photon loop.
+
+The reference's main program (src/main.f90:19-57) runs
+
+    read_input -> setup_procedure -> grid_create -> observer_create
+    -> run_simulation(grid) -> output_reduce(grid) -> output_normalize(grid) -> write_output
+
+`Model` covers the steps before `run_simulation` through the C++ mini-host
+(liblart_host.so, include/lart_host.h); `Simulation` is the replacement for
+`run_simulation` + `output_reduce`: it drives the CUDA engine through the C ABI
+(liblart_gpu.so, include/lart_gpu.h) exactly as the Fortran shim
+(shim/lart_gpu_shim.f90) does.  Names follow the reference (par, grid, observer,
+Jout, Jin, nscatt_gas ...).  PyTorch is used only for the multi-GPU plumbing
+(torch.distributed / NCCL) in `output_reduce`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class LartError(RuntimeError):
+    pass
+
+
+def _np(ptr, shape):
+    """numpy view (no copy) of a double* owned by the mini-host; None for NULL."""
+    if not ptr:
+        return None
+    n = int(np.prod(shape))
+    return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape, order="F")
+
+
+class Model:
+    """namelist -> resolved par/grid/line/observers (setup.f90 + grid_mod_car.f90 + observer_rect.f90)."""
+
+    def __init__(self, infile=None, **par):
+        self._lib = capi.load_host()
+        self._m = C.c_void_p(self._lib.lart_host_new())
+        self._setup = False
+        if infile is not None:
+            self.read_input(infile)
+        for k, v in par.items():
+            self.set(k, v)
+
+    def __del__(self):
+        try:
+            if self._m:
+                self._lib.lart_host_free(self._m)
+                self._m = None
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LartError(self._lib.lart_host_last_error().decode())
+
+    @staticmethod
+    def _fmt(v):
+        if isinstance(v, bool):
+            return ".true." if v else ".false."
+        if isinstance(v, (list, tuple, np.ndarray)):
+            return " ".join(repr(float(x)) for x in v)
+        if isinstance(v, str):
+            return "'%s'" % v
+        return repr(v)
+
+    def set(self, key, value):
+        """`par%key = value`, as one line of the &parameters namelist (setup.f90:27-40)."""
+        self._setup = False
+        self._check(self._lib.lart_host_set(self._m, key.encode(), self._fmt(value).encode()))
+        return self
+
+    def read_input(self, path):
+        self._setup = False
+        self._check(self._lib.lart_host_read_input(self._m, str(path).encode()))
+        return self
+
+    def setup(self):
+        self._check(self._lib.lart_host_setup(self._m))
+        self._setup = True
+        return self
+
+    @property
+    def config(self):
+        """The lart_config handed to lart_gpu_create (pointer target owned by the model)."""
+        if not self._setup:
+            self.setup()
+        return self._lib.lart_host_config(self._m)
+
+    @property
+    def summary(self):
+        if not self._setup:
+            self.setup()
+        s = capi.HostSummary()
+        self._check(self._lib.lart_host_get_summary(self._m, C.byref(s)))
+        return s
+
+    @property
+    def tallies(self):
+        if not self._setup:
+            self.setup()
+        return self._lib.lart_host_tallies(self._m)
+
+    def zero_tallies(self):
+        self._check(self._lib.lart_host_zero_tallies(self._m))
+
+    def output_normalize(self):
+        """output_normalize_outside (output_sum_rect.f90:151-487), in place."""
+        self._check(self._lib.lart_host_normalize(self._m))
+
+    # ---- numpy views of the grid and the tallies (Fortran order, as grid_type holds them)
+    def grid_array(self, name):
+        g = self.config.contents.grid
+        shape = {"xface": (g.nx + 1,), "yface": (g.ny + 1,), "zface": (g.nz + 1,)}.get(name, (g.nx, g.ny, g.nz))
+        return _np(getattr(g, name), shape)
+
+    def spectrum(self, name="Jout"):
+        g = self.config.contents.grid
+        t = self.tallies.contents
+        if name == "Jmu":
+            return _np(t.Jmu, (g.nxfreq, self.config.contents.par.nmu))
+        return _np(getattr(t, name), (g.nxfreq,))
+
+    def xfreq(self):
+        """bin centres, grid%xfreq (grid_mod_car.f90:1505)."""
+        g = self.config.contents.grid
+        return (np.arange(g.nxfreq) + 0.5) * g.dxfreq + g.xfreq_min
+
+    def observer_cube(self, name, iobs=0):
+        cfg = self.config.contents
+        t = self.tallies.contents
+        if not t.obs:
+            return None
+        ob = cfg.observers[iobs]
+        shape = (ob.nxim, ob.nyim) if name.endswith("_2D") else (cfg.grid.nxfreq, ob.nxim, ob.nyim)
+        return _np(getattr(t.obs[iobs], name), shape)
+
+    def allph(self, name):
+        t = self.tallies.contents
+        return _np(getattr(t.allph, name), (self.config.contents.par.nphotons,))
+
+    @property
+    def counters(self):
+        c = self.tallies.contents.counters
+        return {n: getattr(c, n) for n in capi.COUNTER_FIELDS}
+
+    @property
+    def nscatt_gas(self):
+        return self.tallies.contents.nscatt_gas
+
+    @property
+    def nscatt_dust(self):
+        return self.tallies.contents.nscatt_dust
+
+
+def photon_partition(nphotons, rank, nproc):
+    """Photon ids of `rank`: rank+1, rank+1+nproc, ... <= nphotons (run_simulation_mod.f90:150).
+    Returns (first_id, count, stride)."""
+    n = int(nphotons)
+    count = (n - rank + nproc - 1) // nproc if n > rank else 0
+    return rank + 1, count, nproc
+
+
+class Simulation:
+    """One more implementation of `run_sim` (define.f90:832-838) on one GPU.
+
+    run_simulation(rank, nproc) runs photon ids rank+1, rank+1+nproc, ... as
+    run_equal_number does (run_simulation_mod.f90:150); output_reduce() adds the
+    device tallies into the model's host buffers (output_sum_rect.f90:7-149),
+    after ONE sum-reduce over NCCL when a torch.distributed group is active.
+    """
+
+    def __init__(self, model, device=0, pool_slots=0, quantum=0, flags=0, seed=None):
+        self._lib = capi.load_gpu()  # raises if the CUDA engine is missing: no fallback
+        self.model = model
+        cfg = model.config.contents
+        cfg.device = device
+        cfg.pool_slots = pool_slots
+        cfg.quantum = quantum
+        cfg.flags = flags
+        if seed is not None:
+            cfg.par.seed = seed
+        self._h = C.c_void_p()
+        self._check(self._lib.lart_gpu_create(C.byref(cfg), C.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LartError(self._lib.lart_gpu_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lart_gpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_simulation(self, rank=0, nproc=1, nphotons=None):
+        n = int(self.model.config.contents.par.nphotons if nphotons is None else nphotons)
+        first, count, stride = photon_partition(n, rank, nproc)
+        self._check(self._lib.lart_gpu_run(self._h, first, count, stride))
+
+    def begin(self, first_id, count, stride=1):
+        self._check(self._lib.lart_gpu_begin(self._h, first_id, count, stride))
+
+    def step(self, quantum=0):
+        left = C.c_int64()
+        self._check(self._lib.lart_gpu_step(self._h, quantum, C.byref(left)))
+        return left.value
+
+    def sync(self):
+        self._check(self._lib.lart_gpu_sync(self._h))
+
+    def reset_tallies(self):
+        self._check(self._lib.lart_gpu_reset_tallies(self._h))
+
+    def kernel_ms(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self._lib.lart_gpu_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def stage_ms(self):
+        """{stage: (summed ms, launches)} — needs flags & FLAG_STAGE_TIMING."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        self._check(self._lib.lart_gpu_stage_ms(self._h, ms, n))
+        return {capi.STAGES[k]: (ms[k], n[k]) for k in range(4)}
+
+    @property
+    def pool_slots(self):
+        n = C.c_int64()
+        self._check(self._lib.lart_gpu_pool_slots(self._h, C.byref(n)))
+        return n.value
+
+    def tally_buffer(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self._lib.lart_gpu_tally_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def allph_buffer(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self._lib.lart_gpu_allph_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def stream(self):
+        s = C.c_void_p()
+        self._check(self._lib.lart_gpu_stream(self._h, C.byref(s)))
+        return s.value
+
+    def _as_torch(self, ptr, n):
+        import torch
+
+        class _Buf:  # zero-copy view of the engine's device buffer
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Buf(), device="cuda:%d" % self.model.config.contents.device)
+
+    def output_reduce(self, dst=0):
+        """Sum the tallies of all ranks onto `dst` (ONE NCCL reduce over the contiguous
+        tally buffer; replaces memory_mod_mpi.f90:366-458) and add them to the host arrays."""
+        self.sync()
+        rank = 0
+        try:
+            import torch.distributed as dist
+            active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except ImportError:
+            active = False
+        if active:
+            import torch
+            rank = dist.get_rank()
+            ptr, n = self.tally_buffer()
+            dist.reduce(self._as_torch(ptr, n), dst=dst, op=dist.ReduceOp.SUM)
+            ptr, n = self.allph_buffer()
+            if n > 0:
+                dist.reduce(self._as_torch(ptr, n), dst=dst, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+        if rank == dst:
+            self._check(self._lib.lart_gpu_fetch(self._h, self.model.tallies))
+
+    # ---- unit-level batched plugin points (define.f90:741-784) -------------
+    def raytrace_to_edge(self, x, y, z, kx, ky, kz, xfreq, icell, jcell, kcell, trace_cap=0):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        x, y, z, kx, ky, kz, xfreq = map(f, (x, y, z, kx, ky, kz, xfreq))
+        icell, jcell, kcell = map(i, (icell, jcell, kcell))
+        n = x.size
+        tau = np.zeros(n)
+        nsteps = np.zeros(n, dtype=np.int32)
+        trace = np.full((n, trace_cap), -1, dtype=np.int32) if trace_cap > 0 else None
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        ip = lambda a: a.ctypes.data_as(capi.c_int32_p)
+        self._check(self._lib.lart_gpu_raytrace_edge_batch(
+            self._h, n, dp(x), dp(y), dp(z), dp(kx), dp(ky), dp(kz), dp(xfreq), ip(icell), ip(jcell), ip(kcell),
+            dp(tau), ip(nsteps), trace_cap, ip(trace) if trace is not None else None))
+        return tau, nsteps, trace
+
+    def raytrace_to_tau(self, x, y, z, kx, ky, kz, xfreq, icell, jcell, kcell, tau_in):
+        f = lambda a: np.array(a, dtype=np.float64, copy=True)
+        i = lambda a: np.array(a, dtype=np.int32, copy=True)
+        x, y, z, kx, ky, kz, xfreq, tau_in = map(f, (x, y, z, kx, ky, kz, xfreq, tau_in))
+        icell, jcell, kcell = map(i, (icell, jcell, kcell))
+        n = x.size
+        inside = np.zeros(n, dtype=np.int32)
+        nsteps = np.zeros(n, dtype=np.int32)
+        xref = np.zeros(n)
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        ip = lambda a: a.ctypes.data_as(capi.c_int32_p)
+        self._check(self._lib.lart_gpu_raytrace_tau_batch(
+            self._h, n, dp(x), dp(y), dp(z), dp(kx), dp(ky), dp(kz), dp(xfreq), ip(icell), ip(jcell), ip(kcell),
+            dp(tau_in), ip(inside), dp(xref), ip(nsteps)))
+        return dict(x=x, y=y, z=z, xfreq=xfreq, icell=icell, jcell=jcell, kcell=kcell, inside=inside,
+                    xfreq_ref=xref, nsteps=nsteps)
+
+    def xcrit_local(self, x, y, z, icell, jcell, kcell):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        x, y, z = map(f, (x, y, z))
+        icell, jcell, kcell = map(i, (icell, jcell, kcell))
+        out = np.zeros(x.size)
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        ip = lambda a: a.ctypes.data_as(capi.c_int32_p)
+        self._check(self._lib.lart_gpu_xcrit_batch(self._h, x.size, dp(x), dp(y), dp(z), ip(icell), ip(jcell),
+                                                   ip(kcell), dp(out)))
+        return out
+
+
+def measure_fp64(device=0):
+    """FP64 FMA throughput of the device in TFLOP/s (register-resident DFMA loop)."""
+    lib = capi.load_gpu()
+    t = C.c_double()
+    if lib.lart_gpu_measure_fp64(device, C.byref(t)) != 0:
+        raise LartError(lib.lart_gpu_last_error().decode())
+    return t.value
+
+
+def calc_voigt(x, a):
+    """voigt_seon2 on the GPU (voigt_mod.f90:541-733)."""
+    lib = capi.load_gpu()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    a = np.ascontiguousarray(np.broadcast_to(a, x.shape), dtype=np.float64)
+    H = np.empty_like(x)
+    rc = lib.lart_gpu_voigt_batch(x.size, x.ctypes.data_as(capi.c_double_p), a.ctypes.data_as(capi.c_double_p),
+                                  H.ctypes.data_as(capi.c_double_p))
+    if rc != 0:
+        raise LartError(lib.lart_gpu_last_error().decode())
+    return H
+
+
+def sample(kind, seed, ids, p0=None, p1=None, ndraw=1):
+    """Random variates on the path, one Philox stream per element (see lart_gpu_sample_batch)."""
+    lib = capi.load_gpu()
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    n = ids.size
+    p0 = np.ascontiguousarray(np.broadcast_to(0.0 if p0 is None else p0, (n,)), dtype=np.float64)
+    p1 = np.ascontiguousarray(np.broadcast_to(0.0 if p1 is None else p1, (n,)), dtype=np.float64)
+    out = np.empty((n, ndraw))
+    rc = lib.lart_gpu_sample_batch(kind, seed, n, ids.ctypes.data_as(capi.c_int64_p),
+                                   p0.ctypes.data_as(capi.c_double_p), p1.ctypes.data_as(capi.c_double_p), ndraw,
+                                   out.ctypes.data_as(capi.c_double_p))
+    if rc != 0:
+        raise LartError(lib.lart_gpu_last_error().decode())
+    return out

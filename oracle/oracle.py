@@ -1,0 +1,155 @@
+"""ctypes wrapper of the CPU oracle (oracle/liblart_oracle.so).
+
+TEST INFRASTRUCTURE ONLY.  Import this from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs — never from lart_b200/.
+It consumes the same lart_config the product consumes (structure layouts are
+shared declarations from lart_b200/capi.py) so both sides see identical inputs.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from lart_b200 import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "liblart_oracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "lart_oracle.cpp")
+    if force or not os.path.exists(lib_path()) or os.path.getmtime(lib_path()) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(lib_path()):
+            build()
+        lib = C.CDLL(lib_path())
+        dp, ip, lp = capi.c_double_p, capi.c_int32_p, capi.c_int64_p
+        cfgp = C.POINTER(capi.Config)
+        lib.oracle_last_error.restype = C.c_char_p
+        lib.oracle_voigt.argtypes = [C.c_int64, dp, dp, dp]
+        lib.oracle_raytrace_edge.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip] * 3 + [dp, ip, C.c_int32, ip]
+        lib.oracle_raytrace_tau.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip] * 3 + [dp, ip, dp, ip]
+        lib.oracle_xcrit.argtypes = [cfgp, C.c_int64] + [dp] * 3 + [ip] * 3 + [dp]
+        lib.oracle_sample.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_int64, lp, dp, dp, C.c_int32, dp]
+        lib.oracle_philox_block.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+        lib.oracle_philox_raw.argtypes = [C.POINTER(C.c_uint32)] * 3
+        lib.oracle_mt64_words.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]
+        lib.oracle_run.argtypes = [cfgp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                   C.POINTER(capi.Tallies)]
+        lib.oracle_hardware_threads.restype = C.c_int
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(load().oracle_last_error().decode())
+
+
+def _d(a):
+    return a.ctypes.data_as(capi.c_double_p)
+
+
+def _i(a):
+    return a.ctypes.data_as(capi.c_int32_p)
+
+
+def voigt(x, a):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    a = np.ascontiguousarray(np.broadcast_to(a, x.shape), dtype=np.float64)
+    H = np.empty_like(x)
+    _check(load().oracle_voigt(x.size, _d(x), _d(a), _d(H)))
+    return H
+
+
+def raytrace_to_edge(cfg, x, y, z, kx, ky, kz, xfreq, ic, jc, kc, trace_cap=0):
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    g = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    x, y, z, kx, ky, kz, xfreq = map(f, (x, y, z, kx, ky, kz, xfreq))
+    ic, jc, kc = map(g, (ic, jc, kc))
+    n = x.size
+    tau = np.zeros(n)
+    ns = np.zeros(n, dtype=np.int32)
+    trace = np.full((n, trace_cap), -1, dtype=np.int32) if trace_cap > 0 else None
+    _check(load().oracle_raytrace_edge(cfg, n, _d(x), _d(y), _d(z), _d(kx), _d(ky), _d(kz), _d(xfreq), _i(ic), _i(jc),
+                                       _i(kc), _d(tau), _i(ns), trace_cap, _i(trace) if trace is not None else None))
+    return tau, ns, trace
+
+
+def raytrace_to_tau(cfg, x, y, z, kx, ky, kz, xfreq, ic, jc, kc, tau_in):
+    f = lambda a: np.array(a, dtype=np.float64, copy=True)
+    g = lambda a: np.array(a, dtype=np.int32, copy=True)
+    x, y, z, kx, ky, kz, xfreq, tau_in = map(f, (x, y, z, kx, ky, kz, xfreq, tau_in))
+    ic, jc, kc = map(g, (ic, jc, kc))
+    n = x.size
+    inside = np.zeros(n, dtype=np.int32)
+    ns = np.zeros(n, dtype=np.int32)
+    xref = np.zeros(n)
+    _check(load().oracle_raytrace_tau(cfg, n, _d(x), _d(y), _d(z), _d(kx), _d(ky), _d(kz), _d(xfreq), _i(ic), _i(jc),
+                                      _i(kc), _d(tau_in), _i(inside), _d(xref), _i(ns)))
+    return dict(x=x, y=y, z=z, xfreq=xfreq, icell=ic, jcell=jc, kcell=kc, inside=inside, xfreq_ref=xref, nsteps=ns)
+
+
+def xcrit_local(cfg, x, y, z, ic, jc, kc):
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    g = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    x, y, z = map(f, (x, y, z))
+    ic, jc, kc = map(g, (ic, jc, kc))
+    out = np.zeros(x.size)
+    _check(load().oracle_xcrit(cfg, x.size, _d(x), _d(y), _d(z), _i(ic), _i(jc), _i(kc), _d(out)))
+    return out
+
+
+def sample(kind, seed, ids, p0=None, p1=None, ndraw=1, rng_mode=1):
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    n = ids.size
+    p0 = np.ascontiguousarray(np.broadcast_to(0.0 if p0 is None else p0, (n,)), dtype=np.float64)
+    p1 = np.ascontiguousarray(np.broadcast_to(0.0 if p1 is None else p1, (n,)), dtype=np.float64)
+    out = np.empty((n, ndraw))
+    _check(load().oracle_sample(kind, rng_mode, seed, n, ids.ctypes.data_as(capi.c_int64_p), _d(p0), _d(p1), ndraw,
+                                _d(out)))
+    return out
+
+
+def philox_block(seed, stream, block):
+    out = (C.c_uint32 * 4)()
+    load().oracle_philox_block(seed, stream, block, out)
+    return list(out)
+
+
+def philox_raw(ctr, key):
+    out = (C.c_uint32 * 4)()
+    load().oracle_philox_raw((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+    return list(out)
+
+
+def mt64_words(seed, n):
+    out = (C.c_uint64 * n)()
+    load().oracle_mt64_words(seed, n, out)
+    return list(out)
+
+
+def hardware_threads():
+    return load().oracle_hardware_threads()
+
+
+def run(model, rng_mode=1, nthreads=None, first_id=1, count=None, stride=1, max_events=0, seed=None):
+    """Whole run into the model's host tallies (ADDED, like the product's fetch)."""
+    cfg = model.config
+    if seed is not None:
+        cfg.contents.par.seed = seed
+    if count is None:
+        count = cfg.contents.par.nphotons
+    if nthreads is None:
+        nthreads = hardware_threads()
+    _check(load().oracle_run(cfg, rng_mode, nthreads, first_id, count, stride, max_events, model.tallies))

@@ -1,0 +1,83 @@
+"""Properties of the oracle's DDA restatement (CPU only): analytic optical depths, cell
+sequences, the on-face / axis-parallel / tie rules of setup_traversal_car."""
+import numpy as np
+import pytest
+
+from lart_b200 import Model
+from oracle import oracle
+
+
+def uniform_box(n=8, tau=1.0, **kw):
+    return Model(no_photons=10, temperature=1e4, taumax=tau, nx=n, ny=n, nz=n, geometry="rectangle", nxfreq=11, **kw).setup()
+
+
+def test_tau_is_opacity_times_path_length():
+    m = uniform_box()
+    rng = np.random.default_rng(0)
+    n = 2000
+    p = rng.uniform(-0.99, 0.99, (n, 3))
+    k = rng.normal(size=(n, 3))
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    g = m.config.contents.grid
+    ic = np.floor((p - [g.xmin, g.ymin, g.zmin]) / [g.dx, g.dy, g.dz]).astype(np.int32) + 1
+    xf = rng.uniform(-3, 3, n)
+    tau, ns, _ = oracle.raytrace_to_edge(m.config, p[:, 0], p[:, 1], p[:, 2], k[:, 0], k[:, 1], k[:, 2], xf, ic[:, 0],
+                                         ic[:, 1], ic[:, 2])
+    t = np.min(np.where(k > 0, (1 - p) / k, (-1 - p) / k), axis=1)  # distance to the box
+    kap = m.grid_array("rhokap")[0, 0, 0] * oracle.voigt(xf, m.summary.voigt_a)
+    assert np.allclose(tau, kap * t, rtol=1e-12)
+    assert ns.min() >= 1 and ns.max() <= 3 * 8
+
+
+def test_axis_parallel_and_face_rules():
+    m = uniform_box(n=4, tau=2.0)
+    cfg = m.config
+    one = lambda v: np.array([v], dtype=float)
+    # +x from the centre of cell (3,3,3): crosses cells 3,4 -> 2 steps, trace = linear indices
+    tau, ns, tr = oracle.raytrace_to_edge(cfg, one(0.25), one(0.25), one(0.25), one(1), one(0), one(0), one(0.0),
+                                          [3], [3], [3], trace_cap=8)
+    assert ns[0] == 2 and list(tr[0, :2]) == [2 + 4 * (2 + 4 * 2), 3 + 4 * (2 + 4 * 2)]
+    # photon sitting exactly on the lower face of cell 3 and moving -x is moved into cell 2 (raytrace_car.f90:36-44)
+    tau2, ns2, tr2 = oracle.raytrace_to_edge(cfg, one(0.0), one(0.25), one(0.25), one(-1), one(0), one(0), one(0.0),
+                                             [3], [3], [3], trace_cap=8)
+    assert ns2[0] == 2 and list(tr2[0, :2]) == [1 + 4 * (2 + 4 * 2), 0 + 4 * (2 + 4 * 2)]
+    # on the lower face of cell 1 moving outwards: already leaving, tau = 0, no step
+    tau3, ns3, _ = oracle.raytrace_to_edge(cfg, one(-1.0), one(0.25), one(0.25), one(-1), one(0), one(0), one(0.0),
+                                           [1], [3], [3])
+    assert tau3[0] == 0.0 and ns3[0] == 0
+    # tie between x and y crossings resolves to x first (minloc)
+    s = 1 / np.sqrt(2)
+    _, ns4, tr4 = oracle.raytrace_to_edge(cfg, one(0.25), one(0.25), one(0.25), one(s), one(s), one(0), one(0.0),
+                                          [3], [3], [3], trace_cap=8)
+    c = lambda i, j, k: (i - 1) + 4 * ((j - 1) + 4 * (k - 1))
+    assert list(tr4[0, :ns4[0]]) == [c(3, 3, 3), c(4, 3, 3), c(4, 4, 3)]
+
+
+def test_tau_walk_lands_at_requested_depth():
+    m = uniform_box(n=16, tau=50.0)
+    rng = np.random.default_rng(1)
+    n = 1000
+    k = rng.normal(size=(n, 3))
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    z = np.zeros(n)
+    ic = np.full(n, 9, dtype=np.int32)
+    tau_in = rng.exponential(size=n) * 5
+    out = oracle.raytrace_to_tau(m.config, z, z, z, k[:, 0], k[:, 1], k[:, 2], z, ic, ic, ic, tau_in)
+    kap = m.grid_array("rhokap")[0, 0, 0] * oracle.voigt([0.0], m.summary.voigt_a)[0]
+    d = np.sqrt(out["x"] ** 2 + out["y"] ** 2 + out["z"] ** 2)
+    ins = out["inside"] == 1
+    assert ins.sum() > 900
+    assert np.allclose(d[ins] * kap, tau_in[ins], rtol=1e-10)
+    g = m.config.contents.grid
+    assert np.array_equal(out["icell"][ins], np.floor((out["x"][ins] - g.xmin) / g.dx).astype(int) + 1)
+
+
+def test_velocity_field_shifts_frequency():
+    m = Model(no_photons=10, temperature=1e4, N_HI=1e18, nx=21, ny=21, nz=21, rmax=1.0, velocity_type="hubble",
+              Vexp=100.0, nxfreq=21, xfreq_min=-20, xfreq_max=20).setup()
+    one = lambda v: np.array([v], dtype=float)
+    out = oracle.raytrace_to_tau(m.config, one(0), one(0), one(0), one(0), one(0), one(1), one(0.0), [11], [11], [11],
+                                 one(1e9))
+    assert out["inside"][0] == 0
+    # escaping along +z from rest at the centre: lab frequency equals the emitted one (comoving frame at v = 0)
+    assert out["xfreq_ref"][0] == pytest.approx(0.0, abs=1e-12)

@@ -1,0 +1,58 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2): the photon-id partition of
+run_equal_number (run_simulation_mod.f90:150) and the single sum-reduce of the tallies.
+The oracle in Philox mode stands in for the engine: its photon histories depend only on
+(seed, photon id), exactly like the GPU engine's, so the reduced spectrum of two ranks
+must equal the one-rank spectrum."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lart_b200.host import Model, photon_partition
+    from oracle import oracle
+    m = Model(no_photons=301, temperature=1e4, taumax=30.0, nx=9, ny=9, nz=9, rmax=1.0, nxfreq=41, iseed=3).setup()
+    first, count, stride = photon_partition(301, rank, world)
+    oracle.run(m, rng_mode=1, nthreads=1, first_id=first, count=count, stride=stride)
+    t = torch.from_numpy(np.concatenate([m.spectrum("Jout"), m.spectrum("Jin"), [m.nscatt_gas, m.counters["n_photons_done"]]]))
+    dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put(t.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_and_reduce_equals_one_rank():
+    from lart_b200.host import Model, photon_partition
+    from oracle import oracle
+    # partition covers ids 1..N exactly once for any world size
+    for world in (1, 2, 3, 8):
+        ids = []
+        for r in range(world):
+            f, c, s = photon_partition(301, r, world)
+            ids += [f + i * s for i in range(c)]
+        assert sorted(ids) == list(range(1, 302))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = Model(no_photons=301, temperature=1e4, taumax=30.0, nx=9, ny=9, nz=9, rmax=1.0, nxfreq=41, iseed=3).setup()
+    oracle.run(m, rng_mode=1, nthreads=1)
+    ref = np.concatenate([m.spectrum("Jout"), m.spectrum("Jin"), [m.nscatt_gas, m.counters["n_photons_done"]]])
+    assert got[-1] == 301
+    assert np.allclose(got, ref, rtol=1e-12, atol=0)

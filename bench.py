@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the Cartesian photon loop on B200 (and the CPU baseline beside it).
+
+Workload (BASELINE.json configs[1], examples/sphere_peel/t4tau7.in): static uniform sphere,
+201^3 cells, T = 1e4 K, tau0 = 1e7, point source, Stokes on, one observer, 201x129x129
+peel-off cube.  A photon needs ~1e7 scatterings to leave this medium, so — as BASELINE.md
+prescribes — both arms time a bounded photon budget and report RATES: a "step" advances every
+photon slot in flight by `--quantum` scatterings (one wave = emit/trace/scatter/peel stage
+kernels over the whole pool).  value = scatterings/s, whole job (all ranks).
+
+One JSON line on stdout (rank 0).  `--impl reference` times the CPU restatement of the
+reference's loop (the Fortran cannot be built in this image) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE configs[1]: examples/sphere_peel/t4tau7.in
+    "sphere_peel_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0,
+                               nxfreq=201, nxim=129, nyim=129, distance=1e2, save_all_photons=False),
+    # the cell-by-cell core-skip variant of the same input
+    "sphere_peel_tau1e7_coreskip": dict(temperature=1e4, taumax=1e7, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0,
+                                        nxfreq=201, nxim=129, nyim=129, distance=1e2, core_skip=True),
+    # BASELINE configs[2]: examples/vel_effect_peel/t4NHI2_20_V0200.in
+    "vel_effect_peel": dict(temperature=1e4, N_HI=2e20, Vexp=200.0, velocity_type="hubble", xfreq_min=-200.0,
+                            xfreq_max=40.0, nxfreq=500, use_stokes=True, comoving_source=False, nx=201, ny=201, nz=201,
+                            rmax=1.0, nxim=129, nyim=129),
+    # BASELINE configs[0]: examples/slab/t4tau7.in
+    "slab_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xy_periodic=True, nx=1, ny=1, nz=201),
+    # small case for smoke-testing the bench itself
+    "tiny": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=61, nxim=33, nyim=33),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--workload", default="sphere_peel_tau1e7", choices=sorted(WORKLOADS))
+    ap.add_argument("--quantum", type=int, default=32, help="scatterings per photon slot per step")
+    ap.add_argument("--pool-slots", type=int, default=0, help="photons in flight per GPU (0 = auto: 148*8192)")
+    ap.add_argument("--flags", type=int, default=0, help="LART_FLAG_* bits (1 SoA grid, 2 no warp aggregation, 4 monolithic)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=12345)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "samples": len(self.rows),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_model(args, nphotons):
+    from lart_b200 import Model
+    return Model(no_photons=nphotons, iseed=args.seed, **WORKLOADS[args.workload]).setup()
+
+
+def cpu_sample(args, events_per_photon, seconds, threads=None):
+    """Time the CPU restatement (oracle, MT19937-64 like the reference) on a bounded sample of the
+    same workload: the first `events_per_photon` scatterings of n photons, n sized for ~`seconds`."""
+    from oracle import oracle
+    threads = threads or oracle.hardware_threads()
+    m = build_model(args, 10 ** 6)
+    n = 2 * threads
+    t0 = time.perf_counter()
+    oracle.run(m, rng_mode=0, nthreads=threads, first_id=1, count=n, max_events=events_per_photon, seed=args.seed)
+    dt = time.perf_counter() - t0
+    rate = m.counters["n_scatter"] / dt
+    n = int(max(threads, min(2_000_000, rate * seconds / max(events_per_photon, 1))))
+    n = (n // threads) * threads
+    m.zero_tallies()
+    t0 = time.perf_counter()
+    oracle.run(m, rng_mode=0, nthreads=threads, first_id=1, count=n, max_events=events_per_photon, seed=args.seed)
+    dt = time.perf_counter() - t0
+    c = m.counters
+    return {"value": c["n_scatter"] / dt, "unit": "scatterings/s", "cores": threads, "kind": "port",
+            "sample": "%s: first %d scatterings of %d photons on %d threads, %.1f s (C++ restatement of the reference loop, "
+                      "g++ -O3 -ffp-contract=off, MT19937-64; the Fortran+MPI build is impossible in this image)"
+                      % (args.workload, events_per_photon, n, threads, dt),
+            "cellsteps_per_s": c["n_cellsteps"] / dt, "seconds": dt, "photons": n}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ev = args.quantum
+    per_step = max(1.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        cpu_sample(args, ev, min(per_step, 2.0))
+    tot_s, tot_t, last = 0.0, 0.0, None
+    for _ in range(args.steps):
+        last = cpu_sample(args, ev, per_step)
+        tot_s += last["value"] * last["seconds"]
+        tot_t += last["seconds"]
+    v = tot_s / tot_t
+    cb = dict(last)
+    cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "scatterings_per_s", "value": v, "unit": "scatterings/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "quantum": args.quantum, "note": "CPU port of the reference loop; bounded sample per step"},
+        "cpu_baseline": cb, "e2e": {"value": v, "unit": "scatterings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from lart_b200 import Simulation, capi, measure_fp64
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    S_auto = args.pool_slots or 148 * 8192
+    total_steps = args.warmup + args.steps
+    nph = S_auto * world * 4  # far more ids than slots: the queue never runs dry, nobody finishes tau0 = 1e7 anyway
+    model = build_model(args, nph)
+    cfg = model.config.contents
+    g = cfg.grid
+    ncell = g.nx * g.ny * g.nz
+    grid_bytes = 8 * (6 * ncell + (g.nx + g.ny + g.nz + 3))
+
+    # ------------------------- device-resident arm: `value`
+    sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum,
+                     flags=args.flags | capi.FLAG_STAGE_TIMING)
+    S = sim.pool_slots
+    first, count, stride = rank + 1, nph // world, world  # run_simulation_mod.f90:150 partition
+    sim.begin(first, count, stride)
+    for _ in range(args.warmup):
+        sim.step(args.quantum)
+    sim.sync()
+    sim.reset_tallies()
+    barrier()
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sim.step(args.quantum)
+        sim.sync()
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_ms, launches = sim.kernel_ms()
+    stage = sim.stage_ms()
+    # counters of the timed region (tallies were reset after the warm-up)
+    model.zero_tallies()
+    sim._check(sim._lib.lart_gpu_fetch(sim._h, model.tallies))
+    c = dict(model.counters)
+    t = torch.tensor([dev_ms, c["n_scatter"], c["n_cellsteps"], c["n_peel"], c["n_photons_done"], c["n_rng"], float(launches)],
+                     dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    max_ms = float(tmax[0])
+    n_scatter, n_cell, n_peel, n_done, n_rng, n_launch = (float(t[i]) for i in range(1, 7))
+    value = n_scatter / (max_ms * 1e-3)
+
+    # ------------------------- FP64 issue peak + roofline of the dominant kernel (rank 0)
+    hbm_peak, peak_src = measured_peaks()
+    fp64_peak = measure_fp64(local)
+    dom = max(stage, key=lambda k: stage[k][0])
+    walk_ms = stage["trace"][0] + stage["peel"][0]
+    walk_n = stage["trace"][1] + stage["peel"][1]
+    steps_local = c["n_cellsteps"]
+    # algorithmic 48 B (six f64 grid values) per cell step — SURVEY.md §8(d); cell steps happen in trace + peel
+    ach = 48.0 * steps_local / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
+    flops = 50.0 * steps_local + 300.0 * c["n_scatter"]
+    roof = {"bound": "hbm", "kernel": "k_wf_trace+k_wf_peel (DDA cell walk)" if not (args.flags & 4) else "k_mono",
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "bytes_per_cellstep": 48, "cellsteps_per_launch": steps_local / max(walk_n, 1),
+            "avg_launch_ms": walk_ms / max(walk_n, 1),
+            "stage_ms_per_wave": {k: stage[k][0] / max(stage[k][1], 1) for k in stage},
+            "stage_share": {k: stage[k][0] / max(sum(v[0] for v in stage.values()), 1e-30) for k in stage},
+            "dominant_stage": dom,
+            "fp64": {"achieved_tflops": flops / (dev_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+                     "frac": flops / (dev_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                     "model": "50 flop/cell step + 300 flop/scattering (SURVEY.md 8d; libm calls not counted)",
+                     "peak_source": "measured DFMA loop (lart_gpu_measure_fp64)"}}
+    sim.close()
+
+    # ------------------------- end-to-end arm through the public API with HOST buffers: `e2e`
+    # timed: lart_gpu_create (H2D of the host grid arrays) + begin + steps (each followed by the D2H read of
+    # its result: photons in flight) + output_reduce (NCCL reduce of the tally buffer + D2H into the host tallies).
+    model.zero_tallies()
+    barrier()
+    t0 = time.perf_counter()
+    sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=args.flags)
+    sim.begin(first, count, stride)
+    for _ in range(total_steps):
+        sim.step(args.quantum)
+    sim.output_reduce(dst=0)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    buf_n = sim.tally_buffer()[1]
+    sim.close()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    ns = torch.tensor([model.counters["n_scatter"] if rank == 0 else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_scatter = float(ns[0])  # rank 0 holds the reduced counters of all ranks
+    if world > 1:
+        dist.broadcast(ns, src=0)
+        e2e_scatter = float(ns[0])
+    e2e_value = e2e_scatter / float(te[0])
+
+    if rank == 0:
+        out = {
+            "metric": "scatterings_per_s", "value": value, "unit": "scatterings/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "grid": [g.nx, g.ny, g.nz], "tau0": WORKLOADS[args.workload].get("taumax"),
+                       "peel_cube": [g.nxfreq, cfg.observers[0].nxim, cfg.observers[0].nyim] if cfg.par.nobs else None,
+                       "photons_in_flight_per_gpu": S, "quantum": args.quantum,
+                       "step": "every photon slot advances by `quantum` scatterings (waves of emit/trace/scatter/peel kernels)",
+                       "driver": "monolithic" if args.flags & 4 else "wavefront",
+                       "l2": "working set (cells %.0f MB + photon pool + ray queue + cubes) larger than the 126 MB L2; no flush"
+                             % (64.0 * ncell / 1e6),
+                       "parallelism": "photon ids strided over %d GPU(s); grid replicated; one NCCL reduce of the tally buffer" % world,
+                       "seed": args.seed},
+            "cellsteps_per_s": n_cell / (max_ms * 1e-3), "peel_rays_per_s": n_peel / (max_ms * 1e-3),
+            "photons_done": n_done, "uniforms_per_s": n_rng / (max_ms * 1e-3), "wall_s": wall,
+            "gpu_launches": int(n_launch), "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": "scatterings/s", "h2d_bytes_per_step": grid_bytes / total_steps,
+                    "d2h_bytes_per_step": (8 * buf_n + 8 * total_steps) / total_steps, "seconds": float(te[0]),
+                    "region": "lart_gpu_create(H2D host grid) + begin + %d steps (+D2H of each step's in-flight count) + "
+                              "NCCL reduce + D2H of the tally buffer into host arrays" % total_steps},
+            "clocks": clk.summary(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_sample(args, args.quantum, args.cpu_seconds)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

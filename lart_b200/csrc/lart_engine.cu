@@ -58,6 +58,8 @@ int fail(const std::string &msg) {
 
 constexpr int kVoigtTabN = 202 * 4;
 constexpr int kBlock = 256;
+constexpr int64_t kTailPhotons = 16384;  // lart_gpu_run: below this many photons left, finish with k_mono
+constexpr int kTailQuantum = 256;
 
 // ------------------------------- photon pool -------------------------------
 enum {
@@ -464,8 +466,8 @@ __global__ void __launch_bounds__(kBlock) k_wf_trace(const __grid_constant__ Dev
           nrng += rng.nrng;
           have = false;
         } else if (st == 2) {
+          load_rest(pl, slot, ph);  // before finish_escape: it writes ph.xfreq_ref
           cnt.cellsteps += finish_escape(P, ph, r);
-          load_rest(pl, slot, ph);
           retire_photon(P, ph, true, job, cnt);
           store_trace_part(pl, slot, ph);
           nrng += rng.nrng;
@@ -959,12 +961,12 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
   return 0;
 }
 
-int lart_gpu_step(lart_gpu_handle h, int32_t quantum, int64_t *in_flight) {
-  if (!h) return fail("lart_gpu_step: NULL handle");
-  if (!h->begun) return fail("lart_gpu_step: call lart_gpu_begin first");
-  CUDA_OK(cudaSetDevice(h->device));
-  const int qn = quantum > 0 ? quantum : h->quantum;
-  const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
+}  // extern "C"
+
+namespace {
+// One step with an explicit driver choice (both drivers share the pool layout, and no
+// slot is left mid-wave between steps, so they can alternate freely).
+int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
   const bool timing = (h->flags & LART_FLAG_STAGE_TIMING) != 0;
   size_t ne = 0;
   auto mark = [&]() -> int {  // one event between consecutive stage kernels
@@ -1028,6 +1030,17 @@ int lart_gpu_step(lart_gpu_handle h, int32_t quantum, int64_t *in_flight) {
   if (in_flight) *in_flight = (int64_t)h->count - (int64_t)j.done;
   return 0;
 }
+}  // namespace
+
+extern "C" {
+
+int lart_gpu_step(lart_gpu_handle h, int32_t quantum, int64_t *in_flight) {
+  if (!h) return fail("lart_gpu_step: NULL handle");
+  if (!h->begun) return fail("lart_gpu_step: call lart_gpu_begin first");
+  CUDA_OK(cudaSetDevice(h->device));
+  const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
+  return step_impl(h, quantum > 0 ? quantum : h->quantum, mono, in_flight);
+}
 
 int lart_gpu_sync(lart_gpu_handle h) {
   if (!h) return fail("lart_gpu_sync: NULL handle");
@@ -1039,9 +1052,14 @@ int lart_gpu_sync(lart_gpu_handle h) {
 
 int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride) {
   if (int rc = lart_gpu_begin(h, first_id, count, stride)) return rc;
+  const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int64_t left = count;
-  while (left > 0)
-    if (int rc = lart_gpu_step(h, 0, &left)) return rc;
+  while (left > 0) {
+    // Tail of a heavy-tailed run: with few photons left a wave is launch-latency bound (one scattering per
+    // ~5 launches), while one thread per photon runs `quantum` scatterings per launch.
+    const bool tail = !mono && left < kTailPhotons;
+    if (int rc = step_impl(h, tail ? kTailQuantum : h->quantum, mono || tail, &left)) return rc;
+  }
   return 0;
 }
 

@@ -24,8 +24,9 @@ def run_gpu(m, flags=0, **kw):
 
 
 def histories_equal(mg, mo, min_frac=0.995):
+    # weighted counts: wgt = 1 - exp(-tau0) carries CUDA-vs-glibc exp rounding, hence isclose, not ==
     ng, no = mg.allph("nscatt_gas"), mo.allph("nscatt_gas")
-    same = ng == no
+    same = np.isclose(ng, no, rtol=1e-12, atol=0)
     assert same.mean() >= min_frac, "identical histories: %.4f" % same.mean()
     for name in ("xfreq1", "xfreq2", "rp", "nscatt_dust", "I", "Q", "U", "V", "rp0"):
         a, b = mg.allph(name), mo.allph(name)
@@ -63,11 +64,12 @@ CASES = {
     "sphere_stokes_peel": dict(),
     "sphere_nostokes_peel2D": dict(use_stokes=False, save_peeloff_2D=True),
     "sphere_two_observers_direc0": dict(obsx=[0.0, 1.0], obsy=[0.0, 0.5], obsz=[1.0, 0.2], save_direc0=True, save_Jmu=True),
-    "hubble_lab_source_coreskip": dict(velocity_type="hubble", Vexp=200.0, N_HI=2e18, taumax=-999.0, comoving_source=False,
+    "hubble_lab_source_coreskip": dict(velocity_type="hubble", Vexp=200.0, N_HI=2e17, taumax=-999.0, comoving_source=False,
                                        core_skip=True, xfreq_min=-60.0, xfreq_max=20.0),
-    "thick_core_skip_recoil": dict(taumax=1e5, core_skip=True, recoil=True, no_photons=300),
-    "dust_hg_nostokes": dict(use_stokes=False, DGR=1.0, cext_dust=3e-21, taumax=-999.0, N_HI=1e19, no_photons=1500),
-    "dust_reduced_wgt": dict(use_stokes=False, DGR=1.0, cext_dust=3e-21, taumax=-999.0, N_HI=1e19, use_reduced_wgt=True,
+    "thick_core_skip_recoil": dict(taumax=1e4, core_skip=True, recoil=True, no_photons=300),
+    # tau0 ~ 1.2e3, tau_dust ~ 0.6: about one dust interaction per photon
+    "dust_hg_nostokes": dict(use_stokes=False, DGR=1.0, cext_dust=3e-17, taumax=-999.0, N_HI=2e16, no_photons=1500),
+    "dust_reduced_wgt": dict(use_stokes=False, DGR=1.0, cext_dust=3e-17, taumax=-999.0, N_HI=2e16, use_reduced_wgt=True,
                              no_photons=1500),
     "slab_zonly": dict(xy_periodic=True, nx=1, ny=1, nz=201, rmax=-999.0, taumax=1e3, nxim=0, nyim=0, nxfreq=121),
     "uniform_sphere_source_continuum": dict(source_geometry="uniform_sphere", spectral_type="continuum", taumax=10.0),
@@ -96,11 +98,11 @@ def test_dust_stokes_mueller_table(tmp_path):
     mu = np.linspace(-1, 1, 81)
     f = tmp_path / "mueller.dat"
     with open(f, "w") as fh:
-        fh.write("lambda(um), Cext(cm^2/H), albedo, <cos>, # of angles\n 0.1216 3.0e-21 0.6 0.3 81\ncos S11 S12 S33 S34\n")
+        fh.write("lambda(um), Cext(cm^2/H), albedo, <cos>, # of angles\n 0.1216 3.0e-17 0.6 0.3 81\ncos S11 S12 S33 S34\n")
         for c in mu:
             s11 = 0.75 * (1 + c * c) * (1 + 0.6 * c)
             fh.write("%.6f %.10e %.10e %.10e %.10e\n" % (c, s11, -0.75 * (1 - c * c) * 0.8, 1.5 * c * 0.9, 0.05 * (1 - c * c)))
-    kw = dict(DGR=1.0, scatt_mat_file=str(f), taumax=-999.0, N_HI=1e19, no_photons=1500)
+    kw = dict(DGR=1.0, scatt_mat_file=str(f), taumax=-999.0, N_HI=2e16, no_photons=1500)
     mg, mo = small_sphere(**kw), small_sphere(**kw)
     assert mg.config.contents.scatt_mat.nPDF == 81 and mg.config.contents.par.albedo == 0.6
     run_gpu(mg, pool_slots=4096)
@@ -115,8 +117,8 @@ def test_results_do_not_depend_on_pool_size_or_scheduling():
     b = run_gpu(small_sphere(), pool_slots=8192, quantum=16)
     c = run_gpu(small_sphere(), flags=capi.FLAG_MONOLITHIC | capi.FLAG_SOA_GRID | capi.FLAG_NO_WARP_AGG, pool_slots=512)
     for name in ("nscatt_gas", "xfreq2", "rp", "Q", "U"):
-        assert np.array_equal(a.allph(name), b.allph(name)), name
-        assert np.array_equal(a.allph(name), c.allph(name)), name
+        assert np.array_equal(a.allph(name), b.allph(name)), name      # same driver: bit-identical
+        assert np.allclose(a.allph(name), c.allph(name), rtol=1e-9, atol=1e-12), name  # other driver: other FMA contraction
     assert np.allclose(a.observer_cube("I"), b.observer_cube("I"), rtol=1e-10, atol=1e-18)
     assert np.allclose(a.observer_cube("Q"), c.observer_cube("Q"), rtol=1e-9, atol=1e-16)
 
@@ -131,6 +133,7 @@ def test_rank_partition_sums_to_single_run():
         sim.output_reduce()
         sim.close()
     assert np.array_equal(m.allph("nscatt_gas"), full.allph("nscatt_gas"))
+    assert np.array_equal(m.allph("xfreq2"), full.allph("xfreq2"))
     assert np.allclose(m.spectrum("Jout"), full.spectrum("Jout"), rtol=1e-12)
     assert np.allclose(m.observer_cube("scatt"), full.observer_cube("scatt"), rtol=1e-9, atol=1e-18)
 
@@ -194,17 +197,17 @@ def neufeld_slab(x, a, tau0):
 
 
 def test_slab_matches_neufeld_solution():
-    # examples/slab geometry (1x1x201, xy_periodic); T = 10 K, tau0 = 1e6 -> a*tau0 = 1.5e4
+    # examples/slab geometry (1x1x201, xy_periodic); T = 10 K, tau0 = 1e5 -> a*tau0 = 1.5e3
     n = 20000
-    m = Model(no_photons=n, temperature=10.0, taumax=1e6, xy_periodic=True, nx=1, ny=1, nz=201, nxfreq=80,
-              xfreq_min=-60.0, xfreq_max=60.0, spectral_type="monochromatic", use_stokes=True, iseed=5).setup()
+    m = Model(no_photons=n, temperature=10.0, taumax=1e5, xy_periodic=True, nx=1, ny=1, nz=201, nxfreq=80,
+              xfreq_min=-30.0, xfreq_max=30.0, spectral_type="monochromatic", use_stokes=True, iseed=5).setup()
     run_gpu(m)
     m.output_normalize()
     x, J, s = m.xfreq(), m.spectrum("Jout"), m.summary
     assert J.sum() * s.dxfreq == pytest.approx(1 / (4 * np.pi), rel=1e-6)
-    ana = neufeld_slab(x, s.voigt_a, 1e6)
+    ana = neufeld_slab(x, s.voigt_a, 1e5)
     peak_mc = np.abs(x[np.argmax(J)])
-    peak_ana = 1.066 * (s.voigt_a * 1e6) ** (1 / 3)
+    peak_ana = 1.066 * (s.voigt_a * 1e5) ** (1 / 3)
     assert peak_mc == pytest.approx(peak_ana, rel=0.12)
     # bin-wise agreement where the analytic curve carries signal (finite a*tau0 -> few % systematic)
     sel = ana > 0.25 * ana.max()
@@ -247,7 +250,7 @@ def test_edge_cases_and_errors():
     run_gpu(m, pool_slots=64)
     oracle.run(mo, rng_mode=1)
     assert m.counters["n_photons_done"] == 512
-    assert (m.allph("nscatt_gas") == mo.allph("nscatt_gas")).mean() > 0.99
+    assert np.isclose(m.allph("nscatt_gas"), mo.allph("nscatt_gas"), rtol=1e-12).mean() > 0.99
     # error behaviour: status code + message, no exception across the ABI
     bad = small_sphere()
     bad.config.contents.line.line_type = 2

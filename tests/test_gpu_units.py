@@ -155,9 +155,10 @@ def test_rand_resonance_vz_matches_oracle_streams(x0, a):
     ids = np.arange(1, 20001, dtype=np.int64)
     g = sample(2, 7, ids, x0, a, ndraw=4)
     o = oracle.sample(2, 7, ids, x0, a, ndraw=4)
-    close = np.isclose(g, o, rtol=1e-9, atol=1e-12)
-    # a last-bit difference in exp/log/atan can flip an accept/reject decision: rare, and then the stream shifts
-    assert close.mean() > 0.999, (x0, a, close.mean())
+    # u = x0 + a*tan(theta) cancels when the atom is nearly at rest (|u| << x0): an ulp of x0 on |u| ~ 1e-3,
+    # amplified by theta sitting ~a/x0 from the pole of tan -> absolute agreement ~1e-10, relative elsewhere
+    close = np.isclose(g, o, rtol=1e-9, atol=2e-10 * max(1.0, abs(x0)))
+    assert close.mean() > 0.9995, (x0, a, close.mean())
     # and the distributions agree regardless (two-sample KS against the oracle's MT19937-64 stream)
     from scipy.stats import ks_2samp
     mt = oracle.sample(2, 99, ids, x0, a, ndraw=4, rng_mode=0)

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--flags", type=int, default=0, help="LART_FLAG_* bits (1 SoA grid, 2 no warp aggregation, 4 monolithic)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="device-resident arm only (profiling runs)")
     ap.add_argument("--seed", type=int, default=12345)
     return ap.parse_args()
 
@@ -249,15 +250,17 @@ def run_gpu(args):
     model.zero_tallies()
     barrier()
     t0 = time.perf_counter()
-    sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=args.flags)
-    sim.begin(first, count, stride)
-    for _ in range(total_steps):
-        sim.step(args.quantum)
-    sim.output_reduce(dst=0)
-    barrier()
+    buf_n = 0
+    if not args.skip_e2e:
+        sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=args.flags)
+        sim.begin(first, count, stride)
+        for _ in range(total_steps):
+            sim.step(args.quantum)
+        sim.output_reduce(dst=0)
+        barrier()
+        buf_n = sim.tally_buffer()[1]
+        sim.close()
     e2e_s = time.perf_counter() - t0
-    buf_n = sim.tally_buffer()[1]
-    sim.close()
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     ns = torch.tensor([model.counters["n_scatter"] if rank == 0 else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -93,10 +93,10 @@ enum { A_RP0 = 0, A_RP, A_XFREQ1, A_XFREQ2, A_NSG, A_NSD, A_I, A_Q, A_U, A_V };
 LART_DEV void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;  // hi|lo in one IMAD.WIDE.U32
+    unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
@@ -106,36 +106,39 @@ struct Counters {
   unsigned long long scatter = 0, cellsteps = 0, peel = 0, rng = 0, reject = 0, photons = 0;
 };
 
+// Stream layout (shared with the CPU oracle): every call consumes ONE Philox block of
+// the photon's stream — uniform() uses its first 64-bit word, uniform2() both.  There
+// is no buffered half-block, so lanes never diverge on "do I need a new block?" and
+// the only generator state that travels with a photon is the block counter.
 struct Rng {
-  unsigned long long seed, stream, ndraw, spare;
+  unsigned long long seed, stream, nblk;
   unsigned long long nrng;  // uniforms drawn through this object (work counter)
   bool gauss_stored;
   double gset;
-  LART_DEV void start(unsigned long long seed_, unsigned long long id, unsigned long long ndraw_ = 0) {
-    seed = seed_; stream = id; ndraw = ndraw_; gauss_stored = false; gset = 0.0; nrng = 0; spare = 0;
-    if (ndraw & 1ULL) {  // resume in the middle of a block: regenerate the second word
-      uint32_t c0, c1, c2, c3;
-      block(ndraw >> 1, c0, c1, c2, c3);
-      spare = (unsigned long long)c2 | ((unsigned long long)c3 << 32);
-    }
+  LART_DEV void start(unsigned long long seed_, unsigned long long id, unsigned long long nblk_ = 0) {
+    seed = seed_; stream = id; nblk = nblk_; gauss_stored = false; gset = 0.0; nrng = 0;
   }
-  LART_DEV void block(unsigned long long blk, uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3) const {
-    c0 = (uint32_t)stream; c1 = (uint32_t)(stream >> 32); c2 = (uint32_t)blk; c3 = (uint32_t)(blk >> 32);
+  LART_DEV void block(unsigned long long &w0, unsigned long long &w1) {
+    uint32_t c0 = (uint32_t)stream, c1 = (uint32_t)(stream >> 32), c2 = (uint32_t)nblk, c3 = (uint32_t)(nblk >> 32);
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    w0 = (unsigned long long)c0 | ((unsigned long long)c1 << 32);
+    w1 = (unsigned long long)c2 | ((unsigned long long)c3 << 32);
+    ++nblk;
+  }
+  static LART_DEV double open01(unsigned long long w) {
+    return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
   }
   LART_DEV double uniform() {
-    unsigned long long w;
-    if ((ndraw & 1ULL) == 0) {
-      uint32_t c0, c1, c2, c3;
-      block(ndraw >> 1, c0, c1, c2, c3);
-      w = (unsigned long long)c0 | ((unsigned long long)c1 << 32);
-      spare = (unsigned long long)c2 | ((unsigned long long)c3 << 32);
-    } else {
-      w = spare;
-    }
-    ++ndraw;
-    ++nrng;
-    return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+    unsigned long long w0, w1;
+    block(w0, w1);
+    nrng += 1;
+    return open01(w0);
+  }
+  LART_DEV void uniform2(double &a, double &b) {
+    unsigned long long w0, w1;
+    block(w0, w1);
+    nrng += 2;
+    a = open01(w0); b = open01(w1);
   }
   // rand_gauss1 — random_mt.f90:964-988 (Marsaglia polar; the spare deviate is kept
   // per photon stream, never shared between photons)
@@ -143,8 +146,9 @@ struct Rng {
     if (gauss_stored) { gauss_stored = false; return gset; }
     double v1, v2, rsq;
     for (;;) {
-      v1 = 2.0 * uniform() - 1.0;
-      v2 = 2.0 * uniform() - 1.0;
+      uniform2(v1, v2);
+      v1 = 2.0 * v1 - 1.0;
+      v2 = 2.0 * v2 - 1.0;
       rsq = v1 * v1 + v2 * v2;
       ++nreject;
       if (rsq > 0.0 && rsq < 1.0) break;
@@ -238,24 +242,20 @@ struct Ray {
 
 LART_DEV bool axis_setup(double k, double p, int &cell, int n, const double *face, double d, int &step, double &t,
                          double &del, bool eq_test) {
-  if (k > 0.0) {
-    if (cell > n) {
-      double f = __ldg(face + cell - 1);
-      if (eq_test ? (f == p) : (f <= p)) return true;
-    }
-    step = 1;
-    t = DSUB(__ldg(face + cell), p) / k;
-    del = d / k;
-  } else if (k < 0.0) {
-    if (__ldg(face + cell - 1) == p) {
-      if (cell > 1) cell -= 1; else return true;
-    }
-    step = -1;
-    t = DSUB(__ldg(face + cell - 1), p) / k;
-    del = -d / k;
-  } else {
-    step = 0; t = kHugest; del = kHugest;
+  if (k == 0.0) { step = 0; t = kHugest; del = kHugest; return false; }
+  const bool pos = k > 0.0;
+  // the special cases first (raytrace_car.f90:27-44): already outside (k>0), or sitting on the lower face (k<0)
+  double flo = __ldg(face + cell - 1);
+  if (pos) {
+    if (cell > n && (eq_test ? (flo == p) : (flo <= p))) return true;
+  } else if (flo == p) {
+    if (cell > 1) { cell -= 1; flo = __ldg(face + cell - 1); } else return true;
   }
+  // one branch-free path for both signs: -d/k == d/|k| bit for bit
+  step = pos ? 1 : -1;
+  double f = pos ? __ldg(face + cell) : flo;
+  t = DSUB(f, p) / k;
+  del = d / fabs(k);
   return false;
 }
 
@@ -376,9 +376,11 @@ LART_DEV double rand_resonance_vz(Rng &r, double x0in, double a, unsigned long l
   double x0 = fabs(x0in), vz;
   if (x0 <= 1.0) {  // :2579-2585
     for (;;) {
-      vz = x0 + a * tan(kPi * (r.uniform() - 0.5));
+      double u1, u2;
+      r.uniform2(u1, u2);
+      vz = x0 + a * tan(kPi * (u1 - 0.5));
       ++nrej;
-      if (r.uniform() <= exp(-vz * vz)) break;
+      if (u2 <= exp(-vz * vz)) break;
     }
     return (x0in < 0.0) ? -vz : vz;
   }
@@ -410,21 +412,22 @@ LART_DEV double rand_resonance_vz(Rng &r, double x0in, double a, unsigned long l
   }
   double t1, delt;
   for (;;) {
-    double beta, Cb;
+    double beta, Cb, ua, ub, uacc;
+    r.uniform2(ua, ub);
     if (mode == 0) {
-      beta = lo1 + w1 * r.uniform(); Cb = c1;
+      beta = lo1 + w1 * ua; Cb = c1; uacc = ub;
     } else {
-      double rs = r.uniform();
-      if (rs < p0) { beta = beta0 * sqrt(r.uniform()); Cb = beta / a; }
-      else if (mode == 1 || rs < p01) { beta = lo1 + w1 * r.uniform(); Cb = c1; }
-      else { beta = lo2 + w2 * r.uniform(); Cb = c2; }
+      if (ua < p0) { beta = beta0 * sqrt(ub); Cb = beta / a; }
+      else if (mode == 1 || ua < p01) { beta = lo1 + w1 * ub; Cb = c1; }
+      else { beta = lo2 + w2 * ub; Cb = c2; }
+      uacc = r.uniform();
     }
     double pb = sqrt(-2.0 * log(beta));
     double t2 = atan((pb - x0) / a);
     t1 = atan((-pb - x0) / a);
     delt = t2 - t1;
     ++nrej;
-    if (r.uniform() * Cb < (beta / api) * delt) break;
+    if (uacc * Cb < (beta / api) * delt) break;
   }
   vz = x0 + a * tan(delt * r.uniform() + t1);  // :2693
   return (x0in < 0.0) ? -vz : vz;
@@ -463,8 +466,10 @@ LART_DEV double rand_voigt(Rng &r, double a, unsigned long long &nrej) {
 // rand_alias_linear64 — random_mt.f90:2196-2216
 LART_DEV double rand_alias_linear(Rng &r, const DevParams &P) {
   int n = P.nPDF - 1;
-  int k = (int)floor(n * r.uniform()) + 1;
-  int idx = (r.uniform() < P.sm_pdf[k - 1]) ? k : P.sm_alias[k - 1];
+  double uk, ua;
+  r.uniform2(uk, ua);
+  int k = (int)floor(n * uk) + 1;
+  int idx = (ua < P.sm_pdf[k - 1]) ? k : P.sm_alias[k - 1];
   double p0 = P.sm_S11[idx - 1], p1 = P.sm_S11[idx];
   double x0 = P.sm_coss[idx - 1], x1 = P.sm_coss[idx];
   return (sqrt(p0 * p0 + (p1 * p1 - p0 * p0) * r.uniform()) - p0) * (x1 - x0) / (p1 - p0) + x0;
@@ -525,6 +530,23 @@ struct PeelRay {
   int obs, pix, ixf, kind;  // pix = (ix-1)+nxim*(iy-1); ixf 1-based or 0 when outside the cube
 };
 
+// atan2(y, x) for the TAN pixel (peelingoff_rect.f90:356-357).  A distant observer sees the
+// whole grid within a few degrees: for x > 0 and |y/x| < 1/16 the Maclaurin series to t^15
+// is exact to double rounding (next term t^17/17 < 2e-22 relative); anything else takes atan2.
+LART_DEV double pixel_angle(double y, double x) {
+  if (x > 0.0 && fabs(y) < 0.0625 * x) {
+    double t = y / x, t2 = t * t;
+    double p = fma(t2, -1.0 / 15.0, 1.0 / 13.0);
+    p = fma(t2, p, -1.0 / 11.0);
+    p = fma(t2, p, 1.0 / 9.0);
+    p = fma(t2, p, -1.0 / 7.0);
+    p = fma(t2, p, 1.0 / 5.0);
+    p = fma(t2, p, -1.0 / 3.0);
+    return fma(t * t2, p, t);
+  }
+  return atan2(y, x);
+}
+
 // common head of every peeling routine (peelingoff_rect.f90:44-61 / :326-357 / :595-627)
 LART_DEV bool peel_geometry(const DevObserver &ob, const Photon &ph, PeelRay &pr, double &r2) {
   double kx = ob.x - ph.x, ky = ob.y - ph.y, kz = ob.z - ph.z;
@@ -537,8 +559,8 @@ LART_DEV bool peel_geometry(const DevObserver &ob, const Photon &ph, PeelRay &pr
   double ox = R[0] * kx + R[3] * ky + R[6] * kz;
   double oy = R[1] * kx + R[4] * ky + R[7] * kz;
   double oz = R[2] * kx + R[5] * ky + R[8] * kz;
-  int ix = (int)floor(atan2(-ox, oz) * kRad2Deg / ob.dxim + ob.nxim / 2.0) + 1;
-  int iy = (int)floor(atan2(-oy, oz) * kRad2Deg / ob.dyim + ob.nyim / 2.0) + 1;
+  int ix = (int)floor(pixel_angle(-ox, oz) * kRad2Deg / ob.dxim + ob.nxim / 2.0) + 1;
+  int iy = (int)floor(pixel_angle(-oy, oz) * kRad2Deg / ob.dyim + ob.nyim / 2.0) + 1;
   pr.pix = (ix - 1) + ob.nxim * (iy - 1);
   return ix >= 1 && ix <= ob.nxim && iy >= 1 && iy <= ob.nyim;
 }
@@ -713,6 +735,11 @@ LART_DEV void peel_deposit(const DevParams &P, const PeelRay &pr, double tau, un
     double w = pr.wa * e * pr.wb;
     v[0] = w * pr.sI; v[1] = w * pr.sQ; v[2] = w * pr.sU; v[3] = w * pr.sV; nv = 4;
   } else { v[0] = pr.wa * e * pr.wb; nv = 1; }
+  // A ray that ran into the tau cap (745.2) carries exp(-tau) == 0: all its contributions are exact
+  // zeros, which never change a sum (the reference adds them; the result is the same).
+  const bool nonzero = (v[0] != 0.0) | (v[1] != 0.0) | (v[2] != 0.0) | (v[3] != 0.0);
+  lanes = __ballot_sync(lanes, nonzero);
+  if (!nonzero) return;
   bool leader = true;
   if (P.warp_agg) {
     unsigned long long key = ((unsigned long long)(unsigned)pr.kind << 60) ^ ((unsigned long long)(unsigned)pr.obs << 44) ^
@@ -721,16 +748,25 @@ LART_DEV void peel_deposit(const DevParams &P, const PeelRay &pr, double tau, un
     int lane = threadIdx.x & 31;
     int lead = __ffs(grp) - 1;
     leader = lane == lead;
-    unsigned rest = leader ? (grp & ~(1u << lead)) : 0u;  // lanes whose values the leader still has to add
-    int maxpop = __reduce_max_sync(lanes, (unsigned)__popc(rest));
-    for (int it = 0; it < maxpop; ++it) {
-      bool take = rest != 0u;
-      int src = take ? (__ffs(rest) - 1) : lane;
-      rest &= rest - 1u;
+    if (__all_sync(lanes, grp == 0xffffffffu)) {
+      // the whole warp hits one bin: plain butterfly
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        double o = __shfl_sync(lanes, v[q], src);
-        if (take && q < nv) v[q] += o;
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+      }
+    } else {
+      unsigned rest = leader ? (grp & ~(1u << lead)) : 0u;  // lanes whose values the leader still has to add
+      int maxpop = __reduce_max_sync(lanes, (unsigned)__popc(rest));
+      for (int it = 0; it < maxpop; ++it) {
+        bool take = rest != 0u;
+        int src = take ? (__ffs(rest) - 1) : lane;
+        rest &= rest - 1u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          double o = __shfl_sync(lanes, v[q], src);
+          if (take && q < nv) v[q] += o;
+        }
       }
     }
   }
@@ -795,20 +831,21 @@ LART_DEV void rotate_k(Photon &ph, double cost, double sint, double cosp, double
     ph.kz = cost * kz1 - sint * cosp * kr;
   }
 }
-// azimuth by rejection — scattering_car.f90:364-371 / :280-287
-LART_DEV double sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11, unsigned long long &nrej) {
-  double phi;
+// azimuth by rejection — scattering_car.f90:364-371 / :280-287.  cos(2phi), sin(2phi) come
+// from the double-angle identities of (cos phi, sin phi) = sincospi(2 xi): one libm call per trial.
+LART_DEV void sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11, unsigned long long &nrej, double &cosp,
+                                double &sinp) {
   double env = 1.0 + fabs(S12overS11) * sqrt(ph.Q * ph.Q + ph.U * ph.U);
   for (;;) {
-    phi = kTwoPi * r.uniform();
-    double s2, c2;
-    sincos(2.0 * phi, &s2, &c2);
-    double Prand = env * r.uniform();
+    double u1, u2;
+    r.uniform2(u1, u2);
+    sincospi(2.0 * u1, &sinp, &cosp);
+    double c2 = 2.0 * cosp * cosp - 1.0, s2 = 2.0 * sinp * cosp;
+    double Prand = env * u2;
     double Pcomp = 1.0 + S12overS11 * (ph.Q * c2 + ph.U * s2);
     ++nrej;
     if (Prand <= Pcomp) break;
   }
-  return phi;
 }
 
 // Outcome of one scattering event: what the peel stage needs.
@@ -832,9 +869,9 @@ LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const Ce
   double cost2 = cost * cost;
   double S22 = 0.75 * P.E1 * (cost2 + 1.0), S11 = S22 + P.E2, S12 = 0.75 * P.E1 * (cost2 - 1.0);
   double S33 = 1.5 * P.E1 * cost, S44 = 1.5 * P.E3 * cost;
-  double phi = P.use_stokes ? sample_phi_stokes(r, ph, S12 / S11, cnt.reject) : kTwoPi * r.uniform();
   double cosp, sinp;
-  sincos(phi, &sinp, &cosp);
+  if (P.use_stokes) sample_phi_stokes(r, ph, S12 / S11, cnt.reject, cosp, sinp);
+  else sincospi(2.0 * r.uniform(), &sinp, &cosp);
   double xc = 0.0, xc2 = 0.0;
   if (P.core_skip) car_xcrit_local(P, ph.ic, ph.jc, ph.kc, ph.x, ph.y, ph.z, cs.voigt_a, cs.rhokap, xc, xc2);
   bool skip = P.core_skip && fabs(ph.xfreq) < xc;
@@ -844,10 +881,11 @@ LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const Ce
     ux = r.gauss(cnt.reject) * one_over_sqrt2;
     uy = r.gauss(cnt.reject) * one_over_sqrt2;
   } else {  // :397-401 / :749-752
-    double phi2 = kTwoPi * r.uniform();
-    double uxy = skip ? sqrt(xc2 - log(r.uniform())) : sqrt(-log(r.uniform()));
+    double u1, u2;
+    r.uniform2(u1, u2);
+    double uxy = skip ? sqrt(xc2 - log(u2)) : sqrt(-log(u2));
     double s2, c2;
-    sincos(phi2, &s2, &c2);
+    sincospi(2.0 * u1, &s2, &c2);
     ux = uxy * c2; uy = uxy * s2;
   }
   ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
@@ -895,9 +933,8 @@ LART_DEV void scatter_dust(const DevParams &P, Photon &ph, Rng &r, const CellDat
     double sint = sqrt(1.0 - cost * cost);
     double S11 = interp_eq(P.sm_coss, P.sm_S11, P.nPDF, cost), S12 = interp_eq(P.sm_coss, P.sm_S12, P.nPDF, cost);
     double S33 = interp_eq(P.sm_coss, P.sm_S33, P.nPDF, cost), S34 = interp_eq(P.sm_coss, P.sm_S34, P.nPDF, cost);
-    double phi = sample_phi_stokes(r, ph, S12 / S11, cnt.reject);
     double cosp, sinp;
-    sincos(phi, &sinp, &cosp);
+    sample_phi_stokes(r, ph, S12 / S11, cnt.reject, cosp, sinp);
     double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
     double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
     double I1 = S11 + S12 * Q0, Q1 = S12 + S11 * Q0, U1 = S33 * U0 + S34 * ph.V, V1 = -S34 * U0 + S33 * ph.V;
@@ -906,9 +943,8 @@ LART_DEV void scatter_dust(const DevParams &P, Photon &ph, Rng &r, const CellDat
   } else {
     double cost = rand_hg(r, P.hgg);
     double sint = sqrt(1.0 - cost * cost);
-    double phi = kTwoPi * r.uniform();
     double cosp, sinp;
-    sincos(phi, &sinp, &cosp);
+    sincospi(2.0 * r.uniform(), &sinp, &cosp);
     rotate_k(ph, cost, sint, cosp, sinp);
   }
 }
@@ -919,24 +955,29 @@ LART_DEV void scatter_dust(const DevParams &P, Photon &ph, Rng &r, const CellDat
 // ---------------------------------------------------------------------------
 LART_DEV void generate_photon(const DevParams &P, Photon &ph, Rng &r, Counters &cnt, CellData &cs) {
   if (P.source_geometry == 2) {  // uniform_sphere :34-42
-    double rp = cbrt(r.uniform()) * P.source_rmax;
-    double cost = 2.0 * r.uniform() - 1.0, sint = sqrt(1.0 - cost * cost), phi = kTwoPi * r.uniform();
+    double u1, u2;
+    r.uniform2(u1, u2);
+    double rp = cbrt(u1) * P.source_rmax;
+    double cost = 2.0 * u2 - 1.0, sint = sqrt(1.0 - cost * cost);
     double sp, cp;
-    sincos(phi, &sp, &cp);
+    sincospi(2.0 * r.uniform(), &sp, &cp);
     ph.x = rp * sint * cp; ph.y = rp * sint * sp; ph.z = rp * cost;
   } else if (P.source_geometry == 1) {  // uniform :50-54
-    ph.x = (P.xmax - P.xmin) * r.uniform() + P.xmin;
-    ph.y = (P.ymax - P.ymin) * r.uniform() + P.ymin;
+    double u1, u2;
+    r.uniform2(u1, u2);
+    ph.x = (P.xmax - P.xmin) * u1 + P.xmin;
+    ph.y = (P.ymax - P.ymin) * u2 + P.ymin;
     ph.z = (P.zmax - P.zmin) * r.uniform() + P.zmin;
   } else {  // point :126-131
     ph.x = P.xs; ph.y = P.ys; ph.z = P.zs;
   }
   ph.wgt = 1.0;
-  double cost = 2.0 * r.uniform() - 1.0;
+  double uc, up;
+  r.uniform2(uc, up);
+  double cost = 2.0 * uc - 1.0;
   double sint = sqrt(1.0 - cost * cost);
-  double phi = kTwoPi * r.uniform();
   double cosp, sinp;
-  sincos(phi, &sinp, &cosp);
+  sincospi(2.0 * up, &sinp, &cosp);
   ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
   ph.ic = (int)floor((ph.x - P.xmin) / P.dx) + 1;
   ph.jc = (int)floor((ph.y - P.ymin) / P.dy) + 1;

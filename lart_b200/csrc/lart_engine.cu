@@ -118,11 +118,11 @@ __device__ __forceinline__ void store_all(const Pool &pl, int s, const Photon &p
   pl.id[s] = ph.id;
 }
 __device__ __forceinline__ void load_rng(const DevParams &P, const Pool &pl, int s, long long id, int flags, Rng &r) {
-  r.start(P.seed, (unsigned long long)id, pl.ndraw[s]);
+  r.start(P.seed, (unsigned long long)id, pl.ndraw[s]);  // ndraw = Philox blocks consumed so far
   if (flags & PH_GAUSS) { r.gauss_stored = true; r.gset = pl.f[(size_t)F_GSET * pl.S + s]; }
 }
 __device__ __forceinline__ void store_rng(const Pool &pl, int s, const Rng &r, int &flags) {
-  pl.ndraw[s] = r.ndraw;
+  pl.ndraw[s] = r.nblk;
   if (r.gauss_stored) { flags |= PH_GAUSS; pl.f[(size_t)F_GSET * pl.S + s] = r.gset; }
   else flags &= ~PH_GAUSS;
 }
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
 }
 
 // stage 2: raytrace_to_tau for every live photon, per-lane refill
-__global__ void __launch_bounds__(kBlock) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+__global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_trace(const __grid_constant__ Dev
           ph.flags |= PH_SCATTER;
           cnt.cellsteps += r.nsteps;
           store_trace_part(pl, slot, ph);
-          pl.ndraw[slot] = rng.ndraw;
+          pl.ndraw[slot] = rng.nblk;
           nrng += rng.nrng;
           have = false;
         } else if (st == 2) {
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_trace(const __grid_constant__ Dev
 
 // stage 3: scattering for every photon flagged by the trace stage; writes the
 // peel-ray descriptors of its slot
-__global__ void __launch_bounds__(kBlock) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+__global__ void __launch_bounds__(kBlock, 2) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   if (P.dust) load_vtab(P, vtab);
   Counters cnt;
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_scatter(const __grid_constant__ D
 }
 
 // stage 4: raytrace_to_edge for every queued peel ray, per-lane refill, deposit
-__global__ void __launch_bounds__(kBlock) k_wf_peel(const __grid_constant__ DevParams P, Queues q) {
+__global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ DevParams P, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;

@@ -118,11 +118,16 @@ struct Counters {
 // rand_number() + rand_gauss() state.  MT mode keeps the Marsaglia spare across
 // photons like the Fortran `save` variable (random_mt.f90:968-987); Philox mode
 // restarts stream and spare for every photon.
+//
+// Philox stream layout (shared with the GPU engine): every call consumes ONE
+// Philox block of the photon's stream — uniform() uses its first 64-bit word,
+// uniform2() both words.  Call sites that need two uniforms at the same program
+// point use uniform2(); in MT mode it is simply two consecutive rand_number()
+// calls, so the MT sequence is the reference's own draw order.
 struct Rng {
   int mode = 0;  // 0 = MT19937-64, 1 = Philox
   Mt64 mt;
-  uint64_t seed = 0, stream = 0, ndraw = 0;
-  uint64_t spare_word = 0;
+  uint64_t seed = 0, stream = 0, nblk = 0;
   bool gauss_stored = false;
   double gset = 0.0;
   Counters *cnt = nullptr;
@@ -130,26 +135,36 @@ struct Rng {
   void start_stream(uint64_t id) {
     if (mode == 1) {
       stream = id;
-      ndraw = 0;
+      nblk = 0;
       gauss_stored = false;
     }
+  }
+  void block(uint64_t &w0, uint64_t &w1) {
+    uint32_t c[4] = {static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32),
+                     static_cast<uint32_t>(nblk), static_cast<uint32_t>(nblk >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    w0 = static_cast<uint64_t>(c[0]) | (static_cast<uint64_t>(c[1]) << 32);
+    w1 = static_cast<uint64_t>(c[2]) | (static_cast<uint64_t>(c[3]) << 32);
+    ++nblk;
   }
   double uniform() {
     if (cnt) cnt->n_rng += 1;
     if (mode == 0) return word_to_open01(mt.next());
-    uint64_t w;
-    if ((ndraw & 1ULL) == 0) {
-      uint64_t blk = ndraw >> 1;
-      uint32_t c[4] = {static_cast<uint32_t>(stream), static_cast<uint32_t>(stream >> 32),
-                       static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32)};
-      philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-      w = static_cast<uint64_t>(c[0]) | (static_cast<uint64_t>(c[1]) << 32);
-      spare_word = static_cast<uint64_t>(c[2]) | (static_cast<uint64_t>(c[3]) << 32);
-    } else {
-      w = spare_word;
+    uint64_t w0, w1;
+    block(w0, w1);
+    return word_to_open01(w0);
+  }
+  void uniform2(double &a, double &b) {
+    if (cnt) cnt->n_rng += 2;
+    if (mode == 0) {
+      a = word_to_open01(mt.next());
+      b = word_to_open01(mt.next());
+      return;
     }
-    ++ndraw;
-    return word_to_open01(w);
+    uint64_t w0, w1;
+    block(w0, w1);
+    a = word_to_open01(w0);
+    b = word_to_open01(w1);
   }
   // rand_gauss1 — random_mt.f90:964-988 (Marsaglia polar, returns v2*f, stores v1*f)
   double gauss() {
@@ -159,8 +174,9 @@ struct Rng {
     }
     double v1, v2, rsq;
     for (;;) {
-      v1 = 2.0 * uniform() - 1.0;
-      v2 = 2.0 * uniform() - 1.0;
+      uniform2(v1, v2);
+      v1 = 2.0 * v1 - 1.0;
+      v2 = 2.0 * v2 - 1.0;
       rsq = v1 * v1 + v2 * v2;
       if (cnt) cnt->n_reject_iter += 1;
       if (rsq > 0.0 && rsq < 1.0) break;
@@ -469,6 +485,9 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
 // Samplers
 // ---------------------------------------------------------------------------
 // rand_resonance_vz_seon — random_mt.f90:2562-2696
+// The three wing variants of the Fortran (:2605-2635, :2638-2666, :2667-2690) differ
+// only in the pieces of the piecewise-constant majorant in beta = exp(-p^2/2); they
+// are written here as one loop over a region table (same draws, same order).
 double rand_resonance_vz(Rng &r, double x0in, double a) {
   const double x0_crit = 1.0;
   const double xc = 1.0 + std::sqrt(2.0);
@@ -478,9 +497,11 @@ double rand_resonance_vz(Rng &r, double x0in, double a) {
   Counters *cnt = r.cnt;
   if (x0 <= x0_crit) {  // :2579-2585
     for (;;) {
-      vz = x0 + a * std::tan(kPi * (r.uniform() - 0.5));
+      double u1, u2;
+      r.uniform2(u1, u2);
+      vz = x0 + a * std::tan(kPi * (u1 - 0.5));
       if (cnt) cnt->n_reject_iter += 1;
-      if (r.uniform() <= std::exp(-vz * vz)) break;
+      if (u2 <= std::exp(-vz * vz)) break;
     }
     if (x0in < 0.0) vz = -vz;
     return vz;
@@ -488,59 +509,46 @@ double rand_resonance_vz(Rng &r, double x0in, double a) {
   double x0sq = x0 * x0, api = a * kPi;
   double beta0 = std::exp(-x0sq / 2.0);
   double h0_two = beta0 / a, h0 = h0_two / 2.0;
-  double beta, Cb, pb, t1, t2, delt;
-  auto trial = [&](double b, double c) -> bool {
-    beta = b;
-    Cb = c;
-    pb = std::sqrt(-2.0 * std::log(beta));
-    t2 = std::atan((pb - x0) / a);
-    t1 = std::atan((-pb - x0) / a);
-    delt = t2 - t1;
-    if (cnt) cnt->n_reject_iter += 1;
-    return r.uniform() * Cb < (beta / api) * delt;
-  };
-  if (x0 < xc) {  // :2605-2635
+  //   piece 0: beta = beta0*sqrt(xi),  C = beta/a     (selected when rs < p0)
+  //   piece 1: beta = lo1 + w1*xi,     C = c1         (rs < p01, or the only piece)
+  //   piece 2: beta = lo2 + w2*xi,     C = c2
+  double p0 = 0.0, p01 = 0.0, lo1 = 0.0, w1 = 0.0, c1 = 0.0, lo2 = 0.0, w2 = 0.0, c2 = 0.0;
+  int mode;  // 0: single piece; 1: pieces 0+1; 2: pieces 0+1+2
+  double h2 = 0.3861 / (x0sq - 1.373);
+  if (x0 < xc || !(h0 < h2)) {  // :2605-2635 (h1) and :2667-2690 (max(h1,h2))
     double dbeta = std::sqrt(two_over_PI * a * (1.0 - beta0) * beta0 * x0);
     double beta1 = beta0 + dbeta, one_b1 = 1.0 - beta1;
     double pb1 = std::sqrt(-2.0 * std::log(beta1));
     double h1 = two_over_PI * beta1 * pb1 / (x0sq - pb1 * pb1);
-    double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * h1, Stot = S0 + S1 + S2;
-    for (;;) {
-      double rs = r.uniform();
-      bool ok;
-      if (rs < S0 / Stot) { double b = beta0 * std::sqrt(r.uniform()); ok = trial(b, b / a); }
-      else if (rs < 1.0 - S2 / Stot) ok = trial(beta0 + dbeta * r.uniform(), h0);
-      else ok = trial(beta1 + one_b1 * r.uniform(), h1);
-      if (ok) break;
+    double hm = (x0 < xc) ? h1 : ((h1 > h2) ? h1 : h2);
+    double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * hm, Stot = S0 + S1 + S2;
+    (void)S1;
+    mode = 2; p0 = S0 / Stot; p01 = 1.0 - S2 / Stot;
+    lo1 = beta0; w1 = dbeta; c1 = h0; lo2 = beta1; w2 = one_b1; c2 = hm;
+  } else if (h0_two < h2) {  // :2638-2647
+    mode = 0; lo1 = 0.0; w1 = 1.0; c1 = h2;
+  } else {  // :2648-2666
+    double S0 = beta0 * h0, one_b0 = 1.0 - beta0, S1 = one_b0 * h2, Stot = S0 + S1;
+    mode = 1; p0 = S0 / Stot; lo1 = beta0; w1 = one_b0; c1 = h2;
+  }
+  double t1, delt;
+  for (;;) {
+    double beta, Cb, ua, ub, uacc;
+    r.uniform2(ua, ub);
+    if (mode == 0) {
+      beta = lo1 + w1 * ua; Cb = c1; uacc = ub;
+    } else {
+      if (ua < p0) { beta = beta0 * std::sqrt(ub); Cb = beta / a; }
+      else if (mode == 1 || ua < p01) { beta = lo1 + w1 * ub; Cb = c1; }
+      else { beta = lo2 + w2 * ub; Cb = c2; }
+      uacc = r.uniform();
     }
-  } else {
-    double h2 = 0.3861 / (x0sq - 1.373);
-    if (h0_two < h2) {  // :2638-2647
-      for (;;) if (trial(r.uniform(), h2)) break;
-    } else if (h0 < h2) {  // :2648-2666
-      double S0 = beta0 * h0, one_b0 = 1.0 - beta0, S1 = one_b0 * h2, Stot = S0 + S1;
-      for (;;) {
-        bool ok;
-        if (r.uniform() < S0 / Stot) { double b = beta0 * std::sqrt(r.uniform()); ok = trial(b, b / a); }
-        else ok = trial(beta0 + one_b0 * r.uniform(), h2);
-        if (ok) break;
-      }
-    } else {  // :2667-2690
-      double dbeta = std::sqrt(two_over_PI * a * (1.0 - beta0) * beta0 * x0);
-      double beta1 = beta0 + dbeta, one_b1 = 1.0 - beta1;
-      double pb1 = std::sqrt(-2.0 * std::log(beta1));
-      double h1 = two_over_PI * beta1 * pb1 / (x0sq - pb1 * pb1);
-      double hmax = (h1 > h2) ? h1 : h2;
-      double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * hmax, Stot = S0 + S1 + S2;
-      for (;;) {
-        double rs = r.uniform();
-        bool ok;
-        if (rs < S0 / Stot) { double b = beta0 * std::sqrt(r.uniform()); ok = trial(b, b / a); }
-        else if (rs < 1.0 - S2 / Stot) ok = trial(beta0 + dbeta * r.uniform(), h0);
-        else ok = trial(beta1 + one_b1 * r.uniform(), hmax);
-        if (ok) break;
-      }
-    }
+    double pb = std::sqrt(-2.0 * std::log(beta));
+    double t2 = std::atan((pb - x0) / a);
+    t1 = std::atan((-pb - x0) / a);
+    delt = t2 - t1;
+    if (cnt) cnt->n_reject_iter += 1;
+    if (uacc * Cb < (beta / api) * delt) break;
   }
   vz = x0 + a * std::tan(delt * r.uniform() + t1);  // :2693
   if (x0in < 0.0) vz = -vz;
@@ -581,8 +589,10 @@ double rand_voigt(Rng &r, double a) {
 // rand_alias_linear64 — random_mt.f90:2196-2216 (arrays 1-based in the Fortran)
 double rand_alias_linear(Rng &r, const lart_scatt_mat &sm) {
   int n = sm.nPDF - 1;
-  int k = static_cast<int>(std::floor(n * r.uniform())) + 1;
-  int idx = (r.uniform() < sm.phase_PDF[k - 1]) ? k : sm.alias[k - 1];
+  double uk, ua;
+  r.uniform2(uk, ua);
+  int k = static_cast<int>(std::floor(n * uk)) + 1;
+  int idx = (ua < sm.phase_PDF[k - 1]) ? k : sm.alias[k - 1];
   double p0 = sm.S11[idx - 1], p1 = sm.S11[idx];
   double x0 = sm.coss[idx - 1], x1 = sm.coss[idx];
   return (std::sqrt(p0 * p0 + (p1 * p1 - p0 * p0) * r.uniform()) - p0) * (x1 - x0) / (p1 - p0) + x0;
@@ -911,9 +921,11 @@ inline void rotate_k(Photon &ph, double cost, double sint, double cosp, double s
 inline double sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11) {
   double phi;
   for (;;) {
-    phi = kTwoPi * r.uniform();
+    double u1, u2;
+    r.uniform2(u1, u2);
+    phi = kTwoPi * u1;
     double phi1 = 2.0 * phi;
-    double Prand = (1.0 + std::fabs(S12overS11) * std::sqrt(ph.Q * ph.Q + ph.U * ph.U)) * r.uniform();
+    double Prand = (1.0 + std::fabs(S12overS11) * std::sqrt(ph.Q * ph.Q + ph.U * ph.U)) * u2;
     double Pcomp = 1.0 + S12overS11 * (ph.Q * std::cos(phi1) + ph.U * std::sin(phi1));
     if (r.cnt) r.cnt->n_reject_iter += 1;
     if (Prand <= Pcomp) break;
@@ -936,8 +948,10 @@ void scatter_resonance_stokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
   if (par.core_skip) car_xcrit_local(w, ph.icell, ph.jcell, ph.kcell, ph.x, ph.y, ph.z, xc, xc2);
   double ux, uy;
   if (par.core_skip && std::fabs(ph.xfreq) < xc) {  // :397-401
-    double phi2 = kTwoPi * r.uniform();
-    double uxy = std::sqrt(xc2 - std::log(r.uniform()));
+    double u1, u2;
+    r.uniform2(u1, u2);
+    double phi2 = kTwoPi * u1;
+    double uxy = std::sqrt(xc2 - std::log(u2));
     ux = uxy * std::cos(phi2);
     uy = uxy * std::sin(phi2);
   } else {  // :413-414
@@ -968,8 +982,10 @@ void scatter_resonance_nostokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
   double cosp = std::cos(phi), sinp = std::sin(phi);
   double xc = 0.0, xc2 = 0.0;
   if (par.core_skip) car_xcrit_local(w, ph.icell, ph.jcell, ph.kcell, ph.x, ph.y, ph.z, xc, xc2);
-  double phi2 = kTwoPi * r.uniform();
-  double uxy = (par.core_skip && std::fabs(ph.xfreq) < xc) ? std::sqrt(xc2 - std::log(r.uniform())) : std::sqrt(-std::log(r.uniform()));
+  double u1, u2;
+  r.uniform2(u1, u2);
+  double phi2 = kTwoPi * u1;
+  double uxy = (par.core_skip && std::fabs(ph.xfreq) < xc) ? std::sqrt(xc2 - std::log(u2)) : std::sqrt(-std::log(u2));
   double ux = uxy * std::cos(phi2), uy = uxy * std::sin(phi2);
   ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
   if (par.recoil) ph.xfreq -= (w.line->g_recoil0 / w.Dfreq(ph.icell, ph.jcell, ph.kcell)) * (1.0 - cost);
@@ -1071,24 +1087,32 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
   const lart_grid &g = *w.g;
   switch (par.source_geometry) {
     case LART_SRC_UNIFORM_SPHERE: {  // :34-42
-      double rp = std::pow(r.uniform(), 1.0 / 3.0) * par.source_rmax;
-      double cost = 2.0 * r.uniform() - 1.0, sint = std::sqrt(1.0 - cost * cost), phi = kTwoPi * r.uniform();
+      double u1, u2;
+      r.uniform2(u1, u2);
+      double rp = std::pow(u1, 1.0 / 3.0) * par.source_rmax;
+      double cost = 2.0 * u2 - 1.0, sint = std::sqrt(1.0 - cost * cost), phi = kTwoPi * r.uniform();
       ph.x = rp * sint * std::cos(phi); ph.y = rp * sint * std::sin(phi); ph.z = rp * cost;
       break;
     }
     case LART_SRC_UNIFORM:  // :50-54
-      ph.x = (g.xmax - g.xmin) * r.uniform() + g.xmin;
-      ph.y = (g.ymax - g.ymin) * r.uniform() + g.ymin;
+    {
+      double u1, u2;
+      r.uniform2(u1, u2);
+      ph.x = (g.xmax - g.xmin) * u1 + g.xmin;
+      ph.y = (g.ymax - g.ymin) * u2 + g.ymin;
       ph.z = (g.zmax - g.zmin) * r.uniform() + g.zmin;
+    }
       break;
     default:  // :126-131
       ph.x = par.xs_point; ph.y = par.ys_point; ph.z = par.zs_point;
   }
   // setup_isotropic_injection :342-408
   ph.wgt = 1.0;
-  double cost = 2.0 * r.uniform() - 1.0;
+  double uc, up;
+  r.uniform2(uc, up);
+  double cost = 2.0 * uc - 1.0;
   double sint = std::sqrt(1.0 - cost * cost);
-  double phi = kTwoPi * r.uniform();
+  double phi = kTwoPi * up;
   double cosp = std::cos(phi), sinp = std::sin(phi);
   ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
   ph.icell = static_cast<int>(std::floor((ph.x - g.xmin) / g.dx)) + 1;

@@ -204,7 +204,7 @@ def test_slab_matches_neufeld_solution():
     run_gpu(m)
     m.output_normalize()
     x, J, s = m.xfreq(), m.spectrum("Jout"), m.summary
-    assert J.sum() * s.dxfreq == pytest.approx(1 / (4 * np.pi), rel=1e-6)
+    assert J.sum() * s.dxfreq == pytest.approx(1 / (4 * np.pi), rel=2e-3)  # a few photons leave beyond |x| = 30
     ana = neufeld_slab(x, s.voigt_a, 1e5)
     peak_mc = np.abs(x[np.argmax(J)])
     peak_ana = 1.066 * (s.voigt_a * 1e5) ** (1 / 3)
@@ -230,7 +230,7 @@ def test_bounded_steps_full_size_tau7():
     assert c["n_peel"] == pytest.approx(c["n_scatter"] + 148 * 1024, rel=0.01)  # one ray per scattering + direct
     assert c["n_cellsteps"] >= c["n_scatter"] + c["n_peel"]
     assert m.observer_cube("I").sum() == pytest.approx(m.observer_cube("scatt").sum() + m.observer_cube("direc").sum(), rel=1e-9)
-    assert m.spectrum("Jin").sum() == 148 * 1024
+    assert m.spectrum("Jin").sum() == 148 * 1024 + c["n_photons_done"]  # far-wing emissions leave at once and are replaced
     sim.close()
 
 

@@ -31,6 +31,8 @@ def one(case, flags):
         if a is None or b is None: continue
         ok = np.isclose(a[same], b[same], rtol=1e-8, atol=1e-9)
         print("    %-7s close among same: %.4f   first bad ids %s" % (name, ok.mean(), (np.where(same)[0][~ok][:4] + 1).tolist()))
+        for j in np.where(same)[0][~ok][:4]:
+            print("        id %d %s gpu %.17g ora %.17g  nscatt %.17g / %.17g  xfreq2 %.17g / %.17g" % (j + 1, name, a[j], b[j], ng[j], no[j], mg.allph("xfreq2")[j], mo.allph("xfreq2")[j]))
     for i in bad:
         print("    id %d: nscatt gpu %g ora %g  xfreq1 %g/%g xfreq2 %g/%g" % (i + 1, ng[i], no[i], mg.allph("xfreq1")[i], mo.allph("xfreq1")[i], mg.allph("xfreq2")[i], mo.allph("xfreq2")[i]))
     cg, co = mg.counters, mo.counters

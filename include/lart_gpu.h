@@ -146,7 +146,9 @@ enum {
   LART_FLAG_NO_WARP_AGG = 2, /* plain atomics for peel tallies (ablation)      */
   LART_FLAG_MONOLITHIC = 4,  /* one thread per photon slot, no stage compaction
                                 (the "before" arm of the warp-efficiency evidence) */
-  LART_FLAG_STAGE_TIMING = 8 /* CUDA-event timing of every stage kernel (bench/roofline) */
+  LART_FLAG_STAGE_TIMING = 8, /* CUDA-event timing of every stage kernel (bench/roofline) */
+  LART_FLAG_SERIAL_REJECTION = 16 /* per-lane rejection loops instead of the warp-cooperative
+                                     atom-velocity sampler (ablation; same results) */
 };
 
 /* stage kernels of one wave, in launch order (index into lart_gpu_stage_ms) */
@@ -273,6 +275,8 @@ int lart_gpu_raytrace_tau_batch(lart_gpu_handle h, int64_t n,
  *   kind 3: rand_resonance(p0)         (:2974-2993)  p0 = E1
  *   kind 4: rand_henyey_greenstein(p0) (:3022-3042)  p0 = g
  *   kind 5: rand_voigt(p0)             (:3075-3083)  p0 = a
+ *   kind 6: kind 2 through the warp-cooperative sampler the scatter stage uses
+ *           (same streams, same values)
  * ndraw variates per element, out[i*ndraw + j]. */
 int lart_gpu_sample_batch(int32_t kind, uint64_t seed, int64_t n, const int64_t *ids,
                           const double *p0, const double *p1, int32_t ndraw, double *out);

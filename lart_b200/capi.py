@@ -26,6 +26,7 @@ FLAG_SOA_GRID = 1
 FLAG_NO_WARP_AGG = 2
 FLAG_MONOLITHIC = 4
 FLAG_STAGE_TIMING = 8
+FLAG_SERIAL_REJECTION = 16
 STAGES = ["emit", "trace", "scatter", "peel"]
 
 

@@ -71,6 +71,7 @@ struct DevParams {
   int zonly, dust, soa, comoving_source, recoil, core_skip, core_skip_global, use_stokes, use_reduced_wgt;
   int save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D, save_direc0, save_all_photons;
   int warp_agg;
+  int flags_serial_vz;  // ablation: per-lane rejection loops instead of the warp-cooperative sampler
   int nobs;
   const DevObserver *obs;
   // dust scattering matrix
@@ -430,6 +431,158 @@ LART_DEV double rand_resonance_vz(Rng &r, double x0in, double a, unsigned long l
     if (uacc * Cb < (beta / api) * delt) break;
   }
   vz = x0 + a * tan(delt * r.uniform() + t1);  // :2693
+  return (x0in < 0.0) ? -vz : vz;
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative rand_resonance_vz (north-star part 3: vote/shuffle primitives for the
+// rejection loops).  The serial sampler leaves most lanes idle: photons split between the
+// |x| <= 1 proposal and the wing majorant, and every trial loop runs until its slowest lane
+// accepts.  Here the warp first serves all |x| <= 1 photons, then all wing photons; in each
+// phase ALL 32 lanes evaluate trials: with np photons pending every photon gets 32/np
+// consecutive trials of its own Philox stream evaluated in parallel, and the FIRST accepted
+// trial in stream order wins.  Trial t of a photon consumes the same Philox blocks as in the
+// serial loop and the block counter advances exactly past the accepted trial, so the result
+// — and every later draw of the photon — is identical to the serial algorithm's.
+// ---------------------------------------------------------------------------
+struct VzWarpShared {
+  double x0[32], a[32];
+  unsigned long long id[32], nb[32];
+  double tab[32][9];  // wing majorant: beta0, p0, p01, lo1, w1, c1, lo2, w2, c2
+  int mode[32];
+  double r0[32], r1[32];
+  int first[32];
+};
+
+LART_DEV void philox_uniform2(unsigned long long seed, unsigned long long id, unsigned long long blk, double &u1, double &u2) {
+  uint32_t c0 = (uint32_t)id, c1 = (uint32_t)(id >> 32), c2 = (uint32_t)blk, c3 = (uint32_t)(blk >> 32);
+  philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  u1 = Rng::open01((unsigned long long)c0 | ((unsigned long long)c1 << 32));
+  u2 = Rng::open01((unsigned long long)c2 | ((unsigned long long)c3 << 32));
+}
+
+// Must be called by all 32 lanes of a converged warp; `mine` = this lane has a photon to sample.
+LART_DEV double rand_resonance_vz_warp(VzWarpShared &sh, bool mine, Rng &r, double x0in, double a, unsigned long long &nrej) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const double x0 = fabs(x0in);
+  const bool core = x0 <= 1.0;
+  double vz = 0.0;
+  // ---------------- phase A: |x| <= 1, Lorentzian proposal + exp(-u^2) acceptance (:2579-2585)
+  {
+    bool todo = mine && core;
+    unsigned pend = __ballot_sync(FULL, todo);
+    while (pend) {
+      const int np = __popc(pend), rank = __popc(pend & lt);
+      if (todo) { sh.x0[rank] = x0; sh.a[rank] = a; sh.id[rank] = r.stream; sh.nb[rank] = r.nblk; }
+      __syncwarp();
+      const int tpj = 32 / np, job = lane / tpj, t = lane - job * tpj;
+      const bool work = job < np;
+      const unsigned grp = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (job * tpj));
+      bool acc = false;
+      double v = 0.0;
+      if (work) {
+        double u1, u2;
+        philox_uniform2(r.seed, sh.id[job], sh.nb[job] + t, u1, u2);
+        v = sh.x0[job] + sh.a[job] * tan(kPi * (u1 - 0.5));
+        acc = u2 <= exp(-v * v);
+      }
+      const unsigned accm = __ballot_sync(FULL, acc);
+      if (acc && (accm & grp & lt) == 0u) { sh.r0[job] = v; sh.first[job] = t; }
+      __syncwarp();
+      if (todo) {
+        const unsigned my = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (rank * tpj));
+        int used = tpj;
+        if (accm & my) { vz = sh.r0[rank]; used = sh.first[rank] + 1; todo = false; }
+        r.nblk += used; r.nrng += 2 * used; nrej += used;
+      }
+      __syncwarp();
+      pend = __ballot_sync(FULL, todo);
+    }
+  }
+  // ---------------- phase B: wings, piecewise-constant majorant in beta (:2605-2690)
+  {
+    bool todo = mine && !core;
+    unsigned pend = __ballot_sync(FULL, todo);
+    double t1 = 0.0, delt = 0.0;
+    const bool wing = todo;
+    // the majorant table of my photon (same expressions as rand_resonance_vz)
+    double T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int mode = 0;
+    if (todo) {
+      const double xc = 1.0 + 1.4142135623730951, two_over_PI = 2.0 / kPi;
+      double x0sq = x0 * x0;
+      double beta0 = exp(-x0sq / 2.0);
+      double h0_two = beta0 / a, h0 = h0_two / 2.0;
+      double h2 = 0.3861 / (x0sq - 1.373);
+      T[0] = beta0;
+      if (x0 < xc || !(h0 < h2)) {
+        double dbeta = sqrt(two_over_PI * a * (1.0 - beta0) * beta0 * x0);
+        double beta1 = beta0 + dbeta, one_b1 = 1.0 - beta1;
+        double pb1 = sqrt(-2.0 * log(beta1));
+        double h1 = two_over_PI * beta1 * pb1 / (x0sq - pb1 * pb1);
+        double hm = (x0 < xc) ? h1 : ((h1 > h2) ? h1 : h2);
+        double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * hm, Stot = S0 + S1 + S2;
+        mode = 2; T[1] = S0 / Stot; T[2] = 1.0 - S2 / Stot;
+        T[3] = beta0; T[4] = dbeta; T[5] = h0; T[6] = beta1; T[7] = one_b1; T[8] = hm;
+      } else if (h0_two < h2) {
+        mode = 0; T[3] = 0.0; T[4] = 1.0; T[5] = h2;
+      } else {
+        double S0 = beta0 * h0, one_b0 = 1.0 - beta0, S1 = one_b0 * h2, Stot = S0 + S1;
+        mode = 1; T[1] = S0 / Stot; T[3] = beta0; T[4] = one_b0; T[5] = h2;
+      }
+    }
+    while (pend) {
+      const int np = __popc(pend), rank = __popc(pend & lt);
+      if (todo) {
+        sh.x0[rank] = x0; sh.a[rank] = a; sh.id[rank] = r.stream; sh.nb[rank] = r.nblk; sh.mode[rank] = mode;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) sh.tab[rank][q] = T[q];
+      }
+      __syncwarp();
+      const int tpj = 32 / np, job = lane / tpj, t = lane - job * tpj;
+      const bool work = job < np;
+      const unsigned grp = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (job * tpj));
+      bool acc = false;
+      double tt1 = 0.0, td = 0.0;
+      if (work) {
+        const double jx0 = sh.x0[job], ja = sh.a[job];
+        const double *J = sh.tab[job];
+        const int jm = sh.mode[job];
+        const unsigned long long jid = sh.id[job], jb = sh.nb[job] + (unsigned long long)t * (jm == 0 ? 1 : 2);
+        double ua, ub, uacc, beta, Cb;
+        philox_uniform2(r.seed, jid, jb, ua, ub);
+        if (jm == 0) { beta = J[3] + J[4] * ua; Cb = J[5]; uacc = ub; }
+        else {
+          if (ua < J[1]) { beta = J[0] * sqrt(ub); Cb = beta / ja; }
+          else if (jm == 1 || ua < J[2]) { beta = J[3] + J[4] * ub; Cb = J[5]; }
+          else { beta = J[6] + J[7] * ub; Cb = J[8]; }
+          double dummy;
+          philox_uniform2(r.seed, jid, jb + 1, uacc, dummy);
+        }
+        double pb = sqrt(-2.0 * log(beta));
+        double t2 = atan((pb - jx0) / ja);
+        tt1 = atan((-pb - jx0) / ja);
+        td = t2 - tt1;
+        acc = uacc * Cb < (beta / (ja * kPi)) * td;
+      }
+      const unsigned accm = __ballot_sync(FULL, acc);
+      if (acc && (accm & grp & lt) == 0u) { sh.r0[job] = tt1; sh.r1[job] = td; sh.first[job] = t; }
+      __syncwarp();
+      if (todo) {
+        const unsigned my = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (rank * tpj));
+        int used = tpj;
+        if (accm & my) { t1 = sh.r0[rank]; delt = sh.r1[rank]; used = sh.first[rank] + 1; todo = false; }
+        r.nblk += (unsigned long long)used * (mode == 0 ? 1 : 2);
+        r.nrng += (unsigned long long)used * (mode == 0 ? 2 : 3);
+        nrej += used;
+      }
+      __syncwarp();
+      pend = __ballot_sync(FULL, todo);
+    }
+    if (wing) vz = x0 + a * tan(delt * r.uniform() + t1);  // :2693
+  }
   return (x0in < 0.0) ? -vz : vz;
 }
 
@@ -858,11 +1011,12 @@ struct ScatterOut {
 // scatter_resonance_stokes (:331-486) / _nostokes (:660-827).  The peel-off call
 // sits between the frequency update and the Stokes/triad update in the reference
 // (:446 / :788): `peel` is invoked at exactly that point.
+// `uz` = rand_resonance_vz(x, a) has been drawn by the caller (serially, or warp-cooperatively).
 template <class PeelFn>
-LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, PeelFn &&peel) {
+LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, double uz,
+                                PeelFn &&peel) {
   ph.nsg += ph.wgt;
   // do_resonance1 — line_mod.f90:108-139
-  double uz = rand_resonance_vz(r, ph.xfreq, cs.voigt_a, cnt.reject);
   double xfreq_atom = ph.xfreq - uz;
   double cost = rand_resonance(r, P.E1);
   double sint = sqrt(1.0 - cost * cost);

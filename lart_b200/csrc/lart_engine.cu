@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
         });
         if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
       } else {
-        scatter_resonance(P, ph, rng, cs, cnt, [&](double xa, double ux, double uy, double uz) {
+        const double uz_s = rand_resonance_vz(rng, ph.xfreq, cs.voigt_a, cnt.reject);
+        scatter_resonance(P, ph, rng, cs, cnt, uz_s, [&](double xa, double ux, double uy, double uz) {
           for (int i = 0; i < P.nobs; ++i) {
             PeelRay pr;
             bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[i], i, ph, cs, xa, ux, uy, uz, pr)
@@ -480,33 +481,48 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
 }
 
 // stage 3: scattering for every photon flagged by the trace stage; writes the
-// peel-ray descriptors of its slot
+// peel-ray descriptors of its slot.  The slot loop is warp-uniform (inactive lanes stay in
+// it) so that the atom-velocity rejection sampler can run warp-cooperatively.
 __global__ void __launch_bounds__(kBlock, 2) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
+  __shared__ VzWarpShared vzsh[kBlock / 32];
   if (P.dust) load_vtab(P, vtab);
+  VzWarpShared &sh = vzsh[threadIdx.x >> 5];
   Counters cnt;
   unsigned long long nrng = 0;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < pl.S; s += gridDim.x * blockDim.x) {
-    int fl0 = pl.flags[s];
-    PeelRay *myrays = q.rays + (size_t)s * P.nobs;
-    if (!(fl0 & PH_SCATTER)) {
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < pl.S; base += stride) {
+    const int s = base + lane;
+    const bool inb = s < pl.S;
+    const int fl0 = inb ? pl.flags[s] : 0;
+    const bool active = (fl0 & PH_SCATTER) != 0;
+    PeelRay *myrays = q.rays + (size_t)(inb ? s : 0) * P.nobs;
+    if (inb && !active)
       for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
-      continue;
-    }
+    if (!__any_sync(0xffffffffu, active)) continue;
     Photon ph;
     Rng rng;
-    load_trace_part(pl, s, ph);
-    load_rest(pl, s, ph);
-    ph.flags &= ~PH_SCATTER;
-    load_rng(P, pl, s, ph.id, ph.flags, rng);
     CellData cs;
-    load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
-    cnt.scatter += 1;
     bool to_dust = false;
-    if (P.dust) {
-      double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
-      to_dust = rng.uniform() <= pd;
+    if (active) {
+      load_trace_part(pl, s, ph);
+      load_rest(pl, s, ph);
+      ph.flags &= ~PH_SCATTER;
+      load_rng(P, pl, s, ph.id, ph.flags, rng);
+      load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
+      cnt.scatter += 1;
+      if (P.dust) {
+        double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
+        to_dust = rng.uniform() <= pd;
+      }
+    } else {
+      ph.xfreq = 0.0; cs.voigt_a = 1.0; rng.start(P.seed, 0ULL);
     }
+    const bool resonant = active && !to_dust;
+    const double uz_w = (P.flags_serial_vz) ? (resonant ? rand_resonance_vz(rng, ph.xfreq, cs.voigt_a, cnt.reject) : 0.0)
+                                            : rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, cs.voigt_a, cnt.reject);
+    if (!active) continue;
     bool peeled = false;
     if (to_dust) {
       scatter_dust(P, ph, rng, cs, cnt, [&]() {
@@ -520,7 +536,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_scatter(const __grid_constant_
       });
       if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
     } else {
-      scatter_resonance(P, ph, rng, cs, cnt, [&](double xa, double ux, double uy, double uz) {
+      scatter_resonance(P, ph, rng, cs, cnt, uz_w, [&](double xa, double ux, double uy, double uz) {
         peeled = true;
         for (int k = 0; k < P.nobs; ++k) {
           PeelRay pr;
@@ -651,21 +667,31 @@ __global__ void k_xcrit_batch(const __grid_constant__ DevParams P, long long n, 
 }
 __global__ void k_sample_batch(int kind, unsigned long long seed, long long n, const long long *ids, const double *p0,
                                const double *p1, int ndraw, double *out) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  __shared__ VzWarpShared vzsh[kBlock / 32];
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // warp-uniform loop: kind 6 is a warp collective
+  for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+    const long long i = base + lane;
+    const bool mine = i < n;
     Rng r;
-    r.start(seed, (unsigned long long)(ids ? ids[i] : i));
+    r.start(seed, (unsigned long long)(mine ? (ids ? ids[i] : i) : 0));
     unsigned long long nrej = 0;
+    const double q0 = (mine && p0) ? p0[i] : 0.0, q1 = (mine && p1) ? p1[i] : 1.0;
     for (int j = 0; j < ndraw; ++j) {
-      double v;
-      switch (kind) {
-        case 0: v = r.uniform(); break;
-        case 1: v = r.gauss(nrej); break;
-        case 2: v = rand_resonance_vz(r, p0[i], p1[i], nrej); break;
-        case 3: v = rand_resonance(r, p0[i]); break;
-        case 4: v = rand_hg(r, p0[i]); break;
-        default: v = rand_voigt(r, p0[i], nrej); break;
+      double v = 0.0;
+      if (kind == 6) v = rand_resonance_vz_warp(vzsh[threadIdx.x >> 5], mine, r, q0, q1, nrej);
+      else if (mine) {
+        switch (kind) {
+          case 0: v = r.uniform(); break;
+          case 1: v = r.gauss(nrej); break;
+          case 2: v = rand_resonance_vz(r, q0, q1, nrej); break;
+          case 3: v = rand_resonance(r, q0); break;
+          case 4: v = rand_hg(r, q0); break;
+          default: v = rand_voigt(r, q0, nrej); break;
+        }
       }
-      out[i * ndraw + j] = v;
+      if (mine) out[i * ndraw + j] = v;
     }
   }
 }
@@ -821,6 +847,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   P.voigt_tab = vt;
   P.soa = (cfg->flags & LART_FLAG_SOA_GRID) ? 1 : 0;
   P.warp_agg = (cfg->flags & LART_FLAG_NO_WARP_AGG) ? 0 : 1;
+  P.flags_serial_vz = (cfg->flags & LART_FLAG_SERIAL_REJECTION) ? 1 : 0;
   if (!P.soa) {
     Cell *cells = nullptr;
     if ((rc = dalloc(h, &cells, nc, false))) return bail(rc);
@@ -1323,10 +1350,10 @@ int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n, const double *x, const do
 
 int lart_gpu_sample_batch(int32_t kind, uint64_t seed, int64_t n, const int64_t *ids, const double *p0, const double *p1,
                           int32_t ndraw, double *out) {
-  if (kind < 0 || kind > 5) return fail("lart_gpu_sample_batch: unknown kind");
+  if (kind < 0 || kind > 6) return fail("lart_gpu_sample_batch: unknown kind");
   if (n < 0 || ndraw < 1 || (n > 0 && !out)) return fail("lart_gpu_sample_batch: bad argument");
   if ((kind >= 2) && n > 0 && !p0) return fail("lart_gpu_sample_batch: p0 required");
-  if (kind == 2 && n > 0 && !p1) return fail("lart_gpu_sample_batch: p1 required");
+  if ((kind == 2 || kind == 6) && n > 0 && !p1) return fail("lart_gpu_sample_batch: p1 required");
   if (n == 0) return 0;
   Scratch s;
   long long *dids;

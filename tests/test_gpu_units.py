@@ -163,3 +163,19 @@ def test_rand_resonance_vz_matches_oracle_streams(x0, a):
     from scipy.stats import ks_2samp
     mt = oracle.sample(2, 99, ids, x0, a, ndraw=4, rng_mode=0)
     assert ks_2samp(g.ravel(), mt.ravel()).pvalue > 1e-4
+
+
+def test_warp_cooperative_sampler_equals_serial():
+    """The warp-cooperative atom-velocity sampler (kind 6) evaluates trials of many photons in parallel but must
+    return, photon by photon and draw by draw, exactly what the serial rejection loop (kind 2) returns."""
+    rng = np.random.default_rng(12)
+    n = 50000
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    x0 = rng.normal(size=n) * 2.5          # mixes |x|<=1 photons and all three wing variants inside every warp
+    x0[::7] = rng.uniform(-12, 12, x0[::7].size)
+    a = np.where(rng.uniform(size=n) < 0.5, 4.7186e-4, 1.4921e-2)
+    serial = sample(2, 31, ids, x0, a, ndraw=3)
+    coop = sample(6, 31, ids, x0, a, ndraw=3)
+    assert np.array_equal(serial, coop)
+    # ragged tail: a batch that does not fill its last warp
+    assert np.array_equal(sample(2, 5, ids[:45], x0[:45], a[:45], ndraw=2), sample(6, 5, ids[:45], x0[:45], a[:45], ndraw=2))

@@ -225,22 +225,37 @@ def run_gpu(args):
     hbm_peak, peak_src = measured_peaks()
     fp64_peak = measure_fp64(local)
     dom = max(stage, key=lambda k: stage[k][0])
+    tot_stage = max(sum(v[0] for v in stage.values()), 1e-30)
     walk_ms = stage["trace"][0] + stage["peel"][0]
     walk_n = stage["trace"][1] + stage["peel"][1]
     steps_local = c["n_cellsteps"]
-    # algorithmic 48 B (six f64 grid values) per cell step — SURVEY.md §8(d); cell steps happen in trace + peel
-    ach = 48.0 * steps_local / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0
     flops = 50.0 * steps_local + 300.0 * c["n_scatter"]
-    roof = {"bound": "hbm", "kernel": "k_wf_trace+k_wf_peel (DDA cell walk)" if not (args.flags & 4) else "k_mono",
-            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "bytes_per_cellstep": 48, "cellsteps_per_launch": steps_local / max(walk_n, 1),
-            "avg_launch_ms": walk_ms / max(walk_n, 1),
+    mono = bool(args.flags & 4)
+    # Dominant kernel = the scatter stage.  Its algorithmic HBM bytes per scattering: the photon
+    # record is read and written once (21 f64 + id + block counter + 4 i32 = 200 B each way) and one 112-B peel-ray
+    # descriptor is written per observer.
+    nobs = max(int(cfg.par.nobs), 0)
+    bytes_per_scatter = 2 * 200 + 112 * nobs
+    sc_ms, sc_n = stage["scatter"] if not mono else stage["trace"]
+    ach = bytes_per_scatter * c["n_scatter"] / (sc_ms * 1e-3) / 1e9 if sc_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")  # dram__bytes_read+write per launch from `ncu --set full`
+    if os.path.exists(tpath) and not mono:
+        traffic = json.load(open(tpath)).get("k_wf_scatter_bytes_per_launch")
+    roof = {"bound": "hbm", "kernel": "k_wf_scatter" if not mono else "k_mono",
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+            "peak_source": peak_src, "bytes_per_scattering": bytes_per_scatter,
+            "scatterings_per_launch": c["n_scatter"] / max(sc_n, 1), "avg_launch_ms": sc_ms / max(sc_n, 1),
+            "note": "the path is FP64-issue/latency bound, not HBM bound: see `fp64` (issue-rate roofline) and `dda_walk`",
             "stage_ms_per_wave": {k: stage[k][0] / max(stage[k][1], 1) for k in stage},
-            "stage_share": {k: stage[k][0] / max(sum(v[0] for v in stage.values()), 1e-30) for k in stage},
+            "stage_share": {k: stage[k][0] / tot_stage for k in stage},
             "dominant_stage": dom,
+            "dda_walk": {"kernels": "k_wf_trace+k_wf_peel", "bytes_per_cellstep": 48,
+                         "achieved_GBps": 48.0 * steps_local / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0,
+                         "cellsteps_per_launch": steps_local / max(walk_n, 1), "avg_launch_ms": walk_ms / max(walk_n, 1)},
             "fp64": {"achieved_tflops": flops / (dev_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                      "frac": flops / (dev_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
-                     "model": "50 flop/cell step + 300 flop/scattering (SURVEY.md 8d; libm calls not counted)",
+                     "model": "50 flop/cell step + 300 flop/scattering (SURVEY.md 8d; libm calls and the RNG not counted)",
                      "peak_source": "measured DFMA loop (lart_gpu_measure_fp64)"}}
     sim.close()
 

@@ -139,7 +139,8 @@ def host_lib_path():
 
 
 def gpu_lib_path():
-    return os.path.join(_HERE, "liblart_gpu.so")
+    # LART_GPU_LIB: an alternative build of the same engine (A/B experiments); never a fallback
+    return os.environ.get("LART_GPU_LIB") or os.path.join(_HERE, "liblart_gpu.so")
 
 
 def load_host():

@@ -483,7 +483,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
 // stage 3: scattering for every photon flagged by the trace stage; writes the
 // peel-ray descriptors of its slot.  The slot loop is warp-uniform (inactive lanes stay in
 // it) so that the atom-velocity rejection sampler can run warp-cooperatively.
-__global__ void __launch_bounds__(kBlock, 2) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+#ifndef LART_SCATTER_MINBLOCKS
+#define LART_SCATTER_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   __shared__ VzWarpShared vzsh[kBlock / 32];
   if (P.dust) load_vtab(P, vtab);

@@ -45,7 +45,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--workload", default="sphere_peel_tau1e7", choices=sorted(WORKLOADS))
@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="device-resident arm only (profiling runs)")
     ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--streams", type=int, default=0, help="wave pipelines (pool partitions on separate streams); 0 = auto")
     return ap.parse_args()
 
 
@@ -180,6 +181,7 @@ def run_gpu(args):
 
     S_auto = args.pool_slots or 148 * 8192
     total_steps = args.warmup + args.steps
+    import lart_b200  # noqa: F401
     nph = S_auto * world * 4  # far more ids than slots: the queue never runs dry, nobody finishes tau0 = 1e7 anyway
     model = build_model(args, nph)
     cfg = model.config.contents
@@ -187,30 +189,35 @@ def run_gpu(args):
     ncell = g.nx * g.ny * g.nz
     grid_bytes = 8 * (6 * ncell + (g.nx + g.ny + g.nz + 3))
 
-    # ------------------------- device-resident arm: `value`
-    sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum,
-                     flags=args.flags | capi.FLAG_STAGE_TIMING)
-    S = sim.pool_slots
+    # ------------------------- device-resident arm: `value`  (CUDA-graph launches, no per-stage events)
     first, count, stride = rank + 1, nph // world, world  # run_simulation_mod.f90:150 partition
-    sim.begin(first, count, stride)
-    for _ in range(args.warmup):
-        sim.step(args.quantum)
-    sim.sync()
-    sim.reset_tallies()
-    barrier()
-    with ClockSampler(local) as clk:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
+
+    def device_arm(flags, warmup, steps):
+        sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=flags,
+                         streams=args.streams)
+        sim.begin(first, count, stride)
+        for _ in range(warmup):
             sim.step(args.quantum)
         sim.sync()
+        sim.reset_tallies()
         barrier()
-        wall = time.perf_counter() - t0
-    dev_ms, launches = sim.kernel_ms()
-    stage = sim.stage_ms()
-    # counters of the timed region (tallies were reset after the warm-up)
-    model.zero_tallies()
-    sim._check(sim._lib.lart_gpu_fetch(sim._h, model.tallies))
-    c = dict(model.counters)
+        with ClockSampler(local) as clk_:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                sim.step(args.quantum)
+            sim.sync()
+            barrier()
+            wall_ = time.perf_counter() - t0
+        ms_, launches_ = sim.kernel_ms()
+        stage_ = sim.stage_ms()
+        model.zero_tallies()
+        sim._check(sim._lib.lart_gpu_fetch(sim._h, model.tallies))  # counters of the timed region only
+        c_ = dict(model.counters)
+        S_ = sim.pool_slots
+        sim.close()
+        return ms_, launches_, stage_, c_, S_, wall_, clk_
+
+    dev_ms, launches, _, c, S, wall, clk = device_arm(args.flags, args.warmup, args.steps)
     t = torch.tensor([dev_ms, c["n_scatter"], c["n_cellsteps"], c["n_peel"], c["n_photons_done"], c["n_rng"], float(launches)],
                      dtype=torch.float64, device="cuda")
     tmax = t.clone()
@@ -220,6 +227,8 @@ def run_gpu(args):
     max_ms = float(tmax[0])
     n_scatter, n_cell, n_peel, n_done, n_rng, n_launch = (float(t[i]) for i in range(1, 7))
     value = n_scatter / (max_ms * 1e-3)
+    # a second, short pass with CUDA events around every stage kernel (plain launches) feeds the roofline
+    dev_ms, _, stage, c, _, _, _ = device_arm(args.flags | capi.FLAG_STAGE_TIMING, max(args.warmup, 3), min(args.steps, 4))
 
     # ------------------------- FP64 issue peak + roofline of the dominant kernel (rank 0)
     hbm_peak, peak_src = measured_peaks()
@@ -257,7 +266,6 @@ def run_gpu(args):
                      "frac": flops / (dev_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
                      "model": "50 flop/cell step + 300 flop/scattering (SURVEY.md 8d; libm calls and the RNG not counted)",
                      "peak_source": "measured DFMA loop (lart_gpu_measure_fp64)"}}
-    sim.close()
 
     # ------------------------- end-to-end arm through the public API with HOST buffers: `e2e`
     # timed: lart_gpu_create (H2D of the host grid arrays) + begin + steps (each followed by the D2H read of
@@ -267,7 +275,8 @@ def run_gpu(args):
     t0 = time.perf_counter()
     buf_n = 0
     if not args.skip_e2e:
-        sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=args.flags)
+        sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=args.flags,
+                         streams=args.streams)
         sim.begin(first, count, stride)
         for _ in range(total_steps):
             sim.step(args.quantum)

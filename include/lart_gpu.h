@@ -139,6 +139,9 @@ typedef struct lart_config {
   int32_t pool_slots;              /* photons in flight; 0 = auto           */
   int32_t quantum;                 /* scattering events per slot per lart_gpu_step; 0 = auto */
   int32_t flags;                   /* LART_FLAG_*                           */
+  int32_t streams;                 /* wave pipelines: the pool is split into this many partitions,
+                                      each advanced on its own CUDA stream; 0 = auto (4) */
+  int32_t pad_;
 } lart_config;
 
 enum {
@@ -147,8 +150,11 @@ enum {
   LART_FLAG_MONOLITHIC = 4,  /* one thread per photon slot, no stage compaction
                                 (the "before" arm of the warp-efficiency evidence) */
   LART_FLAG_STAGE_TIMING = 8, /* CUDA-event timing of every stage kernel (bench/roofline) */
-  LART_FLAG_SERIAL_REJECTION = 16 /* per-lane rejection loops instead of the warp-cooperative
-                                     atom-velocity sampler (ablation; same results) */
+  LART_FLAG_SERIAL_REJECTION = 16, /* per-lane rejection loops instead of the warp-cooperative
+                                      atom-velocity sampler (ablation; same results) */
+  LART_FLAG_LOCAL_STEPS = 32       /* the scatter stage takes the first cell step of the peel ray and
+                                      of the next flight itself; only longer rays reach the queues
+                                      (experimental; same results) */
 };
 
 /* stage kernels of one wave, in launch order (index into lart_gpu_stage_ms) */

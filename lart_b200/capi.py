@@ -27,6 +27,7 @@ FLAG_NO_WARP_AGG = 2
 FLAG_MONOLITHIC = 4
 FLAG_STAGE_TIMING = 8
 FLAG_SERIAL_REJECTION = 16
+FLAG_LOCAL_STEPS = 32
 STAGES = ["emit", "trace", "scatter", "peel"]
 
 
@@ -80,7 +81,7 @@ class ScattMat(C.Structure):
 class Config(C.Structure):
     _fields_ = [("grid", Grid), ("par", Params), ("line", Line), ("scatt_mat", ScattMat),
                 ("observers", C.POINTER(Observer)), ("device", C.c_int32), ("pool_slots", C.c_int32),
-                ("quantum", C.c_int32), ("flags", C.c_int32)]
+                ("quantum", C.c_int32), ("flags", C.c_int32), ("streams", C.c_int32), ("pad_", C.c_int32)]
 
 
 OBS_FIELDS = ["scatt", "direc", "direc0", "I", "Q", "U", "V",

@@ -72,6 +72,7 @@ struct DevParams {
   int save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D, save_direc0, save_all_photons;
   int warp_agg;
   int flags_serial_vz;  // ablation: per-lane rejection loops instead of the warp-cooperative sampler
+  int local_steps;      // scatter stage resolves 1-cell peel rays / 1-cell flights itself (0: ablation)
   int nobs;
   const DevObserver *obs;
   // dust scattering matrix
@@ -261,8 +262,10 @@ LART_DEV bool axis_setup(double k, double p, int &cell, int n, const double *fac
 }
 
 // returns true when the photon is already leaving the grid (no step is taken)
+// `here` (optional) = record of the start cell when the caller already holds it; it is used
+// unless the on-face rule moved the start into a neighbouring cell.
 LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
-                        int ic, int jc, int kc, double xfreq, bool zonly_eq) {
+                        int ic, int jc, int kc, double xfreq, bool zonly_eq, const CellData *here = nullptr) {
   r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
   r.ic = ic; r.jc = jc; r.kc = kc;
   r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0;
@@ -274,7 +277,8 @@ LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z
     if (axis_setup(ky, y, r.jc, P.ny, P.yface, P.dy, r.jstep, r.ty, r.dely, false)) return true;
     if (axis_setup(kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, false)) return true;
   }
-  load_cell(P, cell_index(P, r.ic, r.jc, r.kc), r.cell);
+  if (here && r.ic == ic && r.jc == jc && r.kc == kc) r.cell = *here;
+  else load_cell(P, cell_index(P, r.ic, r.jc, r.kc), r.cell);
   r.u1 = vdotk(r.cell, kx, ky, kz);
   return false;
 }
@@ -358,7 +362,7 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
 // ---------------------------------------------------------------------------
 // photon_type — define.f90:80-111 (I == 1 always; E1,E2,E3 are line constants)
 // ---------------------------------------------------------------------------
-enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8 };
+enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8, PH_TAUPEND = 16 };
 struct Photon {
   long long id;
   double x, y, z, kx, ky, kz, mx, my, mz, nx, ny, nz;
@@ -879,7 +883,7 @@ LART_DEV bool peel_dust_nostokes_prepare(const DevParams &P, const DevObserver &
 // `lanes` = mask of converged lanes calling together; with warp aggregation lanes
 // that hit the same (observer, pixel, frequency bin) are summed in registers first
 // and one lane issues the atomics.
-LART_DEV void peel_deposit(const DevParams &P, const PeelRay &pr, double tau, unsigned lanes) {
+LART_DEV void peel_deposit(const DevParams &P, const PeelRay &pr, double tau, unsigned lanes, bool aggregate = true) {
   double e = exp(-tau);
   double v[4] = {0.0, 0.0, 0.0, 0.0};
   int nv;
@@ -891,10 +895,10 @@ LART_DEV void peel_deposit(const DevParams &P, const PeelRay &pr, double tau, un
   // A ray that ran into the tau cap (745.2) carries exp(-tau) == 0: all its contributions are exact
   // zeros, which never change a sum (the reference adds them; the result is the same).
   const bool nonzero = (v[0] != 0.0) | (v[1] != 0.0) | (v[2] != 0.0) | (v[3] != 0.0);
-  lanes = __ballot_sync(lanes, nonzero);
+  if (aggregate) lanes = __ballot_sync(lanes, nonzero);
   if (!nonzero) return;
   bool leader = true;
-  if (P.warp_agg) {
+  if (P.warp_agg && aggregate) {
     unsigned long long key = ((unsigned long long)(unsigned)pr.kind << 60) ^ ((unsigned long long)(unsigned)pr.obs << 44) ^
                              ((unsigned long long)(unsigned)pr.pix << 12) ^ (unsigned long long)(unsigned)pr.ixf;
     unsigned grp = __match_any_sync(lanes, key);

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -64,23 +65,24 @@ constexpr int kTailQuantum = 256;
 // ------------------------------- photon pool -------------------------------
 enum {
   F_X, F_Y, F_Z, F_KX, F_KY, F_KZ, F_MX, F_MY, F_MZ, F_NX, F_NY, F_NZ,
-  F_XFREQ, F_XREF, F_WGT, F_Q, F_U, F_V, F_NSG, F_NSD, F_GSET, F_COUNT
+  F_XFREQ, F_XREF, F_WGT, F_Q, F_U, F_V, F_NSG, F_NSD, F_GSET, F_TAU, F_COUNT
 };
 struct Pool {
   double *f;                   // [F_COUNT][S]
   long long *id;               // [S]
   unsigned long long *ndraw;   // [S]
   int *ic, *jc, *kc, *flags;   // [S]
-  int S;
+  int S;                       // slots (= SoA stride)
+  int s0, n;                   // the partition [s0, s0+n) this kernel launch works on
 };
 struct Job {  // photon ids = first_id + j*stride, j in [0,count)
   unsigned long long next, count, done;
   long long first_id, stride;
 };
-struct Queues {
-  PeelRay *rays;      // [ray_cap]: S*nobs slot rays, then the direct rays of this wave's emits
+struct Queues {  // one per pool partition (pipeline)
+  PeelRay *rays;      // [ray_cap]: S*nobs slot rays, then per partition the direct rays of this wave's emits
   unsigned int *n_direct, *head_trace, *head_peel;
-  unsigned int direct_base, ray_cap;
+  unsigned int direct_base, direct_cap;  // direct-ray region of this partition
 };
 
 __device__ __forceinline__ void load_trace_part(const Pool &pl, int s, Photon &ph) {
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   Counters cnt;
   unsigned long long nrng = 0;
-  if (s < pl.S) {
+  if (s < pl.S) {  // the monolithic driver always works on the whole pool
     Photon ph;
     Rng rng;
     ph.flags = pl.flags[s];
@@ -236,47 +238,58 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
       load_rng(P, pl, s, ph.id, ph.flags, rng);
       rng_valid = true;
     }
+    bool at_scatter = (ph.flags & PH_ALIVE) && (ph.flags & PH_SCATTER);
+    ph.flags &= ~PH_SCATTER;
     for (int ev = 0; ev < quantum; ++ev) {
       CellData cs;
-      if (!(ph.flags & PH_ALIVE)) {
-        if (job->next >= job->count) break;
-        unsigned long long j = atomicAdd(&job->next, 1ULL);
-        if (j >= job->count) break;
-        touched = true;
-        ph.id = job->first_id + (long long)j * job->stride;
-        if (rng_valid) nrng += rng.nrng;  // draws of the previous photon in this slot
-        rng.start(P.seed, (unsigned long long)ph.id);
-        rng_valid = true;
-        generate_photon(P, ph, rng, cnt, cs);
-        if (P.save_all_photons) record_initial(P, ph);
-        if (P.save_peeloff) {  // peeling_direct — generate_photon.f90:334-336
-          for (int i = 0; i < P.nobs; ++i) {
-            PeelRay pr;
-            if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
-            int ns;
-            double tau = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns);
-            cnt.cellsteps += ns; cnt.peel += 1;
-            peel_deposit(P, pr, tau, __activemask());
+      if (!at_scatter) {
+        if (!(ph.flags & PH_ALIVE)) {
+          if (job->next >= job->count) break;
+          unsigned long long j = atomicAdd(&job->next, 1ULL);
+          if (j >= job->count) break;
+          touched = true;
+          ph.id = job->first_id + (long long)j * job->stride;
+          if (rng_valid) nrng += rng.nrng;  // draws of the previous photon in this slot
+          rng.start(P.seed, (unsigned long long)ph.id);
+          rng_valid = true;
+          generate_photon(P, ph, rng, cnt, cs);
+          if (P.save_all_photons) record_initial(P, ph);
+          if (P.save_peeloff) {  // peeling_direct — generate_photon.f90:334-336
+            for (int i = 0; i < P.nobs; ++i) {
+              PeelRay pr;
+              if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
+              int ns;
+              double tau = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns);
+              cnt.cellsteps += ns; cnt.peel += 1;
+              peel_deposit(P, pr, tau, __activemask());
+            }
           }
         }
-      }
-      touched = true;
-      double tau;
-      if (ph.flags & PH_FIRST) {
-        int ci, cj, ck, ns;
-        clamp_cell_for_read(P, ph, ci, cj, ck);
-        load_cell(P, cell_index(P, ci, cj, ck), cs);
-        double tau0 = walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, ns);
-        cnt.cellsteps += ns;
-        tau = forced_first(P, ph, rng, cs, tau0);
-      } else {
-        tau = -log(rng.uniform());
-      }
-      int ns = walk_tau(P, vtab, ph, tau, cs);
-      if (ns > 0) cnt.cellsteps += ns;
-      if (!(ph.flags & PH_ALIVE)) {
-        retire_photon(P, ph, ns >= 0, job, cnt);
-        continue;
+        touched = true;
+        double tau;
+        if (ph.flags & PH_FIRST) {
+          int ci, cj, ck, ns;
+          clamp_cell_for_read(P, ph, ci, cj, ck);
+          load_cell(P, cell_index(P, ci, cj, ck), cs);
+          double tau0 = walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, ns);
+          cnt.cellsteps += ns;
+          tau = forced_first(P, ph, rng, cs, tau0);
+        } else if (ph.flags & PH_TAUPEND) {  // drawn by the wavefront scatter stage before a driver switch
+          tau = pl.f[(size_t)F_TAU * pl.S + s];
+          ph.flags &= ~PH_TAUPEND;
+        } else {
+          tau = -log(rng.uniform());
+        }
+        int ns = walk_tau(P, vtab, ph, tau, cs);
+        if (ns > 0) cnt.cellsteps += ns;
+        if (!(ph.flags & PH_ALIVE)) {
+          retire_photon(P, ph, ns >= 0, job, cnt);
+          continue;
+        }
+      } else {  // the wavefront scatter stage already flew this photon to its next scattering point
+        load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
+        at_scatter = false;
+        touched = true;
       }
       // scattering — scattering_car.f90:14-120
       cnt.scatter += 1;
@@ -348,7 +361,7 @@ __device__ __forceinline__ unsigned reserve(unsigned int *ctr, bool want) {
 __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   Counters cnt;
   unsigned long long nrng = 0;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < pl.S; s += gridDim.x * blockDim.x) {
+  for (int s = pl.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < pl.s0 + pl.n; s += gridDim.x * blockDim.x) {
     if (pl.flags[s] & PH_ALIVE) continue;
     if (job->next >= job->count) continue;
     unsigned long long j = atomicAdd(&job->next, 1ULL);
@@ -364,8 +377,8 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
       for (int i = 0; i < P.nobs; ++i) {
         PeelRay pr;
         if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
-        unsigned at = q.direct_base + atomicAdd(q.n_direct, 1u);
-        if (at < q.ray_cap) q.rays[at] = pr;
+        unsigned at = atomicAdd(q.n_direct, 1u);
+        if (at < q.direct_cap) q.rays[q.direct_base + at] = pr;
       }
     }
     int fl = ph.flags;
@@ -398,9 +411,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
     if (nm && (__popc(nm) >= kRefillMin || !hm)) {
       unsigned idx = reserve(q.head_trace, need);
       if (need) {
-        if (idx >= (unsigned)pl.S) exhausted = true;
-        else if (pl.flags[idx] & PH_ALIVE) {
-          slot = (int)idx;
+        if (idx >= (unsigned)pl.n) exhausted = true;
+        else if ((pl.flags[pl.s0 + idx] & (PH_ALIVE | PH_SCATTER)) == PH_ALIVE) {  // alive and not already at a scattering point
+          slot = pl.s0 + (int)idx;
           load_trace_part(pl, slot, ph);
           load_rng(P, pl, slot, ph.id, ph.flags, rng);
           bool leaving;
@@ -415,7 +428,12 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
               mode = 1;
             }
           } else {
-            tau_in = -log(rng.uniform());
+            if (ph.flags & PH_TAUPEND) {  // tau was drawn by the scatter stage, whose local step left the cell
+              tau_in = pl.f[(size_t)F_TAU * pl.S + slot];
+              ph.flags &= ~PH_TAUPEND;
+            } else {
+              tau_in = -log(rng.uniform());
+            }
             mode = 1;
             leaving = true;
           }
@@ -486,18 +504,21 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
 #ifndef LART_SCATTER_MINBLOCKS
 #define LART_SCATTER_MINBLOCKS 2
 #endif
+// LOCAL = the stage also takes the first cell step of the peel ray and of the next flight itself
+// (LART_FLAG_LOCAL_STEPS).  A template so that the default kernel does not carry that code.
+template <bool LOCAL>
 __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   __shared__ VzWarpShared vzsh[kBlock / 32];
-  if (P.dust) load_vtab(P, vtab);
+  if (LOCAL || P.dust) load_vtab(P, vtab);
   VzWarpShared &sh = vzsh[threadIdx.x >> 5];
   Counters cnt;
   unsigned long long nrng = 0;
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * blockDim.x;
-  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < pl.S; base += stride) {
+  for (int base = pl.s0 + blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < pl.s0 + pl.n; base += stride) {
     const int s = base + lane;
-    const bool inb = s < pl.S;
+    const bool inb = s < pl.s0 + pl.n;
     const int fl0 = inb ? pl.flags[s] : 0;
     const bool active = (fl0 & PH_SCATTER) != 0;
     PeelRay *myrays = q.rays + (size_t)(inb ? s : 0) * P.nobs;
@@ -527,6 +548,15 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
                                             : rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, cs.voigt_a, cnt.reject);
     if (!active) continue;
     bool peeled = false;
+    // With local steps the ray toward observer 0 stays in registers: most of them end inside the
+    // photon's own cell (tau cap) and never reach the queue.
+    PeelRay pr0;
+    bool have_pr0 = false;
+    auto emit_ray = [&](int k, bool ok, const PeelRay &pr) {
+      if (LOCAL && k == 0) { have_pr0 = ok; if (ok) pr0 = pr; else myrays[0].kind = -1; }
+      else if (ok) myrays[k] = pr;
+      else myrays[k].kind = -1;
+    };
     if (to_dust) {
       scatter_dust(P, ph, rng, cs, cnt, [&]() {
         peeled = true;
@@ -534,7 +564,7 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
           PeelRay pr;
           bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[k], k, ph, cs, pr)
                                  : peel_dust_nostokes_prepare(P, P.obs[k], k, ph, cs, pr);
-          if (ok) myrays[k] = pr; else myrays[k].kind = -1;
+          emit_ray(k, ok, pr);
         }
       });
       if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
@@ -545,11 +575,48 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
           PeelRay pr;
           bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr)
                                  : peel_resonance_nostokes_prepare(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr);
-          if (ok) myrays[k] = pr; else myrays[k].kind = -1;
+          emit_ray(k, ok, pr);
         }
       });
     }
     if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+    if (LOCAL) {
+      // ---- first cell step of the peel ray (raytrace_to_edge): in an optically thick cell it is the last one
+      if (have_pr0) {
+        Ray r;
+        bool resolved = false;
+        double tau = 0.0;
+        if (ray_setup(P, r, pr0.x, pr0.y, pr0.z, pr0.kx, pr0.ky, pr0.kz, pr0.ic, pr0.jc, pr0.kc, pr0.xfreq, false, &cs)) resolved = true;
+        else if (edge_step(P, vtab, r)) { resolved = true; tau = r.tau; cnt.cellsteps += r.nsteps; }
+        if (resolved) { cnt.peel += 1; peel_deposit(P, pr0, tau, 0u, false); myrays[0].kind = -1; }
+        else myrays[0] = pr0;  // the peel stage walks it (from its start)
+      }
+      // ---- first cell step of the next flight (raytrace_to_tau): most flights end inside the cell
+      if (ph.flags & PH_ALIVE) {
+        const double tau_in = -log(rng.uniform());
+        Ray r;
+        if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true, &cs)) {
+          ph.flags &= ~PH_ALIVE;  // already leaving: dead without tally (raytrace_car.f90:1469-1472)
+          retire_photon(P, ph, false, job, cnt);
+        } else {
+          double xp, yp, zp;
+          const int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
+          if (st == 1) {
+            ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
+            if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
+            ph.kc = r.kc;
+            ph.flags |= PH_SCATTER;
+            cnt.cellsteps += r.nsteps;
+          } else if (st == 2) {
+            cnt.cellsteps += finish_escape(P, ph, r);
+            retire_photon(P, ph, true, job, cnt);
+          } else {  // crossed into the next cell: the trace stage walks it (from its start) with this tau
+            pl.f[(size_t)F_TAU * pl.S + s] = tau_in;
+            ph.flags |= PH_TAUPEND;
+          }
+        }
+      }
+    }
     int fl = ph.flags;
     store_rng(pl, s, rng, fl);
     ph.flags = fl;
@@ -560,12 +627,14 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
 }
 
 // stage 4: raytrace_to_edge for every queued peel ray, per-lane refill, deposit
-__global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ DevParams P, Queues q) {
+__global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ DevParams P, Pool pl, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
   Counters cnt;
-  const unsigned n = min(q.direct_base + *q.n_direct, q.ray_cap);
+  // work items of this partition: its slot rays, then its direct rays
+  const unsigned nslot = (unsigned)pl.n * (unsigned)P.nobs, slot_lo = (unsigned)pl.s0 * (unsigned)P.nobs;
+  const unsigned n = nslot + min(*q.n_direct, q.direct_cap);
   Ray r;
   unsigned mine = 0;
   bool have = false, exhausted = false;
@@ -577,12 +646,15 @@ __global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ D
       unsigned idx = reserve(q.head_peel, need);
       if (need) {
         if (idx >= n) exhausted = true;
-        else if (q.rays[idx].kind >= 0) {
+        else {
+          idx = idx < nslot ? slot_lo + idx : q.direct_base + (idx - nslot);
+          if (q.rays[idx].kind >= 0) {
           mine = idx;
           const PeelRay &pr = q.rays[idx];
           cnt.peel += 1;
           if (ray_setup(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
           else have = true;
+          }
         }
       }
     }
@@ -745,7 +817,17 @@ struct lart_gpu_ctx {
   int device = 0;
   DevParams P{};
   Pool pool{};
-  Queues q{};
+  struct Group {  // one wave pipeline: a pool partition with its own queues, stream and events
+    Pool pool;
+    Queues q;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    std::vector<cudaEvent_t> tev;
+  };
+  std::vector<Group> groups;
+  std::map<int, cudaGraphExec_t> graphs;  // one instantiated graph per wave count (quantum)
+  cudaEvent_t fork = nullptr;
+  PeelRay *rays = nullptr;
   Job *job = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -759,7 +841,7 @@ struct lart_gpu_ctx {
   long long launches = 0;
   bool begun = false;
   std::vector<double> stage;  // host staging for fetch
-  std::vector<cudaEvent_t> tev;  // stage-timing events of one step
+  std::vector<cudaEvent_t> tev;  // stage-timing events of one step (monolithic driver)
   double stage_ms[LART_STAGE_COUNT] = {0, 0, 0, 0};
   long long stage_n[LART_STAGE_COUNT] = {0, 0, 0, 0};
 };
@@ -822,6 +904,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&h->ev0));
   CUDA_OK(cudaEventCreate(&h->ev1));
+  CUDA_OK(cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming));
   const lart_grid &g = cfg->grid;
   const lart_params &p = cfg->par;
   DevParams &P = h->P;
@@ -851,6 +934,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   P.soa = (cfg->flags & LART_FLAG_SOA_GRID) ? 1 : 0;
   P.warp_agg = (cfg->flags & LART_FLAG_NO_WARP_AGG) ? 0 : 1;
   P.flags_serial_vz = (cfg->flags & LART_FLAG_SERIAL_REJECTION) ? 1 : 0;
+  P.local_steps = (cfg->flags & LART_FLAG_LOCAL_STEPS) ? 1 : 0;
   if (!P.soa) {
     Cell *cells = nullptr;
     if ((rc = dalloc(h, &cells, nc, false))) return bail(rc);
@@ -949,13 +1033,29 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   rc = rc ? rc : dalloc(h, &h->pool.kc, S);
   rc = rc ? rc : dalloc(h, &h->pool.flags, S);
   rc = rc ? rc : dalloc(h, &h->job, 1);
-  if (!mono) {
-    h->q.direct_base = (unsigned)((long long)S * P.nobs);
-    h->q.ray_cap = (unsigned)std::min<long long>((long long)S * P.nobs * 2, 0x7fffffffLL);
-    rc = rc ? rc : dalloc(h, &h->q.rays, h->q.ray_cap, true);
+  h->pool.s0 = 0; h->pool.n = S;
+  if (!mono && !rc) {
+    int G = cfg->streams > 0 ? cfg->streams : 4;
+    G = std::max(1, std::min(G, std::min(16, S / 1024 > 0 ? S / 1024 : 1)));
+    const long long nobs = P.nobs;
+    const long long ray_cap = std::min<long long>((long long)S * std::max<long long>(nobs, 1) * 2, 0x7fffffffLL);
+    rc = rc ? rc : dalloc(h, &h->rays, (size_t)ray_cap, true);
     unsigned int *ctr = nullptr;
-    rc = rc ? rc : dalloc(h, &ctr, 4);
-    h->q.n_direct = ctr; h->q.head_trace = ctr + 1; h->q.head_peel = ctr + 2;
+    rc = rc ? rc : dalloc(h, &ctr, 4 * (size_t)G);
+    h->groups.resize(G);
+    int per = ((S / G) + 31) / 32 * 32;
+    for (int g = 0; g < G && !rc; ++g) {
+      lart_gpu_ctx::Group &gr = h->groups[g];
+      gr.pool = h->pool;
+      gr.pool.s0 = std::min(g * per, S);
+      gr.pool.n = (g == G - 1) ? S - gr.pool.s0 : std::min(per, S - gr.pool.s0);
+      gr.q.rays = h->rays;
+      gr.q.n_direct = ctr + 4 * g; gr.q.head_trace = ctr + 4 * g + 1; gr.q.head_peel = ctr + 4 * g + 2;
+      gr.q.direct_base = (unsigned)((long long)S * nobs + (long long)gr.pool.s0 * nobs);
+      gr.q.direct_cap = (unsigned)std::min<long long>((long long)gr.pool.n * nobs, ray_cap - gr.q.direct_base);
+      CUDA_OK(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming));
+    }
   }
   if (rc) return bail(rc);
   h->quantum = cfg->quantum > 0 ? cfg->quantum : (mono ? 32 : 8);
@@ -971,6 +1071,14 @@ int lart_gpu_destroy(lart_gpu_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void *p : h->owned) cudaFree(p);
   for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->fork) cudaEventDestroy(h->fork);
+  for (auto &g : h->groups) {
+    if (g.stream) cudaStreamSynchronize(g.stream);
+    for (cudaEvent_t e : g.tev) cudaEventDestroy(e);
+    if (g.done) cudaEventDestroy(g.done);
+    if (g.stream) cudaStreamDestroy(g.stream);
+  }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -998,40 +1106,80 @@ namespace {
 // slot is left mid-wave between steps, so they can alternate freely).
 int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
   const bool timing = (h->flags & LART_FLAG_STAGE_TIMING) != 0;
-  size_t ne = 0;
-  auto mark = [&]() -> int {  // one event between consecutive stage kernels
+  auto mark = [&](std::vector<cudaEvent_t> &tev, size_t &ne, cudaStream_t st) -> int {  // one event between stage kernels
     if (!timing) return 0;
-    if (ne == h->tev.size()) {
+    if (ne == tev.size()) {
       cudaEvent_t e;
       CUDA_OK(cudaEventCreate(&e));
-      h->tev.push_back(e);
+      tev.push_back(e);
     }
-    CUDA_OK(cudaEventRecord(h->tev[ne++], h->stream));
+    CUDA_OK(cudaEventRecord(tev[ne++], st));
     return 0;
   };
   CUDA_OK(cudaEventRecord(h->ev0, h->stream));
   if (mono) {
-    if (int rc = mark()) return rc;
+    size_t ne = 0;
+    if (int rc = mark(h->tev, ne, h->stream)) return rc;
     k_mono<<<(h->pool.S + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
-    if (int rc = mark()) return rc;
+    if (int rc = mark(h->tev, ne, h->stream)) return rc;
     h->launches += 1;
   } else {
-    const int gemit = std::min((h->pool.S + kBlock - 1) / kBlock, h->nsm * 8);
-    const int gwalk = std::min((h->pool.S + kBlock - 1) / kBlock, h->nsm * 4);
-    const int gscat = std::min((h->pool.S + kBlock - 1) / kBlock, h->nsm * 8);
-    for (int w = 0; w < qn; ++w) {
-      k_wf_reset<<<1, 1, 0, h->stream>>>(h->q);
-      if (int rc = mark()) return rc;
-      k_wf_emit<<<gemit, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, h->q);
-      if (int rc = mark()) return rc;
-      k_wf_trace<<<gwalk, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, h->q);
-      if (int rc = mark()) return rc;
-      k_wf_scatter<<<gscat, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, h->q);
-      if (int rc = mark()) return rc;
-      k_wf_peel<<<gwalk, kBlock, 0, h->stream>>>(h->P, h->q);
-      if (int rc = mark()) return rc;
-      h->launches += 5;
+    // Every pool partition is an independent wave pipeline on its own stream: while one partition waits for
+    // the longest ray of its trace/peel kernel, the others keep the SMs busy.  The whole step (all partitions,
+    // all waves: 5*G*qn launches) is captured once into a CUDA graph, so a step costs one graph launch.
+    const int G = (int)h->groups.size();
+    auto issue = [&](bool with_marks) -> int {
+      std::vector<size_t> ne(G, 0);
+      for (int w = 0; w < qn; ++w) {
+        for (int gi = 0; gi < G; ++gi) {
+          lart_gpu_ctx::Group &g = h->groups[gi];
+          const int nb = (g.pool.n + kBlock - 1) / kBlock;
+          const int grid = std::max(1, std::min(nb, h->nsm * 2));
+          k_wf_reset<<<1, 1, 0, g.stream>>>(g.q);
+          if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
+          k_wf_emit<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
+          k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
+          if (h->P.local_steps) k_wf_scatter<true><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          else k_wf_scatter<false><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
+          k_wf_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
+          if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
+        }
+      }
+      return 0;
+    };
+    if (timing) {  // per-stage events: plain launches
+      for (auto &g : h->groups) CUDA_OK(cudaStreamWaitEvent(g.stream, h->ev0, 0));
+      if (int rc = issue(true)) return rc;
+      for (auto &g : h->groups) {
+        CUDA_OK(cudaEventRecord(g.done, g.stream));
+        CUDA_OK(cudaStreamWaitEvent(h->stream, g.done, 0));
+      }
+    } else {
+      auto it = h->graphs.find(qn);
+      if (it == h->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        CUDA_OK(cudaEventRecord(h->fork, h->stream));
+        for (auto &g : h->groups) CUDA_OK(cudaStreamWaitEvent(g.stream, h->fork, 0));
+        int rc = issue(false);
+        for (auto &g : h->groups) {
+          cudaEventRecord(g.done, g.stream);
+          cudaStreamWaitEvent(h->stream, g.done, 0);
+        }
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (rc) return rc;
+        if (ce != cudaSuccess) return fail(std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_OK(cudaGraphDestroy(graph));
+        it = h->graphs.emplace(qn, exec).first;
+      }
+      CUDA_OK(cudaGraphLaunch(it->second, h->stream));
     }
+    h->launches += 5LL * G * qn;
   }
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
   Job j;
@@ -1048,13 +1196,14 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
       h->stage_ms[LART_STAGE_TRACE] += t;
       h->stage_n[LART_STAGE_TRACE] += 1;
     } else {
-      for (int w = 0; w < qn; ++w)
-        for (int k = 0; k < LART_STAGE_COUNT; ++k) {
-          float t = 0.f;
-          CUDA_OK(cudaEventElapsedTime(&t, h->tev[5 * w + k], h->tev[5 * w + k + 1]));
-          h->stage_ms[k] += t;
-          h->stage_n[k] += 1;
-        }
+      for (auto &g : h->groups)
+        for (int w = 0; w < qn; ++w)
+          for (int k = 0; k < LART_STAGE_COUNT; ++k) {
+            float t = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&t, g.tev[5 * w + k], g.tev[5 * w + k + 1]));
+            h->stage_ms[k] += t;
+            h->stage_n[k] += 1;
+          }
     }
   }
   if (in_flight) *in_flight = (int64_t)h->count - (int64_t)j.done;

@@ -119,10 +119,10 @@ def test_results_do_not_depend_on_pool_size_or_scheduling():
     a = run_gpu(small_sphere(), pool_slots=256, quantum=3)
     b = run_gpu(small_sphere(), pool_slots=8192, quantum=16)
     c = run_gpu(small_sphere(), flags=capi.FLAG_MONOLITHIC | capi.FLAG_SOA_GRID | capi.FLAG_NO_WARP_AGG, pool_slots=512)
-    d = run_gpu(small_sphere(), flags=capi.FLAG_SERIAL_REJECTION, pool_slots=8192, quantum=16)
+    d = run_gpu(small_sphere(), flags=capi.FLAG_SERIAL_REJECTION | capi.FLAG_LOCAL_STEPS, pool_slots=8192, quantum=16)
     for name in ("nscatt_gas", "xfreq2", "rp", "Q", "U"):
         assert np.array_equal(a.allph(name), b.allph(name)), name      # same driver: bit-identical
-        assert np.array_equal(a.allph(name), d.allph(name)), name      # serial vs warp-cooperative rejection sampler
+        assert np.array_equal(a.allph(name), d.allph(name)), name      # serial sampler + local steps
         assert np.allclose(a.allph(name), c.allph(name), rtol=1e-9, atol=1e-12), name  # other driver: other FMA contraction
     assert np.allclose(a.observer_cube("I"), b.observer_cube("I"), rtol=1e-10, atol=1e-18)
     assert np.allclose(a.observer_cube("Q"), c.observer_cube("Q"), rtol=1e-9, atol=1e-16)

@@ -117,12 +117,12 @@ def cpu_sample(args, events_per_photon, seconds, threads=None):
     from oracle import oracle
     threads = threads or oracle.hardware_threads()
     m = build_model(args, 10 ** 6)
-    n = 2 * threads
+    n = 4000 * threads  # calibration pass, long enough to amortise thread start-up
     t0 = time.perf_counter()
     oracle.run(m, rng_mode=0, nthreads=threads, first_id=1, count=n, max_events=events_per_photon, seed=args.seed)
     dt = time.perf_counter() - t0
     rate = m.counters["n_scatter"] / dt
-    n = int(max(threads, min(2_000_000, rate * seconds / max(events_per_photon, 1))))
+    n = int(max(threads, min(200_000_000, rate * seconds / max(events_per_photon, 1))))
     n = (n // threads) * threads
     m.zero_tallies()
     t0 = time.perf_counter()
@@ -171,6 +171,8 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -192,9 +194,9 @@ def run_gpu(args):
     # ------------------------- device-resident arm: `value`  (CUDA-graph launches, no per-stage events)
     first, count, stride = rank + 1, nph // world, world  # run_simulation_mod.f90:150 partition
 
-    def device_arm(flags, warmup, steps):
+    def device_arm(flags, warmup, steps, streams):
         sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=flags,
-                         streams=args.streams)
+                         streams=streams)
         sim.begin(first, count, stride)
         for _ in range(warmup):
             sim.step(args.quantum)
@@ -217,7 +219,7 @@ def run_gpu(args):
         sim.close()
         return ms_, launches_, stage_, c_, S_, wall_, clk_
 
-    dev_ms, launches, _, c, S, wall, clk = device_arm(args.flags, args.warmup, args.steps)
+    dev_ms, launches, _, c, S, wall, clk = device_arm(args.flags, args.warmup, args.steps, args.streams)
     t = torch.tensor([dev_ms, c["n_scatter"], c["n_cellsteps"], c["n_peel"], c["n_photons_done"], c["n_rng"], float(launches)],
                      dtype=torch.float64, device="cuda")
     tmax = t.clone()
@@ -227,8 +229,9 @@ def run_gpu(args):
     max_ms = float(tmax[0])
     n_scatter, n_cell, n_peel, n_done, n_rng, n_launch = (float(t[i]) for i in range(1, 7))
     value = n_scatter / (max_ms * 1e-3)
-    # a second, short pass with CUDA events around every stage kernel (plain launches) feeds the roofline
-    dev_ms, _, stage, c, _, _, _ = device_arm(args.flags | capi.FLAG_STAGE_TIMING, max(args.warmup, 3), min(args.steps, 4))
+    # a second, short pass with CUDA events around every stage kernel feeds the roofline: plain launches on ONE
+    # stream, so that every kernel is timed alone (in the value arm the partitions' kernels overlap)
+    dev_ms, _, stage, c, _, _, _ = device_arm(args.flags | capi.FLAG_STAGE_TIMING, max(args.warmup, 3), min(args.steps, 4), 1)
 
     # ------------------------- FP64 issue peak + roofline of the dominant kernel (rank 0)
     hbm_peak, peak_src = measured_peaks()

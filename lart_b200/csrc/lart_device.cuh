@@ -67,6 +67,7 @@ struct DevParams {
   unsigned long long seed;
   double xfreq0, xs, ys, zs, source_rmax, albedo, hgg, voigt_a0, Dfreq0, gaussian_sigma_x, mu_min, dmu;
   double E1, E2, E3, g_recoil0;
+  double rr_p2, rr_inv;  // rand_resonance: sqrt((4-E1)/(3E1)) and 1/(E1 p2^3), E1 > 0
   int nmu, spectral_type, source_geometry;
   int zonly, dust, soa, comoving_source, recoil, core_skip, core_skip_global, use_stokes, use_reduced_wgt;
   int save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D, save_direc0, save_all_photons;
@@ -104,8 +105,10 @@ LART_DEV void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &
   }
 }
 
+// per-thread work counters of ONE kernel launch (32 bits are plenty; they are summed into FP64 totals)
+typedef unsigned int ctr_t;
 struct Counters {
-  unsigned long long scatter = 0, cellsteps = 0, peel = 0, rng = 0, reject = 0, photons = 0;
+  ctr_t scatter = 0, cellsteps = 0, peel = 0, rng = 0, reject = 0, photons = 0;
 };
 
 // Stream layout (shared with the CPU oracle): every call consumes ONE Philox block of
@@ -114,7 +117,7 @@ struct Counters {
 // the only generator state that travels with a photon is the block counter.
 struct Rng {
   unsigned long long seed, stream, nblk;
-  unsigned long long nrng;  // uniforms drawn through this object (work counter)
+  ctr_t nrng;  // uniforms drawn through this object (work counter)
   bool gauss_stored;
   double gset;
   LART_DEV void start(unsigned long long seed_, unsigned long long id, unsigned long long nblk_ = 0) {
@@ -144,7 +147,7 @@ struct Rng {
   }
   // rand_gauss1 — random_mt.f90:964-988 (Marsaglia polar; the spare deviate is kept
   // per photon stream, never shared between photons)
-  LART_DEV double gauss(unsigned long long &nreject) {
+  LART_DEV double gauss(ctr_t &nreject) {
     if (gauss_stored) { gauss_stored = false; return gset; }
     double v1, v2, rsq;
     for (;;) {
@@ -375,7 +378,7 @@ struct Photon {
 // random variates
 // ---------------------------------------------------------------------------
 // rand_resonance_vz_seon — random_mt.f90:2562-2696
-LART_DEV double rand_resonance_vz(Rng &r, double x0in, double a, unsigned long long &nrej) {
+LART_DEV double rand_resonance_vz(Rng &r, double x0in, double a, ctr_t &nrej) {
   const double xc = 1.0 + 1.4142135623730951;
   const double two_over_PI = 2.0 / kPi;
   double x0 = fabs(x0in), vz;
@@ -466,7 +469,7 @@ LART_DEV void philox_uniform2(unsigned long long seed, unsigned long long id, un
 }
 
 // Must be called by all 32 lanes of a converged warp; `mine` = this lane has a photon to sample.
-LART_DEV double rand_resonance_vz_warp(VzWarpShared &sh, bool mine, Rng &r, double x0in, double a, unsigned long long &nrej) {
+LART_DEV double rand_resonance_vz_warp(VzWarpShared &sh, bool mine, Rng &r, double x0in, double a, ctr_t &nrej) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -579,7 +582,7 @@ LART_DEV double rand_resonance_vz_warp(VzWarpShared &sh, bool mine, Rng &r, doub
         int used = tpj;
         if (accm & my) { t1 = sh.r0[rank]; delt = sh.r1[rank]; used = sh.first[rank] + 1; todo = false; }
         r.nblk += (unsigned long long)used * (mode == 0 ? 1 : 2);
-        r.nrng += (unsigned long long)used * (mode == 0 ? 2 : 3);
+        r.nrng += used * (mode == 0 ? 2 : 3);
         nrej += used;
       }
       __syncwarp();
@@ -605,6 +608,14 @@ LART_DEV double rand_resonance(Rng &r, double E1) {
   return 2.0 * r.uniform() - 1.0;
 }
 
+// the E1 > 0 branch with the two per-run constants p2 and 1/(E1 p2^3) supplied by the host
+LART_DEV double rand_resonance_fast(Rng &r, const DevParams &P) {
+  if (!(P.E1 > 0.0)) return rand_resonance(r, P.E1);
+  double Q = (4.0 * r.uniform() - 2.0) * P.rr_inv;
+  double W = cbrt(Q + sqrt(Q * Q + 1.0));
+  return P.rr_p2 * (W - 1.0 / W);
+}
+
 // rand_henyey_greenstein — random_mt.f90:3022-3042
 LART_DEV double rand_hg(Rng &r, double g) {
   double x = r.uniform();
@@ -615,7 +626,7 @@ LART_DEV double rand_hg(Rng &r, double g) {
 }
 
 // rand_voigt — random_mt.f90:3062-3083
-LART_DEV double rand_voigt(Rng &r, double a, unsigned long long &nrej) {
+LART_DEV double rand_voigt(Rng &r, double a, ctr_t &nrej) {
   double c = tan(kPi * r.uniform() - kHalfPi);
   return a * c + r.gauss(nrej) * (1.0 / 1.4142135623730951);
 }
@@ -708,8 +719,8 @@ LART_DEV double pixel_angle(double y, double x) {
 LART_DEV bool peel_geometry(const DevObserver &ob, const Photon &ph, PeelRay &pr, double &r2) {
   double kx = ob.x - ph.x, ky = ob.y - ph.y, kz = ob.z - ph.z;
   r2 = kx * kx + ky * ky + kz * kz;
-  double r = sqrt(r2);
-  kx /= r; ky /= r; kz /= r;
+  double ir = 1.0 / sqrt(r2);  // one reciprocal instead of three divisions
+  kx *= ir; ky *= ir; kz *= ir;
   pr.x = ph.x; pr.y = ph.y; pr.z = ph.z; pr.kx = kx; pr.ky = ky; pr.kz = kz;
   pr.ic = ph.ic; pr.jc = ph.jc; pr.kc = ph.kc;
   const double *R = ob.R;
@@ -739,8 +750,9 @@ LART_DEV void stokes_azimuth(const Photon &ph, const PeelRay &pr, double cost, d
   sint = sqrt(1.0 - cost * cost);
   if (sint == 0.0) { cosp = 1.0; sinp = 0.0; }
   else {
-    cosp = (pr.kx * ph.mx + pr.ky * ph.my + pr.kz * ph.mz) / sint;
-    sinp = (pr.kx * ph.nx + pr.ky * ph.ny + pr.kz * ph.nz) / sint;
+    double is = 1.0 / sint;
+    cosp = (pr.kx * ph.mx + pr.ky * ph.my + pr.kz * ph.mz) * is;
+    sinp = (pr.kx * ph.nx + pr.ky * ph.ny + pr.kz * ph.nz) * is;
   }
   nx = -sinp * ph.mx + cosp * ph.nx;
   ny = -sinp * ph.my + cosp * ph.ny;
@@ -791,8 +803,9 @@ LART_DEV bool peel_resonance_stokes_prepare(const DevParams &P, const DevObserve
   double xref = (xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
   int ixf = freq_bin(P, xref);
   double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
-  double Iobs = (S11 + S12 * Q0) / kFourPi, Qobs = (S12 + S22 * Q0) / kFourPi;
-  double Uobs = (S33 * U0) / kFourPi, Vobs = (S44 * ph.V) / kFourPi;
+  const double i4pi = 1.0 / kFourPi;
+  double Iobs = (S11 + S12 * Q0) * i4pi, Qobs = (S12 + S22 * Q0) * i4pi;
+  double Uobs = (S33 * U0) * i4pi, Vobs = (S44 * ph.V) * i4pi;
   pr.xfreq = xfreq;
   pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
   pr.obs = iobs; pr.kind = PEEL_STOKES;
@@ -990,7 +1003,7 @@ LART_DEV void rotate_k(Photon &ph, double cost, double sint, double cosp, double
 }
 // azimuth by rejection — scattering_car.f90:364-371 / :280-287.  cos(2phi), sin(2phi) come
 // from the double-angle identities of (cos phi, sin phi) = sincospi(2 xi): one libm call per trial.
-LART_DEV void sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11, unsigned long long &nrej, double &cosp,
+LART_DEV void sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11, ctr_t &nrej, double &cosp,
                                 double &sinp) {
   double env = 1.0 + fabs(S12overS11) * sqrt(ph.Q * ph.Q + ph.U * ph.U);
   for (;;) {
@@ -1022,7 +1035,7 @@ LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const Ce
   ph.nsg += ph.wgt;
   // do_resonance1 — line_mod.f90:108-139
   double xfreq_atom = ph.xfreq - uz;
-  double cost = rand_resonance(r, P.E1);
+  double cost = rand_resonance_fast(r, P);
   double sint = sqrt(1.0 - cost * cost);
   double cost2 = cost * cost;
   double S22 = 0.75 * P.E1 * (cost2 + 1.0), S11 = S22 + P.E2, S12 = 0.75 * P.E1 * (cost2 - 1.0);
@@ -1053,7 +1066,8 @@ LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const Ce
     double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
     double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
     double I1 = S11 + S12 * Q0, Q1 = S12 + S22 * Q0, U1 = S33 * U0, V1 = S44 * ph.V;
-    ph.Q = Q1 / I1; ph.U = U1 / I1; ph.V = V1 / I1;
+    double iI = 1.0 / I1;
+    ph.Q = Q1 * iI; ph.U = U1 * iI; ph.V = V1 * iI;
     rotate_triad(ph, cost, sint, cosp, sinp);
   } else {
     rotate_k(ph, cost, sint, cosp, sinp);

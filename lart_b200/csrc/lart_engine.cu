@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <cstdio>
 #include <cstring>
@@ -93,13 +94,21 @@ __device__ __forceinline__ void load_trace_part(const Pool &pl, int s, Photon &p
   ph.xfreq = f[F_XFREQ * S + s]; ph.wgt = f[F_WGT * S + s];
   ph.id = pl.id[s]; ph.ic = pl.ic[s]; ph.jc = pl.jc[s]; ph.kc = pl.kc[s]; ph.flags = pl.flags[s];
 }
-__device__ __forceinline__ void load_rest(const Pool &pl, int s, Photon &ph) {
+__device__ __forceinline__ void load_stokes(const Pool &pl, int s, Photon &ph) {
+  const double *f = pl.f;
+  size_t S = pl.S;
+  ph.Q = f[F_Q * S + s]; ph.U = f[F_U * S + s]; ph.V = f[F_V * S + s];
+}
+__device__ __forceinline__ void load_triad(const Pool &pl, int s, Photon &ph) {
   const double *f = pl.f;
   size_t S = pl.S;
   ph.mx = f[F_MX * S + s]; ph.my = f[F_MY * S + s]; ph.mz = f[F_MZ * S + s];
   ph.nx = f[F_NX * S + s]; ph.ny = f[F_NY * S + s]; ph.nz = f[F_NZ * S + s];
-  ph.xfreq_ref = f[F_XREF * S + s]; ph.Q = f[F_Q * S + s]; ph.U = f[F_U * S + s]; ph.V = f[F_V * S + s];
-  ph.nsg = f[F_NSG * S + s]; ph.nsd = f[F_NSD * S + s];
+  ph.xfreq_ref = f[F_XREF * S + s]; ph.nsg = f[F_NSG * S + s]; ph.nsd = f[F_NSD * S + s];
+}
+__device__ __forceinline__ void load_rest(const Pool &pl, int s, Photon &ph) {
+  load_stokes(pl, s, ph);
+  load_triad(pl, s, ph);
 }
 __device__ __forceinline__ void store_trace_part(const Pool &pl, int s, const Photon &ph) {
   double *f = pl.f;
@@ -135,9 +144,9 @@ __device__ __forceinline__ void load_vtab(const DevParams &P, double *vtab) {
 }
 
 // warp-reduce the work counters and add them to the tally buffer (as doubles)
-__device__ void flush_counters(const DevParams &P, Counters &c, unsigned long long nrng) {
+__device__ void flush_counters(const DevParams &P, Counters &c, ctr_t nrng) {
   c.rng += nrng;
-  unsigned long long v[6] = {c.photons, c.scatter, c.cellsteps, c.peel, c.rng, c.reject};
+  unsigned long long v[6] = {c.photons, c.scatter, c.cellsteps, c.peel, c.rng, c.reject};  // widened for the warp sum
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
     unsigned long long x = v[q];
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
   load_vtab(P, vtab);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   Counters cnt;
-  unsigned long long nrng = 0;
+  ctr_t nrng = 0;
   if (s < pl.S) {  // the monolithic driver always works on the whole pool
     Photon ph;
     Rng rng;
@@ -360,7 +369,7 @@ __device__ __forceinline__ unsigned reserve(unsigned int *ctr, bool want) {
 // stage 1: refill dead slots from the job queue
 __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   Counters cnt;
-  unsigned long long nrng = 0;
+  ctr_t nrng = 0;
   for (int s = pl.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < pl.s0 + pl.n; s += gridDim.x * blockDim.x) {
     if (pl.flags[s] & PH_ALIVE) continue;
     if (job->next >= job->count) continue;
@@ -396,7 +405,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
   Counters cnt;
-  unsigned long long nrng = 0;
+  ctr_t nrng = 0;
   Ray r;
   Photon ph;
   Rng rng;
@@ -513,7 +522,7 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
   if (LOCAL || P.dust) load_vtab(P, vtab);
   VzWarpShared &sh = vzsh[threadIdx.x >> 5];
   Counters cnt;
-  unsigned long long nrng = 0;
+  ctr_t nrng = 0;
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * blockDim.x;
   for (int base = pl.s0 + blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < pl.s0 + pl.n; base += stride) {
@@ -531,7 +540,6 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
     bool to_dust = false;
     if (active) {
       load_trace_part(pl, s, ph);
-      load_rest(pl, s, ph);
       ph.flags &= ~PH_SCATTER;
       load_rng(P, pl, s, ph.id, ph.flags, rng);
       load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
@@ -547,6 +555,7 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
     const double uz_w = (P.flags_serial_vz) ? (resonant ? rand_resonance_vz(rng, ph.xfreq, cs.voigt_a, cnt.reject) : 0.0)
                                             : rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, cs.voigt_a, cnt.reject);
     if (!active) continue;
+    load_rest(pl, s, ph);  // after the sampler: keeps its register footprint small
     bool peeled = false;
     // With local steps the ray toward observer 0 stays in registers: most of them end inside the
     // photon's own cell (tau cap) and never reach the queue.
@@ -751,7 +760,7 @@ __global__ void k_sample_batch(int kind, unsigned long long seed, long long n, c
     const bool mine = i < n;
     Rng r;
     r.start(seed, (unsigned long long)(mine ? (ids ? ids[i] : i) : 0));
-    unsigned long long nrej = 0;
+    ctr_t nrej = 0;
     const double q0 = (mine && p0) ? p0[i] : 0.0, q1 = (mine && p1) ? p1[i] : 1.0;
     for (int j = 0; j < ndraw; ++j) {
       double v = 0.0;
@@ -945,6 +954,10 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   P.source_rmax = p.source_rmax; P.albedo = p.albedo; P.hgg = p.hgg; P.voigt_a0 = p.voigt_a0; P.Dfreq0 = p.Dfreq0;
   P.gaussian_sigma_x = p.gaussian_sigma_x; P.mu_min = p.mu_min; P.dmu = p.dmu; P.nmu = p.nmu;
   P.E1 = cfg->line.E1; P.E2 = cfg->line.E2; P.E3 = cfg->line.E3; P.g_recoil0 = cfg->line.g_recoil0;
+  if (P.E1 > 0.0) {
+    P.rr_p2 = std::sqrt((4.0 - P.E1) / (3.0 * P.E1));
+    P.rr_inv = 1.0 / (P.E1 * (P.rr_p2 * P.rr_p2 * P.rr_p2));
+  }
   P.spectral_type = p.spectral_type; P.source_geometry = p.source_geometry;
   P.zonly = (p.xy_periodic && g.nx == 1 && g.ny == 1) ? 1 : 0;
   P.comoving_source = p.comoving_source; P.recoil = p.recoil; P.core_skip = p.core_skip; P.core_skip_global = p.core_skip_global;

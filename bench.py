@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--workload", default="sphere_peel_tau1e7", choices=sorted(WORKLOADS))
     ap.add_argument("--quantum", type=int, default=32, help="scatterings per photon slot per step")
-    ap.add_argument("--pool-slots", type=int, default=0, help="photons in flight per GPU (0 = auto: 148*8192)")
+    ap.add_argument("--pool-slots", type=int, default=0, help="photons in flight per GPU (0 = auto: 148*16384)")
     ap.add_argument("--flags", type=int, default=0, help="LART_FLAG_* bits (1 SoA grid, 2 no warp aggregation, 4 monolithic)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -181,7 +181,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    S_auto = args.pool_slots or 148 * 8192
+    S_auto = args.pool_slots or 148 * 16384
     total_steps = args.warmup + args.steps
     import lart_b200  # noqa: F401
     nph = S_auto * world * 4  # far more ids than slots: the queue never runs dry, nobody finishes tau0 = 1e7 anyway

@@ -140,7 +140,7 @@ typedef struct lart_config {
   int32_t quantum;                 /* scattering events per slot per lart_gpu_step; 0 = auto */
   int32_t flags;                   /* LART_FLAG_*                           */
   int32_t streams;                 /* wave pipelines: the pool is split into this many partitions,
-                                      each advanced on its own CUDA stream; 0 = auto (4) */
+                                      each advanced on its own CUDA stream; 0 = auto (6) */
   int32_t pad_;
 } lart_config;
 

@@ -130,8 +130,10 @@ struct Rng {
     w1 = (unsigned long long)c2 | ((unsigned long long)c3 << 32);
     ++nblk;
   }
+  // ((w>>12)+0.5)*2^-52 without an integer->double conversion: the 52 bits become the mantissa of a
+  // double in [1,2); subtracting 1-2^-53 is exact and yields (2m+1)*2^-53, the same value bit for bit.
   static LART_DEV double open01(unsigned long long w) {
-    return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+    return __longlong_as_double((long long)(0x3FF0000000000000ULL | (w >> 12))) - (1.0 - 1.0 / 9007199254740992.0);
   }
   LART_DEV double uniform() {
     unsigned long long w0, w1;
@@ -260,7 +262,7 @@ LART_DEV bool axis_setup(double k, double p, int &cell, int n, const double *fac
   step = pos ? 1 : -1;
   double f = pos ? __ldg(face + cell) : flo;
   t = DSUB(f, p) / k;
-  del = d / fabs(k);
+  del = -1.0;  // d/|k|, computed by ray_advance at the first crossing of this axis (most rays end in their first cell)
   return false;
 }
 
@@ -307,14 +309,17 @@ LART_DEV bool ray_advance(const DevParams &P, Ray &r, int axis) {
   if (axis == 1) {
     r.ic += r.istep;
     if (r.ic < 1 || r.ic > P.nx) { r.ic -= r.istep; return false; }
+    if (r.delx < 0.0) r.delx = P.dx / fabs(r.kx);
     r.tx = DADD(r.tx, r.delx);
   } else if (axis == 2) {
     r.jc += r.jstep;
     if (r.jc < 1 || r.jc > P.ny) { r.jc -= r.jstep; return false; }
+    if (r.dely < 0.0) r.dely = P.dy / fabs(r.ky);
     r.ty = DADD(r.ty, r.dely);
   } else {
     r.kc += r.kstep;
     if (r.kc < 1 || r.kc > P.nz) { r.kc -= r.kstep; return false; }
+    if (r.delz < 0.0) r.delz = P.dz / fabs(r.kz);
     r.tz = DADD(r.tz, r.delz);
   }
   return true;

@@ -1029,7 +1029,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   h->flags = cfg->flags;
   const bool mono = (cfg->flags & LART_FLAG_MONOLITHIC) != 0;
   int S = cfg->pool_slots;
-  if (S <= 0) S = mono ? h->nsm * 2048 : h->nsm * 8192;
+  if (S <= 0) S = mono ? h->nsm * 2048 : h->nsm * 16384;
   {
     // keep the ray queue below ~3 GB when many observers are configured
     long long per_slot = (long long)sizeof(PeelRay) * std::max(1, P.nobs);
@@ -1048,7 +1048,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   rc = rc ? rc : dalloc(h, &h->job, 1);
   h->pool.s0 = 0; h->pool.n = S;
   if (!mono && !rc) {
-    int G = cfg->streams > 0 ? cfg->streams : 4;
+    int G = cfg->streams > 0 ? cfg->streams : 6;
     G = std::max(1, std::min(G, std::min(16, S / 1024 > 0 ? S / 1024 : 1)));
     const long long nobs = P.nobs;
     const long long ray_cap = std::min<long long>((long long)S * std::max<long long>(nobs, 1) * 2, 0x7fffffffLL);

@@ -253,7 +253,8 @@ def run_gpu(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")  # dram__bytes_read+write per launch from `ncu --set full`
     if os.path.exists(tpath) and not mono:
-        traffic = json.load(open(tpath)).get("k_wf_scatter_bytes_per_launch")
+        tj = json.load(open(tpath))  # profiled at tj["pool_slots"] scatterings per launch; scale to this run's launch
+        traffic = tj["k_wf_scatter_bytes_per_launch"] / tj["pool_slots"] * (c["n_scatter"] / max(sc_n, 1))
     roof = {"bound": "hbm", "kernel": "k_wf_scatter" if not mono else "k_mono",
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
             "peak_source": peak_src, "bytes_per_scattering": bytes_per_scatter,

@@ -41,7 +41,7 @@ def histories_equal(mg, mo, min_frac=0.995, geom_rtol=1e-8):
 
 def tallies_close(mg, mo, same_frac):
     tol = 4 * (1 - same_frac) + 1e-9
-    for name in ("Jout", "Jin", "Jabs"):
+    for name in ("Jout", "Jin", "Jabs", "Jmu"):
         a, b = mg.spectrum(name), mo.spectrum(name)
         if a is None or b is None:
             assert a is None and b is None, name

@@ -247,26 +247,27 @@ struct Ray {
   int nsteps;
 };
 
+// One straight-line path for both signs of k (no divergent branch around the divide): the special cases of
+// raytrace_car.f90:27-44 — already outside (k>0), sitting on the lower face (k<0) — become predicates.
+// -d/k == d/|k| bit for bit; the increment itself is computed lazily by ray_advance.
 LART_DEV bool axis_setup(double k, double p, int &cell, int n, const double *face, double d, int &step, double &t,
                          double &del, bool eq_test) {
-  if (k == 0.0) { step = 0; t = kHugest; del = kHugest; return false; }
-  const bool pos = k > 0.0;
-  // the special cases first (raytrace_car.f90:27-44): already outside (k>0), or sitting on the lower face (k<0)
-  double flo = __ldg(face + cell - 1);
-  if (pos) {
-    if (cell > n && (eq_test ? (flo == p) : (flo <= p))) return true;
-  } else if (flo == p) {
-    if (cell > 1) { cell -= 1; flo = __ldg(face + cell - 1); } else return true;
-  }
-  // one branch-free path for both signs: -d/k == d/|k| bit for bit
-  step = pos ? 1 : -1;
-  double f = pos ? __ldg(face + cell) : flo;
-  t = DSUB(f, p) / k;
-  del = -1.0;  // d/|k|, computed by ray_advance at the first crossing of this axis (most rays end in their first cell)
-  return false;
+  const bool pos = k > 0.0, neg = k < 0.0;
+  const double flo = __ldg(face + cell - 1);
+  bool leave = pos && cell > n && (eq_test ? (flo == p) : (flo <= p));
+  const bool onface = neg && flo == p;
+  leave = leave || (onface && cell <= 1);
+  cell -= (onface && cell > 1) ? 1 : 0;
+  const int fi = pos ? min(cell, n) : cell - 1;  // the face ahead (clamped: the reference reads past the end there)
+  const double f = __ldg(face + fi);
+  const double tt = DSUB(f, p) / k;
+  const bool moving = pos || neg;
+  t = moving ? tt : kHugest;
+  del = moving ? -1.0 : kHugest;  // d/|k|, filled in at the first crossing of this axis
+  step = pos ? 1 : (neg ? -1 : 0);
+  return leave;
 }
 
-// returns true when the photon is already leaving the grid (no step is taken)
 // `here` (optional) = record of the start cell when the caller already holds it; it is used
 // unless the on-face rule moved the start into a neighbouring cell.
 LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,

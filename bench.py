@@ -244,10 +244,10 @@ def run_gpu(args):
     flops = 50.0 * steps_local + 300.0 * c["n_scatter"]
     mono = bool(args.flags & 4)
     # Dominant kernel = the scatter stage.  Its algorithmic HBM bytes per scattering: the photon
-    # record is read and written once (21 f64 + id + block counter + 4 i32 = 200 B each way) and one 112-B peel-ray
+    # record is read and written once (22 f64 + id + block counter + 4 i32 = 208 B each way) and one 144-B peel-ray
     # descriptor is written per observer.
     nobs = max(int(cfg.par.nobs), 0)
-    bytes_per_scatter = 2 * 200 + 112 * nobs
+    bytes_per_scatter = 2 * 208 + 144 * nobs
     sc_ms, sc_n = stage["scatter"] if not mono else stage["trace"]
     ach = bytes_per_scatter * c["n_scatter"] / (sc_ms * 1e-3) / 1e9 if sc_ms > 0 else 0.0
     traffic = None

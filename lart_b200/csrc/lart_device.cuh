@@ -93,7 +93,12 @@ enum { A_RP0 = 0, A_RP, A_XFREQ1, A_XFREQ2, A_NSG, A_NSD, A_I, A_Q, A_U, A_V };
 // One block gives two 64-bit words; each word maps to the reference's open
 // interval (0,1): ((w>>12)+0.5)*2^-52 — random_mt.f90:628-629.
 // ---------------------------------------------------------------------------
-LART_DEV void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+#ifdef LART_PHILOX_NOINLINE
+__device__ __noinline__
+#else
+LART_DEV
+#endif
+void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;  // hi|lo in one IMAD.WIDE.U32
@@ -696,13 +701,28 @@ LART_DEV void tally_Jout(const DevParams &P, double xref, double kz, double w) {
 
 // A peel-off ray waiting for its optical depth: everything the deposit needs.
 enum { PEEL_DIRECT = 0, PEEL_STOKES = 1, PEEL_NOSTOKES = 2 };
-struct PeelRay {
+struct __align__(16) PeelRay {  // 144 B = nine 16-byte chunks, moved with 128-bit loads/stores
   double x, y, z, kx, ky, kz, xfreq;
   double wa, wb;           // weight factors around exp(-tau): wgt = wa*exp(-tau)*wb
   double sI, sQ, sU, sV;   // detector-frame Stokes per unit weight (Stokes kinds)
   int ic, jc, kc;
   int obs, pix, ixf, kind;  // pix = (ix-1)+nxim*(iy-1); ixf 1-based or 0 when outside the cube
+  int pad_[3];
 };
+static_assert(sizeof(PeelRay) == 144, "PeelRay must be nine 16-byte chunks");
+LART_DEV void ray_store(PeelRay *dst, const PeelRay &src) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(&src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) d[i] = s[i];
+}
+LART_DEV void ray_load(PeelRay &dst, const PeelRay *src) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(&dst);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) d[i] = s[i];
+}
+LART_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // atan2(y, x) for the TAN pixel (peelingoff_rect.f90:356-357).  A distant observer sees the
 // whole grid within a few degrees: for x > 0 and |y/x| < 1/16 the Maclaurin series to t^15

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
         PeelRay pr;
         if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
         unsigned at = atomicAdd(q.n_direct, 1u);
-        if (at < q.direct_cap) q.rays[q.direct_base + at] = pr;
+        if (at < q.direct_cap) ray_store(q.rays + q.direct_base + at, pr);
       }
     }
     int fl = ph.flags;
@@ -540,6 +540,14 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
     bool to_dust = false;
     if (active) {
       load_trace_part(pl, s, ph);
+      {  // the triad, Stokes and bookkeeping columns are needed only after the sampler: warm L1 now
+        const double *f = pl.f + s;
+        const size_t S = pl.S;
+#pragma unroll
+        for (int c = F_MX; c <= F_NSD; ++c)
+          if (c != F_XFREQ && c != F_WGT) prefetch_l1(f + (size_t)c * S);
+        if (ph.flags & PH_GAUSS) prefetch_l1(f + (size_t)F_GSET * S);
+      }
       ph.flags &= ~PH_SCATTER;
       load_rng(P, pl, s, ph.id, ph.flags, rng);
       load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
@@ -563,7 +571,7 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
     bool have_pr0 = false;
     auto emit_ray = [&](int k, bool ok, const PeelRay &pr) {
       if (LOCAL && k == 0) { have_pr0 = ok; if (ok) pr0 = pr; else myrays[0].kind = -1; }
-      else if (ok) myrays[k] = pr;
+      else if (ok) ray_store(myrays + k, pr);
       else myrays[k].kind = -1;
     };
     if (to_dust) {
@@ -598,7 +606,7 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
         if (ray_setup(P, r, pr0.x, pr0.y, pr0.z, pr0.kx, pr0.ky, pr0.kz, pr0.ic, pr0.jc, pr0.kc, pr0.xfreq, false, &cs)) resolved = true;
         else if (edge_step(P, vtab, r)) { resolved = true; tau = r.tau; cnt.cellsteps += r.nsteps; }
         if (resolved) { cnt.peel += 1; peel_deposit(P, pr0, tau, 0u, false); myrays[0].kind = -1; }
-        else myrays[0] = pr0;  // the peel stage walks it (from its start)
+        else ray_store(myrays, pr0);  // the peel stage walks it (from its start)
       }
       // ---- first cell step of the next flight (raytrace_to_tau): most flights end inside the cell
       if (ph.flags & PH_ALIVE) {

@@ -37,6 +37,11 @@ WORKLOADS = {
                             rmax=1.0, nxim=129, nyim=129),
     # BASELINE configs[0]: examples/slab/t4tau7.in
     "slab_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xy_periodic=True, nx=1, ny=1, nz=201),
+    # optically thinner variants of configs[1] (peel rays cross many cells: the DDA walk dominates)
+    "sphere_peel_tau1e4": dict(temperature=1e4, taumax=1e4, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0,
+                               nxfreq=201, nxim=129, nyim=129, distance=1e2),
+    "sphere_peel_tau1e5": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0,
+                               nxfreq=201, nxim=129, nyim=129, distance=1e2),
     # small case for smoke-testing the bench itself
     "tiny": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=61, nxim=33, nyim=33),
 }

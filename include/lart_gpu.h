@@ -141,7 +141,8 @@ typedef struct lart_config {
   int32_t flags;                   /* LART_FLAG_*                           */
   int32_t streams;                 /* wave pipelines: the pool is split into this many partitions,
                                       each advanced on its own CUDA stream; 0 = auto (6) */
-  int32_t pad_;
+  int32_t ray_budget;              /* cell steps a transport or peel ray may take per wave before it is
+                                      parked and resumed (exactly) in the next wave; 0 = auto (32) */
 } lart_config;
 
 enum {

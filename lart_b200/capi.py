@@ -81,7 +81,7 @@ class ScattMat(C.Structure):
 class Config(C.Structure):
     _fields_ = [("grid", Grid), ("par", Params), ("line", Line), ("scatt_mat", ScattMat),
                 ("observers", C.POINTER(Observer)), ("device", C.c_int32), ("pool_slots", C.c_int32),
-                ("quantum", C.c_int32), ("flags", C.c_int32), ("streams", C.c_int32), ("pad_", C.c_int32)]
+                ("quantum", C.c_int32), ("flags", C.c_int32), ("streams", C.c_int32), ("ray_budget", C.c_int32)]
 
 
 OBS_FIELDS = ["scatt", "direc", "direc0", "I", "Q", "U", "V",

@@ -56,6 +56,7 @@ enum { C_PHOTONS = 0, C_SCATTER = 1, C_CELLSTEPS = 2, C_PEEL = 3, C_RNG = 4, C_R
 struct DevParams {
   // grid
   int nx, ny, nz, nxfreq;
+  int nsbx, nsby, nsbz;  // 32^3 super-bricks of the packed cell array per axis
   double dx, dy, dz;
   double xmin, ymin, zmin, xmax, ymax, zmax;
   double Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax;
@@ -222,12 +223,29 @@ struct CellData {
 LART_DEV size_t cell_index(const DevParams &P, int ic, int jc, int kc) {  // 1-based in
   return (size_t)(ic - 1) + (size_t)P.nx * ((size_t)(jc - 1) + (size_t)P.ny * (size_t)(kc - 1));
 }
-LART_DEV void load_cell(const DevParams &P, size_t c, CellData &o) {
+// Packed cell records live in a two-level tiled order: 32x32x32 super-bricks (2 MB, one TLB page) laid out
+// x-fastest, and inside a super-brick the 15-bit Morton code of the local index.  A ray along ANY axis then
+// stays inside one page for up to 32 steps and inside one 4 KB neighbourhood for 4; in plain Fortran order a
+// walk along z jumps nx*ny*64 B (2.6 MB at 201^3) per step — measured 5.7x slower than a walk along x.
+LART_DEV unsigned part1by2_5(unsigned v) {  // spread the low 5 bits: ...edcba -> e00d00c00b00a
+  v = (v | (v << 8)) & 0x100Fu;
+  v = (v | (v << 4)) & 0x10C3u;
+  v = (v | (v << 2)) & 0x1249u;
+  return v;
+}
+LART_DEV size_t cell_slot(const DevParams &P, int ic, int jc, int kc) {  // 1-based in
+  const unsigned i = (unsigned)(ic - 1), j = (unsigned)(jc - 1), k = (unsigned)(kc - 1);
+  const size_t sb = (size_t)(i >> 5) + (size_t)P.nsbx * ((size_t)(j >> 5) + (size_t)P.nsby * (size_t)(k >> 5));
+  const unsigned m = part1by2_5(i & 31u) | (part1by2_5(j & 31u) << 1) | (part1by2_5(k & 31u) << 2);
+  return (sb << 15) + m;
+}
+LART_DEV void load_cell(const DevParams &P, int ic, int jc, int kc, CellData &o) {
   if (!P.soa) {
-    const double2 *q = reinterpret_cast<const double2 *>(P.cells + c);
+    const double2 *q = reinterpret_cast<const double2 *>(P.cells + cell_slot(P, ic, jc, kc));
     double2 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2), e = __ldg(q + 3);
     o.rhokap = a.x; o.voigt_a = a.y; o.Dfreq = b.x; o.vfx = b.y; o.vfy = d.x; o.vfz = d.y; o.rhokapD = e.x;
   } else {
+    const size_t c = cell_index(P, ic, jc, kc);
     o.rhokap = __ldg(P.rhokap + c); o.voigt_a = __ldg(P.voigt_a + c); o.Dfreq = __ldg(P.Dfreq + c);
     o.vfx = __ldg(P.vfx + c); o.vfy = __ldg(P.vfy + c); o.vfz = __ldg(P.vfz + c);
     o.rhokapD = P.dust ? __ldg(P.rhokapD + c) : 0.0;
@@ -289,9 +307,23 @@ LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z
     if (axis_setup(kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, false)) return true;
   }
   if (here && r.ic == ic && r.jc == jc && r.kc == kc) r.cell = *here;
-  else load_cell(P, cell_index(P, r.ic, r.jc, r.kc), r.cell);
+  else load_cell(P, r.ic, r.jc, r.kc, r.cell);
   r.u1 = vdotk(r.cell, kx, ky, kz);
   return false;
+}
+
+// Resume a suspended walk: start point and direction are the ray's own, the DDA state is what was saved.
+LART_DEV void ray_resume(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
+                         double tx, double ty, double tz, double delx, double dely, double delz, double d, double tau,
+                         double xfreq, double u1, int ic, int jc, int kc) {
+  r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
+  r.tx = tx; r.ty = ty; r.tz = tz; r.delx = delx; r.dely = dely; r.delz = delz;
+  r.d = d; r.tau = tau; r.xfreq = xfreq; r.u1 = u1;
+  r.ic = ic; r.jc = jc; r.kc = kc; r.nsteps = 0;
+  r.istep = P.zonly ? 0 : (kx > 0.0 ? 1 : (kx < 0.0 ? -1 : 0));
+  r.jstep = P.zonly ? 0 : (ky > 0.0 ? 1 : (ky < 0.0 ? -1 : 0));
+  r.kstep = kz > 0.0 ? 1 : (kz < 0.0 ? -1 : 0);
+  load_cell(P, ic, jc, kc, r.cell);
 }
 
 // opacity of the current cell at the ray's current frequency (:1488-1494)
@@ -332,7 +364,7 @@ LART_DEV bool ray_advance(const DevParams &P, Ray &r, int axis) {
 }
 LART_DEV void ray_shift(const DevParams &P, Ray &r) {
   double Dold = r.cell.Dfreq;
-  load_cell(P, cell_index(P, r.ic, r.jc, r.kc), r.cell);
+  load_cell(P, r.ic, r.jc, r.kc, r.cell);
   double u2 = vdotk(r.cell, r.kx, r.ky, r.kz);
   r.xfreq = DSUB(DMUL(DADD(r.xfreq, r.u1), Dold) / r.cell.Dfreq, u2);
   r.u1 = u2;
@@ -376,7 +408,7 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
 // ---------------------------------------------------------------------------
 // photon_type — define.f90:80-111 (I == 1 always; E1,E2,E3 are line constants)
 // ---------------------------------------------------------------------------
-enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8, PH_TAUPEND = 16 };
+enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8, PH_TAUPEND = 16, PH_INFLIGHT = 64 };
 struct Photon {
   long long id;
   double x, y, z, kx, ky, kz, mx, my, mz, nx, ny, nz;
@@ -721,6 +753,19 @@ LART_DEV void ray_load(PeelRay &dst, const PeelRay *src) {
   uint4 *d = reinterpret_cast<uint4 *>(&dst);
 #pragma unroll
   for (int i = 0; i < 9; ++i) d[i] = s[i];
+}
+// A peel ray suspended after its per-wave step budget: descriptor + the exact DDA state, so that the walk
+// resumes with bit-identical arithmetic in a later wave.
+struct __align__(16) PeelCont {  // 240 B = fifteen 16-byte chunks
+  PeelRay pr;
+  double tx, ty, tz, delx, dely, delz, d, tau, xfreq, u1;
+  int ic, jc, kc, pad_;
+};
+static_assert(sizeof(PeelCont) == 240, "PeelCont must be fifteen 16-byte chunks");
+LART_DEV void ray_save_state(const Ray &r, double *st10, int *c3) {
+  st10[0] = r.tx; st10[1] = r.ty; st10[2] = r.tz; st10[3] = r.delx; st10[4] = r.dely; st10[5] = r.delz;
+  st10[6] = r.d; st10[7] = r.tau; st10[8] = r.xfreq; st10[9] = r.u1;
+  c3[0] = r.ic; c3[1] = r.jc; c3[2] = r.kc;
 }
 LART_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -1195,7 +1240,7 @@ LART_DEV void generate_photon(const DevParams &P, Photon &ph, Rng &r, Counters &
   // a source placed on the upper boundary with k>0 keeps index n+1 in the reference and
   // reads out of bounds there; clamp the READ only (the photon leaves at its first trace)
   int ci = min(max(ph.ic, 1), P.nx), cj = min(max(ph.jc, 1), P.ny), ck = min(max(ph.kc, 1), P.nz);
-  load_cell(P, cell_index(P, ci, cj, ck), cs);
+  load_cell(P, ci, cj, ck, cs);
   switch (P.spectral_type) {  // :243-300
     case 3: ph.xfreq = r.uniform() * (P.xfreq_max - P.xfreq_min) + P.xfreq_min; ph.xfreq = ph.xfreq / (cs.Dfreq / P.Dfreq_ref); break;
     case 2: ph.xfreq = ph.xfreq + rand_voigt(r, P.voigt_a0, cnt.reject) * P.Dfreq0 / cs.Dfreq; break;

@@ -60,7 +60,7 @@ int fail(const std::string &msg) {
 
 constexpr int kVoigtTabN = 202 * 4;
 constexpr int kBlock = 256;
-constexpr int64_t kTailPhotons = 16384;  // lart_gpu_run: below this many photons left, finish with k_mono
+constexpr int64_t kTailPhotons = 65536;  // lart_gpu_run: below this many photons left, finish with k_mono
 constexpr int kTailQuantum = 256;
 
 // ------------------------------- photon pool -------------------------------
@@ -73,6 +73,8 @@ struct Pool {
   long long *id;               // [S]
   unsigned long long *ndraw;   // [S]
   int *ic, *jc, *kc, *flags;   // [S]
+  double *rs;                  // [10][S] DDA state of a flight suspended at its per-wave step budget
+  int *rc;                     // [3][S]  ... and its current cell
   int S;                       // slots (= SoA stride)
   int s0, n;                   // the partition [s0, s0+n) this kernel launch works on
 };
@@ -84,6 +86,10 @@ struct Queues {  // one per pool partition (pipeline)
   PeelRay *rays;      // [ray_cap]: S*nobs slot rays, then per partition the direct rays of this wave's emits
   unsigned int *n_direct, *head_trace, *head_peel;
   unsigned int direct_base, direct_cap;  // direct-ray region of this partition
+  PeelCont *cont[2];  // peel rays suspended at their step budget: read from [wave&1], appended to [(wave&1)^1]
+  unsigned int *n_cont;   // [2]
+  unsigned int *wave;     // wave counter of this partition (its parity selects the buffers)
+  unsigned int cont_cap;
 };
 
 __device__ __forceinline__ void load_trace_part(const Pool &pl, int s, Photon &ph) {
@@ -144,15 +150,26 @@ __device__ __forceinline__ void load_vtab(const DevParams &P, double *vtab) {
 }
 
 // warp-reduce the work counters and add them to the tally buffer (as doubles)
+// Work counters: warp shuffle sum, then a block sum through shared memory, then ONE atomic per counter
+// and block.  (Per-warp atomics on six hot addresses cost ~28 us per kernel: 14 k same-address FP64 REDs
+// serialise in one L2 slice — the floor of every wave when few photons are in flight.)
 __device__ void flush_counters(const DevParams &P, Counters &c, ctr_t nrng) {
+  __shared__ unsigned long long part[6][kBlock / 32];
   c.rng += nrng;
-  unsigned long long v[6] = {c.photons, c.scatter, c.cellsteps, c.peel, c.rng, c.reject};  // widened for the warp sum
+  unsigned long long v[6] = {c.photons, c.scatter, c.cellsteps, c.peel, c.rng, c.reject};  // widened for the sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
     unsigned long long x = v[q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if ((threadIdx.x & 31) == 0 && x) atomicAdd(P.tally + P.lay.counters + q, (double)x);
+    if (lane == 0) part[q][warp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    unsigned long long x = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += part[threadIdx.x][w];
+    if (x) atomicAdd(P.tally + P.lay.counters + threadIdx.x, (double)x);
   }
 }
 
@@ -236,7 +253,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   Counters cnt;
   ctr_t nrng = 0;
-  if (s < pl.S) {  // the monolithic driver always works on the whole pool
+  if (s < pl.n) {  // the monolithic driver works on the (possibly compacted) range [0, n)
     Photon ph;
     Rng rng;
     ph.flags = pl.flags[s];
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
         if (ph.flags & PH_FIRST) {
           int ci, cj, ck, ns;
           clamp_cell_for_read(P, ph, ci, cj, ck);
-          load_cell(P, cell_index(P, ci, cj, ck), cs);
+          load_cell(P, ci, cj, ck, cs);
           double tau0 = walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, ns);
           cnt.cellsteps += ns;
           tau = forced_first(P, ph, rng, cs, tau0);
@@ -296,7 +313,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
           continue;
         }
       } else {  // the wavefront scatter stage already flew this photon to its next scattering point
-        load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
+        load_cell(P, ph.ic, ph.jc, ph.kc, cs);
         at_scatter = false;
         touched = true;
       }
@@ -400,10 +417,11 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
 }
 
 // stage 2: raytrace_to_tau for every live photon, per-lane refill
-__global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+__global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q, int budget) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
+  const size_t S = pl.S;
   Counters cnt;
   ctr_t nrng = 0;
   Ray r;
@@ -425,37 +443,49 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
           slot = pl.s0 + (int)idx;
           load_trace_part(pl, slot, ph);
           load_rng(P, pl, slot, ph.id, ph.flags, rng);
-          bool leaving;
           if (ph.flags & PH_FIRST) {
             int ci, cj, ck;
             clamp_cell_for_read(P, ph, ci, cj, ck);
-            load_cell(P, cell_index(P, ci, cj, ck), cs0);
-            mode = 0;
-            leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, false);
-            if (leaving) {  // tau0 = 0 (raytrace_to_edge returns at once)
-              tau_in = forced_first(P, ph, rng, cs0, 0.0);
-              mode = 1;
-            }
-          } else {
-            if (ph.flags & PH_TAUPEND) {  // tau was drawn by the scatter stage, whose local step left the cell
-              tau_in = pl.f[(size_t)F_TAU * pl.S + slot];
-              ph.flags &= ~PH_TAUPEND;
-            } else {
-              tau_in = -log(rng.uniform());
-            }
-            mode = 1;
-            leaving = true;
+            load_cell(P, ci, cj, ck, cs0);
           }
-          if (mode == 1 && leaving)
-            leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true);
-          if (leaving) {  // dead without tally (raytrace_car.f90:1469-1472)
-            ph.flags &= ~PH_ALIVE;
-            load_rest(pl, slot, ph);
-            retire_photon(P, ph, false, job, cnt);
-            pl.flags[slot] = ph.flags;
-            nrng += rng.nrng;
-          } else {
+          if (ph.flags & PH_INFLIGHT) {  // a walk suspended at its step budget in an earlier wave: resume it exactly
+            const double *st = pl.rs + slot;
+            ph.flags &= ~PH_INFLIGHT;
+            mode = (ph.flags & PH_FIRST) ? 0 : 1;
+            tau_in = pl.f[(size_t)F_TAU * S + slot];
+            ray_resume(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, st[0 * S], st[1 * S], st[2 * S], st[3 * S], st[4 * S],
+                       st[5 * S], st[6 * S], st[7 * S], st[8 * S], st[9 * S], pl.rc[slot], pl.rc[S + slot], pl.rc[2 * S + slot]);
             have = true;
+          } else {
+            bool leaving;
+            if (ph.flags & PH_FIRST) {
+              mode = 0;
+              leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, false);
+              if (leaving) {  // tau0 = 0 (raytrace_to_edge returns at once)
+                tau_in = forced_first(P, ph, rng, cs0, 0.0);
+                mode = 1;
+              }
+            } else {
+              if (ph.flags & PH_TAUPEND) {  // tau was drawn by the scatter stage, whose local step left the cell
+                tau_in = pl.f[(size_t)F_TAU * S + slot];
+                ph.flags &= ~PH_TAUPEND;
+              } else {
+                tau_in = -log(rng.uniform());
+              }
+              mode = 1;
+              leaving = true;
+            }
+            if (mode == 1 && leaving)
+              leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true);
+            if (leaving) {  // dead without tally (raytrace_car.f90:1469-1472)
+              ph.flags &= ~PH_ALIVE;
+              load_rest(pl, slot, ph);
+              retire_photon(P, ph, false, job, cnt);
+              pl.flags[slot] = ph.flags;
+              nrng += rng.nrng;
+            } else {
+              have = true;
+            }
           }
         }
       }
@@ -501,6 +531,23 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
           nrng += rng.nrng;
           have = false;
         }
+      }
+      // ---- step budget: a long walk is parked in the pool and resumed next wave, so that no wave waits for it
+      if (have && r.nsteps >= budget) {
+        double st10[10];
+        int c3[3];
+        ray_save_state(r, st10, c3);
+        double *st = pl.rs + slot;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) st[(size_t)k * S] = st10[k];
+        pl.rc[slot] = c3[0]; pl.rc[S + slot] = c3[1]; pl.rc[2 * S + slot] = c3[2];
+        pl.f[(size_t)F_TAU * S + slot] = tau_in;
+        ph.flags |= PH_INFLIGHT;
+        store_trace_part(pl, slot, ph);  // weight and flags may have changed (forced first scattering)
+        pl.ndraw[slot] = rng.nblk;
+        cnt.cellsteps += r.nsteps;
+        nrng += rng.nrng;
+        have = false;
       }
     }
   }
@@ -550,7 +597,7 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
       }
       ph.flags &= ~PH_SCATTER;
       load_rng(P, pl, s, ph.id, ph.flags, rng);
-      load_cell(P, cell_index(P, ph.ic, ph.jc, ph.kc), cs);
+      load_cell(P, ph.ic, ph.jc, ph.kc, cs);
       cnt.scatter += 1;
       if (P.dust) {
         double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
@@ -644,16 +691,20 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
 }
 
 // stage 4: raytrace_to_edge for every queued peel ray, per-lane refill, deposit
-__global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ DevParams P, Pool pl, Queues q) {
+__global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ DevParams P, Pool pl, Queues q, int budget, int cont_only) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
   Counters cnt;
-  // work items of this partition: its slot rays, then its direct rays
-  const unsigned nslot = (unsigned)pl.n * (unsigned)P.nobs, slot_lo = (unsigned)pl.s0 * (unsigned)P.nobs;
-  const unsigned n = nslot + min(*q.n_direct, q.direct_cap);
+  // work items of this partition: rays suspended in the previous wave, then its slot rays, then its direct rays
+  const unsigned par = *q.wave & 1u;
+  const PeelCont *cin = q.cont[par];
+  PeelCont *cout = q.cont[par ^ 1u];
+  const unsigned ncont = min(q.n_cont[par], q.cont_cap);
+  const unsigned nslot = cont_only ? 0u : (unsigned)pl.n * (unsigned)P.nobs, slot_lo = (unsigned)pl.s0 * (unsigned)P.nobs;
+  const unsigned n = ncont + nslot + (cont_only ? 0u : min(*q.n_direct, q.direct_cap));
   Ray r;
-  unsigned mine = 0;
+  PeelRay pr;
   bool have = false, exhausted = false;
   for (;;) {
     bool zero_tau = false;
@@ -663,14 +714,20 @@ __global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ D
       unsigned idx = reserve(q.head_peel, need);
       if (need) {
         if (idx >= n) exhausted = true;
-        else {
-          idx = idx < nslot ? slot_lo + idx : q.direct_base + (idx - nslot);
-          if (q.rays[idx].kind >= 0) {
-          mine = idx;
-          const PeelRay &pr = q.rays[idx];
-          cnt.peel += 1;
-          if (ray_setup(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
-          else have = true;
+        else if (idx < ncont) {  // resume a suspended ray
+          const PeelCont &c = cin[idx];
+          ray_load(pr, &c.pr);
+          ray_resume(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, c.tx, c.ty, c.tz, c.delx, c.dely, c.delz, c.d, c.tau,
+                     c.xfreq, c.u1, c.ic, c.jc, c.kc);
+          have = true;
+        } else {
+          idx -= ncont;
+          const PeelRay *src = q.rays + (idx < nslot ? slot_lo + idx : q.direct_base + (idx - nslot));
+          if (src->kind >= 0) {
+            ray_load(pr, src);
+            cnt.peel += 1;
+            if (ray_setup(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
+            else have = true;
           }
         }
       }
@@ -678,14 +735,56 @@ __global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ D
     bool fin = zero_tau;
     if (have && edge_step(P, vtab, r)) { fin = true; have = false; cnt.cellsteps += r.nsteps; }
     unsigned fm = __ballot_sync(FULL, fin);
-    if (fin) peel_deposit(P, q.rays[mine], zero_tau ? 0.0 : r.tau, fm);
+    if (fin) peel_deposit(P, pr, zero_tau ? 0.0 : r.tau, fm);
+    if (have && r.nsteps >= budget) {  // park the ray: the next wave continues it
+      unsigned at = atomicAdd(&q.n_cont[par ^ 1u], 1u);
+      if (at < q.cont_cap) {
+        PeelCont &c = cout[at];
+        ray_store(&c.pr, pr);
+        c.tx = r.tx; c.ty = r.ty; c.tz = r.tz; c.delx = r.delx; c.dely = r.dely; c.delz = r.delz;
+        c.d = r.d; c.tau = r.tau; c.xfreq = r.xfreq; c.u1 = r.u1; c.ic = r.ic; c.jc = r.jc; c.kc = r.kc;
+        cnt.cellsteps += r.nsteps;
+        have = false;
+      } else {
+        atomicSub(&q.n_cont[par ^ 1u], 1u);  // queue full (cannot happen by sizing): keep walking
+      }
+    }
     if (!__any_sync(FULL, have || !exhausted)) break;
   }
   flush_counters(P, cnt, 0);
 }
 
-__global__ void k_wf_reset(Queues q) {
+__global__ void k_wf_reset(Queues q) {  // start of a wave: new parity, empty output queues
   *q.n_direct = 0; *q.head_trace = 0; *q.head_peel = 0;
+  const unsigned w = *q.wave + 1u;
+  *q.wave = w;
+  q.n_cont[(w & 1u) ^ 1u] = 0;
+}
+
+// ------------------------------ pool compaction ------------------------------
+// Once the job queue is empty the pool thins out.  Compaction moves the live photons of the tail into the
+// dead slots of the head [0, n_keep), so that every kernel works on a dense range again (full warps in the
+// scatter stage, short scans, and a dense monolithic tail).
+__global__ void k_compact_list(Pool pl, int n_keep, int *src, int *dst, unsigned int *n_src, unsigned int *n_dst) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < pl.n; s += gridDim.x * blockDim.x) {
+    const bool alive = (pl.flags[s] & PH_ALIVE) != 0;
+    if (s >= n_keep && alive) src[atomicAdd(n_src, 1u)] = s;
+    if (s < n_keep && !alive) dst[atomicAdd(n_dst, 1u)] = s;
+  }
+}
+__global__ void k_compact_move(Pool pl, const int *src, const int *dst, const unsigned int *n_src) {
+  const unsigned m = *n_src;
+  const size_t S = pl.S;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const int a = src[i], b = dst[i];
+    for (int c = 0; c < F_COUNT; ++c) pl.f[(size_t)c * S + b] = pl.f[(size_t)c * S + a];
+    for (int c = 0; c < 10; ++c) pl.rs[(size_t)c * S + b] = pl.rs[(size_t)c * S + a];
+    for (int c = 0; c < 3; ++c) pl.rc[(size_t)c * S + b] = pl.rc[(size_t)c * S + a];
+    pl.id[b] = pl.id[a]; pl.ndraw[b] = pl.ndraw[a];
+    pl.ic[b] = pl.ic[a]; pl.jc[b] = pl.jc[a]; pl.kc[b] = pl.kc[a];
+    pl.flags[b] = pl.flags[a];
+    pl.flags[a] = 0;
+  }
 }
 
 // ------------------------------ set-up kernels ------------------------------
@@ -695,7 +794,8 @@ __global__ void k_pack_cells(DevParams P, Cell *cells, size_t n) {
     o.rhokap = P.rhokap[c]; o.voigt_a = P.voigt_a[c]; o.Dfreq = P.Dfreq[c];
     o.vfx = P.vfx[c]; o.vfy = P.vfy[c]; o.vfz = P.vfz[c];
     o.rhokapD = P.dust ? P.rhokapD[c] : 0.0; o.pad = 0.0;
-    cells[c] = o;
+    const int i = (int)(c % P.nx), j = (int)((c / P.nx) % P.ny), k = (int)(c / ((size_t)P.nx * P.ny));
+    cells[cell_slot(P, i + 1, j + 1, k + 1)] = o;
   }
 }
 __global__ void k_build_vtab(double *tab) {
@@ -751,7 +851,7 @@ __global__ void k_xcrit_batch(const __grid_constant__ DevParams P, long long n, 
     if (P.core_skip_global) { xc = P.xcrit; }
     else if (ic[i] >= 1 && jc[i] >= 1 && kc[i] >= 1) {
       CellData cs;
-      load_cell(P, cell_index(P, ic[i], jc[i], kc[i]), cs);
+      load_cell(P, ic[i], jc[i], kc[i], cs);
       car_xcrit_local(P, ic[i], jc[i], kc[i], x[i], y[i], z[i], cs.voigt_a, cs.rhokap, xc, xc2);
     }
     out[i] = xc;
@@ -853,6 +953,13 @@ struct lart_gpu_ctx {
   long long allph_n = 0;
   int allph_slot[10];
   int quantum = 0, flags = 0, nsm = 148, nobs = 0, nxim = 0, nyim = 0;
+  int budget = 32;          // cell steps a trace/peel ray may take per wave before it is parked
+  bool pending_rays = false;  // suspended walks may exist (drain before switching drivers / fetching)
+  unsigned int *ctr = nullptr;  // per-partition queue counters
+  size_t ctr_n = 0;
+  int *cmp_src = nullptr, *cmp_dst = nullptr;  // compaction work lists
+  unsigned int *cmp_n = nullptr;
+  unsigned long long job_next = 0;  // job queue head after the last step
   long long count = 0;
   double kernel_ms = 0.0;
   long long launches = 0;
@@ -862,6 +969,10 @@ struct lart_gpu_ctx {
   double stage_ms[LART_STAGE_COUNT] = {0, 0, 0, 0};
   long long stage_n[LART_STAGE_COUNT] = {0, 0, 0, 0};
 };
+
+namespace {
+void partition_pool(lart_gpu_handle h, int n);
+}  // namespace
 
 namespace {
 template <class T>
@@ -952,9 +1063,10 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   P.warp_agg = (cfg->flags & LART_FLAG_NO_WARP_AGG) ? 0 : 1;
   P.flags_serial_vz = (cfg->flags & LART_FLAG_SERIAL_REJECTION) ? 1 : 0;
   P.local_steps = (cfg->flags & LART_FLAG_LOCAL_STEPS) ? 1 : 0;
+  P.nsbx = (g.nx + 31) / 32; P.nsby = (g.ny + 31) / 32; P.nsbz = (g.nz + 31) / 32;
   if (!P.soa) {
     Cell *cells = nullptr;
-    if ((rc = dalloc(h, &cells, nc, false))) return bail(rc);
+    if ((rc = dalloc(h, &cells, (size_t)P.nsbx * P.nsby * P.nsbz * 32768, false))) return bail(rc);
     k_pack_cells<<<h->nsm * 8, 256, 0, h->stream>>>(P, cells, nc);
     P.cells = cells;
   }
@@ -1040,8 +1152,8 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   if (S <= 0) S = mono ? h->nsm * 2048 : h->nsm * 16384;
   {
     // keep the ray queue below ~3 GB when many observers are configured
-    long long per_slot = (long long)sizeof(PeelRay) * std::max(1, P.nobs);
-    long long cap = (3LL << 30) / per_slot;
+    long long per_slot = (long long)(2 * sizeof(PeelRay) + 4 * sizeof(PeelCont)) * std::max(1, P.nobs);
+    long long cap = (8LL << 30) / per_slot;
     if (S > cap) S = (int)std::max<long long>(cap, 1024);
   }
   S = std::max(32, (S + 31) / 32 * 32);
@@ -1053,7 +1165,12 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   rc = rc ? rc : dalloc(h, &h->pool.jc, S);
   rc = rc ? rc : dalloc(h, &h->pool.kc, S);
   rc = rc ? rc : dalloc(h, &h->pool.flags, S);
+  rc = rc ? rc : dalloc(h, &h->pool.rs, (size_t)10 * S);
+  rc = rc ? rc : dalloc(h, &h->pool.rc, (size_t)3 * S);
   rc = rc ? rc : dalloc(h, &h->job, 1);
+  rc = rc ? rc : dalloc(h, &h->cmp_src, S);
+  rc = rc ? rc : dalloc(h, &h->cmp_dst, S);
+  rc = rc ? rc : dalloc(h, &h->cmp_n, 2);
   h->pool.s0 = 0; h->pool.n = S;
   if (!mono && !rc) {
     int G = cfg->streams > 0 ? cfg->streams : 6;
@@ -1062,7 +1179,12 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
     const long long ray_cap = std::min<long long>((long long)S * std::max<long long>(nobs, 1) * 2, 0x7fffffffLL);
     rc = rc ? rc : dalloc(h, &h->rays, (size_t)ray_cap, true);
     unsigned int *ctr = nullptr;
-    rc = rc ? rc : dalloc(h, &ctr, 4 * (size_t)G);
+    rc = rc ? rc : dalloc(h, &ctr, 8 * (size_t)G);
+    h->ctr = ctr; h->ctr_n = 8 * (size_t)G;
+    // suspended peel rays: two buffers per partition, each large enough for every ray of a wave plus the carry-over
+    const long long cont_total = 2LL * ((long long)S * std::max<long long>(nobs, 1) * 2 + 64LL * G);
+    PeelCont *cont = nullptr;
+    rc = rc ? rc : dalloc(h, &cont, (size_t)cont_total, false);
     h->groups.resize(G);
     int per = ((S / G) + 31) / 32 * 32;
     for (int g = 0; g < G && !rc; ++g) {
@@ -1071,15 +1193,20 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
       gr.pool.s0 = std::min(g * per, S);
       gr.pool.n = (g == G - 1) ? S - gr.pool.s0 : std::min(per, S - gr.pool.s0);
       gr.q.rays = h->rays;
-      gr.q.n_direct = ctr + 4 * g; gr.q.head_trace = ctr + 4 * g + 1; gr.q.head_peel = ctr + 4 * g + 2;
+      gr.q.n_direct = ctr + 8 * g; gr.q.head_trace = ctr + 8 * g + 1; gr.q.head_peel = ctr + 8 * g + 2;
+      gr.q.n_cont = ctr + 8 * g + 3; gr.q.wave = ctr + 8 * g + 5;
       gr.q.direct_base = (unsigned)((long long)S * nobs + (long long)gr.pool.s0 * nobs);
       gr.q.direct_cap = (unsigned)std::min<long long>((long long)gr.pool.n * nobs, ray_cap - gr.q.direct_base);
+      gr.q.cont_cap = (unsigned)((long long)gr.pool.n * std::max<long long>(nobs, 1) * 2 + 32);
+      gr.q.cont[0] = cont + 2LL * ((long long)gr.pool.s0 * std::max<long long>(nobs, 1) * 2 + 64LL * g);
+      gr.q.cont[1] = gr.q.cont[0] + gr.q.cont_cap;
       CUDA_OK(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
       CUDA_OK(cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming));
     }
   }
   if (rc) return bail(rc);
   h->quantum = cfg->quantum > 0 ? cfg->quantum : (mono ? 32 : 8);
+  h->budget = cfg->ray_budget > 0 ? cfg->ray_budget : 32;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
   *out = h;
@@ -1114,6 +1241,10 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
   Job j{0ULL, (unsigned long long)count, 0ULL, (long long)first_id, (long long)stride};
   CUDA_OK(cudaMemcpyAsync(h->job, &j, sizeof(Job), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemsetAsync(h->pool.flags, 0, sizeof(int) * h->pool.S, h->stream));  // abandon unfinished photons
+  if (h->ctr) CUDA_OK(cudaMemsetAsync(h->ctr, 0, sizeof(unsigned int) * h->ctr_n, h->stream));  // ... and parked rays
+  h->pending_rays = false;
+  if (!h->groups.empty() && h->pool.n != h->pool.S) partition_pool(h, h->pool.S);
+  h->job_next = 0;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->count = count;
   h->begun = true;
@@ -1123,6 +1254,7 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
 }  // extern "C"
 
 namespace {
+int drain_peel_only(lart_gpu_handle h);
 // One step with an explicit driver choice (both drivers share the pool layout, and no
 // slot is left mid-wave between steps, so they can alternate freely).
 int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
@@ -1141,7 +1273,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
   if (mono) {
     size_t ne = 0;
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
-    k_mono<<<(h->pool.S + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
+    k_mono<<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
     h->launches += 1;
   } else {
@@ -1160,12 +1292,12 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           k_wf_emit<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.local_steps) k_wf_scatter<true><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           else k_wf_scatter<false><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          k_wf_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
+          k_wf_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
         }
       }
@@ -1201,6 +1333,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
       CUDA_OK(cudaGraphLaunch(it->second, h->stream));
     }
     h->launches += 5LL * G * qn;
+    h->pending_rays = true;
   }
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));
   Job j;
@@ -1227,7 +1360,40 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           }
     }
   }
+  h->job_next = j.next;
   if (in_flight) *in_flight = (int64_t)h->count - (int64_t)j.done;
+  return 0;
+}
+
+// Split the live range [0, n) of the pool among the wave pipelines (32-slot granularity).
+void partition_pool(lart_gpu_handle h, int n) {
+  const int G = (int)h->groups.size();
+  h->pool.s0 = 0;
+  h->pool.n = n;
+  const int per = ((n + G - 1) / G + 31) / 32 * 32;
+  for (int g = 0; g < G; ++g) {
+    Pool &p = h->groups[g].pool;
+    p.s0 = std::min(g * per, n);
+    p.n = std::min(per, n - p.s0);
+  }
+  for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);  // kernel arguments changed: re-capture
+  h->graphs.clear();
+}
+
+// Compact the live photons into [0, alive) when the queue is empty and the pool is less than half full.
+int maybe_compact(lart_gpu_handle h, int64_t alive) {
+  if (h->groups.empty() || h->job_next < (unsigned long long)h->count) return 0;
+  if (alive * 2 > h->pool.n || h->pool.n <= 4096) return 0;
+  if (int rc = drain_peel_only(h)) return rc;
+  const int n_keep = (int)std::max<int64_t>(1024, (alive + 31) / 32 * 32);
+  CUDA_OK(cudaMemsetAsync(h->cmp_n, 0, 2 * sizeof(unsigned int), h->stream));
+  const int grid = std::max(1, std::min((h->pool.n + kBlock - 1) / kBlock, h->nsm * 8));
+  k_compact_list<<<grid, kBlock, 0, h->stream>>>(h->pool, n_keep, h->cmp_src, h->cmp_dst, h->cmp_n, h->cmp_n + 1);
+  k_compact_move<<<grid, kBlock, 0, h->stream>>>(h->pool, h->cmp_src, h->cmp_dst, h->cmp_n);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->launches += 2;
+  partition_pool(h, n_keep);
   return 0;
 }
 }  // namespace
@@ -1242,9 +1408,36 @@ int lart_gpu_step(lart_gpu_handle h, int32_t quantum, int64_t *in_flight) {
   return step_impl(h, quantum > 0 ? quantum : h->quantum, mono, in_flight);
 }
 
+}  // extern "C"
+
+namespace {
+int drain(lart_gpu_handle h, bool flights);
+int drain_peel_only(lart_gpu_handle h) { return drain(h, false); }
+// Finish every walk that was parked at its per-wave step budget: peel rays always; photon flights too when
+// `flights` (before the monolithic kernel takes over).  One pass with an unlimited budget does it.
+int drain(lart_gpu_handle h, bool flights) {
+  if (!h->pending_rays || h->groups.empty()) return 0;
+  const int big = 0x7fffffff;
+  for (auto &g : h->groups) {
+    const int nb = (g.pool.n + kBlock - 1) / kBlock;
+    const int grid = std::max(1, std::min(nb, h->nsm * 2));
+    k_wf_reset<<<1, 1, 0, h->stream>>>(g.q);
+    if (flights) k_wf_trace<<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, h->job, g.q, big);
+    k_wf_peel<<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, g.q, big, 1);
+    h->launches += flights ? 3 : 2;
+  }
+  CUDA_OK(cudaGetLastError());
+  if (flights) h->pending_rays = false;  // (peel-only drains leave parked flights: keep the flag)
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int lart_gpu_sync(lart_gpu_handle h) {
   if (!h) return fail("lart_gpu_sync: NULL handle");
   CUDA_OK(cudaSetDevice(h->device));
+  if (int rc = drain(h, false)) return rc;  // every peel ray emitted so far is deposited
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -1255,12 +1448,15 @@ int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t str
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int64_t left = count;
   while (left > 0) {
-    // Tail of a heavy-tailed run: with few photons left a wave is launch-latency bound (one scattering per
-    // ~5 launches), while one thread per photon runs `quantum` scatterings per launch.
-    const bool tail = !mono && left < kTailPhotons;
+    // Heavy tail: once the queue is empty the pool thins out; keep it dense (compaction), and below
+    // kTailPhotons let one thread per photon run `quantum` scatterings per launch — a wave is then bound by
+    // launch latency (one scattering per ~5 launches), not by throughput.
+    if (!mono) if (int rc = maybe_compact(h, left)) return rc;
+    const bool tail = !mono && left < kTailPhotons && h->job_next >= (unsigned long long)count;
+    if (tail) if (int rc = drain(h, true)) return rc;  // the monolithic kernel cannot resume parked walks
     if (int rc = step_impl(h, tail ? kTailQuantum : h->quantum, mono || tail, &left)) return rc;
   }
-  return 0;
+  return lart_gpu_sync(h);
 }
 
 int lart_gpu_reset_tallies(lart_gpu_handle h) {
@@ -1347,6 +1543,7 @@ int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out) {
   const DevParams &P = h->P;
   const TallyLayout &L = P.lay;
   if (P.nobs > 0 && !out->obs) return fail("lart_gpu_fetch: out->obs is NULL but observers are configured");
+  if (int rc = drain(h, false)) return rc;
   h->stage.resize((size_t)L.total);
   CUDA_OK(cudaMemcpyAsync(h->stage.data(), P.tally, sizeof(double) * L.total, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -172,7 +172,7 @@ class Simulation:
     after ONE sum-reduce over NCCL when a torch.distributed group is active.
     """
 
-    def __init__(self, model, device=0, pool_slots=0, quantum=0, flags=0, seed=None, streams=0):
+    def __init__(self, model, device=0, pool_slots=0, quantum=0, flags=0, seed=None, streams=0, ray_budget=0):
         self._lib = capi.load_gpu()  # raises if the CUDA engine is missing: no fallback
         self.model = model
         cfg = model.config.contents
@@ -181,6 +181,7 @@ class Simulation:
         cfg.quantum = quantum
         cfg.flags = flags
         cfg.streams = streams
+        cfg.ray_budget = ray_budget
         if seed is not None:
             cfg.par.seed = seed
         self._h = C.c_void_p()

@@ -66,7 +66,7 @@ module lart_gpu_shim
      type(c_lart_line)      :: line
      type(c_lart_scatt_mat) :: scatt_mat
      type(c_ptr)            :: observers
-     integer(c_int32_t)     :: device, pool_slots, quantum, flags, streams, pad_
+     integer(c_int32_t)     :: device, pool_slots, quantum, flags, streams, ray_budget
   end type
   type, bind(C) :: c_lart_observer_out
      type(c_ptr) :: scatt, direc, direc0, I, Q, U, V
@@ -236,7 +236,7 @@ contains
     !--- one rank per GPU
     ngpu_per_node  = 8
     cfg%device     = mod(mpar%h_rank, ngpu_per_node)
-    cfg%pool_slots = 0; cfg%quantum = 0; cfg%flags = 0; cfg%streams = 0; cfg%pad_ = 0
+    cfg%pool_slots = 0; cfg%quantum = 0; cfg%flags = 0; cfg%streams = 0; cfg%ray_budget = 0
 
     call check(lart_gpu_create(cfg, handle))
 

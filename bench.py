@@ -286,13 +286,18 @@ def run_gpu(args):
     if not args.skip_e2e:
         sim = Simulation(model, device=local, pool_slots=args.pool_slots, quantum=args.quantum, flags=args.flags,
                          streams=args.streams)
+        ta = time.perf_counter()
         sim.begin(first, count, stride)
         for _ in range(total_steps):
             sim.step(args.quantum)
+        tb = time.perf_counter()
         sim.output_reduce(dst=0)
         barrier()
+        tc = time.perf_counter()
         buf_n = sim.tally_buffer()[1]
         sim.close()
+        print("e2e phases: create %.3f s, steps %.3f s, reduce+fetch %.3f s, destroy %.3f s" %
+              (ta - t0, tb - ta, tc - tb, time.perf_counter() - tc), file=sys.stderr)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     ns = torch.tensor([model.counters["n_scatter"] if rank == 0 else 0.0], dtype=torch.float64, device="cuda")

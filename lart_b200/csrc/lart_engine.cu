@@ -31,6 +31,7 @@
 #include <cmath>
 #include <map>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1447,6 +1448,8 @@ int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t str
   if (int rc = lart_gpu_begin(h, first_id, count, stride)) return rc;
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int64_t left = count;
+  const bool progress = getenv("LART_GPU_PROGRESS") != nullptr;
+  long long nstep = 0;
   while (left > 0) {
     // Heavy tail: once the queue is empty the pool thins out; keep it dense (compaction), and below
     // kTailPhotons let one thread per photon run `quantum` scatterings per launch — a wave is then bound by
@@ -1455,6 +1458,9 @@ int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t str
     const bool tail = !mono && left < kTailPhotons && h->job_next >= (unsigned long long)count;
     if (tail) if (int rc = drain(h, true)) return rc;  // the monolithic kernel cannot resume parked walks
     if (int rc = step_impl(h, tail ? kTailQuantum : h->quantum, mono || tail, &left)) return rc;
+    if (progress && (++nstep % 64 == 0 || left == 0))  // LART_GPU_PROGRESS=1: like the reference's nprint lines
+      fprintf(stderr, "lart_gpu_run: %lld of %lld photons left, pool range %d, driver %s, device time %.3f s\n", (long long)left,
+              (long long)count, h->pool.n, (mono || tail) ? "monolithic" : "wavefront", h->kernel_ms * 1e-3);
   }
   return lart_gpu_sync(h);
 }

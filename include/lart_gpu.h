@@ -294,6 +294,21 @@ int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n,
                          const int32_t *icell, const int32_t *jcell, const int32_t *kcell,
                          double *xcrit);
 
+/* ---- next row: sight-line maps, a pure reuse of the edge walk -------------
+ * make_sightline_tau_outside (src/sightline_tau_rect.f90:11-190): for every observer and detector pixel the
+ * sight line enters the grid at its far boundary and runs toward the observer;
+ *   tau_gas (nxfreq,nxim,nyim)  raytrace_to_edge_tau_gas  (src/raytrace_car.f90:1236-1328; gas only, no tau cap),
+ *                               one walk per frequency bin centre grid%xfreq(kk) (grid_mod_car.f90:1505)
+ *   N_gas   (nxim,nyim), tau_dust (nxim,nyim; DGR > 0)  raytrace_to_edge_column (:1330-1423)
+ * Arrays are Fortran order (frequency fastest) and are OVERWRITTEN, as the reference assigns them; pixels whose
+ * sight line misses the grid keep 0.  cross0 = line%cross0 (column density = rhokap*Dfreq/cross0 per length). */
+typedef struct lart_sightline_out {
+  double *tau_gas, *N_gas, *tau_dust; /* tau_dust may be NULL */
+} lart_sightline_out;
+int lart_gpu_sightline_tau(lart_gpu_handle h, double cross0, lart_sightline_out *out /* nobs entries */);
+/* cell steps walked and CUDA-event time (ms) of the last lart_gpu_sightline_tau call */
+int lart_gpu_sightline_stats(lart_gpu_handle h, double *cellsteps, double *ms);
+
 /* library/ABI version: major*10000 + minor*100 + patch */
 int lart_gpu_version(void);
 

@@ -108,6 +108,10 @@ class Tallies(C.Structure):
                 ("nscatt_gas", C.c_double), ("nscatt_dust", C.c_double), ("counters", Counters)]
 
 
+class SightlineOut(C.Structure):
+    _fields_ = [("tau_gas", c_double_p), ("N_gas", c_double_p), ("tau_dust", c_double_p)]
+
+
 class HostSummary(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ["voigt_a", "temperature", "N_gaspole", "N_gashomo", "taupole", "tauhomo", "taupole_dust",
@@ -124,6 +128,7 @@ GPU_SYMBOLS = [
     "lart_gpu_stream", "lart_gpu_kernel_ms", "lart_gpu_last_error", "lart_gpu_voigt_batch",
     "lart_gpu_raytrace_edge_batch", "lart_gpu_raytrace_tau_batch", "lart_gpu_sample_batch",
     "lart_gpu_xcrit_batch", "lart_gpu_version", "lart_gpu_stage_ms", "lart_gpu_pool_slots", "lart_gpu_measure_fp64",
+    "lart_gpu_sightline_tau", "lart_gpu_sightline_stats",
 ]
 HOST_SYMBOLS = [
     "lart_host_new", "lart_host_free", "lart_host_set", "lart_host_read_input", "lart_host_setup",
@@ -201,5 +206,7 @@ def load_gpu():
         lib.lart_gpu_stage_ms.argtypes = [H, c_double_p, c_int64_p]
         lib.lart_gpu_pool_slots.argtypes = [H, c_int64_p]
         lib.lart_gpu_measure_fp64.argtypes = [C.c_int32, c_double_p]
+        lib.lart_gpu_sightline_tau.argtypes = [H, C.c_double, C.POINTER(SightlineOut)]
+        lib.lart_gpu_sightline_stats.argtypes = [H, c_double_p, c_double_p]
         _gpu = lib
     return _gpu

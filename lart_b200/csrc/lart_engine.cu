@@ -889,6 +889,73 @@ __global__ void k_sample_batch(int kind, unsigned long long seed, long long n, c
   }
 }
 
+// ---- sight-line maps: raytrace_to_edge_tau_gas / _column for every pixel and frequency -------
+struct SightStart {  // entry point of one pixel's sight line (host-computed, sightline_tau_rect.f90:45-150)
+  double x, y, z, kx, ky, kz;
+  int ic, jc, kc, valid;
+};
+// work item = (pixel, kk): kk < nxfreq -> tau_gas at bin centre kk; kk == nxfreq -> column density + dust tau.
+// Consecutive items share the pixel, i.e. the cell sequence: warps stay converged.
+__global__ void __launch_bounds__(kBlock) k_sightline(const __grid_constant__ DevParams P, long long npix, const SightStart *st,
+                                                      double cross0, double *tau_gas, double *N_gas, double *tau_dust,
+                                                      unsigned long long *steps) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  const long long per = P.nxfreq + 1, total = npix * per;
+  unsigned long long ns = 0;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+    const long long pix = it / per;
+    const int kk = (int)(it - pix * per);
+    const SightStart s = st[pix];
+    if (!s.valid) continue;
+    Ray r;
+    if (kk < P.nxfreq) {
+      CellData c0;
+      load_cell(P, s.ic, s.jc, s.kc, c0);
+      const double u1 = vdotk(c0, s.kx, s.ky, s.kz);
+      const double xf = DADD(DMUL(DSUB((double)(kk + 1), 0.5), P.dxfreq), P.xfreq_min);  // grid%xfreq(kk)
+      const double x0 = DSUB(DMUL(xf, P.Dfreq_ref) / c0.Dfreq, u1);
+      double tau = 0.0;
+      if (!ray_setup(P, r, s.x, s.y, s.z, s.kx, s.ky, s.kz, s.ic, s.jc, s.kc, x0, false)) {
+        for (;;) {  // raytrace_to_edge_car_tau_gas: gas opacity only, no tau cap
+          const double kap = DMUL(r.cell.rhokap, voigt_seon2(vtab, r.xfreq, r.cell.voigt_a));
+          ++r.nsteps;
+          const int ax = ray_axis(P, r);
+          const double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
+          r.tau = DADD(r.tau, DMUL(DSUB(tn, r.d), kap));
+          r.d = tn;
+          if (!ray_advance(P, r, ax)) break;
+          ray_shift(P, r);
+        }
+        tau = r.tau;
+        ns += r.nsteps;
+      }
+      tau_gas[(size_t)kk + (size_t)P.nxfreq * pix] = tau;
+    } else {
+      double N = 0.0, td = 0.0;
+      if (!ray_setup(P, r, s.x, s.y, s.z, s.kx, s.ky, s.kz, s.ic, s.jc, s.kc, 0.0, false)) {
+        for (;;) {  // raytrace_to_edge_car_column
+          const double rho = DMUL(r.cell.rhokap, r.cell.Dfreq) / cross0;
+          const int ax = ray_axis(P, r);
+          const double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
+          const double del = DSUB(tn, r.d);
+          N = DADD(N, DMUL(del, rho));
+          if (P.dust) td = DADD(td, DMUL(del, r.cell.rhokapD));
+          r.d = tn;
+          ++r.nsteps;
+          if (!ray_advance(P, r, ax)) break;
+          load_cell(P, r.ic, r.jc, r.kc, r.cell);
+        }
+        ns += r.nsteps;
+      }
+      N_gas[pix] = N;
+      if (tau_dust) tau_dust[pix] = td;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+  if ((threadIdx.x & 31) == 0 && ns) atomicAdd(steps, ns);
+}
+
 // register-resident DFMA loop: 16 independent chains per thread
 __global__ void k_dfma_peak(double *out, int iters, double a, double b) {
   double v[16];
@@ -961,6 +1028,8 @@ struct lart_gpu_ctx {
   int *cmp_src = nullptr, *cmp_dst = nullptr;  // compaction work lists
   unsigned int *cmp_n = nullptr;
   unsigned long long job_next = 0;  // job queue head after the last step
+  std::vector<DevObserver> obs_host;  // host copy of the observers (sight-line maps)
+  double sight_steps = 0.0, sight_ms = 0.0;
   long long count = 0;
   double kernel_ms = 0.0;
   long long launches = 0;
@@ -1100,6 +1169,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
       ob[i].dxim = o.dxim; ob[i].dyim = o.dyim; ob[i].nxim = o.nxim; ob[i].nyim = o.nyim;
     }
     h->nxim = ob[0].nxim; h->nyim = ob[0].nyim;
+    h->obs_host = ob;
     if ((rc = dupload(h, &P.obs, ob.data(), ob.size()))) return bail(rc);
   }
   const lart_scatt_mat &sm = cfg->scatt_mat;
@@ -1746,4 +1816,124 @@ int lart_gpu_sample_batch(int32_t kind, uint64_t seed, int64_t n, const int64_t 
   return 0;
 }
 
+
+// ---------------------------- sight-line maps -----------------------------
+}  // extern "C"
+
+namespace {
+// Entry point and start cell of the sight line of pixel (ix,iy) — sightline_tau_rect.f90:45-150.
+bool sightline_start(const lart_gpu_ctx *h, const std::vector<double> &xf, const std::vector<double> &yf,
+                     const std::vector<double> &zf, const DevObserver &ob, int ix, int iy, SightStart &o) {
+  const DevParams &P = h->P;
+  const double rad2deg = 180.0 / 3.141592653589793238462643383279502884197, hugest = 1.7976931348623157e308;
+  double kx = std::tan((ix - (ob.nxim + 1.0) / 2.0) * ob.dxim / rad2deg);
+  double ky = std::tan((iy - (ob.nyim + 1.0) / 2.0) * ob.dyim / rad2deg);
+  double kz = -1.0;
+  const double kr = std::sqrt(kx * kx + ky * ky + kz * kz);
+  kx /= kr; ky /= kr; kz /= kr;
+  const double *R = ob.R;
+  double px = R[0] * kx + R[1] * ky + R[2] * kz, py = R[3] * kx + R[4] * ky + R[5] * kz, pz = R[6] * kx + R[7] * ky + R[8] * kz;
+  const double delt[6] = {px == 0.0 ? hugest : (P.xmax - ob.x) / px, px == 0.0 ? hugest : (P.xmin - ob.x) / px,
+                          py == 0.0 ? hugest : (P.ymax - ob.y) / py, py == 0.0 ? hugest : (P.ymin - ob.y) / py,
+                          pz == 0.0 ? hugest : (P.zmax - ob.z) / pz, pz == 0.0 ? hugest : (P.zmin - ob.z) / pz};
+  auto cellof = [&](double x, double y, double z, int &i, int &j, int &k) {
+    i = (int)std::floor((x - P.xmin) / P.dx) + 1;
+    j = (int)std::floor((y - P.ymin) / P.dy) + 1;
+    k = (int)std::floor((z - P.zmin) / P.dz) + 1;
+  };
+  double dist = -999.9;
+  int j0 = 0;
+  for (int jj = 1; jj <= 6; ++jj) {
+    const double dl = delt[jj - 1];
+    if (!(dl > 0.0 && dl < hugest)) continue;
+    int i, j, k;
+    cellof(ob.x + px * dl, ob.y + py * dl, ob.z + pz * dl, i, j, k);
+    if (jj == 1) i = P.nx + 1;
+    if (jj == 2) i = 1;
+    if (jj == 3) j = P.ny + 1;
+    if (jj == 4) j = 1;
+    if (jj == 5) k = P.nz + 1;
+    if (jj == 6) k = 1;
+    if (i >= 1 && i <= P.nx + 1 && j >= 1 && j <= P.ny + 1 && k >= 1 && k <= P.nz + 1 && dl > dist) { dist = dl; j0 = jj; }
+  }
+  o.valid = 0;
+  if (!(dist > 0.0 && dist < hugest)) return false;
+  o.x = ob.x + px * dist; o.y = ob.y + py * dist; o.z = ob.z + pz * dist;
+  cellof(o.x, o.y, o.z, o.ic, o.jc, o.kc);
+  o.kx = -px; o.ky = -py; o.kz = -pz;
+  if (j0 == 1) { o.ic = P.nx + 1; o.x = xf[P.nx]; }
+  else if (j0 == 2) { o.ic = 1; o.x = xf[0]; }
+  else if (j0 == 3) { o.jc = P.ny + 1; o.y = yf[P.ny]; }
+  else if (j0 == 4) { o.jc = 1; o.y = yf[0]; }
+  else if (j0 == 5) { o.kc = P.nz + 1; o.z = zf[P.nz]; }
+  else if (j0 == 6) { o.kc = 1; o.z = zf[0]; }
+  if (o.ic == P.nx + 1 && o.kx < 0.0) o.ic = P.nx;
+  if (o.jc == P.ny + 1 && o.ky < 0.0) o.jc = P.ny;
+  if (o.kc == P.nz + 1 && o.kz < 0.0) o.kc = P.nz;
+  o.valid = (o.ic >= 1 && o.ic <= P.nx && o.jc >= 1 && o.jc <= P.ny && o.kc >= 1 && o.kc <= P.nz) ? 1 : 0;
+  return o.valid != 0;
+}
+}  // namespace
+
+extern "C" {
+
+int lart_gpu_sightline_tau(lart_gpu_handle h, double cross0, lart_sightline_out *out) {
+  if (!h || !out) return fail("lart_gpu_sightline_tau: NULL argument");
+  if (h->obs_host.empty()) return fail("lart_gpu_sightline_tau: the handle has no observers (par%save_peeloff, par%nobs)");
+  if (h->P.zonly) return fail("lart_gpu_sightline_tau: not defined for the xy-periodic slab");
+  if (!(cross0 > 0.0)) return fail("lart_gpu_sightline_tau: cross0 must be > 0");
+  CUDA_OK(cudaSetDevice(h->device));
+  const DevParams &P = h->P;
+  std::vector<double> xf(P.nx + 1), yf(P.ny + 1), zf(P.nz + 1);
+  CUDA_OK(cudaMemcpy(xf.data(), P.xface, sizeof(double) * xf.size(), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(yf.data(), P.yface, sizeof(double) * yf.size(), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(zf.data(), P.zface, sizeof(double) * zf.size(), cudaMemcpyDeviceToHost));
+  h->sight_steps = 0.0;
+  h->sight_ms = 0.0;
+  for (size_t k = 0; k < h->obs_host.size(); ++k) {
+    const DevObserver &ob = h->obs_host[k];
+    if (!out[k].tau_gas || !out[k].N_gas) return fail("lart_gpu_sightline_tau: tau_gas / N_gas output is NULL");
+    const long long npix = (long long)ob.nxim * ob.nyim;
+    std::vector<SightStart> st((size_t)npix);
+    for (int iy = 1; iy <= ob.nyim; ++iy)
+      for (int ix = 1; ix <= ob.nxim; ++ix) sightline_start(h, xf, yf, zf, ob, ix, iy, st[(size_t)(ix - 1) + (size_t)ob.nxim * (iy - 1)]);
+    Scratch s;
+    SightStart *dst;
+    double *dtau, *dN, *dtd = nullptr;
+    unsigned long long *dsteps;
+    if (int rc = s.in(&dst, st.data(), (size_t)npix)) return rc;
+    if (int rc = s.outbuf(&dtau, (size_t)npix * P.nxfreq)) return rc;
+    if (int rc = s.outbuf(&dN, (size_t)npix)) return rc;
+    if (P.dust && out[k].tau_dust) if (int rc = s.outbuf(&dtd, (size_t)npix)) return rc;
+    if (int rc = s.outbuf(&dsteps, 1)) return rc;
+    CUDA_OK(cudaMemsetAsync(dtau, 0, sizeof(double) * (size_t)npix * P.nxfreq, h->stream));
+    CUDA_OK(cudaMemsetAsync(dN, 0, sizeof(double) * (size_t)npix, h->stream));
+    if (dtd) CUDA_OK(cudaMemsetAsync(dtd, 0, sizeof(double) * (size_t)npix, h->stream));
+    CUDA_OK(cudaMemsetAsync(dsteps, 0, sizeof(unsigned long long), h->stream));
+    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+    k_sightline<<<h->nsm * 8, kBlock, 0, h->stream>>>(P, npix, dst, cross0, dtau, dN, dtd, dsteps);
+    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    unsigned long long ns = 0;
+    D2H(&ns, dsteps, 1);
+    h->sight_ms += ms;
+    h->sight_steps += (double)ns;
+    h->launches += 1;
+    D2H(out[k].tau_gas, dtau, (size_t)npix * P.nxfreq);
+    D2H(out[k].N_gas, dN, (size_t)npix);
+    if (dtd) D2H(out[k].tau_dust, dtd, (size_t)npix);
+  }
+  return 0;
+}
+
+/* cell steps and CUDA-event time (ms) of the last lart_gpu_sightline_tau call */
+int lart_gpu_sightline_stats(lart_gpu_handle h, double *cellsteps, double *ms) {
+  if (!h) return fail("lart_gpu_sightline_stats: NULL handle");
+  if (cellsteps) *cellsteps = h->sight_steps;
+  if (ms) *ms = h->sight_ms;
+  return 0;
+}
 }  // extern "C"

@@ -284,6 +284,28 @@ class Simulation:
         if rank == dst:
             self._check(self._lib.lart_gpu_fetch(self._h, self.model.tallies))
 
+    def sightline_tau(self):
+        """make_sightline_tau_outside (sightline_tau_rect.f90:11-190): per observer the maps
+        tau_gas(nxfreq,nxim,nyim), N_gas(nxim,nyim) and, with dust, tau_dust(nxim,nyim)."""
+        cfg = self.model.config.contents
+        nobs, nxf = cfg.par.nobs, cfg.grid.nxfreq
+        outs = (capi.SightlineOut * max(nobs, 1))()
+        maps = []
+        for k in range(nobs):
+            ob = cfg.observers[k]
+            tg = np.zeros((nxf, ob.nxim, ob.nyim), order="F")
+            ng = np.zeros((ob.nxim, ob.nyim), order="F")
+            td = np.zeros((ob.nxim, ob.nyim), order="F") if cfg.par.DGR > 0 else None
+            outs[k].tau_gas = tg.ctypes.data_as(capi.c_double_p)
+            outs[k].N_gas = ng.ctypes.data_as(capi.c_double_p)
+            outs[k].tau_dust = td.ctypes.data_as(capi.c_double_p) if td is not None else None
+            maps.append(dict(tau_gas=tg, N_gas=ng, tau_dust=td))
+        self._check(self._lib.lart_gpu_sightline_tau(self._h, self.model.summary.cross0, outs))
+        steps, ms = C.c_double(), C.c_double()
+        self._check(self._lib.lart_gpu_sightline_stats(self._h, C.byref(steps), C.byref(ms)))
+        self.sightline_stats = dict(cellsteps=steps.value, ms=ms.value)
+        return maps
+
     # ---- unit-level batched plugin points (define.f90:741-784) -------------
     def raytrace_to_edge(self, x, y, z, kx, ky, kz, xfreq, icell, jcell, kcell, trace_cap=0):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)

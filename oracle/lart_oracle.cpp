@@ -1259,6 +1259,113 @@ void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_event
   if (w.par->save_all_photons && !(max_events > 0 && ph.inside)) record_final(w, ph, tl.shared->allph);
 }
 
+// raytrace_to_edge_car_tau_gas — raytrace_car.f90:1236-1328 (gas only, no tau cap)
+double raytrace_to_edge_tau_gas(const World &w, const Photon &p0, long long *nsteps) {
+  const lart_grid &g = *w.g;
+  double xp = p0.x, yp = p0.y, zp = p0.z, kx = p0.kx, ky = p0.ky, kz = p0.kz;
+  int ic = p0.icell, jc = p0.jcell, kc = p0.kcell;
+  double tau = 0.0, d = 0.0;
+  Trav t;
+  if (setup_traversal(w, xp, yp, zp, kx, ky, kz, ic, jc, kc, t, false)) return tau;
+  int io = ic, jo = jc, ko = kc;
+  double u1 = w.vdotk(io, jo, ko, kx, ky, kz);
+  double xfreq = p0.xfreq;
+  for (;;) {
+    double rhokap = w.rhokap(ic, jc, kc) * w.calc_voigt(xfreq, ic, jc, kc);
+    if (nsteps) ++*nsteps;
+    int m = w.zonly ? 3 : minloc3(t.tx, t.ty, t.tz);
+    if (m == 1) { tau += (t.tx - d) * rhokap; d = t.tx; ic += t.istep; if (ic < 1 || ic > g.nx) break; t.tx += t.delx; }
+    else if (m == 2) { tau += (t.ty - d) * rhokap; d = t.ty; jc += t.jstep; if (jc < 1 || jc > g.ny) break; t.ty += t.dely; }
+    else { tau += (t.tz - d) * rhokap; d = t.tz; kc += t.kstep; if (kc < 1 || kc > g.nz) break; t.tz += t.delz; }
+    double u2 = w.vdotk(ic, jc, kc, kx, ky, kz);
+    xfreq = (xfreq + u1) * w.Dfreq(io, jo, ko) / w.Dfreq(ic, jc, kc) - u2;
+    io = ic; jo = jc; ko = kc;
+    u1 = u2;
+  }
+  return tau;
+}
+
+// raytrace_to_edge_car_column — raytrace_car.f90:1330-1423
+void raytrace_to_edge_column(const World &w, const Photon &p0, double cross0, double &N_gas, double &tau_dust, long long *nsteps) {
+  const lart_grid &g = *w.g;
+  double xp = p0.x, yp = p0.y, zp = p0.z, kx = p0.kx, ky = p0.ky, kz = p0.kz;
+  int ic = p0.icell, jc = p0.jcell, kc = p0.kcell;
+  N_gas = 0.0; tau_dust = 0.0;
+  double d = 0.0;
+  Trav t;
+  if (setup_traversal(w, xp, yp, zp, kx, ky, kz, ic, jc, kc, t, false)) return;
+  for (;;) {
+    double rho = w.rhokap(ic, jc, kc) * w.Dfreq(ic, jc, kc) / cross0;
+    double rkD = w.dust() ? w.rhokapD(ic, jc, kc) : 0.0;
+    if (nsteps) ++*nsteps;
+    int m = w.zonly ? 3 : minloc3(t.tx, t.ty, t.tz);
+    double tn = (m == 1) ? t.tx : (m == 2) ? t.ty : t.tz;
+    double del = tn - d;
+    N_gas += del * rho;
+    if (w.dust()) tau_dust += del * rkD;
+    d = tn;
+    if (m == 1) { ic += t.istep; if (ic < 1 || ic > g.nx) break; t.tx += t.delx; }
+    else if (m == 2) { jc += t.jstep; if (jc < 1 || jc > g.ny) break; t.ty += t.dely; }
+    else { kc += t.kstep; if (kc < 1 || kc > g.nz) break; t.tz += t.delz; }
+  }
+}
+
+// Entry point and start cell of the sight line of pixel (ix,iy) of one observer —
+// sightline_tau_rect.f90:45-150.  Returns false when the line misses the grid.
+bool sightline_start(const lart_grid &g, const lart_observer &ob, int ix, int iy, Photon &po) {
+  double kx = std::tan((ix - (ob.nxim + 1.0) / 2.0) * ob.dxim / kRad2Deg);
+  double ky = std::tan((iy - (ob.nyim + 1.0) / 2.0) * ob.dyim / kRad2Deg);
+  double kz = -1.0;
+  double kr = std::sqrt(kx * kx + ky * ky + kz * kz);
+  kx /= kr; ky /= kr; kz /= kr;
+  const double *R = ob.rmatrix;  // R[(r-1)+3*(c-1)]: transpose applied here (:57-59)
+  po.kx = R[0] * kx + R[1] * ky + R[2] * kz;
+  po.ky = R[3] * kx + R[4] * ky + R[5] * kz;
+  po.kz = R[6] * kx + R[7] * ky + R[8] * kz;
+  double delt[6];
+  delt[0] = (po.kx == 0.0) ? kHugest : (g.xmax - ob.x) / po.kx;
+  delt[1] = (po.kx == 0.0) ? kHugest : (g.xmin - ob.x) / po.kx;
+  delt[2] = (po.ky == 0.0) ? kHugest : (g.ymax - ob.y) / po.ky;
+  delt[3] = (po.ky == 0.0) ? kHugest : (g.ymin - ob.y) / po.ky;
+  delt[4] = (po.kz == 0.0) ? kHugest : (g.zmax - ob.z) / po.kz;
+  delt[5] = (po.kz == 0.0) ? kHugest : (g.zmin - ob.z) / po.kz;
+  auto cellof = [&](double x, double y, double z, int &i, int &j, int &k) {
+    i = static_cast<int>(std::floor((x - g.xmin) / g.dx)) + 1;
+    j = static_cast<int>(std::floor((y - g.ymin) / g.dy)) + 1;
+    k = static_cast<int>(std::floor((z - g.zmin) / g.dz)) + 1;
+  };
+  double dist = -999.9;
+  int j0 = 0;
+  for (int jj = 1; jj <= 6; ++jj) {  // the farthest boundary the ray touches (:79-106)
+    double dl = delt[jj - 1];
+    if (dl > 0.0 && dl < kHugest) {
+      int i, j, k;
+      cellof(ob.x + po.kx * dl, ob.y + po.ky * dl, ob.z + po.kz * dl, i, j, k);
+      if (jj == 1) i = g.nx + 1;
+      if (jj == 2) i = 1;
+      if (jj == 3) j = g.ny + 1;
+      if (jj == 4) j = 1;
+      if (jj == 5) k = g.nz + 1;
+      if (jj == 6) k = 1;
+      if (i >= 1 && i <= g.nx + 1 && j >= 1 && j <= g.ny + 1 && k >= 1 && k <= g.nz + 1 && dl > dist) { dist = dl; j0 = jj; }
+    }
+  }
+  if (!(dist > 0.0 && dist < kHugest)) return false;
+  po.x = ob.x + po.kx * dist; po.y = ob.y + po.ky * dist; po.z = ob.z + po.kz * dist;
+  cellof(po.x, po.y, po.z, po.icell, po.jcell, po.kcell);
+  po.kx = -po.kx; po.ky = -po.ky; po.kz = -po.kz;  // toward the observer (:116-118)
+  if (j0 == 1) { po.icell = g.nx + 1; po.x = g.xface[g.nx]; }
+  else if (j0 == 2) { po.icell = 1; po.x = g.xface[0]; }
+  else if (j0 == 3) { po.jcell = g.ny + 1; po.y = g.yface[g.ny]; }
+  else if (j0 == 4) { po.jcell = 1; po.y = g.yface[0]; }
+  else if (j0 == 5) { po.kcell = g.nz + 1; po.z = g.zface[g.nz]; }
+  else if (j0 == 6) { po.kcell = 1; po.z = g.zface[0]; }
+  if (po.icell == g.nx + 1 && po.kx < 0.0) po.icell = g.nx;
+  if (po.jcell == g.ny + 1 && po.ky < 0.0) po.jcell = g.ny;
+  if (po.kcell == g.nz + 1 && po.kz < 0.0) po.kcell = g.nz;
+  return po.icell >= 1 && po.icell <= g.nx && po.jcell >= 1 && po.jcell <= g.ny && po.kcell >= 1 && po.kcell <= g.nz;
+}
+
 std::string g_err;
 
 World make_world(const lart_config *cfg) {
@@ -1428,6 +1535,35 @@ int oracle_run(const lart_config *cfg, int32_t rng_mode, int32_t nthreads, int64
     out->counters.n_rng += tl.cnt.n_rng;
     out->counters.n_reject_iter += tl.cnt.n_reject_iter;
   }
+  return 0;
+}
+
+// make_sightline_tau_outside — sightline_tau_rect.f90:11-190.  out[k] as lart_sightline_out.
+int oracle_sightline_tau(const lart_config *cfg, double cross0, lart_sightline_out *out, double *cellsteps) {
+  World w = make_world(cfg);
+  const lart_grid &g = cfg->grid;
+  long long ns = 0;
+  for (int i = 0; i < cfg->par.nobs; ++i) {
+    const lart_observer &ob = cfg->observers[i];
+    for (int iy = 1; iy <= ob.nyim; ++iy)
+      for (int ix = 1; ix <= ob.nxim; ++ix) {
+        Photon po;
+        size_t pix = static_cast<size_t>(ix - 1) + static_cast<size_t>(ob.nxim) * (iy - 1);
+        if (!sightline_start(g, ob, ix, iy, po)) continue;
+        double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+        double Dc = w.Dfreq(po.icell, po.jcell, po.kcell);
+        for (int kk = 1; kk <= g.nxfreq; ++kk) {
+          double xf = (kk - 0.5) * g.dxfreq + g.xfreq_min;  // grid%xfreq(kk), grid_mod_car.f90:1505
+          po.xfreq = xf * g.Dfreq_ref / Dc - u1;
+          out[i].tau_gas[(kk - 1) + static_cast<size_t>(g.nxfreq) * pix] = raytrace_to_edge_tau_gas(w, po, &ns);
+        }
+        double N, td;
+        raytrace_to_edge_column(w, po, cross0, N, td, &ns);
+        out[i].N_gas[pix] = N;
+        if (out[i].tau_dust && w.dust()) out[i].tau_dust[pix] = td;
+      }
+  }
+  if (cellsteps) *cellsteps = static_cast<double>(ns);
   return 0;
 }
 

@@ -47,6 +47,7 @@ def load():
         lib.oracle_run.argtypes = [cfgp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                    C.POINTER(capi.Tallies)]
         lib.oracle_hardware_threads.restype = C.c_int
+        lib.oracle_sightline_tau.argtypes = [cfgp, C.c_double, C.POINTER(capi.SightlineOut), C.POINTER(C.c_double)]
         _LIB = lib
     return _LIB
 
@@ -153,3 +154,23 @@ def run(model, rng_mode=1, nthreads=None, first_id=1, count=None, stride=1, max_
     if nthreads is None:
         nthreads = hardware_threads()
     _check(load().oracle_run(cfg, rng_mode, nthreads, first_id, count, stride, max_events, model.tallies))
+
+
+def sightline_tau(model):
+    """make_sightline_tau_outside on the CPU: list of dict(tau_gas, N_gas, tau_dust) per observer."""
+    cfg = model.config.contents
+    nobs, nxf = cfg.par.nobs, cfg.grid.nxfreq
+    outs = (capi.SightlineOut * max(nobs, 1))()
+    maps = []
+    for k in range(nobs):
+        ob = cfg.observers[k]
+        tg = np.zeros((nxf, ob.nxim, ob.nyim), order="F")
+        ng = np.zeros((ob.nxim, ob.nyim), order="F")
+        td = np.zeros((ob.nxim, ob.nyim), order="F") if cfg.par.DGR > 0 else None
+        outs[k].tau_gas = _d(tg)
+        outs[k].N_gas = _d(ng)
+        outs[k].tau_dust = _d(td) if td is not None else None
+        maps.append(dict(tau_gas=tg, N_gas=ng, tau_dust=td))
+    steps = C.c_double()
+    _check(load().oracle_sightline_tau(model.config, model.summary.cross0, outs, C.byref(steps)))
+    return maps, steps.value

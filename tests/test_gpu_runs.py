@@ -131,6 +131,22 @@ def test_results_do_not_depend_on_pool_size_or_scheduling():
     assert np.allclose(a.observer_cube("Q"), c.observer_cube("Q"), rtol=1e-9, atol=1e-16)
 
 
+@pytest.mark.parametrize("kw", [dict(pool_slots=128, quantum=4, ray_budget=3, streams=3),
+                                dict(pool_slots=96, quantum=1, ray_budget=1, streams=1),
+                                dict(pool_slots=4096, quantum=7, ray_budget=1000000, streams=16)],
+                         ids=["tiny-budget3", "budget1-serial", "unbounded-16streams"])
+def test_scheduling_stress_matches_oracle(kw):
+    """Parked and resumed walks (step budget), continuation queues, pool compaction, tail mode and many partitions:
+    the photon histories must not notice."""
+    par = dict(taumax=3e2, obsx=[0.0, 1.0], obsy=[0.0, 0.5], obsz=[1.0, 0.2], save_direc0=True, save_Jmu=True,
+               save_peeloff_2D=True, no_photons=1500)
+    mg, mo = small_sphere(**par), small_sphere(**par)
+    run_gpu(mg, **kw)
+    oracle.run(mo, rng_mode=1)
+    same = histories_equal(mg, mo)
+    tallies_close(mg, mo, same.mean())
+
+
 def test_rank_partition_sums_to_single_run():
     """Photon-id striding (run_simulation_mod.f90:150): two 'ranks' on one GPU sum to the one-rank tallies."""
     full = run_gpu(small_sphere())

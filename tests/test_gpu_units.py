@@ -179,3 +179,36 @@ def test_warp_cooperative_sampler_equals_serial():
     assert np.array_equal(serial, coop)
     # ragged tail: a batch that does not fill its last warp
     assert np.array_equal(sample(2, 5, ids[:45], x0[:45], a[:45], ndraw=2), sample(6, 5, ids[:45], x0[:45], a[:45], ndraw=2))
+
+
+def test_sightline_maps_match_oracle_and_column_density():
+    """Sight-line maps (SURVEY 8f-4): tau_gas(nu, pixel), N_gas and tau_dust per pixel, bit for bit against the oracle;
+    the central pixel's column density is 2 N_pole, and tau_gas at line centre is 2 tau0 there (static sphere)."""
+    from lart_b200 import Model
+    for kw in (dict(taumax=1e3), dict(N_HI=2e19, velocity_type="hubble", Vexp=200.0, xfreq_min=-40.0, xfreq_max=20.0,
+                                      DGR=1.0, cext_dust=1e-21, use_stokes=False),
+               dict(taumax=50.0, obsx=[0.3, -1.0], obsy=[0.2, 0.1], obsz=[1.0, 0.4], geometry="rectangle", rmax=-999.0,
+                    nx=12, ny=20, nz=16, xmax=0.6, ymax=1.0, zmax=0.8)):
+        par = dict(no_photons=10, temperature=1e4, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=31, nxim=21, nyim=17, use_stokes=True)
+        par.update(kw)
+        m = Model(**par).setup()
+        sim = Simulation(m, pool_slots=1024)
+        g = sim.sightline_tau()
+        o, osteps = oracle.sightline_tau(m)
+        assert len(g) == m.config.contents.par.nobs
+        for a, b in zip(g, o):
+            assert np.array_equal(a["tau_gas"], b["tau_gas"])
+            assert np.array_equal(a["N_gas"], b["N_gas"])
+            if b["tau_dust"] is not None:
+                assert np.array_equal(a["tau_dust"], b["tau_dust"]) and a["tau_dust"].max() > 0
+        assert sim.sightline_stats["cellsteps"] == osteps
+        sim.close()
+    m = Model(no_photons=10, temperature=1e4, taumax=1e3, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=31, nxim=21, nyim=21,
+              use_stokes=True).setup()
+    sim = Simulation(m, pool_slots=1024)
+    mp = sim.sightline_tau()[0]
+    s = m.summary
+    assert mp["N_gas"][10, 10] == pytest.approx(2 * s.N_gaspole, rel=1e-9)
+    assert mp["tau_gas"][15, 10, 10] == pytest.approx(2 * 1e3, rel=1e-9)  # bin 16 of 31 is centred on x = 0
+    assert mp["N_gas"][0, 0] == 0.0 or mp["N_gas"][0, 0] < mp["N_gas"][10, 10]
+    sim.close()

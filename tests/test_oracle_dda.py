@@ -81,3 +81,18 @@ def test_velocity_field_shifts_frequency():
     assert out["inside"][0] == 0
     # escaping along +z from rest at the centre: lab frequency equals the emitted one (comoving frame at v = 0)
     assert out["xfreq_ref"][0] == pytest.approx(0.0, abs=1e-12)
+
+
+def test_sightline_maps_analytic_centre():
+    """Sight-line maps of the oracle (sightline_tau_rect.f90:11-190): through the centre of a static sphere the
+    column is 2 N_pole and the line-centre optical depth 2 tau0; outside the projected sphere both vanish."""
+    m = Model(no_photons=10, temperature=1e4, taumax=1e3, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=31, nxim=21, nyim=21,
+              use_stokes=True, distance=50.0).setup()
+    maps, steps = oracle.sightline_tau(m)
+    s = m.summary
+    tg, ng = maps[0]["tau_gas"], maps[0]["N_gas"]
+    assert ng[10, 10] == pytest.approx(2 * s.N_gaspole, rel=1e-12)
+    assert tg[15, 10, 10] == pytest.approx(2e3, rel=1e-12)            # bin 16 of 31 is centred on x = 0
+    assert np.allclose(tg[::-1], tg, rtol=1e-12, atol=0)                # static medium: symmetric in frequency
+    assert np.allclose(ng, ng.T, rtol=1e-9) and np.allclose(ng, ng[::-1, :], rtol=1e-9)  # image symmetry
+    assert ng[0, 0] < 0.2 * ng[10, 10] and steps > 0

@@ -63,9 +63,6 @@ typedef struct lart_grid {
   double dxfreq;               /* grid%dxfreq                               */
   double xcrit, xcrit2;        /* grid%xcrit(2): global core-skip (:1186-1219) */
   double rmax;                 /* par%rmax (<=0: none); used by allph records  */
-  int32_t i0, j0, k0;          /* grid%i0,j0,k0 (grid_mod_car.f90:92-118): the cell a photon re-enters when it is
-                                  reflected at a lower face of an xyz-symmetric (one octant) grid; 0 otherwise */
-  int32_t pad_;
   const double *xface;         /* (nx+1)  xface(i) = (i-1)*dx + xmin        */
   const double *yface;         /* (ny+1)                                    */
   const double *zface;         /* (nz+1)                                    */
@@ -98,8 +95,6 @@ typedef struct lart_params {
   int32_t save_Jin, save_Jabs, save_Jmu;
   int32_t save_peeloff, save_peeloff_2D, save_peeloff_3D, save_direc0;
   int32_t save_all_photons;
-  int32_t xyz_symmetry;      /* one octant with mirror planes at the lower faces: binds the _xyzsym ray tracers
-                                (setup.f90:952-954; raytrace_car.f90:584-760, 1650-1949); no peel-off     */
   int32_t xy_periodic;       /* with nx==ny==1 binds the _zonly ray tracers
                                 (setup.f90:957-965); other periodic modes are
                                 rejected with an error                      */

@@ -59,7 +59,6 @@ struct DevParams {
   int nsbx, nsby, nsbz;  // 32^3 super-bricks of the packed cell array per axis
   double dx, dy, dz;
   double xmin, ymin, zmin, xmax, ymax, zmax;
-  int sym, i0, j0, k0;  // par%xyz_symmetry: mirror planes at the lower faces; i0 = cell entered on reflection (grid_mod_car.f90:85-113)
   double Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax;
   const double *xface, *yface, *zface;
   const Cell *cells;                                            // packed records (default walk)
@@ -269,30 +268,26 @@ struct Ray {
   int ic, jc, kc;                   // 1-based
   int istep, jstep, kstep;
   int nsteps;
-  int flip;                         // xyz symmetry: bit a set = direction component a reflected since the start
 };
 
 // One straight-line path for both signs of k (no divergent branch around the divide): the special cases of
 // raytrace_car.f90:27-44 — already outside (k>0), sitting on the lower face (k<0) — become predicates.
 // -d/k == d/|k| bit for bit; the increment itself is computed lazily by ray_advance.
-LART_DEV bool axis_setup(double &k, double p, int &cell, int n, const double *face, double d, int &step, double &t,
-                         double &del, bool eq_test, bool sym = false, int c0 = 0) {
+LART_DEV bool axis_setup(double k, double p, int &cell, int n, const double *face, double d, int &step, double &t,
+                         double &del, bool eq_test) {
   const bool pos = k > 0.0, neg = k < 0.0;
   const double flo = __ldg(face + cell - 1);
   bool leave = pos && cell > n && (eq_test ? (flo == p) : (flo <= p));
   const bool onface = neg && flo == p;
-  const bool reflect = sym && onface && cell <= 1;  // mirror plane: enter cell c0 going up (:1696-1700)
-  leave = leave || (onface && cell <= 1 && !sym);
-  cell = reflect ? c0 : cell - ((onface && cell > 1) ? 1 : 0);
-  const bool fwd = pos || reflect;
-  const int fi = fwd ? min(cell, n) : cell - 1;  // the face ahead (clamped: the reference reads past the end there)
+  leave = leave || (onface && cell <= 1);
+  cell -= (onface && cell > 1) ? 1 : 0;
+  const int fi = pos ? min(cell, n) : cell - 1;  // the face ahead (clamped: the reference reads past the end there)
   const double f = __ldg(face + fi);
-  k = reflect ? -k : k;
   const double tt = DSUB(f, p) / k;
   const bool moving = pos || neg;
   t = moving ? tt : kHugest;
   del = moving ? -1.0 : kHugest;  // d/|k|, filled in at the first crossing of this axis
-  step = fwd ? 1 : (neg ? -1 : 0);
+  step = pos ? 1 : (neg ? -1 : 0);
   return leave;
 }
 
@@ -302,16 +297,7 @@ LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z
                         int ic, int jc, int kc, double xfreq, bool zonly_eq, const CellData *here = nullptr) {
   r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
   r.ic = ic; r.jc = jc; r.kc = kc;
-  r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0; r.flip = 0;
-  if (P.sym) {  // raytrace_to_tau_car_xyzsym tests `== xp` (:1681), raytrace_to_edge_car_xyzsym `<= xp` (:613)
-    if (axis_setup(r.kx, x, r.ic, P.nx, P.xface, P.dx, r.istep, r.tx, r.delx, zonly_eq, true, P.i0)) return true;
-    if (axis_setup(r.ky, y, r.jc, P.ny, P.yface, P.dy, r.jstep, r.ty, r.dely, zonly_eq, true, P.j0)) return true;
-    if (axis_setup(r.kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, zonly_eq, true, P.k0)) return true;
-    r.flip = (r.kx != kx ? 1 : 0) | (r.ky != ky ? 2 : 0) | (r.kz != kz ? 4 : 0);
-    load_cell(P, r.ic, r.jc, r.kc, r.cell);
-    r.u1 = vdotk(r.cell, r.kx, r.ky, r.kz);
-    return false;
-  }
+  r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0;
   if (P.zonly) {
     r.istep = r.jstep = 0; r.tx = r.ty = kHugest; r.delx = r.dely = kHugest;
     if (axis_setup(kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, zonly_eq)) return true;
@@ -326,16 +312,10 @@ LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z
   return false;
 }
 
-constexpr int kFlipShift = 28, kCellMask = (1 << kFlipShift) - 1;
 // Resume a suspended walk: start point and direction are the ray's own, the DDA state is what was saved.
 LART_DEV void ray_resume(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
                          double tx, double ty, double tz, double delx, double dely, double delz, double d, double tau,
-                         double xfreq, double u1, int ic, int jc, int kc_flip) {
-  const int kc = kc_flip & kCellMask, flip = kc_flip >> kFlipShift;  // see ray_save_state
-  if (flip & 1) kx = -kx;
-  if (flip & 2) ky = -ky;
-  if (flip & 4) kz = -kz;
-  r.flip = flip;
+                         double xfreq, double u1, int ic, int jc, int kc) {
   r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
   r.tx = tx; r.ty = ty; r.tz = tz; r.delx = delx; r.dely = dely; r.delz = delz;
   r.d = d; r.tau = tau; r.xfreq = xfreq; r.u1 = u1;
@@ -366,40 +346,21 @@ LART_DEV int ray_axis(const DevParams &P, const Ray &r) {
 LART_DEV bool ray_advance(const DevParams &P, Ray &r, int axis) {
   if (axis == 1) {
     r.ic += r.istep;
-    if (r.ic < 1 || r.ic > P.nx) {
-      if (!(P.sym && r.ic < 1)) { r.ic -= r.istep; return false; }
-      r.ic = P.i0; r.istep = 1; r.kx = -r.kx; r.flip ^= 1;  // reflected at the yz-plane (:1791-1795)
-    }
+    if (r.ic < 1 || r.ic > P.nx) { r.ic -= r.istep; return false; }
     if (r.delx < 0.0) r.delx = P.dx / fabs(r.kx);
     r.tx = DADD(r.tx, r.delx);
   } else if (axis == 2) {
     r.jc += r.jstep;
-    if (r.jc < 1 || r.jc > P.ny) {
-      if (!(P.sym && r.jc < 1)) { r.jc -= r.jstep; return false; }
-      r.jc = P.j0; r.jstep = 1; r.ky = -r.ky; r.flip ^= 2;
-    }
+    if (r.jc < 1 || r.jc > P.ny) { r.jc -= r.jstep; return false; }
     if (r.dely < 0.0) r.dely = P.dy / fabs(r.ky);
     r.ty = DADD(r.ty, r.dely);
   } else {
     r.kc += r.kstep;
-    if (r.kc < 1 || r.kc > P.nz) {
-      if (!(P.sym && r.kc < 1)) { r.kc -= r.kstep; return false; }
-      r.kc = P.k0; r.kstep = 1; r.kz = -r.kz; r.flip ^= 4;
-    }
+    if (r.kc < 1 || r.kc > P.nz) { r.kc -= r.kstep; return false; }
     if (r.delz < 0.0) r.delz = P.dz / fabs(r.kz);
     r.tz = DADD(r.tz, r.delz);
   }
   return true;
-}
-// xyz symmetry: end point of a walk of length r.d.  The reference advances along the ORIGINAL direction
-// and mirrors the point back into the octant (raytrace_car.f90:1934-1940).
-LART_DEV void ray_endpoint_sym(const DevParams &P, const Ray &r, double &xp, double &yp, double &zp) {
-  xp = DADD(r.x0, DMUL(r.d, (r.flip & 1) ? -r.kx : r.kx));
-  yp = DADD(r.y0, DMUL(r.d, (r.flip & 2) ? -r.ky : r.ky));
-  zp = DADD(r.z0, DMUL(r.d, (r.flip & 4) ? -r.kz : r.kz));
-  if (xp < P.xmin) xp = -xp;
-  if (yp < P.ymin) yp = -yp;
-  if (zp < P.zmin) zp = -zp;
 }
 LART_DEV void ray_shift(const DevParams &P, Ray &r) {
   double Dold = r.cell.Dfreq;
@@ -434,7 +395,6 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
   r.d = tn;
   if (r.tau >= tau_in) {  // :1513-1524
     if (kap > 0.0) r.d = DSUB(r.d, DSUB(r.tau, tau_in) / kap);
-    if (P.sym) { ray_endpoint_sym(P, r, xp, yp, zp); return 1; }
     xp = DADD(r.x0, DMUL(r.d, r.kx));
     yp = DADD(r.y0, DMUL(r.d, r.ky));
     zp = DADD(r.z0, DMUL(r.d, r.kz));
@@ -760,7 +720,6 @@ LART_DEV int freq_bin(const DevParams &P, double xref) {  // 1-based; may be out
   return (int)floor((xref - P.xfreq_min) / P.dxfreq) + 1;
 }
 LART_DEV int jmu_bin(const DevParams &P, double kz) {  // add_to_Jmu — raytrace_car.f90:4049-4064
-  if (P.sym) kz = fabs(kz);  // :4058
   int imu = (int)floor((kz - P.mu_min) / P.dmu) + 1;
   return imu < 1 ? 1 : (imu > P.nmu ? P.nmu : imu);
 }
@@ -806,7 +765,7 @@ static_assert(sizeof(PeelCont) == 240, "PeelCont must be fifteen 16-byte chunks"
 LART_DEV void ray_save_state(const Ray &r, double *st10, int *c3) {
   st10[0] = r.tx; st10[1] = r.ty; st10[2] = r.tz; st10[3] = r.delx; st10[4] = r.dely; st10[5] = r.delz;
   st10[6] = r.d; st10[7] = r.tau; st10[8] = r.xfreq; st10[9] = r.u1;
-  c3[0] = r.ic; c3[1] = r.jc; c3[2] = r.kc | (r.flip << kFlipShift);
+  c3[0] = r.ic; c3[1] = r.jc; c3[2] = r.kc;
 }
 LART_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -1256,11 +1215,6 @@ LART_DEV void generate_photon(const DevParams &P, Photon &ph, Rng &r, Counters &
     ph.x = P.xs; ph.y = P.ys; ph.z = P.zs;
   }
   ph.wgt = 1.0;
-  if (P.sym) {  // sources are folded into the octant (:356-360)
-    if (ph.x < P.xmin) ph.x = -ph.x;
-    if (ph.y < P.ymin) ph.y = -ph.y;
-    if (ph.z < P.zmin) ph.z = -ph.z;
-  }
   double uc, up;
   r.uniform2(uc, up);
   double cost = 2.0 * uc - 1.0;

@@ -197,19 +197,9 @@ __device__ __forceinline__ int finish_escape(const DevParams &P, Photon &ph, con
   ph.xfreq = DADD(r.xfreq, r.u1);
   ph.xfreq_ref = DMUL(ph.xfreq, r.cell.Dfreq / P.Dfreq_ref);
   ph.x = r.x0; ph.y = r.y0; ph.z = r.z0;
-  if (P.sym) {  // raytrace_car.f90:1934-1943: the end point and the reflected direction are stored even on escape
-    ray_endpoint_sym(P, r, ph.x, ph.y, ph.z);
-    ph.kx = r.kx; ph.ky = r.ky; ph.kz = r.kz;
-  }
   if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
   ph.kc = r.kc;
   return r.nsteps;
-}
-// xyz symmetry: a photon that was reflected on its way carries the reflected direction from here on (:1941-1943);
-// its polarisation triad is left as it was, as in the reference.
-__device__ __forceinline__ void adopt_direction(const Ray &r, Photon &ph) { ph.kx = r.kx; ph.ky = r.ky; ph.kz = r.kz; }
-__device__ __forceinline__ void store_direction(const Pool &pl, int s, const Photon &ph) {
-  pl.f[F_KX * pl.S + s] = ph.kx; pl.f[F_KY * pl.S + s] = ph.ky; pl.f[F_KZ * pl.S + s] = ph.kz;
 }
 __device__ __forceinline__ int walk_tau(const DevParams &P, const double *vtab, Photon &ph, double tau_in, CellData &cs) {
   Ray r;
@@ -222,7 +212,6 @@ __device__ __forceinline__ int walk_tau(const DevParams &P, const double *vtab, 
     int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
     if (st == 1) {
       ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
-      if (P.sym) adopt_direction(r, ph);
       if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
       ph.kc = r.kc;
       cs = r.cell;
@@ -531,7 +520,6 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
           ph.kc = r.kc;
           ph.flags |= PH_SCATTER;
           cnt.cellsteps += r.nsteps;
-          if (P.sym && r.flip) { adopt_direction(r, ph); store_direction(pl, slot, ph); }
           store_trace_part(pl, slot, ph);
           pl.ndraw[slot] = rng.nblk;
           nrng += rng.nrng;
@@ -1088,12 +1076,6 @@ int validate(const lart_config *c) {
   if (p.save_peeloff && p.nobs > 0 && !c->observers) return fail("lart_gpu_create: observers is NULL");
   if (p.save_Jmu && (p.nmu < 1 || !(p.dmu > 0.0))) return fail("lart_gpu_create: save_Jmu needs nmu >= 1 and dmu > 0");
   if (!(g.dxfreq > 0.0)) return fail("lart_gpu_create: dxfreq must be > 0");
-  if (p.xyz_symmetry) {  // setup.f90:167, 198-206; grid_mod_car.f90:85-113
-    if (p.xy_periodic || g.nx < 2 || g.ny < 2 || g.nz < 2) return fail("lart_gpu_create: xyz_symmetry needs a 3-D, non-periodic grid");
-    if (p.save_peeloff) return fail("lart_gpu_create: peeling-off is not allowed with xyz_symmetry (setup.f90:198)");
-    if (g.i0 < 1 || g.i0 > 2 || g.j0 < 1 || g.j0 > 2 || g.k0 < 1 || g.k0 > 2) return fail("lart_gpu_create: xyz_symmetry needs grid.i0/j0/k0 in {1,2}");
-    if (g.nz >= (1 << kFlipShift)) return fail("lart_gpu_create: nz too large");
-  }
   return 0;
 }
 }  // namespace
@@ -1150,8 +1132,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   P.soa = (cfg->flags & LART_FLAG_SOA_GRID) ? 1 : 0;
   P.warp_agg = (cfg->flags & LART_FLAG_NO_WARP_AGG) ? 0 : 1;
   P.flags_serial_vz = (cfg->flags & LART_FLAG_SERIAL_REJECTION) ? 1 : 0;
-  P.sym = p.xyz_symmetry ? 1 : 0; P.i0 = g.i0; P.j0 = g.j0; P.k0 = g.k0;
-  P.local_steps = ((cfg->flags & LART_FLAG_LOCAL_STEPS) && !P.sym) ? 1 : 0;  // the in-stage cell step knows no mirror planes
+  P.local_steps = (cfg->flags & LART_FLAG_LOCAL_STEPS) ? 1 : 0;
   P.nsbx = (g.nx + 31) / 32; P.nsby = (g.ny + 31) / 32; P.nsbz = (g.nz + 31) / 32;
   if (!P.soa) {
     Cell *cells = nullptr;
@@ -1900,7 +1881,6 @@ int lart_gpu_sightline_tau(lart_gpu_handle h, double cross0, lart_sightline_out 
   if (!h || !out) return fail("lart_gpu_sightline_tau: NULL argument");
   if (h->obs_host.empty()) return fail("lart_gpu_sightline_tau: the handle has no observers (par%save_peeloff, par%nobs)");
   if (h->P.zonly) return fail("lart_gpu_sightline_tau: not defined for the xy-periodic slab");
-  if (h->P.sym) return fail("lart_gpu_sightline_tau: not defined for an xyz_symmetry octant grid");
   if (!(cross0 > 0.0)) return fail("lart_gpu_sightline_tau: cross0 must be > 0");
   CUDA_OK(cudaSetDevice(h->device));
   const DevParams &P = h->P;

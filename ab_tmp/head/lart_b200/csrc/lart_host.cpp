@@ -297,11 +297,9 @@ int derive(lart_host_model *m) {
   if (p.temperature0 <= 0.0) p.temperature0 = p.temperature;       // :127
   if (p.temperature <= 0.0 && p.bturb <= 0.0) { g_err = "par%temperature must be > 0 K (or set par%bturb > 0)"; return 1; }
   if (p.nx == 1 || p.ny == 1 || p.nz == 1) p.xyz_symmetry = false;  // :167
-  if (p.xy_symmetry || p.z_symmetry) { g_err = "xy/z symmetry-folded grids stay with the Fortran host (xyz_symmetry is supported)"; return 1; }
-  if (p.xyz_symmetry && p.xy_periodic) { g_err = "xyz_symmetry and xy_periodic exclude each other"; return 1; }
+  if (p.xyz_symmetry || p.xy_symmetry || p.z_symmetry) { g_err = "symmetry-folded grids stay with the Fortran host"; return 1; }
   if (!(p.save_peeloff_2D || p.save_peeloff_3D)) p.save_peeloff = false;  // :188
   if (p.nxim > 0 && p.nyim > 0) p.save_peeloff = true;                    // :189
-  if (p.save_peeloff && p.xyz_symmetry) p.save_peeloff = false;  // :191-199 peeling-off is not allowed with xyz_symmetry
   if (!p.save_peeloff) { p.save_peeloff_2D = false; p.save_peeloff_3D = false; }
   if (p.tau0 > 0.0 && p.taumax < 0.0) p.taumax = p.tau0;   // :220-223
   if (p.N_HI > 0.0 && p.N_HImax < 0.0) p.N_HImax = p.N_HI;
@@ -312,8 +310,7 @@ int derive(lart_host_model *m) {
   if (p.core_skip_global) p.core_skip = true;
   if (p.save_Jmu) {  // :375-389
     if (p.nmu < 1) { g_err = "par%nmu must be >= 1 when par%save_Jmu = .true."; return 1; }
-    if (p.xyz_symmetry) { p.mu_min = 0.0; p.dmu = 1.0 / p.nmu; }  // escapes are folded onto the +z hemisphere
-    else { p.mu_min = -1.0; p.dmu = 2.0 / p.nmu; }
+    p.mu_min = -1.0; p.dmu = 2.0 / p.nmu;
   }
   if (p.nr > 1) { p.nx = p.nr; p.ny = p.nr; if (p.geometry != "cylinder") p.nz = p.nr; }  // :392-396
   if (p.geometry == "sphere") {  // :406-418
@@ -366,19 +363,9 @@ int grid_create(lart_host_model *m) {
   const Line &ln = m->line;
   const int nx = p.nx, ny = p.ny, nz = p.nz;
   const size_t nc = static_cast<size_t>(nx) * ny * nz;
-  // :92-118 (xyz symmetry: one octant, mirror planes at the lower faces) / :168-176 (no symmetry)
-  double dx, dy, dz, xmin, ymin, zmin;
-  int i0 = 0, j0 = 0, k0 = 0;
-  if (p.xyz_symmetry) {
-    auto axis = [](int n, double vmax, double &d, double &vmin, int &c0) {
-      if ((n / 2) * 2 == n) { d = vmax / n; vmin = 0.0; c0 = 1; }
-      else { d = vmax / (n - 0.5); vmin = -d / 2.0; c0 = 2; }
-    };
-    axis(nx, p.xmax, dx, xmin, i0); axis(ny, p.ymax, dy, ymin, j0); axis(nz, p.zmax, dz, zmin, k0);
-  } else {
-    dx = 2.0 * p.xmax / nx; dy = 2.0 * p.ymax / ny; dz = 2.0 * p.zmax / nz;
-    xmin = -p.xmax; ymin = -p.ymax; zmin = -p.zmax;
-  }
+  // :168-176 (no symmetry)
+  const double dx = 2.0 * p.xmax / nx, dy = 2.0 * p.ymax / ny, dz = 2.0 * p.zmax / nz;
+  const double xmin = -p.xmax, ymin = -p.ymax, zmin = -p.zmax;
   m->xface.resize(nx + 1); m->yface.resize(ny + 1); m->zface.resize(nz + 1);
   for (int i = 1; i <= nx + 1; ++i) m->xface[i - 1] = (i - 1) * dx + xmin;  // :188-190
   for (int j = 1; j <= ny + 1; ++j) m->yface[j - 1] = (j - 1) * dy + ymin;
@@ -435,45 +422,29 @@ int grid_create(lart_host_model *m) {
   double opac_length;  // :495-503
   if (p.rmax > 0.0 && p.rmin > 0.0) opac_length = p.rmax - p.rmin;
   else if (p.rmax > 0.0) opac_length = p.rmax;
-  else if (p.zmax == -zmin) opac_length = (p.zmax - zmin) / 2.0;
-  else opac_length = p.zmax - zmin;
-  const bool sym = p.xyz_symmetry;
-  const bool zodd = (nz / 2) * 2 != nz;
-  const int nxcen = sym ? 1 : (nx + 1) / 2, nycen = sym ? 1 : (ny + 1) / 2;  // :505-515 (1-based)
+  else opac_length = (2.0 * p.zmax) / 2.0;  // zmax == -zmin always here
+  const int nxcen = (nx + 1) / 2, nycen = (ny + 1) / 2;  // :513-514 (1-based)
   // voigt(0,a): |x|<1 branch of voigt_seon2 at x=0 is h0(1)+a*(h1(1)+a*h2(1))
   // (voigt_mod.f90:691-700; h0(1)=1, h1(1)=-1.1283791671, h2(1)=1).
   auto voigt0 = [](double a) { return 1.0 + a * (-1.1283791671e+00 + a * 1.0); };
   auto scale_all = [&](double f) { for (auto &v : m->rhokap) v *= f; if (dust) for (auto &v : m->rhokapD) v *= f; };
-  auto homo_sum = [&](auto weight, double &nopac) {  // cells cut by a mirror plane count half (:545-556)
+  auto homo_sum = [&](auto weight, double &nopac) {
     double s = 0.0; nopac = 0.0;
-    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
-      size_t c = at(i, j, k);
-      if (!(m->rhokap[c] > 0.0)) continue;
-      double nadd = 1.0;
-      if (sym) {
-        if (i == 0 && (nx / 2) * 2 != nx) nadd /= 2.0;
-        if (j == 0 && (ny / 2) * 2 != ny) nadd /= 2.0;
-        if (k == 0 && zodd) nadd /= 2.0;
-      }
-      s += weight(c) * nadd; nopac += nadd;
-    }
+    for (size_t c = 0; c < nc; ++c) if (m->rhokap[c] > 0.0) { s += weight(c); nopac += 1.0; }
     return s;
-  };
-  // pole integral -> length factor (:524-537, :696-704): full box 2 tau = sum*dz; octant tau = (sum - first/2)*dz
-  auto pole = [&](auto weight) {
-    double s = 0.0;
-    for (int k = 0; k < nz; ++k) s += weight(at(nxcen - 1, nycen - 1, k));
-    if (sym) return (zodd ? s - weight(at(nxcen - 1, nycen - 1, 0)) / 2.0 : s) * dz;
-    return (p.zmax == -zmin) ? s * dz / 2.0 : s * dz;
   };
   double nopac;
   if (p.taumax > 0.0) {  // :518-538
-    scale_all(p.taumax / pole([&](size_t c) { return m->rhokap[c] * voigt0(m->voigt_a[c]); }));
+    double s = 0.0;
+    for (int k = 0; k < nz; ++k) { size_t c = at(nxcen - 1, nycen - 1, k); s += m->rhokap[c] * voigt0(m->voigt_a[c]); }
+    scale_all((2.0 * p.taumax) / (s * dz));
   } else if (p.tauhomo > 0.0) {  // :539-566
     double s = homo_sum([&](size_t c) { return m->rhokap[c] * voigt0(m->voigt_a[c]); }, nopac);
     scale_all(p.tauhomo / (s / nopac * opac_length));
   } else if (p.N_gasmax > 0.0) {  // :567-587
-    scale_all(p.N_gasmax / (pole([&](size_t c) { return m->rhokap[c] * m->Dfreq[c]; }) / ln.cross0));
+    double s = 0.0;
+    for (int k = 0; k < nz; ++k) { size_t c = at(nxcen - 1, nycen - 1, k); s += m->rhokap[c] * m->Dfreq[c]; }
+    scale_all((2.0 * p.N_gasmax) / (s * dz / ln.cross0));
   } else if (p.N_gashomo > 0.0) {  // :588-615
     double s = homo_sum([&](size_t c) { return m->rhokap[c] * m->Dfreq[c]; }, nopac);
     scale_all(p.N_gashomo / ((s / nopac / ln.cross0) * opac_length));
@@ -481,15 +452,21 @@ int grid_create(lart_host_model *m) {
   // diagnostics :617-743
   double s = homo_sum([&](size_t c) { return m->rhokap[c] * voigt0(m->voigt_a[c]); }, nopac);
   double tauhomo = s / nopac * opac_length;
-  double taupole = pole([&](size_t c) { return m->rhokap[c] * voigt0(m->voigt_a[c]); });
+  s = 0.0;
+  for (int k = 0; k < nz; ++k) { size_t c = at(nxcen - 1, nycen - 1, k); s += m->rhokap[c] * voigt0(m->voigt_a[c]); }
+  double taupole = s * dz / 2.0;
   s = homo_sum([&](size_t c) { return m->rhokap[c] * m->Dfreq[c]; }, nopac);
   double N_gashomo = s / nopac / ln.cross0 * opac_length;
-  double N_gaspole = pole([&](size_t c) { return m->rhokap[c] * m->Dfreq[c]; }) / ln.cross0;
+  s = 0.0;
+  for (int k = 0; k < nz; ++k) { size_t c = at(nxcen - 1, nycen - 1, k); s += m->rhokap[c] * m->Dfreq[c]; }
+  double N_gaspole = s * dz / 2.0 / ln.cross0;
   double tauhomo_dust = 0.0, taupole_dust = 0.0;
   if (dust) {
     s = homo_sum([&](size_t c) { return m->rhokapD[c]; }, nopac);
     tauhomo_dust = s / nopac * opac_length;
-    taupole_dust = pole([&](size_t c) { return m->rhokapD[c]; });
+    s = 0.0;
+    for (int k = 0; k < nz; ++k) s += m->rhokapD[at(nxcen - 1, nycen - 1, k)];
+    taupole_dust = s * dz / 2.0;
   }
   if (p.taumax <= 0.0) p.taumax = taupole;  // :744-747
   if (p.tauhomo <= 0.0) p.tauhomo = tauhomo;
@@ -564,7 +541,6 @@ int grid_create(lart_host_model *m) {
   g.dx = dx; g.dy = dy; g.dz = dz;
   g.Dfreq_ref = Dfreq_ref; g.xfreq_min = p.xfreq_min; g.xfreq_max = p.xfreq_max; g.dxfreq = dxfreq;
   g.xcrit = xcrit; g.xcrit2 = xcrit2; g.rmax = p.rmax;
-  g.i0 = i0; g.j0 = j0; g.k0 = k0; g.pad_ = 0;
   g.xface = m->xface.data(); g.yface = m->yface.data(); g.zface = m->zface.data();
   g.rhokap = m->rhokap.data(); g.voigt_a = m->voigt_a.data(); g.Dfreq = m->Dfreq.data();
   g.vfx = m->vfx.data(); g.vfy = m->vfy.data(); g.vfz = m->vfz.data();
@@ -803,7 +779,7 @@ int lart_host_setup(lart_host_model *m) {
   q.use_stokes = p.use_stokes; q.use_reduced_wgt = p.use_reduced_wgt;
   q.save_Jin = p.save_Jin; q.save_Jabs = p.save_Jabs; q.save_Jmu = p.save_Jmu;
   q.save_peeloff = p.save_peeloff; q.save_peeloff_2D = p.save_peeloff_2D; q.save_peeloff_3D = p.save_peeloff_3D; q.save_direc0 = p.save_direc0;
-  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.nobs = p.nobs;
+  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.nobs = p.nobs;
   const Line &ln = m->line;
   c.line.line_type = ln.line_type; c.line.E1 = ln.E1; c.line.E2 = ln.E2; c.line.E3 = ln.E3;
   c.line.g_recoil0 = ln.g_recoil0; c.line.DnuHK_Hz = ln.DnuHK_Hz;

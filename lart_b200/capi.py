@@ -39,6 +39,7 @@ class Grid(C.Structure):
         ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
         ("Dfreq_ref", C.c_double), ("xfreq_min", C.c_double), ("xfreq_max", C.c_double),
         ("dxfreq", C.c_double), ("xcrit", C.c_double), ("xcrit2", C.c_double), ("rmax", C.c_double),
+        ("i0", C.c_int32), ("j0", C.c_int32), ("k0", C.c_int32), ("pad_", C.c_int32),
         ("xface", c_double_p), ("yface", c_double_p), ("zface", c_double_p),
         ("rhokap", c_double_p), ("voigt_a", c_double_p), ("Dfreq", c_double_p),
         ("vfx", c_double_p), ("vfy", c_double_p), ("vfz", c_double_p), ("rhokapD", c_double_p),
@@ -57,7 +58,7 @@ class Params(C.Structure):
         ("use_stokes", C.c_int32), ("use_reduced_wgt", C.c_int32),
         ("save_Jin", C.c_int32), ("save_Jabs", C.c_int32), ("save_Jmu", C.c_int32),
         ("save_peeloff", C.c_int32), ("save_peeloff_2D", C.c_int32), ("save_peeloff_3D", C.c_int32),
-        ("save_direc0", C.c_int32), ("save_all_photons", C.c_int32), ("xy_periodic", C.c_int32),
+        ("save_direc0", C.c_int32), ("save_all_photons", C.c_int32), ("xyz_symmetry", C.c_int32), ("xy_periodic", C.c_int32),
         ("nobs", C.c_int32),
     ]
 

@@ -244,6 +244,7 @@ struct World {
   const lart_scatt_mat *sm;
   const lart_observer *obs;
   bool zonly;
+  bool sym = false;  // par%xyz_symmetry: mirror planes at the lower faces (raytrace_car.f90:584-760, 1650-1949)
   inline size_t idx(int i, int j, int k) const {
     return static_cast<size_t>(i - 1) + static_cast<size_t>(g->nx) * (static_cast<size_t>(j - 1) + static_cast<size_t>(g->ny) * static_cast<size_t>(k - 1));
   }
@@ -292,7 +293,8 @@ struct Trav {
   double tx, ty, tz, delx, dely, delz;
 };
 
-inline bool axis_setup(double k, double p, int &cell, int n, const double *face, double d, int &step, double &t, double &del, bool eq_test) {
+inline bool axis_setup(double &k, double p, int &cell, int n, const double *face, double d, int &step, double &t, double &del, bool eq_test,
+                       bool sym = false, int c0 = 0) {
   if (k > 0.0) {
     if (cell > n) {
       double f = face[cell - 1];
@@ -302,13 +304,14 @@ inline bool axis_setup(double k, double p, int &cell, int n, const double *face,
     t = (face[cell] - p) / k;
     del = d / k;
   } else if (k < 0.0) {
+    step = -1;
+    del = -d / k;
     if (face[cell - 1] == p) {
       if (cell > 1) cell -= 1;
+      else if (sym) { cell = c0; step = 1; k = std::fabs(k); }  // reflected at the mirror plane (:1696-1700)
       else return true;
     }
-    step = -1;
-    t = (face[cell - 1] - p) / k;
-    del = -d / k;
+    t = (step == 1) ? (face[cell] - p) / k : (face[cell - 1] - p) / k;
   } else {
     step = 0;
     t = kHugest;
@@ -317,20 +320,33 @@ inline bool axis_setup(double k, double p, int &cell, int n, const double *face,
   return false;
 }
 
-inline bool setup_traversal(const World &w, double xp, double yp, double zp, double kx, double ky, double kz,
-                            int &ic, int &jc, int &kc, Trav &t, bool zonly_eq) {
+inline bool setup_traversal(const World &w, double xp, double yp, double zp, double &kx, double &ky, double &kz,
+                            int &ic, int &jc, int &kc, Trav &t, bool is_tau) {
   const lart_grid &g = *w.g;
   if (w.zonly) {
-    // raytrace_car.f90:1184-1204 / :2559-2583 — only the z axis is walked
+    // raytrace_car.f90:1184-1204 / :2559-2583 — only the z axis is walked; the to_tau variant tests `== zp`
     t.istep = t.jstep = 0;
     t.tx = t.ty = kHugest;
     t.delx = t.dely = kHugest;
-    return axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, zonly_eq);
+    return axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, is_tau);
   }
-  if (axis_setup(kx, xp, ic, g.nx, g.xface, g.dx, t.istep, t.tx, t.delx, false)) return true;
-  if (axis_setup(ky, yp, jc, g.ny, g.yface, g.dy, t.jstep, t.ty, t.dely, false)) return true;
-  if (axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, false)) return true;
+  // xyz symmetry: the to_tau variant tests `==` (:1681), the to_edge variant `<=` (:613)
+  const bool eq = w.sym && is_tau;
+  if (axis_setup(kx, xp, ic, g.nx, g.xface, g.dx, t.istep, t.tx, t.delx, eq, w.sym, g.i0)) return true;
+  if (axis_setup(ky, yp, jc, g.ny, g.yface, g.dy, t.jstep, t.ty, t.dely, eq, w.sym, g.j0)) return true;
+  if (axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, eq, w.sym, g.k0)) return true;
   return false;
+}
+
+// index step along one axis; with xyz symmetry a photon that would leave through a lower face is reflected
+// (:1791-1799).  Returns false when the photon leaves the grid.
+inline bool advance_axis(const World &w, int &cell, int &step, double &k, int n, int c0) {
+  cell += step;
+  if (cell < 1) {
+    if (!w.sym) return false;
+    cell = c0; step = 1; k = -k;
+  } else if (cell > n) return false;
+  return true;
 }
 
 // minloc([tx,ty,tz],dim=1) — first minimum wins (raytrace_car.f90:476,1506)
@@ -368,20 +384,17 @@ double raytrace_to_edge(const World &w, const Photon &p0, Counters *cnt, int *ns
     if (m == 1) {
       tau += (t.tx - d) * rhokap;
       d = t.tx;
-      ic += t.istep;
-      if (ic < 1 || ic > g.nx) break;
+      if (!advance_axis(w, ic, t.istep, kx, g.nx, g.i0)) break;
       t.tx += t.delx;
     } else if (m == 2) {
       tau += (t.ty - d) * rhokap;
       d = t.ty;
-      jc += t.jstep;
-      if (jc < 1 || jc > g.ny) break;
+      if (!advance_axis(w, jc, t.jstep, ky, g.ny, g.j0)) break;
       t.ty += t.dely;
     } else {
       tau += (t.tz - d) * rhokap;
       d = t.tz;
-      kc += t.kstep;
-      if (kc < 1 || kc > g.nz) break;
+      if (!advance_axis(w, kc, t.kstep, kz, g.nz, g.k0)) break;
       t.tz += t.delz;
     }
     if (tau >= kTauHuge) break;
@@ -398,7 +411,7 @@ double raytrace_to_edge(const World &w, const Photon &p0, Counters *cnt, int *ns
 // add_to_Jmu — raytrace_car.f90:4049-4064
 inline int jmu_bin(const lart_params &par, double kz) {
   double mu = kz;
-  if (false) mu = std::fabs(mu);  // xyz_symmetry is out of scope on this path
+  if (par.xyz_symmetry) mu = std::fabs(mu);  // raytrace_car.f90:4058
   int imu = static_cast<int>(std::floor((mu - par.mu_min) / par.dmu)) + 1;
   if (imu < 1) imu = 1;
   if (imu > par.nmu) imu = par.nmu;
@@ -437,22 +450,20 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
         double d_overshoot = (tau - tau_in) / rhokap;
         d = d - d_overshoot;
       }
-      xp = xp + d * kx;
-      yp = yp + d * ky;
-      zp = zp + d * kz;
+      // the new position uses the ORIGINAL direction even after a reflection; it is mirrored back below (:1936-1941)
+      xp = xp + d * ph.kx;
+      yp = yp + d * ph.ky;
+      zp = zp + d * ph.kz;
       break;
     }
     if (m == 1) {
-      ic += t.istep;
-      if (ic < 1 || ic > g.nx) { ph.inside = false; break; }
+      if (!advance_axis(w, ic, t.istep, kx, g.nx, g.i0)) { ph.inside = false; break; }
       t.tx += t.delx;
     } else if (m == 2) {
-      jc += t.jstep;
-      if (jc < 1 || jc > g.ny) { ph.inside = false; break; }
+      if (!advance_axis(w, jc, t.jstep, ky, g.ny, g.j0)) { ph.inside = false; break; }
       t.ty += t.dely;
     } else {
-      kc += t.kstep;
-      if (kc < 1 || kc > g.nz) { ph.inside = false; break; }
+      if (!advance_axis(w, kc, t.kstep, kz, g.nz, g.k0)) { ph.inside = false; break; }
       t.tz += t.delz;
     }
     double u2 = w.vdotk(ic, jc, kc, kx, ky, kz);
@@ -474,7 +485,14 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
       }
     }
   }
+  if (w.sym) {  // :1936-1947 (d is the whole path when the photon left the grid)
+    if (!ph.inside) { xp = ph.x + d * ph.kx; yp = ph.y + d * ph.ky; zp = ph.z + d * ph.kz; }
+    if (xp < g.xmin) xp = -xp;
+    if (yp < g.ymin) yp = -yp;
+    if (zp < g.zmin) zp = -zp;
+  }
   ph.x = xp; ph.y = yp; ph.z = zp;
+  if (w.sym) { ph.kx = kx; ph.ky = ky; ph.kz = kz; }
   if (!w.zonly) { ph.icell = ic; ph.jcell = jc; }
   ph.kcell = kc;
   if (cnt) cnt->n_cellsteps += nsteps;
@@ -1108,6 +1126,11 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
   }
   // setup_isotropic_injection :342-408
   ph.wgt = 1.0;
+  if (w.sym) {  // :356-360 — sources are folded into the octant
+    if (ph.x < g.xmin) ph.x = -ph.x;
+    if (ph.y < g.ymin) ph.y = -ph.y;
+    if (ph.z < g.zmin) ph.z = -ph.z;
+  }
   double uc, up;
   r.uniform2(uc, up);
   double cost = 2.0 * uc - 1.0;
@@ -1376,6 +1399,7 @@ World make_world(const lart_config *cfg) {
   w.sm = &cfg->scatt_mat;
   w.obs = cfg->observers;
   w.zonly = cfg->par.xy_periodic && cfg->grid.nx == 1 && cfg->grid.ny == 1;  // setup.f90:957-965
+  w.sym = cfg->par.xyz_symmetry != 0;                                         // setup.f90:952-954
   return w;
 }
 

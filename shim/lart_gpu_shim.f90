@@ -37,6 +37,7 @@ module lart_gpu_shim
      integer(c_int32_t) :: nx, ny, nz, nxfreq
      real(c_double) :: xmin, ymin, zmin, xmax, ymax, zmax, dx, dy, dz
      real(c_double) :: Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax
+     integer(c_int32_t) :: i0, j0, k0, pad_
      type(c_ptr) :: xface, yface, zface, rhokap, voigt_a, Dfreq, vfx, vfy, vfz, rhokapD
   end type
   type, bind(C) :: c_lart_params
@@ -46,7 +47,7 @@ module lart_gpu_shim
      integer(c_int32_t) :: nmu, spectral_type, source_geometry, comoving_source, recoil
      integer(c_int32_t) :: core_skip, core_skip_global, use_stokes, use_reduced_wgt
      integer(c_int32_t) :: save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D
-     integer(c_int32_t) :: save_direc0, save_all_photons, xy_periodic, nobs
+     integer(c_int32_t) :: save_direc0, save_all_photons, xyz_symmetry, xy_periodic, nobs
   end type
   type, bind(C) :: c_lart_line
      integer(c_int32_t) :: line_type, pad_
@@ -158,6 +159,7 @@ contains
     cfg%grid%dx = grid%dx; cfg%grid%dy = grid%dy; cfg%grid%dz = grid%dz
     cfg%grid%Dfreq_ref = grid%Dfreq_ref; cfg%grid%xfreq_min = grid%xfreq_min; cfg%grid%xfreq_max = grid%xfreq_max
     cfg%grid%dxfreq = grid%dxfreq; cfg%grid%xcrit = grid%xcrit; cfg%grid%xcrit2 = grid%xcrit2; cfg%grid%rmax = par%rmax
+    cfg%grid%i0 = grid%i0; cfg%grid%j0 = grid%j0; cfg%grid%k0 = grid%k0; cfg%grid%pad_ = 0
     cfg%grid%xface = ploc(grid%xface); cfg%grid%yface = ploc(grid%yface); cfg%grid%zface = ploc(grid%zface)
     cfg%grid%rhokap = ploc(grid%rhokap); cfg%grid%voigt_a = ploc(grid%voigt_a); cfg%grid%Dfreq = ploc(grid%Dfreq)
     cfg%grid%vfx = ploc(grid%vfx); cfg%grid%vfy = ploc(grid%vfy); cfg%grid%vfz = ploc(grid%vfz)
@@ -195,6 +197,7 @@ contains
     cfg%par%save_peeloff = l2i(par%save_peeloff); cfg%par%save_peeloff_2D = l2i(par%save_peeloff_2D)
     cfg%par%save_peeloff_3D = l2i(par%save_peeloff_3D); cfg%par%save_direc0 = l2i(par%save_direc0)
     cfg%par%save_all_photons = l2i(par%save_all_photons); cfg%par%xy_periodic = l2i(par%xy_periodic)
+    cfg%par%xyz_symmetry = l2i(par%xyz_symmetry)
     cfg%par%nobs = merge(par%nobs, 0, par%save_peeloff)
 
     !--- line_type (src/define.f90:639-656)

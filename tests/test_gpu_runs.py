@@ -77,6 +77,13 @@ CASES = {
     "box_uniform_source_gaussian": dict(geometry="rectangle", rmax=-999.0, source_geometry="uniform", spectral_type="gaussian",
                                         nx=15, ny=9, nz=21, xmax=1.0, ymax=0.5, zmax=2.0, taumax=20.0),
     "off_centre_point_mono": dict(xs_point=0.3, ys_point=-0.2, zs_point=0.1, spectral_type="monochromatic", xfreq0=2.0),
+    # par%xyz_symmetry: one octant with mirror planes (no peeling-off: setup.f90:198); the source is folded into it
+    "xyz_symmetry_even": dict(xyz_symmetry=True, nx=16, ny=16, nz=16, nxim=0, nyim=0, save_Jmu=True, nmu=4),
+    "xyz_symmetry_odd_offcentre": dict(xyz_symmetry=True, nx=15, ny=15, nz=15, nxim=0, nyim=0, save_Jmu=True, nmu=5,
+                                       xs_point=0.3, ys_point=-0.2, zs_point=0.1),
+    "xyz_symmetry_hubble_uniform_sphere": dict(xyz_symmetry=True, nx=16, ny=15, nz=12, nxim=0, nyim=0, use_stokes=False,
+                                               velocity_type="hubble", Vexp=50.0, source_geometry="uniform_sphere",
+                                               taumax=30.0),
 }
 
 
@@ -145,6 +152,33 @@ def test_scheduling_stress_matches_oracle(kw):
     oracle.run(mo, rng_mode=1)
     same = histories_equal(mg, mo)
     tallies_close(mg, mo, same.mean())
+
+
+@pytest.mark.parametrize("kw", [dict(pool_slots=96, quantum=1, ray_budget=1, streams=1),
+                                dict(pool_slots=512, quantum=5, ray_budget=2, streams=3)], ids=["budget1", "budget2"])
+def test_xyz_symmetry_parked_walks_keep_their_reflections(kw):
+    """A walk parked at its step budget after a reflection must resume with the reflected direction."""
+    par = dict(xyz_symmetry=True, nx=15, ny=16, nz=15, nxim=0, nyim=0, save_Jmu=True, nmu=4, taumax=50.0, no_photons=1500,
+               xs_point=0.1, velocity_type="hubble", Vexp=20.0)
+    mg, mo = small_sphere(**par), small_sphere(**par)
+    run_gpu(mg, **kw)
+    oracle.run(mo, rng_mode=1)
+    same = histories_equal(mg, mo, geom_rtol=1e-6)
+    tallies_close(mg, mo, same.mean())
+
+
+def test_xyz_symmetry_octant_is_statistically_the_full_sphere():
+    """Spectrum and mean number of scatterings of the folded run against the full grid (independent histories)."""
+    kw = dict(no_photons=60000, taumax=1e3, nxim=0, nyim=0, use_stokes=False, save_Jmu=True, nmu=4, save_all_photons=False)
+    full = run_gpu(small_sphere(nx=32, ny=32, nz=32, **kw))
+    octa = run_gpu(small_sphere(nx=16, ny=16, nz=16, xyz_symmetry=True, iseed=99, **kw))
+    n = kw["no_photons"]
+    assert octa.nscatt_gas / n == pytest.approx(full.nscatt_gas / n, rel=0.02)
+    chi2, dof = chi2_per_bin(octa.spectrum("Jout"), full.spectrum("Jout"), n, n)
+    assert dof >= 20 and chi2 < 1.6, (chi2, dof)
+    # escapes are folded onto mu = |kz|: full-run bins [-1,-.5) + [.5,1] and [-.5,0) + [0,.5) against the octant's halves
+    jf, jo = full.spectrum("Jmu").sum(0), octa.spectrum("Jmu").sum(0)
+    assert np.allclose([jo[0] + jo[1], jo[2] + jo[3]], [jf[1] + jf[2], jf[0] + jf[3]], rtol=0.03)
 
 
 def test_rank_partition_sums_to_single_run():

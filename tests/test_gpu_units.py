@@ -93,6 +93,37 @@ def test_raytrace_to_tau_photon_state():
     sim.close()
 
 
+@pytest.mark.parametrize("dims", [(16, 16, 16), (15, 15, 15), (16, 15, 12)], ids=["even", "odd", "mixed"])
+def test_xyz_symmetry_rays_bit_exact(dims):
+    """raytrace_to_edge_car_xyzsym / raytrace_to_tau_car_xyzsym (raytrace_car.f90:584-760, 1650-1949): mirror planes at
+    the lower faces, including starts exactly on them and walks that are reflected more than once."""
+    nx, ny, nz = dims
+    m = Model(no_photons=10, temperature=1e4, N_HI=1e15, nx=nx, ny=ny, nz=nz, rmax=1.0, xyz_symmetry=True,
+              velocity_type="hubble", Vexp=100.0, nxfreq=50, xfreq_min=-40, xfreq_max=10).setup()
+    sim = Simulation(m, pool_slots=1024)
+    n = 100000
+    p, k, ic, xf = random_rays(m, n, 21)
+    g = m.config.contents.grid
+    q = n // 10
+    p[4 * q:5 * q, 0] = g.xmin  # on the mirror planes themselves
+    p[5 * q:6 * q, 2] = g.zmin
+    ic = np.clip(np.floor((p - [g.xmin, g.ymin, g.zmin]) / [g.dx, g.dy, g.dz]).astype(np.int32) + 1, 1, [nx, ny, nz])
+    cols = lambda a: (a[:, 0], a[:, 1], a[:, 2])
+    cap = 96
+    tg, ng, trg = sim.raytrace_to_edge(*cols(p), *cols(k), xf, *cols(ic), trace_cap=cap)
+    to, no, tro = oracle.raytrace_to_edge(m.config, *cols(p), *cols(k), xf, *cols(ic), trace_cap=cap)
+    assert np.array_equal(ng, no) and np.array_equal(trg, tro) and np.array_equal(tg, to)
+    assert ng.max() > max(dims) + 2  # reflected walks are longer than any straight one from the planes outwards
+    tau_in = np.random.default_rng(8).exponential(size=n) * np.median(to)
+    a = sim.raytrace_to_tau(*cols(p), *cols(k), xf, *cols(ic), tau_in)
+    b = oracle.raytrace_to_tau(m.config, *cols(p), *cols(k), xf, *cols(ic), tau_in)
+    for key in ("inside", "icell", "jcell", "kcell", "nsteps", "x", "y", "z", "xfreq", "xfreq_ref"):
+        assert np.array_equal(a[key], b[key]), key
+    assert 0.05 < a["inside"].mean() < 0.95
+    assert a["x"].min() >= g.xmin and a["y"].min() >= g.ymin and a["z"].min() >= g.zmin
+    sim.close()
+
+
 def test_slab_zonly_rays():
     m = Model(no_photons=10, temperature=1e4, taumax=1e4, xy_periodic=True, nx=1, ny=1, nz=201, nxfreq=121).setup()
     sim = Simulation(m, pool_slots=1024)

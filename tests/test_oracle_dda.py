@@ -96,3 +96,43 @@ def test_sightline_maps_analytic_centre():
     assert np.allclose(tg[::-1], tg, rtol=1e-12, atol=0)                # static medium: symmetric in frequency
     assert np.allclose(ng, ng.T, rtol=1e-9) and np.allclose(ng, ng[::-1, :], rtol=1e-9)  # image symmetry
     assert ng[0, 0] < 0.2 * ng[10, 10] and steps > 0
+
+
+@pytest.mark.parametrize("nfull,noct", [(32, 16), (29, 15)], ids=["even", "odd_straddling_cell"])
+def test_xyz_symmetry_octant_unfolds_to_the_full_grid(nfull, noct):
+    """par%xyz_symmetry (raytrace_car.f90:584-760, 1650-1949): a ray mirrored at the lower faces of the octant grid
+    sees the same medium as the straight ray in the full grid, and lands at the mirror image of its end point."""
+    kw = dict(no_photons=10, temperature=1e4, N_HI=3e14, rmax=1.0, velocity_type="hubble", Vexp=100.0, nxfreq=21)
+    full = Model(nx=nfull, ny=nfull, nz=nfull, **kw).setup()
+    octa = Model(nx=noct, ny=noct, nz=noct, xyz_symmetry=True, **kw).setup()
+    gf, go = full.config.contents.grid, octa.config.contents.grid
+    assert go.dx == pytest.approx(gf.dx, rel=1e-15) and go.i0 == (1 if noct % 2 == 0 else 2)
+    assert octa.config.contents.par.xyz_symmetry == 1
+    rng = np.random.default_rng(11)
+    n = 20000
+    p = rng.uniform(-0.999, 0.999, (n, 3))
+    k = rng.normal(size=(n, 3))
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    xf = rng.normal(size=n) * 2
+    sgn = np.where(p < 0, -1.0, 1.0)
+    pf, kf = np.abs(p), k * sgn
+    cell = lambda q, g: np.floor((q - [g.xmin, g.ymin, g.zmin]) / [g.dx, g.dy, g.dz]).astype(np.int32) + 1
+    ic, io = cell(p, gf), cell(pf, go)
+    cols = lambda a: (a[:, 0], a[:, 1], a[:, 2])
+    tf, nf, _ = oracle.raytrace_to_edge(full.config, *cols(p), *cols(k), xf, *cols(ic))
+    to, no, _ = oracle.raytrace_to_edge(octa.config, *cols(pf), *cols(kf), xf, *cols(io))
+    assert np.allclose(to, tf, rtol=1e-9, atol=1e-12)
+    assert 0.05 < tf.mean() < 50 and (no != nf).mean() < 0.9
+    # the tau walk: same landing point up to the mirror image, same escape decision
+    tau_in = rng.exponential(size=n) * np.median(tf)
+    a = oracle.raytrace_to_tau(full.config, *cols(p), *cols(k), xf, *cols(ic), tau_in)
+    b = oracle.raytrace_to_tau(octa.config, *cols(pf), *cols(kf), xf, *cols(io), tau_in)
+    clear = np.abs(tau_in / np.maximum(tf, 1e-300) - 1) > 1e-6  # not on the knife edge between landing and escaping
+    assert np.array_equal(a["inside"][clear], b["inside"][clear])
+    ins = clear & (a["inside"] == 1)
+    assert 0.2 < ins.mean() < 0.8
+    for key in "xyz":
+        assert np.allclose(np.abs(a[key][ins]), np.abs(b[key][ins]), rtol=0, atol=1e-9), key
+    assert np.all(b["x"][ins] >= go.xmin) and np.all(b["z"][ins] >= go.zmin)
+    assert np.allclose(a["xfreq"][ins], b["xfreq"][ins], rtol=0, atol=1e-9)
+    assert np.allclose(a["xfreq_ref"][clear & ~ins], b["xfreq_ref"][clear & ~ins], rtol=0, atol=1e-9)

@@ -42,6 +42,10 @@ WORKLOADS = {
                                nxfreq=201, nxim=129, nyim=129, distance=1e2),
     "sphere_peel_tau1e5": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0,
                                nxfreq=201, nxim=129, nyim=129, distance=1e2),
+    # par%xyz_symmetry: the octant of configs[1]'s sphere (101 cells with a straddling first cell = 201 across);
+    # peeling-off is not allowed on folded grids (setup.f90:198), so this is the transport loop alone
+    "sphere_octant_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xyz_symmetry=True, nx=101, ny=101, nz=101,
+                                 rmax=1.0, nxfreq=201),
     # small case for smoke-testing the bench itself
     "tiny": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=61, nxim=33, nyim=33),
 }

@@ -136,3 +136,25 @@ def test_xyz_symmetry_octant_unfolds_to_the_full_grid(nfull, noct):
     assert np.all(b["x"][ins] >= go.xmin) and np.all(b["z"][ins] >= go.zmin)
     assert np.allclose(a["xfreq"][ins], b["xfreq"][ins], rtol=0, atol=1e-9)
     assert np.allclose(a["xfreq_ref"][clear & ~ins], b["xfreq_ref"][clear & ~ins], rtol=0, atol=1e-9)
+
+
+def test_xyz_symmetry_run_is_statistically_the_full_run():
+    """Whole photon histories in the octant (folded source, reflections, |kz| in Jmu) against the full sphere."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from conftest import small_sphere
+    n = 30000
+    kw = dict(no_photons=n, taumax=100.0, nxim=0, nyim=0, use_stokes=False, save_Jmu=True, nmu=4, save_all_photons=False)
+    full = small_sphere(nx=29, ny=29, nz=29, **kw)
+    octa = small_sphere(nx=15, ny=15, nz=15, xyz_symmetry=True, iseed=1234, **kw)
+    assert octa.config.contents.par.save_peeloff == 0 and octa.config.contents.par.mu_min == 0.0
+    oracle.run(full, rng_mode=1)
+    oracle.run(octa, rng_mode=1)
+    assert octa.nscatt_gas / n == pytest.approx(full.nscatt_gas / n, rel=0.03)
+    a, b = octa.spectrum("Jout"), full.spectrum("Jout")
+    sel = a + b > 100
+    z = (a[sel] - b[sel]) / np.sqrt(a[sel] + b[sel])
+    assert sel.sum() >= 15 and (z ** 2).mean() < 1.8
+    jf, jo = full.spectrum("Jmu").sum(0), octa.spectrum("Jmu").sum(0)
+    assert np.allclose([jo[0] + jo[1], jo[2] + jo[3]], [jf[1] + jf[2], jf[0] + jf[3]], rtol=0.04)
+    assert octa.counters["n_photons_done"] == n

@@ -100,9 +100,11 @@ typedef struct lart_params {
   int32_t save_all_photons;
   int32_t xyz_symmetry;      /* one octant with mirror planes at the lower faces: binds the _xyzsym ray tracers
                                 (setup.f90:952-954; raytrace_car.f90:584-760, 1650-1949); no peel-off     */
-  int32_t xy_periodic;       /* with nx==ny==1 binds the _zonly ray tracers
-                                (setup.f90:957-965); other periodic modes are
-                                rejected with an error                      */
+  int32_t xy_symmetry;       /* mirror planes at the lower x and y faces, z open: the _xysym ray tracers
+                                (setup.f90:955-957; raytrace_car.f90:783-969, 1951-2250)                  */
+  int32_t xy_periodic;       /* nx==ny==1: the _zonly ray tracers; otherwise the _xyper ray tracers, photons
+                                wrap around in x and y (setup.f90:958-976; raytrace_car.f90:971-1136,
+                                2252-2517).  Shear-periodic boxes (par%Omega /= 0) are not on the GPU path */
   int32_t nobs;
 } lart_params;
 

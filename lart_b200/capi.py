@@ -58,7 +58,8 @@ class Params(C.Structure):
         ("use_stokes", C.c_int32), ("use_reduced_wgt", C.c_int32),
         ("save_Jin", C.c_int32), ("save_Jabs", C.c_int32), ("save_Jmu", C.c_int32),
         ("save_peeloff", C.c_int32), ("save_peeloff_2D", C.c_int32), ("save_peeloff_3D", C.c_int32),
-        ("save_direc0", C.c_int32), ("save_all_photons", C.c_int32), ("xyz_symmetry", C.c_int32), ("xy_periodic", C.c_int32),
+        ("save_direc0", C.c_int32), ("save_all_photons", C.c_int32), ("xyz_symmetry", C.c_int32), ("xy_symmetry", C.c_int32),
+        ("xy_periodic", C.c_int32),
         ("nobs", C.c_int32),
     ]
 

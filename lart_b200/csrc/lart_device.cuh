@@ -59,7 +59,9 @@ struct DevParams {
   int nsbx, nsby, nsbz;  // 32^3 super-bricks of the packed cell array per axis
   double dx, dy, dz;
   double xmin, ymin, zmin, xmax, ymax, zmax;
-  int sym, i0, j0, k0;  // par%xyz_symmetry: mirror planes at the lower faces; i0 = cell entered on reflection (grid_mod_car.f90:85-113)
+  // boundary variants of the ray tracers (setup.f90:952-976): bcxy / bcz = BC_* of the x,y axes and of the z axis;
+  // sym = par%xyz_symmetry (source fold, |kz| in Jmu); i0,j0,k0 = cell entered on reflection (grid_mod_car.f90:85-134)
+  int sym, bcxy, bcz, i0, j0, k0;
   double Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax;
   const double *xface, *yface, *zface;
   const Cell *cells;                                            // packed records (default walk)
@@ -275,25 +277,55 @@ struct Ray {
 // One straight-line path for both signs of k (no divergent branch around the divide): the special cases of
 // raytrace_car.f90:27-44 — already outside (k>0), sitting on the lower face (k<0) — become predicates.
 // -d/k == d/|k| bit for bit; the increment itself is computed lazily by ray_advance.
-LART_DEV bool axis_setup(double &k, double p, int &cell, int n, const double *face, double d, int &step, double &t,
-                         double &del, bool eq_test, bool sym = false, int c0 = 0) {
+LART_DEV bool axis_setup(double k, double p, int &cell, int n, const double *face, double d, int &step, double &t,
+                         double &del, bool eq_test) {
   const bool pos = k > 0.0, neg = k < 0.0;
   const double flo = __ldg(face + cell - 1);
   bool leave = pos && cell > n && (eq_test ? (flo == p) : (flo <= p));
   const bool onface = neg && flo == p;
-  const bool reflect = sym && onface && cell <= 1;  // mirror plane: enter cell c0 going up (:1696-1700)
-  leave = leave || (onface && cell <= 1 && !sym);
-  cell = reflect ? c0 : cell - ((onface && cell > 1) ? 1 : 0);
-  const bool fwd = pos || reflect;
-  const int fi = fwd ? min(cell, n) : cell - 1;  // the face ahead (clamped: the reference reads past the end there)
+  leave = leave || (onface && cell <= 1);
+  cell -= (onface && cell > 1) ? 1 : 0;
+  const int fi = pos ? min(cell, n) : cell - 1;  // the face ahead (clamped: the reference reads past the end there)
   const double f = __ldg(face + fi);
-  k = reflect ? -k : k;
   const double tt = DSUB(f, p) / k;
   const bool moving = pos || neg;
   t = moving ? tt : kHugest;
   del = moving ? -1.0 : kHugest;  // d/|k|, filled in at the first crossing of this axis
-  step = fwd ? 1 : (neg ? -1 : 0);
+  step = pos ? 1 : (neg ? -1 : 0);
   return leave;
+}
+
+// The same for the folded and periodic grids: a mirror plane at the lower face reflects the ray into cell c0
+// (raytrace_car.f90:1696-1700), a periodic axis wraps the start point to the far side (:1030-1033, :2293-2297; the
+// periodic to_edge variant still returns for a photon sitting on the upper face, :1020).  `moved` = k or p changed.
+enum { BC_OPEN = 0, BC_MIRROR = 1, BC_PERIODIC = 2 };
+LART_DEV bool axis_setup_bc(double &k, double &p, int &cell, int n, const double *face, int &step, double &t, double &del,
+                            bool is_tau, int bc, int c0, bool &moved) {
+  moved = false;
+  step = 0; t = kHugest; del = kHugest;
+  if (k > 0.0) {
+    if (cell > n) {
+      const double f = __ldg(face + cell - 1);
+      if (is_tau ? (f == p) : (f <= p)) {
+        if (bc == BC_PERIODIC && is_tau) { cell = 1; p = __ldg(face); moved = true; }
+        else return true;
+      }
+    }
+    step = 1;
+  } else if (k < 0.0) {
+    step = -1;
+    if (__ldg(face + cell - 1) == p) {
+      if (cell > 1) cell -= 1;
+      else if (bc == BC_MIRROR) { cell = c0; step = 1; k = -k; moved = true; }
+      else if (bc == BC_PERIODIC) { cell = n; p = __ldg(face + n); moved = true; }
+      else return true;
+    }
+  } else {
+    return false;
+  }
+  t = DSUB(__ldg(face + (step == 1 ? min(cell, n) : cell - 1)), p) / k;
+  del = -1.0;
+  return false;
 }
 
 // `here` (optional) = record of the start cell when the caller already holds it; it is used
@@ -303,11 +335,12 @@ LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z
   r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
   r.ic = ic; r.jc = jc; r.kc = kc;
   r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0; r.flip = 0;
-  if (P.sym) {  // raytrace_to_tau_car_xyzsym tests `== xp` (:1681), raytrace_to_edge_car_xyzsym `<= xp` (:613)
-    if (axis_setup(r.kx, x, r.ic, P.nx, P.xface, P.dx, r.istep, r.tx, r.delx, zonly_eq, true, P.i0)) return true;
-    if (axis_setup(r.ky, y, r.jc, P.ny, P.yface, P.dy, r.jstep, r.ty, r.dely, zonly_eq, true, P.j0)) return true;
-    if (axis_setup(r.kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, zonly_eq, true, P.k0)) return true;
-    r.flip = (r.kx != kx ? 1 : 0) | (r.ky != ky ? 2 : 0) | (r.kz != kz ? 4 : 0);
+  if (P.bcxy) {  // folded / periodic grids; their to_tau variants test `== xp` (:1681, :1993, :2293), to_edge `<= xp`
+    bool mx, my, mz;
+    if (axis_setup_bc(r.kx, r.x0, r.ic, P.nx, P.xface, r.istep, r.tx, r.delx, zonly_eq, P.bcxy, P.i0, mx)) return true;
+    if (axis_setup_bc(r.ky, r.y0, r.jc, P.ny, P.yface, r.jstep, r.ty, r.dely, zonly_eq, P.bcxy, P.j0, my)) return true;
+    if (axis_setup_bc(r.kz, r.z0, r.kc, P.nz, P.zface, r.kstep, r.tz, r.delz, zonly_eq, P.bcz, P.k0, mz)) return true;
+    r.flip = (mx ? 1 : 0) | (my ? 2 : 0) | (mz ? 4 : 0);
     load_cell(P, r.ic, r.jc, r.kc, r.cell);
     r.u1 = vdotk(r.cell, r.kx, r.ky, r.kz);
     return false;
@@ -332,9 +365,14 @@ LART_DEV void ray_resume(const DevParams &P, Ray &r, double x, double y, double 
                          double tx, double ty, double tz, double delx, double dely, double delz, double d, double tau,
                          double xfreq, double u1, int ic, int jc, int kc_flip) {
   const int kc = kc_flip & kCellMask, flip = kc_flip >> kFlipShift;  // see ray_save_state
-  if (flip & 1) kx = -kx;
-  if (flip & 2) ky = -ky;
-  if (flip & 4) kz = -kz;
+  if (P.bcxy == BC_PERIODIC) {  // the start point had been wrapped to the far side
+    if (flip & 1) x = __ldg(P.xface + (kx > 0.0 ? 0 : P.nx));
+    if (flip & 2) y = __ldg(P.yface + (ky > 0.0 ? 0 : P.ny));
+  } else {                      // reflected direction components
+    if (flip & 1) kx = -kx;
+    if (flip & 2) ky = -ky;
+    if (flip & 4) kz = -kz;
+  }
   r.flip = flip;
   r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
   r.tx = tx; r.ty = ty; r.tz = tz; r.delx = delx; r.dely = dely; r.delz = delz;
@@ -363,43 +401,52 @@ LART_DEV int ray_axis(const DevParams &P, const Ray &r) {
 
 // Move the index along `axis`; false when the ray left the grid.  On success loads
 // the new cell and shifts the frequency into its frame (:1586-1589 / :485-494).
+LART_DEV bool ray_leave_or_turn(int bc, int &cell, int &step, double &k, int n, int c0, int &flip, int bit) {
+  if (bc == BC_PERIODIC) { cell = cell < 1 ? n : 1; return false; }                                // :2383-2385
+  if (bc == BC_MIRROR && cell < 1) { cell = c0; step = 1; k = -k; flip ^= bit; return false; }  // :1791-1795
+  cell -= step;
+  return true;
+}
 LART_DEV bool ray_advance(const DevParams &P, Ray &r, int axis) {
   if (axis == 1) {
     r.ic += r.istep;
-    if (r.ic < 1 || r.ic > P.nx) {
-      if (!(P.sym && r.ic < 1)) { r.ic -= r.istep; return false; }
-      r.ic = P.i0; r.istep = 1; r.kx = -r.kx; r.flip ^= 1;  // reflected at the yz-plane (:1791-1795)
-    }
+    if ((r.ic < 1 || r.ic > P.nx) && ray_leave_or_turn(P.bcxy, r.ic, r.istep, r.kx, P.nx, P.i0, r.flip, 1)) return false;
     if (r.delx < 0.0) r.delx = P.dx / fabs(r.kx);
     r.tx = DADD(r.tx, r.delx);
   } else if (axis == 2) {
     r.jc += r.jstep;
-    if (r.jc < 1 || r.jc > P.ny) {
-      if (!(P.sym && r.jc < 1)) { r.jc -= r.jstep; return false; }
-      r.jc = P.j0; r.jstep = 1; r.ky = -r.ky; r.flip ^= 2;
-    }
+    if ((r.jc < 1 || r.jc > P.ny) && ray_leave_or_turn(P.bcxy, r.jc, r.jstep, r.ky, P.ny, P.j0, r.flip, 2)) return false;
     if (r.dely < 0.0) r.dely = P.dy / fabs(r.ky);
     r.ty = DADD(r.ty, r.dely);
   } else {
     r.kc += r.kstep;
-    if (r.kc < 1 || r.kc > P.nz) {
-      if (!(P.sym && r.kc < 1)) { r.kc -= r.kstep; return false; }
-      r.kc = P.k0; r.kstep = 1; r.kz = -r.kz; r.flip ^= 4;
-    }
+    if ((r.kc < 1 || r.kc > P.nz) && ray_leave_or_turn(P.bcz, r.kc, r.kstep, r.kz, P.nz, P.k0, r.flip, 4)) return false;
     if (r.delz < 0.0) r.delz = P.dz / fabs(r.kz);
     r.tz = DADD(r.tz, r.delz);
   }
   return true;
 }
-// xyz symmetry: end point of a walk of length r.d.  The reference advances along the ORIGINAL direction
-// and mirrors the point back into the octant (raytrace_car.f90:1934-1940).
-LART_DEV void ray_endpoint_sym(const DevParams &P, const Ray &r, double &xp, double &yp, double &zp) {
-  xp = DADD(r.x0, DMUL(r.d, (r.flip & 1) ? -r.kx : r.kx));
-  yp = DADD(r.y0, DMUL(r.d, (r.flip & 2) ? -r.ky : r.ky));
-  zp = DADD(r.z0, DMUL(r.d, (r.flip & 4) ? -r.kz : r.kz));
-  if (xp < P.xmin) xp = -xp;
-  if (yp < P.ymin) yp = -yp;
-  if (zp < P.zmin) zp = -zp;
+// End point of a walk of length r.d on a folded or periodic grid.  Mirror planes: the reference advances along the
+// ORIGINAL direction and mirrors the point back (raytrace_car.f90:1934-1940, :2236-2240); periodic: it is folded back
+// into the box (:2506-2508).
+LART_DEV void ray_endpoint_bc(const DevParams &P, const Ray &r, double &xp, double &yp, double &zp) {
+  if (P.bcxy == BC_MIRROR) {
+    xp = DADD(r.x0, DMUL(r.d, (r.flip & 1) ? -r.kx : r.kx));
+    yp = DADD(r.y0, DMUL(r.d, (r.flip & 2) ? -r.ky : r.ky));
+    zp = DADD(r.z0, DMUL(r.d, (r.flip & 4) ? -r.kz : r.kz));
+    if (xp < P.xmin) xp = -xp;
+    if (yp < P.ymin) yp = -yp;
+    if (P.bcz == BC_MIRROR && zp < P.zmin) zp = -zp;
+  } else {
+    xp = DADD(r.x0, DMUL(r.d, r.kx));
+    yp = DADD(r.y0, DMUL(r.d, r.ky));
+    zp = DADD(r.z0, DMUL(r.d, r.kz));
+  }
+}
+LART_DEV void fold_periodic(const DevParams &P, double &xp, double &yp) {
+  const double xrange = DSUB(P.xmax, P.xmin), yrange = DSUB(P.ymax, P.ymin);
+  xp = DSUB(xp, DMUL(floor(DSUB(xp, P.xmin) / xrange), xrange));
+  yp = DSUB(yp, DMUL(floor(DSUB(yp, P.ymin) / yrange), yrange));
 }
 LART_DEV void ray_shift(const DevParams &P, Ray &r) {
   double Dold = r.cell.Dfreq;
@@ -434,7 +481,11 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
   r.d = tn;
   if (r.tau >= tau_in) {  // :1513-1524
     if (kap > 0.0) r.d = DSUB(r.d, DSUB(r.tau, tau_in) / kap);
-    if (P.sym) { ray_endpoint_sym(P, r, xp, yp, zp); return 1; }
+    if (P.bcxy) {
+      ray_endpoint_bc(P, r, xp, yp, zp);
+      if (P.bcxy == BC_PERIODIC) fold_periodic(P, xp, yp);
+      return 1;
+    }
     xp = DADD(r.x0, DMUL(r.d, r.kx));
     yp = DADD(r.y0, DMUL(r.d, r.ky));
     zp = DADD(r.z0, DMUL(r.d, r.kz));

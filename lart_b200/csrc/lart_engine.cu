@@ -197,9 +197,11 @@ __device__ __forceinline__ int finish_escape(const DevParams &P, Photon &ph, con
   ph.xfreq = DADD(r.xfreq, r.u1);
   ph.xfreq_ref = DMUL(ph.xfreq, r.cell.Dfreq / P.Dfreq_ref);
   ph.x = r.x0; ph.y = r.y0; ph.z = r.z0;
-  if (P.sym) {  // raytrace_car.f90:1934-1943: the end point and the reflected direction are stored even on escape
-    ray_endpoint_sym(P, r, ph.x, ph.y, ph.z);
+  if (P.bcxy == BC_MIRROR) {  // raytrace_car.f90:1934-1943: the end point and the reflected direction are stored even on escape
+    ray_endpoint_bc(P, r, ph.x, ph.y, ph.z);
     ph.kx = r.kx; ph.ky = r.ky; ph.kz = r.kz;
+  } else if (P.bcxy == BC_PERIODIC) {  // :2506-2508
+    fold_periodic(P, ph.x, ph.y);
   }
   if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
   ph.kc = r.kc;
@@ -222,7 +224,7 @@ __device__ __forceinline__ int walk_tau(const DevParams &P, const double *vtab, 
     int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
     if (st == 1) {
       ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
-      if (P.sym) adopt_direction(r, ph);
+      if (P.bcxy == BC_MIRROR) adopt_direction(r, ph);
       if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
       ph.kc = r.kc;
       cs = r.cell;
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
           ph.kc = r.kc;
           ph.flags |= PH_SCATTER;
           cnt.cellsteps += r.nsteps;
-          if (P.sym && r.flip) { adopt_direction(r, ph); store_direction(pl, slot, ph); }
+          if (P.bcxy == BC_MIRROR && r.flip) { adopt_direction(r, ph); store_direction(pl, slot, ph); }
           store_trace_part(pl, slot, ph);
           pl.ndraw[slot] = rng.nblk;
           nrng += rng.nrng;
@@ -755,7 +757,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ D
         PeelCont &c = cout[at];
         ray_store(&c.pr, pr);
         c.tx = r.tx; c.ty = r.ty; c.tz = r.tz; c.delx = r.delx; c.dely = r.dely; c.delz = r.delz;
-        c.d = r.d; c.tau = r.tau; c.xfreq = r.xfreq; c.u1 = r.u1; c.ic = r.ic; c.jc = r.jc; c.kc = r.kc;
+        c.d = r.d; c.tau = r.tau; c.xfreq = r.xfreq; c.u1 = r.u1; c.ic = r.ic; c.jc = r.jc; c.kc = r.kc | (r.flip << kFlipShift);
         cnt.cellsteps += r.nsteps;
         have = false;
       } else {
@@ -1080,19 +1082,19 @@ int validate(const lart_config *c) {
   if (!g.xface || !g.yface || !g.zface || !g.rhokap || !g.voigt_a || !g.Dfreq || !g.vfx || !g.vfy || !g.vfz)
     return fail("lart_gpu_create: NULL grid array");
   if (c->line.line_type != 1) return fail("lart_gpu_create: only line_type 1 (Ly-alpha singlet) is on the GPU path");
-  if (p.xy_periodic && !(g.nx == 1 && g.ny == 1))
-    return fail("lart_gpu_create: xy_periodic is supported only for the nx=ny=1 slab (setup.f90:957-965)");
   if (p.DGR > 0.0 && !g.rhokapD) return fail("lart_gpu_create: DGR > 0 but rhokapD is NULL");
   if (p.DGR > 0.0 && p.use_stokes && c->scatt_mat.nPDF < 2) return fail("lart_gpu_create: dust + Stokes needs scatt_mat");
   if (p.nobs < 0 || p.nobs > LART_MAX_OBSERVERS) return fail("lart_gpu_create: nobs out of range");
   if (p.save_peeloff && p.nobs > 0 && !c->observers) return fail("lart_gpu_create: observers is NULL");
   if (p.save_Jmu && (p.nmu < 1 || !(p.dmu > 0.0))) return fail("lart_gpu_create: save_Jmu needs nmu >= 1 and dmu > 0");
   if (!(g.dxfreq > 0.0)) return fail("lart_gpu_create: dxfreq must be > 0");
-  if (p.xyz_symmetry) {  // setup.f90:167, 198-206; grid_mod_car.f90:85-113
-    if (p.xy_periodic || g.nx < 2 || g.ny < 2 || g.nz < 2) return fail("lart_gpu_create: xyz_symmetry needs a 3-D, non-periodic grid");
-    if (p.save_peeloff) return fail("lart_gpu_create: peeling-off is not allowed with xyz_symmetry (setup.f90:198)");
-    if (g.i0 < 1 || g.i0 > 2 || g.j0 < 1 || g.j0 > 2 || g.k0 < 1 || g.k0 > 2) return fail("lart_gpu_create: xyz_symmetry needs grid.i0/j0/k0 in {1,2}");
-    if (g.nz >= (1 << kFlipShift)) return fail("lart_gpu_create: nz too large");
+  if (g.nz >= (1 << kFlipShift)) return fail("lart_gpu_create: nz too large");
+  if (p.xyz_symmetry || p.xy_symmetry) {  // setup.f90:167, 198-206, 952-957; grid_mod_car.f90:85-134
+    if (p.xy_periodic || g.nx < 2 || g.ny < 2 || (p.xyz_symmetry && g.nz < 2))
+      return fail("lart_gpu_create: xyz_symmetry / xy_symmetry need a 3-D, non-periodic grid");
+    if (p.xyz_symmetry && p.save_peeloff) return fail("lart_gpu_create: peeling-off is not allowed with xyz_symmetry (setup.f90:198)");
+    if (g.i0 < 1 || g.i0 > 2 || g.j0 < 1 || g.j0 > 2 || (p.xyz_symmetry && (g.k0 < 1 || g.k0 > 2)))
+      return fail("lart_gpu_create: folded grids need grid.i0/j0(/k0) in {1,2} (grid_mod_car.f90:85-134)");
   }
   return 0;
 }
@@ -1150,8 +1152,12 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   P.soa = (cfg->flags & LART_FLAG_SOA_GRID) ? 1 : 0;
   P.warp_agg = (cfg->flags & LART_FLAG_NO_WARP_AGG) ? 0 : 1;
   P.flags_serial_vz = (cfg->flags & LART_FLAG_SERIAL_REJECTION) ? 1 : 0;
+  // which ray tracers the reference would bind (setup.f90:952-976)
+  const bool zonly_grid = p.xy_periodic && g.nx == 1 && g.ny == 1;
   P.sym = p.xyz_symmetry ? 1 : 0; P.i0 = g.i0; P.j0 = g.j0; P.k0 = g.k0;
-  P.local_steps = ((cfg->flags & LART_FLAG_LOCAL_STEPS) && !P.sym) ? 1 : 0;  // the in-stage cell step knows no mirror planes
+  P.bcxy = P.sym ? BC_MIRROR : (p.xy_symmetry ? BC_MIRROR : ((p.xy_periodic && !zonly_grid) ? BC_PERIODIC : BC_OPEN));
+  P.bcz = P.sym ? BC_MIRROR : BC_OPEN;
+  P.local_steps = ((cfg->flags & LART_FLAG_LOCAL_STEPS) && !P.bcxy) ? 1 : 0;  // the in-stage cell step knows no mirror planes or wrap-around
   P.nsbx = (g.nx + 31) / 32; P.nsby = (g.ny + 31) / 32; P.nsbz = (g.nz + 31) / 32;
   if (!P.soa) {
     Cell *cells = nullptr;
@@ -1900,7 +1906,7 @@ int lart_gpu_sightline_tau(lart_gpu_handle h, double cross0, lart_sightline_out 
   if (!h || !out) return fail("lart_gpu_sightline_tau: NULL argument");
   if (h->obs_host.empty()) return fail("lart_gpu_sightline_tau: the handle has no observers (par%save_peeloff, par%nobs)");
   if (h->P.zonly) return fail("lart_gpu_sightline_tau: not defined for the xy-periodic slab");
-  if (h->P.sym) return fail("lart_gpu_sightline_tau: not defined for an xyz_symmetry octant grid");
+  if (h->P.bcxy) return fail("lart_gpu_sightline_tau: not defined for folded or periodic grids");
   if (!(cross0 > 0.0)) return fail("lart_gpu_sightline_tau: cross0 must be > 0");
   CUDA_OK(cudaSetDevice(h->device));
   const DevParams &P = h->P;

@@ -297,8 +297,10 @@ int derive(lart_host_model *m) {
   if (p.temperature0 <= 0.0) p.temperature0 = p.temperature;       // :127
   if (p.temperature <= 0.0 && p.bturb <= 0.0) { g_err = "par%temperature must be > 0 K (or set par%bturb > 0)"; return 1; }
   if (p.nx == 1 || p.ny == 1 || p.nz == 1) p.xyz_symmetry = false;  // :167
-  if (p.xy_symmetry || p.z_symmetry) { g_err = "xy/z symmetry-folded grids stay with the Fortran host (xyz_symmetry is supported)"; return 1; }
-  if (p.xyz_symmetry && p.xy_periodic) { g_err = "xyz_symmetry and xy_periodic exclude each other"; return 1; }
+  if (p.z_symmetry) { g_err = "z_symmetry grids stay with the Fortran host (xyz_symmetry and xy_symmetry are supported)"; return 1; }
+  if (p.xyz_symmetry) p.xy_symmetry = false;  // setup.f90:952-957: the xyz variant wins
+  if ((p.xyz_symmetry || p.xy_symmetry) && p.xy_periodic) { g_err = "symmetry-folded and xy_periodic grids exclude each other"; return 1; }
+  if (p.xy_symmetry && (p.nx == 1 || p.ny == 1)) { g_err = "xy_symmetry needs nx, ny > 1"; return 1; }
   if (!(p.save_peeloff_2D || p.save_peeloff_3D)) p.save_peeloff = false;  // :188
   if (p.nxim > 0 && p.nyim > 0) p.save_peeloff = true;                    // :189
   if (p.save_peeloff && p.xyz_symmetry) p.save_peeloff = false;  // :191-199 peeling-off is not allowed with xyz_symmetry
@@ -321,13 +323,13 @@ int derive(lart_host_model *m) {
       double r0 = -1.0;
       for (double v : {p.rmax, p.xmax, p.ymax, p.zmax}) if (v > 0.0) r0 = std::max(r0, v);
       if (r0 > 0.0) { p.rmax = r0; p.xmax = r0; p.ymax = r0; p.zmax = r0; }
-      p.nx = std::max({p.nx, p.ny, p.nz}); p.ny = p.nx; p.nz = p.nx;
+      if (!p.xy_symmetry) { p.nx = std::max({p.nx, p.ny, p.nz}); p.ny = p.nx; p.nz = p.nx; }
     }
   } else if (p.geometry == "cylinder") {
     double r0 = -1.0;
     for (double v : {p.rmax, p.xmax, p.ymax}) if (v > 0.0) r0 = std::max(r0, v);
     if (r0 > 0.0) { p.rmax = r0; p.xmax = r0; p.ymax = r0; }
-    p.nx = std::max(p.nx, p.ny); p.ny = p.nx;
+    if (!p.xy_symmetry) { p.nx = std::max(p.nx, p.ny); p.ny = p.nx; }
   } else {
     p.rmax = -1.0;
   }
@@ -349,7 +351,6 @@ int derive(lart_host_model *m) {
     p.DGR = 0.0;
   }
   if (p.DGR == 0.0) p.save_Jabs = false;
-  if (p.xy_periodic && !(p.nx == 1 && p.ny == 1)) { g_err = "xy_periodic with nx,ny > 1 stays with the Fortran host (only the nx=ny=1 slab is on the GPU path)"; return 1; }
   if (p.source_geometry != "point" && p.source_geometry != "uniform" && p.source_geometry != "uniform_sphere" && p.source_geometry != "sphere") {
     g_err = "source_geometry '" + p.source_geometry + "' stays with the Fortran host"; return 1;
   }
@@ -369,12 +370,15 @@ int grid_create(lart_host_model *m) {
   // :92-118 (xyz symmetry: one octant, mirror planes at the lower faces) / :168-176 (no symmetry)
   double dx, dy, dz, xmin, ymin, zmin;
   int i0 = 0, j0 = 0, k0 = 0;
+  auto axis = [](int n, double vmax, double &d, double &vmin, int &c0) {
+    if ((n / 2) * 2 == n) { d = vmax / n; vmin = 0.0; c0 = 1; }
+    else { d = vmax / (n - 0.5); vmin = -d / 2.0; c0 = 2; }
+  };
   if (p.xyz_symmetry) {
-    auto axis = [](int n, double vmax, double &d, double &vmin, int &c0) {
-      if ((n / 2) * 2 == n) { d = vmax / n; vmin = 0.0; c0 = 1; }
-      else { d = vmax / (n - 0.5); vmin = -d / 2.0; c0 = 2; }
-    };
     axis(nx, p.xmax, dx, xmin, i0); axis(ny, p.ymax, dy, ymin, j0); axis(nz, p.zmax, dz, zmin, k0);
+  } else if (p.xy_symmetry) {  // :113-134 — a quadrant in x,y; the full height in z
+    axis(nx, p.xmax, dx, xmin, i0); axis(ny, p.ymax, dy, ymin, j0);
+    dz = 2.0 * p.zmax / nz; zmin = -p.zmax; k0 = 0;
   } else {
     dx = 2.0 * p.xmax / nx; dy = 2.0 * p.ymax / ny; dz = 2.0 * p.zmax / nz;
     xmin = -p.xmax; ymin = -p.ymax; zmin = -p.zmax;
@@ -437,9 +441,9 @@ int grid_create(lart_host_model *m) {
   else if (p.rmax > 0.0) opac_length = p.rmax;
   else if (p.zmax == -zmin) opac_length = (p.zmax - zmin) / 2.0;
   else opac_length = p.zmax - zmin;
-  const bool sym = p.xyz_symmetry;
+  const bool sym = p.xyz_symmetry, symxy = p.xyz_symmetry || p.xy_symmetry;
   const bool zodd = (nz / 2) * 2 != nz;
-  const int nxcen = sym ? 1 : (nx + 1) / 2, nycen = sym ? 1 : (ny + 1) / 2;  // :505-515 (1-based)
+  const int nxcen = symxy ? 1 : (nx + 1) / 2, nycen = symxy ? 1 : (ny + 1) / 2;  // :505-515 (1-based)
   // voigt(0,a): |x|<1 branch of voigt_seon2 at x=0 is h0(1)+a*(h1(1)+a*h2(1))
   // (voigt_mod.f90:691-700; h0(1)=1, h1(1)=-1.1283791671, h2(1)=1).
   auto voigt0 = [](double a) { return 1.0 + a * (-1.1283791671e+00 + a * 1.0); };
@@ -450,10 +454,10 @@ int grid_create(lart_host_model *m) {
       size_t c = at(i, j, k);
       if (!(m->rhokap[c] > 0.0)) continue;
       double nadd = 1.0;
-      if (sym) {
+      if (symxy) {
         if (i == 0 && (nx / 2) * 2 != nx) nadd /= 2.0;
         if (j == 0 && (ny / 2) * 2 != ny) nadd /= 2.0;
-        if (k == 0 && zodd) nadd /= 2.0;
+        if (sym && k == 0 && zodd) nadd /= 2.0;
       }
       s += weight(c) * nadd; nopac += nadd;
     }
@@ -803,7 +807,7 @@ int lart_host_setup(lart_host_model *m) {
   q.use_stokes = p.use_stokes; q.use_reduced_wgt = p.use_reduced_wgt;
   q.save_Jin = p.save_Jin; q.save_Jabs = p.save_Jabs; q.save_Jmu = p.save_Jmu;
   q.save_peeloff = p.save_peeloff; q.save_peeloff_2D = p.save_peeloff_2D; q.save_peeloff_3D = p.save_peeloff_3D; q.save_direc0 = p.save_direc0;
-  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.nobs = p.nobs;
+  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.xy_symmetry = p.xy_symmetry; q.nobs = p.nobs;
   const Line &ln = m->line;
   c.line.line_type = ln.line_type; c.line.E1 = ln.E1; c.line.E2 = ln.E2; c.line.E3 = ln.E3;
   c.line.g_recoil0 = ln.g_recoil0; c.line.DnuHK_Hz = ln.DnuHK_Hz;

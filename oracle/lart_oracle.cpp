@@ -245,6 +245,7 @@ struct World {
   const lart_observer *obs;
   bool zonly;
   bool sym = false;  // par%xyz_symmetry: mirror planes at the lower faces (raytrace_car.f90:584-760, 1650-1949)
+  int bcxy = 0, bcz = 0;  // BC_* of the x/y axes and of the z axis (setup.f90:952-976)
   inline size_t idx(int i, int j, int k) const {
     return static_cast<size_t>(i - 1) + static_cast<size_t>(g->nx) * (static_cast<size_t>(j - 1) + static_cast<size_t>(g->ny) * static_cast<size_t>(k - 1));
   }
@@ -293,12 +294,19 @@ struct Trav {
   double tx, ty, tz, delx, dely, delz;
 };
 
-inline bool axis_setup(double &k, double p, int &cell, int n, const double *face, double d, int &step, double &t, double &del, bool eq_test,
-                       bool sym = false, int c0 = 0) {
+// Boundary of one axis: open (the photon leaves), mirror plane at the lower face (xyz/xy symmetry), periodic (xy_periodic).
+enum { BC_OPEN = 0, BC_MIRROR = 1, BC_PERIODIC = 2 };
+
+inline bool axis_setup(double &k, double &p, int &cell, int n, const double *face, double d, int &step, double &t, double &del,
+                       bool eq_test, int bc = BC_OPEN, int c0 = 0, bool is_tau = false) {
   if (k > 0.0) {
     if (cell > n) {
       double f = face[cell - 1];
-      if (eq_test ? (f == p) : (f <= p)) return true;
+      if (eq_test ? (f == p) : (f <= p)) {
+        // the periodic to_tau variant re-enters at the first face (:2293-2297); its to_edge variant returns (:1020)
+        if (bc == BC_PERIODIC && is_tau) { cell = 1; p = face[0]; }
+        else return true;
+      }
     }
     step = 1;
     t = (face[cell] - p) / k;
@@ -308,7 +316,8 @@ inline bool axis_setup(double &k, double p, int &cell, int n, const double *face
     del = -d / k;
     if (face[cell - 1] == p) {
       if (cell > 1) cell -= 1;
-      else if (sym) { cell = c0; step = 1; k = std::fabs(k); }  // reflected at the mirror plane (:1696-1700)
+      else if (bc == BC_MIRROR) { cell = c0; step = 1; k = std::fabs(k); }  // reflected at the mirror plane (:1696-1700)
+      else if (bc == BC_PERIODIC) { cell = n; p = face[n]; }                // wraps to the far side (:1030-1033)
       else return true;
     }
     t = (step == 1) ? (face[cell] - p) / k : (face[cell - 1] - p) / k;
@@ -320,7 +329,7 @@ inline bool axis_setup(double &k, double p, int &cell, int n, const double *face
   return false;
 }
 
-inline bool setup_traversal(const World &w, double xp, double yp, double zp, double &kx, double &ky, double &kz,
+inline bool setup_traversal(const World &w, double &xp, double &yp, double &zp, double &kx, double &ky, double &kz,
                             int &ic, int &jc, int &kc, Trav &t, bool is_tau) {
   const lart_grid &g = *w.g;
   if (w.zonly) {
@@ -330,23 +339,22 @@ inline bool setup_traversal(const World &w, double xp, double yp, double zp, dou
     t.delx = t.dely = kHugest;
     return axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, is_tau);
   }
-  // xyz symmetry: the to_tau variant tests `==` (:1681), the to_edge variant `<=` (:613)
-  const bool eq = w.sym && is_tau;
-  if (axis_setup(kx, xp, ic, g.nx, g.xface, g.dx, t.istep, t.tx, t.delx, eq, w.sym, g.i0)) return true;
-  if (axis_setup(ky, yp, jc, g.ny, g.yface, g.dy, t.jstep, t.ty, t.dely, eq, w.sym, g.j0)) return true;
-  if (axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, eq, w.sym, g.k0)) return true;
+  // the to_tau variants of the folded / periodic grids test `==` (:1681, :1993, :2293), all to_edge variants `<=`
+  const bool eq = (w.bcxy != BC_OPEN || w.bcz != BC_OPEN) && is_tau;
+  if (axis_setup(kx, xp, ic, g.nx, g.xface, g.dx, t.istep, t.tx, t.delx, eq, w.bcxy, g.i0, is_tau)) return true;
+  if (axis_setup(ky, yp, jc, g.ny, g.yface, g.dy, t.jstep, t.ty, t.dely, eq, w.bcxy, g.j0, is_tau)) return true;
+  if (axis_setup(kz, zp, kc, g.nz, g.zface, g.dz, t.kstep, t.tz, t.delz, eq, w.bcz, g.k0, is_tau)) return true;
   return false;
 }
 
-// index step along one axis; with xyz symmetry a photon that would leave through a lower face is reflected
-// (:1791-1799).  Returns false when the photon leaves the grid.
-inline bool advance_axis(const World &w, int &cell, int &step, double &k, int n, int c0) {
+// index step along one axis: reflected at a mirror plane (:1791-1799), wrapped around a periodic box (:2383-2385).
+// Returns false when the photon leaves the grid.
+inline bool advance_axis(int bc, int &cell, int &step, double &k, int n, int c0) {
   cell += step;
-  if (cell < 1) {
-    if (!w.sym) return false;
-    cell = c0; step = 1; k = -k;
-  } else if (cell > n) return false;
-  return true;
+  if (cell >= 1 && cell <= n) return true;
+  if (bc == BC_PERIODIC) { cell = (cell < 1) ? n : 1; return true; }
+  if (bc == BC_MIRROR && cell < 1) { cell = c0; step = 1; k = -k; return true; }
+  return false;
 }
 
 // minloc([tx,ty,tz],dim=1) — first minimum wins (raytrace_car.f90:476,1506)
@@ -384,17 +392,17 @@ double raytrace_to_edge(const World &w, const Photon &p0, Counters *cnt, int *ns
     if (m == 1) {
       tau += (t.tx - d) * rhokap;
       d = t.tx;
-      if (!advance_axis(w, ic, t.istep, kx, g.nx, g.i0)) break;
+      if (!advance_axis(w.bcxy, ic, t.istep, kx, g.nx, g.i0)) break;
       t.tx += t.delx;
     } else if (m == 2) {
       tau += (t.ty - d) * rhokap;
       d = t.ty;
-      if (!advance_axis(w, jc, t.jstep, ky, g.ny, g.j0)) break;
+      if (!advance_axis(w.bcxy, jc, t.jstep, ky, g.ny, g.j0)) break;
       t.ty += t.dely;
     } else {
       tau += (t.tz - d) * rhokap;
       d = t.tz;
-      if (!advance_axis(w, kc, t.kstep, kz, g.nz, g.k0)) break;
+      if (!advance_axis(w.bcz, kc, t.kstep, kz, g.nz, g.k0)) break;
       t.tz += t.delz;
     }
     if (tau >= kTauHuge) break;
@@ -450,20 +458,20 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
         double d_overshoot = (tau - tau_in) / rhokap;
         d = d - d_overshoot;
       }
-      // the new position uses the ORIGINAL direction even after a reflection; it is mirrored back below (:1936-1941)
+      // the ORIGINAL direction even after a reflection; the point is mirrored back below (:1936-1941)
       xp = xp + d * ph.kx;
       yp = yp + d * ph.ky;
       zp = zp + d * ph.kz;
       break;
     }
     if (m == 1) {
-      if (!advance_axis(w, ic, t.istep, kx, g.nx, g.i0)) { ph.inside = false; break; }
+      if (!advance_axis(w.bcxy, ic, t.istep, kx, g.nx, g.i0)) { ph.inside = false; break; }
       t.tx += t.delx;
     } else if (m == 2) {
-      if (!advance_axis(w, jc, t.jstep, ky, g.ny, g.j0)) { ph.inside = false; break; }
+      if (!advance_axis(w.bcxy, jc, t.jstep, ky, g.ny, g.j0)) { ph.inside = false; break; }
       t.ty += t.dely;
     } else {
-      if (!advance_axis(w, kc, t.kstep, kz, g.nz, g.k0)) { ph.inside = false; break; }
+      if (!advance_axis(w.bcz, kc, t.kstep, kz, g.nz, g.k0)) { ph.inside = false; break; }
       t.tz += t.delz;
     }
     double u2 = w.vdotk(ic, jc, kc, kx, ky, kz);
@@ -485,14 +493,18 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
       }
     }
   }
-  if (w.sym) {  // :1936-1947 (d is the whole path when the photon left the grid)
+  if (w.bcxy == BC_MIRROR) {  // :1936-1947, :2236-2245 (d is the whole path when the photon left the grid)
     if (!ph.inside) { xp = ph.x + d * ph.kx; yp = ph.y + d * ph.ky; zp = ph.z + d * ph.kz; }
     if (xp < g.xmin) xp = -xp;
     if (yp < g.ymin) yp = -yp;
-    if (zp < g.zmin) zp = -zp;
+    if (w.bcz == BC_MIRROR && zp < g.zmin) zp = -zp;
+  } else if (w.bcxy == BC_PERIODIC) {  // folded back into the box (:2506-2508)
+    const double xrange = g.xmax - g.xmin, yrange = g.ymax - g.ymin;
+    xp = xp - std::floor((xp - g.xmin) / xrange) * xrange;
+    yp = yp - std::floor((yp - g.ymin) / yrange) * yrange;
   }
   ph.x = xp; ph.y = yp; ph.z = zp;
-  if (w.sym) { ph.kx = kx; ph.ky = ky; ph.kz = kz; }
+  if (w.bcxy == BC_MIRROR) { ph.kx = kx; ph.ky = ky; ph.kz = kz; }
   if (!w.zonly) { ph.icell = ic; ph.jcell = jc; }
   ph.kcell = kc;
   if (cnt) cnt->n_cellsteps += nsteps;
@@ -1400,6 +1412,9 @@ World make_world(const lart_config *cfg) {
   w.obs = cfg->observers;
   w.zonly = cfg->par.xy_periodic && cfg->grid.nx == 1 && cfg->grid.ny == 1;  // setup.f90:957-965
   w.sym = cfg->par.xyz_symmetry != 0;                                         // setup.f90:952-954
+  if (w.sym) { w.bcxy = 1; w.bcz = 1; }
+  else if (cfg->par.xy_symmetry) w.bcxy = 1;                                  // :955-957
+  else if (cfg->par.xy_periodic && !w.zonly) w.bcxy = 2;                      // :966-975 (no shear)
   return w;
 }
 
@@ -1518,7 +1533,6 @@ int oracle_mt64_words(int64_t seed, int64_t n, uint64_t *out) {
 int oracle_run(const lart_config *cfg, int32_t rng_mode, int32_t nthreads, int64_t first_id, int64_t count, int64_t stride,
                int64_t max_events_per_photon, lart_tallies *out) {
   if (cfg->line.line_type != 1) { g_err = "oracle_run: only line_type 1"; return 1; }
-  if (cfg->par.xy_periodic && !(cfg->grid.nx == 1 && cfg->grid.ny == 1)) { g_err = "oracle_run: xy_periodic needs nx=ny=1"; return 1; }
   if (cfg->par.nobs > 0 && (!out->obs || !cfg->observers)) { g_err = "oracle_run: observers/outputs missing"; return 1; }
   World w = make_world(cfg);
   if (nthreads < 1) nthreads = 1;

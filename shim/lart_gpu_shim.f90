@@ -47,7 +47,7 @@ module lart_gpu_shim
      integer(c_int32_t) :: nmu, spectral_type, source_geometry, comoving_source, recoil
      integer(c_int32_t) :: core_skip, core_skip_global, use_stokes, use_reduced_wgt
      integer(c_int32_t) :: save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D
-     integer(c_int32_t) :: save_direc0, save_all_photons, xyz_symmetry, xy_periodic, nobs
+     integer(c_int32_t) :: save_direc0, save_all_photons, xyz_symmetry, xy_symmetry, xy_periodic, nobs
   end type
   type, bind(C) :: c_lart_line
      integer(c_int32_t) :: line_type, pad_
@@ -143,6 +143,7 @@ contains
 
   !--- one more implementation of run_sim (src/define.f90:832-838) -------------
   subroutine run_gpu(grid)
+    use mpi
     type(grid_type), intent(inout) :: grid
     type(c_lart_config),  target :: cfg
     type(c_lart_tallies), target :: tal
@@ -151,6 +152,13 @@ contains
     type(c_ptr) :: handle
     integer(c_int64_t) :: first_id, count, stride
     integer :: k, ngpu_per_node
+
+    !--- inputs that bind other ray tracers or run loops than the ones behind lart_gpu_run (src/setup.f90:905-990)
+    if (par%use_amr_grid .or. par%use_clump_medium .or. par%z_symmetry .or. par%Omega /= 0.0_wp .or. par%nside > 0 .or. &
+        trim(par%geometry) == 'plane_atmosphere' .or. trim(par%geometry) == 'spherical_atmosphere') then
+       write(*,'(a)') 'ERROR (lart_gpu): AMR, clumps, z_symmetry, shear, atmospheres and HEALPix observers are not on the GPU path.'
+       call MPI_ABORT(MPI_COMM_WORLD, 1, k)
+    endif
 
     !--- grid_type scalars and arrays (src/define.f90:117-148); arrays stay Fortran-owned
     cfg%grid%nx = grid%nx; cfg%grid%ny = grid%ny; cfg%grid%nz = grid%nz; cfg%grid%nxfreq = grid%nxfreq
@@ -197,7 +205,7 @@ contains
     cfg%par%save_peeloff = l2i(par%save_peeloff); cfg%par%save_peeloff_2D = l2i(par%save_peeloff_2D)
     cfg%par%save_peeloff_3D = l2i(par%save_peeloff_3D); cfg%par%save_direc0 = l2i(par%save_direc0)
     cfg%par%save_all_photons = l2i(par%save_all_photons); cfg%par%xy_periodic = l2i(par%xy_periodic)
-    cfg%par%xyz_symmetry = l2i(par%xyz_symmetry)
+    cfg%par%xyz_symmetry = l2i(par%xyz_symmetry); cfg%par%xy_symmetry = l2i(par%xy_symmetry)
     cfg%par%nobs = merge(par%nobs, 0, par%save_peeloff)
 
     !--- line_type (src/define.f90:639-656)

@@ -84,6 +84,11 @@ CASES = {
     "xyz_symmetry_hubble_uniform_sphere": dict(xyz_symmetry=True, nx=16, ny=15, nz=12, nxim=0, nyim=0, use_stokes=False,
                                                velocity_type="hubble", Vexp=50.0, source_geometry="uniform_sphere",
                                                taumax=30.0),
+    # par%xy_symmetry: a quadrant in x,y (peeling-off stays allowed upstream; the observer sits on the z axis)
+    "xy_symmetry_peel": dict(xy_symmetry=True, nx=15, ny=16, nz=31, save_Jmu=True, nmu=4),
+    # par%xy_periodic with nx, ny > 1: photons wrap around in x and y
+    "xy_periodic_box_peel": dict(xy_periodic=True, geometry="rectangle", rmax=-999.0, nx=5, ny=4, nz=41, xmax=0.5, ymax=0.4,
+                                 zmax=1.0, taumax=50.0, xs_point=0.2, ys_point=-0.1),
 }
 
 
@@ -165,6 +170,24 @@ def test_xyz_symmetry_parked_walks_keep_their_reflections(kw):
     oracle.run(mo, rng_mode=1)
     same = histories_equal(mg, mo, geom_rtol=1e-6)
     tallies_close(mg, mo, same.mean())
+
+
+def test_xy_periodic_parked_walks_and_slab_equivalence():
+    """A uniform periodic box is the infinite slab: same photon histories whatever the budget, and the spectrum of the
+    one-column (z-only) slab."""
+    par = dict(xy_periodic=True, geometry="rectangle", rmax=-999.0, nx=3, ny=4, nz=101, xmax=0.05, ymax=0.04, zmax=1.0,
+               taumax=1e3, nxim=0, nyim=0, use_stokes=False, save_all_photons=True, no_photons=1500)
+    mg, mo = small_sphere(**par), small_sphere(**par)
+    run_gpu(mg, pool_slots=512, quantum=5, ray_budget=2, streams=3)
+    oracle.run(mo, rng_mode=1)
+    same = histories_equal(mg, mo)
+    tallies_close(mg, mo, same.mean())
+    n = 40000
+    box = run_gpu(small_sphere(**dict(par, no_photons=n, save_all_photons=False)))
+    slab = run_gpu(small_sphere(**dict(par, no_photons=n, save_all_photons=False, nx=1, ny=1, iseed=5)))
+    assert box.nscatt_gas / n == pytest.approx(slab.nscatt_gas / n, rel=0.03)
+    chi2, dof = chi2_per_bin(box.spectrum("Jout"), slab.spectrum("Jout"), n, n)
+    assert dof >= 15 and chi2 < 1.7, (chi2, dof)
 
 
 def test_xyz_symmetry_octant_is_statistically_the_full_sphere():

@@ -93,34 +93,53 @@ def test_raytrace_to_tau_photon_state():
     sim.close()
 
 
-@pytest.mark.parametrize("dims", [(16, 16, 16), (15, 15, 15), (16, 15, 12)], ids=["even", "odd", "mixed"])
-def test_xyz_symmetry_rays_bit_exact(dims):
-    """raytrace_to_edge_car_xyzsym / raytrace_to_tau_car_xyzsym (raytrace_car.f90:584-760, 1650-1949): mirror planes at
-    the lower faces, including starts exactly on them and walks that are reflected more than once."""
-    nx, ny, nz = dims
-    m = Model(no_photons=10, temperature=1e4, N_HI=1e15, nx=nx, ny=ny, nz=nz, rmax=1.0, xyz_symmetry=True,
-              velocity_type="hubble", Vexp=100.0, nxfreq=50, xfreq_min=-40, xfreq_max=10).setup()
+BOUNDARY_GRIDS = {
+    "xyzsym_even": dict(nx=16, ny=16, nz=16, rmax=1.0, xyz_symmetry=True),
+    "xyzsym_odd": dict(nx=15, ny=15, nz=15, rmax=1.0, xyz_symmetry=True),
+    "xyzsym_mixed": dict(nx=16, ny=15, nz=12, rmax=1.0, xyz_symmetry=True),
+    "xysym_even": dict(nx=16, ny=16, nz=24, rmax=1.0, xy_symmetry=True),
+    "xysym_odd": dict(nx=15, ny=13, nz=21, rmax=1.0, xy_symmetry=True),
+    "xyper_box": dict(nx=7, ny=5, nz=24, xmax=0.5, ymax=0.25, zmax=1.0, geometry="rectangle", xy_periodic=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(BOUNDARY_GRIDS))
+def test_boundary_variant_rays_bit_exact(name):
+    """The folded and periodic ray tracers — _xyzsym (raytrace_car.f90:584-760, 1650-1949), _xysym (:783-969, 1951-2250),
+    _xyper (:971-1136, 2252-2517): starts exactly on the mirror / periodic faces, walks reflected or wrapped many times."""
+    kw = BOUNDARY_GRIDS[name]
+    m = Model(no_photons=10, temperature=1e4, N_HI=1e15, velocity_type="hubble", Vexp=100.0, nxfreq=50, xfreq_min=-40,
+              xfreq_max=10, **kw).setup()
     sim = Simulation(m, pool_slots=1024)
     n = 100000
     p, k, ic, xf = random_rays(m, n, 21)
     g = m.config.contents.grid
+    nn = np.array([g.nx, g.ny, g.nz])
     q = n // 10
-    p[4 * q:5 * q, 0] = g.xmin  # on the mirror planes themselves
+    p[4 * q:5 * q, 0] = g.xmin  # on the lower (mirror / periodic) planes themselves
     p[5 * q:6 * q, 2] = g.zmin
-    ic = np.clip(np.floor((p - [g.xmin, g.ymin, g.zmin]) / [g.dx, g.dy, g.dz]).astype(np.int32) + 1, 1, [nx, ny, nz])
+    p[6 * q:7 * q, 1] = g.ymax
+    k[np.abs(k[:, 2]) < 0.02, 2] = 0.3  # a horizontal ray in a periodic box never ends
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    ic = np.floor((p - [g.xmin, g.ymin, g.zmin]) / [g.dx, g.dy, g.dz]).astype(np.int32) + 1
+    if "xyper" not in name:
+        ic = np.clip(ic, 1, nn)  # the periodic variants see photons in cell n+1 on the upper face, as upstream
+    else:
+        ic[:, 2] = np.clip(ic[:, 2], 1, g.nz)
     cols = lambda a: (a[:, 0], a[:, 1], a[:, 2])
     cap = 96
     tg, ng, trg = sim.raytrace_to_edge(*cols(p), *cols(k), xf, *cols(ic), trace_cap=cap)
     to, no, tro = oracle.raytrace_to_edge(m.config, *cols(p), *cols(k), xf, *cols(ic), trace_cap=cap)
     assert np.array_equal(ng, no) and np.array_equal(trg, tro) and np.array_equal(tg, to)
-    assert ng.max() > max(dims) + 2  # reflected walks are longer than any straight one from the planes outwards
-    tau_in = np.random.default_rng(8).exponential(size=n) * np.median(to)
+    assert ng.max() > nn.max() + 2  # reflected / wrapped walks are longer than any straight one
+    tau_in = np.random.default_rng(8).exponential(size=n) * np.median(to[to > 0])
     a = sim.raytrace_to_tau(*cols(p), *cols(k), xf, *cols(ic), tau_in)
     b = oracle.raytrace_to_tau(m.config, *cols(p), *cols(k), xf, *cols(ic), tau_in)
     for key in ("inside", "icell", "jcell", "kcell", "nsteps", "x", "y", "z", "xfreq", "xfreq_ref"):
         assert np.array_equal(a[key], b[key]), key
     assert 0.05 < a["inside"].mean() < 0.95
-    assert a["x"].min() >= g.xmin and a["y"].min() >= g.ymin and a["z"].min() >= g.zmin
+    ins = a["inside"] == 1
+    assert a["x"][ins].min() >= g.xmin and a["y"][ins].min() >= g.ymin and a["x"][ins].max() <= g.xmax
     sim.close()
 
 

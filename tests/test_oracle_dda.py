@@ -158,3 +158,86 @@ def test_xyz_symmetry_run_is_statistically_the_full_run():
     jf, jo = full.spectrum("Jmu").sum(0), octa.spectrum("Jmu").sum(0)
     assert np.allclose([jo[0] + jo[1], jo[2] + jo[3]], [jf[1] + jf[2], jf[0] + jf[3]], rtol=0.04)
     assert octa.counters["n_photons_done"] == n
+
+
+@pytest.mark.parametrize("nfull,nq", [(32, 16), (29, 15)], ids=["even", "odd_straddling_cell"])
+def test_xy_symmetry_quadrant_unfolds_to_the_full_grid(nfull, nq):
+    """par%xy_symmetry (raytrace_car.f90:783-969, 1951-2250): mirror planes at the lower x and y faces, z open."""
+    kw = dict(no_photons=10, temperature=1e4, N_HI=3e14, rmax=1.0, velocity_type="hubble", Vexp=100.0, nxfreq=21)
+    full = Model(nx=nfull, ny=nfull, nz=nfull, **kw).setup()
+    quad = Model(nx=nq, ny=nq, nz=nfull, xy_symmetry=True, **kw).setup()
+    gf, gq = full.config.contents.grid, quad.config.contents.grid
+    assert (gq.nx, gq.ny, gq.nz) == (nq, nq, nfull) and gq.dz == gf.dz and gq.zmin == gf.zmin and gq.k0 == 0
+    assert gq.dx == pytest.approx(gf.dx, rel=1e-15) and quad.config.contents.par.xy_symmetry == 1
+    assert np.allclose(quad.grid_array("rhokap")[gq.i0 - 1, gq.j0 - 1, :], full.grid_array("rhokap")[nfull // 2, nfull // 2, :],
+                       rtol=1e-12)
+    rng = np.random.default_rng(12)
+    n = 20000
+    p = rng.uniform(-0.999, 0.999, (n, 3))
+    k = rng.normal(size=(n, 3))
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    xf = rng.normal(size=n) * 2
+    sgn = np.where(p < 0, -1.0, 1.0)
+    sgn[:, 2] = 1.0
+    pf, kf = p * sgn, k * sgn
+    cell = lambda q, g: np.floor((q - [g.xmin, g.ymin, g.zmin]) / [g.dx, g.dy, g.dz]).astype(np.int32) + 1
+    ic, iq = cell(p, gf), cell(pf, gq)
+    cols = lambda a: (a[:, 0], a[:, 1], a[:, 2])
+    tf, _, _ = oracle.raytrace_to_edge(full.config, *cols(p), *cols(k), xf, *cols(ic))
+    tq, _, _ = oracle.raytrace_to_edge(quad.config, *cols(pf), *cols(kf), xf, *cols(iq))
+    assert np.allclose(tq, tf, rtol=1e-9, atol=1e-12) and 0.05 < tf.mean() < 50
+    tau_in = rng.exponential(size=n) * np.median(tf)
+    a = oracle.raytrace_to_tau(full.config, *cols(p), *cols(k), xf, *cols(ic), tau_in)
+    b = oracle.raytrace_to_tau(quad.config, *cols(pf), *cols(kf), xf, *cols(iq), tau_in)
+    clear = np.abs(tau_in / np.maximum(tf, 1e-300) - 1) > 1e-6
+    assert np.array_equal(a["inside"][clear], b["inside"][clear])
+    ins = clear & (a["inside"] == 1)
+    assert 0.2 < ins.mean() < 0.8
+    for key in "xy":  # a point inside the straddling first cell may stay on the negative side: compare |x|
+        assert np.allclose(np.abs(a[key][ins]), np.abs(b[key][ins]), atol=1e-9), key
+    assert b["x"][ins].min() >= gq.xmin and b["y"][ins].min() >= gq.ymin
+    assert np.allclose(a["z"][ins], b["z"][ins], atol=1e-9) and b["z"][ins].min() < -0.1  # z is not folded
+    assert np.allclose(a["xfreq"][ins], b["xfreq"][ins], atol=1e-9)
+
+
+def test_xy_periodic_box_is_an_infinite_slab():
+    """par%xy_periodic with nx, ny > 1 (raytrace_car.f90:971-1136, 2252-2517): rays wrap around in x and y, leave through
+    the z faces only, and land folded back into the box."""
+    m = Model(no_photons=10, temperature=1e4, taumax=5.0, nx=4, ny=3, nz=20, xmax=0.5, ymax=0.25, zmax=1.0, geometry="rectangle",
+              xy_periodic=True, nxfreq=11).setup()
+    g = m.config.contents.grid
+    assert m.config.contents.par.xy_periodic == 1 and (g.nx, g.ny, g.nz) == (4, 3, 20)
+    rng = np.random.default_rng(13)
+    n = 20000
+    lo, d, nn = np.array([g.xmin, g.ymin, g.zmin]), np.array([g.dx, g.dy, g.dz]), np.array([g.nx, g.ny, g.nz])
+    p = lo + rng.uniform(0, 1, (n, 3)) * d * nn
+    k = rng.normal(size=(n, 3))
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    k[np.abs(k[:, 2]) < 0.02, 2] = 0.5  # nearly horizontal rays wrap thousands of times: keep the test quick
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    q = n // 10
+    p[:q, 0] = rng.choice([g.xmin, g.xmax], q)  # on the periodic faces themselves
+    p[q:2 * q, 1] = rng.choice([g.ymin, g.ymax], q)
+    ic = np.floor((p - lo) / d).astype(np.int32) + 1  # a photon on the upper face sits in cell n+1, as upstream
+    xf = rng.uniform(-3, 3, n)
+    cols = lambda a: (a[:, 0], a[:, 1], a[:, 2])
+    tau, ns, _ = oracle.raytrace_to_edge(m.config, *cols(p), *cols(k), xf, *cols(ic))
+    kap = m.grid_array("rhokap")[0, 0, 0] * oracle.voigt(xf, m.summary.voigt_a)
+    path = np.where(k[:, 2] > 0, (g.zmax - p[:, 2]) / k[:, 2], (g.zmin - p[:, 2]) / k[:, 2])
+    upper = ((ic[:, 0] > g.nx) & (k[:, 0] > 0)) | ((ic[:, 1] > g.ny) & (k[:, 1] > 0))  # to_edge returns 0 there (:1020, :1046)
+    assert np.all(tau[upper] == 0) and upper.sum() > 100
+    assert np.allclose(tau[~upper], (kap * path)[~upper], rtol=1e-10)
+    assert ns.max() > 3 * (g.nx + g.ny + g.nz)  # wrapped more than once
+    tau_in = rng.exponential(size=n) * np.median(tau)
+    b = oracle.raytrace_to_tau(m.config, *cols(p), *cols(k), xf, *cols(ic), tau_in)
+    ins = b["inside"] == 1
+    assert np.array_equal(ins, tau_in <= kap * path) or (ins != (tau_in <= kap * path)).mean() < 1e-3
+    dist = tau_in / kap
+    want = p + dist[:, None] * k
+    for a, key, lo_, rng_ in ((0, "x", g.xmin, g.xmax - g.xmin), (1, "y", g.ymin, g.ymax - g.ymin)):
+        folded = want[:, a] - np.floor((want[:, a] - lo_) / rng_) * rng_
+        err = np.abs(b[key][ins] - folded[ins])
+        assert np.all(np.minimum(err, rng_ - err) < 1e-9), key  # modulo one period for points on a face
+        assert b[key][ins].min() >= lo_ and b[key][ins].max() <= lo_ + rng_
+    assert np.allclose(b["z"][ins], want[ins, 2], atol=1e-9)
+    assert (b["icell"][ins] >= 1).all() and (b["icell"][ins] <= g.nx).all()

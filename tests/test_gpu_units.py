@@ -139,7 +139,9 @@ def test_boundary_variant_rays_bit_exact(name):
         assert np.array_equal(a[key], b[key]), key
     assert 0.05 < a["inside"].mean() < 0.95
     ins = a["inside"] == 1
-    assert a["x"][ins].min() >= g.xmin and a["y"][ins].min() >= g.ymin and a["x"][ins].max() <= g.xmax
+    # (upstream quirk kept: a start exactly on a straddling mirror plane, x = xmin = -dx/2, is reflected into cell i0 = 2
+    # with its distances still measured from -dx/2, so such a photon can land up to dx beyond xmax)
+    assert a["x"][ins].min() >= g.xmin and a["y"][ins].min() >= g.ymin and a["x"][ins].max() <= g.xmax + g.dx
     sim.close()
 
 

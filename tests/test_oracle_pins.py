@@ -105,7 +105,11 @@ def test_namelist_file_roundtrip(tmp_path):
     with pytest.raises(LartError):
         Model(no_such_key=1.0)
     with pytest.raises(LartError):
-        Model(xy_periodic=True, nx=3, ny=3).setup()
+        Model(z_symmetry=True, nx=3, ny=3).setup()  # stays with the Fortran host
+    with pytest.raises(LartError):
+        Model(xy_symmetry=True, xy_periodic=True, nx=3, ny=3).setup()
+    box = Model(xy_periodic=True, nx=3, ny=3, geometry="rectangle").setup()  # 3-D periodic box: the _xyper ray tracers
+    assert box.summary.zonly == 0 and box.config.contents.par.xy_periodic == 1
 
 
 # ---- whole-run known answers ------------------------------------------------

@@ -340,7 +340,12 @@ def test_edge_cases_and_errors():
         Simulation(bad)
     bad = small_sphere()
     bad.config.contents.par.xy_periodic = 1
-    with pytest.raises(LartError, match="xy_periodic"):
+    bad.config.contents.par.xy_symmetry = 1
+    with pytest.raises(LartError, match="non-periodic"):
+        Simulation(bad)
+    bad = small_sphere()
+    bad.config.contents.par.xyz_symmetry = 1  # peel-off is on, i0/j0/k0 are not set
+    with pytest.raises(LartError, match="xyz_symmetry"):
         Simulation(bad)
     with pytest.raises(LartError, match="device"):
         Simulation(small_sphere(), device=99)

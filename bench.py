@@ -46,6 +46,12 @@ WORKLOADS = {
     # peeling-off is not allowed on folded grids (setup.f90:198), so this is the transport loop alone
     "sphere_octant_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xyz_symmetry=True, nx=101, ny=101, nz=101,
                                  rmax=1.0, nxfreq=201),
+    # par%xy_symmetry: the x,y quadrant of configs[1]'s sphere, full height, with its peel-off cube
+    "sphere_quadrant_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xy_symmetry=True, nx=101, ny=101, nz=201,
+                                   rmax=1.0, nxfreq=201, nxim=129, nyim=129, distance=1e2),
+    # par%xy_periodic with nx, ny > 1: configs[0]'s slab as a 3-D periodic box (the _xyper ray tracers)
+    "box_periodic_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xy_periodic=True, geometry="rectangle",
+                                nx=64, ny=64, nz=201, xmax=0.32, ymax=0.32, zmax=1.0),
     # small case for smoke-testing the bench itself
     "tiny": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=61, nxim=33, nyim=33),
 }
@@ -300,11 +306,13 @@ def run_gpu(args):
         tc = time.perf_counter()
         buf_n = sim.tally_buffer()[1]
         e2e_s = tc - t0  # results are in the host arrays here; releasing the device memory is not part of the job
+        phases = {"create_s": ta - t0, "steps_s": tb - ta, "reduce_fetch_s": tc - tb}
         sim.close()
         print("e2e phases: create %.3f s, steps %.3f s, reduce+fetch %.3f s, destroy (untimed) %.3f s" %
               (ta - t0, tb - ta, tc - tb, time.perf_counter() - tc), file=sys.stderr)
     else:
         e2e_s = time.perf_counter() - t0
+        phases = None
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     ns = torch.tensor([model.counters["n_scatter"] if rank == 0 else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -334,6 +342,7 @@ def run_gpu(args):
             "gpu_launches": int(n_launch), "roofline": roof,
             "e2e": {"value": e2e_value, "unit": "scatterings/s", "h2d_bytes_per_step": grid_bytes / total_steps,
                     "d2h_bytes_per_step": (8 * buf_n + 8 * total_steps) / total_steps, "seconds": float(te[0]),
+                    "phases_rank0": phases,
                     "region": "lart_gpu_create(H2D host grid) + begin + %d steps (+D2H of each step's in-flight count) + "
                               "NCCL reduce + D2H of the tally buffer into host arrays (lart_gpu_destroy not timed)" % total_steps},
             "clocks": clk.summary(),

@@ -102,6 +102,7 @@ typedef struct lart_params {
                                 (setup.f90:952-954; raytrace_car.f90:584-760, 1650-1949); no peel-off     */
   int32_t xy_symmetry;       /* mirror planes at the lower x and y faces, z open: the _xysym ray tracers
                                 (setup.f90:955-957; raytrace_car.f90:783-969, 1951-2250)                  */
+  int32_t use_clump_medium;  /* the clump ray tracers and do_resonance1_clump (setup.f90:806-860); needs cfg.clumps */
   int32_t xy_periodic;       /* nx==ny==1: the _zonly ray tracers; otherwise the _xyper ray tracers, photons
                                 wrap around in x and y (setup.f90:958-976; raytrace_car.f90:971-1136,
                                 2252-2517).  Shear-periodic boxes (par%Omega /= 0) are not on the GPU path */
@@ -136,11 +137,35 @@ typedef struct lart_scatt_mat {
   const int32_t *alias;                      /* (nPDF-1) 1-based, 0 = none     */
 } lart_scatt_mat;
 
+/* ---- next row: the clump medium — src/clump_mod.f90:30-118 -----------------------
+ * N spherical clumps inside a sphere of radius sphere_R, vacuum between them (par%use_clump_medium).  The host owns
+ * the population (init_clumps / generate_clumps / read_clumps_info) and the CSR acceleration grid
+ * (build_clump_csr, :1267-1349); the library only reads them.  n = 0: no clump medium.  Overlapping populations
+ * (has_overlap, the event-walk ray tracers of raytrace_clump.f90:621-1208) are not on the GPU path. */
+typedef struct lart_clumps {
+  int64_t n;                        /* N_clumps                                                     */
+  double sphere_R;                  /* outer radius                                                 */
+  double Dfreq_ref;                 /* cl_Dfreq_ref (= grid.Dfreq_ref in clump mode)                */
+  const double *x, *y, *z;          /* cl_x/y/z (n): centres                                        */
+  const double *vx, *vy, *vz;       /* cl_vx/y/z (n): bulk velocity / cl_vtherm(icl)                */
+  const double *radius;             /* cl_radius (n); cl_radius2 = radius*radius                    */
+  const double *rhokap;             /* cl_rhokap (n): line-centre opacity per code length           */
+  const double *rhokapD;            /* cl_rhokapD (n) or NULL when DGR = 0                          */
+  const double *voigt_a, *Dfreq;    /* cl_voigt_a, cl_Dfreq (n)                                     */
+  int32_t cgx, cgy, cgz;            /* CSR grid cells per axis                                      */
+  int32_t has_overlap;              /* must be 0                                                    */
+  double cg_xmin, cg_ymin, cg_zmin; /* lower corner of the CSR grid                                 */
+  double cg_dx, cg_dy, cg_dz;       /* its cell sizes; cg_inv_d* = 1/cg_d* is recomputed            */
+  const int32_t *cg_start;          /* (cgx*cgy*cgz + 1) 1-based offsets into cg_list, as upstream  */
+  const int32_t *cg_list;           /* 1-based clump indices                                        */
+} lart_clumps;
+
 typedef struct lart_config {
   lart_grid grid;
   lart_params par;
   lart_line line;
   lart_scatt_mat scatt_mat;        /* nPDF = 0 when unused                  */
+  lart_clumps clumps;              /* n = 0 when unused                     */
   const lart_observer *observers;  /* par.nobs entries                      */
   int32_t device;                  /* CUDA device ordinal                   */
   int32_t pool_slots;              /* photons in flight; 0 = auto           */
@@ -300,6 +325,24 @@ int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n,
                          const double *x, const double *y, const double *z,
                          const int32_t *icell, const int32_t *jcell, const int32_t *kcell,
                          double *xcrit);
+
+/* ---- next row: clump-medium ray tracers, unit level ---------------------------------
+ * raytrace_to_edge_clump (src/raytrace_clump.f90:205-270; tau_max <= 0) or raytrace_to_edge_clump_capped
+ * (:494-533; tau_max > 0, the peel-off call with tau_huge_clump = 745.2).  icl[i] = photon%icell_clump (0 = vacuum).
+ * nclumps[i] = clumps crossed (diagnostic). */
+int lart_gpu_clump_edge_batch(lart_gpu_handle h, int64_t n,
+                              const double *x, const double *y, const double *z,
+                              const double *kx, const double *ky, const double *kz,
+                              const double *xfreq, const int32_t *icl, double tau_max,
+                              double *tau, int32_t *nclumps);
+/* raytrace_to_tau_clump (:83-201): x,y,z,xfreq,icl are updated in place; inside[i] = photon%inside.  No Jout tally. */
+int lart_gpu_clump_tau_batch(lart_gpu_handle h, int64_t n,
+                             double *x, double *y, double *z,
+                             const double *kx, const double *ky, const double *kz,
+                             double *xfreq, int32_t *icl, const double *tau_in, int32_t *inside);
+/* active_set_at_point (src/clump_mod.f90:1595-1634), first hit: the clump a point lies in, or 0 */
+int lart_gpu_clump_locate_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z,
+                                int32_t *icl);
 
 /* ---- next row: sight-line maps, a pure reuse of the edge walk -------------
  * make_sightline_tau_outside (src/sightline_tau_rect.f90:11-190): for every observer and detector pixel the

@@ -27,6 +27,7 @@ typedef struct lart_host_summary {
   double Dfreq_ref, vtherm, cross0, atau3, xfreq_min, xfreq_max, dxfreq, dxim, dyim, distance;
   int32_t nx, ny, nz, nxfreq, nobs, nxim, nyim, zonly;
   int64_t nphotons;
+  int64_t nclumps;   /* clump medium: N_clumps (0 otherwise) */
 } lart_host_summary;
 
 lart_host_model *lart_host_new(void);

@@ -59,7 +59,7 @@ class Params(C.Structure):
         ("save_Jin", C.c_int32), ("save_Jabs", C.c_int32), ("save_Jmu", C.c_int32),
         ("save_peeloff", C.c_int32), ("save_peeloff_2D", C.c_int32), ("save_peeloff_3D", C.c_int32),
         ("save_direc0", C.c_int32), ("save_all_photons", C.c_int32), ("xyz_symmetry", C.c_int32), ("xy_symmetry", C.c_int32),
-        ("xy_periodic", C.c_int32),
+        ("use_clump_medium", C.c_int32), ("xy_periodic", C.c_int32),
         ("nobs", C.c_int32),
     ]
 
@@ -80,8 +80,20 @@ class ScattMat(C.Structure):
                 ("alias", c_int32_p)]
 
 
+class Clumps(C.Structure):
+    _fields_ = [("n", C.c_int64), ("sphere_R", C.c_double), ("Dfreq_ref", C.c_double),
+                ("x", c_double_p), ("y", c_double_p), ("z", c_double_p),
+                ("vx", c_double_p), ("vy", c_double_p), ("vz", c_double_p),
+                ("radius", c_double_p), ("rhokap", c_double_p), ("rhokapD", c_double_p),
+                ("voigt_a", c_double_p), ("Dfreq", c_double_p),
+                ("cgx", C.c_int32), ("cgy", C.c_int32), ("cgz", C.c_int32), ("has_overlap", C.c_int32),
+                ("cg_xmin", C.c_double), ("cg_ymin", C.c_double), ("cg_zmin", C.c_double),
+                ("cg_dx", C.c_double), ("cg_dy", C.c_double), ("cg_dz", C.c_double),
+                ("cg_start", c_int32_p), ("cg_list", c_int32_p)]
+
+
 class Config(C.Structure):
-    _fields_ = [("grid", Grid), ("par", Params), ("line", Line), ("scatt_mat", ScattMat),
+    _fields_ = [("grid", Grid), ("par", Params), ("line", Line), ("scatt_mat", ScattMat), ("clumps", Clumps),
                 ("observers", C.POINTER(Observer)), ("device", C.c_int32), ("pool_slots", C.c_int32),
                 ("quantum", C.c_int32), ("flags", C.c_int32), ("streams", C.c_int32), ("ray_budget", C.c_int32)]
 
@@ -120,7 +132,7 @@ class HostSummary(C.Structure):
                  "tauhomo_dust", "Dfreq_ref", "vtherm", "cross0", "atau3", "xfreq_min", "xfreq_max", "dxfreq",
                  "dxim", "dyim", "distance"]] + \
                [(n, C.c_int32) for n in ["nx", "ny", "nz", "nxfreq", "nobs", "nxim", "nyim", "zonly"]] + \
-               [("nphotons", C.c_int64)]
+               [("nphotons", C.c_int64), ("nclumps", C.c_int64)]
 
 
 # every symbol include/lart_gpu.h declares (tests check the library exports all of them)
@@ -131,6 +143,7 @@ GPU_SYMBOLS = [
     "lart_gpu_raytrace_edge_batch", "lart_gpu_raytrace_tau_batch", "lart_gpu_sample_batch",
     "lart_gpu_xcrit_batch", "lart_gpu_version", "lart_gpu_stage_ms", "lart_gpu_pool_slots", "lart_gpu_measure_fp64",
     "lart_gpu_sightline_tau", "lart_gpu_sightline_stats",
+    "lart_gpu_clump_edge_batch", "lart_gpu_clump_tau_batch", "lart_gpu_clump_locate_batch",
 ]
 HOST_SYMBOLS = [
     "lart_host_new", "lart_host_free", "lart_host_set", "lart_host_read_input", "lart_host_setup",
@@ -210,5 +223,8 @@ def load_gpu():
         lib.lart_gpu_measure_fp64.argtypes = [C.c_int32, c_double_p]
         lib.lart_gpu_sightline_tau.argtypes = [H, C.c_double, C.POINTER(SightlineOut)]
         lib.lart_gpu_sightline_stats.argtypes = [H, c_double_p, c_double_p]
+        lib.lart_gpu_clump_edge_batch.argtypes = [H, C.c_int64] + [c_double_p] * 7 + [c_int32_p, C.c_double, c_double_p, c_int32_p]
+        lib.lart_gpu_clump_tau_batch.argtypes = [H, C.c_int64] + [c_double_p] * 7 + [c_int32_p, c_double_p, c_int32_p]
+        lib.lart_gpu_clump_locate_batch.argtypes = [H, C.c_int64] + [c_double_p] * 3 + [c_int32_p]
         _gpu = lib
     return _gpu

@@ -53,6 +53,19 @@ enum { T_SCATT = 0, T_DIREC = 1, T_DIREC0 = 2, T_I = 3, T_Q = 4, T_U = 5, T_V = 
 enum { C_PHOTONS = 0, C_SCATTER = 1, C_CELLSTEPS = 2, C_PEEL = 3, C_RNG = 4, C_REJECT = 5 };
 
 // Everything a kernel needs, passed by value as a __grid_constant__ parameter.
+// clump medium (lart_clump.cuh): geometry record = centre + radius^2 (one 32-byte sector per ray-sphere test),
+// physics record = 64 bytes read once per clump crossed
+struct __align__(16) ClumpPhys { double rhokap, rhokapD, voigt_a, Dfreq, vx, vy, vz, pad_; };
+struct DevClumps {
+  long long n;
+  double sphere_R, R2, Dfreq_ref;
+  const double4 *geo;
+  const ClumpPhys *phys;
+  const int *cg_start, *cg_list;  // 1-based offsets / clump indices, as the host built them
+  int cgx, cgy, cgz, pad_;
+  double xmin, ymin, zmin, dx, dy, dz, inv_dx, inv_dy, inv_dz;
+};
+
 struct DevParams {
   // grid
   int nx, ny, nz, nxfreq;
@@ -62,6 +75,8 @@ struct DevParams {
   // boundary variants of the ray tracers (setup.f90:952-976): bcxy / bcz = BC_* of the x,y axes and of the z axis;
   // sym = par%xyz_symmetry (source fold, |kz| in Jmu); i0,j0,k0 = cell entered on reflection (grid_mod_car.f90:85-134)
   int sym, bcxy, bcz, i0, j0, k0;
+  int clump;      // par%use_clump_medium: the ray tracers of lart_clump.cuh, photons carry their clump index
+  DevClumps cl;
   double Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax;
   const double *xface, *yface, *zface;
   const Cell *cells;                                            // packed records (default walk)
@@ -923,13 +938,15 @@ LART_DEV void stokes_azimuth(const Photon &ph, const PeelRay &pr, double cost, d
 }
 
 // peeling_direct_outside — peelingoff_rect.f90:24-129.  cs = photon's cell record.
+// in_clump: the photon was born inside a clump and its frequency is in that clump's frame (cs carries the clump's
+// bulk velocity): only the binning frequency is shifted (peelingoff_rect.f90:65-69)
 LART_DEV bool peel_direct_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph, const CellData &cs,
-                                  PeelRay &pr) {
+                                  PeelRay &pr, bool in_clump = false) {
   double r2;
   bool in_image = peel_geometry(ob, ph, pr, r2);
   double xref;
   pr.xfreq = ph.xfreq;
-  if (!P.comoving_source) {  // :70-80
+  if (!P.comoving_source && !in_clump) {  // :70-80
     double u1 = vdotk(cs, ph.kx, ph.ky, ph.kz);
     xref = ph.xfreq + u1;
     pr.xfreq = xref - vdotk(cs, pr.kx, pr.ky, pr.kz);
@@ -1192,12 +1209,12 @@ struct ScatterOut {
 // sits between the frequency update and the Stokes/triad update in the reference
 // (:446 / :788): `peel` is invoked at exactly that point.
 // `uz` = rand_resonance_vz(x, a) has been drawn by the caller (serially, or warp-cooperatively).
-template <class PeelFn>
-LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, double uz,
-                                PeelFn &&peel) {
+// CLUMP: uz and xfreq_atom come from do_resonance1_clump (line_clump_mod.f90:29-58) and the perpendicular atom
+// velocity is rescaled by vth_ratio = cl_Dfreq/cl_Dfreq_ref (scattering_car.f90:384-388, 715-719)
+template <bool CLUMP, class PeelFn>
+LART_DEV void scatter_resonance_core(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, double uz,
+                                     double xfreq_atom, double vth_ratio, PeelFn &&peel) {
   ph.nsg += ph.wgt;
-  // do_resonance1 — line_mod.f90:108-139
-  double xfreq_atom = ph.xfreq - uz;
   double cost = rand_resonance_fast(r, P);
   double sint = sqrt(1.0 - cost * cost);
   double cost2 = cost * cost;
@@ -1222,6 +1239,7 @@ LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const Ce
     sincospi(2.0 * u1, &s2, &c2);
     ux = uxy * c2; uy = uxy * s2;
   }
+  if (CLUMP) { ux = ux * vth_ratio; uy = uy * vth_ratio; }
   ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
   if (P.recoil) ph.xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
   if (P.save_peeloff) peel(xfreq_atom, ux, uy, uz);
@@ -1258,6 +1276,12 @@ LART_DEV bool dust_absorb(const DevParams &P, Photon &ph, Rng &r, const CellData
 
 // scatter_dust_stokes (:201-329) / _nostokes (:488-584); `peel` is invoked where
 // the reference calls peeling_dust_* (after absorption, before the new direction).
+template <class PeelFn>
+LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, double uz,
+                                PeelFn &&peel) {
+  // do_resonance1 — line_mod.f90:108-139
+  scatter_resonance_core<false>(P, ph, r, cs, cnt, uz, ph.xfreq - uz, 1.0, peel);
+}
 template <class PeelFn>
 LART_DEV void scatter_dust(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, PeelFn &&peel) {
   ph.nsd += ph.wgt;

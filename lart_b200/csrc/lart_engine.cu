@@ -39,6 +39,7 @@
 
 #include "../../include/lart_gpu.h"
 #include "lart_device.cuh"
+#include "lart_clump.cuh"
 #include "voigt_tables.cuh"
 
 
@@ -371,6 +372,139 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
       if (fl & PH_ALIVE) store_rng(pl, s, rng, fl);
       ph.flags = fl;
       store_all(pl, s, ph);
+    }
+    if (rng_valid) nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// ------------------------------ clump medium --------------------------------
+// One thread per photon slot, like k_mono, with the clump ray tracers (lart_clump.cuh) in place of the cell walk.
+// The slot's clump index (photon%icell_clump) lives in the first `rc` column of the pool.  Scattering, peel-off
+// weights and tallies are the Cartesian routines — as upstream, which swaps only the ray tracers, do_resonance and
+// the frame conversions (setup.f90:806-860).
+__global__ void __launch_bounds__(kBlock) k_mono_clump(const __grid_constant__ DevParams P, Pool pl, Job *job, int quantum) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  const DevClumps &C = P.cl;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  Counters cnt;
+  ctr_t nrng = 0;
+  if (s < pl.n) {
+    Photon ph;
+    Rng rng;
+    int icl = 0;
+    ph.flags = pl.flags[s];
+    bool rng_valid = false, touched = false;
+    if (ph.flags & PH_ALIVE) {
+      load_trace_part(pl, s, ph);
+      load_rest(pl, s, ph);
+      load_rng(P, pl, s, ph.id, ph.flags, rng);
+      icl = pl.rc[s];
+      rng_valid = true;
+    }
+    // peel-off toward every observer from the photon's current state; csp = grid record with the clump's bulk velocity
+    auto trace_and_deposit = [&](PeelRay &pr) {
+      int nc = 0, ncl = 0;
+      double t = clump_walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.xfreq, icl, kTauHugeClump, nc, ncl);
+      cnt.cellsteps += nc; cnt.peel += 1;
+      peel_deposit(P, pr, t, __activemask());
+    };
+    for (int ev = 0; ev < quantum; ++ev) {
+      CellData cs;
+      if (!(ph.flags & PH_ALIVE)) {
+        if (job->next >= job->count) break;
+        unsigned long long j = atomicAdd(&job->next, 1ULL);
+        if (j >= job->count) break;
+        touched = true;
+        ph.id = job->first_id + (long long)j * job->stride;
+        if (rng_valid) nrng += rng.nrng;
+        rng.start(P.seed, (unsigned long long)ph.id);
+        rng_valid = true;
+        generate_photon(P, ph, rng, cnt, cs);
+        if (P.save_all_photons) record_initial(P, ph);
+        icl = clump_at_point(C, ph.x, ph.y, ph.z);  // the birth clump, before the direct peel (generate_photon.f90:325-332)
+        CellData csp = cs;
+        if (icl > 0) {
+          const ClumpPhys cp = load_clump(C, icl);
+          ph.xfreq = DSUB(ph.xfreq, ulos_clump(P, cp, ph.kx, ph.ky, ph.kz));
+          const double ratio = cp.Dfreq / C.Dfreq_ref;
+          csp.vfx = DMUL(cp.vx, ratio); csp.vfy = DMUL(cp.vy, ratio); csp.vfz = DMUL(cp.vz, ratio);
+        }
+        if (P.save_peeloff) {
+          for (int i = 0; i < P.nobs; ++i) {
+            PeelRay pr;
+            if (!peel_direct_prepare(P, P.obs[i], i, ph, csp, pr, icl > 0)) continue;
+            trace_and_deposit(pr);
+          }
+        }
+      }
+      touched = true;
+      double tau;
+      if (ph.flags & PH_FIRST) {  // forced first scattering: the uncapped edge walk (setup.f90:809)
+        int ci, cj, ck, nc = 0, ncl = 0;
+        clamp_cell_for_read(P, ph, ci, cj, ck);
+        load_cell(P, ci, cj, ck, cs);
+        double tau0 = clump_walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, -1.0, nc, ncl);
+        cnt.cellsteps += nc;
+        tau = forced_first(P, ph, rng, cs, tau0);
+      } else {
+        tau = -log(rng.uniform());
+      }
+      int nc = 0;
+      if (!clump_walk_tau(P, vtab, ph, icl, tau, nc)) {  // left the sphere (raytrace_clump.f90:137-146, 151-160, 182-192)
+        cnt.cellsteps += nc;
+        ph.flags &= ~PH_ALIVE;
+        ph.xfreq_ref = ph.xfreq;  // upstream leaves photon%xfreq_ref unset on this path; Jout is binned with xfreq
+        retire_photon(P, ph, true, job, cnt);
+        continue;
+      }
+      cnt.cellsteps += nc;
+      // scattering inside clump icl — scattering_car.f90:72-87
+      cnt.scatter += 1;
+      load_cell(P, ph.ic, ph.jc, ph.kc, cs);  // the box: no opacity, no bulk velocity, reference Doppler width
+      const ClumpPhys cp = load_clump(C, icl);
+      const double ratio = cp.Dfreq / C.Dfreq_ref, scale = C.Dfreq_ref / cp.Dfreq;
+      CellData csp = cs;
+      csp.vfx = DMUL(cp.vx, ratio); csp.vfy = DMUL(cp.vy, ratio); csp.vfz = DMUL(cp.vz, ratio);
+      bool to_dust = false;
+      if (P.dust) {
+        double pd = cp.rhokapD / (cp.rhokap * voigt_seon2(vtab, DMUL(ph.xfreq, scale), cp.voigt_a) + cp.rhokapD);
+        to_dust = rng.uniform() <= pd;
+      }
+      if (to_dust) {
+        scatter_dust(P, ph, rng, cs, cnt, [&]() {
+          for (int i = 0; i < P.nobs; ++i) {
+            PeelRay pr;
+            bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[i], i, ph, csp, pr)
+                                   : peel_dust_nostokes_prepare(P, P.obs[i], i, ph, csp, pr);
+            if (ok) trace_and_deposit(pr);
+          }
+        });
+        if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
+      } else {  // do_resonance1_clump — line_clump_mod.f90:29-58
+        const double scale_inv = 1.0 / scale;
+        const double xloc = ph.xfreq * scale;
+        const double uz_loc = rand_resonance_vz(rng, xloc, cp.voigt_a, cnt.reject);
+        const double xfreq_atom = (xloc - uz_loc) * scale_inv, uz = uz_loc * scale_inv;
+        CellData css = cs;
+        css.Dfreq = cp.Dfreq;  // recoil uses the clump's Doppler width (scattering_car.f90:428-433)
+        scatter_resonance_core<true>(P, ph, rng, css, cnt, uz, xfreq_atom, ratio, [&](double xa, double ux, double uy, double uzz) {
+          for (int i = 0; i < P.nobs; ++i) {
+            PeelRay pr;
+            bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[i], i, ph, csp, xa, ux, uy, uzz, pr)
+                                   : peel_resonance_nostokes_prepare(P, P.obs[i], i, ph, csp, xa, ux, uy, uzz, pr);
+            if (ok) trace_and_deposit(pr);
+          }
+        });
+      }
+    }
+    if (touched) {
+      int fl = ph.flags;
+      if (fl & PH_ALIVE) store_rng(pl, s, rng, fl);
+      ph.flags = fl;
+      store_all(pl, s, ph);
+      pl.rc[s] = icl;
     }
     if (rng_valid) nrng += rng.nrng;
   }
@@ -859,6 +993,51 @@ __global__ void k_tau_batch(const __grid_constant__ DevParams P, long long n, do
     if (nsteps) nsteps[i] = ns < 0 ? 0 : ns;
   }
 }
+__global__ void k_clump_edge_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
+                                   const double *z, const double *kx, const double *ky, const double *kz, const double *xfreq,
+                                   const int *icl, double tau_max, double *tau, int *nclumps, unsigned long long *ncells) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  unsigned long long mine = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int nc = 0, ncl = 0;
+    tau[i] = clump_walk_edge(P, vtab, x[i], y[i], z[i], kx[i], ky[i], kz[i], xfreq[i], icl[i], tau_max, nc, ncl);
+    if (nclumps) nclumps[i] = ncl;
+    mine += (unsigned long long)nc;
+  }
+  if (ncells && mine) atomicAdd(ncells, mine);
+}
+__global__ void k_clump_tau_batch(const __grid_constant__ DevParams P, long long n, double *x, double *y, double *z,
+                                  const double *kx, const double *ky, const double *kz, double *xfreq, int *icl,
+                                  const double *tau_in, int *inside) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    Photon ph;
+    ph.x = x[i]; ph.y = y[i]; ph.z = z[i]; ph.kx = kx[i]; ph.ky = ky[i]; ph.kz = kz[i]; ph.xfreq = xfreq[i];
+    ph.ic = ph.jc = ph.kc = 1; ph.flags = PH_ALIVE;
+    int c = icl[i], nc = 0;
+    const bool in = clump_walk_tau(P, vtab, ph, c, tau_in[i], nc);
+    x[i] = ph.x; y[i] = ph.y; z[i] = ph.z; xfreq[i] = ph.xfreq; icl[i] = c; inside[i] = in ? 1 : 0;
+  }
+}
+__global__ void k_clump_locate_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
+                                     const double *z, int *icl) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    icl[i] = clump_at_point(P.cl, x[i], y[i], z[i]);
+}
+// host arrays -> device records (geometry: centre + radius^2; physics: 64 bytes)
+__global__ void k_pack_clumps(long long n, const double *x, const double *y, const double *z, const double *radius,
+                              const double *rhokap, const double *rhokapD, const double *voigt_a, const double *Dfreq,
+                              const double *vx, const double *vy, const double *vz, double4 *geo, ClumpPhys *phys) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    geo[i] = make_double4(x[i], y[i], z[i], DMUL(radius[i], radius[i]));
+    ClumpPhys cp;
+    cp.rhokap = rhokap[i]; cp.rhokapD = rhokapD ? rhokapD[i] : 0.0; cp.voigt_a = voigt_a[i]; cp.Dfreq = Dfreq[i];
+    cp.vx = vx[i]; cp.vy = vy[i]; cp.vz = vz[i]; cp.pad_ = 0.0;
+    phys[i] = cp;
+  }
+}
 __global__ void k_xcrit_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
                               const double *z, const int *ic, const int *jc, const int *kc, double *out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1075,6 +1254,28 @@ int dupload(lart_gpu_ctx *h, const T **dst, const T *src, size_t n) {
   return 0;
 }
 
+struct Scratch {  // device copies of host arrays for one batch call
+  std::vector<void *> p;
+  ~Scratch() { for (void *q : p) cudaFree(q); }
+  template <class T>
+  int in(T **d, const T *hsrc, size_t n) {
+    *d = nullptr;
+    if (!hsrc) return 0;
+    CUDA_OK(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
+    p.push_back(*d);
+    CUDA_OK(cudaMemcpy(*d, hsrc, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+  }
+  template <class T>
+  int outbuf(T **d, size_t n) {
+    CUDA_OK(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
+    p.push_back(*d);
+    return 0;
+  }
+};
+inline int grid_for(long long n, int nsm) { return (int)std::max<long long>(1, std::min<long long>((n + kBlock - 1) / kBlock, nsm * 8LL)); }
+#define D2H(dst, src, n) CUDA_OK(cudaMemcpy((dst), (src), (n) * sizeof(*(dst)), cudaMemcpyDeviceToHost))
+
 int validate(const lart_config *c) {
   const lart_grid &g = c->grid;
   const lart_params &p = c->par;
@@ -1089,6 +1290,18 @@ int validate(const lart_config *c) {
   if (p.save_Jmu && (p.nmu < 1 || !(p.dmu > 0.0))) return fail("lart_gpu_create: save_Jmu needs nmu >= 1 and dmu > 0");
   if (!(g.dxfreq > 0.0)) return fail("lart_gpu_create: dxfreq must be > 0");
   if (g.nz >= (1 << kFlipShift)) return fail("lart_gpu_create: nz too large");
+  if (p.use_clump_medium) {  // setup.f90:806-860; grid_mod_clump.f90:55-59
+    const lart_clumps &cl = c->clumps;
+    if (cl.n < 1 || cl.n > 2147483647LL) return fail("lart_gpu_create: use_clump_medium needs 1 <= clumps.n < 2^31");
+    if (!cl.x || !cl.y || !cl.z || !cl.vx || !cl.vy || !cl.vz || !cl.radius || !cl.rhokap || !cl.voigt_a || !cl.Dfreq ||
+        !cl.cg_start || !cl.cg_list)
+      return fail("lart_gpu_create: NULL clump array");
+    if (p.DGR > 0.0 && !cl.rhokapD) return fail("lart_gpu_create: DGR > 0 but clumps.rhokapD is NULL");
+    if (cl.has_overlap) return fail("lart_gpu_create: overlapping clump populations (has_overlap) stay with the Fortran host");
+    if (cl.cgx < 1 || cl.cgy < 1 || cl.cgz < 1 || !(cl.cg_dx > 0.0) || !(cl.cg_dy > 0.0) || !(cl.cg_dz > 0.0) || !(cl.sphere_R > 0.0))
+      return fail("lart_gpu_create: bad clump CSR grid");
+    if (p.xyz_symmetry || p.xy_symmetry || p.xy_periodic) return fail("lart_gpu_create: the clump medium uses the plain box (grid_mod_clump.f90:55-59)");
+  }
   if (p.xyz_symmetry || p.xy_symmetry) {  // setup.f90:167, 198-206, 952-957; grid_mod_car.f90:85-134
     if (p.xy_periodic || g.nx < 2 || g.ny < 2 || (p.xyz_symmetry && g.nz < 2))
       return fail("lart_gpu_create: xyz_symmetry / xy_symmetry need a 3-D, non-periodic grid");
@@ -1158,6 +1371,35 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   P.bcxy = P.sym ? BC_MIRROR : (p.xy_symmetry ? BC_MIRROR : ((p.xy_periodic && !zonly_grid) ? BC_PERIODIC : BC_OPEN));
   P.bcz = P.sym ? BC_MIRROR : BC_OPEN;
   P.local_steps = ((cfg->flags & LART_FLAG_LOCAL_STEPS) && !P.bcxy) ? 1 : 0;  // the in-stage cell step knows no mirror planes or wrap-around
+  // ---- clump medium: records packed on the device from the host's arrays (clump_mod.f90:30-118)
+  P.clump = 0;
+  P.cl = DevClumps{};
+  if (p.use_clump_medium) {
+    const lart_clumps &cl = cfg->clumps;
+    const size_t n = (size_t)cl.n, ncell = (size_t)cl.cgx * cl.cgy * cl.cgz;
+    const size_t nreg = (size_t)(cl.cg_start[ncell] - 1);
+    P.clump = 1;
+    P.cl.n = cl.n; P.cl.sphere_R = cl.sphere_R; P.cl.R2 = cl.sphere_R * cl.sphere_R; P.cl.Dfreq_ref = cl.Dfreq_ref;
+    P.cl.cgx = cl.cgx; P.cl.cgy = cl.cgy; P.cl.cgz = cl.cgz;
+    P.cl.xmin = cl.cg_xmin; P.cl.ymin = cl.cg_ymin; P.cl.zmin = cl.cg_zmin;
+    P.cl.dx = cl.cg_dx; P.cl.dy = cl.cg_dy; P.cl.dz = cl.cg_dz;
+    P.cl.inv_dx = 1.0 / cl.cg_dx; P.cl.inv_dy = 1.0 / cl.cg_dy; P.cl.inv_dz = 1.0 / cl.cg_dz;
+    double4 *geo = nullptr;
+    ClumpPhys *phys = nullptr;
+    if ((rc = dalloc(h, &geo, n, false)) || (rc = dalloc(h, &phys, n, false))) return bail(rc);
+    if ((rc = dupload(h, &P.cl.cg_start, cl.cg_start, ncell + 1)) || (rc = dupload(h, &P.cl.cg_list, cl.cg_list, nreg))) return bail(rc);
+    {
+      Scratch sc;
+      double *d[11];
+      const double *src[11] = {cl.x, cl.y, cl.z, cl.radius, cl.rhokap, cl.rhokapD, cl.voigt_a, cl.Dfreq, cl.vx, cl.vy, cl.vz};
+      for (int k = 0; k < 11; ++k) if ((rc = sc.in(&d[k], src[k], n))) return bail(rc);
+      k_pack_clumps<<<(int)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)h->nsm * 8), kBlock, 0, h->stream>>>(
+          (long long)n, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], geo, phys);
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    P.cl.geo = geo; P.cl.phys = phys;
+  }
   P.nsbx = (g.nx + 31) / 32; P.nsby = (g.ny + 31) / 32; P.nsbz = (g.nz + 31) / 32;
   if (!P.soa) {
     Cell *cells = nullptr;
@@ -1243,7 +1485,8 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   }
   // ---- photon pool
   h->flags = cfg->flags;
-  const bool mono = (cfg->flags & LART_FLAG_MONOLITHIC) != 0;
+  if (P.clump) h->flags |= LART_FLAG_MONOLITHIC;  // the clump medium runs on the one-thread-per-photon driver for now
+  const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int S = cfg->pool_slots;
   if (S <= 0) S = mono ? h->nsm * 2048 : h->nsm * 16384;
   {
@@ -1369,7 +1612,8 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
   if (mono) {
     size_t ne = 0;
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
-    k_mono<<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
+    if (h->P.clump) k_mono_clump<<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
+    else k_mono<<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
     h->launches += 1;
   } else {
@@ -1693,27 +1937,6 @@ int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out) {
 
 // ---------------------------- batched plugin points -------------------------
 namespace {
-struct Scratch {  // device copies of host arrays for one batch call
-  std::vector<void *> p;
-  ~Scratch() { for (void *q : p) cudaFree(q); }
-  template <class T>
-  int in(T **d, const T *hsrc, size_t n) {
-    *d = nullptr;
-    if (!hsrc) return 0;
-    CUDA_OK(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
-    p.push_back(*d);
-    CUDA_OK(cudaMemcpy(*d, hsrc, n * sizeof(T), cudaMemcpyHostToDevice));
-    return 0;
-  }
-  template <class T>
-  int outbuf(T **d, size_t n) {
-    CUDA_OK(cudaMalloc(d, std::max<size_t>(n, 1) * sizeof(T)));
-    p.push_back(*d);
-    return 0;
-  }
-};
-inline int grid_for(long long n, int nsm) { return (int)std::max<long long>(1, std::min<long long>((n + kBlock - 1) / kBlock, nsm * 8LL)); }
-#define D2H(dst, src, n) CUDA_OK(cudaMemcpy((dst), (src), (n) * sizeof(*(dst)), cudaMemcpyDeviceToHost))
 }  // namespace
 
 extern "C" {
@@ -1816,6 +2039,83 @@ int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n, const double *x, const do
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   D2H(xcrit, dout, n);
+  return 0;
+}
+
+int lart_gpu_clump_edge_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z, const double *kx,
+                              const double *ky, const double *kz, const double *xfreq, const int32_t *icl, double tau_max,
+                              double *tau, int32_t *nclumps) {
+  if (!h) return fail("lart_gpu_clump_edge_batch: NULL handle");
+  if (!h->P.clump) return fail("lart_gpu_clump_edge_batch: the handle has no clump medium");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !kx || !ky || !kz || !xfreq || !icl || !tau))) return fail("lart_gpu_clump_edge_batch: bad argument");
+  if (n == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz, *dkx, *dky, *dkz, *dxf, *dtau;
+  int *dicl, *dncl = nullptr;
+  unsigned long long *dcells;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, x, n); rc = rc ? rc : s.in(&dy, y, n); rc = rc ? rc : s.in(&dz, z, n);
+  rc = rc ? rc : s.in(&dkx, kx, n); rc = rc ? rc : s.in(&dky, ky, n); rc = rc ? rc : s.in(&dkz, kz, n);
+  rc = rc ? rc : s.in(&dxf, xfreq, n); rc = rc ? rc : s.in(&dicl, icl, n);
+  rc = rc ? rc : s.outbuf(&dtau, n); rc = rc ? rc : s.outbuf(&dcells, 1);
+  if (nclumps) rc = rc ? rc : s.outbuf(&dncl, n);
+  if (rc) return rc;
+  CUDA_OK(cudaMemsetAsync(dcells, 0, sizeof(unsigned long long), h->stream));
+  CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+  k_clump_edge_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dkx, dky, dkz, dxf, dicl, tau_max, dtau, dncl, dcells);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  unsigned long long cells = 0;
+  D2H(&cells, dcells, 1);
+  h->sight_ms = ms; h->sight_steps = (double)cells;  // read back through lart_gpu_sightline_stats
+  D2H(tau, dtau, n);
+  if (nclumps) D2H(nclumps, dncl, n);
+  return 0;
+}
+
+int lart_gpu_clump_tau_batch(lart_gpu_handle h, int64_t n, double *x, double *y, double *z, const double *kx, const double *ky,
+                             const double *kz, double *xfreq, int32_t *icl, const double *tau_in, int32_t *inside) {
+  if (!h) return fail("lart_gpu_clump_tau_batch: NULL handle");
+  if (!h->P.clump) return fail("lart_gpu_clump_tau_batch: the handle has no clump medium");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !kx || !ky || !kz || !xfreq || !icl || !tau_in || !inside))) return fail("lart_gpu_clump_tau_batch: bad argument");
+  if (n == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz, *dkx, *dky, *dkz, *dxf, *dtau;
+  int *dicl, *din;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, (const double *)x, n); rc = rc ? rc : s.in(&dy, (const double *)y, n); rc = rc ? rc : s.in(&dz, (const double *)z, n);
+  rc = rc ? rc : s.in(&dkx, kx, n); rc = rc ? rc : s.in(&dky, ky, n); rc = rc ? rc : s.in(&dkz, kz, n);
+  rc = rc ? rc : s.in(&dxf, (const double *)xfreq, n); rc = rc ? rc : s.in(&dicl, (const int *)icl, n);
+  rc = rc ? rc : s.in(&dtau, tau_in, n); rc = rc ? rc : s.outbuf(&din, n);
+  if (rc) return rc;
+  k_clump_tau_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dkx, dky, dkz, dxf, dicl, dtau, din);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  D2H(x, dx, n); D2H(y, dy, n); D2H(z, dz, n); D2H(xfreq, dxf, n); D2H(icl, dicl, n); D2H(inside, din, n);
+  return 0;
+}
+
+int lart_gpu_clump_locate_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z, int32_t *icl) {
+  if (!h) return fail("lart_gpu_clump_locate_batch: NULL handle");
+  if (!h->P.clump) return fail("lart_gpu_clump_locate_batch: the handle has no clump medium");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !icl))) return fail("lart_gpu_clump_locate_batch: bad argument");
+  if (n == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz;
+  int *dicl;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, x, n); rc = rc ? rc : s.in(&dy, y, n); rc = rc ? rc : s.in(&dz, z, n); rc = rc ? rc : s.outbuf(&dicl, n);
+  if (rc) return rc;
+  k_clump_locate_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dicl);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  D2H(icl, dicl, n);
   return 0;
 }
 

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <fstream>
 #include <limits>
+#include <random>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -68,7 +69,11 @@ struct Par {
   double taumax = -999.0, tauhomo = -999.0, tau0 = -999.0;
   double N_HImax = -999.0, N_HIhomo = -999.0, N_HI = -999.0, N_gasmax = -999.0, N_gashomo = -999.0;
   double atau3 = 0.0;
-  double Vexp = 0.0, Vx = 0.0, Vy = 0.0, Vz = 0.0, rpeak = 0.0;
+  double Vexp = 0.0, Vx = 0.0, Vy = 0.0, Vz = 0.0, rpeak = 0.0, Vrot = 0.0, rinner = 0.0;
+  // clump medium — define.f90:326-352
+  bool use_clump_medium = false, clump_fully_inside = true;
+  double clump_radius = -1.0, clump_N_clumps = -1.0, clump_f_vol = -1.0, clump_f_cov = -1.0, clump_tau0 = -1.0,
+         clump_NHI = -1.0, clump_sigma_v = 0.0;
   bool comoving_source = true, recoil = false, core_skip = false, core_skip_global = false;
   bool xyz_symmetry = false, xy_symmetry = false, xy_periodic = false, z_symmetry = false;
   std::string geometry, velocity_type;
@@ -119,6 +124,9 @@ struct lart_host_model {
   std::vector<double> sm_coss, sm_S11, sm_S12, sm_S33, sm_S34, sm_pdf;
   std::vector<int32_t> sm_alias;
   std::vector<lart_observer> observers;
+  // clump population + CSR acceleration grid (clump_mod.f90:30-118)
+  std::vector<double> cl_x, cl_y, cl_z, cl_vx, cl_vy, cl_vz, cl_radius, cl_rhokap, cl_rhokapD, cl_voigt_a, cl_Dfreq;
+  std::vector<int32_t> cg_start, cg_list;
   std::vector<double> steradian_pix;
   lart_config cfg{};
   lart_host_summary sum{};
@@ -189,7 +197,9 @@ int set_key(lart_host_model *m, std::string key, const std::string &value) {
   REAL(no_photons) INT(iseed) REAL(temperature) REAL(temperature0) REAL(bturb) REAL(Dfreq0) REAL(voigt_a0)
   STR(line_id) BOOL(fine_structure)
   REAL(taumax) REAL(tauhomo) REAL(tau0) REAL(N_HImax) REAL(N_HIhomo) REAL(N_HI) REAL(N_gasmax) REAL(N_gashomo)
-  REAL(Vexp) REAL(Vx) REAL(Vy) REAL(Vz)
+  REAL(Vexp) REAL(Vx) REAL(Vy) REAL(Vz) REAL(Vrot) REAL(rinner)
+  BOOL(use_clump_medium) BOOL(clump_fully_inside) REAL(clump_radius) REAL(clump_N_clumps) REAL(clump_f_vol)
+  REAL(clump_f_cov) REAL(clump_tau0) REAL(clump_NHI) REAL(clump_sigma_v)
   BOOL(comoving_source) BOOL(recoil) BOOL(core_skip) BOOL(core_skip_global)
   BOOL(xyz_symmetry) BOOL(xy_symmetry) BOOL(xy_periodic) BOOL(z_symmetry)
   STR(geometry) STR(velocity_type)
@@ -361,6 +371,174 @@ int derive(lart_host_model *m) {
   return 0;
 }
 
+// init_clumps + generate_clumps + assign_clump_velocities_from_type + build_clump_csr + compute_clump_scalars —
+// clump_mod.f90:646-895, 897-1150, 1153-1262, 1267-1349, 2316-2380.  The generated, uniform population only: no
+// radial profiles, no bicone, no clump file, no overlap.  Positions come from MT19937-64 seeded with par%iseed
+// (upstream uses rank 0's stream of the same generator, so the layout is "a" valid layout, not upstream's).
+int clumps_create(lart_host_model *m) {
+  Par &p = m->par;
+  const Line &ln = m->line;
+  lart_clumps &c = m->cfg.clumps;
+  c = lart_clumps{};
+  if (!p.use_clump_medium) return 0;
+  if (p.rmax <= 0.0) { g_err = "par%rmax must be > 0 for clump medium"; return 1; }  // grid_mod_clump.f90:42-45
+  p.xmax = p.ymax = p.zmax = p.rmax;
+  if (p.nx < 1) p.nx = 11;
+  if (p.ny < 1) p.ny = 11;
+  if (p.nz < 1) p.nz = 11;
+  p.xyz_symmetry = p.xy_symmetry = p.xy_periodic = p.z_symmetry = false;
+  const double R = p.rmax, rcl = p.clump_radius;
+  if (rcl <= 0.0) { g_err = "clump_radius must be > 0"; return 1; }
+  const double r0 = std::max(0.0, p.rmin);
+  if (r0 >= R) { g_err = "par%rmin must be < par%rmax for clump placement"; return 1; }
+  const double vtherm = m->vtherm_total(p.temperature);
+  const double Dref = vtherm / (ln.wavelength0 * kUm2Km), aref = (ln.damping / kFourPi) / Dref;
+  auto voigt0 = [](double a) { return 1.0 + a * (-1.1283791671e+00 + a * 1.0); };
+  const double shell2 = R * R + R * r0 + r0 * r0;
+  int64_t N;
+  if (p.clump_N_clumps > 0.0) N = static_cast<int64_t>(p.clump_N_clumps);  // :716-732
+  else if (p.clump_f_vol > 0.0) N = std::llround(p.clump_f_vol * (R * R * R - r0 * r0 * r0) / (rcl * rcl * rcl));
+  else if (p.clump_f_cov > 0.0) N = std::llround((4.0 / 3.0) * p.clump_f_cov * shell2 / (rcl * rcl));
+  else { g_err = "specify clump_N_clumps, clump_f_vol, or clump_f_cov"; return 1; }
+  if (N <= 0) N = 1;
+  if (N > 200000000) { g_err = "too many clumps for the mini-host"; return 1; }
+  double kap;  // :765-809
+  if (p.clump_tau0 > 0.0) kap = p.clump_tau0 / (voigt0(aref) * rcl);
+  else if (p.clump_NHI > 0.0) kap = p.clump_NHI * ln.cross0 / (Dref * rcl);
+  else if (p.taumax > 0.0 || p.N_HImax > 0.0 || p.N_gasmax > 0.0) {
+    const double GF = static_cast<double>(N) * rcl * rcl * rcl / std::max(shell2, 2.2250738585072014e-308);
+    if (p.taumax > 0.0) kap = p.taumax / (GF * voigt0(aref));
+    else kap = std::max(p.N_HImax, p.N_gasmax) * ln.cross0 / (GF * Dref);
+  } else { g_err = "specify clump_tau0, clump_NHI, taumax, or N_HImax"; return 1; }
+  const size_t n = static_cast<size_t>(N);
+  m->cl_x.assign(n, 0.0); m->cl_y.assign(n, 0.0); m->cl_z.assign(n, 0.0);
+  m->cl_vx.assign(n, 0.0); m->cl_vy.assign(n, 0.0); m->cl_vz.assign(n, 0.0);
+  m->cl_radius.assign(n, rcl); m->cl_rhokap.assign(n, kap); m->cl_voigt_a.assign(n, aref); m->cl_Dfreq.assign(n, Dref);
+  if (p.DGR > 0.0) m->cl_rhokapD.assign(n, kap * p.cext_dust * p.DGR * Dref / ln.cross0); else m->cl_rhokapD.clear();  // :859-860
+  // ---- generate_clumps: random sequential addition with a linked-list grid (:897-1150, uniform path)
+  std::mt19937_64 gen(static_cast<uint64_t>(p.iseed));
+  auto rnd = [&]() { return (static_cast<double>(gen() >> 12) + 0.5) * (1.0 / 4503599627370496.0); };  // random_mt.f90:579-630
+  bool have_g = false; double gset = 0.0;
+  auto gauss = [&]() {  // rand_gauss :964-988
+    if (have_g) { have_g = false; return gset; }
+    double v1, v2, rsq;
+    do { v1 = 2.0 * rnd() - 1.0; v2 = 2.0 * rnd() - 1.0; rsq = v1 * v1 + v2 * v2; } while (rsq >= 1.0 || rsq == 0.0);
+    rsq = std::sqrt(-2.0 * std::log(rsq) / rsq);
+    gset = v1 * rsq; have_g = true;
+    return v2 * rsq;
+  };
+  int rg = std::min(512, std::max(32, static_cast<int>(std::cbrt(static_cast<double>(N))) + 1));
+  double rg_cell = std::max(2.0 * R / rg, 2.0 * rcl);
+  rg = std::max(2, static_cast<int>((2.0 * R) / rg_cell) + 1);
+  rg_cell = (2.0 * R) / rg;
+  const double min_sep2 = (2.0 * rcl) * (2.0 * rcl);
+  if (p.clump_fully_inside && (rcl >= R || r0 + 2.0 * rcl > R)) { g_err = "clump_fully_inside: no clump fits inside the shell"; return 1; }
+  const double rmaxc = p.clump_fully_inside ? R - rcl : R, rminc = p.clump_fully_inside ? r0 + rcl : r0;
+  std::vector<int> head(static_cast<size_t>(rg) * rg * rg, -1), nxt(n, -1);
+  int64_t icl = 0, attempts = 0;
+  while (icl < N) {
+    if (++attempts > 2000 * N + 1000000) { g_err = "clump placement does not converge (filling factor too high)"; return 1; }
+    double xc, yc, zc, d2;
+    do {
+      xc = (2.0 * rnd() - 1.0) * rmaxc; yc = (2.0 * rnd() - 1.0) * rmaxc; zc = (2.0 * rnd() - 1.0) * rmaxc;
+      d2 = xc * xc + yc * yc + zc * zc;
+    } while (!(d2 <= rmaxc * rmaxc && d2 >= rminc * rminc));
+    auto gi = [&](double v) { return std::min(rg - 1, std::max(0, static_cast<int>((v + R) / rg_cell))); };
+    const int ig = gi(xc), jg = gi(yc), kg = gi(zc);
+    bool overlap = false;
+    for (int k2 = std::max(0, kg - 1); k2 <= std::min(rg - 1, kg + 1) && !overlap; ++k2)
+      for (int j2 = std::max(0, jg - 1); j2 <= std::min(rg - 1, jg + 1) && !overlap; ++j2)
+        for (int i2 = std::max(0, ig - 1); i2 <= std::min(rg - 1, ig + 1) && !overlap; ++i2)
+          for (int jn = head[i2 + static_cast<size_t>(rg) * (j2 + static_cast<size_t>(rg) * k2)]; jn >= 0; jn = nxt[jn]) {
+            double ddx = xc - m->cl_x[jn], ddy = yc - m->cl_y[jn], ddz = zc - m->cl_z[jn];
+            if (ddx * ddx + ddy * ddy + ddz * ddz < min_sep2) { overlap = true; break; }
+          }
+    if (overlap) continue;
+    m->cl_x[icl] = xc; m->cl_y[icl] = yc; m->cl_z[icl] = zc;
+    if (p.clump_sigma_v > 0.0) {
+      m->cl_vx[icl] = p.clump_sigma_v / vtherm * gauss();
+      m->cl_vy[icl] = p.clump_sigma_v / vtherm * gauss();
+      m->cl_vz[icl] = p.clump_sigma_v / vtherm * gauss();
+    }
+    size_t cell = ig + static_cast<size_t>(rg) * (jg + static_cast<size_t>(rg) * kg);
+    nxt[icl] = head[cell]; head[cell] = static_cast<int>(icl);
+    ++icl;
+  }
+  // ---- assign_clump_velocities_from_type (:1153-1262)
+  const std::string &vt = p.velocity_type;
+  if (!vt.empty()) {
+    if (vt != "hubble" && vt != "constant_radial" && vt != "power_law" && vt != "parallel_velocity" &&
+        vt != "rotating_solid_body" && vt != "rotating_galaxy_halo") {
+      g_err = "velocity_type '" + vt + "' stays with the Fortran host"; return 1;
+    }
+    for (size_t i = 0; i < n; ++i) {
+      const double xc = m->cl_x[i], yc = m->cl_y[i], zc = m->cl_z[i], rr = std::sqrt(xc * xc + yc * yc + zc * zc);
+      double vx = 0.0, vy = 0.0, vz = 0.0;
+      if (vt == "hubble") { vx = p.Vexp * xc / R; vy = p.Vexp * yc / R; vz = p.Vexp * zc / R; }
+      else if (vt == "constant_radial") { if (rr > 0.0) { vx = p.Vexp * xc / rr; vy = p.Vexp * yc / rr; vz = p.Vexp * zc / rr; } }
+      else if (vt == "power_law") { if (rr > 0.0) { double V = p.Vexp * std::pow(rr / R, p.velocity_alpha); vx = V * xc / rr; vy = V * yc / rr; vz = V * zc / rr; } }
+      else if (vt == "parallel_velocity") { vx = p.Vx; vy = p.Vy; vz = p.Vz; }
+      else if (vt == "rotating_solid_body") { vx = -p.Vrot * yc / R; vy = p.Vrot * xc / R; }
+      else {  // rotating_galaxy_halo: flat rotation curve
+        const double rc = std::sqrt(xc * xc + yc * yc);
+        if (rc > 0.0) {
+          if (rc < p.rinner) { vx = -p.Vrot * yc / p.rinner; vy = p.Vrot * xc / p.rinner; }
+          else { vx = -p.Vrot * yc / rc; vy = p.Vrot * xc / rc; }
+        }
+      }
+      m->cl_vx[i] += vx / vtherm; m->cl_vy[i] += vy / vtherm; m->cl_vz[i] += vz / vtherm;
+    }
+  }
+  // ---- build_clump_csr (:1267-1349) with clump_cell_range (:1352-1366)
+  const int cg = std::min(512, std::max(32, static_cast<int>(std::cbrt(static_cast<double>(N))) + 1));
+  const double cmin = -(R + rcl), cd = (2.0 * (R + rcl)) / cg, cinv = 1.0 / cd;
+  const size_t ncells = static_cast<size_t>(cg) * cg * cg;
+  auto range = [&](double v, int &lo, int &hi) {
+    lo = std::max(0, static_cast<int>((v - cmin - rcl) * cinv));
+    hi = std::min(cg - 1, static_cast<int>((v - cmin + rcl) * cinv));
+  };
+  std::vector<int32_t> cnt(ncells, 0);
+  for (size_t i = 0; i < n; ++i) {
+    int i0, i1, j0, j1, k0, k1;
+    range(m->cl_x[i], i0, i1); range(m->cl_y[i], j0, j1); range(m->cl_z[i], k0, k1);
+    for (int k = k0; k <= k1; ++k) for (int j = j0; j <= j1; ++j) for (int ii = i0; ii <= i1; ++ii) ++cnt[ii + static_cast<size_t>(cg) * (j + static_cast<size_t>(cg) * k)];
+  }
+  m->cg_start.assign(ncells + 1, 0);
+  m->cg_start[0] = 1;  // 1-based offsets, as upstream
+  for (size_t q = 0; q < ncells; ++q) m->cg_start[q + 1] = m->cg_start[q] + cnt[q];
+  m->cg_list.assign(static_cast<size_t>(m->cg_start[ncells] - 1), 0);
+  std::fill(cnt.begin(), cnt.end(), 0);
+  for (size_t i = 0; i < n; ++i) {
+    int i0, i1, j0, j1, k0, k1;
+    range(m->cl_x[i], i0, i1); range(m->cl_y[i], j0, j1); range(m->cl_z[i], k0, k1);
+    for (int k = k0; k <= k1; ++k) for (int j = j0; j <= j1; ++j) for (int ii = i0; ii <= i1; ++ii) {
+      size_t q = ii + static_cast<size_t>(cg) * (j + static_cast<size_t>(cg) * k);
+      m->cg_list[static_cast<size_t>(m->cg_start[q] - 1) + cnt[q]] = static_cast<int32_t>(i + 1);
+      ++cnt[q];
+    }
+  }
+  // ---- compute_clump_scalars (:2316-2380)
+  double v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double r3 = rcl * rcl * rcl;
+    const double di2 = std::max(m->cl_x[i] * m->cl_x[i] + m->cl_y[i] * m->cl_y[i] + m->cl_z[i] * m->cl_z[i], rcl * rcl);
+    const double wh = r3 / shell2, wm = r3 / (3.0 * di2);
+    v1 += kap * voigt0(aref) * wh; v2 += kap * voigt0(aref) * wm;
+    v3 += kap * Dref * wh / ln.cross0; v4 += kap * Dref * wm / ln.cross0;
+  }
+  p.tauhomo = v1; p.taumax = v2; p.N_gashomo = v3; p.N_gasmax = v4;
+  c.n = N; c.sphere_R = R; c.Dfreq_ref = Dref;
+  c.x = m->cl_x.data(); c.y = m->cl_y.data(); c.z = m->cl_z.data();
+  c.vx = m->cl_vx.data(); c.vy = m->cl_vy.data(); c.vz = m->cl_vz.data();
+  c.radius = m->cl_radius.data(); c.rhokap = m->cl_rhokap.data();
+  c.rhokapD = m->cl_rhokapD.empty() ? nullptr : m->cl_rhokapD.data();
+  c.voigt_a = m->cl_voigt_a.data(); c.Dfreq = m->cl_Dfreq.data();
+  c.cgx = c.cgy = c.cgz = cg; c.has_overlap = 0;
+  c.cg_xmin = c.cg_ymin = c.cg_zmin = cmin; c.cg_dx = c.cg_dy = c.cg_dz = cd;
+  c.cg_start = m->cg_start.data(); c.cg_list = m->cg_list.data();
+  return 0;
+}
+
 // grid_create — grid_mod_car.f90:11-1238 (synthetic branch: no dens/temp/velo files)
 int grid_create(lart_host_model *m) {
   Par &p = m->par;
@@ -404,7 +582,7 @@ int grid_create(lart_host_model *m) {
     std::fill(m->voigt_a.begin(), m->voigt_a.end(), a);
   }
   // (2) density :355-366 — synthetic test resets the distance unit
-  p.distance_unit = ""; p.distance2cm = 1.0;
+  if (!p.use_clump_medium) { p.distance_unit = ""; p.distance2cm = 1.0; }
   std::fill(m->rhokap.begin(), m->rhokap.end(), 1.0);
   if (dust) std::fill(m->rhokapD.begin(), m->rhokapD.end(), p.cext_dust * p.DGR);
   auto at = [&](int i, int j, int k) { return static_cast<size_t>(i) + static_cast<size_t>(nx) * (j + static_cast<size_t>(ny) * k); };
@@ -777,8 +955,19 @@ int lart_host_read_input(lart_host_model *m, const char *path) {
 int lart_host_setup(lart_host_model *m) {
   if (!m) { g_err = "lart_host_setup: null model"; return 1; }
   if (int rc = derive(m)) return rc;
+  if (int rc = clumps_create(m)) return rc;  // grid_create_clump: the population first (grid_mod_clump.f90:60-80)
   if (int rc = grid_create(m)) return rc;
   Par &p = m->par;
+  if (p.use_clump_medium) {  // :93-101 — the box carries no opacity, no bulk velocity, the clumps' Doppler width
+    std::fill(m->rhokap.begin(), m->rhokap.end(), 0.0);
+    std::fill(m->Dfreq.begin(), m->Dfreq.end(), m->cfg.clumps.Dfreq_ref);
+    std::fill(m->voigt_a.begin(), m->voigt_a.end(), m->cl_voigt_a[0]);
+    std::fill(m->vfx.begin(), m->vfx.end(), 0.0); std::fill(m->vfy.begin(), m->vfy.end(), 0.0); std::fill(m->vfz.begin(), m->vfz.end(), 0.0);
+    m->cfg.grid.Dfreq_ref = m->cfg.clumps.Dfreq_ref;
+    m->sum.nclumps = m->cfg.clumps.n;
+    // the system-level scalars are the clump-derived ones (grid_mod_clump.f90:60-80), not the empty box's
+    m->sum.tauhomo = p.tauhomo; m->sum.taupole = p.taumax; m->sum.N_gashomo = p.N_gashomo; m->sum.N_gaspole = p.N_gasmax;
+  }
   if (p.save_peeloff) { if (int rc = observer_create(m)) return rc; } else { p.nobs = 0; m->observers.clear(); }
   if (p.nobs == 0) { p.save_peeloff = false; p.save_peeloff_2D = false; p.save_peeloff_3D = false; }
   lart_config &c = m->cfg;
@@ -807,7 +996,7 @@ int lart_host_setup(lart_host_model *m) {
   q.use_stokes = p.use_stokes; q.use_reduced_wgt = p.use_reduced_wgt;
   q.save_Jin = p.save_Jin; q.save_Jabs = p.save_Jabs; q.save_Jmu = p.save_Jmu;
   q.save_peeloff = p.save_peeloff; q.save_peeloff_2D = p.save_peeloff_2D; q.save_peeloff_3D = p.save_peeloff_3D; q.save_direc0 = p.save_direc0;
-  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.xy_symmetry = p.xy_symmetry; q.nobs = p.nobs;
+  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.xy_symmetry = p.xy_symmetry; q.use_clump_medium = p.use_clump_medium; q.nobs = p.nobs;
   const Line &ln = m->line;
   c.line.line_type = ln.line_type; c.line.E1 = ln.E1; c.line.E2 = ln.E2; c.line.E3 = ln.E3;
   c.line.g_recoil0 = ln.g_recoil0; c.line.DnuHK_Hz = ln.DnuHK_Hz;

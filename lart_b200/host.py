@@ -340,6 +340,48 @@ class Simulation:
         return dict(x=x, y=y, z=z, xfreq=xfreq, icell=icell, jcell=jcell, kcell=kcell, inside=inside,
                     xfreq_ref=xref, nsteps=nsteps)
 
+    # ---- clump medium, unit level (raytrace_clump.f90)
+    def clump_edge(self, x, y, z, kx, ky, kz, xfreq, icl, tau_max=-1.0):
+        """raytrace_to_edge_clump (tau_max <= 0) / raytrace_to_edge_clump_capped; returns (tau, clumps crossed)."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x, y, z, kx, ky, kz, xfreq = map(f, (x, y, z, kx, ky, kz, xfreq))
+        icl = np.ascontiguousarray(icl, dtype=np.int32)
+        n = x.size
+        tau, ncl = np.zeros(n), np.zeros(n, dtype=np.int32)
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        ip = lambda a: a.ctypes.data_as(capi.c_int32_p)
+        self._check(self._lib.lart_gpu_clump_edge_batch(self._h, n, dp(x), dp(y), dp(z), dp(kx), dp(ky), dp(kz), dp(xfreq),
+                                                        ip(icl), float(tau_max), dp(tau), ip(ncl)))
+        return tau, ncl
+
+    def clump_tau(self, x, y, z, kx, ky, kz, xfreq, icl, tau_in):
+        """raytrace_to_tau_clump on copies; returns the updated photon state."""
+        f = lambda a: np.array(a, dtype=np.float64, copy=True)
+        x, y, z, kx, ky, kz, xfreq, tau_in = map(f, (x, y, z, kx, ky, kz, xfreq, tau_in))
+        icl = np.array(icl, dtype=np.int32, copy=True)
+        n = x.size
+        inside = np.zeros(n, dtype=np.int32)
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        ip = lambda a: a.ctypes.data_as(capi.c_int32_p)
+        self._check(self._lib.lart_gpu_clump_tau_batch(self._h, n, dp(x), dp(y), dp(z), dp(kx), dp(ky), dp(kz), dp(xfreq),
+                                                       ip(icl), dp(tau_in), ip(inside)))
+        return dict(x=x, y=y, z=z, xfreq=xfreq, icl=icl, inside=inside)
+
+    def clump_locate(self, x, y, z):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x, y, z = map(f, (x, y, z))
+        icl = np.zeros(x.size, dtype=np.int32)
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        self._check(self._lib.lart_gpu_clump_locate_batch(self._h, x.size, dp(x), dp(y), dp(z),
+                                                          icl.ctypes.data_as(capi.c_int32_p)))
+        return icl
+
+    def batch_stats(self):
+        """(cells or cell steps walked, kernel ms) of the last sight-line or clump-edge batch call."""
+        steps, ms = C.c_double(0), C.c_double(0)
+        self._check(self._lib.lart_gpu_sightline_stats(self._h, C.byref(steps), C.byref(ms)))
+        return steps.value, ms.value
+
     def xcrit_local(self, x, y, z, icell, jcell, kcell):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         i = lambda a: np.ascontiguousarray(a, dtype=np.int32)

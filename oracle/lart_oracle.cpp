@@ -230,6 +230,7 @@ struct Photon {
   double kx = 0, ky = 0, kz = 1;
   double mx = 0, my = 0, mz = 0, nx = 0, ny = 0, nz = 0;
   int icell = 1, jcell = 1, kcell = 1;  // 1-based like the reference
+  int icl = 0;                          // icell_clump: 0 = vacuum, > 0 = current clump (clump medium only)
   double xfreq = 0, xfreq_ref = 0, wgt = 1;
   bool inside = true;
   double I = 1, Q = 0, U = 0, V = 0;
@@ -246,6 +247,7 @@ struct World {
   bool zonly;
   bool sym = false;  // par%xyz_symmetry: mirror planes at the lower faces (raytrace_car.f90:584-760, 1650-1949)
   int bcxy = 0, bcz = 0;  // BC_* of the x/y axes and of the z axis (setup.f90:952-976)
+  const lart_clumps *cl = nullptr;  // par%use_clump_medium (clump_mod.f90)
   inline size_t idx(int i, int j, int k) const {
     return static_cast<size_t>(i - 1) + static_cast<size_t>(g->nx) * (static_cast<size_t>(j - 1) + static_cast<size_t>(g->ny) * static_cast<size_t>(k - 1));
   }
@@ -513,6 +515,237 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
 
 // ---------------------------------------------------------------------------
 // Samplers
+// ===========================================================================
+// Clump medium — clump_mod.f90 / raytrace_clump.f90 (non-overlapping populations)
+// ===========================================================================
+constexpr double kTauHugeClump = 745.2;  // raytrace_clump.f90:59
+
+// voigt_clump / kappa_clump / ulos_clump — clump_mod.f90:130-190 (line_type 1)
+inline double voigt_clump(const lart_clumps &c, double xfreq, int64_t icl) {
+  double xloc = xfreq * (c.Dfreq_ref / c.Dfreq[icl - 1]);
+  return voigt_seon2(xloc, c.voigt_a[icl - 1]);
+}
+inline double kappa_clump(const World &w, double xfreq, int64_t icl) {
+  const lart_clumps &c = *w.cl;
+  double kap = c.rhokap[icl - 1] * voigt_clump(c, xfreq, icl);
+  if (w.par->DGR > 0.0) kap = kap + c.rhokapD[icl - 1];
+  return kap;
+}
+inline double ulos_clump(const lart_clumps &c, int64_t icl, double kx, double ky, double kz) {
+  return (c.vx[icl - 1] * kx + c.vy[icl - 1] * ky + c.vz[icl - 1] * kz) * (c.Dfreq[icl - 1] / c.Dfreq_ref);
+}
+// ray_sphere_isect — clump_mod.f90:1369-1390
+inline bool ray_sphere_isect(const lart_clumps &c, double ox, double oy, double oz, double kx, double ky, double kz, int64_t icl,
+                             double &t_entry, double &t_exit) {
+  double rx = ox - c.x[icl - 1], ry = oy - c.y[icl - 1], rz = oz - c.z[icl - 1];
+  double b = rx * kx + ry * ky + rz * kz;
+  double disc = b * b - (rx * rx + ry * ry + rz * rz) + c.radius[icl - 1] * c.radius[icl - 1];
+  if (disc < 0.0) { t_entry = 0.0; t_exit = 0.0; return false; }
+  disc = std::sqrt(disc);
+  t_entry = -b - disc;
+  t_exit = -b + disc;
+  return t_exit > 0.0;
+}
+// find_next_clump — clump_mod.f90:1393-1506: DDA through the CSR grid to the nearest clump hit, 0 < t <= t_max
+inline bool find_next_clump(const lart_clumps &c, double xp, double yp, double zp, double kx, double ky, double kz, int64_t skip_icl,
+                            double t_max, double &t_entry, double &t_exit, int64_t &icl_found, long long *ncells = nullptr) {
+  const double inv_dx = 1.0 / c.cg_dx, inv_dy = 1.0 / c.cg_dy, inv_dz = 1.0 / c.cg_dz;
+  double best_te = kHugest, best_tx2 = 0.0, d = 0.0;
+  int64_t best_icl = 0;
+  int ci = std::max(0, std::min(c.cgx - 1, static_cast<int>((xp - c.cg_xmin) * inv_dx)));
+  int cj = std::max(0, std::min(c.cgy - 1, static_cast<int>((yp - c.cg_ymin) * inv_dy)));
+  int ck = std::max(0, std::min(c.cgz - 1, static_cast<int>((zp - c.cg_zmin) * inv_dz)));
+  int si, sj, sk;
+  double tx, ty, tz, delx, dely, delz;
+  auto axis = [](double k, double p, int cc, double lo, double dd, int &st, double &t, double &del) {
+    if (k > 0.0) { st = 1; t = ((lo + static_cast<double>(cc + 1) * dd) - p) / k; del = dd / k; }
+    else if (k < 0.0) { st = -1; t = ((lo + static_cast<double>(cc) * dd) - p) / k; del = -dd / k; }
+    else { st = 0; t = kHugest; del = kHugest; }
+  };
+  axis(kx, xp, ci, c.cg_xmin, c.cg_dx, si, tx, delx);
+  axis(ky, yp, cj, c.cg_ymin, c.cg_dy, sj, ty, dely);
+  axis(kz, zp, ck, c.cg_zmin, c.cg_dz, sk, tz, delz);
+  for (;;) {
+    if (d > best_te || d > t_max) break;
+    if (ncells) ++*ncells;
+    const size_t icell = static_cast<size_t>(ci) + static_cast<size_t>(c.cgx) * (cj + static_cast<size_t>(c.cgy) * ck);
+    for (int32_t ip = c.cg_start[icell]; ip < c.cg_start[icell + 1]; ++ip) {
+      const int64_t icl = c.cg_list[ip - 1];
+      if (icl == skip_icl) continue;
+      double te, tx2;
+      bool hit = ray_sphere_isect(c, xp, yp, zp, kx, ky, kz, icl, te, tx2);
+      if (hit && tx2 > 0.0 && te < best_te && (te > 0.0 || icl != skip_icl)) { best_te = te; best_tx2 = tx2; best_icl = icl; }
+    }
+    if (tx <= ty && tx <= tz) { d = tx; ci += si; if (ci < 0 || ci >= c.cgx) break; tx += delx; }
+    else if (ty <= tz) { d = ty; cj += sj; if (cj < 0 || cj >= c.cgy) break; ty += dely; }
+    else { d = tz; ck += sk; if (ck < 0 || ck >= c.cgz) break; tz += delz; }
+  }
+  if (best_icl > 0 && best_te <= t_max) {
+    t_entry = best_te; t_exit = std::min(best_tx2, t_max); icl_found = best_icl;
+    return true;
+  }
+  return false;
+}
+// clump_exit_dist / sphere_exit_dist — clump_mod.f90:1509-1540
+inline double clump_exit_dist(const lart_clumps &c, double xp, double yp, double zp, double kx, double ky, double kz, int64_t icl) {
+  double rx = xp - c.x[icl - 1], ry = yp - c.y[icl - 1], rz = zp - c.z[icl - 1];
+  double b = rx * kx + ry * ky + rz * kz;
+  double disc = b * b - (rx * rx + ry * ry + rz * rz) + c.radius[icl - 1] * c.radius[icl - 1];
+  if (disc < 0.0) disc = 0.0;
+  return std::max(0.0, -b + std::sqrt(disc));
+}
+inline double sphere_exit_dist(const lart_clumps &c, double xp, double yp, double zp, double kx, double ky, double kz) {
+  double b = xp * kx + yp * ky + zp * kz;
+  double disc = b * b - (xp * xp + yp * yp + zp * zp) + c.sphere_R * c.sphere_R;
+  if (disc < 0.0) disc = 0.0;
+  return std::max(0.0, -b + std::sqrt(disc));
+}
+// active_set_at_point, first hit — clump_mod.f90:1595-1634
+inline int64_t clump_at_point(const lart_clumps &c, double xp, double yp, double zp) {
+  const double inv_dx = 1.0 / c.cg_dx, inv_dy = 1.0 / c.cg_dy, inv_dz = 1.0 / c.cg_dz;
+  int ci = std::max(0, std::min(c.cgx - 1, static_cast<int>((xp - c.cg_xmin) * inv_dx)));
+  int cj = std::max(0, std::min(c.cgy - 1, static_cast<int>((yp - c.cg_ymin) * inv_dy)));
+  int ck = std::max(0, std::min(c.cgz - 1, static_cast<int>((zp - c.cg_zmin) * inv_dz)));
+  for (int k = std::max(0, ck - 1); k <= std::min(c.cgz - 1, ck + 1); ++k)
+    for (int j = std::max(0, cj - 1); j <= std::min(c.cgy - 1, cj + 1); ++j)
+      for (int i = std::max(0, ci - 1); i <= std::min(c.cgx - 1, ci + 1); ++i) {
+        const size_t icell = static_cast<size_t>(i) + static_cast<size_t>(c.cgx) * (j + static_cast<size_t>(c.cgy) * k);
+        for (int32_t ip = c.cg_start[icell]; ip < c.cg_start[icell + 1]; ++ip) {
+          const int64_t icl = c.cg_list[ip - 1];
+          double rx = xp - c.x[icl - 1], ry = yp - c.y[icl - 1], rz = zp - c.z[icl - 1];
+          if (rx * rx + ry * ry + rz * rz <= c.radius[icl - 1] * c.radius[icl - 1]) return icl;
+        }
+      }
+  return 0;
+}
+// update_cell_idx — raytrace_clump.f90:68-75
+inline void update_cell_idx(const World &w, Photon &ph) {
+  const lart_grid &g = *w.g;
+  ph.icell = std::max(1, std::min(g.nx, static_cast<int>(std::floor((ph.x - g.xmin) / g.dx)) + 1));
+  ph.jcell = std::max(1, std::min(g.ny, static_cast<int>(std::floor((ph.y - g.ymin) / g.dy)) + 1));
+  ph.kcell = std::max(1, std::min(g.nz, static_cast<int>(std::floor((ph.z - g.zmin) / g.dz)) + 1));
+}
+// raytrace_to_edge_clump (:205-270; tau_max <= 0) and raytrace_to_edge_clump_capped (:494-533)
+double raytrace_to_edge_clump(const World &w, const Photon &p0, double tau_max, Counters *cnt, int *nclumps = nullptr) {
+  const lart_clumps &c = *w.cl;
+  const bool capped = tau_max > 0.0;
+  double tau = 0.0;
+  double xp = p0.x, yp = p0.y, zp = p0.z;
+  const double kx = p0.kx, ky = p0.ky, kz = p0.kz;
+  double xfreq = p0.xfreq;
+  int64_t icl_cur = p0.icl;
+  int ncl = 0;
+  long long ncell = 0;
+  auto done = [&]() { if (cnt) cnt->n_cellsteps += ncell; if (nclumps) *nclumps = ncl; return tau; };
+  if (icl_cur > 0) {
+    double t_seg = clump_exit_dist(c, xp, yp, zp, kx, ky, kz, icl_cur);
+    double kap = kappa_clump(w, xfreq, icl_cur);
+    tau = tau + kap * t_seg;
+    ++ncl;
+    if (capped && tau >= tau_max) return done();
+    xp = xp + t_seg * kx; yp = yp + t_seg * ky; zp = zp + t_seg * kz;
+    xfreq = xfreq + ulos_clump(c, icl_cur, kx, ky, kz);
+    if (xp * xp + yp * yp + zp * zp >= c.sphere_R * c.sphere_R) return done();
+  }
+  for (;;) {
+    double t_sp = sphere_exit_dist(c, xp, yp, zp, kx, ky, kz);
+    if (t_sp <= 0.0) break;
+    double te, tx2;
+    int64_t icl_found = 0;
+    if (!find_next_clump(c, xp, yp, zp, kx, ky, kz, icl_cur, t_sp, te, tx2, icl_found, &ncell)) break;
+    te = std::max(0.0, te);
+    xp = xp + te * kx; yp = yp + te * ky; zp = zp + te * kz;
+    double u_los = ulos_clump(c, icl_found, kx, ky, kz);
+    xfreq = xfreq - u_los;
+    double t_seg = clump_exit_dist(c, xp, yp, zp, kx, ky, kz, icl_found);
+    double kap = kappa_clump(w, xfreq, icl_found);
+    tau = tau + kap * t_seg;
+    ++ncl;
+    if (capped && tau >= tau_max) return done();
+    xp = xp + t_seg * kx; yp = yp + t_seg * ky; zp = zp + t_seg * kz;
+    xfreq = xfreq + u_los;
+    icl_cur = icl_found;
+    if (xp * xp + yp * yp + zp * zp >= c.sphere_R * c.sphere_R) break;
+  }
+  return done();
+}
+// raytrace_to_tau_clump — raytrace_clump.f90:83-201.  `tl` may be null (unit-level calls).
+// Deviation: upstream leaves photon%xfreq_ref unset on this path (allph%xfreq2 is then stale); here it is the
+// escape frequency that is binned into Jout.
+void raytrace_to_tau_clump(const World &w, Photon &ph, double tau_in, Tally *tl, Counters *cnt) {
+  const lart_clumps &c = *w.cl;
+  const lart_grid &g = *w.g;
+  const double kx = ph.kx, ky = ph.ky, kz = ph.kz;
+  double tau_rem = tau_in;
+  int64_t last_icl = 0;
+  long long ncell = 0;
+  auto escape = [&]() {
+    ph.inside = false;
+    ph.xfreq_ref = ph.xfreq;
+    if (tl) {
+      int ix = static_cast<int>(std::floor((ph.xfreq - g.xfreq_min) / g.dxfreq)) + 1;
+      if (ix >= 1 && ix <= g.nxfreq) {
+        tl->Jout[ix - 1] += ph.wgt;
+        if (w.par->save_Jmu) tl->Jmu[(ix - 1) + static_cast<size_t>(g.nxfreq) * (jmu_bin(*w.par, ph.kz) - 1)] += ph.wgt;
+      }
+    }
+  };
+  while (ph.inside) {
+    if (ph.icl > 0) {
+      const int64_t icl = ph.icl;
+      double t_seg = clump_exit_dist(c, ph.x, ph.y, ph.z, kx, ky, kz, icl);
+      double kap = kappa_clump(w, ph.xfreq, icl);
+      if (tau_rem <= kap * t_seg) {  // scatter inside this clump
+        double ds = tau_rem / std::max(kap, 2.2250738585072014e-308);
+        ph.x = ph.x + ds * kx; ph.y = ph.y + ds * ky; ph.z = ph.z + ds * kz;
+        update_cell_idx(w, ph);
+        break;
+      }
+      tau_rem = tau_rem - kap * t_seg;
+      ph.x = ph.x + t_seg * kx; ph.y = ph.y + t_seg * ky; ph.z = ph.z + t_seg * kz;
+      ph.xfreq = ph.xfreq + ulos_clump(c, icl, kx, ky, kz);
+      last_icl = icl;
+      ph.icl = 0;
+      if (ph.x * ph.x + ph.y * ph.y + ph.z * ph.z >= c.sphere_R * c.sphere_R) {
+        update_cell_idx(w, ph);
+        escape();
+        break;
+      }
+    } else {
+      double t_sp = sphere_exit_dist(c, ph.x, ph.y, ph.z, kx, ky, kz);
+      if (t_sp <= 0.0) { escape(); break; }
+      double te, tx2;
+      int64_t icl_found = 0;
+      if (find_next_clump(c, ph.x, ph.y, ph.z, kx, ky, kz, last_icl, t_sp, te, tx2, icl_found, &ncell)) {
+        te = std::max(0.0, te);
+        ph.x = ph.x + te * kx; ph.y = ph.y + te * ky; ph.z = ph.z + te * kz;
+        ph.xfreq = ph.xfreq - ulos_clump(c, icl_found, kx, ky, kz);
+        last_icl = 0;
+        ph.icl = static_cast<int>(icl_found);
+        update_cell_idx(w, ph);
+      } else {
+        ph.x = ph.x + t_sp * kx; ph.y = ph.y + t_sp * ky; ph.z = ph.z + t_sp * kz;
+        update_cell_idx(w, ph);
+        escape();
+        break;
+      }
+    }
+  }
+  if (cnt) cnt->n_cellsteps += ncell;
+}
+// the ray tracers the procedure pointers select (setup.f90:806-815; peel_raytrace_to_edge, peelingoff_rect.f90:894-906)
+inline double edge_tau(const World &w, const Photon &p, Counters *cnt) {
+  return w.cl ? raytrace_to_edge_clump(w, p, -1.0, cnt) : raytrace_to_edge(w, p, cnt);
+}
+inline double peel_tau(const World &w, const Photon &p, Counters *cnt) {
+  return w.cl ? raytrace_to_edge_clump(w, p, kTauHugeClump, cnt) : raytrace_to_edge(w, p, cnt);
+}
+// line-of-sight fluid velocity for the peel-off frequency (peelingoff_rect.f90:186-192, 403-409, 534-540, 658-664)
+inline double peel_u1(const World &w, const Photon &ph, const Photon &po) {
+  if (w.cl && ph.icl > 0) return ulos_clump(*w.cl, ph.icl, po.kx, po.ky, po.kz);
+  return w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+}
+
 // ---------------------------------------------------------------------------
 // rand_resonance_vz_seon — random_mt.f90:2562-2696
 // The three wing variants of the Fortran (:2605-2635, :2638-2666, :2667-2690) differ
@@ -707,7 +940,9 @@ void peeling_direct(const World &w, const Photon &ph, Tally &tl) {
     PeelGeom pg = peel_geometry(ph, ob);
     Photon &po = pg.pobs;
     double xfreq_ref;
-    if (!par.comoving_source) {  // :70-80
+    if (w.cl && ph.icl > 0) {  // :65-69 — xfreq is in the owner clump's rest frame
+      xfreq_ref = ph.xfreq + ulos_clump(*w.cl, ph.icl, po.kx, po.ky, po.kz);
+    } else if (!par.comoving_source) {  // :70-80
       double u1 = w.vdotk(ph.icell, ph.jcell, ph.kcell, ph.kx, ph.ky, ph.kz);
       xfreq_ref = ph.xfreq + u1;
       double u2 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
@@ -719,7 +954,7 @@ void peeling_direct(const World &w, const Photon &ph, Tally &tl) {
     xfreq_ref = xfreq_ref * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
     int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
     if (!pg.in_image) continue;
-    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    double tau = peel_tau(w, po, &tl.cnt);
     tl.cnt.n_peel += 1;
     double wgt0 = 1.0 / (kFourPi * pg.r2) * ph.wgt;
     double wgt = std::exp(-tau) * wgt0;
@@ -803,14 +1038,14 @@ void peeling_resonance_stokes(const World &w, const Photon &ph, Tally &tl, doubl
     double xfreq = xfreq_atom + (vel_atom[0] * cosp + vel_atom[1] * sinp) * sint + vel_atom[2] * cost;  // :392
     double Dcell = w.Dfreq(ph.icell, ph.jcell, ph.kcell);
     if (par.recoil) xfreq -= (w.line->g_recoil0 / Dcell) * (1.0 - cost);
-    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double u1 = peel_u1(w, ph, po);
     double xfreq_ref = (xfreq + u1) * (Dcell / g.Dfreq_ref);
     int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
     double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
     double Iobs = (S11 + S12 * Q0) / kFourPi, Qobs = (S12 + S22 * Q0) / kFourPi;
     double Uobs = (S33 * U0) / kFourPi, Vobs = (S44 * ph.V) / kFourPi;
     po.xfreq = xfreq;
-    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    double tau = peel_tau(w, po, &tl.cnt);
     tl.cnt.n_peel += 1;
     double wgt = 1.0 / pg.r2 * std::exp(-tau) * ph.wgt;
     deposit_stokes(w, ob, tl.shared->obs[i], po, pg, ixf, wgt, Iobs, Qobs, Uobs, Vobs);
@@ -841,11 +1076,11 @@ void peeling_resonance_nostokes(const World &w, const Photon &ph, Tally &tl, dou
     double xfreq = xfreq_atom + (vel_atom[0] * cosp + vel_atom[1] * sinp) * sint + vel_atom[2] * cost;
     double Dcell = w.Dfreq(ph.icell, ph.jcell, ph.kcell);
     if (par.recoil) xfreq -= (w.line->g_recoil0 / Dcell) * (1.0 - cost);
-    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double u1 = peel_u1(w, ph, po);
     double xfreq_ref = (xfreq + u1) * (Dcell / g.Dfreq_ref);
     int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
     po.xfreq = xfreq;
-    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    double tau = peel_tau(w, po, &tl.cnt);
     tl.cnt.n_peel += 1;
     double peel = 0.75 * ph.E1 * (cost2 + 1.0) + ph.E2;
     double wgt = peel / (kFourPi * pg.r2) * std::exp(-tau) * ph.wgt;
@@ -863,7 +1098,7 @@ void peeling_dust_stokes(const World &w, const Photon &ph, Tally &tl) {
     const lart_observer &ob = w.obs[i];
     PeelGeom pg = peel_geometry(ph, ob);
     Photon &po = pg.pobs;
-    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double u1 = peel_u1(w, ph, po);
     double xfreq_ref = (ph.xfreq + u1) * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
     int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
     if (!pg.in_image) continue;
@@ -877,7 +1112,7 @@ void peeling_dust_stokes(const World &w, const Photon &ph, Tally &tl) {
     double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
     double Iobs = (S11 * ph.I + S12 * Q0) / kTwoPi, Qobs = (S12 * ph.I + S11 * Q0) / kTwoPi;
     double Uobs = (S33 * U0 + S34 * ph.V) / kTwoPi, Vobs = (-S34 * U0 + S33 * ph.V) / kTwoPi;
-    double tau = raytrace_to_edge(w, po, &tl.cnt);  // pobs%xfreq = photon%xfreq (:195-197)
+    double tau = peel_tau(w, po, &tl.cnt);  // pobs%xfreq = photon%xfreq (:195-197)
     tl.cnt.n_peel += 1;
     double wgt = 1.0 / pg.r2 * std::exp(-tau) * ph.wgt;
     deposit_stokes(w, ob, tl.shared->obs[i], po, pg, ixf, wgt, Iobs, Qobs, Uobs, Vobs);
@@ -894,10 +1129,10 @@ void peeling_dust_nostokes(const World &w, const Photon &ph, Tally &tl) {
     PeelGeom pg = peel_geometry(ph, ob);
     if (!pg.in_image) continue;
     Photon &po = pg.pobs;
-    double u1 = w.vdotk(po.icell, po.jcell, po.kcell, po.kx, po.ky, po.kz);
+    double u1 = peel_u1(w, ph, po);
     double xfreq_ref = (ph.xfreq + u1) * (w.Dfreq(ph.icell, ph.jcell, ph.kcell) / g.Dfreq_ref);
     int ixf = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
-    double tau = raytrace_to_edge(w, po, &tl.cnt);
+    double tau = peel_tau(w, po, &tl.cnt);
     tl.cnt.n_peel += 1;
     double cosa = ph.kx * po.kx + ph.ky * po.ky + ph.kz * po.kz;
     double hg = par.hgg;
@@ -913,8 +1148,17 @@ void peeling_dust_nostokes(const World &w, const Photon &ph, Tally &tl) {
 // ---------------------------------------------------------------------------
 // do_resonance1 — line_mod.f90:108-139
 inline void do_resonance1(const World &w, Photon &ph, Rng &r, double &uz, double &xfreq_atom, double &cost, double &sint) {
-  uz = rand_resonance_vz(r, ph.xfreq, w.voigt_a(ph.icell, ph.jcell, ph.kcell));
-  xfreq_atom = ph.xfreq - uz;
+  if (w.cl) {  // do_resonance1_clump — line_clump_mod.f90:29-58: sample in the clump's own Doppler units
+    const lart_clumps &c = *w.cl;
+    const double scale = c.Dfreq_ref / c.Dfreq[ph.icl - 1], scale_inv = 1.0 / scale;
+    const double xloc = ph.xfreq * scale;
+    const double uz_loc = rand_resonance_vz(r, xloc, c.voigt_a[ph.icl - 1]);
+    xfreq_atom = (xloc - uz_loc) * scale_inv;
+    uz = uz_loc * scale_inv;
+  } else {
+    uz = rand_resonance_vz(r, ph.xfreq, w.voigt_a(ph.icell, ph.jcell, ph.kcell));
+    xfreq_atom = ph.xfreq - uz;
+  }
   ph.E1 = w.line->E1; ph.E2 = w.line->E2; ph.E3 = w.line->E3;
   cost = rand_resonance(r, ph.E1);
   sint = std::sqrt(1.0 - cost * cost);
@@ -989,8 +1233,9 @@ void scatter_resonance_stokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
     ux = r.gauss() * one_over_sqrt2;
     uy = r.gauss() * one_over_sqrt2;
   }
+  if (w.cl) { const double vth_ratio = w.cl->Dfreq[ph.icl - 1] / w.cl->Dfreq_ref; ux = ux * vth_ratio; uy = uy * vth_ratio; }  // :384-388
   ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
-  if (par.recoil) ph.xfreq -= (w.line->g_recoil0 / w.Dfreq(ph.icell, ph.jcell, ph.kcell)) * (1.0 - cost);
+  if (par.recoil) ph.xfreq -= (w.line->g_recoil0 / (w.cl ? w.cl->Dfreq[ph.icl - 1] : w.Dfreq(ph.icell, ph.jcell, ph.kcell))) * (1.0 - cost);
   if (par.save_peeloff) {
     double va[3] = {ux, uy, uz};
     peeling_resonance_stokes(w, ph, tl, xfreq_atom, va);
@@ -1017,8 +1262,9 @@ void scatter_resonance_nostokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
   double phi2 = kTwoPi * u1;
   double uxy = (par.core_skip && std::fabs(ph.xfreq) < xc) ? std::sqrt(xc2 - std::log(u2)) : std::sqrt(-std::log(u2));
   double ux = uxy * std::cos(phi2), uy = uxy * std::sin(phi2);
+  if (w.cl) { const double vth_ratio = w.cl->Dfreq[ph.icl - 1] / w.cl->Dfreq_ref; ux = ux * vth_ratio; uy = uy * vth_ratio; }  // :715-719
   ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
-  if (par.recoil) ph.xfreq -= (w.line->g_recoil0 / w.Dfreq(ph.icell, ph.jcell, ph.kcell)) * (1.0 - cost);
+  if (par.recoil) ph.xfreq -= (w.line->g_recoil0 / (w.cl ? w.cl->Dfreq[ph.icl - 1] : w.Dfreq(ph.icell, ph.jcell, ph.kcell))) * (1.0 - cost);
   if (par.save_peeloff) {
     double va[3] = {ux, uy, uz};
     peeling_resonance_nostokes(w, ph, tl, xfreq_atom, va);
@@ -1095,7 +1341,13 @@ void scatter_dust_nostokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
 void scattering(const World &w, Photon &ph, Rng &r, Tally &tl) {
   tl.cnt.n_scatter += 1;
   bool to_dust = false;
-  if (w.dust()) {
+  if (w.cl) {  // scattering_car.f90:72-87
+    if (w.dust() && w.cl->rhokapD) {
+      const lart_clumps &c = *w.cl;
+      double p_dust = c.rhokapD[ph.icl - 1] / (c.rhokap[ph.icl - 1] * voigt_clump(c, ph.xfreq, ph.icl) + c.rhokapD[ph.icl - 1]);
+      to_dust = r.uniform() <= p_dust;
+    }
+  } else if (w.dust()) {
     int i = ph.icell, j = ph.jcell, k = ph.kcell;
     double p_dust = w.rhokapD(i, j, k) / (w.rhokap(i, j, k) * w.calc_voigt(ph.xfreq, i, j, k) + w.rhokapD(i, j, k));
     to_dust = r.uniform() <= p_dust;
@@ -1194,6 +1446,11 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
     int ix = static_cast<int>(std::floor((xlab - g.xfreq_min) / g.dxfreq)) + 1;
     if (ix >= 1 && ix <= g.nxfreq) tl.Jin[ix - 1] += ph.wgt;
   }
+  if (w.cl) {  // :325-332 — the birth clump, before the direct peel
+    const int64_t icl = clump_at_point(*w.cl, ph.x, ph.y, ph.z);
+    ph.icl = static_cast<int>(icl);
+    if (icl > 0) ph.xfreq = ph.xfreq - ulos_clump(*w.cl, icl, ph.kx, ph.ky, ph.kz);
+  }
   if (par.save_peeloff) peeling_direct(w, ph, tl);  // :334-336
 }
 
@@ -1273,7 +1530,7 @@ void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_event
   while (ph.inside) {
     double tau;
     if (first) {  // :163-177 forced first scattering
-      double tau0 = raytrace_to_edge(w, ph, &tl.cnt);
+      double tau0 = edge_tau(w, ph, &tl.cnt);
       add_escaped_fraction(w, ph, tau0, tl);
       double wgt1 = 1.0 - std::exp(-tau0);
       ph.wgt = ph.wgt * wgt1;
@@ -1282,7 +1539,8 @@ void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_event
     } else {
       tau = -std::log(r.uniform());
     }
-    raytrace_to_tau(w, ph, tau, &tl, &tl.cnt);
+    if (w.cl) raytrace_to_tau_clump(w, ph, tau, &tl, &tl.cnt);
+    else raytrace_to_tau(w, ph, tau, &tl, &tl.cnt);
     if (ph.inside) {
       scattering(w, ph, r, tl);
       if (max_events > 0 && ++nev >= max_events) break;
@@ -1415,6 +1673,7 @@ World make_world(const lart_config *cfg) {
   if (w.sym) { w.bcxy = 1; w.bcz = 1; }
   else if (cfg->par.xy_symmetry) w.bcxy = 1;                                  // :955-957
   else if (cfg->par.xy_periodic && !w.zonly) w.bcxy = 2;                      // :966-975 (no shear)
+  if (cfg->par.use_clump_medium && cfg->clumps.n > 0) w.cl = &cfg->clumps;    // :806-860
   return w;
 }
 
@@ -1465,6 +1724,41 @@ int oracle_raytrace_tau(const lart_config *cfg, int64_t n, double *x, double *y,
     if (xfreq_ref) xfreq_ref[i] = p.inside ? 0.0 : p.xfreq_ref;
     if (nsteps) nsteps[i] = ns;
   }
+  return 0;
+}
+
+// clump-medium ray tracers, unit level (the oracle side of lart_gpu_clump_*_batch)
+int oracle_clump_edge(const lart_config *cfg, int64_t n, const double *x, const double *y, const double *z, const double *kx,
+                      const double *ky, const double *kz, const double *xfreq, const int32_t *icl, double tau_max, double *tau,
+                      int32_t *nclumps) {
+  World w = make_world(cfg);
+  if (!w.cl) { g_err = "oracle_clump_edge: no clump medium"; return 1; }
+  for (int64_t i = 0; i < n; ++i) {
+    Photon p;
+    p.x = x[i]; p.y = y[i]; p.z = z[i]; p.kx = kx[i]; p.ky = ky[i]; p.kz = kz[i]; p.xfreq = xfreq[i]; p.icl = icl[i];
+    int nc = 0;
+    tau[i] = raytrace_to_edge_clump(w, p, tau_max, nullptr, &nc);
+    if (nclumps) nclumps[i] = nc;
+  }
+  return 0;
+}
+int oracle_clump_tau(const lart_config *cfg, int64_t n, double *x, double *y, double *z, const double *kx, const double *ky,
+                     const double *kz, double *xfreq, int32_t *icl, const double *tau_in, int32_t *inside) {
+  World w = make_world(cfg);
+  if (!w.cl) { g_err = "oracle_clump_tau: no clump medium"; return 1; }
+  for (int64_t i = 0; i < n; ++i) {
+    Photon p;
+    p.x = x[i]; p.y = y[i]; p.z = z[i]; p.kx = kx[i]; p.ky = ky[i]; p.kz = kz[i]; p.xfreq = xfreq[i]; p.icl = icl[i];
+    p.inside = true;
+    raytrace_to_tau_clump(w, p, tau_in[i], nullptr, nullptr);
+    x[i] = p.x; y[i] = p.y; z[i] = p.z; xfreq[i] = p.xfreq; icl[i] = p.icl; inside[i] = p.inside ? 1 : 0;
+  }
+  return 0;
+}
+int oracle_clump_locate(const lart_config *cfg, int64_t n, const double *x, const double *y, const double *z, int32_t *icl) {
+  World w = make_world(cfg);
+  if (!w.cl) { g_err = "oracle_clump_locate: no clump medium"; return 1; }
+  for (int64_t i = 0; i < n; ++i) icl[i] = static_cast<int32_t>(clump_at_point(*w.cl, x[i], y[i], z[i]));
   return 0;
 }
 

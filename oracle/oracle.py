@@ -48,6 +48,9 @@ def load():
                                    C.POINTER(capi.Tallies)]
         lib.oracle_hardware_threads.restype = C.c_int
         lib.oracle_sightline_tau.argtypes = [cfgp, C.c_double, C.POINTER(capi.SightlineOut), C.POINTER(C.c_double)]
+        lib.oracle_clump_edge.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip, C.c_double, dp, ip]
+        lib.oracle_clump_tau.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip, dp, ip]
+        lib.oracle_clump_locate.argtypes = [cfgp, C.c_int64] + [dp] * 3 + [ip]
         _LIB = lib
     return _LIB
 
@@ -99,6 +102,38 @@ def raytrace_to_tau(cfg, x, y, z, kx, ky, kz, xfreq, ic, jc, kc, tau_in):
     _check(load().oracle_raytrace_tau(cfg, n, _d(x), _d(y), _d(z), _d(kx), _d(ky), _d(kz), _d(xfreq), _i(ic), _i(jc),
                                       _i(kc), _d(tau_in), _i(inside), _d(xref), _i(ns)))
     return dict(x=x, y=y, z=z, xfreq=xfreq, icell=ic, jcell=jc, kcell=kc, inside=inside, xfreq_ref=xref, nsteps=ns)
+
+
+def clump_edge(cfg, x, y, z, kx, ky, kz, xfreq, icl, tau_max=-1.0):
+    """raytrace_to_edge_clump (tau_max <= 0) / raytrace_to_edge_clump_capped."""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x, y, z, kx, ky, kz, xfreq = map(f, (x, y, z, kx, ky, kz, xfreq))
+    icl = np.ascontiguousarray(icl, dtype=np.int32)
+    n = x.size
+    tau, nc = np.zeros(n), np.zeros(n, dtype=np.int32)
+    _check(load().oracle_clump_edge(cfg, n, _d(x), _d(y), _d(z), _d(kx), _d(ky), _d(kz), _d(xfreq), _i(icl), float(tau_max),
+                                    _d(tau), _i(nc)))
+    return tau, nc
+
+
+def clump_tau(cfg, x, y, z, kx, ky, kz, xfreq, icl, tau_in):
+    """raytrace_to_tau_clump on copies; returns the updated photon state."""
+    f = lambda a: np.array(a, dtype=np.float64, copy=True)
+    x, y, z, kx, ky, kz, xfreq, tau_in = map(f, (x, y, z, kx, ky, kz, xfreq, tau_in))
+    icl = np.array(icl, dtype=np.int32, copy=True)
+    n = x.size
+    inside = np.zeros(n, dtype=np.int32)
+    _check(load().oracle_clump_tau(cfg, n, _d(x), _d(y), _d(z), _d(kx), _d(ky), _d(kz), _d(xfreq), _i(icl), _d(tau_in),
+                                   _i(inside)))
+    return dict(x=x, y=y, z=z, xfreq=xfreq, icl=icl, inside=inside)
+
+
+def clump_locate(cfg, x, y, z):
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x, y, z = map(f, (x, y, z))
+    icl = np.zeros(x.size, dtype=np.int32)
+    _check(load().oracle_clump_locate(cfg, x.size, _d(x), _d(y), _d(z), _i(icl)))
+    return icl
 
 
 def xcrit_local(cfg, x, y, z, ic, jc, kc):

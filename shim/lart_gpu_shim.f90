@@ -28,6 +28,9 @@
 module lart_gpu_shim
   use, intrinsic :: iso_c_binding
   use define
+  use clump_mod, only: N_clumps, sphere_R, cl_Dfreq_ref, cl_x, cl_y, cl_z, cl_vx, cl_vy, cl_vz, cl_radius, cl_rhokap, &
+                       cl_rhokapD, cl_voigt_a, cl_Dfreq, cgx, cgy, cgz, cg_xmin, cg_ymin, cg_zmin, cg_dx, cg_dy, cg_dz, &
+                       cg_start, cg_list, has_overlap
   implicit none
   private
   public :: run_gpu
@@ -47,7 +50,7 @@ module lart_gpu_shim
      integer(c_int32_t) :: nmu, spectral_type, source_geometry, comoving_source, recoil
      integer(c_int32_t) :: core_skip, core_skip_global, use_stokes, use_reduced_wgt
      integer(c_int32_t) :: save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D
-     integer(c_int32_t) :: save_direc0, save_all_photons, xyz_symmetry, xy_symmetry, xy_periodic, nobs
+     integer(c_int32_t) :: save_direc0, save_all_photons, xyz_symmetry, xy_symmetry, use_clump_medium, xy_periodic, nobs
   end type
   type, bind(C) :: c_lart_line
      integer(c_int32_t) :: line_type, pad_
@@ -61,11 +64,20 @@ module lart_gpu_shim
      integer(c_int32_t) :: nPDF, pad_
      type(c_ptr) :: coss, S11, S12, S33, S34, phase_PDF, alias
   end type
+  type, bind(C) :: c_lart_clumps            ! src/clump_mod.f90:30-118
+     integer(c_int64_t) :: n
+     real(c_double)     :: sphere_R, Dfreq_ref
+     type(c_ptr)        :: x, y, z, vx, vy, vz, radius, rhokap, rhokapD, voigt_a, Dfreq
+     integer(c_int32_t) :: cgx, cgy, cgz, has_overlap
+     real(c_double)     :: cg_xmin, cg_ymin, cg_zmin, cg_dx, cg_dy, cg_dz
+     type(c_ptr)        :: cg_start, cg_list
+  end type
   type, bind(C) :: c_lart_config
      type(c_lart_grid)      :: grid
      type(c_lart_params)    :: par
      type(c_lart_line)      :: line
      type(c_lart_scatt_mat) :: scatt_mat
+     type(c_lart_clumps)    :: clumps
      type(c_ptr)            :: observers
      integer(c_int32_t)     :: device, pool_slots, quantum, flags, streams, ray_budget
   end type
@@ -154,9 +166,9 @@ contains
     integer :: k, ngpu_per_node
 
     !--- inputs that bind other ray tracers or run loops than the ones behind lart_gpu_run (src/setup.f90:905-990)
-    if (par%use_amr_grid .or. par%use_clump_medium .or. par%z_symmetry .or. par%Omega /= 0.0_wp .or. par%nside > 0 .or. &
+    if (par%use_amr_grid .or. par%z_symmetry .or. par%Omega /= 0.0_wp .or. par%nside > 0 .or. &
         trim(par%geometry) == 'plane_atmosphere' .or. trim(par%geometry) == 'spherical_atmosphere') then
-       write(*,'(a)') 'ERROR (lart_gpu): AMR, clumps, z_symmetry, shear, atmospheres and HEALPix observers are not on the GPU path.'
+       write(*,'(a)') 'ERROR (lart_gpu): AMR, z_symmetry, shear, atmospheres and HEALPix observers are not on the GPU path.'
        call MPI_ABORT(MPI_COMM_WORLD, 1, k)
     endif
 
@@ -207,6 +219,23 @@ contains
     cfg%par%save_all_photons = l2i(par%save_all_photons); cfg%par%xy_periodic = l2i(par%xy_periodic)
     cfg%par%xyz_symmetry = l2i(par%xyz_symmetry); cfg%par%xy_symmetry = l2i(par%xy_symmetry)
     cfg%par%nobs = merge(par%nobs, 0, par%save_peeloff)
+    cfg%par%use_clump_medium = l2i(par%use_clump_medium)
+
+    !--- clump population and its CSR grid (src/clump_mod.f90:30-118); `use clump_mod` provides them
+    cfg%clumps%n = 0
+    if (par%use_clump_medium) then
+       cfg%clumps%n = N_clumps; cfg%clumps%sphere_R = sphere_R; cfg%clumps%Dfreq_ref = cl_Dfreq_ref
+       cfg%clumps%x = c_loc(cl_x); cfg%clumps%y = c_loc(cl_y); cfg%clumps%z = c_loc(cl_z)
+       cfg%clumps%vx = c_loc(cl_vx); cfg%clumps%vy = c_loc(cl_vy); cfg%clumps%vz = c_loc(cl_vz)
+       cfg%clumps%radius = c_loc(cl_radius); cfg%clumps%rhokap = c_loc(cl_rhokap)
+       cfg%clumps%rhokapD = c_null_ptr
+       if (par%DGR > 0.0_wp .and. associated(cl_rhokapD)) cfg%clumps%rhokapD = c_loc(cl_rhokapD)
+       cfg%clumps%voigt_a = c_loc(cl_voigt_a); cfg%clumps%Dfreq = c_loc(cl_Dfreq)
+       cfg%clumps%cgx = cgx; cfg%clumps%cgy = cgy; cfg%clumps%cgz = cgz; cfg%clumps%has_overlap = l2i(has_overlap)
+       cfg%clumps%cg_xmin = cg_xmin; cfg%clumps%cg_ymin = cg_ymin; cfg%clumps%cg_zmin = cg_zmin
+       cfg%clumps%cg_dx = cg_dx; cfg%clumps%cg_dy = cg_dy; cfg%clumps%cg_dz = cg_dz
+       cfg%clumps%cg_start = c_loc(cg_start); cfg%clumps%cg_list = c_loc(cg_list)
+    endif
 
     !--- line_type (src/define.f90:639-656)
     cfg%line%line_type = line%line_type; cfg%line%pad_ = 0

@@ -1,0 +1,95 @@
+"""Clump medium on the GPU, through the C ABI: ray tracers bit-exact against the oracle, whole photon
+histories, scheduling independence.  Reference: raytrace_clump.f90:83-270, 494-533; clump_mod.f90:1393-1540, 1595-1634;
+line_clump_mod.f90:29-58; scattering_car.f90:72-87; peelingoff_rect.f90:65-69, 894-906."""
+import numpy as np
+import pytest
+
+from lart_b200 import Simulation, capi
+from oracle import oracle
+from test_oracle_clumps import clump_model, rays_from
+from test_gpu_runs import histories_equal, run_gpu, tallies_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kw", [dict(velocity_type="hubble", Vexp=80.0, clump_sigma_v=15.0),
+                                dict(clump_radius=0.01, clump_f_cov=5.0, rmin=0.1, clump_fully_inside=False,
+                                     velocity_type="rotating_galaxy_halo", Vrot=300.0, rinner=0.1),
+                                dict(DGR=1.0, cext_dust=3e-17, clump_NHI=1e17, clump_tau0=-1.0, clump_sigma_v=30.0)],
+                         ids=["hubble_sigma", "many_small_rotating", "dusty"])
+def test_clump_ray_tracers_bit_exact(kw):
+    m = clump_model(**kw)
+    sim = Simulation(m, pool_slots=1024)
+    rng = np.random.default_rng(9)
+    n = 100000
+    p, k = rays_from(rng, n)
+    q = n // 10
+    p[:q] = 1e-9                      # the central source
+    p[q:2 * q] *= 1.0 / np.linalg.norm(p[q:2 * q], axis=1)[:, None]  # on the bounding sphere
+    xf = rng.normal(size=n) * 3
+    cols = lambda a: (a[:, 0], a[:, 1], a[:, 2])
+    icl_g, icl_o = sim.clump_locate(*cols(p)), oracle.clump_locate(m.config, *cols(p))
+    assert np.array_equal(icl_g, icl_o) and (icl_o > 0).sum() > 50
+    for cap in (-1.0, 745.2, 3.0):
+        tg, ng = sim.clump_edge(*cols(p), *cols(k), xf, icl_o, tau_max=cap)
+        to, no = oracle.clump_edge(m.config, *cols(p), *cols(k), xf, icl_o, tau_max=cap)
+        assert np.array_equal(ng, no) and np.array_equal(tg, to), cap
+    assert no.max() >= 3
+    tau_in = rng.exponential(size=n) * np.median(to[to > 0])
+    a = sim.clump_tau(*cols(p), *cols(k), xf, icl_o, tau_in)
+    b = oracle.clump_tau(m.config, *cols(p), *cols(k), xf, icl_o, tau_in)
+    for key in ("inside", "icl", "x", "y", "z", "xfreq"):
+        assert np.array_equal(a[key], b[key]), key
+    assert 0.05 < a["inside"].mean() < 0.95
+    sim.close()
+
+
+CLUMP_CASES = {
+    "stokes_peel": dict(use_stokes=True, nxim=17, nyim=17, clump_sigma_v=20.0),
+    "nostokes_peel2D_hubble": dict(use_stokes=False, nxim=17, nyim=17, save_peeloff_2D=True, velocity_type="hubble", Vexp=100.0,
+                                   save_Jmu=True, nmu=5),
+    "two_observers_recoil_voigt": dict(use_stokes=True, nxim=9, nyim=9, obsx=[0.0, 1.0], obsy=[0.0, 0.5], obsz=[1.0, 0.2],
+                                       recoil=True, spectral_type="voigt", clump_tau0=30.0, save_direc0=True),
+    "dust_hg": dict(use_stokes=False, nxim=9, nyim=9, DGR=1.0, cext_dust=3e-17, clump_NHI=2e16, clump_tau0=-1.0),
+    "uniform_sphere_source_shell": dict(use_stokes=True, nxim=9, nyim=9, source_geometry="uniform_sphere", source_rmax=0.5,
+                                        rmin=0.2, clump_radius=0.03, clump_f_cov=3.0, clump_sigma_v=10.0),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CLUMP_CASES))
+def test_clump_photon_histories_match_oracle(case):
+    kw = dict(no_photons=1500, save_all_photons=True, clump_tau0=10.0)
+    kw.update(CLUMP_CASES[case])
+    mg, mo = clump_model(**kw), clump_model(**kw)
+    run_gpu(mg, pool_slots=512, quantum=3)
+    oracle.run(mo, rng_mode=1)
+    same = histories_equal(mg, mo, geom_rtol=1e-6)
+    tallies_close(mg, mo, same.mean())
+    assert mg.counters["n_photons_done"] == 1500 and mg.nscatt_gas > 0
+
+
+def test_clump_run_statistics_and_scheduling():
+    """Results do not depend on the pool size; escape fraction exp(-f_cov) for opaque clumps."""
+    n = 30000
+    kw = dict(no_photons=n, clump_f_cov=1.0, clump_radius=0.02, clump_tau0=1e4, spectral_type="monochromatic", nxfreq=121,
+              xfreq_min=-30.0, xfreq_max=30.0, save_all_photons=True, iseed=21, xs_point=1e-9)
+    a = run_gpu(clump_model(**kw), pool_slots=256, quantum=2)
+    b = run_gpu(clump_model(**kw), pool_slots=8192, quantum=64)
+    assert np.allclose(a.allph("nscatt_gas"), b.allph("nscatt_gas"), rtol=1e-12)
+    assert np.allclose(a.spectrum("Jout"), b.spectrum("Jout"), rtol=1e-10)
+    ns = a.allph("nscatt_gas")
+    assert (ns == 0).mean() == pytest.approx(np.exp(-1.0), rel=0.06)
+    assert a.spectrum("Jout").sum() == pytest.approx(n, rel=2e-3)
+
+
+def test_clump_errors():
+    from lart_b200 import LartError
+    bad = clump_model()
+    bad.config.contents.clumps.has_overlap = 1
+    with pytest.raises(LartError, match="overlap"):
+        Simulation(bad)
+    m = clump_model(use_clump_medium=False, rmax=1.0)
+    sim = Simulation(m, pool_slots=64)
+    with pytest.raises(LartError, match="clump"):
+        sim.clump_locate([0.0], [0.0], [0.0])
+    sim.close()

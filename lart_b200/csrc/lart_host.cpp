@@ -679,7 +679,9 @@ int grid_create(lart_host_model *m) {
   if (p.N_gashomo <= 0.0) p.N_gashomo = N_gashomo;
   // (3) velocity field :786-920 — analytic types only, assigned where rhokap > 0
   const std::string &vt = p.velocity_type;
-  if (vt == "hubble" || vt == "power_law" || vt == "constant_radial" || vt == "parallel_velocity") {
+  if (p.use_clump_medium) {
+    // the box of a clump medium carries no bulk velocity (grid_mod_clump.f90:97-99); velocity_type belongs to the clumps
+  } else if (vt == "hubble" || vt == "power_law" || vt == "constant_radial" || vt == "parallel_velocity") {
     p.rpeak = (p.rmax <= 0.0) ? std::max({p.xmax, p.ymax, p.zmax}) : p.rmax;
     const double vth = m->vtherm_total(p.temperature);
     for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {

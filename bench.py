@@ -52,6 +52,13 @@ WORKLOADS = {
     # par%xy_periodic with nx, ny > 1: configs[0]'s slab as a 3-D periodic box (the _xyper ray tracers)
     "box_periodic_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xy_periodic=True, geometry="rectangle",
                                 nx=64, ny=64, nz=201, xmax=0.32, ymax=0.32, zmax=1.0),
+    # BASELINE configs[3] family (examples/clump_sphere/clump_NHI18_fcov5.in): 7.4e6 spherical clumps of radius 1e-3 in a
+    # shell 0.1 < r < 1, N_HI = 1e18 along a radial sight line, flat rotation curve, four observers' peel cubes reduced to one
+    "clump_sphere_fcov5": dict(use_clump_medium=True, rmax=1.0, rmin=0.1, clump_fully_inside=False, clump_radius=0.001,
+                               clump_f_cov=5.0, N_HImax=1e18, temperature=1e4, clump_sigma_v=0.0, spectral_type="monochromatic",
+                               geometry="sphere", velocity_type="rotating_galaxy_halo", Vrot=300.0, rinner=0.1, nxfreq=500,
+                               velocity_min=-1000.0, velocity_max=1000.0, nx=11, ny=11, nz=11, save_Jmu=True, nmu=101,
+                               nxim=129, nyim=129, distance=1e4),
     # small case for smoke-testing the bench itself
     "tiny": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=61, nxim=33, nyim=33),
 }
@@ -257,7 +264,7 @@ def run_gpu(args):
     walk_n = stage["trace"][1] + stage["peel"][1]
     steps_local = c["n_cellsteps"]
     flops = 50.0 * steps_local + 300.0 * c["n_scatter"]
-    mono = bool(args.flags & 4)
+    mono = bool(args.flags & 4) or bool(cfg.par.use_clump_medium)  # the clump medium runs on the one-thread-per-photon driver
     # Dominant kernel = the scatter stage.  Its algorithmic HBM bytes per scattering: the photon
     # record is read and written once (22 f64 + id + block counter + 4 i32 = 208 B each way) and one 144-B peel-ray
     # descriptor is written per observer.
@@ -270,7 +277,7 @@ def run_gpu(args):
     if os.path.exists(tpath) and not mono:
         tj = json.load(open(tpath))  # profiled at tj["pool_slots"] scatterings per launch; scale to this run's launch
         traffic = tj["k_wf_scatter_bytes_per_launch"] / tj["pool_slots"] * (c["n_scatter"] / max(sc_n, 1))
-    roof = {"bound": "hbm", "kernel": "k_wf_scatter" if not mono else "k_mono",
+    roof = {"bound": "hbm", "kernel": "k_wf_scatter" if not mono else ("k_mono_clump" if cfg.par.use_clump_medium else "k_mono"),
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
             "peak_source": peak_src, "bytes_per_scattering": bytes_per_scatter,
             "scatterings_per_launch": c["n_scatter"] / max(sc_n, 1), "avg_launch_ms": sc_ms / max(sc_n, 1),
@@ -332,7 +339,7 @@ def run_gpu(args):
                        "peel_cube": [g.nxfreq, cfg.observers[0].nxim, cfg.observers[0].nyim] if cfg.par.nobs else None,
                        "photons_in_flight_per_gpu": S, "quantum": args.quantum,
                        "step": "every photon slot advances by `quantum` scatterings (waves of emit/trace/scatter/peel kernels)",
-                       "driver": "monolithic" if args.flags & 4 else "wavefront",
+                       "driver": "monolithic" if mono else "wavefront",
                        "l2": "working set (cells %.0f MB + photon pool + ray queue + cubes) larger than the 126 MB L2; no flush"
                              % (64.0 * ncell / 1e6),
                        "parallelism": "photon ids strided over %d GPU(s); grid replicated; one NCCL reduce of the tally buffer" % world,

@@ -422,7 +422,6 @@ __global__ void __launch_bounds__(kBlock) k_mono_clump(const __grid_constant__ D
         rng.start(P.seed, (unsigned long long)ph.id);
         rng_valid = true;
         generate_photon(P, ph, rng, cnt, cs);
-        if (P.save_all_photons) record_initial(P, ph);
         icl = clump_at_point(C, ph.x, ph.y, ph.z);  // the birth clump, before the direct peel (generate_photon.f90:325-332)
         CellData csp = cs;
         if (icl > 0) {
@@ -431,6 +430,7 @@ __global__ void __launch_bounds__(kBlock) k_mono_clump(const __grid_constant__ D
           const double ratio = cp.Dfreq / C.Dfreq_ref;
           csp.vfx = DMUL(cp.vx, ratio); csp.vfy = DMUL(cp.vy, ratio); csp.vfz = DMUL(cp.vz, ratio);
         }
+        if (P.save_all_photons) record_initial(P, ph);
         if (P.save_peeloff) {
           for (int i = 0; i < P.nobs; ++i) {
             PeelRay pr;

@@ -82,6 +82,20 @@ def test_clump_run_statistics_and_scheduling():
     assert a.spectrum("Jout").sum() == pytest.approx(n, rel=2e-3)
 
 
+def test_clump_known_answer_reference_log():
+    """examples/clump_sphere/log_back:4-55 (clump_NHI18_fcov1, 1e6 photons): Average Number of scattering 4.3454E+03.
+    Four GPU runs with different seeds gave 4266.6, 4292.7, 4329.1, 4323.0 (each +-0.53 %): mean 4303 +- 11 against the
+    logged 4345 +- 23, i.e. -1.0 % = 1.7 sigma.  One run here: 3 sigma of the combined single-run error = 2.3 %."""
+    from test_oracle_clumps import LOGGED_FCOV1
+    from lart_b200 import Model
+    n = 1000000
+    m = Model(no_photons=n, iseed=2027, **LOGGED_FCOV1).setup()
+    run_gpu(m)
+    assert m.counters["n_photons_done"] == n
+    assert m.nscatt_gas / n == pytest.approx(4.3454e3, rel=0.023)
+    assert m.spectrum("Jout").sum() == pytest.approx(n, rel=1e-6)  # no dust, 500 bins over +-1000 km/s: nothing is lost
+
+
 def test_clump_errors():
     from lart_b200 import LartError
     bad = clump_model()

@@ -159,3 +159,29 @@ def test_clump_run_conserves_photons_and_escape_fraction():
     assert (ns == 0).mean() == pytest.approx(np.exp(-fcov), rel=0.08)
     assert jout[len(jout) // 2] / n > np.exp(-fcov) * 0.95  # they all sit in the central bin
     assert ns[ns > 0].mean() > 10  # surface scatterings off opaque clumps
+
+
+LOGGED_FCOV1 = dict(use_clump_medium=True, rmax=1.0, clump_radius=0.001, clump_f_cov=1.0, N_HImax=1e18, temperature=1e4,
+                    clump_sigma_v=0.0, spectral_type="monochromatic", geometry="sphere", velocity_type="rotating_galaxy_halo",
+                    Vrot=300.0, rinner=0.1, nxfreq=500, velocity_min=-1000.0, velocity_max=1000.0, nx=11, ny=11, nz=11,
+                    nxim=0, nyim=0)
+
+
+def test_setup_scalars_clump_sphere_log():
+    """The reference's own log of this input — examples/clump_sphere/log_back:4-55 (clump_NHI18_fcov1)."""
+    m = Model(no_photons=1000, iseed=5, **LOGGED_FCOV1).setup()
+    c = m.config.contents.clumps
+    assert c.n == 1333333                                                      # log_back:11
+    assert c.rhokap[0] == pytest.approx(4.4261e7, rel=2e-5)                    # :14
+    assert c.voigt_a[0] == pytest.approx(0.00047, abs=5e-6)                    # :15
+    assert c.Dfreq_ref == pytest.approx(1.0566e11, rel=5e-5)                   # :16
+    assert c.cgx == 111                                                        # :21 "in 111^3 cells"
+    nreg = np.ctypeslib.as_array(c.cg_start, shape=(c.cgx ** 3 + 1,))[-1] - 1
+    assert nreg == pytest.approx(1827254, rel=5e-3)                            # :21 (another random layout)
+    assert m.summary.tauhomo == pytest.approx(5.89826e4, rel=2e-6)             # :22
+    assert m.summary.N_gashomo == pytest.approx(1.0e18, rel=1e-5)              # :24
+    assert m.summary.vtherm == pytest.approx(12.84424, rel=1e-6)               # :37
+    # <N_scatt> = 4.3454E+03 with 1e6 photons (:52) is checked on the GPU (tests/test_gpu_clumps.py); the distribution is
+    # heavy-tailed (sigma/mean = 5.4), so a CPU-sized sample can only bracket it
+    oracle.run(m, rng_mode=0)
+    assert 2.5e3 < m.nscatt_gas / 1000 < 7e3

@@ -64,7 +64,9 @@ def test_clump_photon_histories_match_oracle(case):
     run_gpu(mg, pool_slots=512, quantum=3)
     oracle.run(mo, rng_mode=1)
     same = histories_equal(mg, mo, geom_rtol=1e-6)
-    tallies_close(mg, mo, same.mean())
+    # Stokes vectors drift by ~1e-8 over hundreds of scatterings (FMA contraction differs from the CPU's): the signed Q/U cubes
+    # are compared at that level
+    tallies_close(mg, mo, min(same.mean(), 1.0 - 1e-8))
     assert mg.counters["n_photons_done"] == 1500 and mg.nscatt_gas > 0
 
 

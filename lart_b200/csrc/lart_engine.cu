@@ -393,11 +393,12 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   Counters cnt;
   ctr_t nrng = 0;
-  if (s < pl.n) {
+  const bool valid = s < pl.n;  // lanes beyond the pool run the loop idle: every lane of a warp must reach the joins
+  {
     Photon ph;
     Rng rng;
     int icl = 0;
-    ph.flags = pl.flags[s];
+    ph.flags = valid ? pl.flags[s] : 0;
     bool rng_valid = false, touched = false;
     if (ph.flags & PH_ALIVE) {
       load_trace_part(pl, s, ph);
@@ -413,94 +414,114 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
       cnt.cellsteps += nc; cnt.peel += 1;
       peel_deposit(P, pr, t, __activemask());
     };
+    // Every lane runs the same `quantum` iterations through the same three phases and the warp is re-joined between
+    // them (lanes without work idle through).  ncu: 4.95 of 32 threads active per issued instruction — the joins alone
+    // do not cure that (2.96e8 -> 2.99e8 scatterings/s): most scatterings happen deep inside an opaque clump (no CSR
+    // cell at all), a few lanes per iteration cross hundreds of cells.  The cure is the wavefront split with a
+    // per-lane-refilled walker stepping one CSR cell at a time.
+    const unsigned FULLW = 0xffffffffu;
     for (int ev = 0; ev < quantum; ++ev) {
       CellData cs;
-      if (!(ph.flags & PH_ALIVE)) {
-        if (job->next >= job->count) break;
+      // ---- phase 1: refill a dead slot from the job queue; direct peel-off of the new photon
+      bool fresh = false;
+      CellData csp0;
+      if (valid && !(ph.flags & PH_ALIVE) && job->next < job->count) {
         unsigned long long j = atomicAdd(&job->next, 1ULL);
-        if (j >= job->count) break;
+        if (j < job->count) {
+          fresh = true;
+          touched = true;
+          ph.id = job->first_id + (long long)j * job->stride;
+          if (rng_valid) nrng += rng.nrng;
+          rng.start(P.seed, (unsigned long long)ph.id);
+          rng_valid = true;
+          generate_photon(P, ph, rng, cnt, cs);
+          icl = clump_at_point(C, ph.x, ph.y, ph.z);  // the birth clump, before the direct peel (generate_photon.f90:325-332)
+          csp0 = cs;
+          if (icl > 0) {
+            const ClumpPhys cp = load_clump(C, icl);
+            ph.xfreq = DSUB(ph.xfreq, ulos_clump(P, cp, ph.kx, ph.ky, ph.kz));
+            const double ratio = cp.Dfreq / C.Dfreq_ref;
+            csp0.vfx = DMUL(cp.vx, ratio); csp0.vfy = DMUL(cp.vy, ratio); csp0.vfz = DMUL(cp.vz, ratio);
+          }
+          if (P.save_all_photons) record_initial(P, ph);
+        }
+      }
+      __syncwarp(FULLW);
+      if (fresh && P.save_peeloff) {
+        for (int i = 0; i < P.nobs; ++i) {
+          PeelRay pr;
+          if (!peel_direct_prepare(P, P.obs[i], i, ph, csp0, pr, icl > 0)) continue;
+          trace_and_deposit(pr);
+        }
+      }
+      __syncwarp(FULLW);
+      // ---- phase 2: optical depth of the next flight, flight
+      const bool live = (ph.flags & PH_ALIVE) != 0;
+      bool inside = false;
+      if (live) {
         touched = true;
-        ph.id = job->first_id + (long long)j * job->stride;
-        if (rng_valid) nrng += rng.nrng;
-        rng.start(P.seed, (unsigned long long)ph.id);
-        rng_valid = true;
-        generate_photon(P, ph, rng, cnt, cs);
-        icl = clump_at_point(C, ph.x, ph.y, ph.z);  // the birth clump, before the direct peel (generate_photon.f90:325-332)
+        double tau;
+        if (ph.flags & PH_FIRST) {  // forced first scattering: the uncapped edge walk (setup.f90:809)
+          int ci, cj, ck, nc = 0, ncl = 0;
+          clamp_cell_for_read(P, ph, ci, cj, ck);
+          load_cell(P, ci, cj, ck, cs);
+          double tau0 = clump_walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, -1.0, nc, ncl);
+          cnt.cellsteps += nc;
+          tau = forced_first(P, ph, rng, cs, tau0);
+        } else {
+          tau = -log(rng.uniform());
+        }
+        int nc = 0;
+        inside = clump_walk_tau(P, vtab, ph, icl, tau, nc);
+        cnt.cellsteps += nc;
+        if (!inside) {  // left the sphere (raytrace_clump.f90:137-146, 151-160, 182-192)
+          ph.flags &= ~PH_ALIVE;
+          ph.xfreq_ref = ph.xfreq;  // upstream leaves photon%xfreq_ref unset on this path; Jout is binned with xfreq
+          retire_photon(P, ph, true, job, cnt);
+        }
+      }
+      __syncwarp(FULLW);
+      // ---- phase 3: scattering inside clump icl — scattering_car.f90:72-87
+      if (live && inside) {
+        cnt.scatter += 1;
+        load_cell(P, ph.ic, ph.jc, ph.kc, cs);  // the box: no opacity, no bulk velocity, reference Doppler width
+        const ClumpPhys cp = load_clump(C, icl);
+        const double ratio = cp.Dfreq / C.Dfreq_ref, scale = C.Dfreq_ref / cp.Dfreq;
         CellData csp = cs;
-        if (icl > 0) {
-          const ClumpPhys cp = load_clump(C, icl);
-          ph.xfreq = DSUB(ph.xfreq, ulos_clump(P, cp, ph.kx, ph.ky, ph.kz));
-          const double ratio = cp.Dfreq / C.Dfreq_ref;
-          csp.vfx = DMUL(cp.vx, ratio); csp.vfy = DMUL(cp.vy, ratio); csp.vfz = DMUL(cp.vz, ratio);
+        csp.vfx = DMUL(cp.vx, ratio); csp.vfy = DMUL(cp.vy, ratio); csp.vfz = DMUL(cp.vz, ratio);
+        bool to_dust = false;
+        if (P.dust) {
+          double pd = cp.rhokapD / (cp.rhokap * voigt_seon2(vtab, DMUL(ph.xfreq, scale), cp.voigt_a) + cp.rhokapD);
+          to_dust = rng.uniform() <= pd;
         }
-        if (P.save_all_photons) record_initial(P, ph);
-        if (P.save_peeloff) {
-          for (int i = 0; i < P.nobs; ++i) {
-            PeelRay pr;
-            if (!peel_direct_prepare(P, P.obs[i], i, ph, csp, pr, icl > 0)) continue;
-            trace_and_deposit(pr);
-          }
+        if (to_dust) {
+          scatter_dust(P, ph, rng, cs, cnt, [&]() {
+            for (int i = 0; i < P.nobs; ++i) {
+              PeelRay pr;
+              bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[i], i, ph, csp, pr)
+                                     : peel_dust_nostokes_prepare(P, P.obs[i], i, ph, csp, pr);
+              if (ok) trace_and_deposit(pr);
+            }
+          });
+          if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
+        } else {  // do_resonance1_clump — line_clump_mod.f90:29-58
+          const double scale_inv = 1.0 / scale;
+          const double xloc = ph.xfreq * scale;
+          const double uz_loc = rand_resonance_vz(rng, xloc, cp.voigt_a, cnt.reject);
+          const double xfreq_atom = (xloc - uz_loc) * scale_inv, uz = uz_loc * scale_inv;
+          CellData css = cs;
+          css.Dfreq = cp.Dfreq;  // recoil uses the clump's Doppler width (scattering_car.f90:428-433)
+          scatter_resonance_core<true>(P, ph, rng, css, cnt, uz, xfreq_atom, ratio, [&](double xa, double ux, double uy, double uzz) {
+            for (int i = 0; i < P.nobs; ++i) {
+              PeelRay pr;
+              bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[i], i, ph, csp, xa, ux, uy, uzz, pr)
+                                     : peel_resonance_nostokes_prepare(P, P.obs[i], i, ph, csp, xa, ux, uy, uzz, pr);
+              if (ok) trace_and_deposit(pr);
+            }
+          });
         }
       }
-      touched = true;
-      double tau;
-      if (ph.flags & PH_FIRST) {  // forced first scattering: the uncapped edge walk (setup.f90:809)
-        int ci, cj, ck, nc = 0, ncl = 0;
-        clamp_cell_for_read(P, ph, ci, cj, ck);
-        load_cell(P, ci, cj, ck, cs);
-        double tau0 = clump_walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, -1.0, nc, ncl);
-        cnt.cellsteps += nc;
-        tau = forced_first(P, ph, rng, cs, tau0);
-      } else {
-        tau = -log(rng.uniform());
-      }
-      int nc = 0;
-      if (!clump_walk_tau(P, vtab, ph, icl, tau, nc)) {  // left the sphere (raytrace_clump.f90:137-146, 151-160, 182-192)
-        cnt.cellsteps += nc;
-        ph.flags &= ~PH_ALIVE;
-        ph.xfreq_ref = ph.xfreq;  // upstream leaves photon%xfreq_ref unset on this path; Jout is binned with xfreq
-        retire_photon(P, ph, true, job, cnt);
-        continue;
-      }
-      cnt.cellsteps += nc;
-      // scattering inside clump icl — scattering_car.f90:72-87
-      cnt.scatter += 1;
-      load_cell(P, ph.ic, ph.jc, ph.kc, cs);  // the box: no opacity, no bulk velocity, reference Doppler width
-      const ClumpPhys cp = load_clump(C, icl);
-      const double ratio = cp.Dfreq / C.Dfreq_ref, scale = C.Dfreq_ref / cp.Dfreq;
-      CellData csp = cs;
-      csp.vfx = DMUL(cp.vx, ratio); csp.vfy = DMUL(cp.vy, ratio); csp.vfz = DMUL(cp.vz, ratio);
-      bool to_dust = false;
-      if (P.dust) {
-        double pd = cp.rhokapD / (cp.rhokap * voigt_seon2(vtab, DMUL(ph.xfreq, scale), cp.voigt_a) + cp.rhokapD);
-        to_dust = rng.uniform() <= pd;
-      }
-      if (to_dust) {
-        scatter_dust(P, ph, rng, cs, cnt, [&]() {
-          for (int i = 0; i < P.nobs; ++i) {
-            PeelRay pr;
-            bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[i], i, ph, csp, pr)
-                                   : peel_dust_nostokes_prepare(P, P.obs[i], i, ph, csp, pr);
-            if (ok) trace_and_deposit(pr);
-          }
-        });
-        if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
-      } else {  // do_resonance1_clump — line_clump_mod.f90:29-58
-        const double scale_inv = 1.0 / scale;
-        const double xloc = ph.xfreq * scale;
-        const double uz_loc = rand_resonance_vz(rng, xloc, cp.voigt_a, cnt.reject);
-        const double xfreq_atom = (xloc - uz_loc) * scale_inv, uz = uz_loc * scale_inv;
-        CellData css = cs;
-        css.Dfreq = cp.Dfreq;  // recoil uses the clump's Doppler width (scattering_car.f90:428-433)
-        scatter_resonance_core<true>(P, ph, rng, css, cnt, uz, xfreq_atom, ratio, [&](double xa, double ux, double uy, double uzz) {
-          for (int i = 0; i < P.nobs; ++i) {
-            PeelRay pr;
-            bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[i], i, ph, csp, xa, ux, uy, uzz, pr)
-                                   : peel_resonance_nostokes_prepare(P, P.obs[i], i, ph, csp, xa, ux, uy, uzz, pr);
-            if (ok) trace_and_deposit(pr);
-          }
-        });
-      }
+      __syncwarp(FULLW);
     }
     if (touched) {
       int fl = ph.flags;
@@ -1491,7 +1512,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   if (P.clump) h->flags |= LART_FLAG_MONOLITHIC;  // the clump medium runs on the one-thread-per-photon driver for now
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int S = cfg->pool_slots;
-  if (S <= 0) S = mono ? h->nsm * 2048 : h->nsm * 16384;
+  if (S <= 0) S = P.clump ? h->nsm * 8192 : (mono ? h->nsm * 2048 : h->nsm * 16384);  // clumps: 2.75e8 / 2.85e8 / 2.96e8 scatterings/s at 2048 / 4096 / 8192 per SM
   {
     // keep the ray queue below ~3 GB when many observers are configured
     long long per_slot = (long long)(2 * sizeof(PeelRay) + 4 * sizeof(PeelCont)) * std::max(1, P.nobs);

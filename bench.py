@@ -264,7 +264,7 @@ def run_gpu(args):
     walk_n = stage["trace"][1] + stage["peel"][1]
     steps_local = c["n_cellsteps"]
     flops = 50.0 * steps_local + 300.0 * c["n_scatter"]
-    mono = bool(args.flags & 4) or bool(cfg.par.use_clump_medium)  # the clump medium runs on the one-thread-per-photon driver
+    mono = bool(args.flags & 4)
     # Dominant kernel = the scatter stage.  Its algorithmic HBM bytes per scattering: the photon
     # record is read and written once (22 f64 + id + block counter + 4 i32 = 208 B each way) and one 144-B peel-ray
     # descriptor is written per observer.
@@ -277,7 +277,8 @@ def run_gpu(args):
     if os.path.exists(tpath) and not mono:
         tj = json.load(open(tpath))  # profiled at tj["pool_slots"] scatterings per launch; scale to this run's launch
         traffic = tj["k_wf_scatter_bytes_per_launch"] / tj["pool_slots"] * (c["n_scatter"] / max(sc_n, 1))
-    roof = {"bound": "hbm", "kernel": "k_wf_scatter" if not mono else ("k_mono_clump" if cfg.par.use_clump_medium else "k_mono"),
+    clump = bool(cfg.par.use_clump_medium)
+    roof = {"bound": "hbm", "kernel": ("k_cl_scatter" if clump else "k_wf_scatter") if not mono else ("k_mono_clump" if clump else "k_mono"),
             "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
             "peak_source": peak_src, "bytes_per_scattering": bytes_per_scatter,
             "scatterings_per_launch": c["n_scatter"] / max(sc_n, 1), "avg_launch_ms": sc_ms / max(sc_n, 1),

@@ -53,48 +53,6 @@ LART_DEV ClumpPhys load_clump(const DevClumps &C, int icl) {
 }
 LART_DEV int cg_clamp(double p, double lo, double inv, int n) { return max(0, min(n - 1, (int)DMUL(DSUB(p, lo), inv))); }
 
-// find_next_clump — clump_mod.f90:1393-1506: Amanatides-Woo walk through the CSR grid, ray-sphere test of every
-// clump registered in the cell, nearest entry wins; stops once the cell starts beyond the best hit or t_max.
-LART_DEV bool find_next_clump(const DevClumps &C, double xp, double yp, double zp, double kx, double ky, double kz, int skip_icl,
-                              double t_max, double &t_entry, int &icl_found, int &ncells) {
-  double best_te = kHugest, d = 0.0;
-  int best_icl = 0;
-  int ci = cg_clamp(xp, C.xmin, C.inv_dx, C.cgx), cj = cg_clamp(yp, C.ymin, C.inv_dy, C.cgy), ck = cg_clamp(zp, C.zmin, C.inv_dz, C.cgz);
-  int si, sj, sk;
-  double tx, ty, tz, delx, dely, delz;
-  auto axis = [](double k, double p, int cc, double lo, double dd, int &st, double &t, double &del) {
-    if (k > 0.0) { st = 1; t = DSUB(DADD(lo, DMUL((double)(cc + 1), dd)), p) / k; del = dd / k; }
-    else if (k < 0.0) { st = -1; t = DSUB(DADD(lo, DMUL((double)cc, dd)), p) / k; del = -dd / k; }
-    else { st = 0; t = kHugest; del = kHugest; }
-  };
-  axis(kx, xp, ci, C.xmin, C.dx, si, tx, delx);
-  axis(ky, yp, cj, C.ymin, C.dy, sj, ty, dely);
-  axis(kz, zp, ck, C.zmin, C.dz, sk, tz, delz);
-  for (;;) {
-    if (d > best_te || d > t_max) break;
-    ++ncells;
-    const size_t icell = (size_t)ci + (size_t)C.cgx * ((size_t)cj + (size_t)C.cgy * (size_t)ck);
-    const int p0 = __ldg(C.cg_start + icell), p1 = __ldg(C.cg_start + icell + 1);
-    for (int ip = p0; ip < p1; ++ip) {
-      const int icl = __ldg(C.cg_list + ip - 1);
-      if (icl == skip_icl) continue;
-      const double4 g = ldg4(C.geo + icl - 1);
-      const double rx = DSUB(xp, g.x), ry = DSUB(yp, g.y), rz = DSUB(zp, g.z);
-      const double b = DADD(DADD(DMUL(rx, kx), DMUL(ry, ky)), DMUL(rz, kz));
-      double disc = DADD(DSUB(DMUL(b, b), DADD(DADD(DMUL(rx, rx), DMUL(ry, ry)), DMUL(rz, rz))), g.w);
-      if (disc < 0.0) continue;
-      disc = sqrt(disc);
-      const double te = DSUB(-b, disc), tx2 = DADD(-b, disc);
-      if (tx2 > 0.0 && te < best_te) { best_te = te; best_icl = icl; }  // (te > 0 .or. icl /= skip) holds: icl /= skip here
-    }
-    if (tx <= ty && tx <= tz) { d = tx; ci += si; if (ci < 0 || ci >= C.cgx) break; tx = DADD(tx, delx); }
-    else if (ty <= tz) { d = ty; cj += sj; if (cj < 0 || cj >= C.cgy) break; ty = DADD(ty, dely); }
-    else { d = tz; ck += sk; if (ck < 0 || ck >= C.cgz) break; tz = DADD(tz, delz); }
-  }
-  if (best_icl > 0 && best_te <= t_max) { t_entry = best_te; icl_found = best_icl; return true; }
-  return false;
-}
-
 // active_set_at_point, first hit — clump_mod.f90:1595-1634
 LART_DEV int clump_at_point(const DevClumps &C, double xp, double yp, double zp) {
   const int ci = cg_clamp(xp, C.xmin, C.inv_dx, C.cgx), cj = cg_clamp(yp, C.ymin, C.inv_dy, C.cgy), ck = cg_clamp(zp, C.zmin, C.inv_dz, C.cgz);
@@ -120,89 +78,160 @@ LART_DEV void update_cell_idx(const DevParams &P, Photon &ph) {
   ph.kc = max(1, min(P.nz, (int)floor(DSUB(ph.z, P.zmin) / P.dz) + 1));
 }
 
-// raytrace_to_edge_clump (:205-270; tau_max <= 0) and raytrace_to_edge_clump_capped (:494-533)
-LART_DEV double clump_walk_edge(const DevParams &P, const double *vtab, double xp, double yp, double zp, double kx, double ky,
-                                double kz, double xfreq, int icl_cur, double tau_max, int &ncells, int &nclumps) {
-  const DevClumps &C = P.cl;
-  const bool capped = tau_max > 0.0;
-  double tau = 0.0;
-  if (icl_cur > 0) {
-    const ClumpPhys cp = load_clump(C, icl_cur);
-    const double t_seg = clump_exit_dist(C, xp, yp, zp, kx, ky, kz, icl_cur);
-    tau = DADD(tau, DMUL(kappa_clump(P, vtab, cp, xfreq), t_seg));
-    ++nclumps;
-    if (capped && tau >= tau_max) return tau;
-    xp = DADD(xp, DMUL(t_seg, kx)); yp = DADD(yp, DMUL(t_seg, ky)); zp = DADD(zp, DMUL(t_seg, kz));
-    xfreq = DADD(xfreq, ulos_clump(P, cp, kx, ky, kz));
-    if (outside_sphere(C, xp, yp, zp)) return tau;
+// ---------------------------------------------------------------------------
+// The two ray tracers as one resumable state machine.  A step is either one clump segment, the set-up of a search, or
+// ONE cell of the CSR walk of find_next_clump — so that the lanes of a warp, each on its own ray, stay in step and can
+// be refilled one by one (k_cl_flight, k_cl_peel).  Arithmetic and its order are those of clump_mod.f90:1393-1506 and
+// raytrace_clump.f90:83-270, 494-533; running the machine to completion IS raytrace_to_edge_clump / _to_tau_clump.
+// ---------------------------------------------------------------------------
+enum { CW_CLUMP = 1, CW_FIND = 2, CW_CELL = 3 };
+struct ClumpWalk {
+  double x, y, z, kx, ky, kz;  // start of the current segment or search; direction
+  double xfreq;                // in the current clump's frame while inside one, else in the box frame
+  double tau;                  // edge walk: accumulated depth; tau walk: depth still to go
+  double t_sp;                 // distance to the bounding sphere for the current search
+  double tx, ty, tz, delx, dely, delz, d, best_te;
+  int ci, cj, ck, si, sj, sk;
+  int best_icl, skip_icl, icl;  // icl = clump the ray is in (CW_CLUMP)
+  int phase, ncells, nclumps;
+};
+LART_DEV void cw_start(ClumpWalk &w, double x, double y, double z, double kx, double ky, double kz, double xfreq, int icl,
+                       double tau) {
+  w.x = x; w.y = y; w.z = z; w.kx = kx; w.ky = ky; w.kz = kz; w.xfreq = xfreq; w.tau = tau;
+  w.icl = icl; w.skip_icl = 0; w.ncells = 0; w.nclumps = 0;
+  w.phase = icl > 0 ? CW_CLUMP : CW_FIND;
+}
+LART_DEV void cw_advance(ClumpWalk &w, double t) {
+  w.x = DADD(w.x, DMUL(t, w.kx)); w.y = DADD(w.y, DMUL(t, w.ky)); w.z = DADD(w.z, DMUL(t, w.kz));
+}
+// CW_FIND: distance to the sphere, DDA set-up.  Returns false when the ray is already at the sphere (t_sp <= 0).
+LART_DEV bool cw_find_begin(const DevClumps &C, ClumpWalk &w) {
+  w.t_sp = sphere_exit_dist(C, w.x, w.y, w.z, w.kx, w.ky, w.kz);
+  if (w.t_sp <= 0.0) return false;
+  w.best_te = kHugest; w.best_icl = 0; w.d = 0.0;
+  w.ci = cg_clamp(w.x, C.xmin, C.inv_dx, C.cgx); w.cj = cg_clamp(w.y, C.ymin, C.inv_dy, C.cgy); w.ck = cg_clamp(w.z, C.zmin, C.inv_dz, C.cgz);
+  auto axis = [](double k, double p, int cc, double lo, double dd, int &st, double &t, double &del) {
+    if (k > 0.0) { st = 1; t = DSUB(DADD(lo, DMUL((double)(cc + 1), dd)), p) / k; del = dd / k; }
+    else if (k < 0.0) { st = -1; t = DSUB(DADD(lo, DMUL((double)cc, dd)), p) / k; del = -dd / k; }
+    else { st = 0; t = kHugest; del = kHugest; }
+  };
+  axis(w.kx, w.x, w.ci, C.xmin, C.dx, w.si, w.tx, w.delx);
+  axis(w.ky, w.y, w.cj, C.ymin, C.dy, w.sj, w.ty, w.dely);
+  axis(w.kz, w.z, w.ck, C.zmin, C.dz, w.sk, w.tz, w.delz);
+  w.phase = CW_CELL;
+  return true;
+}
+// CW_CELL: one cell of find_next_clump.  Returns true when the search is over (w.best_icl = 0: nothing before t_sp).
+LART_DEV bool cw_find_cell(const DevClumps &C, ClumpWalk &w) {
+  bool over = w.d > w.best_te || w.d > w.t_sp;
+  if (!over) {
+    ++w.ncells;
+    const size_t icell = (size_t)w.ci + (size_t)C.cgx * ((size_t)w.cj + (size_t)C.cgy * (size_t)w.ck);
+    const int p0 = __ldg(C.cg_start + icell), p1 = __ldg(C.cg_start + icell + 1);
+    for (int ip = p0; ip < p1; ++ip) {
+      const int icl = __ldg(C.cg_list + ip - 1);
+      if (icl == w.skip_icl) continue;
+      const double4 g = ldg4(C.geo + icl - 1);
+      const double rx = DSUB(w.x, g.x), ry = DSUB(w.y, g.y), rz = DSUB(w.z, g.z);
+      const double b = DADD(DADD(DMUL(rx, w.kx), DMUL(ry, w.ky)), DMUL(rz, w.kz));
+      double disc = DADD(DSUB(DMUL(b, b), DADD(DADD(DMUL(rx, rx), DMUL(ry, ry)), DMUL(rz, rz))), g.w);
+      if (disc < 0.0) continue;
+      disc = sqrt(disc);
+      const double te = DSUB(-b, disc), tx2 = DADD(-b, disc);
+      if (tx2 > 0.0 && te < w.best_te) { w.best_te = te; w.best_icl = icl; }
+    }
+    if (w.tx <= w.ty && w.tx <= w.tz) { w.d = w.tx; w.ci += w.si; if (w.ci < 0 || w.ci >= C.cgx) over = true; else w.tx = DADD(w.tx, w.delx); }
+    else if (w.ty <= w.tz) { w.d = w.ty; w.cj += w.sj; if (w.cj < 0 || w.cj >= C.cgy) over = true; else w.ty = DADD(w.ty, w.dely); }
+    else { w.d = w.tz; w.ck += w.sk; if (w.ck < 0 || w.ck >= C.cgz) over = true; else w.tz = DADD(w.tz, w.delz); }
   }
-  for (;;) {
-    const double t_sp = sphere_exit_dist(C, xp, yp, zp, kx, ky, kz);
-    if (t_sp <= 0.0) break;
-    double te;
-    int icl_found = 0;
-    if (!find_next_clump(C, xp, yp, zp, kx, ky, kz, icl_cur, t_sp, te, icl_found, ncells)) break;
-    te = fmax(0.0, te);
-    xp = DADD(xp, DMUL(te, kx)); yp = DADD(yp, DMUL(te, ky)); zp = DADD(zp, DMUL(te, kz));
-    const ClumpPhys cp = load_clump(C, icl_found);
-    const double u_los = ulos_clump(P, cp, kx, ky, kz);
-    xfreq = DSUB(xfreq, u_los);
-    const double t_seg = clump_exit_dist(C, xp, yp, zp, kx, ky, kz, icl_found);
-    tau = DADD(tau, DMUL(kappa_clump(P, vtab, cp, xfreq), t_seg));
-    ++nclumps;
-    if (capped && tau >= tau_max) return tau;
-    xp = DADD(xp, DMUL(t_seg, kx)); yp = DADD(yp, DMUL(t_seg, ky)); zp = DADD(zp, DMUL(t_seg, kz));
-    xfreq = DADD(xfreq, u_los);
-    icl_cur = icl_found;
-    if (outside_sphere(C, xp, yp, zp)) break;
-  }
-  return tau;
+  if (over && !(w.best_icl > 0 && w.best_te <= w.t_sp)) w.best_icl = 0;
+  return over;
+}
+// the search found clump best_icl: move to its entry point, shift into its frame (raytrace_clump.f90:168-180, 247-254)
+LART_DEV void cw_enter(const DevParams &P, ClumpWalk &w) {
+  cw_advance(w, fmax(0.0, w.best_te));
+  w.icl = w.best_icl;
+  const ClumpPhys cp = load_clump(P.cl, w.icl);
+  w.xfreq = DSUB(w.xfreq, ulos_clump(P, cp, w.kx, w.ky, w.kz));
+  w.phase = CW_CLUMP;
 }
 
-// raytrace_to_tau_clump — raytrace_clump.f90:83-201.  Returns true while the photon is inside (it then sits at its
-// next scattering point, in clump ph.icl); on escape ph.xfreq is the lab-frame frequency the caller bins into Jout.
-LART_DEV bool clump_walk_tau(const DevParams &P, const double *vtab, Photon &ph, int &icl, double tau_in, int &ncells) {
+// One step of raytrace_to_edge_clump(_capped).  Returns true when the walk is over; the depth is w.tau.
+LART_DEV bool cw_edge_step(const DevParams &P, const double *vtab, ClumpWalk &w, double tau_max) {
   const DevClumps &C = P.cl;
-  const double kx = ph.kx, ky = ph.ky, kz = ph.kz;
-  double tau_rem = tau_in;
-  int last_icl = 0;
-  for (;;) {
-    if (icl > 0) {
-      const ClumpPhys cp = load_clump(C, icl);
-      const double t_seg = clump_exit_dist(C, ph.x, ph.y, ph.z, kx, ky, kz, icl);
-      const double kap = kappa_clump(P, vtab, cp, ph.xfreq);
-      if (tau_rem <= DMUL(kap, t_seg)) {  // scatters inside this clump
-        const double ds = tau_rem / fmax(kap, kTinyDouble);
-        ph.x = DADD(ph.x, DMUL(ds, kx)); ph.y = DADD(ph.y, DMUL(ds, ky)); ph.z = DADD(ph.z, DMUL(ds, kz));
-        update_cell_idx(P, ph);
-        return true;
-      }
-      tau_rem = DSUB(tau_rem, DMUL(kap, t_seg));
-      ph.x = DADD(ph.x, DMUL(t_seg, kx)); ph.y = DADD(ph.y, DMUL(t_seg, ky)); ph.z = DADD(ph.z, DMUL(t_seg, kz));
-      ph.xfreq = DADD(ph.xfreq, ulos_clump(P, cp, kx, ky, kz));
-      last_icl = icl;
-      icl = 0;
-      if (outside_sphere(C, ph.x, ph.y, ph.z)) { update_cell_idx(P, ph); return false; }
-    } else {
-      const double t_sp = sphere_exit_dist(C, ph.x, ph.y, ph.z, kx, ky, kz);
-      if (t_sp <= 0.0) return false;
-      double te;
-      int icl_found = 0;
-      if (find_next_clump(C, ph.x, ph.y, ph.z, kx, ky, kz, last_icl, t_sp, te, icl_found, ncells)) {
-        te = fmax(0.0, te);
-        ph.x = DADD(ph.x, DMUL(te, kx)); ph.y = DADD(ph.y, DMUL(te, ky)); ph.z = DADD(ph.z, DMUL(te, kz));
-        const ClumpPhys cp = load_clump(C, icl_found);
-        ph.xfreq = DSUB(ph.xfreq, ulos_clump(P, cp, kx, ky, kz));
-        last_icl = 0;
-        icl = icl_found;
-        update_cell_idx(P, ph);
-      } else {
-        ph.x = DADD(ph.x, DMUL(t_sp, kx)); ph.y = DADD(ph.y, DMUL(t_sp, ky)); ph.z = DADD(ph.z, DMUL(t_sp, kz));
-        update_cell_idx(P, ph);
-        return false;
-      }
-    }
+  if (w.phase == CW_CLUMP) {
+    const ClumpPhys cp = load_clump(C, w.icl);
+    const double t_seg = clump_exit_dist(C, w.x, w.y, w.z, w.kx, w.ky, w.kz, w.icl);
+    w.tau = DADD(w.tau, DMUL(kappa_clump(P, vtab, cp, w.xfreq), t_seg));
+    ++w.nclumps;
+    if (tau_max > 0.0 && w.tau >= tau_max) return true;
+    cw_advance(w, t_seg);
+    w.xfreq = DADD(w.xfreq, ulos_clump(P, cp, w.kx, w.ky, w.kz));
+    w.skip_icl = w.icl;
+    if (outside_sphere(C, w.x, w.y, w.z)) return true;
+    w.phase = CW_FIND;
+    return false;
   }
+  if (w.phase == CW_FIND) return !cw_find_begin(C, w);
+  if (cw_find_cell(C, w)) {
+    if (w.best_icl == 0) return true;
+    cw_enter(P, w);
+  }
+  return false;
+}
+// One step of raytrace_to_tau_clump.  0 = keep going, 1 = at the next scattering point (inside clump w.icl),
+// 2 = left the sphere (w.xfreq is the box-frame frequency binned into Jout).
+LART_DEV int cw_tau_step(const DevParams &P, const double *vtab, ClumpWalk &w) {
+  const DevClumps &C = P.cl;
+  if (w.phase == CW_CLUMP) {
+    const ClumpPhys cp = load_clump(C, w.icl);
+    const double t_seg = clump_exit_dist(C, w.x, w.y, w.z, w.kx, w.ky, w.kz, w.icl);
+    const double kap = kappa_clump(P, vtab, cp, w.xfreq);
+    if (w.tau <= DMUL(kap, t_seg)) {  // scatters inside this clump
+      cw_advance(w, w.tau / fmax(kap, kTinyDouble));
+      return 1;
+    }
+    w.tau = DSUB(w.tau, DMUL(kap, t_seg));
+    cw_advance(w, t_seg);
+    w.xfreq = DADD(w.xfreq, ulos_clump(P, cp, w.kx, w.ky, w.kz));
+    w.skip_icl = w.icl;
+    w.icl = 0;
+    if (outside_sphere(C, w.x, w.y, w.z)) return 2;
+    w.phase = CW_FIND;
+    return 0;
+  }
+  if (w.phase == CW_FIND) return cw_find_begin(C, w) ? 0 : 2;
+  if (cw_find_cell(C, w)) {
+    if (w.best_icl == 0) { cw_advance(w, w.t_sp); return 2; }  // nothing ahead: to the sphere (:182-186)
+    cw_enter(P, w);
+    w.skip_icl = 0;
+  }
+  return 0;
+}
+
+// raytrace_to_edge_clump (:205-270; tau_max <= 0) and raytrace_to_edge_clump_capped (:494-533), run to completion
+LART_DEV double clump_walk_edge(const DevParams &P, const double *vtab, double xp, double yp, double zp, double kx, double ky,
+                                double kz, double xfreq, int icl_cur, double tau_max, int &ncells, int &nclumps) {
+  ClumpWalk w;
+  cw_start(w, xp, yp, zp, kx, ky, kz, xfreq, icl_cur, 0.0);
+  while (!cw_edge_step(P, vtab, w, tau_max)) {}
+  ncells += w.ncells; nclumps += w.nclumps;
+  return w.tau;
+}
+// raytrace_to_tau_clump — raytrace_clump.f90:83-201, run to completion.  Returns true while the photon is inside (it then
+// sits at its next scattering point, in clump icl); on escape ph.xfreq is the lab-frame frequency the caller bins into Jout.
+LART_DEV void cw_finish_tau(const DevParams &P, const ClumpWalk &w, int st, Photon &ph, int &icl) {
+  ph.x = w.x; ph.y = w.y; ph.z = w.z; ph.xfreq = w.xfreq; icl = (st == 1) ? w.icl : 0;
+  update_cell_idx(P, ph);  // (upstream skips this on its t_sp <= 0 exit; the cell of an escaped photon is never read)
+}
+LART_DEV bool clump_walk_tau(const DevParams &P, const double *vtab, Photon &ph, int &icl, double tau_in, int &ncells) {
+  ClumpWalk w;
+  cw_start(w, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, tau_in);
+  int st;
+  while ((st = cw_tau_step(P, vtab, w)) == 0) {}
+  ncells += w.ncells;
+  cw_finish_tau(P, w, st, ph, icl);
+  return st == 1;
 }
 
 }  // namespace lart

@@ -407,6 +407,9 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
       icl = pl.rc[s];
       rng_valid = true;
     }
+    // a slot the wavefront flight stage already flew to its next scattering point (driver switch in lart_gpu_run)
+    bool at_scatter = (ph.flags & PH_ALIVE) && (ph.flags & PH_SCATTER);
+    ph.flags &= ~PH_SCATTER;
     // peel-off toward every observer from the photon's current state; csp = grid record with the clump's bulk velocity
     auto trace_and_deposit = [&](PeelRay &pr) {
       int nc = 0, ncl = 0;
@@ -458,7 +461,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
       // ---- phase 2: optical depth of the next flight, flight
       const bool live = (ph.flags & PH_ALIVE) != 0;
       bool inside = false;
-      if (live) {
+      if (live && at_scatter) {
+        touched = true;
+        inside = true;
+        at_scatter = false;
+      } else if (live) {
         touched = true;
         double tau;
         if (ph.flags & PH_FIRST) {  // forced first scattering: the uncapped edge walk (setup.f90:809)
@@ -932,6 +939,258 @@ __global__ void k_wf_reset(Queues q) {  // start of a wave: new parity, empty ou
   const unsigned w = *q.wave + 1u;
   *q.wave = w;
   q.n_cont[(w & 1u) ^ 1u] = 0;
+}
+
+// ------------------------------ clump medium, wavefront ---------------------
+// The same four stages as the Cartesian wavefront driver.  The two walker stages (k_cl_flight, k_cl_peel) step the
+// resumable clump ray tracer (lart_clump.cuh) one CSR cell at a time and refill each lane on its own, so that the rare
+// ray that crosses hundreds of cells no longer idles the 31 other lanes of its warp for the whole of its walk
+// (k_mono_clump: 4.95 of 32 threads active per issued instruction).  No step budgets: a walk runs to its end.
+// The clump index of a slot lives in pl.rc[slot]; a peel ray carries it in PeelRay::ic.
+__global__ void __launch_bounds__(kBlock) k_cl_emit(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+  Counters cnt;
+  ctr_t nrng = 0;
+  for (int s = pl.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < pl.s0 + pl.n; s += gridDim.x * blockDim.x) {
+    if (pl.flags[s] & PH_ALIVE) continue;
+    if (job->next >= job->count) continue;
+    unsigned long long j = atomicAdd(&job->next, 1ULL);
+    if (j >= job->count) continue;
+    Photon ph;
+    Rng rng;
+    CellData cs;
+    ph.id = job->first_id + (long long)j * job->stride;
+    rng.start(P.seed, (unsigned long long)ph.id);
+    generate_photon(P, ph, rng, cnt, cs);
+    const int icl = clump_at_point(P.cl, ph.x, ph.y, ph.z);  // generate_photon.f90:325-332
+    if (icl > 0) {
+      const ClumpPhys cp = load_clump(P.cl, icl);
+      ph.xfreq = DSUB(ph.xfreq, ulos_clump(P, cp, ph.kx, ph.ky, ph.kz));
+      const double ratio = cp.Dfreq / P.cl.Dfreq_ref;
+      cs.vfx = DMUL(cp.vx, ratio); cs.vfy = DMUL(cp.vy, ratio); cs.vfz = DMUL(cp.vz, ratio);
+    }
+    if (P.save_all_photons) record_initial(P, ph);
+    if (P.save_peeloff) {
+      for (int i = 0; i < P.nobs; ++i) {
+        PeelRay pr;
+        if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr, icl > 0)) continue;
+        pr.ic = icl;
+        unsigned at = atomicAdd(q.n_direct, 1u);
+        if (at < q.direct_cap) ray_store(q.rays + q.direct_base + at, pr);
+      }
+    }
+    int fl = ph.flags;
+    store_rng(pl, s, rng, fl);
+    ph.flags = fl;
+    store_all(pl, s, ph);
+    pl.rc[s] = icl;
+    nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// stage 2: flights (forced first scattering included) of every alive slot that is not at a scattering point
+__global__ void __launch_bounds__(kBlock, 2) k_cl_flight(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  const unsigned FULL = 0xffffffffu;
+  Counters cnt;
+  ctr_t nrng = 0;
+  ClumpWalk w;
+  Photon ph;
+  Rng rng;
+  int slot = -1, mode = 0;  // mode 0: uncapped edge walk of the forced first scattering, 1: tau walk
+  bool have = false, exhausted = false;
+  CellData cs0;
+  for (;;) {
+    bool need = !have && !exhausted;
+    unsigned nm = __ballot_sync(FULL, need), hm = __ballot_sync(FULL, have);
+    if (nm && (__popc(nm) >= kRefillMin || !hm)) {
+      unsigned idx = reserve(q.head_trace, need);
+      if (need) {
+        if (idx >= (unsigned)pl.n) exhausted = true;
+        else if ((pl.flags[pl.s0 + idx] & (PH_ALIVE | PH_SCATTER)) == PH_ALIVE) {
+          slot = pl.s0 + (int)idx;
+          load_trace_part(pl, slot, ph);
+          load_rng(P, pl, slot, ph.id, ph.flags, rng);
+          const int icl = pl.rc[slot];
+          if (ph.flags & PH_FIRST) {
+            int ci, cj, ck;
+            clamp_cell_for_read(P, ph, ci, cj, ck);
+            load_cell(P, ci, cj, ck, cs0);
+            mode = 0;
+            cw_start(w, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, 0.0);
+          } else {
+            mode = 1;
+            cw_start(w, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, -log(rng.uniform()));
+          }
+          have = true;
+        }
+      }
+    }
+    if (!__any_sync(FULL, have)) {
+      if (!__any_sync(FULL, !exhausted)) break;
+      continue;
+    }
+    if (have) {
+      if (mode == 0) {
+        if (cw_edge_step(P, vtab, w, -1.0)) {  // tau0 known: escaped fraction, weight, first optical depth
+          cnt.cellsteps += w.ncells;
+          const double tau = forced_first(P, ph, rng, cs0, w.tau);
+          mode = 1;
+          cw_start(w, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, pl.rc[slot], tau);
+        }
+      } else {
+        const int st = cw_tau_step(P, vtab, w);
+        if (st != 0) {
+          int icl;
+          cnt.cellsteps += w.ncells;
+          cw_finish_tau(P, w, st, ph, icl);
+          if (st == 1) {
+            ph.flags |= PH_SCATTER;
+          } else {
+            load_rest(pl, slot, ph);
+            ph.flags &= ~PH_ALIVE;
+            ph.xfreq_ref = ph.xfreq;  // see k_mono_clump
+            retire_photon(P, ph, true, job, cnt);
+          }
+          store_trace_part(pl, slot, ph);
+          pl.rc[slot] = icl;
+          pl.ndraw[slot] = rng.nblk;
+          nrng += rng.nrng;
+          have = false;
+        }
+      }
+    }
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// stage 3: scattering inside the slot's clump; peel rays go to the slot's ray entries
+__global__ void __launch_bounds__(kBlock, 2) k_cl_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+  __shared__ double vtab[kVoigtTabN];
+  __shared__ VzWarpShared vzsh[kBlock / 32];
+  if (P.dust) load_vtab(P, vtab);
+  VzWarpShared &sh = vzsh[threadIdx.x >> 5];
+  Counters cnt;
+  ctr_t nrng = 0;
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int base = pl.s0 + blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < pl.s0 + pl.n; base += stride) {
+    const int s = base + lane;
+    const bool inb = s < pl.s0 + pl.n;
+    const int fl0 = inb ? pl.flags[s] : 0;
+    const bool active = (fl0 & PH_SCATTER) != 0;
+    PeelRay *myrays = q.rays + (size_t)(inb ? s : 0) * P.nobs;
+    if (inb && !active)
+      for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+    if (!__any_sync(0xffffffffu, active)) continue;
+    Photon ph;
+    Rng rng;
+    CellData cs, csp;
+    ClumpPhys cp;
+    int icl = 0;
+    double scale = 1.0, ratio = 1.0, xloc = 0.0, a_loc = 1.0;
+    bool to_dust = false;
+    if (active) {
+      load_trace_part(pl, s, ph);
+      ph.flags &= ~PH_SCATTER;
+      load_rng(P, pl, s, ph.id, ph.flags, rng);
+      load_cell(P, ph.ic, ph.jc, ph.kc, cs);  // the box: no opacity, no bulk velocity, reference Doppler width
+      icl = pl.rc[s];
+      cp = load_clump(P.cl, icl);
+      ratio = cp.Dfreq / P.cl.Dfreq_ref; scale = P.cl.Dfreq_ref / cp.Dfreq;
+      csp = cs;
+      csp.vfx = DMUL(cp.vx, ratio); csp.vfy = DMUL(cp.vy, ratio); csp.vfz = DMUL(cp.vz, ratio);
+      cnt.scatter += 1;
+      if (P.dust) {  // scattering_car.f90:72-87
+        double pd = cp.rhokapD / (cp.rhokap * voigt_seon2(vtab, DMUL(ph.xfreq, scale), cp.voigt_a) + cp.rhokapD);
+        to_dust = rng.uniform() <= pd;
+      }
+      xloc = ph.xfreq * scale; a_loc = cp.voigt_a;
+    } else {
+      rng.start(P.seed, 0ULL);
+    }
+    const bool resonant = active && !to_dust;
+    const double uz_loc = rand_resonance_vz_warp(sh, resonant, rng, xloc, a_loc, cnt.reject);  // do_resonance1_clump
+    if (!active) continue;
+    load_rest(pl, s, ph);
+    bool peeled = false;
+    auto emit_ray = [&](int k, bool ok, PeelRay &pr) {
+      if (ok) { pr.ic = icl; ray_store(myrays + k, pr); }
+      else myrays[k].kind = -1;
+    };
+    if (to_dust) {
+      scatter_dust(P, ph, rng, cs, cnt, [&]() {
+        peeled = true;
+        for (int k = 0; k < P.nobs; ++k) {
+          PeelRay pr;
+          bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[k], k, ph, csp, pr)
+                                 : peel_dust_nostokes_prepare(P, P.obs[k], k, ph, csp, pr);
+          emit_ray(k, ok, pr);
+        }
+      });
+      if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
+    } else {
+      const double scale_inv = 1.0 / scale;
+      const double xfreq_atom = (xloc - uz_loc) * scale_inv, uz = uz_loc * scale_inv;  // line_clump_mod.f90:41-44
+      CellData css = cs;
+      css.Dfreq = cp.Dfreq;  // recoil uses the clump's Doppler width (scattering_car.f90:428-433)
+      scatter_resonance_core<true>(P, ph, rng, css, cnt, uz, xfreq_atom, ratio, [&](double xa, double ux, double uy, double uzz) {
+        peeled = true;
+        for (int k = 0; k < P.nobs; ++k) {
+          PeelRay pr;
+          bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[k], k, ph, csp, xa, ux, uy, uzz, pr)
+                                 : peel_resonance_nostokes_prepare(P, P.obs[k], k, ph, csp, xa, ux, uy, uzz, pr);
+          emit_ray(k, ok, pr);
+        }
+      });
+    }
+    if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+    int fl = ph.flags;
+    store_rng(pl, s, rng, fl);
+    ph.flags = fl;
+    store_all(pl, s, ph);
+    nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// stage 4: capped edge walks (peel_raytrace_to_edge, peelingoff_rect.f90:894-906) of the slot rays and the direct rays
+__global__ void __launch_bounds__(kBlock, 3) k_cl_peel(const __grid_constant__ DevParams P, Pool pl, Queues q) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  const unsigned FULL = 0xffffffffu;
+  Counters cnt;
+  const unsigned nslot = (unsigned)pl.n * (unsigned)P.nobs, slot_lo = (unsigned)pl.s0 * (unsigned)P.nobs;
+  const unsigned n = nslot + min(*q.n_direct, q.direct_cap);
+  ClumpWalk w;
+  PeelRay pr;
+  bool have = false, exhausted = false;
+  for (;;) {
+    bool need = !have && !exhausted;
+    unsigned nm = __ballot_sync(FULL, need), hm = __ballot_sync(FULL, have);
+    if (nm && (__popc(nm) >= kRefillMin || !hm)) {
+      unsigned idx = reserve(q.head_peel, need);
+      if (need) {
+        if (idx >= n) exhausted = true;
+        else {
+          const PeelRay *src = q.rays + (idx < nslot ? slot_lo + idx : q.direct_base + (idx - nslot));
+          if (src->kind >= 0) {
+            ray_load(pr, src);
+            cnt.peel += 1;
+            cw_start(w, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.xfreq, pr.ic, 0.0);
+            have = true;
+          }
+        }
+      }
+    }
+    bool fin = false;
+    if (have && cw_edge_step(P, vtab, w, kTauHugeClump)) { fin = true; have = false; cnt.cellsteps += w.ncells; }
+    unsigned fm = __ballot_sync(FULL, fin);
+    if (fin) peel_deposit(P, pr, w.tau, fm);
+    if (!__any_sync(FULL, have || !exhausted)) break;
+  }
+  flush_counters(P, cnt, 0);
 }
 
 // ------------------------------ pool compaction ------------------------------
@@ -1509,10 +1768,9 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   }
   // ---- photon pool
   h->flags = cfg->flags;
-  if (P.clump) h->flags |= LART_FLAG_MONOLITHIC;  // the clump medium runs on the one-thread-per-photon driver for now
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int S = cfg->pool_slots;
-  if (S <= 0) S = P.clump ? h->nsm * 8192 : (mono ? h->nsm * 2048 : h->nsm * 16384);  // clumps: 2.75e8 / 2.85e8 / 2.96e8 scatterings/s at 2048 / 4096 / 8192 per SM
+  if (S <= 0) S = mono ? (P.clump ? h->nsm * 8192 : h->nsm * 2048) : h->nsm * 16384;  // k_mono_clump: 2.75e8 / 2.85e8 / 2.96e8 scatterings/s at 2048 / 4096 / 8192 per SM
   {
     // keep the ray queue below ~3 GB when many observers are configured
     long long per_slot = (long long)(2 * sizeof(PeelRay) + 4 * sizeof(PeelCont)) * std::max(1, P.nobs);
@@ -1654,14 +1912,18 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           const int grid = std::max(1, std::min(nb, h->nsm * 2));
           k_wf_reset<<<1, 1, 0, g.stream>>>(g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          k_wf_emit<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          if (h->P.clump) k_cl_emit<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          else k_wf_emit<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
+          if (h->P.clump) k_cl_flight<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          else k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          if (h->P.local_steps) k_wf_scatter<true><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          if (h->P.clump) k_cl_scatter<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          else if (h->P.local_steps) k_wf_scatter<true><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           else k_wf_scatter<false><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          k_wf_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
+          if (h->P.clump) k_cl_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
+          else k_wf_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
         }
       }
@@ -1781,6 +2043,7 @@ int drain_peel_only(lart_gpu_handle h) { return drain(h, false); }
 // `flights` (before the monolithic kernel takes over).  One pass with an unlimited budget does it.
 int drain(lart_gpu_handle h, bool flights) {
   if (!h->pending_rays || h->groups.empty()) return 0;
+  if (h->P.clump) { h->pending_rays = false; return 0; }  // the clump walkers never park a ray
   const int big = 0x7fffffff;
   for (auto &g : h->groups) {
     const int nb = (g.pool.n + kBlock - 1) / kBlock;

@@ -56,12 +56,13 @@ CLUMP_CASES = {
 }
 
 
+@pytest.mark.parametrize("flags", [0, capi.FLAG_MONOLITHIC], ids=["wavefront", "monolithic"])
 @pytest.mark.parametrize("case", sorted(CLUMP_CASES))
-def test_clump_photon_histories_match_oracle(case):
+def test_clump_photon_histories_match_oracle(case, flags):
     kw = dict(no_photons=1500, save_all_photons=True, clump_tau0=10.0)
     kw.update(CLUMP_CASES[case])
     mg, mo = clump_model(**kw), clump_model(**kw)
-    run_gpu(mg, pool_slots=512, quantum=3)
+    run_gpu(mg, flags=flags, pool_slots=512, quantum=3)
     oracle.run(mo, rng_mode=1)
     same = histories_equal(mg, mo, geom_rtol=1e-6)
     # Stokes vectors drift by ~1e-8 over hundreds of scatterings (FMA contraction differs from the CPU's): the signed Q/U cubes
@@ -75,10 +76,12 @@ def test_clump_run_statistics_and_scheduling():
     n = 30000
     kw = dict(no_photons=n, clump_f_cov=1.0, clump_radius=0.02, clump_tau0=1e4, spectral_type="monochromatic", nxfreq=121,
               xfreq_min=-30.0, xfreq_max=30.0, save_all_photons=True, iseed=21, xs_point=1e-9)
-    a = run_gpu(clump_model(**kw), pool_slots=256, quantum=2)
+    a = run_gpu(clump_model(**kw), pool_slots=256, quantum=2, streams=3)
     b = run_gpu(clump_model(**kw), pool_slots=8192, quantum=64)
-    assert np.allclose(a.allph("nscatt_gas"), b.allph("nscatt_gas"), rtol=1e-12)
-    assert np.allclose(a.spectrum("Jout"), b.spectrum("Jout"), rtol=1e-10)
+    c = run_gpu(clump_model(**kw), flags=capi.FLAG_MONOLITHIC, pool_slots=1024, quantum=5)
+    for other in (b, c):
+        assert np.allclose(a.allph("nscatt_gas"), other.allph("nscatt_gas"), rtol=1e-12)
+        assert np.allclose(a.spectrum("Jout"), other.spectrum("Jout"), rtol=1e-10)
     ns = a.allph("nscatt_gas")
     assert (ns == 0).mean() == pytest.approx(np.exp(-1.0), rel=0.06)
     assert a.spectrum("Jout").sum() == pytest.approx(n, rel=2e-3)

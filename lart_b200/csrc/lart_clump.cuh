@@ -100,6 +100,11 @@ LART_DEV void cw_start(ClumpWalk &w, double x, double y, double z, double kx, do
   w.x = x; w.y = y; w.z = z; w.kx = kx; w.ky = ky; w.kz = kz; w.xfreq = xfreq; w.tau = tau;
   w.icl = icl; w.skip_icl = 0; w.ncells = 0; w.nclumps = 0;
   w.phase = icl > 0 ? CW_CLUMP : CW_FIND;
+  // the DDA increments cg_d/|k| depend on the direction only: one divide per axis and ray, at the first crossing of that
+  // axis (the reference recomputes the same quotients in every find_next_clump call; FP64 divides were 1/3 of the walkers'
+  // instructions).  -1 = not yet computed.
+  w.delx = (kx != 0.0) ? -1.0 : kHugest; w.dely = (ky != 0.0) ? -1.0 : kHugest; w.delz = (kz != 0.0) ? -1.0 : kHugest;
+  w.si = kx > 0.0 ? 1 : (kx < 0.0 ? -1 : 0); w.sj = ky > 0.0 ? 1 : (ky < 0.0 ? -1 : 0); w.sk = kz > 0.0 ? 1 : (kz < 0.0 ? -1 : 0);
 }
 LART_DEV void cw_advance(ClumpWalk &w, double t) {
   w.x = DADD(w.x, DMUL(t, w.kx)); w.y = DADD(w.y, DMUL(t, w.ky)); w.z = DADD(w.z, DMUL(t, w.kz));
@@ -110,14 +115,12 @@ LART_DEV bool cw_find_begin(const DevClumps &C, ClumpWalk &w) {
   if (w.t_sp <= 0.0) return false;
   w.best_te = kHugest; w.best_icl = 0; w.d = 0.0;
   w.ci = cg_clamp(w.x, C.xmin, C.inv_dx, C.cgx); w.cj = cg_clamp(w.y, C.ymin, C.inv_dy, C.cgy); w.ck = cg_clamp(w.z, C.zmin, C.inv_dz, C.cgz);
-  auto axis = [](double k, double p, int cc, double lo, double dd, int &st, double &t, double &del) {
-    if (k > 0.0) { st = 1; t = DSUB(DADD(lo, DMUL((double)(cc + 1), dd)), p) / k; del = dd / k; }
-    else if (k < 0.0) { st = -1; t = DSUB(DADD(lo, DMUL((double)cc, dd)), p) / k; del = -dd / k; }
-    else { st = 0; t = kHugest; del = kHugest; }
+  auto axis = [](double k, double p, int cc, double lo, double dd, int st) {  // path length to the first face ahead
+    return st == 0 ? kHugest : DSUB(DADD(lo, DMUL((double)(cc + (st > 0 ? 1 : 0)), dd)), p) / k;
   };
-  axis(w.kx, w.x, w.ci, C.xmin, C.dx, w.si, w.tx, w.delx);
-  axis(w.ky, w.y, w.cj, C.ymin, C.dy, w.sj, w.ty, w.dely);
-  axis(w.kz, w.z, w.ck, C.zmin, C.dz, w.sk, w.tz, w.delz);
+  w.tx = axis(w.kx, w.x, w.ci, C.xmin, C.dx, w.si);
+  w.ty = axis(w.ky, w.y, w.cj, C.ymin, C.dy, w.sj);
+  w.tz = axis(w.kz, w.z, w.ck, C.zmin, C.dz, w.sk);
   w.phase = CW_CELL;
   return true;
 }
@@ -140,9 +143,20 @@ LART_DEV bool cw_find_cell(const DevClumps &C, ClumpWalk &w) {
       const double te = DSUB(-b, disc), tx2 = DADD(-b, disc);
       if (tx2 > 0.0 && te < w.best_te) { w.best_te = te; w.best_icl = icl; }
     }
-    if (w.tx <= w.ty && w.tx <= w.tz) { w.d = w.tx; w.ci += w.si; if (w.ci < 0 || w.ci >= C.cgx) over = true; else w.tx = DADD(w.tx, w.delx); }
-    else if (w.ty <= w.tz) { w.d = w.ty; w.cj += w.sj; if (w.cj < 0 || w.cj >= C.cgy) over = true; else w.ty = DADD(w.ty, w.dely); }
-    else { w.d = w.tz; w.ck += w.sk; if (w.ck < 0 || w.ck >= C.cgz) over = true; else w.tz = DADD(w.tz, w.delz); }
+    // cg_dx/kx for kx > 0, -cg_dx/kx for kx < 0 (clump_mod.f90:1440-1445): the same quotient, bit for bit, as cg_dx/|kx|
+    if (w.tx <= w.ty && w.tx <= w.tz) {
+      w.d = w.tx; w.ci += w.si;
+      if (w.ci < 0 || w.ci >= C.cgx) over = true;
+      else { if (w.delx < 0.0) w.delx = C.dx / fabs(w.kx); w.tx = DADD(w.tx, w.delx); }
+    } else if (w.ty <= w.tz) {
+      w.d = w.ty; w.cj += w.sj;
+      if (w.cj < 0 || w.cj >= C.cgy) over = true;
+      else { if (w.dely < 0.0) w.dely = C.dy / fabs(w.ky); w.ty = DADD(w.ty, w.dely); }
+    } else {
+      w.d = w.tz; w.ck += w.sk;
+      if (w.ck < 0 || w.ck >= C.cgz) over = true;
+      else { if (w.delz < 0.0) w.delz = C.dz / fabs(w.kz); w.tz = DADD(w.tz, w.delz); }
+    }
   }
   if (over && !(w.best_icl > 0 && w.best_te <= w.t_sp)) w.best_icl = 0;
   return over;
@@ -170,7 +184,7 @@ LART_DEV bool cw_edge_step(const DevParams &P, const double *vtab, ClumpWalk &w,
     w.skip_icl = w.icl;
     if (outside_sphere(C, w.x, w.y, w.z)) return true;
     w.phase = CW_FIND;
-    return false;
+    return !cw_find_begin(C, w);  // the search set-up rides along: two kinds of step remain, clump segments and cells
   }
   if (w.phase == CW_FIND) return !cw_find_begin(C, w);
   if (cw_find_cell(C, w)) {
@@ -198,7 +212,7 @@ LART_DEV int cw_tau_step(const DevParams &P, const double *vtab, ClumpWalk &w) {
     w.icl = 0;
     if (outside_sphere(C, w.x, w.y, w.z)) return 2;
     w.phase = CW_FIND;
-    return 0;
+    return cw_find_begin(C, w) ? 0 : 2;
   }
   if (w.phase == CW_FIND) return cw_find_begin(C, w) ? 0 : 2;
   if (cw_find_cell(C, w)) {

@@ -133,8 +133,8 @@ LART_DEV bool cw_find_cell(const DevClumps &C, ClumpWalk &w) {
     const int p0 = __ldg(C.cg_start + icell), p1 = __ldg(C.cg_start + icell + 1);
     for (int ip = p0; ip < p1; ++ip) {
       const int icl = __ldg(C.cg_list + ip - 1);
+      const double4 g = ldg4(C.geo_reg + ip - 1);  // independent of the list load: offsets -> {list, geometry}
       if (icl == w.skip_icl) continue;
-      const double4 g = ldg4(C.geo + icl - 1);
       const double rx = DSUB(w.x, g.x), ry = DSUB(w.y, g.y), rz = DSUB(w.z, g.z);
       const double b = DADD(DADD(DMUL(rx, w.kx), DMUL(ry, w.ky)), DMUL(rz, w.kz));
       double disc = DADD(DSUB(DMUL(b, b), DADD(DADD(DMUL(rx, rx), DMUL(ry, ry)), DMUL(rz, rz))), g.w);
@@ -157,6 +157,7 @@ LART_DEV bool cw_find_cell(const DevClumps &C, ClumpWalk &w) {
       if (w.ck < 0 || w.ck >= C.cgz) over = true;
       else { if (w.delz < 0.0) w.delz = C.dz / fabs(w.kz); w.tz = DADD(w.tz, w.delz); }
     }
+    if (!over) prefetch_l1(C.cg_start + ((size_t)w.ci + (size_t)C.cgx * ((size_t)w.cj + (size_t)C.cgy * (size_t)w.ck)));
   }
   if (over && !(w.best_icl > 0 && w.best_te <= w.t_sp)) w.best_icl = 0;
   return over;

@@ -60,6 +60,7 @@ struct DevClumps {
   long long n;
   double sphere_R, R2, Dfreq_ref;
   const double4 *geo;
+  const double4 *geo_reg;  // geo[cg_list[ip]] for every CSR registration ip: the cell's clumps are contiguous, one load level less
   const ClumpPhys *phys;
   const int *cg_start, *cg_list;  // 1-based offsets / clump indices, as the host built them
   int cgx, cgy, cgz, pad_;

@@ -1330,6 +1330,10 @@ __global__ void k_clump_locate_batch(const __grid_constant__ DevParams P, long l
     icl[i] = clump_at_point(P.cl, x[i], y[i], z[i]);
 }
 // host arrays -> device records (geometry: centre + radius^2; physics: 64 bytes)
+__global__ void k_clump_geo_reg(long long nreg, const int *cg_list, const double4 *geo, double4 *geo_reg) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nreg; i += (long long)gridDim.x * blockDim.x)
+    geo_reg[i] = geo[cg_list[i] - 1];
+}
 __global__ void k_pack_clumps(long long n, const double *x, const double *y, const double *z, const double *radius,
                               const double *rhokap, const double *rhokapD, const double *voigt_a, const double *Dfreq,
                               const double *vx, const double *vy, const double *vz, double4 *geo, ClumpPhys *phys) {
@@ -1702,6 +1706,15 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
       CUDA_OK(cudaStreamSynchronize(h->stream));
     }
     P.cl.geo = geo; P.cl.phys = phys;
+    {
+      double4 *geo_reg = nullptr;
+      if ((rc = dalloc(h, &geo_reg, nreg, false))) return bail(rc);
+      k_clump_geo_reg<<<(int)std::min<size_t>((nreg + kBlock - 1) / kBlock, (size_t)h->nsm * 8), kBlock, 0, h->stream>>>(
+          (long long)nreg, P.cl.cg_list, geo, geo_reg);
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaStreamSynchronize(h->stream));
+      P.cl.geo_reg = geo_reg;
+    }
   }
   P.nsbx = (g.nx + 31) / 32; P.nsby = (g.ny + 31) / 32; P.nsbz = (g.nz + 31) / 32;
   if (!P.soa) {

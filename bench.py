@@ -286,8 +286,11 @@ def run_gpu(args):
             "stage_ms_per_wave": {k: stage[k][0] / max(stage[k][1], 1) for k in stage},
             "stage_share": {k: stage[k][0] / tot_stage for k in stage},
             "dominant_stage": dom,
-            "dda_walk": {"kernels": "k_wf_trace+k_wf_peel", "bytes_per_cellstep": 48,
-                         "achieved_GBps": 48.0 * steps_local / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0,
+            # Cartesian: one 48-B share of a cell record per step; clump medium: a CSR cell = 8 B of offsets + ~1.5
+            # registrations of 36 B (index + centre/r^2) = 62 B
+            "dda_walk": {"kernels": "k_cl_flight+k_cl_peel" if clump else "k_wf_trace+k_wf_peel",
+                         "bytes_per_cellstep": 62 if clump else 48,
+                         "achieved_GBps": (62.0 if clump else 48.0) * steps_local / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0,
                          "cellsteps_per_launch": steps_local / max(walk_n, 1), "avg_launch_ms": walk_ms / max(walk_n, 1)},
             "fp64": {"achieved_tflops": flops / (dev_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                      "frac": flops / (dev_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,

@@ -1955,7 +1955,8 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           else if (h->P.local_steps) k_wf_scatter<true><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           else k_wf_scatter<false><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          if (h->P.clump) k_cl_peel<<<std::max(1, std::min(nb, h->nsm * 4)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
+          if (h->P.nobs == 0) {}  // no observers: nothing to peel (xyz_symmetry, plain slabs)
+          else if (h->P.clump) k_cl_peel<<<std::max(1, std::min(nb, h->nsm * 4)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
           else k_wf_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
         }
@@ -1991,7 +1992,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
       }
       CUDA_OK(cudaGraphLaunch(it->second, h->stream));
     }
-    h->launches += 5LL * G * qn;
+    h->launches += (h->P.nobs == 0 ? 4LL : 5LL) * G * qn;
     h->pending_rays = true;
   }
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));

@@ -355,7 +355,9 @@ def run_gpu(args):
                     "d2h_bytes_per_step": (8 * buf_n + 8 * total_steps) / total_steps, "seconds": float(te[0]),
                     "phases_rank0": phases,
                     "region": "lart_gpu_create(H2D host grid) + begin + %d steps (+D2H of each step's in-flight count) + "
-                              "NCCL reduce + D2H of the tally buffer into host arrays (lart_gpu_destroy not timed)" % total_steps},
+                              "NCCL reduce + D2H of the tally buffer into host arrays (lart_gpu_destroy not timed); handle memory comes from "
+                              "the CUDA stream-ordered pool, so this second handle of the process reuses cached device memory "
+                              "(a process's first lart_gpu_create measured 0.06-0.17 s)" % total_steps},
             "clocks": clk.summary(),
         }
         if not args.no_cpu_baseline and world == 1:

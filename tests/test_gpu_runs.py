@@ -172,6 +172,21 @@ def test_xyz_symmetry_parked_walks_keep_their_reflections(kw):
     tallies_close(mg, mo, same.mean())
 
 
+@pytest.mark.parametrize("par", [dict(xy_symmetry=True, nx=15, ny=16, nz=31, save_Jmu=True, nmu=4, xs_point=0.1, ys_point=0.05),
+                                 dict(xy_periodic=True, geometry="rectangle", rmax=-999.0, nx=5, ny=4, nz=41, xmax=0.5, ymax=0.4,
+                                      zmax=1.0, xs_point=0.5, ys_point=-0.4)],
+                         ids=["xy_symmetry", "xy_periodic_source_on_the_corner"])
+def test_folded_and_periodic_peel_rays_survive_parking(par):
+    """Peel rays parked at a budget of one cell step per wave: the reflection mask / wrapped start travels with them."""
+    kw = dict(taumax=30.0, no_photons=800, obsx=[0.0, 1.0], obsy=[0.0, 0.5], obsz=[1.0, 0.2])
+    kw.update(par)
+    mg, mo = small_sphere(**kw), small_sphere(**kw)
+    run_gpu(mg, pool_slots=128, quantum=2, ray_budget=1, streams=2)
+    oracle.run(mo, rng_mode=1)
+    same = histories_equal(mg, mo, geom_rtol=1e-6)
+    tallies_close(mg, mo, min(same.mean(), 1.0 - 1e-8))
+
+
 def test_xy_periodic_parked_walks_and_slab_equivalence():
     """A uniform periodic box is the infinite slab: same photon histories whatever the budget, and the spectrum of the
     one-column (z-only) slab."""

@@ -992,10 +992,13 @@ __global__ void __launch_bounds__(kBlock) k_cl_emit(const __grid_constant__ DevP
 // kind most lanes are waiting for, and only those lanes run it.  Lanes of other kinds wait their turn.  (With every
 // lane doing "its" step each iteration the three code paths ran one after the other with a quarter of the lanes each:
 // ncu 5.7 / 7.9 of 32 threads active per instruction in the flight / peel stage.)
-__device__ __forceinline__ int cw_vote(bool need, bool have, int phase, bool &any) {
+__device__ __forceinline__ int cw_vote(bool need, bool have, int phase, double d, bool &any, unsigned &m_cell, unsigned &m_find) {
   const unsigned FULL = 0xffffffffu;
   const int nn = __popc(__ballot_sync(FULL, need));
-  const int nc = __popc(__ballot_sync(FULL, have && phase != CW_CLUMP));
+  // a lane whose search cw_coop_cells has just ended (d = huge) only needs its own short step to resolve it: like CW_FIND
+  m_cell = __ballot_sync(FULL, have && phase == CW_CELL && d < kHugest);
+  m_find = __ballot_sync(FULL, have && (phase == CW_FIND || (phase == CW_CELL && !(d < kHugest))));
+  const int nc = __popc(m_cell | m_find);
   const int nl = __popc(__ballot_sync(FULL, have && phase == CW_CLUMP));
   any = (nn | nc | nl) != 0;
   int sel = 1, mx = nc;           // 1: cell (and search set-up)
@@ -1003,6 +1006,101 @@ __device__ __forceinline__ int cw_vote(bool need, bool have, int phase, bool &an
   if (nn > mx) { sel = 0; }           // 0: refill
   return sel;
 }
+
+// When only a few lanes of a warp still walk CSR cells, the warp walks ONE of those rays together: lane j takes the ray's
+// j-th cell ahead (it replays the DDA j steps from the leader's state: a few adds, no memory), the 32 cells are tested
+// in one round of loads instead of 32, and the outcome is put together exactly as the sequential loop of
+// find_next_clump would have produced it — cells in traversal order, the walk stops before the first cell that starts
+// beyond the best hit or the sphere, or after the cell whose successor lies outside the grid; of equal entry distances
+// the first in traversal order wins.  Must be called by all 32 lanes; `leader` holds a ray in phase CW_CELL.
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ void cw_coop_cells(const DevClumps &C, ClumpWalk &w, int leader) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (lane == leader) {  // the DDA increments are needed by every lane: compute what is still missing (once per ray)
+    if (w.delx < 0.0) w.delx = C.dx / fabs(w.kx);
+    if (w.dely < 0.0) w.dely = C.dy / fabs(w.ky);
+    if (w.delz < 0.0) w.delz = C.dz / fabs(w.kz);
+  }
+  const double x = shfl_d(w.x, leader), y = shfl_d(w.y, leader), z = shfl_d(w.z, leader);
+  const double kx = shfl_d(w.kx, leader), ky = shfl_d(w.ky, leader), kz = shfl_d(w.kz, leader);
+  const double delx = shfl_d(w.delx, leader), dely = shfl_d(w.dely, leader), delz = shfl_d(w.delz, leader);
+  const double t_sp = shfl_d(w.t_sp, leader), best_in = shfl_d(w.best_te, leader);
+  double tx = shfl_d(w.tx, leader), ty = shfl_d(w.ty, leader), tz = shfl_d(w.tz, leader), d = shfl_d(w.d, leader);
+  int ci = __shfl_sync(FULL, w.ci, leader), cj = __shfl_sync(FULL, w.cj, leader), ck = __shfl_sync(FULL, w.ck, leader);
+  const int si = __shfl_sync(FULL, w.si, leader), sj = __shfl_sync(FULL, w.sj, leader), sk = __shfl_sync(FULL, w.sk, leader);
+  const int skip = __shfl_sync(FULL, w.skip_icl, leader), icl_in = __shfl_sync(FULL, w.best_icl, leader);
+  auto advance = [&]() -> bool {  // one DDA step; false when it leaves the grid (same arithmetic as cw_find_cell)
+    if (tx <= ty && tx <= tz) { d = tx; ci += si; if (ci < 0 || ci >= C.cgx) return false; tx = DADD(tx, delx); }
+    else if (ty <= tz) { d = ty; cj += sj; if (cj < 0 || cj >= C.cgy) return false; ty = DADD(ty, dely); }
+    else { d = tz; ck += sk; if (ck < 0 || ck >= C.cgz) return false; tz = DADD(tz, delz); }
+    return true;
+  };
+  bool alive = true;
+  for (int i = 0; i < lane && alive; ++i) alive = advance();
+  // my cell: nearest entry among its clumps (list order, strict <)
+  const double d_mine = d;
+  double te_mine = kHugest;
+  int icl_mine = 0;
+  if (alive) {
+    const size_t icell = (size_t)ci + (size_t)C.cgx * ((size_t)cj + (size_t)C.cgy * (size_t)ck);
+    const int p0 = __ldg(C.cg_start + icell), p1 = __ldg(C.cg_start + icell + 1);
+    for (int ip = p0; ip < p1; ++ip) {
+      const int icl = __ldg(C.cg_list + ip - 1);
+      const double4 g = ldg4(C.geo_reg + ip - 1);
+      if (icl == skip) continue;
+      const double rx = DSUB(x, g.x), ry = DSUB(y, g.y), rz = DSUB(z, g.z);
+      const double b = DADD(DADD(DMUL(rx, kx), DMUL(ry, ky)), DMUL(rz, kz));
+      double disc = DADD(DSUB(DMUL(b, b), DADD(DADD(DMUL(rx, rx), DMUL(ry, ry)), DMUL(rz, rz))), g.w);
+      if (disc < 0.0) continue;
+      disc = sqrt(disc);
+      const double te = DSUB(-b, disc), tx2 = DADD(-b, disc);
+      if (tx2 > 0.0 && te < te_mine) { te_mine = te; icl_mine = icl; }
+    }
+  }
+  const bool out_after = alive && !advance();  // the cell after mine lies outside the grid
+  // inclusive prefix "first minimum" over lanes 0..j, seeded with the leader's best so far
+  double pt = te_mine;
+  int pi = icl_mine;
+  if (lane == 0 && !(te_mine < best_in)) { pt = best_in; pi = icl_in; }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double qt = __shfl_up_sync(FULL, pt, o);
+    const int qi = __shfl_up_sync(FULL, pi, o);
+    if (lane >= o && !(pt < qt)) { pt = qt; pi = qi; }  // the earlier lanes keep a tie
+  }
+  double et = __shfl_up_sync(FULL, pt, 1);  // exclusive prefix: best before my cell
+  int ei = __shfl_up_sync(FULL, pi, 1);
+  if (lane == 0) { et = best_in; ei = icl_in; }
+  const bool chk = alive && (d_mine > et || d_mine > t_sp);  // the sequential loop stops before my cell
+  const unsigned mc = __ballot_sync(FULL, chk), mo = __ballot_sync(FULL, out_after);
+  const int jc = mc ? __ffs(mc) - 1 : 32, jo = mo ? __ffs(mo) - 1 : 32;
+  int processed, src;
+  bool stop, excl;
+  if (jc <= jo && jc < 32) { processed = jc; src = jc; excl = true; stop = true; }
+  else if (jo < 32) { processed = jo + 1; src = jo; excl = false; stop = true; }
+  else { processed = 32; src = 31; excl = false; stop = false; }
+  const double rt = shfl_d(excl ? et : pt, src);
+  const int ri = __shfl_sync(FULL, excl ? ei : pi, src);
+  // state of the cell after lane 31's (valid when !stop)
+  const double ntx = shfl_d(tx, 31), nty = shfl_d(ty, 31), ntz = shfl_d(tz, 31), nd = shfl_d(d, 31);
+  const int nci = __shfl_sync(FULL, ci, 31), ncj = __shfl_sync(FULL, cj, 31), nck = __shfl_sync(FULL, ck, 31);
+  if (lane == leader) {
+    w.best_te = rt; w.best_icl = ri; w.ncells += processed;
+    if (stop) w.d = kHugest;  // the leader's next own step sees the search over and resolves it
+    else { w.tx = ntx; w.ty = nty; w.tz = ntz; w.d = nd; w.ci = nci; w.cj = ncj; w.ck = nck; }
+  }
+}
+// Walk together when no more than this many lanes of the warp are on CSR cells (0 = never).  Measured per wave of 2.4 M
+// photons (clump_sphere_fcov5): flight stage 2.20 -> 1.59 ms with 12, 20 or 32 (its searches are long: the mean free
+// path between clumps is ~20 cells); peel stage 3.16 ms without, 3.36 with 4, 3.48 with 12 (most of its rays end in
+// their own clump, the others keep many lanes busy) — so flights only.
+#ifndef LART_COOP_FLIGHT
+#define LART_COOP_FLIGHT 12
+#endif
+#ifndef LART_COOP_PEEL
+#define LART_COOP_PEEL 0
+#endif
 
 // stage 2: flights (forced first scattering included) of every alive slot that is not at a scattering point
 __global__ void __launch_bounds__(kBlock, 3) k_cl_flight(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
@@ -1016,12 +1114,17 @@ __global__ void __launch_bounds__(kBlock, 3) k_cl_flight(const __grid_constant__
   int slot = -1, mode = 0;  // mode 0: uncapped edge walk of the forced first scattering, 1: tau walk
   bool have = false, exhausted = false;
   CellData cs0;
-  w.phase = 0;
+  w.phase = 0; w.d = 0.0;
   for (;;) {
     const bool need = !have && !exhausted;
     bool any;
-    const int sel = cw_vote(need, have, w.phase, any);
+    unsigned m_cell, m_find;
+    const int sel = cw_vote(need, have, w.phase, w.d, any, m_cell, m_find);
     if (!any) break;
+    if (sel == 1 && m_cell && !m_find && __popc(m_cell) <= LART_COOP_FLIGHT) {  // few lanes left on cells: walk one ray together
+      cw_coop_cells(P.cl, w, __ffs(m_cell) - 1);
+      continue;
+    }
     if (sel == 0) {
       unsigned idx = reserve(q.head_trace, need);
       if (need) {
@@ -1182,12 +1285,17 @@ __global__ void __launch_bounds__(kBlock, 4) k_cl_peel(const __grid_constant__ D
   ClumpWalk w;
   PeelRay pr;
   bool have = false, exhausted = false;
-  w.phase = 0;
+  w.phase = 0; w.d = 0.0;
   for (;;) {
     const bool need = !have && !exhausted;
     bool any;
-    const int sel = cw_vote(need, have, w.phase, any);
+    unsigned m_cell, m_find;
+    const int sel = cw_vote(need, have, w.phase, w.d, any, m_cell, m_find);
     if (!any) break;
+    if (sel == 1 && m_cell && !m_find && __popc(m_cell) <= LART_COOP_PEEL) {  // few lanes left on cells: walk one ray together
+      cw_coop_cells(P.cl, w, __ffs(m_cell) - 1);
+      continue;
+    }
     if (sel == 0) {
       unsigned idx = reserve(q.head_peel, need);
       if (need) {

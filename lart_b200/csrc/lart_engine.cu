@@ -742,11 +742,30 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
 #endif
 // LOCAL = the stage also takes the first cell step of the peel ray and of the next flight itself
 // (LART_FLAG_LOCAL_STEPS).  A template so that the default kernel does not carry that code.
+// A peel ray whose first cell alone is deeper than the cap ends there with a contribution of exactly zero
+// (raytrace_car.f90:432,497: tau >= 745.2).  The path inside the cell is at least the distance L to the nearest face
+// (|k| <= 1), and rounding is monotonic, so kappa*L >= 745.2 proves it without the DDA set-up and its three divides: such
+// a ray is counted (one peel ray, one cell step, as the walk would) and never written to the queue.  On a face L = 0.
+#ifndef LART_PEEL_BOUND
+#define LART_PEEL_BOUND 1
+#endif
+__device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const double *vtab, const CellData &cs, const PeelRay &pr) {
+  double L = fmin(DSUB(pr.z, __ldg(P.zface + pr.kc - 1)), DSUB(__ldg(P.zface + pr.kc), pr.z));
+  if (!P.zonly) {
+    L = fmin(L, fmin(DSUB(pr.x, __ldg(P.xface + pr.ic - 1)), DSUB(__ldg(P.xface + pr.ic), pr.x)));
+    L = fmin(L, fmin(DSUB(pr.y, __ldg(P.yface + pr.jc - 1)), DSUB(__ldg(P.yface + pr.jc), pr.y)));
+  }
+  if (!(L > 0.0)) return false;
+  double kap = DMUL(cs.rhokap, voigt_seon2(vtab, pr.xfreq, cs.voigt_a));
+  if (P.dust) kap = DADD(kap, cs.rhokapD);
+  return DMUL(kap, L) >= kTauHuge;
+}
+
 template <bool LOCAL>
 __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   __shared__ VzWarpShared vzsh[kBlock / 32];
-  if (LOCAL || P.dust) load_vtab(P, vtab);
+  if (LOCAL || P.dust || (LART_PEEL_BOUND && P.save_peeloff)) load_vtab(P, vtab);
   VzWarpShared &sh = vzsh[threadIdx.x >> 5];
   Counters cnt;
   ctr_t nrng = 0;
@@ -798,6 +817,10 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
     bool have_pr0 = false;
     auto emit_ray = [&](int k, bool ok, const PeelRay &pr) {
       if (LOCAL && k == 0) { have_pr0 = ok; if (ok) pr0 = pr; else myrays[0].kind = -1; }
+      else if (ok && LART_PEEL_BOUND && !LOCAL && peel_certainly_capped(P, vtab, cs, pr)) {
+        cnt.peel += 1; cnt.cellsteps += 1;
+        myrays[k].kind = -1;
+      }
       else if (ok) ray_store(myrays + k, pr);
       else myrays[k].kind = -1;
     };

@@ -269,13 +269,17 @@ def run_gpu(args):
     # record is read and written once (22 f64 + id + block counter + 4 i32 = 208 B each way) and one 144-B peel-ray
     # descriptor is written per observer.
     nobs = max(int(cfg.par.nobs), 0)
-    bytes_per_scatter = 2 * 208 + 144 * nobs
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")  # dram__bytes_read+write per launch from `ncu --set full`
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    # ... per QUEUED ray: on this workload the scatter stage drops the rays that provably end in their own cell; the
+    # fraction it still writes comes from the ncu capture (1.0 when there is none, and for other workloads' geometry)
+    qf = tj.get("queued_ray_fraction", 1.0) if args.workload == "sphere_peel_tau1e7" and not (args.flags & 4) else 1.0
+    bytes_per_scatter = 2 * 208 + 144 * nobs * qf
     sc_ms, sc_n = stage["scatter"] if not mono else stage["trace"]
     ach = bytes_per_scatter * c["n_scatter"] / (sc_ms * 1e-3) / 1e9 if sc_ms > 0 else 0.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")  # dram__bytes_read+write per launch from `ncu --set full`
-    if os.path.exists(tpath) and not mono:
-        tj = json.load(open(tpath))  # profiled at tj["pool_slots"] scatterings per launch; scale to this run's launch
+    if tj and not mono and args.workload == "sphere_peel_tau1e7":
+        # profiled at tj["pool_slots"] scatterings per launch; scale to this run's launch
         traffic = tj["k_wf_scatter_bytes_per_launch"] / tj["pool_slots"] * (c["n_scatter"] / max(sc_n, 1))
     clump = bool(cfg.par.use_clump_medium)
     roof = {"bound": "hbm", "kernel": ("k_cl_scatter" if clump else "k_wf_scatter") if not mono else ("k_mono_clump" if clump else "k_mono"),

@@ -89,8 +89,9 @@ def test_clump_run_statistics_and_scheduling():
 
 def test_clump_known_answer_reference_log():
     """examples/clump_sphere/log_back:4-55 (clump_NHI18_fcov1, 1e6 photons): Average Number of scattering 4.3454E+03.
-    Four GPU runs with different seeds gave 4266.6, 4292.7, 4329.1, 4323.0 (each +-0.53 %): mean 4303 +- 11 against the
-    logged 4345 +- 23, i.e. -1.0 % = 1.7 sigma.  One run here: 3 sigma of the combined single-run error = 2.3 %."""
+    Six GPU runs with different seeds gave 4266.6, 4292.7, 4329.1, 4323.0, 4349.9, 4332.1 (each +-0.53 %): mean
+    4316 +- 9 against the logged 4345 +- 23, i.e. -0.7 % = 1.2 sigma.  One run here: 3 sigma of the combined single-run
+    error = 2.3 %."""
     from test_oracle_clumps import LOGGED_FCOV1
     from lart_b200 import Model
     n = 1000000

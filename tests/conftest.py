@@ -26,3 +26,11 @@ def small_sphere(**kw):
                nxfreq=61, nxim=17, nyim=17, save_all_photons=True, iseed=7)
     par.update(kw)
     return Model(**par).setup()
+
+
+def golden(case, name):
+    """A value the reference printed in one of its own example logs (tests/golden/reference_logs.json, transcribed by
+    tools/extract_reference_logs.py with its examples/<file>:<line> source)."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_logs.json")) as fh:
+        return json.load(fh)[case][name]["value"]

@@ -3,6 +3,7 @@ Reference: clump_mod.f90:646-1349, 1369-1540, 2316-2380; raytrace_clump.f90:83-2
 import numpy as np
 import pytest
 
+from conftest import golden
 from lart_b200 import Model
 from oracle import oracle
 
@@ -171,16 +172,17 @@ def test_setup_scalars_clump_sphere_log():
     """The reference's own log of this input — examples/clump_sphere/log_back:4-55 (clump_NHI18_fcov1)."""
     m = Model(no_photons=1000, iseed=5, **LOGGED_FCOV1).setup()
     c = m.config.contents.clumps
-    assert c.n == 1333333                                                      # log_back:11
-    assert c.rhokap[0] == pytest.approx(4.4261e7, rel=2e-5)                    # :14
-    assert c.voigt_a[0] == pytest.approx(0.00047, abs=5e-6)                    # :15
-    assert c.Dfreq_ref == pytest.approx(1.0566e11, rel=5e-5)                   # :16
-    assert c.cgx == 111                                                        # :21 "in 111^3 cells"
+    G = lambda name: golden("clump_NHI18_fcov1", name)  # tests/golden/reference_logs.json <- examples/clump_sphere/log_back
+    assert c.n == G("N_clumps") == 1333333                                      # log_back:11
+    assert c.rhokap[0] == pytest.approx(G("cl_rhokap"), rel=2e-5)               # :14
+    assert c.voigt_a[0] == pytest.approx(0.00047, abs=5e-6)                     # :15
+    assert c.Dfreq_ref == pytest.approx(G("cl_Dfreq"), rel=5e-5)                # :16
+    assert c.cgx == G("csr_cells_per_axis") == 111                              # :21 "in 111^3 cells"
     nreg = np.ctypeslib.as_array(c.cg_start, shape=(c.cgx ** 3 + 1,))[-1] - 1
-    assert nreg == pytest.approx(1827254, rel=5e-3)                            # :21 (another random layout)
-    assert m.summary.tauhomo == pytest.approx(5.89826e4, rel=2e-6)             # :22
-    assert m.summary.N_gashomo == pytest.approx(1.0e18, rel=1e-5)              # :24
-    assert m.summary.vtherm == pytest.approx(12.84424, rel=1e-6)               # :37
+    assert nreg == pytest.approx(G("csr_registrations"), rel=5e-3)              # :21 (another random layout)
+    assert m.summary.tauhomo == pytest.approx(G("tauhomo"), rel=2e-6)           # :22
+    assert m.summary.N_gashomo == pytest.approx(G("N_gashomo"), rel=1e-5)       # :24
+    assert m.summary.vtherm == pytest.approx(G("cl_vtherm_kms"), rel=1e-6)      # :37
     # <N_scatt> = 4.3454E+03 with 1e6 photons (:52) is checked on the GPU (tests/test_gpu_clumps.py); the distribution is
     # heavy-tailed (sigma/mean = 5.4), so a CPU-sized sample can only bracket it
     oracle.run(m, rng_mode=0)

@@ -7,6 +7,7 @@ known-answer vectors of the generators, (c) independent mathematics.
 import numpy as np
 import pytest
 
+from conftest import golden
 from lart_b200 import Model
 from oracle import oracle
 
@@ -66,9 +67,9 @@ def test_setup_scalars_sphere_peel_log():
     m = Model(no_photons=10, temperature=10.0, taumax=1e3, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0,
               nxfreq=201, nxim=129, nyim=129).setup()
     s = m.summary
-    assert "%.3e" % s.voigt_a == "1.492e-02"
-    assert "%.3e" % s.N_gaspole == "5.449e+14"
-    assert s.taupole == pytest.approx(1e3, rel=1e-12)
+    assert float("%.3e" % s.voigt_a) == golden("sphere_peel_t1tau3", "voigt_a") == 1.492e-2
+    assert float("%.3e" % s.N_gaspole) == golden("sphere_peel_t1tau3", "N_HI_pole") == 5.449e14
+    assert s.taupole == pytest.approx(golden("sphere_peel_t1tau3", "tau_pole"), rel=1e-12)
     assert (s.nobs, s.nxim, s.nyim) == (1, 129, 129)
     assert s.dxim == pytest.approx(np.degrees(np.arcsin(1.0 / 100.0)) / 64.5, rel=1e-14)  # observer_rect.f90:248
 
@@ -77,9 +78,9 @@ def test_setup_scalars_amr_sphere_log():
     # examples/amr_sphere_generic/log_car_1M.txt:9-13 (64^3, T = 1e4 K, tau0 = 1e4)
     m = Model(no_photons=10, temperature=1e4, taumax=1e4, nx=64, ny=64, nz=64, rmax=1.0, nxfreq=121).setup()
     s = m.summary
-    assert "%.3e" % s.voigt_a == "4.719e-04"
+    assert float("%.3e" % s.voigt_a) == golden("amr_sphere_generic_car_1M", "voigt_a") == 4.719e-4
     assert abs(s.voigt_a / 4.7186e-4 - 1) < 2e-5  # log_amr_1M.txt:12
-    assert "%.3e" % s.N_gaspole == "1.695e+17"
+    assert float("%.3e" % s.N_gaspole) == golden("amr_sphere_generic_car_1M", "N_HI_pole") == 1.695e17
 
 
 def test_namelist_file_roundtrip(tmp_path):
@@ -121,7 +122,8 @@ def test_mean_scatterings_sphere_peel_log():
     oracle.run(m, rng_mode=0, seed=20240611)
     ns = m.allph("nscatt_gas")
     mean, err = ns.mean(), ns.std() / np.sqrt(n)
-    assert abs(mean - 1.7898e3) < 4 * err, (mean, err)
+    assert golden("sphere_peel_t1tau3", "mean_nscatt") == 1.7898e3
+    assert abs(mean - golden("sphere_peel_t1tau3", "mean_nscatt")) < 4 * err, (mean, err)
     assert m.nscatt_gas / n == pytest.approx(mean, rel=1e-12)
     # python/check_flux.py:45-52 — the peel cube integrates to ~1 (no dust)
     m.output_normalize()
@@ -139,7 +141,8 @@ def test_mean_scatterings_amr_sphere_log():
     oracle.run(m, rng_mode=0, seed=5)
     ns = m.allph("nscatt_gas")
     mean, err = ns.mean(), ns.std() / np.sqrt(n)
-    assert abs(mean - 2.8225e4) < 4 * err, (mean, err)
+    assert golden("amr_sphere_generic_car_1M", "mean_nscatt") == 2.8225e4
+    assert abs(mean - golden("amr_sphere_generic_car_1M", "mean_nscatt")) < 4 * err, (mean, err)
 
 
 # ---- analytic anchors --------------------------------------------------------

@@ -756,6 +756,9 @@ __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const 
     L = fmin(L, fmin(DSUB(pr.y, __ldg(P.yface + pr.jc - 1)), DSUB(__ldg(P.yface + pr.jc), pr.y)));
   }
   if (!(L > 0.0)) return false;
+  // H(x,a) <= H(0,a) < 1: a cell that is too thin even at line centre cannot cap any ray (no Voigt evaluation then:
+  // on the tau0 = 1e4 sphere, 100 per cell, the unconditional test cost 9 %)
+  if (!(DMUL(DADD(cs.rhokap, P.dust ? cs.rhokapD : 0.0), L) >= kTauHuge)) return false;
   double kap = DMUL(cs.rhokap, voigt_seon2(vtab, pr.xfreq, cs.voigt_a));
   if (P.dust) kap = DADD(kap, cs.rhokapD);
   return DMUL(kap, L) >= kTauHuge;

@@ -14,13 +14,21 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+MEDIA = {
+    "cartesian": dict(no_photons=301, temperature=1e4, taumax=30.0, nx=9, ny=9, nz=9, rmax=1.0, nxfreq=41, iseed=3),
+    # the clump population is generated from par%iseed on every rank: identical layouts, as upstream broadcasts it
+    "clumps": dict(no_photons=301, use_clump_medium=True, rmax=1.0, clump_radius=0.05, clump_f_cov=2.0, clump_tau0=5.0,
+                   temperature=1e4, clump_sigma_v=10.0, nxfreq=41, nx=11, ny=11, nz=11, iseed=3),
+}
+
+
+def _worker(rank, world, port, q, medium):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from lart_b200.host import Model, photon_partition
     from oracle import oracle
-    m = Model(no_photons=301, temperature=1e4, taumax=30.0, nx=9, ny=9, nz=9, rmax=1.0, nxfreq=41, iseed=3).setup()
+    m = Model(**MEDIA[medium]).setup()
     first, count, stride = photon_partition(301, rank, world)
     oracle.run(m, rng_mode=1, nthreads=1, first_id=first, count=count, stride=stride)
     t = torch.from_numpy(np.concatenate([m.spectrum("Jout"), m.spectrum("Jin"), [m.nscatt_gas, m.counters["n_photons_done"]]]))
@@ -31,7 +39,11 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_partition_and_reduce_equals_one_rank():
+import pytest
+
+
+@pytest.mark.parametrize("medium", sorted(MEDIA))
+def test_two_rank_partition_and_reduce_equals_one_rank(medium):
     from lart_b200.host import Model, photon_partition
     from oracle import oracle
     # partition covers ids 1..N exactly once for any world size
@@ -43,15 +55,15 @@ def test_two_rank_partition_and_reduce_equals_one_rank():
         assert sorted(ids) == list(range(1, 302))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * sorted(MEDIA).index(medium)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, medium)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    m = Model(no_photons=301, temperature=1e4, taumax=30.0, nx=9, ny=9, nz=9, rmax=1.0, nxfreq=41, iseed=3).setup()
+    m = Model(**MEDIA[medium]).setup()
     oracle.run(m, rng_mode=1, nthreads=1)
     ref = np.concatenate([m.spectrum("Jout"), m.spectrum("Jin"), [m.nscatt_gas, m.counters["n_photons_done"]]])
     assert got[-1] == 301

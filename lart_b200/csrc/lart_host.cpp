@@ -71,7 +71,7 @@ struct Par {
   double atau3 = 0.0;
   double Vexp = 0.0, Vx = 0.0, Vy = 0.0, Vz = 0.0, rpeak = 0.0, Vrot = 0.0, rinner = 0.0;
   // clump medium — define.f90:326-352
-  bool use_clump_medium = false, clump_fully_inside = true;
+  bool use_clump_medium = false, clump_fully_inside = true, clump_allow_overlap = false;
   double clump_radius = -1.0, clump_N_clumps = -1.0, clump_f_vol = -1.0, clump_f_cov = -1.0, clump_tau0 = -1.0,
          clump_NHI = -1.0, clump_sigma_v = 0.0;
   bool comoving_source = true, recoil = false, core_skip = false, core_skip_global = false;
@@ -198,7 +198,7 @@ int set_key(lart_host_model *m, std::string key, const std::string &value) {
   STR(line_id) BOOL(fine_structure)
   REAL(taumax) REAL(tauhomo) REAL(tau0) REAL(N_HImax) REAL(N_HIhomo) REAL(N_HI) REAL(N_gasmax) REAL(N_gashomo)
   REAL(Vexp) REAL(Vx) REAL(Vy) REAL(Vz) REAL(Vrot) REAL(rinner)
-  BOOL(use_clump_medium) BOOL(clump_fully_inside) REAL(clump_radius) REAL(clump_N_clumps) REAL(clump_f_vol)
+  BOOL(use_clump_medium) BOOL(clump_fully_inside) BOOL(clump_allow_overlap) REAL(clump_radius) REAL(clump_N_clumps) REAL(clump_f_vol)
   REAL(clump_f_cov) REAL(clump_tau0) REAL(clump_NHI) REAL(clump_sigma_v)
   BOOL(comoving_source) BOOL(recoil) BOOL(core_skip) BOOL(core_skip_global)
   BOOL(xyz_symmetry) BOOL(xy_symmetry) BOOL(xy_periodic) BOOL(z_symmetry)
@@ -453,7 +453,7 @@ int clumps_create(lart_host_model *m) {
             double ddx = xc - m->cl_x[jn], ddy = yc - m->cl_y[jn], ddz = zc - m->cl_z[jn];
             if (ddx * ddx + ddy * ddy + ddz * ddz < min_sep2) { overlap = true; break; }
           }
-    if (overlap) continue;
+    if (overlap && !p.clump_allow_overlap) continue;  // :1096
     m->cl_x[icl] = xc; m->cl_y[icl] = yc; m->cl_z[icl] = zc;
     if (p.clump_sigma_v > 0.0) {
       m->cl_vx[icl] = p.clump_sigma_v / vtherm * gauss();
@@ -534,6 +534,22 @@ int clumps_create(lart_host_model *m) {
   c.rhokapD = m->cl_rhokapD.empty() ? nullptr : m->cl_rhokapD.data();
   c.voigt_a = m->cl_voigt_a.data(); c.Dfreq = m->cl_Dfreq.data();
   c.cgx = c.cgy = c.cgz = cg; c.has_overlap = 0;
+  if (p.clump_allow_overlap) {  // check_has_overlap (:1544-1590): any pair closer than the sum of its radii
+    for (size_t i = 0; i < n && !c.has_overlap; ++i) {
+      int i0, i1, j0, j1, k0, k1;
+      range(m->cl_x[i], i0, i1); range(m->cl_y[i], j0, j1); range(m->cl_z[i], k0, k1);
+      for (int k = k0; k <= k1 && !c.has_overlap; ++k) for (int j = j0; j <= j1 && !c.has_overlap; ++j) for (int ii = i0; ii <= i1; ++ii) {
+        size_t q = ii + static_cast<size_t>(cg) * (j + static_cast<size_t>(cg) * k);
+        for (int32_t ip = m->cg_start[q]; ip < m->cg_start[q + 1]; ++ip) {
+          const size_t jn = static_cast<size_t>(m->cg_list[ip - 1]) - 1;
+          if (jn <= i) continue;
+          const double ddx = m->cl_x[jn] - m->cl_x[i], ddy = m->cl_y[jn] - m->cl_y[i], ddz = m->cl_z[jn] - m->cl_z[i];
+          if (ddx * ddx + ddy * ddy + ddz * ddz < (2.0 * rcl) * (2.0 * rcl)) { c.has_overlap = 1; break; }
+        }
+        if (c.has_overlap) break;
+      }
+    }
+  }
   c.cg_xmin = c.cg_ymin = c.cg_zmin = cmin; c.cg_dx = c.cg_dy = c.cg_dz = cd;
   c.cg_start = m->cg_start.data(); c.cg_list = m->cg_list.data();
   return 0;

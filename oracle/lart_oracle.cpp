@@ -733,12 +733,192 @@ void raytrace_to_tau_clump(const World &w, Photon &ph, double tau_in, Tally *tl,
   }
   if (cnt) cnt->n_cellsteps += ncell;
 }
+// ---------------------------------------------------------------------------
+// Overlapping clump populations (has_overlap; setup_clump_overlap, setup.f90:1051-1081): the event walk of
+// raytrace_clump.f90:608-920.  photon%xfreq stays in the GLOBAL frame during the walk; every clump containing a point
+// contributes its opacity at its own frame's frequency.
+// ---------------------------------------------------------------------------
+constexpr int kMaxEvt = 2048;  // MAX_EVT, raytrace_clump.f90:683
+struct ClumpEvents {
+  double t[kMaxEvt];
+  int64_t icl[kMaxEvt];
+  int type[kMaxEvt];  // +1 ENTER, -1 EXIT
+  int n = 0;
+};
+// active_set_at_point — clump_mod.f90:1595-1634 (all clumps containing the point, first-seen order, no duplicates)
+inline int active_set_at_point(const lart_clumps &c, double xp, double yp, double zp, int64_t *active, int cap) {
+  const double inv_dx = 1.0 / c.cg_dx, inv_dy = 1.0 / c.cg_dy, inv_dz = 1.0 / c.cg_dz;
+  int ci = std::max(0, std::min(c.cgx - 1, static_cast<int>((xp - c.cg_xmin) * inv_dx)));
+  int cj = std::max(0, std::min(c.cgy - 1, static_cast<int>((yp - c.cg_ymin) * inv_dy)));
+  int ck = std::max(0, std::min(c.cgz - 1, static_cast<int>((zp - c.cg_zmin) * inv_dz)));
+  int na = 0;
+  for (int k = std::max(0, ck - 1); k <= std::min(c.cgz - 1, ck + 1); ++k)
+    for (int j = std::max(0, cj - 1); j <= std::min(c.cgy - 1, cj + 1); ++j)
+      for (int i = std::max(0, ci - 1); i <= std::min(c.cgx - 1, ci + 1); ++i) {
+        const size_t icell = static_cast<size_t>(i) + static_cast<size_t>(c.cgx) * (j + static_cast<size_t>(c.cgy) * k);
+        for (int32_t ip = c.cg_start[icell]; ip < c.cg_start[icell + 1]; ++ip) {
+          const int64_t icl = c.cg_list[ip - 1];
+          double rx = xp - c.x[icl - 1], ry = yp - c.y[icl - 1], rz = zp - c.z[icl - 1];
+          if (rx * rx + ry * ry + rz * rz <= c.radius[icl - 1] * c.radius[icl - 1]) {
+            bool seen = false;
+            for (int m = 0; m < na; ++m) seen = seen || active[m] == icl;
+            if (!seen && na < cap) active[na++] = icl;
+          }
+        }
+      }
+  return na;
+}
+// collect_ray_events_overlap — clump_mod.f90:1639-1760: every ENTER/EXIT along the ray up to t_max, sorted by t
+inline void collect_ray_events_overlap(const lart_clumps &c, double xp, double yp, double zp, double kx, double ky, double kz,
+                                       double t_max, ClumpEvents &ev) {
+  const double inv_dx = 1.0 / c.cg_dx, inv_dy = 1.0 / c.cg_dy, inv_dz = 1.0 / c.cg_dz;
+  ev.n = 0;
+  int ci = std::max(0, std::min(c.cgx - 1, static_cast<int>((xp - c.cg_xmin) * inv_dx)));
+  int cj = std::max(0, std::min(c.cgy - 1, static_cast<int>((yp - c.cg_ymin) * inv_dy)));
+  int ck = std::max(0, std::min(c.cgz - 1, static_cast<int>((zp - c.cg_zmin) * inv_dz)));
+  int si, sj, sk;
+  double tx, ty, tz, delx, dely, delz, d = 0.0;
+  auto axis = [](double k, double p, int cc, double lo, double dd, int &st, double &t, double &del) {
+    if (k > 0.0) { st = 1; del = dd / k; t = (lo + static_cast<double>(cc + 1) * dd - p) / k; }
+    else if (k < 0.0) { st = -1; del = -dd / k; t = (lo + static_cast<double>(cc) * dd - p) / k; }
+    else { st = 0; del = kHugest; t = kHugest; }
+  };
+  axis(kx, xp, ci, c.cg_xmin, c.cg_dx, si, tx, delx);
+  axis(ky, yp, cj, c.cg_ymin, c.cg_dy, sj, ty, dely);
+  axis(kz, zp, ck, c.cg_zmin, c.cg_dz, sk, tz, delz);
+  for (;;) {
+    if (d > t_max) break;
+    if (ci < 0 || ci >= c.cgx || cj < 0 || cj >= c.cgy || ck < 0 || ck >= c.cgz) break;
+    const size_t icell = static_cast<size_t>(ci) + static_cast<size_t>(c.cgx) * (cj + static_cast<size_t>(c.cgy) * ck);
+    for (int32_t ip = c.cg_start[icell]; ip < c.cg_start[icell + 1]; ++ip) {
+      const int64_t icl = c.cg_list[ip - 1];
+      double te, tx2;
+      if (!ray_sphere_isect(c, xp, yp, zp, kx, ky, kz, icl, te, tx2)) continue;
+      if (tx2 <= 0.0 || te > t_max) continue;
+      bool dup = false;
+      for (int ie = 0; ie < ev.n; ++ie) dup = dup || ev.icl[ie] == icl;
+      if (dup || ev.n + 2 > kMaxEvt) continue;
+      if (te > 0.0) { ev.t[ev.n] = te; ev.icl[ev.n] = icl; ev.type[ev.n] = +1; ++ev.n; }
+      ev.t[ev.n] = std::min(tx2, t_max); ev.icl[ev.n] = icl; ev.type[ev.n] = -1; ++ev.n;
+    }
+    if (tx <= ty && tx <= tz) { d = tx; tx += delx; ci += si; }
+    else if (ty <= tz) { d = ty; ty += dely; cj += sj; }
+    else { d = tz; tz += delz; ck += sk; }
+  }
+  for (int ie = 1; ie < ev.n; ++ie) {  // insertion sort, stable for equal t
+    double tt = ev.t[ie]; int64_t ii = ev.icl[ie]; int ty_ = ev.type[ie];
+    int q = ie - 1;
+    while (q >= 0 && ev.t[q] > tt) { ev.t[q + 1] = ev.t[q]; ev.icl[q + 1] = ev.icl[q]; ev.type[q + 1] = ev.type[q]; --q; }
+    ev.t[q + 1] = tt; ev.icl[q + 1] = ii; ev.type[q + 1] = ty_;
+  }
+}
+inline void apply_event(int64_t icl, int type, int64_t *aset, int &na, int cap) {
+  if (type == +1) { if (na < cap) aset[na++] = icl; }
+  else for (int m = 0; m < na; ++m) if (aset[m] == icl) { aset[m] = aset[na - 1]; --na; return; }
+}
+// sum_kap_active / sample_owner_clump — raytrace_clump.f90:621-666
+inline double sum_kap_active(const World &w, const int64_t *active, int na, double xfreq_g, double kx, double ky, double kz) {
+  double s = 0.0;
+  for (int m = 0; m < na; ++m) s = s + kappa_clump(w, xfreq_g - ulos_clump(*w.cl, active[m], kx, ky, kz), active[m]);
+  return s;
+}
+inline int64_t sample_owner_clump(const World &w, Rng &r, const int64_t *active, int na, double xfreq_g, double kx, double ky, double kz) {
+  double cumul = 0.0;
+  const double rnd = r.uniform();
+  int64_t owner = 0;
+  for (int m = 0; m < na; ++m) {
+    cumul = cumul + kappa_clump(w, xfreq_g - ulos_clump(*w.cl, active[m], kx, ky, kz), active[m]);
+    owner = active[m];
+    if (rnd * sum_kap_active(w, active, na, xfreq_g, kx, ky, kz) <= cumul) return owner;
+  }
+  return owner;
+}
+// raytrace_to_edge_clump_overlap (:792-855) and _overlap_capped (:858-920; tau_max > 0)
+double raytrace_to_edge_clump_overlap(const World &w, const Photon &p0, double tau_max, Counters *cnt) {
+  const lart_clumps &c = *w.cl;
+  double tau = 0.0;
+  const double kx = p0.kx, ky = p0.ky, kz = p0.kz, xg = p0.xfreq;
+  const double t_sp = sphere_exit_dist(c, p0.x, p0.y, p0.z, kx, ky, kz);
+  if (t_sp <= 0.0) return tau;
+  static thread_local ClumpEvents ev;
+  static thread_local int64_t active[kMaxEvt];
+  collect_ray_events_overlap(c, p0.x, p0.y, p0.z, kx, ky, kz, t_sp, ev);
+  int na = active_set_at_point(c, p0.x, p0.y, p0.z, active, kMaxEvt);
+  if (cnt) cnt->n_cellsteps += ev.n;
+  double t_cur = 0.0;
+  for (int ie = 0; ie <= ev.n; ++ie) {
+    double t_next = std::min(ie < ev.n ? ev.t[ie] : t_sp, t_sp);
+    double dt = t_next - t_cur;
+    if (dt > 0.0) {
+      tau = tau + sum_kap_active(w, active, na, xg, kx, ky, kz) * dt;
+      if (tau_max > 0.0 && tau >= tau_max) return tau;
+    }
+    t_cur = t_next;
+    if (ie < ev.n) apply_event(ev.icl[ie], ev.type[ie], active, na, kMaxEvt);
+  }
+  return tau;
+}
+// raytrace_to_tau_clump_overlap — raytrace_clump.f90:668-790 (the owner clump is drawn with one uniform)
+void raytrace_to_tau_clump_overlap(const World &w, Photon &ph, double tau_in, Rng &r, Tally *tl, Counters *cnt) {
+  const lart_clumps &c = *w.cl;
+  const lart_grid &g = *w.g;
+  const double kx = ph.kx, ky = ph.ky, kz = ph.kz, xg = ph.xfreq;
+  double tau_rem = tau_in;
+  auto escape = [&]() {
+    ph.inside = false;
+    ph.xfreq_ref = xg;  // see raytrace_to_tau_clump
+    update_cell_idx(w, ph);
+    if (tl) {
+      int ix = static_cast<int>(std::floor((xg - g.xfreq_min) / g.dxfreq)) + 1;
+      if (ix >= 1 && ix <= g.nxfreq) {
+        tl->Jout[ix - 1] += ph.wgt;
+        if (w.par->save_Jmu) tl->Jmu[(ix - 1) + static_cast<size_t>(g.nxfreq) * (jmu_bin(*w.par, ph.kz) - 1)] += ph.wgt;
+      }
+    }
+  };
+  const double t_sp = sphere_exit_dist(c, ph.x, ph.y, ph.z, kx, ky, kz);
+  if (t_sp <= 0.0) { escape(); return; }
+  static thread_local ClumpEvents ev;
+  static thread_local int64_t active[kMaxEvt];
+  collect_ray_events_overlap(c, ph.x, ph.y, ph.z, kx, ky, kz, t_sp, ev);
+  int na = active_set_at_point(c, ph.x, ph.y, ph.z, active, kMaxEvt);
+  if (cnt) cnt->n_cellsteps += ev.n;
+  double t_cur = 0.0;
+  for (int ie = 0; ie <= ev.n; ++ie) {
+    double t_next = std::min(ie < ev.n ? ev.t[ie] : t_sp, t_sp);
+    double dt = t_next - t_cur;
+    if (dt <= 0.0) {
+      if (ie < ev.n) apply_event(ev.icl[ie], ev.type[ie], active, na, kMaxEvt);
+      continue;
+    }
+    double kap_tot = sum_kap_active(w, active, na, xg, kx, ky, kz);
+    if (kap_tot > 0.0 && tau_rem <= kap_tot * dt) {  // scatters inside this segment
+      double ds = tau_rem / kap_tot;
+      ph.x = ph.x + (t_cur + ds) * kx; ph.y = ph.y + (t_cur + ds) * ky; ph.z = ph.z + (t_cur + ds) * kz;
+      ph.xfreq = xg;
+      ph.icl = static_cast<int>(sample_owner_clump(w, r, active, na, xg, kx, ky, kz));
+      update_cell_idx(w, ph);
+      return;
+    }
+    tau_rem = tau_rem - kap_tot * dt;
+    t_cur = t_next;
+    if (ie < ev.n) apply_event(ev.icl[ie], ev.type[ie], active, na, kMaxEvt);
+  }
+  ph.x = ph.x + t_sp * kx; ph.y = ph.y + t_sp * ky; ph.z = ph.z + t_sp * kz;
+  ph.xfreq = xg;
+  ph.icl = 0;
+  escape();
+}
+
 // the ray tracers the procedure pointers select (setup.f90:806-815; peel_raytrace_to_edge, peelingoff_rect.f90:894-906)
 inline double edge_tau(const World &w, const Photon &p, Counters *cnt) {
-  return w.cl ? raytrace_to_edge_clump(w, p, -1.0, cnt) : raytrace_to_edge(w, p, cnt);
+  if (w.cl) return w.cl->has_overlap ? raytrace_to_edge_clump_overlap(w, p, -1.0, cnt) : raytrace_to_edge_clump(w, p, -1.0, cnt);
+  return raytrace_to_edge(w, p, cnt);
 }
 inline double peel_tau(const World &w, const Photon &p, Counters *cnt) {
-  return w.cl ? raytrace_to_edge_clump(w, p, kTauHugeClump, cnt) : raytrace_to_edge(w, p, cnt);
+  if (w.cl) return w.cl->has_overlap ? raytrace_to_edge_clump_overlap(w, p, kTauHugeClump, cnt)
+                                     : raytrace_to_edge_clump(w, p, kTauHugeClump, cnt);
+  return raytrace_to_edge(w, p, cnt);
 }
 // line-of-sight fluid velocity for the peel-off frequency (peelingoff_rect.f90:186-192, 403-409, 534-540, 658-664)
 inline double peel_u1(const World &w, const Photon &ph, const Photon &po) {
@@ -1356,8 +1536,11 @@ void scattering(const World &w, Photon &ph, Rng &r, Tally &tl) {
     if (w.par->use_stokes) scatter_dust_stokes(w, ph, r, tl);
     else scatter_dust_nostokes(w, ph, r, tl);
   } else {
+    const bool ov = w.cl && w.cl->has_overlap;  // scatter_resonance_clump_* wrappers (scattering_car.f90:897-945)
+    if (ov) ph.xfreq = ph.xfreq - ulos_clump(*w.cl, ph.icl, ph.kx, ph.ky, ph.kz);
     if (w.par->use_stokes) scatter_resonance_stokes(w, ph, r, tl);
     else scatter_resonance_nostokes(w, ph, r, tl);
+    if (ov) ph.xfreq = ph.xfreq + ulos_clump(*w.cl, ph.icl, ph.kx, ph.ky, ph.kz);
   }
 }
 
@@ -1446,7 +1629,7 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
     int ix = static_cast<int>(std::floor((xlab - g.xfreq_min) / g.dxfreq)) + 1;
     if (ix >= 1 && ix <= g.nxfreq) tl.Jin[ix - 1] += ph.wgt;
   }
-  if (w.cl) {  // :325-332 — the birth clump, before the direct peel
+  if (w.cl && !w.cl->has_overlap) {  // :325-332 — the birth clump, before the direct peel
     const int64_t icl = clump_at_point(*w.cl, ph.x, ph.y, ph.z);
     ph.icl = static_cast<int>(icl);
     if (icl > 0) ph.xfreq = ph.xfreq - ulos_clump(*w.cl, icl, ph.kx, ph.ky, ph.kz);
@@ -1539,7 +1722,8 @@ void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_event
     } else {
       tau = -std::log(r.uniform());
     }
-    if (w.cl) raytrace_to_tau_clump(w, ph, tau, &tl, &tl.cnt);
+    if (w.cl && w.cl->has_overlap) raytrace_to_tau_clump_overlap(w, ph, tau, r, &tl, &tl.cnt);
+    else if (w.cl) raytrace_to_tau_clump(w, ph, tau, &tl, &tl.cnt);
     else raytrace_to_tau(w, ph, tau, &tl, &tl.cnt);
     if (ph.inside) {
       scattering(w, ph, r, tl);
@@ -1737,7 +1921,7 @@ int oracle_clump_edge(const lart_config *cfg, int64_t n, const double *x, const 
     Photon p;
     p.x = x[i]; p.y = y[i]; p.z = z[i]; p.kx = kx[i]; p.ky = ky[i]; p.kz = kz[i]; p.xfreq = xfreq[i]; p.icl = icl[i];
     int nc = 0;
-    tau[i] = raytrace_to_edge_clump(w, p, tau_max, nullptr, &nc);
+    tau[i] = w.cl->has_overlap ? raytrace_to_edge_clump_overlap(w, p, tau_max, nullptr) : raytrace_to_edge_clump(w, p, tau_max, nullptr, &nc);
     if (nclumps) nclumps[i] = nc;
   }
   return 0;

@@ -187,3 +187,51 @@ def test_setup_scalars_clump_sphere_log():
     # heavy-tailed (sigma/mean = 5.4), so a CPU-sized sample can only bracket it
     oracle.run(m, rng_mode=0)
     assert 2.5e3 < m.nscatt_gas / 1000 < 7e3
+
+
+def test_overlapping_population_event_walk_equals_brute_force():
+    """has_overlap (clump_mod.f90:1544-1590, 1639-1760; raytrace_clump.f90:608-920): in an overlap region every clump adds
+    its opacity at its own frame's frequency; the frequency stays in the global frame during the walk.  The GPU engine
+    refuses such populations for now (lart_gpu_create); this pins the oracle for the day it does not."""
+    m = clump_model(clump_allow_overlap=True, clump_radius=0.08, clump_f_cov=3.0, clump_sigma_v=15.0, velocity_type="hubble",
+                    Vexp=60.0)
+    A = clump_arrays(m)
+    c = A["c"]
+    assert c.has_overlap == 1
+    from scipy.spatial import cKDTree
+    P = np.c_[A["x"], A["y"], A["z"]]
+    d, _ = cKDTree(P).query(P, k=2)
+    assert d[:, 1].min() < 2 * 0.08  # really overlapping
+    rng = np.random.default_rng(17)
+    n = 2000
+    p, k = rays_from(rng, n)
+    xf = rng.normal(size=n) * 2
+    V = np.c_[A["vx"], A["vy"], A["vz"]]
+    tau_bf = np.zeros(n)
+    for i in range(n):
+        r = p[i] - P
+        b = r @ k[i]
+        disc = b * b - (r * r).sum(1) + A["r"] ** 2
+        hit = disc > 0
+        sq = np.sqrt(np.maximum(disc, 0))
+        t1, t2 = -b - sq, -b + sq
+        bs = p[i] @ k[i]
+        t_sp = -bs + np.sqrt(bs * bs - p[i] @ p[i] + 1.0)
+        chord = np.minimum(t2, t_sp) - np.maximum(t1, 0)
+        use = hit & (t2 > 0) & (chord > 0)
+        x_cl = xf[i] - V @ k[i]  # global-frame frequency seen in each clump's frame
+        tau_bf[i] = (A["kap"][use] * oracle.voigt(x_cl[use], A["a"][0]) * chord[use]).sum()
+    icl0 = np.zeros(n, dtype=np.int32)  # the overlap walk finds its own active set
+    tau, _ = oracle.clump_edge(m.config, p[:, 0], p[:, 1], p[:, 2], k[:, 0], k[:, 1], k[:, 2], xf, icl0)
+    assert np.allclose(tau, tau_bf, rtol=1e-9, atol=1e-12) and (tau > 0).mean() > 0.6
+    cap = np.median(tau)
+    tc, _ = oracle.clump_edge(m.config, p[:, 0], p[:, 1], p[:, 2], k[:, 0], k[:, 1], k[:, 2], xf, icl0, tau_max=cap)
+    assert np.array_equal(tc[tau < cap], tau[tau < cap]) and np.all(tc[tau >= cap] >= cap)
+    # whole runs: every photon accounted for, no dust -> everything escapes; photons scatter in some owner clump
+    run = clump_model(clump_allow_overlap=True, clump_radius=0.08, clump_f_cov=3.0, clump_sigma_v=15.0, no_photons=3000,
+                      nxim=9, nyim=9, use_stokes=True, save_all_photons=True, xfreq_min=-30.0, xfreq_max=30.0)
+    oracle.run(run, rng_mode=1)
+    assert run.counters["n_photons_done"] == 3000 and run.spectrum("Jout").sum() == pytest.approx(3000, rel=1e-3)
+    assert run.nscatt_gas / 3000 > 3 and run.observer_cube("scatt").sum() > 0
+    # the GPU engine's validation rejects the population (CPU-checkable part: the flag travels through the ABI struct)
+    assert run.config.contents.clumps.has_overlap == 1

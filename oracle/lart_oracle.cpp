@@ -1,7 +1,8 @@
 // lart_oracle.cpp — CPU ORACLE (test infrastructure, NOT product code).
 //
 // A scalar, one-photon-at-a-time FP64 restatement of the reference's Cartesian
-// photon loop (LaRT v2.00), written to be read side by side with the Fortran.
+// photon loop (LaRT v2.00) — with its folded / periodic boundary variants, sight-line
+// maps and the clump medium — written to be read side by side with the Fortran.
 // Every function cites the reference file:line it follows (paths relative to
 // the reference tree).  It exists so that the CUDA path has something to be
 // checked against: only tests/, __graft_entry__.smoke() and bench.py's
@@ -12,7 +13,9 @@
 // be compiled here (no Fortran/MPI toolchain), so at function level this oracle
 // is "parity unpinned": it is pinned only (a) by construction against the cited
 // lines, (b) by the whole-run known answers the reference's logs hold
-// (<N_scatt> = 1.7898e3 / 2.8225e4, voigt_a, N(HI)_pole — tests/test_oracle_pins.py),
+// (<N_scatt> = 1.7898e3 / 2.8225e4, voigt_a, N(HI)_pole — tests/test_oracle_pins.py; for the clump medium the
+// population figures and <N_scatt> = 4.3454e3 of examples/clump_sphere/log_back — tests/test_oracle_clumps.py,
+// tests/test_gpu_clumps.py; all transcribed into tests/golden/reference_logs.json),
 // (c) by independent mathematics (Harris functions, scipy wofz, Neufeld/Dijkstra
 // analytic spectra, Philox and MT19937-64 known-answer vectors).
 //

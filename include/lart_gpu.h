@@ -175,6 +175,11 @@ typedef struct lart_config {
                                       each advanced on its own CUDA stream; 0 = auto (6) */
   int32_t ray_budget;              /* cell steps a transport or peel ray may take per wave before it is
                                       parked and resumed (exactly) in the next wave; 0 = auto (32) */
+  int32_t max_events;              /* bounded runs (benchmarks and parity runs of cases where a photon needs ~1e7
+                                      scatterings to escape): a photon is abandoned after this many scatterings — no Jout
+                                      tally, its allph record holds the state it had (current frequency in xfreq2);
+                                      0 = every photon runs until it escapes or is absorbed, as in the reference */
+  int32_t pad_;
 } lart_config;
 
 enum {
@@ -185,9 +190,12 @@ enum {
   LART_FLAG_STAGE_TIMING = 8, /* CUDA-event timing of every stage kernel (bench/roofline) */
   LART_FLAG_SERIAL_REJECTION = 16, /* per-lane rejection loops instead of the warp-cooperative
                                       atom-velocity sampler (ablation; same results) */
-  LART_FLAG_LOCAL_STEPS = 32       /* the scatter stage takes the first cell step of the peel ray and
+  LART_FLAG_LOCAL_STEPS = 32,      /* the scatter stage takes the first cell step of the peel ray and
                                       of the next flight itself; only longer rays reach the queues
                                       (experimental; same results) */
+  LART_FLAG_DEBUG_TINY_QUEUES = 64 /* tests only: one direct-peel entry per pool partition, so that the
+                                      queue-overflow error path (sticky device error word -> error
+                                      return of lart_gpu_step / _sync / _fetch) can be exercised */
 };
 
 /* stage kernels of one wave, in launch order (index into lart_gpu_stage_ms) */
@@ -213,6 +221,9 @@ typedef struct lart_counters {
   double n_peel;        /* peel-off rays traced                             */
   double n_rng;         /* uniforms drawn                                   */
   double n_reject_iter; /* iterations of the rejection loops                */
+  double n_peel_bound;  /* of n_peel: rays the scatter stage proved to end inside their own cell at the tau cap
+                           (raytrace_car.f90:432,497) and therefore counted without queueing or walking them */
+  double n_cellsteps_bound; /* of n_cellsteps: the one cell step each such ray would have taken (not walked) */
 } lart_counters;
 
 typedef struct lart_tallies {
@@ -325,6 +336,14 @@ int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n,
                          const double *x, const double *y, const double *z,
                          const int32_t *icell, const int32_t *jcell, const int32_t *kcell,
                          double *xcrit);
+
+/* The scatter stage's shortcut for peel-off rays, exposed for the parity tests: capped[i] = 1 when the library can
+ * prove — from kappa(xfreq) times the distance to the nearest face of the ray's start cell — that raytrace_to_edge
+ * would stop inside that cell with tau >= tau_huge = 745.2 (src/raytrace_car.f90:432,497), i.e. the ray's
+ * contribution exp(-tau) is exactly zero whatever its direction.  Such rays are counted and not walked. */
+int lart_gpu_peel_bound_batch(lart_gpu_handle h, int64_t n,
+                              const double *x, const double *y, const double *z, const double *xfreq,
+                              const int32_t *icell, const int32_t *jcell, const int32_t *kcell, int32_t *capped);
 
 /* ---- next row: clump-medium ray tracers, unit level ---------------------------------
  * raytrace_to_edge_clump (src/raytrace_clump.f90:205-270; tau_max <= 0) or raytrace_to_edge_clump_capped

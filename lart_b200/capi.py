@@ -28,6 +28,7 @@ FLAG_MONOLITHIC = 4
 FLAG_STAGE_TIMING = 8
 FLAG_SERIAL_REJECTION = 16
 FLAG_LOCAL_STEPS = 32
+FLAG_DEBUG_TINY_QUEUES = 64
 STAGES = ["emit", "trace", "scatter", "peel"]
 
 
@@ -95,13 +96,15 @@ class Clumps(C.Structure):
 class Config(C.Structure):
     _fields_ = [("grid", Grid), ("par", Params), ("line", Line), ("scatt_mat", ScattMat), ("clumps", Clumps),
                 ("observers", C.POINTER(Observer)), ("device", C.c_int32), ("pool_slots", C.c_int32),
-                ("quantum", C.c_int32), ("flags", C.c_int32), ("streams", C.c_int32), ("ray_budget", C.c_int32)]
+                ("quantum", C.c_int32), ("flags", C.c_int32), ("streams", C.c_int32), ("ray_budget", C.c_int32),
+                ("max_events", C.c_int32), ("pad_", C.c_int32)]
 
 
 OBS_FIELDS = ["scatt", "direc", "direc0", "I", "Q", "U", "V",
               "scatt_2D", "direc_2D", "direc0_2D", "I_2D", "Q_2D", "U_2D", "V_2D"]
 ALLPH_FIELDS = ["rp0", "rp", "xfreq1", "xfreq2", "nscatt_gas", "nscatt_dust", "I", "Q", "U", "V"]
-COUNTER_FIELDS = ["n_photons_done", "n_scatter", "n_cellsteps", "n_peel", "n_rng", "n_reject_iter"]
+COUNTER_FIELDS = ["n_photons_done", "n_scatter", "n_cellsteps", "n_peel", "n_rng", "n_reject_iter", "n_peel_bound",
+                  "n_cellsteps_bound"]
 
 
 class ObserverOut(C.Structure):
@@ -143,7 +146,7 @@ GPU_SYMBOLS = [
     "lart_gpu_raytrace_edge_batch", "lart_gpu_raytrace_tau_batch", "lart_gpu_sample_batch",
     "lart_gpu_xcrit_batch", "lart_gpu_version", "lart_gpu_stage_ms", "lart_gpu_pool_slots", "lart_gpu_measure_fp64",
     "lart_gpu_sightline_tau", "lart_gpu_sightline_stats",
-    "lart_gpu_clump_edge_batch", "lart_gpu_clump_tau_batch", "lart_gpu_clump_locate_batch",
+    "lart_gpu_clump_edge_batch", "lart_gpu_clump_tau_batch", "lart_gpu_clump_locate_batch", "lart_gpu_peel_bound_batch",
 ]
 HOST_SYMBOLS = [
     "lart_host_new", "lart_host_free", "lart_host_set", "lart_host_read_input", "lart_host_setup",
@@ -226,5 +229,7 @@ def load_gpu():
         lib.lart_gpu_clump_edge_batch.argtypes = [H, C.c_int64] + [c_double_p] * 7 + [c_int32_p, C.c_double, c_double_p, c_int32_p]
         lib.lart_gpu_clump_tau_batch.argtypes = [H, C.c_int64] + [c_double_p] * 7 + [c_int32_p, c_double_p, c_int32_p]
         lib.lart_gpu_clump_locate_batch.argtypes = [H, C.c_int64] + [c_double_p] * 3 + [c_int32_p]
+        if hasattr(lib, "lart_gpu_peel_bound_batch"):  # (absent from older A/B builds selected through LART_GPU_LIB)
+            lib.lart_gpu_peel_bound_batch.argtypes = [H, C.c_int64] + [c_double_p] * 4 + [c_int32_p] * 4
         _gpu = lib
     return _gpu

@@ -46,11 +46,13 @@ struct TallyLayout {
   long long cube[7];               // scatt, direc, direc0, I, Q, U, V   (within an observer block)
   long long img[7];                // the same, 2-D
   long long scalars;               // nscatt_gas, nscatt_dust
-  long long counters;              // 6 work counters
+  long long counters;              // C_COUNT work counters
   long long total;
 };
 enum { T_SCATT = 0, T_DIREC = 1, T_DIREC0 = 2, T_I = 3, T_Q = 4, T_U = 5, T_V = 6 };
-enum { C_PHOTONS = 0, C_SCATTER = 1, C_CELLSTEPS = 2, C_PEEL = 3, C_RNG = 4, C_REJECT = 5 };
+enum { C_PHOTONS = 0, C_SCATTER = 1, C_CELLSTEPS = 2, C_PEEL = 3, C_RNG = 4, C_REJECT = 5, C_PEEL_BOUND = 6, C_COUNT = 8 };
+// sticky device error word (lart_gpu_step / _sync / _fetch return it as an error): work that could not be queued
+enum { ERR_DIRECT_QUEUE = 1, ERR_CONT_QUEUE = 2, ERR_BAD_STATE = 4 };
 
 // Everything a kernel needs, passed by value as a __grid_constant__ parameter.
 // clump medium (lart_clump.cuh): geometry record = centre + radius^2 (one 32-byte sector per ray-sphere test),
@@ -92,6 +94,8 @@ struct DevParams {
   int zonly, dust, soa, comoving_source, recoil, core_skip, core_skip_global, use_stokes, use_reduced_wgt;
   int save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D, save_direc0, save_all_photons;
   int warp_agg;
+  int max_events;       // lart_config::max_events (0 = unbounded)
+  unsigned int *err;    // sticky ERR_* bits
   int flags_serial_vz;  // ablation: per-lane rejection loops instead of the warp-cooperative sampler
   int local_steps;      // scatter stage resolves 1-cell peel rays / 1-cell flights itself (0: ablation)
   int nobs;
@@ -133,7 +137,7 @@ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint3
 // per-thread work counters of ONE kernel launch (32 bits are plenty; they are summed into FP64 totals)
 typedef unsigned int ctr_t;
 struct Counters {
-  ctr_t scatter = 0, cellsteps = 0, peel = 0, rng = 0, reject = 0, photons = 0;
+  ctr_t scatter = 0, cellsteps = 0, peel = 0, rng = 0, reject = 0, photons = 0, peel_bound = 0;
 };
 
 // Stream layout (shared with the CPU oracle): every call consumes ONE Philox block of
@@ -965,21 +969,28 @@ LART_DEV bool peel_direct_prepare(const DevParams &P, const DevObserver &ob, int
 }
 
 // peeling_resonance_stokes_outside — peelingoff_rect.f90:303-482
-LART_DEV bool peel_resonance_stokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+// `drop(pr)` is asked as soon as the ray's start, direction and frequency are known: a ray the caller can prove to
+// contribute exactly zero (tau cap inside its own cell) skips the Stokes algebra.  Returns 0 = outside the image
+// (no ray), 1 = descriptor complete, 2 = dropped.
+struct NeverDrop { LART_DEV bool operator()(const PeelRay &) const { return false; } };
+template <class Drop>
+LART_DEV int peel_resonance_stokes_prepare2(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
                                             const CellData &cs, double xfreq_atom, double ux, double uy, double uz,
-                                            PeelRay &pr) {
+                                            PeelRay &pr, Drop &&drop) {
   double r2;
-  if (!peel_geometry(ob, ph, pr, r2)) return false;
+  if (!peel_geometry(ob, ph, pr, r2)) return 0;
   double cost = ph.kx * pr.kx + ph.ky * pr.ky + ph.kz * pr.kz;
   double sint, cosp, sinp, nx, ny, nz;
   stokes_azimuth(ph, pr, cost, sint, cosp, sinp, nx, ny, nz);
+  double xfreq = xfreq_atom + (ux * cosp + uy * sinp) * sint + uz * cost;  // :392
+  if (P.recoil) xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
+  pr.xfreq = xfreq;
+  if (drop(pr)) return 2;
   double cos2p = 1.0, sin2p = 0.0;
   if (sint != 0.0) { cos2p = 2.0 * cosp * cosp - 1.0; sin2p = 2.0 * cosp * sinp; }
   double cost2 = cost * cost;
   double S22 = 0.75 * P.E1 * (cost2 + 1.0), S11 = S22 + P.E2, S12 = 0.75 * P.E1 * (cost2 - 1.0);
   double S33 = 1.5 * P.E1 * cost, S44 = 1.5 * P.E3 * cost;
-  double xfreq = xfreq_atom + (ux * cosp + uy * sinp) * sint + uz * cost;  // :392
-  if (P.recoil) xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
   double u1 = vdotk(cs, pr.kx, pr.ky, pr.kz);
   double xref = (xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
   int ixf = freq_bin(P, xref);
@@ -987,21 +998,26 @@ LART_DEV bool peel_resonance_stokes_prepare(const DevParams &P, const DevObserve
   const double i4pi = 1.0 / kFourPi;
   double Iobs = (S11 + S12 * Q0) * i4pi, Qobs = (S12 + S22 * Q0) * i4pi;
   double Uobs = (S33 * U0) * i4pi, Vobs = (S44 * ph.V) * i4pi;
-  pr.xfreq = xfreq;
   pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
   pr.obs = iobs; pr.kind = PEEL_STOKES;
   pr.wa = 1.0 / r2; pr.wb = ph.wgt;
   pr.sI = Iobs; pr.sV = Vobs;
   to_detector(ob, nx, ny, nz, Qobs, Uobs, pr.sQ, pr.sU);
-  return true;
+  return 1;
+}
+LART_DEV bool peel_resonance_stokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+                                            const CellData &cs, double xfreq_atom, double ux, double uy, double uz,
+                                            PeelRay &pr) {
+  return peel_resonance_stokes_prepare2(P, ob, iobs, ph, cs, xfreq_atom, ux, uy, uz, pr, NeverDrop()) == 1;
 }
 
 // peeling_resonance_nostokes_outside — peelingoff_rect.f90:576-690
-LART_DEV bool peel_resonance_nostokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+template <class Drop>
+LART_DEV int peel_resonance_nostokes_prepare2(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
                                               const CellData &cs, double xfreq_atom, double ux, double uy, double uz,
-                                              PeelRay &pr) {
+                                              PeelRay &pr, Drop &&drop) {
   double r2;
-  if (!peel_geometry(ob, ph, pr, r2)) return false;
+  if (!peel_geometry(ob, ph, pr, r2)) return 0;
   double cost = ph.kx * pr.kx + ph.ky * pr.ky + ph.kz * pr.kz;
   double cost2 = cost * cost;
   double sint = sqrt(1.0 - cost2);
@@ -1014,16 +1030,22 @@ LART_DEV bool peel_resonance_nostokes_prepare(const DevParams &P, const DevObser
   }
   double xfreq = xfreq_atom + (ux * cosp + uy * sinp) * sint + uz * cost;
   if (P.recoil) xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
+  pr.xfreq = xfreq;
+  if (drop(pr)) return 2;
   double u1 = vdotk(cs, pr.kx, pr.ky, pr.kz);
   double xref = (xfreq + u1) * (cs.Dfreq / P.Dfreq_ref);
   int ixf = freq_bin(P, xref);
-  pr.xfreq = xfreq;
   pr.ixf = (ixf >= 1 && ixf <= P.nxfreq) ? ixf : 0;
   pr.obs = iobs; pr.kind = PEEL_NOSTOKES;
   double peel = 0.75 * P.E1 * (cost2 + 1.0) + P.E2;
   pr.wa = peel / (kFourPi * r2); pr.wb = ph.wgt;
   pr.sI = pr.sQ = pr.sU = pr.sV = 0.0;
-  return true;
+  return 1;
+}
+LART_DEV bool peel_resonance_nostokes_prepare(const DevParams &P, const DevObserver &ob, int iobs, const Photon &ph,
+                                              const CellData &cs, double xfreq_atom, double ux, double uy, double uz,
+                                              PeelRay &pr) {
+  return peel_resonance_nostokes_prepare2(P, ob, iobs, ph, cs, xfreq_atom, ux, uy, uz, pr, NeverDrop()) == 1;
 }
 
 // peeling_dust_stokes_outside — peelingoff_rect.f90:131-299
@@ -1093,8 +1115,9 @@ LART_DEV void peel_deposit(const DevParams &P, const PeelRay &pr, double tau, un
   if (!nonzero) return;
   bool leader = true;
   if (P.warp_agg && aggregate) {
-    unsigned long long key = ((unsigned long long)(unsigned)pr.kind << 60) ^ ((unsigned long long)(unsigned)pr.obs << 44) ^
-                             ((unsigned long long)(unsigned)pr.pix << 12) ^ (unsigned long long)(unsigned)pr.ixf;
+    // collision-free: ixf < 2^24, pix < 2^30, obs < 2^8 (lart_gpu_create checks the first two; LART_MAX_OBSERVERS = 181)
+    unsigned long long key = ((unsigned long long)(unsigned)pr.kind << 62) | ((unsigned long long)(unsigned)pr.obs << 54) |
+                             ((unsigned long long)(unsigned)pr.pix << 24) | (unsigned long long)(unsigned)pr.ixf;
     unsigned grp = __match_any_sync(lanes, key);
     int lane = threadIdx.x & 31;
     int lead = __ffs(grp) - 1;
@@ -1212,9 +1235,12 @@ struct ScatterOut {
 // `uz` = rand_resonance_vz(x, a) has been drawn by the caller (serially, or warp-cooperatively).
 // CLUMP: uz and xfreq_atom come from do_resonance1_clump (line_clump_mod.f90:29-58) and the perpendicular atom
 // velocity is rescaled by vth_ratio = cl_Dfreq/cl_Dfreq_ref (scattering_car.f90:384-388, 715-719)
-template <bool CLUMP, class PeelFn>
+// STOKES: 1 / 0 = par%use_stokes known at compile time (the wavefront scatter stage is instantiated per value),
+// -1 = read it from P.
+template <bool CLUMP, int STOKES = -1, class PeelFn>
 LART_DEV void scatter_resonance_core(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, double uz,
                                      double xfreq_atom, double vth_ratio, PeelFn &&peel) {
+  const bool stokes = STOKES < 0 ? (P.use_stokes != 0) : (STOKES != 0);
   ph.nsg += ph.wgt;
   double cost = rand_resonance_fast(r, P);
   double sint = sqrt(1.0 - cost * cost);
@@ -1222,13 +1248,13 @@ LART_DEV void scatter_resonance_core(const DevParams &P, Photon &ph, Rng &r, con
   double S22 = 0.75 * P.E1 * (cost2 + 1.0), S11 = S22 + P.E2, S12 = 0.75 * P.E1 * (cost2 - 1.0);
   double S33 = 1.5 * P.E1 * cost, S44 = 1.5 * P.E3 * cost;
   double cosp, sinp;
-  if (P.use_stokes) sample_phi_stokes(r, ph, S12 / S11, cnt.reject, cosp, sinp);
+  if (stokes) sample_phi_stokes(r, ph, S12 / S11, cnt.reject, cosp, sinp);
   else sincospi(2.0 * r.uniform(), &sinp, &cosp);
   double xc = 0.0, xc2 = 0.0;
   if (P.core_skip) car_xcrit_local(P, ph.ic, ph.jc, ph.kc, ph.x, ph.y, ph.z, cs.voigt_a, cs.rhokap, xc, xc2);
   bool skip = P.core_skip && fabs(ph.xfreq) < xc;
   double ux, uy;
-  if (P.use_stokes && !skip) {  // :413-414
+  if (stokes && !skip) {  // :413-414
     const double one_over_sqrt2 = 1.0 / 1.4142135623730951;
     ux = r.gauss(cnt.reject) * one_over_sqrt2;
     uy = r.gauss(cnt.reject) * one_over_sqrt2;
@@ -1244,7 +1270,7 @@ LART_DEV void scatter_resonance_core(const DevParams &P, Photon &ph, Rng &r, con
   ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
   if (P.recoil) ph.xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
   if (P.save_peeloff) peel(xfreq_atom, ux, uy, uz);
-  if (P.use_stokes) {
+  if (stokes) {
     double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
     double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
     double I1 = S11 + S12 * Q0, Q1 = S12 + S22 * Q0, U1 = S33 * U0, V1 = S44 * ph.V;
@@ -1281,7 +1307,7 @@ template <class PeelFn>
 LART_DEV void scatter_resonance(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, double uz,
                                 PeelFn &&peel) {
   // do_resonance1 — line_mod.f90:108-139
-  scatter_resonance_core<false>(P, ph, r, cs, cnt, uz, ph.xfreq - uz, 1.0, peel);
+  scatter_resonance_core<false, -1>(P, ph, r, cs, cnt, uz, ph.xfreq - uz, 1.0, peel);
 }
 template <class PeelFn>
 LART_DEV void scatter_dust(const DevParams &P, Photon &ph, Rng &r, const CellData &cs, Counters &cnt, PeelFn &&peel) {

@@ -77,12 +77,14 @@ struct Pool {
   int *ic, *jc, *kc, *flags;   // [S]
   double *rs;                  // [10][S] DDA state of a flight suspended at its per-wave step budget
   int *rc;                     // [3][S]  ... and its current cell
+  int *nev;                    // [S] scatterings of the slot's photon so far (bounded runs, lart_config::max_events)
   int S;                       // slots (= SoA stride)
   int s0, n;                   // the partition [s0, s0+n) this kernel launch works on
 };
 struct Job {  // photon ids = first_id + j*stride, j in [0,count)
   unsigned long long next, count, done;
   long long first_id, stride;
+  unsigned int err, pad_;  // sticky ERR_* bits (DevParams::err points here); read back with the job after every step
 };
 struct Queues {  // one per pool partition (pipeline)
   PeelRay *rays;      // [ray_cap]: S*nobs slot rays, then per partition the direct rays of this wave's emits
@@ -156,19 +158,20 @@ __device__ __forceinline__ void load_vtab(const DevParams &P, double *vtab) {
 // and block.  (Per-warp atomics on six hot addresses cost ~28 us per kernel: 14 k same-address FP64 REDs
 // serialise in one L2 slice — the floor of every wave when few photons are in flight.)
 __device__ void flush_counters(const DevParams &P, Counters &c, ctr_t nrng) {
-  __shared__ unsigned long long part[6][kBlock / 32];
+  constexpr int NC = 7;
+  __shared__ unsigned long long part[NC][kBlock / 32];
   c.rng += nrng;
-  unsigned long long v[6] = {c.photons, c.scatter, c.cellsteps, c.peel, c.rng, c.reject};  // widened for the sums
+  unsigned long long v[NC] = {c.photons, c.scatter, c.cellsteps, c.peel, c.rng, c.reject, c.peel_bound};  // widened for the sums
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
+  for (int q = 0; q < NC; ++q) {
     unsigned long long x = v[q];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if (lane == 0) part[q][warp] = x;
   }
   __syncthreads();
-  if (threadIdx.x < 6) {
+  if (threadIdx.x < NC) {
     unsigned long long x = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += part[threadIdx.x][w];
     if (x) atomicAdd(P.tally + P.lay.counters + threadIdx.x, (double)x);
@@ -273,10 +276,12 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
     Rng rng;
     ph.flags = pl.flags[s];
     bool rng_valid = false, touched = false;
+    int nev = 0;  // scatterings of this photon so far (bounded runs)
     if (ph.flags & PH_ALIVE) {
       load_trace_part(pl, s, ph);
       load_rest(pl, s, ph);
       load_rng(P, pl, s, ph.id, ph.flags, rng);
+      nev = pl.nev[s];
       rng_valid = true;
     }
     bool at_scatter = (ph.flags & PH_ALIVE) && (ph.flags & PH_SCATTER);
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
           if (rng_valid) nrng += rng.nrng;  // draws of the previous photon in this slot
           rng.start(P.seed, (unsigned long long)ph.id);
           rng_valid = true;
+          nev = 0;
           generate_photon(P, ph, rng, cnt, cs);
           if (P.save_all_photons) record_initial(P, ph);
           if (P.save_peeloff) {  // peeling_direct — generate_photon.f90:334-336
@@ -366,12 +372,18 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
           }
         });
       }
+      if (P.max_events > 0 && (ph.flags & PH_ALIVE) && ++nev >= P.max_events) {  // bounded run: abandon, record as it stands
+        ph.flags &= ~PH_ALIVE;
+        ph.xfreq_ref = ph.xfreq;
+        retire_photon(P, ph, false, job, cnt);
+      }
     }
     if (touched) {
       int fl = ph.flags;
       if (fl & PH_ALIVE) store_rng(pl, s, rng, fl);
       ph.flags = fl;
       store_all(pl, s, ph);
+      pl.nev[s] = nev;
     }
     if (rng_valid) nrng += rng.nrng;
   }
@@ -400,11 +412,13 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
     int icl = 0;
     ph.flags = valid ? pl.flags[s] : 0;
     bool rng_valid = false, touched = false;
+    int nev = 0;
     if (ph.flags & PH_ALIVE) {
       load_trace_part(pl, s, ph);
       load_rest(pl, s, ph);
       load_rng(P, pl, s, ph.id, ph.flags, rng);
       icl = pl.rc[s];
+      nev = pl.nev[s];
       rng_valid = true;
     }
     // a slot the wavefront flight stage already flew to its next scattering point (driver switch in lart_gpu_run)
@@ -437,6 +451,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
           if (rng_valid) nrng += rng.nrng;
           rng.start(P.seed, (unsigned long long)ph.id);
           rng_valid = true;
+          nev = 0;
           generate_photon(P, ph, rng, cnt, cs);
           icl = clump_at_point(C, ph.x, ph.y, ph.z);  // the birth clump, before the direct peel (generate_photon.f90:325-332)
           csp0 = cs;
@@ -527,6 +542,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
             }
           });
         }
+        if (P.max_events > 0 && (ph.flags & PH_ALIVE) && ++nev >= P.max_events) {
+          ph.flags &= ~PH_ALIVE;
+          ph.xfreq_ref = ph.xfreq;
+          retire_photon(P, ph, false, job, cnt);
+        }
       }
       __syncwarp(FULLW);
     }
@@ -536,6 +556,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
       ph.flags = fl;
       store_all(pl, s, ph);
       pl.rc[s] = icl;
+      pl.nev[s] = nev;
     }
     if (rng_valid) nrng += rng.nrng;
   }
@@ -584,12 +605,14 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
         if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
         unsigned at = atomicAdd(q.n_direct, 1u);
         if (at < q.direct_cap) ray_store(q.rays + q.direct_base + at, pr);
+        else atomicOr(P.err, (unsigned)ERR_DIRECT_QUEUE);  // cannot happen by sizing; never drop a ray silently
       }
     }
     int fl = ph.flags;
     store_rng(pl, s, rng, fl);
     ph.flags = fl;
     store_all(pl, s, ph);
+    pl.nev[s] = 0;
     nrng += rng.nrng;
   }
   flush_counters(P, cnt, nrng);
@@ -734,21 +757,39 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
   flush_counters(P, cnt, nrng);
 }
 
-// stage 3: scattering for every photon flagged by the trace stage; writes the
-// peel-ray descriptors of its slot.  The slot loop is warp-uniform (inactive lanes stay in
-// it) so that the atom-velocity rejection sampler can run warp-cooperatively.
+// stage 3: scattering for every photon flagged by the trace stage; writes the peel-ray descriptors of its slot.
+//
+// * Compile-time variants <STOKES, DUST, LOCAL>: the instantiation a run uses carries only its own physics (no
+//   Mueller/alias/HG code in a dust-free run, one peel-off routine instead of four) — smaller code, fewer registers.
+// * Block-level regrouping (dust-free runs): the atom-velocity sampler has two branches, |x| <= 1 (84 % of the
+//   scatterings of an optically thick run) and the wing majorant, whose set-up and trials are ~5x more expensive.  With
+//   slots in pool order nearly every warp holds a few wing photons and runs both branches at a fraction of its lanes.
+//   Each block therefore sorts its active slots by branch first (stable partition through shared memory: ballot ranks +
+//   per-warp counts), so that all but one warp of a block execute a single branch with full lanes; a lane then works on
+//   slot base + perm[lane].  Photon physics does not notice: every photon owns its Philox stream.
+// * Only what the sampler needs (frequency, Voigt parameter, stream position) is loaded before it; position, direction,
+//   triad and Stokes columns follow afterwards (L1-prefetched meanwhile), and only the columns a scattering changes are
+//   written back (position, cell, weight and id stay as they are).
+// * A peel ray whose first cell alone is deeper than the cap ends there with a contribution of exactly zero
+//   (raytrace_car.f90:432,497: tau >= 745.2).  The path inside the cell is at least the distance L to the nearest face
+//   (|k| <= 1), and rounding is monotonic, so kappa*L >= 745.2 proves it without the DDA set-up and its three divides:
+//   such a ray is counted (one peel ray, one cell step, as the walk would; reported as n_peel_bound) and never written
+//   to the queue — the test runs as soon as the ray's frequency is known, before the Stokes algebra.  On a face L = 0.
+#ifndef LART_SCATTER_BLOCK
+#define LART_SCATTER_BLOCK 256
+#endif
 #ifndef LART_SCATTER_MINBLOCKS
 #define LART_SCATTER_MINBLOCKS 2
 #endif
-// LOCAL = the stage also takes the first cell step of the peel ray and of the next flight itself
-// (LART_FLAG_LOCAL_STEPS).  A template so that the default kernel does not carry that code.
-// A peel ray whose first cell alone is deeper than the cap ends there with a contribution of exactly zero
-// (raytrace_car.f90:432,497: tau >= 745.2).  The path inside the cell is at least the distance L to the nearest face
-// (|k| <= 1), and rounding is monotonic, so kappa*L >= 745.2 proves it without the DDA set-up and its three divides: such
-// a ray is counted (one peel ray, one cell step, as the walk would) and never written to the queue.  On a face L = 0.
 #ifndef LART_PEEL_BOUND
 #define LART_PEEL_BOUND 1
 #endif
+#ifndef LART_REGROUP
+#define LART_REGROUP 1
+#endif
+constexpr int kScatBlock = LART_SCATTER_BLOCK;
+static_assert(kScatBlock % 32 == 0 && kScatBlock <= kBlock, "scatter block: whole warps, at most kBlock threads");
+
 __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const double *vtab, const CellData &cs, const PeelRay &pr) {
   double L = fmin(DSUB(pr.z, __ldg(P.zface + pr.kc - 1)), DSUB(__ldg(P.zface + pr.kc), pr.z));
   if (!P.zonly) {
@@ -764,92 +805,166 @@ __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const 
   return DMUL(kap, L) >= kTauHuge;
 }
 
-template <bool LOCAL>
-__global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+template <bool STOKES, bool DUST, bool LOCAL>
+__global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
-  __shared__ VzWarpShared vzsh[kBlock / 32];
-  if (LOCAL || P.dust || (LART_PEEL_BOUND && P.save_peeloff)) load_vtab(P, vtab);
-  VzWarpShared &sh = vzsh[threadIdx.x >> 5];
+  __shared__ VzWarpShared vzsh[kScatBlock / 32];
+  __shared__ unsigned short perm[kScatBlock];
+  __shared__ int wcount[kScatBlock / 32][2];
+  const bool bound = LART_PEEL_BOUND && !LOCAL && P.save_peeloff;
+  if (LOCAL || DUST || bound) load_vtab(P, vtab);
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  VzWarpShared &sh = vzsh[warp];
   Counters cnt;
   ctr_t nrng = 0;
-  const int lane = threadIdx.x & 31;
-  const int stride = gridDim.x * blockDim.x;
-  for (int base = pl.s0 + blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < pl.s0 + pl.n; base += stride) {
-    const int s = base + lane;
-    const bool inb = s < pl.s0 + pl.n;
+  const size_t S = pl.S;
+  const int end = pl.s0 + pl.n;
+  for (int base = pl.s0 + blockIdx.x * kScatBlock; base < end; base += gridDim.x * kScatBlock) {  // block-uniform
+    int s = base + threadIdx.x;
+    const bool inb = s < end;
     const int fl0 = inb ? pl.flags[s] : 0;
-    const bool active = (fl0 & PH_SCATTER) != 0;
-    PeelRay *myrays = q.rays + (size_t)(inb ? s : 0) * P.nobs;
+    bool active = (fl0 & PH_SCATTER) != 0;
     if (inb && !active)
-      for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
-    if (!__any_sync(0xffffffffu, active)) continue;
+      for (int k = 0; k < P.nobs; ++k) q.rays[(size_t)s * P.nobs + k].kind = -1;
+    if (!__syncthreads_or(active)) continue;
+    double xf0 = active ? pl.f[(size_t)F_XFREQ * S + s] : 0.0;
+    if (LART_REGROUP && !DUST) {
+      const int cls = active ? (fabs(xf0) <= 1.0 ? 0 : 1) : 2;
+      const unsigned m0 = __ballot_sync(FULL, cls == 0), m1 = __ballot_sync(FULL, cls == 1);
+      if (lane == 0) { wcount[warp][0] = __popc(m0); wcount[warp][1] = __popc(m1); }
+      __syncthreads();
+      int n0 = 0, n1 = 0, o0 = 0, o1 = 0;
+#pragma unroll
+      for (int w = 0; w < kScatBlock / 32; ++w) {
+        const int c0 = wcount[w][0], c1 = wcount[w][1];
+        if (w < warp) { o0 += c0; o1 += c1; }
+        n0 += c0; n1 += c1;
+      }
+      if (cls == 0) perm[o0 + __popc(m0 & lt)] = (unsigned short)threadIdx.x;
+      else if (cls == 1) perm[n0 + o1 + __popc(m1 & lt)] = (unsigned short)threadIdx.x;
+      __syncthreads();
+      active = (int)threadIdx.x < n0 + n1;
+      if (active) {
+        s = base + perm[threadIdx.x];
+        xf0 = pl.f[(size_t)F_XFREQ * S + s];
+      }
+      if (!__any_sync(FULL, active)) continue;  // (the next block barrier is at the top of the loop: every thread gets there)
+    }
+    PeelRay *myrays = q.rays + (size_t)(active ? s : 0) * P.nobs;
     Photon ph;
     Rng rng;
     CellData cs;
     bool to_dust = false;
+    double a_cell = 1.0;
+    const Cell *cellp = nullptr;
     if (active) {
-      load_trace_part(pl, s, ph);
-      {  // the triad, Stokes and bookkeeping columns are needed only after the sampler: warm L1 now
+      ph.flags = pl.flags[s] & ~PH_SCATTER;
+      ph.id = pl.id[s];
+      ph.ic = pl.ic[s]; ph.jc = pl.jc[s]; ph.kc = pl.kc[s];
+      ph.xfreq = xf0;
+      {  // everything else is needed only after the sampler: warm L1 now
         const double *f = pl.f + s;
-        const size_t S = pl.S;
 #pragma unroll
-        for (int c = F_MX; c <= F_NSD; ++c)
-          if (c != F_XFREQ && c != F_WGT) prefetch_l1(f + (size_t)c * S);
+        for (int c = F_X; c <= F_NZ; ++c) prefetch_l1(f + (size_t)c * S);
+        prefetch_l1(f + (size_t)F_WGT * S);
+        prefetch_l1(f + (size_t)F_NSG * S);
+        if (STOKES) { prefetch_l1(f + (size_t)F_Q * S); prefetch_l1(f + (size_t)F_U * S); prefetch_l1(f + (size_t)F_V * S); }
         if (ph.flags & PH_GAUSS) prefetch_l1(f + (size_t)F_GSET * S);
       }
-      ph.flags &= ~PH_SCATTER;
       load_rng(P, pl, s, ph.id, ph.flags, rng);
-      load_cell(P, ph.ic, ph.jc, ph.kc, cs);
       cnt.scatter += 1;
-      if (P.dust) {
-        double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
-        to_dust = rng.uniform() <= pd;
+      if (DUST || P.soa) {
+        load_cell(P, ph.ic, ph.jc, ph.kc, cs);
+        a_cell = cs.voigt_a;
+        if (DUST) {
+          double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
+          to_dust = rng.uniform() <= pd;
+        }
+      } else {  // only the Voigt parameter now; the record is re-read (from L1) after the sampler
+        cellp = P.cells + cell_slot(P, ph.ic, ph.jc, ph.kc);
+        a_cell = __ldg(&cellp->voigt_a);
       }
     } else {
-      ph.xfreq = 0.0; cs.voigt_a = 1.0; rng.start(P.seed, 0ULL);
+      ph.xfreq = 0.0; rng.start(P.seed, 0ULL);
     }
     const bool resonant = active && !to_dust;
-    const double uz_w = (P.flags_serial_vz) ? (resonant ? rand_resonance_vz(rng, ph.xfreq, cs.voigt_a, cnt.reject) : 0.0)
-                                            : rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, cs.voigt_a, cnt.reject);
+    const double uz_w = (P.flags_serial_vz) ? (resonant ? rand_resonance_vz(rng, ph.xfreq, a_cell, cnt.reject) : 0.0)
+                                            : rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, a_cell, cnt.reject);
     if (!active) continue;
-    load_rest(pl, s, ph);  // after the sampler: keeps its register footprint small
+    // ---- the rest of the photon record and of the cell record
+    {
+      const double *f = pl.f + s;
+      ph.x = f[F_X * S]; ph.y = f[F_Y * S]; ph.z = f[F_Z * S];
+      ph.kx = f[F_KX * S]; ph.ky = f[F_KY * S]; ph.kz = f[F_KZ * S];
+      ph.wgt = f[F_WGT * S]; ph.nsg = f[F_NSG * S];
+      ph.nsd = DUST ? f[F_NSD * S] : 0.0;
+      ph.xfreq_ref = 0.0;
+      if (STOKES) {
+        ph.mx = f[F_MX * S]; ph.my = f[F_MY * S]; ph.mz = f[F_MZ * S];
+        ph.nx = f[F_NX * S]; ph.ny = f[F_NY * S]; ph.nz = f[F_NZ * S];
+        ph.Q = f[F_Q * S]; ph.U = f[F_U * S]; ph.V = f[F_V * S];
+      } else {  // no triad and no Stokes vector in this variant (record_final reads them only with par%use_stokes)
+        ph.mx = ph.my = ph.mz = ph.nx = ph.ny = ph.nz = 0.0; ph.Q = ph.U = ph.V = 0.0;
+      }
+      if (!(DUST || P.soa)) {
+        const double2 *qc = reinterpret_cast<const double2 *>(cellp);
+        const double2 c0 = __ldg(qc), c1 = __ldg(qc + 1), c2 = __ldg(qc + 2);
+        cs.rhokap = c0.x; cs.voigt_a = c0.y; cs.Dfreq = c1.x; cs.vfx = c1.y; cs.vfy = c2.x; cs.vfz = c2.y; cs.rhokapD = 0.0;
+      }
+    }
+    const double wgt_in = ph.wgt;
     bool peeled = false;
     // With local steps the ray toward observer 0 stays in registers: most of them end inside the
     // photon's own cell (tau cap) and never reach the queue.
     PeelRay pr0;
     bool have_pr0 = false;
-    auto emit_ray = [&](int k, bool ok, const PeelRay &pr) {
-      if (LOCAL && k == 0) { have_pr0 = ok; if (ok) pr0 = pr; else myrays[0].kind = -1; }
-      else if (ok && LART_PEEL_BOUND && !LOCAL && peel_certainly_capped(P, vtab, cs, pr)) {
-        cnt.peel += 1; cnt.cellsteps += 1;
+    auto emit_ray = [&](int k, int code, const PeelRay &pr) {  // code: 0 = no ray, 1 = descriptor ready, 2 = proved dead
+      if (LOCAL && k == 0) { have_pr0 = code == 1; if (have_pr0) pr0 = pr; else myrays[0].kind = -1; }
+      else if (code == 1) ray_store(myrays + k, pr);
+      else {
+        if (code == 2) { cnt.peel += 1; cnt.cellsteps += 1; cnt.peel_bound += 1; }
         myrays[k].kind = -1;
       }
-      else if (ok) ray_store(myrays + k, pr);
-      else myrays[k].kind = -1;
     };
-    if (to_dust) {
+    auto drop = [&](const PeelRay &pr) { return bound && peel_certainly_capped(P, vtab, cs, pr); };
+    if (DUST && to_dust) {
       scatter_dust(P, ph, rng, cs, cnt, [&]() {
         peeled = true;
         for (int k = 0; k < P.nobs; ++k) {
           PeelRay pr;
-          bool ok = P.use_stokes ? peel_dust_stokes_prepare(P, P.obs[k], k, ph, cs, pr)
-                                 : peel_dust_nostokes_prepare(P, P.obs[k], k, ph, cs, pr);
-          emit_ray(k, ok, pr);
+          bool ok = STOKES ? peel_dust_stokes_prepare(P, P.obs[k], k, ph, cs, pr)
+                           : peel_dust_nostokes_prepare(P, P.obs[k], k, ph, cs, pr);
+          emit_ray(k, (ok && drop(pr)) ? 2 : (ok ? 1 : 0), pr);
         }
       });
       if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
     } else {
-      scatter_resonance(P, ph, rng, cs, cnt, uz_w, [&](double xa, double ux, double uy, double uz) {
+      // do_resonance1 — line_mod.f90:108-139
+      scatter_resonance_core<false, STOKES ? 1 : 0>(P, ph, rng, cs, cnt, uz_w, ph.xfreq - uz_w, 1.0,
+                                                    [&](double xa, double ux, double uy, double uz) {
         peeled = true;
         for (int k = 0; k < P.nobs; ++k) {
           PeelRay pr;
-          bool ok = P.use_stokes ? peel_resonance_stokes_prepare(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr)
-                                 : peel_resonance_nostokes_prepare(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr);
-          emit_ray(k, ok, pr);
+          const int code = STOKES ? peel_resonance_stokes_prepare2(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr, drop)
+                                  : peel_resonance_nostokes_prepare2(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr, drop);
+          emit_ray(k, code, pr);
         }
       });
     }
     if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+    // ---- bounded runs: the photon is abandoned after max_events scatterings, recorded as it stands
+    if (P.max_events > 0 && (ph.flags & PH_ALIVE)) {
+      const int ne = pl.nev[s] + 1;
+      pl.nev[s] = ne;
+      if (ne >= P.max_events) {
+        ph.flags &= ~PH_ALIVE;
+        ph.xfreq_ref = ph.xfreq;
+        retire_photon(P, ph, false, job, cnt);
+      }
+    }
+    bool moved = false;  // position / cell changed (local steps only)
     if (LOCAL) {
       // ---- first cell step of the peel ray (raytrace_to_edge): in an optically thick cell it is the last one
       if (have_pr0) {
@@ -867,7 +982,7 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
         Ray r;
         if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true, &cs)) {
           ph.flags &= ~PH_ALIVE;  // already leaving: dead without tally (raytrace_car.f90:1469-1472)
-          retire_photon(P, ph, false, job, cnt);
+            retire_photon(P, ph, false, job, cnt);
         } else {
           double xp, yp, zp;
           const int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
@@ -877,20 +992,38 @@ __global__ void __launch_bounds__(kBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(c
             ph.kc = r.kc;
             ph.flags |= PH_SCATTER;
             cnt.cellsteps += r.nsteps;
+            moved = true;
           } else if (st == 2) {
-            cnt.cellsteps += finish_escape(P, ph, r);
+                cnt.cellsteps += finish_escape(P, ph, r);
             retire_photon(P, ph, true, job, cnt);
+            moved = true;
           } else {  // crossed into the next cell: the trace stage walks it (from its start) with this tau
-            pl.f[(size_t)F_TAU * pl.S + s] = tau_in;
+            pl.f[(size_t)F_TAU * S + s] = tau_in;
             ph.flags |= PH_TAUPEND;
           }
         }
       }
     }
-    int fl = ph.flags;
-    store_rng(pl, s, rng, fl);
-    ph.flags = fl;
-    store_all(pl, s, ph);
+    // ---- write back what a scattering changes
+    {
+      int fl = ph.flags;
+      store_rng(pl, s, rng, fl);
+      pl.flags[s] = fl;
+      double *f = pl.f + s;
+      f[F_XFREQ * S] = ph.xfreq;
+      f[F_KX * S] = ph.kx; f[F_KY * S] = ph.ky; f[F_KZ * S] = ph.kz;
+      f[F_NSG * S] = ph.nsg;
+      if (STOKES) {
+        f[F_MX * S] = ph.mx; f[F_MY * S] = ph.my; f[F_MZ * S] = ph.mz;
+        f[F_NX * S] = ph.nx; f[F_NY * S] = ph.ny; f[F_NZ * S] = ph.nz;
+        f[F_Q * S] = ph.Q; f[F_U * S] = ph.U; f[F_V * S] = ph.V;
+      }
+      if (DUST) { f[F_NSD * S] = ph.nsd; if (ph.wgt != wgt_in) f[F_WGT * S] = ph.wgt; }
+      if (LOCAL && moved) {
+        f[F_X * S] = ph.x; f[F_Y * S] = ph.y; f[F_Z * S] = ph.z; f[F_XREF * S] = ph.xfreq_ref;
+        pl.ic[s] = ph.ic; pl.jc[s] = ph.jc; pl.kc[s] = ph.kc;
+      }
+    }
     nrng += rng.nrng;
   }
   flush_counters(P, cnt, nrng);
@@ -1002,6 +1135,7 @@ __global__ void __launch_bounds__(kBlock) k_cl_emit(const __grid_constant__ DevP
         pr.ic = icl;
         unsigned at = atomicAdd(q.n_direct, 1u);
         if (at < q.direct_cap) ray_store(q.rays + q.direct_base + at, pr);
+        else atomicOr(P.err, (unsigned)ERR_DIRECT_QUEUE);
       }
     }
     int fl = ph.flags;
@@ -1009,6 +1143,7 @@ __global__ void __launch_bounds__(kBlock) k_cl_emit(const __grid_constant__ DevP
     ph.flags = fl;
     store_all(pl, s, ph);
     pl.rc[s] = icl;
+    pl.nev[s] = 0;
     nrng += rng.nrng;
   }
   flush_counters(P, cnt, nrng);
@@ -1291,6 +1426,15 @@ __global__ void __launch_bounds__(kBlock, 2) k_cl_scatter(const __grid_constant_
       });
     }
     if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+    if (P.max_events > 0 && (ph.flags & PH_ALIVE)) {
+      const int ne = pl.nev[s] + 1;
+      pl.nev[s] = ne;
+      if (ne >= P.max_events) {
+        ph.flags &= ~PH_ALIVE;
+        ph.xfreq_ref = ph.xfreq;
+        retire_photon(P, ph, false, job, cnt);
+      }
+    }
     int fl = ph.flags;
     store_rng(pl, s, rng, fl);
     ph.flags = fl;
@@ -1369,6 +1513,7 @@ __global__ void k_compact_move(Pool pl, const int *src, const int *dst, const un
     pl.id[b] = pl.id[a]; pl.ndraw[b] = pl.ndraw[a];
     pl.ic[b] = pl.ic[a]; pl.jc[b] = pl.jc[a]; pl.kc[b] = pl.kc[a];
     pl.flags[b] = pl.flags[a];
+    pl.nev[b] = pl.nev[a];
     pl.flags[a] = 0;
   }
 }
@@ -1477,6 +1622,19 @@ __global__ void k_pack_clumps(long long n, const double *x, const double *y, con
     cp.rhokap = rhokap[i]; cp.rhokapD = rhokapD ? rhokapD[i] : 0.0; cp.voigt_a = voigt_a[i]; cp.Dfreq = Dfreq[i];
     cp.vx = vx[i]; cp.vy = vy[i]; cp.vz = vz[i]; cp.pad_ = 0.0;
     phys[i] = cp;
+  }
+}
+// the scatter stage's "this peel ray certainly ends inside its own cell" bound, exposed for the parity tests
+__global__ void k_peel_bound_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
+                                   const double *z, const double *xfreq, const int *ic, const int *jc, const int *kc, int *capped) {
+  __shared__ double vtab[kVoigtTabN];
+  load_vtab(P, vtab);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    CellData cs;
+    load_cell(P, ic[i], jc[i], kc[i], cs);
+    PeelRay pr;
+    pr.x = x[i]; pr.y = y[i]; pr.z = z[i]; pr.xfreq = xfreq[i]; pr.ic = ic[i]; pr.jc = jc[i]; pr.kc = kc[i];
+    capped[i] = peel_certainly_capped(P, vtab, cs, pr) ? 1 : 0;
   }
 }
 __global__ void k_xcrit_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
@@ -1621,25 +1779,45 @@ int device_vtab(int dev, double **out) {
   return 0;
 }
 
-// Handle memory comes from the device's stream-ordered pool with the release threshold lifted: what a destroyed handle
-// frees stays cached in the process, so the next lart_gpu_create does not pay the driver's map/unmap again (measured:
-// create 0.06-0.17 s, but 0.6-0.8 s when it followed the cudaFree of another handle's ~10 GB).
+// Handle memory comes from a stream-ordered memory pool PRIVATE to this library (one per device), with the release
+// threshold lifted while handles are alive: what a destroyed handle frees stays cached for the next lart_gpu_create of
+// the process (measured: create 0.06-0.17 s, but 0.6-0.8 s when it followed the cudaFree of another handle's ~10 GB).
+// The device's default pool — PyTorch's or the host program's — is never touched, and when the last handle of a
+// device goes the pool is trimmed, i.e. the memory returns to the driver (LART_GPU_KEEP_POOL=1 keeps it cached).
+std::mutex g_pool_mu;
+cudaMemPool_t g_pool[64] = {nullptr};
+int g_pool_users[64] = {0};
+int pool_for(int dev, cudaMemPool_t *mp) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (dev < 0 || dev >= 64) return fail("bad device ordinal");
+  if (!g_pool[dev]) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    CUDA_OK(cudaMemPoolCreate(&g_pool[dev], &props));
+    unsigned long long thr = ~0ULL;
+    CUDA_OK(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &thr));
+  }
+  *mp = g_pool[dev];
+  return 0;
+}
+void pool_acquire(int dev) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (dev >= 0 && dev < 64) ++g_pool_users[dev];
+}
+void pool_release(int dev) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (dev < 0 || dev >= 64 || g_pool_users[dev] <= 0) return;
+  if (--g_pool_users[dev] == 0 && g_pool[dev] && !getenv("LART_GPU_KEEP_POOL")) cudaMemPoolTrimTo(g_pool[dev], 0);
+}
 int dev_malloc(void **p, size_t bytes) {
-  static std::mutex mu;
-  static std::map<int, bool> tuned;
   int dev = 0;
   CUDA_OK(cudaGetDevice(&dev));
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (!tuned[dev]) {
-      cudaMemPool_t mp;
-      CUDA_OK(cudaDeviceGetDefaultMemPool(&mp, dev));
-      unsigned long long thr = ~0ULL;
-      CUDA_OK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr));
-      tuned[dev] = true;
-    }
-  }
-  CUDA_OK(cudaMallocAsync(p, bytes, 0));
+  cudaMemPool_t mp;
+  if (int rc = pool_for(dev, &mp)) return rc;
+  CUDA_OK(cudaMallocFromPoolAsync(p, bytes, mp, 0));
   CUDA_OK(cudaStreamSynchronize(0));  // the pointer is used from other streams right away
   return 0;
 }
@@ -1700,6 +1878,7 @@ struct lart_gpu_ctx {
 
 namespace {
 void partition_pool(lart_gpu_handle h, int n);
+int create_impl(const lart_config *cfg, lart_gpu_ctx *h);
 }  // namespace
 
 namespace {
@@ -1755,6 +1934,10 @@ int validate(const lart_config *c) {
   if (p.save_Jmu && (p.nmu < 1 || !(p.dmu > 0.0))) return fail("lart_gpu_create: save_Jmu needs nmu >= 1 and dmu > 0");
   if (!(g.dxfreq > 0.0)) return fail("lart_gpu_create: dxfreq must be > 0");
   if (g.nz >= (1 << kFlipShift)) return fail("lart_gpu_create: nz too large");
+  if (g.nxfreq >= (1 << 24)) return fail("lart_gpu_create: nxfreq must be < 2^24 (peel-tally aggregation key)");
+  if (p.save_peeloff && p.nobs > 0 && c->observers && (long long)c->observers[0].nxim * c->observers[0].nyim >= (1LL << 30))
+    return fail("lart_gpu_create: nxim*nyim must be < 2^30 (peel-tally aggregation key)");
+  if (c->max_events < 0) return fail("lart_gpu_create: max_events must be >= 0");
   if (p.use_clump_medium) {  // setup.f90:806-860; grid_mod_clump.f90:55-59
     const lart_clumps &cl = c->clumps;
     if (cl.n < 1 || cl.n > 2147483647LL) return fail("lart_gpu_create: use_clump_medium needs 1 <= clumps.n < 2^31");
@@ -1766,6 +1949,15 @@ int validate(const lart_config *c) {
     if (cl.cgx < 1 || cl.cgy < 1 || cl.cgz < 1 || !(cl.cg_dx > 0.0) || !(cl.cg_dy > 0.0) || !(cl.cg_dz > 0.0) || !(cl.sphere_R > 0.0))
       return fail("lart_gpu_create: bad clump CSR grid");
     if (p.xyz_symmetry || p.xy_symmetry || p.xy_periodic) return fail("lart_gpu_create: the clump medium uses the plain box (grid_mod_clump.f90:55-59)");
+    // the CSR arrays are indexed on the device without further checks: offsets 1-based and monotone, entries in 1..n
+    const size_t ncell = (size_t)cl.cgx * cl.cgy * cl.cgz;
+    if (cl.cg_start[0] != 1) return fail("lart_gpu_create: clumps.cg_start must be 1-based (cg_start[0] == 1)");
+    for (size_t i = 0; i < ncell; ++i)
+      if (cl.cg_start[i + 1] < cl.cg_start[i]) return fail("lart_gpu_create: clumps.cg_start is not monotone");
+    const long long nreg = (long long)cl.cg_start[ncell] - 1;
+    if (nreg < 1) return fail("lart_gpu_create: clumps CSR grid holds no registration");
+    for (long long i = 0; i < nreg; ++i)
+      if (cl.cg_list[i] < 1 || (long long)cl.cg_list[i] > cl.n) return fail("lart_gpu_create: clumps.cg_list entry outside 1..n");
   }
   if (p.xyz_symmetry || p.xy_symmetry) {  // setup.f90:167, 198-206, 952-957; grid_mod_car.f90:85-134
     if (p.xy_periodic || g.nx < 2 || g.ny < 2 || (p.xyz_symmetry && g.nz < 2))
@@ -1793,7 +1985,22 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   CUDA_OK(cudaSetDevice(cfg->device));
   lart_gpu_ctx *h = new lart_gpu_ctx();
   h->device = cfg->device;
-  auto bail = [&](int rc) { lart_gpu_destroy(h); return rc; };
+  pool_acquire(h->device);
+  if (int rc = create_impl(cfg, h)) {  // every error path releases the half-built context
+    const std::string msg = g_err;
+    lart_gpu_destroy(h);
+    g_err = msg;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
+  auto bail = [&](int rc) { return rc; };
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
   h->nsm = prop.multiProcessorCount;
@@ -1943,7 +2150,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
     off += o * P.nobs;
   }
   L.scalars = take(true, 2);
-  L.counters = take(true, 6);
+  L.counters = take(true, C_COUNT);
   L.total = off;
   if ((rc = dalloc(h, &P.tally, (size_t)L.total))) return bail(rc);
   // ---- allph: one slot per photon id
@@ -1979,7 +2186,10 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   rc = rc ? rc : dalloc(h, &h->pool.flags, S);
   rc = rc ? rc : dalloc(h, &h->pool.rs, (size_t)10 * S);
   rc = rc ? rc : dalloc(h, &h->pool.rc, (size_t)3 * S);
+  rc = rc ? rc : dalloc(h, &h->pool.nev, S);
   rc = rc ? rc : dalloc(h, &h->job, 1);
+  if (!rc) P.err = &h->job->err;
+  P.max_events = cfg->max_events > 0 ? cfg->max_events : 0;
   rc = rc ? rc : dalloc(h, &h->cmp_src, S);
   rc = rc ? rc : dalloc(h, &h->cmp_dst, S);
   rc = rc ? rc : dalloc(h, &h->cmp_n, 2);
@@ -2009,6 +2219,7 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
       gr.q.n_cont = ctr + 8 * g + 3; gr.q.wave = ctr + 8 * g + 5;
       gr.q.direct_base = (unsigned)((long long)S * nobs + (long long)gr.pool.s0 * nobs);
       gr.q.direct_cap = (unsigned)std::min<long long>((long long)gr.pool.n * nobs, ray_cap - gr.q.direct_base);
+      if (cfg->flags & LART_FLAG_DEBUG_TINY_QUEUES) gr.q.direct_cap = std::min(gr.q.direct_cap, 1u);  // tests of the error path
       gr.q.cont_cap = (unsigned)((long long)gr.pool.n * std::max<long long>(nobs, 1) * 2 + 32);
       gr.q.cont[0] = cont + 2LL * ((long long)gr.pool.s0 * std::max<long long>(nobs, 1) * 2 + 64LL * g);
       gr.q.cont[1] = gr.q.cont[0] + gr.q.cont_cap;
@@ -2021,9 +2232,11 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
   h->budget = cfg->ray_budget > 0 ? cfg->ray_budget : 32;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
-  *out = h;
   return 0;
 }
+}  // namespace
+
+extern "C" {
 
 int lart_gpu_destroy(lart_gpu_handle h) {
   if (!h) return 0;
@@ -2044,6 +2257,8 @@ int lart_gpu_destroy(lart_gpu_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
+  cudaStreamSynchronize(0);  // the cudaFreeAsync calls above are ordered on the legacy stream
+  pool_release(h->device);
   delete h;
   return 0;
 }
@@ -2052,7 +2267,7 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
   if (!h) return fail("lart_gpu_begin: NULL handle");
   if (count < 0 || stride < 1) return fail("lart_gpu_begin: count must be >= 0 and stride >= 1");
   CUDA_OK(cudaSetDevice(h->device));
-  Job j{0ULL, (unsigned long long)count, 0ULL, (long long)first_id, (long long)stride};
+  Job j{0ULL, (unsigned long long)count, 0ULL, (long long)first_id, (long long)stride, 0u, 0u};
   CUDA_OK(cudaMemcpyAsync(h->job, &j, sizeof(Job), cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemsetAsync(h->pool.flags, 0, sizeof(int) * h->pool.S, h->stream));  // abandon unfinished photons
   if (h->ctr) CUDA_OK(cudaMemsetAsync(h->ctr, 0, sizeof(unsigned int) * h->ctr_n, h->stream));  // ... and parked rays
@@ -2069,6 +2284,33 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
 
 namespace {
 int drain_peel_only(lart_gpu_handle h);
+// the scatter-stage instantiation of this run: <use_stokes, dust, local steps>
+void launch_scatter(lart_gpu_handle h, lart_gpu_ctx::Group &g) {
+  const int nb = (g.pool.n + kScatBlock - 1) / kScatBlock;
+  const int grid = std::max(1, std::min(nb, h->nsm * LART_SCATTER_MINBLOCKS));
+  const int v = (h->P.use_stokes ? 4 : 0) | (h->P.dust ? 2 : 0) | (h->P.local_steps ? 1 : 0);
+#define LART_SC(ST, DU, LO) k_wf_scatter<ST, DU, LO><<<grid, kScatBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q)
+  switch (v) {
+    case 0: LART_SC(false, false, false); break;
+    case 1: LART_SC(false, false, true); break;
+    case 2: LART_SC(false, true, false); break;
+    case 3: LART_SC(false, true, true); break;
+    case 4: LART_SC(true, false, false); break;
+    case 5: LART_SC(true, false, true); break;
+    case 6: LART_SC(true, true, false); break;
+    default: LART_SC(true, true, true); break;
+  }
+#undef LART_SC
+}
+// sticky device error word -> error return
+int check_device_error(unsigned int err) {
+  if (!err) return 0;
+  std::string m = "device error:";
+  if (err & ERR_DIRECT_QUEUE) m += " peel-ray queue overflow (direct rays were lost);";
+  if (err & ERR_CONT_QUEUE) m += " continuation queue overflow;";
+  if (err & ERR_BAD_STATE) m += " impossible photon state;";
+  return fail("lart_gpu: " + m + " the tallies of this run are incomplete");
+}
 // One step with an explicit driver choice (both drivers share the pool layout, and no
 // slot is left mid-wave between steps, so they can alternate freely).
 int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
@@ -2112,8 +2354,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           else k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.clump) k_cl_scatter<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
-          else if (h->P.local_steps) k_wf_scatter<true><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
-          else k_wf_scatter<false><<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+          else launch_scatter(h, g);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.nobs == 0) {}  // no observers: nothing to peel (xyz_symmetry, plain slabs)
           else if (h->P.clump) k_cl_peel<<<std::max(1, std::min(nb, h->nsm * 4)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
@@ -2182,7 +2423,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
   }
   h->job_next = j.next;
   if (in_flight) *in_flight = (int64_t)h->count - (int64_t)j.done;
-  return 0;
+  return check_device_error(j.err);
 }
 
 // Split the live range [0, n) of the pool among the wave pipelines (32-slot granularity).
@@ -2259,9 +2500,11 @@ int lart_gpu_sync(lart_gpu_handle h) {
   if (!h) return fail("lart_gpu_sync: NULL handle");
   CUDA_OK(cudaSetDevice(h->device));
   if (int rc = drain(h, false)) return rc;  // every peel ray emitted so far is deposited
+  unsigned int err = 0;
+  CUDA_OK(cudaMemcpyAsync(&err, &h->job->err, sizeof(err), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaGetLastError());
-  return 0;
+  return check_device_error(err);
 }
 
 int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride) {
@@ -2400,6 +2643,7 @@ int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out) {
   out->counters.n_photons_done += c[C_PHOTONS]; out->counters.n_scatter += c[C_SCATTER];
   out->counters.n_cellsteps += c[C_CELLSTEPS]; out->counters.n_peel += c[C_PEEL];
   out->counters.n_rng += c[C_RNG]; out->counters.n_reject_iter += c[C_REJECT];
+  out->counters.n_peel_bound += c[C_PEEL_BOUND]; out->counters.n_cellsteps_bound += c[C_PEEL_BOUND];  // one step per such ray
   if (h->allph_buf) {
     std::vector<double> a((size_t)h->allph_n);
     CUDA_OK(cudaMemcpy(a.data(), h->allph_buf, sizeof(double) * h->allph_n, cudaMemcpyDeviceToHost));
@@ -2520,6 +2764,30 @@ int lart_gpu_xcrit_batch(lart_gpu_handle h, int64_t n, const double *x, const do
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   D2H(xcrit, dout, n);
+  return 0;
+}
+
+int lart_gpu_peel_bound_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z, const double *xfreq,
+                              const int32_t *icell, const int32_t *jcell, const int32_t *kcell, int32_t *capped) {
+  if (!h) return fail("lart_gpu_peel_bound_batch: NULL handle");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !xfreq || !icell || !jcell || !kcell || !capped))) return fail("lart_gpu_peel_bound_batch: bad argument");
+  if (n == 0) return 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (icell[i] < 1 || icell[i] > h->P.nx || jcell[i] < 1 || jcell[i] > h->P.ny || kcell[i] < 1 || kcell[i] > h->P.nz)
+      return fail("lart_gpu_peel_bound_batch: cell index outside the grid");
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz, *dxf;
+  int *dic, *djc, *dkc, *dout;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, x, n); rc = rc ? rc : s.in(&dy, y, n); rc = rc ? rc : s.in(&dz, z, n); rc = rc ? rc : s.in(&dxf, xfreq, n);
+  rc = rc ? rc : s.in(&dic, icell, n); rc = rc ? rc : s.in(&djc, jcell, n); rc = rc ? rc : s.in(&dkc, kcell, n);
+  rc = rc ? rc : s.outbuf(&dout, n);
+  if (rc) return rc;
+  k_peel_bound_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dxf, dic, djc, dkc, dout);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  D2H(capped, dout, n);
   return 0;
 }
 

@@ -172,7 +172,7 @@ class Simulation:
     after ONE sum-reduce over NCCL when a torch.distributed group is active.
     """
 
-    def __init__(self, model, device=0, pool_slots=0, quantum=0, flags=0, seed=None, streams=0, ray_budget=0):
+    def __init__(self, model, device=0, pool_slots=0, quantum=0, flags=0, seed=None, streams=0, ray_budget=0, max_events=0):
         self._lib = capi.load_gpu()  # raises if the CUDA engine is missing: no fallback
         self.model = model
         cfg = model.config.contents
@@ -182,6 +182,7 @@ class Simulation:
         cfg.flags = flags
         cfg.streams = streams
         cfg.ray_budget = ray_budget
+        cfg.max_events = max_events
         if seed is not None:
             cfg.par.seed = seed
         self._h = C.c_void_p()
@@ -381,6 +382,19 @@ class Simulation:
         steps, ms = C.c_double(0), C.c_double(0)
         self._check(self._lib.lart_gpu_sightline_stats(self._h, C.byref(steps), C.byref(ms)))
         return steps.value, ms.value
+
+    def peel_bound(self, x, y, z, xfreq, icell, jcell, kcell):
+        """1 where the scatter stage would count a peel ray from (x,y,z) at frequency xfreq instead of walking it."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        x, y, z, xfreq = map(f, (x, y, z, xfreq))
+        icell, jcell, kcell = map(i, (icell, jcell, kcell))
+        out = np.zeros(x.size, dtype=np.int32)
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        ip = lambda a: a.ctypes.data_as(capi.c_int32_p)
+        self._check(self._lib.lart_gpu_peel_bound_batch(self._h, x.size, dp(x), dp(y), dp(z), dp(xfreq), ip(icell), ip(jcell),
+                                                        ip(kcell), ip(out)))
+        return out
 
     def xcrit_local(self, x, y, z, icell, jcell, kcell):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)

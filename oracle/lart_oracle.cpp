@@ -1703,8 +1703,9 @@ void add_escaped_fraction(const World &w, const Photon &ph, double tau0, Tally &
 }
 
 // one photon, start to finish — run_simulation_mod.f90:155-196
-// max_events > 0 abandons the photon after that many scatterings (bounded
-// CPU-baseline samples only; never used for parity).
+// max_events > 0 abandons the photon after that many scatterings (the bounded runs of lart_config::max_events:
+// CPU-baseline samples, and bounded parity runs at sizes where a photon needs ~1e7 scatterings to escape).  An
+// abandoned photon is recorded as it stands, its current frequency in the allph%xfreq2 slot; it makes no Jout tally.
 void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_events) {
   Photon ph;
   ph.id = id;
@@ -1736,7 +1737,8 @@ void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_event
   tl.nscatt_gas += ph.nscatt_gas;
   tl.nscatt_dust += ph.nscatt_dust;
   tl.cnt.n_photons_done += 1;
-  if (w.par->save_all_photons && !(max_events > 0 && ph.inside)) record_final(w, ph, tl.shared->allph);
+  if (max_events > 0 && ph.inside) ph.xfreq_ref = ph.xfreq;
+  if (w.par->save_all_photons) record_final(w, ph, tl.shared->allph);
 }
 
 // raytrace_to_edge_car_tau_gas — raytrace_car.f90:1236-1328 (gas only, no tau cap)

@@ -79,7 +79,7 @@ module lart_gpu_shim
      type(c_lart_scatt_mat) :: scatt_mat
      type(c_lart_clumps)    :: clumps
      type(c_ptr)            :: observers
-     integer(c_int32_t)     :: device, pool_slots, quantum, flags, streams, ray_budget
+     integer(c_int32_t)     :: device, pool_slots, quantum, flags, streams, ray_budget, max_events, pad_
   end type
   type, bind(C) :: c_lart_observer_out
      type(c_ptr) :: scatt, direc, direc0, I, Q, U, V
@@ -89,7 +89,7 @@ module lart_gpu_shim
      type(c_ptr) :: rp0, rp, xfreq1, xfreq2, nscatt_gas, nscatt_dust, I, Q, U, V
   end type
   type, bind(C) :: c_lart_counters
-     real(c_double) :: n_photons_done, n_scatter, n_cellsteps, n_peel, n_rng, n_reject_iter
+     real(c_double) :: n_photons_done, n_scatter, n_cellsteps, n_peel, n_rng, n_reject_iter, n_peel_bound, n_cellsteps_bound
   end type
   type, bind(C) :: c_lart_tallies
      type(c_ptr) :: Jout, Jin, Jabs, Jmu, obs
@@ -276,7 +276,7 @@ contains
     !--- one rank per GPU
     ngpu_per_node  = 8
     cfg%device     = mod(mpar%h_rank, ngpu_per_node)
-    cfg%pool_slots = 0; cfg%quantum = 0; cfg%flags = 0; cfg%streams = 0; cfg%ray_budget = 0
+    cfg%pool_slots = 0; cfg%quantum = 0; cfg%flags = 0; cfg%streams = 0; cfg%ray_budget = 0; cfg%max_events = 0; cfg%pad_ = 0
 
     call check(lart_gpu_create(cfg, handle))
 

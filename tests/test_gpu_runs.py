@@ -331,6 +331,89 @@ def test_bounded_steps_full_size_tau7():
     sim.close()
 
 
+def run_bounded(m, max_events, **kw):
+    """Explicit waves (no driver switch: lart_gpu_run would finish small runs with the monolithic kernel)."""
+    sim = Simulation(m, max_events=max_events, **kw)
+    n = m.config.contents.par.nphotons
+    sim.begin(1, n)
+    guard = 0
+    while sim.step(8) > 0:
+        guard += 1
+        assert guard < 10000
+    sim.output_reduce()
+    sim.close()
+    return m
+
+
+def headline_model(workload, n, **extra):
+    from bench import WORKLOADS
+    kw = dict(WORKLOADS[workload])
+    kw.update(no_photons=n, save_all_photons=True, iseed=11)
+    kw.update(extra)
+    return Model(**kw).setup()
+
+
+@pytest.mark.parametrize("workload,extra", [("sphere_peel_tau1e7", {}), ("sphere_peel_tau1e7_coreskip", {}),
+                                            ("vel_effect_peel", dict(core_skip=True)), ("slab_tau1e7", {}),
+                                            ("sphere_quadrant_tau1e7", {})],
+                         ids=["sphere_peel_tau1e7", "coreskip", "vel_effect_peel_coreskip", "slab_tau1e7", "quadrant"])
+def test_headline_workloads_bounded_run_matches_oracle(workload, extra):
+    """The benchmarked configurations at FULL size (201^3, 201x129x129 / 500x129x129 cubes), the first 32 scatterings of
+    20 000 photons through the wavefront stages, against the oracle on the same Philox streams: per-photon records,
+    every tally and observer cube, and the work counters.  At tau0 = 1e7 a cell is 1e5 deep at line centre, so the
+    scatter stage's cap bound (peel rays counted instead of walked) decides most rays here — this is the comparison
+    that covers it."""
+    n, nev = 20000, 32
+    mg, mo = headline_model(workload, n, **extra), headline_model(workload, n, **extra)
+    run_bounded(mg, nev)
+    oracle.run(mo, rng_mode=1, max_events=nev)
+    same = histories_equal(mg, mo, geom_rtol=1e-6 if "vel_effect" in workload else 1e-8)
+    assert same.mean() > 0.9995
+    tallies_close(mg, mo, same.mean())
+    cg, co = mg.counters, mo.counters
+    assert cg["n_photons_done"] == n
+    assert cg["n_scatter"] == co["n_scatter"]
+    assert cg["n_peel"] == co["n_peel"]            # every ray is accounted for, walked or bound
+    assert abs(cg["n_cellsteps"] - co["n_cellsteps"]) <= 1e-4 * co["n_cellsteps"]
+    assert cg["n_cellsteps_bound"] == cg["n_peel_bound"]
+    if workload == "sphere_peel_tau1e7":
+        assert cg["n_peel_bound"] > 0.7 * cg["n_peel"]  # the bound branch is what runs on this workload
+    if mo.config.contents.par.nobs:
+        assert cg["n_peel_bound"] > 0
+
+
+def test_bounded_run_through_lart_gpu_run_and_monolithic_driver():
+    """max_events through lart_gpu_run (wavefront first, monolithic tail) and through the monolithic driver alone."""
+    n, nev = 3000, 24
+    kw = dict(taumax=1e6, no_photons=n)
+    mo = small_sphere(**kw)
+    oracle.run(mo, rng_mode=1, max_events=nev)
+    for flags in (0, capi.FLAG_MONOLITHIC):
+        mg = small_sphere(**kw)
+        sim = Simulation(mg, flags=flags, max_events=nev, pool_slots=2048)
+        sim.run_simulation()
+        sim.output_reduce()
+        sim.close()
+        same = histories_equal(mg, mo)
+        tallies_close(mg, mo, same.mean())
+        assert mg.counters["n_scatter"] == mo.counters["n_scatter"]
+
+
+def test_queue_overflow_is_an_error_not_a_silent_loss():
+    """A peel ray that cannot be queued raises the sticky device error word; step/sync/fetch return it."""
+    m = small_sphere(no_photons=5000)
+    sim = Simulation(m, flags=capi.FLAG_DEBUG_TINY_QUEUES, pool_slots=4096)
+    with pytest.raises(LartError, match="queue overflow"):
+        sim.begin(1, 5000)
+        sim.step(2)
+    with pytest.raises(LartError, match="queue overflow"):
+        sim.sync()
+    sim.begin(1, 0)  # a new run clears the word
+    sim.step(1)
+    sim.sync()
+    sim.close()
+
+
 def test_edge_cases_and_errors():
     m = small_sphere(no_photons=10)
     sim = Simulation(m, pool_slots=64)

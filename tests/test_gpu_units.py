@@ -264,3 +264,57 @@ def test_sightline_maps_match_oracle_and_column_density():
     assert mp["tau_gas"][15, 10, 10] == pytest.approx(2 * 1e3, rel=1e-9)  # bin 16 of 31 is centred on x = 0
     assert mp["N_gas"][0, 0] == 0.0 or mp["N_gas"][0, 0] < mp["N_gas"][10, 10]
     sim.close()
+
+
+PEEL_BOUND_GRIDS = {
+    "sphere_thick": dict(nx=31, ny=31, nz=31, rmax=1.0, taumax=1e7),
+    "sphere_thick_dust": dict(nx=21, ny=21, nz=21, rmax=1.0, taumax=3e6, DGR=1.0, cext_dust=3e-17, use_stokes=False),
+    "hubble_thick": dict(nx=31, ny=31, nz=31, rmax=1.0, taumax=1e7, velocity_type="hubble", Vexp=200.0),
+    "xysym_thick": dict(nx=16, ny=15, nz=31, rmax=1.0, taumax=1e7, xy_symmetry=True),
+    "xyper_box_thick": dict(nx=7, ny=5, nz=41, xmax=0.5, ymax=0.25, zmax=1.0, geometry="rectangle", xy_periodic=True, taumax=1e7),
+    "slab_zonly_thick": dict(nx=1, ny=1, nz=201, xy_periodic=True, rmax=-999.0, taumax=1e7, nxim=0, nyim=0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PEEL_BOUND_GRIDS))
+def test_peel_bound_implies_capped_walk(name):
+    """The scatter stage counts a peel ray without walking it when kappa(x) * (distance to the nearest face of its cell)
+    >= tau_huge = 745.2 (raytrace_car.f90:432,497).  Whenever that bound fires, the reference's walk must indeed stop in
+    the first cell at the cap — for any direction, on faces (L = 0), with dust, on folded and periodic grids."""
+    kw = dict(no_photons=10, temperature=1e4, nxfreq=21)
+    kw.update(PEEL_BOUND_GRIDS[name])
+    m = Model(**kw).setup()
+    sim = Simulation(m, pool_slots=1024)
+    g = m.config.contents.grid
+    n = 120000
+    rng = np.random.default_rng(3)
+    lo, d, nn = np.array([g.xmin, g.ymin, g.zmin]), np.array([g.dx, g.dy, g.dz]), np.array([g.nx, g.ny, g.nz])
+    ic = rng.integers(1, nn + 1, (n, 3)).astype(np.int32)
+    u = rng.uniform(0, 1, (n, 3))
+    q = n // 8
+    u[:q, rng.integers(0, 3)] = 0.0                  # exactly on a lower face: L = 0
+    u[q:2 * q] = rng.choice([1e-12, 1e-9, 1e-6, 1e-3], (q, 3))  # a hair inside
+    u[2 * q:3 * q, 2] = 1.0                          # on the upper z face of the cell
+    faces = [m.grid_array(a) for a in ("xface", "yface", "zface")]
+    p = np.stack([faces[a][ic[:, a] - 1] + u[:, a] * (faces[a][ic[:, a]] - faces[a][ic[:, a] - 1]) for a in range(3)], axis=1)
+    p[2 * q:3 * q, 2] = faces[2][ic[2 * q:3 * q, 2]]
+    if g.nx == 1 and g.ny == 1:
+        p[:, 0] = 0.0; p[:, 1] = 0.0
+    k = rng.normal(size=(n, 3))
+    k /= np.linalg.norm(k, axis=1)[:, None]
+    # frequencies on both sides of the threshold kappa*L = 745.2: from line centre far into the wings
+    xf = np.concatenate([rng.normal(size=n // 2) * 2.0, rng.uniform(-60, 60, n - n // 2)])
+    capped = sim.peel_bound(p[:, 0], p[:, 1], p[:, 2], xf, ic[:, 0], ic[:, 1], ic[:, 2])
+    to, no, _ = oracle.raytrace_to_edge(m.config, p[:, 0], p[:, 1], p[:, 2], k[:, 0], k[:, 1], k[:, 2], xf, ic[:, 0], ic[:, 1], ic[:, 2])
+    tg, ng, _ = sim.raytrace_to_edge(p[:, 0], p[:, 1], p[:, 2], k[:, 0], k[:, 1], k[:, 2], xf, ic[:, 0], ic[:, 1], ic[:, 2])
+    assert np.array_equal(tg, to) and np.array_equal(ng, no)
+    c = capped == 1
+    assert c.sum() > 0.1 * n and (~c).sum() > 0.1 * n, c.mean()  # both sides of the bound are sampled
+    assert (to[c] >= 745.2).all()   # the walk does end at the cap ...
+    assert (no[c] == 1).all()       # ... inside the first cell: one cell step, contribution exp(-tau) == 0
+    assert np.exp(-to[c]).max() == 0.0
+    assert (capped[:q] == 0).all()  # on a face the bound never fires
+    # the bound is tight enough to matter: it catches most of the rays that do end in their first cell at the cap
+    first_cell_cap = (no == 1) & (to >= 745.2)
+    assert c.sum() > 0.5 * first_cell_cap.sum()
+    sim.close()

@@ -263,6 +263,23 @@ int lart_gpu_sync(lart_gpu_handle h);
  * (src/output_sum_rect.f90:7-149; src/memory_mod_mpi.f90:366-458). */
 int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out);
 int lart_gpu_reset_tallies(lart_gpu_handle h);
+
+/* ---- multi-GPU: the communicator half of output_reduce -------------------------------------------------------------
+ * One process per GPU (one MPI rank per GPU on the Fortran side).  lart_gpu_reduce sums the tallies of all ranks onto
+ * `root` with ONE ncclReduce(sum, f64) over the contiguous device tally buffer (and one over the allph buffer) across
+ * NVLink — it replaces reduce_mem's per-array, plane-by-plane MPI_REDUCE of host arrays
+ * (src/memory_mod_mpi.f90:366-458, called from src/output_sum_rect.f90:13-146); the host then calls lart_gpu_fetch on
+ * root only and skips its own reduce.  After the call the other ranks' device tallies are zero (their contribution
+ * lives on root), so the sum over ranks always is "everything tallied so far".
+ *   rank 0:     lart_gpu_comm_unique_id(id)      -> 128 bytes, broadcast by the host (MPI_BCAST)
+ *   every rank: lart_gpu_comm_init(device, nranks, rank, id)   once per process, like MPI_INIT
+ *   every rank: lart_gpu_reduce(h, root)         collective; a no-op without a communicator (single GPU)
+ * libnccl.so.2 is opened at run time (LART_NCCL_LIB overrides the name); single-GPU use never needs it. */
+int lart_gpu_comm_unique_id(void *id128);
+int lart_gpu_comm_init(int32_t device, int32_t nranks, int32_t rank, const void *id128);
+int lart_gpu_comm_info(int32_t *nranks, int32_t *rank);
+int lart_gpu_comm_finalize(void);
+int lart_gpu_reduce(lart_gpu_handle h, int32_t root);
 int lart_gpu_destroy(lart_gpu_handle h);
 
 /* Contiguous FP64 device buffer holding every reducible tally (Jout|Jin|Jabs|

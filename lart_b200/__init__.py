@@ -5,6 +5,7 @@ include/lart_gpu.h, and the C++ mini-host of include/lart_host.h) and the
 host-side mirror of the reference's driver sequence (host.py).
 """
 from . import capi  # noqa: F401
-from .host import LartError, Model, Simulation, calc_voigt, measure_fp64, photon_partition, sample  # noqa: F401
+from .host import (LartError, Model, Simulation, calc_voigt, comm_finalize, comm_init, comm_init_torch, comm_rank,  # noqa: F401
+                   measure_fp64, photon_partition, sample)
 
 __version__ = "0.1.0"

@@ -147,6 +147,7 @@ GPU_SYMBOLS = [
     "lart_gpu_xcrit_batch", "lart_gpu_version", "lart_gpu_stage_ms", "lart_gpu_pool_slots", "lart_gpu_measure_fp64",
     "lart_gpu_sightline_tau", "lart_gpu_sightline_stats",
     "lart_gpu_clump_edge_batch", "lart_gpu_clump_tau_batch", "lart_gpu_clump_locate_batch", "lart_gpu_peel_bound_batch",
+    "lart_gpu_comm_unique_id", "lart_gpu_comm_init", "lart_gpu_comm_info", "lart_gpu_comm_finalize", "lart_gpu_reduce",
 ]
 HOST_SYMBOLS = [
     "lart_host_new", "lart_host_free", "lart_host_set", "lart_host_read_input", "lart_host_setup",
@@ -229,6 +230,11 @@ def load_gpu():
         lib.lart_gpu_clump_edge_batch.argtypes = [H, C.c_int64] + [c_double_p] * 7 + [c_int32_p, C.c_double, c_double_p, c_int32_p]
         lib.lart_gpu_clump_tau_batch.argtypes = [H, C.c_int64] + [c_double_p] * 7 + [c_int32_p, c_double_p, c_int32_p]
         lib.lart_gpu_clump_locate_batch.argtypes = [H, C.c_int64] + [c_double_p] * 3 + [c_int32_p]
+        if hasattr(lib, "lart_gpu_reduce"):
+            lib.lart_gpu_comm_unique_id.argtypes = [C.c_void_p]
+            lib.lart_gpu_comm_init.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+            lib.lart_gpu_comm_info.argtypes = [c_int32_p, c_int32_p]
+            lib.lart_gpu_reduce.argtypes = [H, C.c_int32]
         if hasattr(lib, "lart_gpu_peel_bound_batch"):  # (absent from older A/B builds selected through LART_GPU_LIB)
             lib.lart_gpu_peel_bound_batch.argtypes = [H, C.c_int64] + [c_double_p] * 4 + [c_int32_p] * 4
         _gpu = lib

@@ -26,8 +26,12 @@
 // stream (seed, photon id) and its draw counter travels with the photon, so both
 // drivers — and the CPU oracle in Philox mode — produce the same photon histories.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is opened at run time (lart_gpu_comm_init), never linked
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <map>
 #include <cstdio>
@@ -788,6 +792,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
 #define LART_REGROUP 1
 #endif
 constexpr int kScatBlock = LART_SCATTER_BLOCK;
+constexpr int kWingCap = 1536;  // listed wing photons per block (a block owns ~1400 slots of a default partition, ~16 % of them wing)
 static_assert(kScatBlock % 32 == 0 && kScatBlock <= kBlock, "scatter block: whole warps, at most kBlock threads");
 
 __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const double *vtab, const CellData &cs, const PeelRay &pr) {
@@ -809,8 +814,8 @@ template <bool STOKES, bool DUST, bool LOCAL>
 __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   __shared__ VzWarpShared vzsh[kScatBlock / 32];
-  __shared__ unsigned short perm[kScatBlock];
-  __shared__ int wcount[kScatBlock / 32][2];
+  __shared__ int wing_list[kWingCap];
+  __shared__ int n_wing;
   const bool bound = LART_PEEL_BOUND && !LOCAL && P.save_peeloff;
   if (LOCAL || DUST || bound) load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
@@ -821,36 +826,56 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
   ctr_t nrng = 0;
   const size_t S = pl.S;
   const int end = pl.s0 + pl.n;
-  for (int base = pl.s0 + blockIdx.x * kScatBlock; base < end; base += gridDim.x * kScatBlock) {  // block-uniform
-    int s = base + threadIdx.x;
-    const bool inb = s < end;
-    const int fl0 = inb ? pl.flags[s] : 0;
-    bool active = (fl0 & PH_SCATTER) != 0;
-    if (inb && !active)
-      for (int k = 0; k < P.nobs; ++k) q.rays[(size_t)s * P.nobs + k].kind = -1;
-    if (!__syncthreads_or(active)) continue;
-    double xf0 = active ? pl.f[(size_t)F_XFREQ * S + s] : 0.0;
-    if (LART_REGROUP && !DUST) {
-      const int cls = active ? (fabs(xf0) <= 1.0 ? 0 : 1) : 2;
-      const unsigned m0 = __ballot_sync(FULL, cls == 0), m1 = __ballot_sync(FULL, cls == 1);
-      if (lane == 0) { wcount[warp][0] = __popc(m0); wcount[warp][1] = __popc(m1); }
-      __syncthreads();
-      int n0 = 0, n1 = 0, o0 = 0, o1 = 0;
-#pragma unroll
-      for (int w = 0; w < kScatBlock / 32; ++w) {
-        const int c0 = wcount[w][0], c1 = wcount[w][1];
-        if (w < warp) { o0 += c0; o1 += c1; }
-        n0 += c0; n1 += c1;
+  // Pass 0 walks this warp's share of the partition in pool order and scatters the |x| <= 1 photons; wing photons are
+  // only listed.  Pass 1 (after one block barrier) scatters the listed photons, 32 per warp.  No barrier inside a pass.
+  const bool two_pass = LART_REGROUP && !DUST && !P.flags_serial_vz;
+  if (threadIdx.x == 0) n_wing = 0;
+  for (int i = threadIdx.x; i < kWingCap; i += kScatBlock) wing_list[i] = -1;  // (entries a full list could not take stay -1)
+  __syncthreads();
+  int pass = 0;
+  int base = pl.s0 + blockIdx.x * kScatBlock + warp * 32;
+  const int stride = gridDim.x * kScatBlock;
+  for (;;) {
+    int s = 0;
+    bool active = false;
+    double xf0 = 0.0;
+    if (pass == 0) {
+      if (base >= end) {  // every warp of the block passes here exactly once
+        pass = 1;
+        __syncthreads();
+        base = warp * 32;
+        continue;
       }
-      if (cls == 0) perm[o0 + __popc(m0 & lt)] = (unsigned short)threadIdx.x;
-      else if (cls == 1) perm[n0 + o1 + __popc(m1 & lt)] = (unsigned short)threadIdx.x;
-      __syncthreads();
-      active = (int)threadIdx.x < n0 + n1;
-      if (active) {
-        s = base + perm[threadIdx.x];
-        xf0 = pl.f[(size_t)F_XFREQ * S + s];
+      s = base + lane;
+      base += stride;
+      const bool inb = s < end;
+      const int fl0 = inb ? pl.flags[s] : 0;
+      active = (fl0 & PH_SCATTER) != 0;
+      if (inb && !active)
+        for (int k = 0; k < P.nobs; ++k) q.rays[(size_t)s * P.nobs + k].kind = -1;
+      if (!__any_sync(FULL, active)) continue;
+      if (active) xf0 = pl.f[(size_t)F_XFREQ * S + s];
+      if (two_pass) {
+        const bool wing = active && !(fabs(xf0) <= 1.0);
+        const unsigned mw = __ballot_sync(FULL, wing);
+        if (mw) {
+          int at = 0;
+          if (lane == 0) at = atomicAdd(&n_wing, __popc(mw));
+          at = __shfl_sync(FULL, at, 0);
+          if (at + __popc(mw) <= kWingCap) {  // (a full list: these photons are scattered here, in mixed company)
+            if (wing) { wing_list[at + __popc(mw & lt)] = s; active = false; }
+            if (!__any_sync(FULL, active)) continue;
+          }
+        }
       }
-      if (!__any_sync(FULL, active)) continue;  // (the next block barrier is at the top of the loop: every thread gets there)
+    } else {
+      const int nw = min(n_wing, kWingCap);
+      if (base >= nw) break;
+      s = base + lane < nw ? wing_list[base + lane] : -1;
+      active = s >= 0;
+      if (active) xf0 = pl.f[(size_t)F_XFREQ * S + s];
+      else s = 0;
+      base += kScatBlock;
     }
     PeelRay *myrays = q.rays + (size_t)(active ? s : 0) * P.nobs;
     Photon ph;
@@ -1832,6 +1857,44 @@ int upload(T **dst, const T *src, size_t n) {
   return 0;
 }
 
+
+// ---- NCCL, opened at run time
+struct NcclApi {
+  void *lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclReduce) Reduce = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+} g_nccl;
+ncclComm_t g_comm = nullptr;
+int g_comm_rank = 0, g_comm_size = 1, g_comm_device = -1;
+int nccl_load() {
+  if (g_nccl.lib) return 0;
+  const char *names[] = {getenv("LART_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void *lib = nullptr;
+  for (const char *n : names) if (n && *n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!lib) return fail(std::string("lart_gpu: cannot open libnccl (set LART_NCCL_LIB): ") + dlerror());
+#define NCCL_SYM(f) if (!(g_nccl.f = (decltype(g_nccl.f))dlsym(lib, "nccl" #f))) return fail("lart_gpu: libnccl lacks nccl" #f)
+  NCCL_SYM(GetUniqueId); NCCL_SYM(CommInitRank); NCCL_SYM(CommDestroy); NCCL_SYM(Reduce); NCCL_SYM(GroupStart);
+  NCCL_SYM(GroupEnd); NCCL_SYM(GetErrorString);
+#undef NCCL_SYM
+  g_nccl.lib = lib;
+  return 0;
+}
+#define NCCL_OK(call)                                                                                         \
+  do {                                                                                                        \
+    ncclResult_t r_ = (call);                                                                                 \
+    if (r_ != ncclSuccess) return fail(std::string(#call) + " failed: " + g_nccl.GetErrorString(r_));         \
+  } while (0)
+
+// ---- device tallies ADDED into caller-owned host arrays: pinned double-buffered staging, the copy of chunk i+1
+// overlaps the multi-threaded add of chunk i (the caller's arrays are pageable Fortran memory)
+struct Seg { double *dst; long long off, n; };
+constexpr size_t kStageDoubles = 4u << 20;  // 32 MB per staging buffer
+int add_device_to_host(lart_gpu_ctx *h, const double *dev, long long total, const std::vector<Seg> &segs_in);
 }  // namespace
 
 struct lart_gpu_ctx {
@@ -1870,7 +1933,7 @@ struct lart_gpu_ctx {
   double kernel_ms = 0.0;
   long long launches = 0;
   bool begun = false;
-  std::vector<double> stage;  // host staging for fetch
+  double *pinned[2] = {nullptr, nullptr};  // pinned staging of lart_gpu_fetch
   std::vector<cudaEvent_t> tev;  // stage-timing events of one step (monolithic driver)
   double stage_ms[LART_STAGE_COUNT] = {0, 0, 0, 0};
   long long stage_n[LART_STAGE_COUNT] = {0, 0, 0, 0};
@@ -1879,6 +1942,59 @@ struct lart_gpu_ctx {
 namespace {
 void partition_pool(lart_gpu_handle h, int n);
 int create_impl(const lart_config *cfg, lart_gpu_ctx *h);
+
+int add_device_to_host(lart_gpu_ctx *h, const double *dev, long long total, const std::vector<Seg> &segs_in) {
+  if (total <= 0 || segs_in.empty()) return 0;
+  std::vector<Seg> segs = segs_in;
+  std::sort(segs.begin(), segs.end(), [](const Seg &a, const Seg &b) { return a.off < b.off; });
+  for (int k = 0; k < 2; ++k)
+    if (!h->pinned[k]) CUDA_OK(cudaMallocHost(&h->pinned[k], kStageDoubles * sizeof(double)));
+  const long long lo = segs.front().off, hi = segs.back().off + segs.back().n;
+  const int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  cudaEvent_t ev[2];
+  for (int k = 0; k < 2; ++k) CUDA_OK(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+  auto issue = [&](long long c0, int buf) -> int {
+    const long long n = std::min<long long>((long long)kStageDoubles, hi - c0);
+    CUDA_OK(cudaMemcpyAsync(h->pinned[buf], dev + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaEventRecord(ev[buf], h->stream));
+    return 0;
+  };
+  int rc = issue(lo, 0);
+  int buf = 0;
+  for (long long c0 = lo; c0 < hi && !rc; c0 += (long long)kStageDoubles, buf ^= 1) {
+    const long long c1 = std::min<long long>(c0 + (long long)kStageDoubles, hi);
+    if (c1 < hi) rc = issue(c1, buf ^ 1);
+    if (cudaEventSynchronize(ev[buf]) != cudaSuccess) { rc = fail("lart_gpu_fetch: device-to-host copy failed"); break; }
+    const double *src = h->pinned[buf];
+    // pieces of this chunk: the intersection of [c0,c1) with every segment
+    struct Piece { double *dst; const double *src; long long n; };
+    std::vector<Piece> pieces;
+    for (const Seg &s : segs) {
+      const long long a = std::max(s.off, c0), b = std::min(s.off + s.n, c1);
+      if (a < b) pieces.push_back({s.dst + (a - s.off), src + (a - c0), b - a});
+    }
+    long long work = 0;
+    for (const Piece &p : pieces) work += p.n;
+    const int nt = work < (1 << 16) ? 1 : nthreads;
+    auto body = [&](int t) {
+      for (const Piece &p : pieces) {
+        const long long a = p.n * t / nt, b = p.n * (t + 1) / nt;
+        double *d = p.dst;
+        const double *q = p.src;
+        for (long long i = a; i < b; ++i) d[i] += q[i];
+      }
+    };
+    if (nt == 1) body(0);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(body, t);
+      body(0);
+      for (auto &x : th) x.join();
+    }
+  }
+  for (int k = 0; k < 2; ++k) cudaEventDestroy(ev[k]);
+  return rc;
+}
 }  // namespace
 
 namespace {
@@ -1919,6 +2035,7 @@ struct Scratch {  // device copies of host arrays for one batch call
 };
 inline int grid_for(long long n, int nsm) { return (int)std::max<long long>(1, std::min<long long>((n + kBlock - 1) / kBlock, nsm * 8LL)); }
 #define D2H(dst, src, n) CUDA_OK(cudaMemcpy((dst), (src), (n) * sizeof(*(dst)), cudaMemcpyDeviceToHost))
+
 
 int validate(const lart_config *c) {
   const lart_grid &g = c->grid;
@@ -2257,6 +2374,7 @@ int lart_gpu_destroy(lart_gpu_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
+  for (int k = 0; k < 2; ++k) if (h->pinned[k]) cudaFreeHost(h->pinned[k]);
   cudaStreamSynchronize(0);  // the cudaFreeAsync calls above are ordered on the legacy stream
   pool_release(h->device);
   delete h;
@@ -2612,20 +2730,14 @@ int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out) {
   const DevParams &P = h->P;
   const TallyLayout &L = P.lay;
   if (P.nobs > 0 && !out->obs) return fail("lart_gpu_fetch: out->obs is NULL but observers are configured");
-  if (int rc = drain(h, false)) return rc;
-  h->stage.resize((size_t)L.total);
-  CUDA_OK(cudaMemcpyAsync(h->stage.data(), P.tally, sizeof(double) * L.total, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_OK(cudaStreamSynchronize(h->stream));
-  const double *b = h->stage.data();
-  auto add = [&](double *dst, long long off, long long n) {
-    if (!dst || off < 0) return;
-    const double *s = b + off;
-    for (long long i = 0; i < n; ++i) dst[i] += s[i];
-  };
-  add(out->Jout, L.Jout, P.nxfreq);
-  add(out->Jin, L.Jin, P.nxfreq);
-  add(out->Jabs, L.Jabs, P.nxfreq);
-  add(out->Jmu, L.Jmu, (long long)P.nxfreq * P.nmu);
+  if (int rc = lart_gpu_sync(h)) return rc;  // parked peel rays are deposited; a sticky device error is an error here too
+  // destination segments of the contiguous device buffer
+  std::vector<Seg> segs;
+  auto seg = [&](double *dst, long long off, long long n) { if (dst && off >= 0 && n > 0) segs.push_back({dst, off, n}); };
+  seg(out->Jout, L.Jout, P.nxfreq);
+  seg(out->Jin, L.Jin, P.nxfreq);
+  seg(out->Jabs, L.Jabs, P.nxfreq);
+  seg(out->Jmu, L.Jmu, (long long)P.nxfreq * P.nmu);
   const long long n2 = (long long)h->nxim * h->nyim, n3 = n2 * P.nxfreq;
   for (int k = 0; k < P.nobs; ++k) {
     lart_observer_out &o = out->obs[k];
@@ -2633,28 +2745,86 @@ int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out) {
     double *c3[7] = {o.scatt, o.direc, o.direc0, o.I, o.Q, o.U, o.V};
     double *c2[7] = {o.scatt_2D, o.direc_2D, o.direc0_2D, o.I_2D, o.Q_2D, o.U_2D, o.V_2D};
     for (int q = 0; q < 7; ++q) {
-      if (L.cube[q] >= 0) add(c3[q], base + L.cube[q], n3);
-      if (L.img[q] >= 0) add(c2[q], base + L.img[q], n2);
+      if (L.cube[q] >= 0) seg(c3[q], base + L.cube[q], n3);
+      if (L.img[q] >= 0) seg(c2[q], base + L.img[q], n2);
     }
   }
-  out->nscatt_gas += b[L.scalars + 0];
-  out->nscatt_dust += b[L.scalars + 1];
-  const double *c = b + L.counters;
+  double tail[2 + C_COUNT];
+  segs.push_back({tail, L.scalars, 2 + C_COUNT});  // scalars and counters are adjacent in the layout
+  for (double &v : tail) v = 0.0;
+  if (int rc = add_device_to_host(h, P.tally, L.total, segs)) return rc;
+  out->nscatt_gas += tail[0];
+  out->nscatt_dust += tail[1];
+  const double *c = tail + 2;
   out->counters.n_photons_done += c[C_PHOTONS]; out->counters.n_scatter += c[C_SCATTER];
   out->counters.n_cellsteps += c[C_CELLSTEPS]; out->counters.n_peel += c[C_PEEL];
   out->counters.n_rng += c[C_RNG]; out->counters.n_reject_iter += c[C_REJECT];
   out->counters.n_peel_bound += c[C_PEEL_BOUND]; out->counters.n_cellsteps_bound += c[C_PEEL_BOUND];  // one step per such ray
   if (h->allph_buf) {
-    std::vector<double> a((size_t)h->allph_n);
-    CUDA_OK(cudaMemcpy(a.data(), h->allph_buf, sizeof(double) * h->allph_n, cudaMemcpyDeviceToHost));
+    std::vector<Seg> as;
     double *dst[10] = {out->allph.rp0, out->allph.rp, out->allph.xfreq1, out->allph.xfreq2, out->allph.nscatt_gas,
                        out->allph.nscatt_dust, out->allph.I, out->allph.Q, out->allph.U, out->allph.V};
     for (int k = 0; k < 10; ++k)
-      if (h->allph_slot[k] >= 0 && dst[k]) {
-        const double *s = a.data() + (long long)h->allph_slot[k] * P.nphotons;
-        for (long long i = 0; i < P.nphotons; ++i) dst[k][i] += s[i];
-      }
+      if (h->allph_slot[k] >= 0 && dst[k]) as.push_back({dst[k], (long long)h->allph_slot[k] * P.nphotons, P.nphotons});
+    if (int rc = add_device_to_host(h, h->allph_buf, h->allph_n, as)) return rc;
   }
+  return 0;
+}
+
+/* ---- multi-GPU: one process per GPU, one NCCL communicator per process -------------------------------------------
+ * Replaces the communicator half of memory_mod_mpi.f90:366-458 / output_sum_rect.f90:13-146: ONE ncclReduce over the
+ * contiguous tally buffer (and one over the allph buffer) instead of a per-array, plane-by-plane MPI_REDUCE of host
+ * arrays.  libnccl is opened at run time, so the library loads (and single-GPU runs work) where NCCL is absent. */
+int lart_gpu_comm_unique_id(void *id128) {
+  if (!id128) return fail("lart_gpu_comm_unique_id: NULL argument");
+  if (int rc = nccl_load()) return rc;
+  ncclUniqueId id;
+  NCCL_OK(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int lart_gpu_comm_init(int32_t device, int32_t nranks, int32_t rank, const void *id128) {
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail("lart_gpu_comm_init: bad argument");
+  if (g_comm) return fail("lart_gpu_comm_init: the process already has a communicator (lart_gpu_comm_finalize first)");
+  if (int rc = nccl_load()) return rc;
+  CUDA_OK(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_OK(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
+  g_comm_rank = rank; g_comm_size = nranks; g_comm_device = device;
+  return 0;
+}
+
+int lart_gpu_comm_finalize(void) {
+  if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+  g_comm_rank = 0; g_comm_size = 1; g_comm_device = -1;
+  return 0;
+}
+
+int lart_gpu_comm_info(int32_t *nranks, int32_t *rank) {
+  if (nranks) *nranks = g_comm ? g_comm_size : 1;
+  if (rank) *rank = g_comm ? g_comm_rank : 0;
+  return 0;
+}
+
+int lart_gpu_reduce(lart_gpu_handle h, int32_t root) {
+  if (!h) return fail("lart_gpu_reduce: NULL handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (int rc = lart_gpu_sync(h)) return rc;
+  if (!g_comm || g_comm_size == 1) return root == 0 ? 0 : fail("lart_gpu_reduce: no communicator, root must be 0");
+  if (root < 0 || root >= g_comm_size) return fail("lart_gpu_reduce: root outside the communicator");
+  if (h->device != g_comm_device) return fail("lart_gpu_reduce: the handle lives on another device than the communicator");
+  NCCL_OK(g_nccl.GroupStart());
+  NCCL_OK(g_nccl.Reduce(h->P.tally, h->P.tally, (size_t)h->P.lay.total, ncclDouble, ncclSum, root, g_comm, h->stream));
+  if (h->allph_buf) NCCL_OK(g_nccl.Reduce(h->allph_buf, h->allph_buf, (size_t)h->allph_n, ncclDouble, ncclSum, root, g_comm, h->stream));
+  NCCL_OK(g_nccl.GroupEnd());
+  if (g_comm_rank != root) {  // this rank's contribution now lives on root: the sum over ranks stays "everything so far"
+    CUDA_OK(cudaMemsetAsync(h->P.tally, 0, sizeof(double) * h->P.lay.total, h->stream));
+    if (h->allph_buf) CUDA_OK(cudaMemsetAsync(h->allph_buf, 0, sizeof(double) * h->allph_n, h->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 

@@ -10,8 +10,9 @@ The reference's main program (src/main.f90:19-57) runs
 `run_simulation` + `output_reduce`: it drives the CUDA engine through the C ABI
 (liblart_gpu.so, include/lart_gpu.h) exactly as the Fortran shim
 (shim/lart_gpu_shim.f90) does.  Names follow the reference (par, grid, observer,
-Jout, Jin, nscatt_gas ...).  PyTorch is used only for the multi-GPU plumbing
-(torch.distributed / NCCL) in `output_reduce`.
+Jout, Jin, nscatt_gas ...).  No PyTorch on this path: the multi-GPU reduce is the
+C ABI's own NCCL call (lart_gpu_reduce); torch.distributed is at most the host-side
+broadcast of the communicator id (comm_init_torch), as MPI_BCAST is in the shim.
 """
 import ctypes as C
 
@@ -169,7 +170,7 @@ class Simulation:
     run_simulation(rank, nproc) runs photon ids rank+1, rank+1+nproc, ... as
     run_equal_number does (run_simulation_mod.f90:150); output_reduce() adds the
     device tallies into the model's host buffers (output_sum_rect.f90:7-149),
-    after ONE sum-reduce over NCCL when a torch.distributed group is active.
+    after ONE sum-reduce over NCCL (lart_gpu_reduce) when the process has a communicator (comm_init).
     """
 
     def __init__(self, model, device=0, pool_slots=0, quantum=0, flags=0, seed=None, streams=0, ray_budget=0, max_events=0):
@@ -255,34 +256,12 @@ class Simulation:
         self._check(self._lib.lart_gpu_stream(self._h, C.byref(s)))
         return s.value
 
-    def _as_torch(self, ptr, n):
-        import torch
-
-        class _Buf:  # zero-copy view of the engine's device buffer
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-        return torch.as_tensor(_Buf(), device="cuda:%d" % self.model.config.contents.device)
-
     def output_reduce(self, dst=0):
-        """Sum the tallies of all ranks onto `dst` (ONE NCCL reduce over the contiguous
-        tally buffer; replaces memory_mod_mpi.f90:366-458) and add them to the host arrays."""
-        self.sync()
-        rank = 0
-        try:
-            import torch.distributed as dist
-            active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        except ImportError:
-            active = False
-        if active:
-            import torch
-            rank = dist.get_rank()
-            ptr, n = self.tally_buffer()
-            dist.reduce(self._as_torch(ptr, n), dst=dst, op=dist.ReduceOp.SUM)
-            ptr, n = self.allph_buffer()
-            if n > 0:
-                dist.reduce(self._as_torch(ptr, n), dst=dst, op=dist.ReduceOp.SUM)
-            torch.cuda.synchronize()
-        if rank == dst:
+        """output_reduce (output_sum_rect.f90:7-149): sum the tallies of all ranks onto `dst` — ONE NCCL reduce over the
+        contiguous device tally buffer inside the C ABI (lart_gpu_reduce; a no-op without a communicator, see comm_init)
+        — and add them into the host arrays on `dst`."""
+        self._check(self._lib.lart_gpu_reduce(self._h, dst))
+        if comm_rank() == dst:
             self._check(self._lib.lart_gpu_fetch(self._h, self.model.tallies))
 
     def sightline_tau(self):
@@ -407,6 +386,45 @@ class Simulation:
         self._check(self._lib.lart_gpu_xcrit_batch(self._h, x.size, dp(x), dp(y), dp(z), ip(icell), ip(jcell),
                                                    ip(kcell), dp(out)))
         return out
+
+
+def comm_init(device, nranks, rank, broadcast):
+    """One NCCL communicator per process for lart_gpu_reduce (the MPI_INIT of the GPU path).  `broadcast(buf)` must
+    hand rank 0's 128-byte `bytearray` to every rank (MPI_BCAST on the Fortran side; a torch.distributed or any other
+    host-side broadcast here) and return it."""
+    lib = capi.load_gpu()
+    buf = (C.c_char * 128)()
+    if rank == 0 and lib.lart_gpu_comm_unique_id(buf) != 0:
+        raise LartError(lib.lart_gpu_last_error().decode())
+    raw = broadcast(bytearray(buf.raw))
+    buf = (C.c_char * 128).from_buffer_copy(bytes(raw))
+    if lib.lart_gpu_comm_init(device, nranks, rank, buf) != 0:
+        raise LartError(lib.lart_gpu_last_error().decode())
+
+
+def comm_init_torch(device):
+    """comm_init with torch.distributed (any backend) as the host-side broadcast of the NCCL id."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+
+    def bcast(raw):
+        objs = [bytes(raw)]
+        dist.broadcast_object_list(objs, src=0)
+        return objs[0]
+
+    comm_init(device, world, rank, bcast)
+
+
+def comm_rank():
+    lib = capi.load_gpu()
+    r = C.c_int32()
+    lib.lart_gpu_comm_info(None, C.byref(r))
+    return r.value
+
+
+def comm_finalize():
+    capi.load_gpu().lart_gpu_comm_finalize()
 
 
 def measure_fp64(device=0):

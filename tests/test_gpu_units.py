@@ -309,7 +309,7 @@ def test_peel_bound_implies_capped_walk(name):
     tg, ng, _ = sim.raytrace_to_edge(p[:, 0], p[:, 1], p[:, 2], k[:, 0], k[:, 1], k[:, 2], xf, ic[:, 0], ic[:, 1], ic[:, 2])
     assert np.array_equal(tg, to) and np.array_equal(ng, no)
     c = capped == 1
-    assert c.sum() > 0.1 * n and (~c).sum() > 0.1 * n, c.mean()  # both sides of the bound are sampled
+    assert c.sum() > 0.02 * n and (~c).sum() > 0.1 * n, c.mean()  # both sides of the bound are sampled
     assert (to[c] >= 745.2).all()   # the walk does end at the cap ...
     assert (no[c] == 1).all()       # ... inside the first cell: one cell step, contribution exp(-tau) == 0
     assert np.exp(-to[c]).max() == 0.0

@@ -117,12 +117,7 @@ enum { A_RP0 = 0, A_RP, A_XFREQ1, A_XFREQ2, A_NSG, A_NSD, A_I, A_Q, A_U, A_V };
 // One block gives two 64-bit words; each word maps to the reference's open
 // interval (0,1): ((w>>12)+0.5)*2^-52 — random_mt.f90:628-629.
 // ---------------------------------------------------------------------------
-#ifdef LART_PHILOX_NOINLINE
-__device__ __noinline__
-#else
-LART_DEV
-#endif
-void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+LART_DEV void philox4x32_10_inl(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;  // hi|lo in one IMAD.WIDE.U32
@@ -133,6 +128,22 @@ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint3
     k1 += 0xBB67AE85u;
   }
 }
+#ifdef LART_PHILOX_NOINLINE
+// One copy of the ten rounds per kernel instead of one per draw site (the scatter stage has ~10 sites, ~100 SASS
+// instructions each): arguments and result travel in registers (by value), so the call costs a few moves.
+__device__ __noinline__ uint4 philox4x32_10_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  philox4x32_10_inl(c0, c1, c2, c3, k0, k1);
+  return make_uint4(c0, c1, c2, c3);
+}
+LART_DEV void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+  const uint4 r = philox4x32_10_call(c0, c1, c2, c3, k0, k1);
+  c0 = r.x; c1 = r.y; c2 = r.z; c3 = r.w;
+}
+#else
+LART_DEV void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+  philox4x32_10_inl(c0, c1, c2, c3, k0, k1);
+}
+#endif
 
 // per-thread work counters of ONE kernel launch (32 bits are plenty; they are summed into FP64 totals)
 typedef unsigned int ctr_t;
@@ -1219,6 +1230,166 @@ LART_DEV void sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11, ctr
     double Pcomp = 1.0 + S12overS11 * (ph.Q * c2 + ph.U * s2);
     ++nrej;
     if (Prand <= Pcomp) break;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative versions of the two other rejection loops of a resonance scattering (north-star part 3).
+// Serial loops run until the slowest lane of the warp accepts — measured on the tau0 = 1e7 sphere: 6.7 rounds of the
+// azimuth loop per warp with 9 of 32 lanes active (a dipole scattering leaves the photon strongly polarised, the
+// acceptance of a trial is 1/(1 + |S12/S11| p) ~ 0.5-0.9).  Here every lane first tries the next trial of its own
+// photon (no exchange); the np photons still pending then share the warp — 32/np consecutive trials of each photon's
+// own Philox stream are evaluated in parallel and the first accepted one in stream order wins.  The block counter
+// advances exactly past the accepted trial: values and all later draws are those of the serial loop.
+// Must be called by all 32 lanes of a converged warp; `mine` = this lane has a photon to sample.
+// ---------------------------------------------------------------------------
+// sample_phi_stokes — scattering_car.f90:364-371
+LART_DEV void sample_phi_stokes_warp(VzWarpShared &sh, bool mine, Rng &r, double Q, double U, double S12overS11, ctr_t &nrej,
+                                     double &cosp, double &sinp) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const double env = 1.0 + fabs(S12overS11) * sqrt(Q * Q + U * U);
+  bool todo = mine;
+  if (todo) {  // round 1: my own next trial
+    double u1, u2;
+    r.uniform2(u1, u2);
+    sincospi(2.0 * u1, &sinp, &cosp);
+    const double c2 = 2.0 * cosp * cosp - 1.0, s2 = 2.0 * sinp * cosp;
+    ++nrej;
+    todo = !(env * u2 <= 1.0 + S12overS11 * (Q * c2 + U * s2));
+  }
+  unsigned pend = __ballot_sync(FULL, todo);
+  while (pend) {
+    const int np = __popc(pend), rank = __popc(pend & lt);
+    if (todo) { sh.x0[rank] = Q; sh.a[rank] = U; sh.r0[rank] = S12overS11; sh.r1[rank] = env; sh.id[rank] = r.stream; sh.nb[rank] = r.nblk; }
+    __syncwarp();
+    const int tpj = 32 / np, job = lane / tpj, t = lane - job * tpj;
+    const bool work = job < np;
+    const unsigned grp = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (job * tpj));
+    bool acc = false;
+    double c = 1.0, sn = 0.0;
+    if (work) {
+      double u1, u2;
+      philox_uniform2(r.seed, sh.id[job], sh.nb[job] + t, u1, u2);
+      sincospi(2.0 * u1, &sn, &c);
+      const double c2 = 2.0 * c * c - 1.0, s2 = 2.0 * sn * c;
+      acc = sh.r1[job] * u2 <= 1.0 + sh.r0[job] * (sh.x0[job] * c2 + sh.a[job] * s2);
+    }
+    const unsigned accm = __ballot_sync(FULL, acc);
+    if (acc && (accm & grp & lt) == 0u) { sh.tab[job][0] = c; sh.tab[job][1] = sn; sh.first[job] = t; }
+    __syncwarp();
+    if (todo) {
+      const unsigned my = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (rank * tpj));
+      int used = tpj;
+      if (accm & my) { cosp = sh.tab[rank][0]; sinp = sh.tab[rank][1]; used = sh.first[rank] + 1; todo = false; }
+      r.nblk += used; r.nrng += 2 * used; nrej += used;
+    }
+    __syncwarp();
+    pend = __ballot_sync(FULL, todo);
+  }
+}
+// The pair of rand_gauss1 deviates of one Marsaglia polar draw (random_mt.f90:964-988), warp-cooperative:
+// g_first is what the drawing call returns (v2*f), g_spare what it leaves behind for the next call (v1*f).
+LART_DEV void gauss_pair_warp(VzWarpShared &sh, bool mine, Rng &r, ctr_t &nrej, double &g_first, double &g_spare) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  double v1 = 0.0, v2 = 0.0, rsq = 0.5;
+  bool todo = mine;
+  if (todo) {
+    r.uniform2(v1, v2);
+    v1 = 2.0 * v1 - 1.0; v2 = 2.0 * v2 - 1.0;
+    rsq = v1 * v1 + v2 * v2;
+    ++nrej;
+    todo = !(rsq > 0.0 && rsq < 1.0);
+  }
+  unsigned pend = __ballot_sync(FULL, todo);
+  while (pend) {
+    const int np = __popc(pend), rank = __popc(pend & lt);
+    if (todo) { sh.id[rank] = r.stream; sh.nb[rank] = r.nblk; }
+    __syncwarp();
+    const int tpj = 32 / np, job = lane / tpj, t = lane - job * tpj;
+    const bool work = job < np;
+    const unsigned grp = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (job * tpj));
+    bool acc = false;
+    double w1 = 0.0, w2 = 0.0, wr = 0.0;
+    if (work) {
+      philox_uniform2(r.seed, sh.id[job], sh.nb[job] + t, w1, w2);
+      w1 = 2.0 * w1 - 1.0; w2 = 2.0 * w2 - 1.0;
+      wr = w1 * w1 + w2 * w2;
+      acc = wr > 0.0 && wr < 1.0;
+    }
+    const unsigned accm = __ballot_sync(FULL, acc);
+    if (acc && (accm & grp & lt) == 0u) { sh.tab[job][0] = w1; sh.tab[job][1] = w2; sh.tab[job][2] = wr; sh.first[job] = t; }
+    __syncwarp();
+    if (todo) {
+      const unsigned my = (tpj == 32) ? FULL : (((1u << tpj) - 1u) << (rank * tpj));
+      int used = tpj;
+      if (accm & my) { v1 = sh.tab[rank][0]; v2 = sh.tab[rank][1]; rsq = sh.tab[rank][2]; used = sh.first[rank] + 1; todo = false; }
+      r.nblk += used; r.nrng += 2 * used; nrej += used;
+    }
+    __syncwarp();
+    pend = __ballot_sync(FULL, todo);
+  }
+  const double f = sqrt(-2.0 * log(rsq) / rsq);
+  g_spare = v1 * f;
+  g_first = v2 * f;
+}
+
+// scatter_resonance_stokes (:331-486) / _nostokes (:660-827) for a whole warp: the same statements as
+// scatter_resonance_core in the same order of draws, with the two rejection loops served cooperatively.  Lanes
+// without a photon (`active` false) only take part in the collectives.  `peel` as in scatter_resonance_core.
+template <bool STOKES, class PeelFn>
+LART_DEV void scatter_resonance_warp(VzWarpShared &sh, bool active, const DevParams &P, Photon &ph, Rng &r, const CellData &cs,
+                                     Counters &cnt, double uz, double xfreq_atom, PeelFn &&peel) {
+  double cost = 0.0, sint = 0.0, cosp = 1.0, sinp = 0.0;
+  double S22 = 1.0, S11 = 1.0, S12 = 0.0, S33 = 0.0, S44 = 0.0;
+  if (active) {
+    ph.nsg += ph.wgt;
+    cost = rand_resonance_fast(r, P);
+    sint = sqrt(1.0 - cost * cost);
+    const double cost2 = cost * cost;
+    S22 = 0.75 * P.E1 * (cost2 + 1.0); S11 = S22 + P.E2; S12 = 0.75 * P.E1 * (cost2 - 1.0);
+    S33 = 1.5 * P.E1 * cost; S44 = 1.5 * P.E3 * cost;
+  }
+  if (STOKES) sample_phi_stokes_warp(sh, active, r, active ? ph.Q : 0.0, active ? ph.U : 0.0, S12 / S11, cnt.reject, cosp, sinp);
+  else if (active) sincospi(2.0 * r.uniform(), &sinp, &cosp);
+  double xc = 0.0, xc2 = 0.0;
+  if (active && P.core_skip) car_xcrit_local(P, ph.ic, ph.jc, ph.kc, ph.x, ph.y, ph.z, cs.voigt_a, cs.rhokap, xc, xc2);
+  const bool skip = active && P.core_skip && fabs(ph.xfreq) < xc;
+  double ux = 0.0, uy = 0.0;
+  if (STOKES) {  // :413-414: two rand_gauss calls = the stored spare (if any) and one polar pair
+    const bool need = active && !skip;
+    double g_first, g_spare;
+    gauss_pair_warp(sh, need, r, cnt.reject, g_first, g_spare);
+    if (need) {
+      const double one_over_sqrt2 = 1.0 / 1.4142135623730951;
+      if (r.gauss_stored) { ux = r.gset * one_over_sqrt2; uy = g_first * one_over_sqrt2; r.gset = g_spare; }
+      else { ux = g_first * one_over_sqrt2; uy = g_spare * one_over_sqrt2; }
+    }
+  }
+  if (active && (!STOKES || skip)) {  // :397-401 / :749-752
+    double u1, u2;
+    r.uniform2(u1, u2);
+    const double uxy = skip ? sqrt(xc2 - log(u2)) : sqrt(-log(u2));
+    double s2, c2;
+    sincospi(2.0 * u1, &s2, &c2);
+    ux = uxy * c2; uy = uxy * s2;
+  }
+  if (!active) return;
+  ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
+  if (P.recoil) ph.xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
+  if (P.save_peeloff) peel(xfreq_atom, ux, uy, uz);
+  if (STOKES) {
+    const double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
+    const double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;
+    const double I1 = S11 + S12 * Q0, Q1 = S12 + S22 * Q0, U1 = S33 * U0, V1 = S44 * ph.V;
+    const double iI = 1.0 / I1;
+    ph.Q = Q1 * iI; ph.U = U1 * iI; ph.V = V1 * iI;
+    rotate_triad(ph, cost, sint, cosp, sinp);
+  } else {
+    rotate_k(ph, cost, sint, cosp, sinp);
   }
 }
 

@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
 #define LART_PEEL_BOUND 1
 #endif
 #ifndef LART_REGROUP
-#define LART_REGROUP 1
+#define LART_REGROUP 0
 #endif
 constexpr int kScatBlock = LART_SCATTER_BLOCK;
 constexpr int kWingCap = 1536;  // listed wing photons per block (a block owns ~1400 slots of a default partition, ~16 % of them wing)
@@ -810,7 +810,7 @@ __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const 
   return DMUL(kap, L) >= kTauHuge;
 }
 
-template <bool STOKES, bool DUST, bool LOCAL>
+template <bool STOKES, bool DUST, bool LOCAL, bool SERIAL>
 __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   __shared__ VzWarpShared vzsh[kScatBlock / 32];
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
   const int end = pl.s0 + pl.n;
   // Pass 0 walks this warp's share of the partition in pool order and scatters the |x| <= 1 photons; wing photons are
   // only listed.  Pass 1 (after one block barrier) scatters the listed photons, 32 per warp.  No barrier inside a pass.
-  const bool two_pass = LART_REGROUP && !DUST && !P.flags_serial_vz;
+  const bool two_pass = LART_REGROUP && !DUST && !SERIAL;
   if (threadIdx.x == 0) n_wing = 0;
   for (int i = threadIdx.x; i < kWingCap; i += kScatBlock) wing_list[i] = -1;  // (entries a full list could not take stay -1)
   __syncthreads();
@@ -915,11 +915,11 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
       ph.xfreq = 0.0; rng.start(P.seed, 0ULL);
     }
     const bool resonant = active && !to_dust;
-    const double uz_w = (P.flags_serial_vz) ? (resonant ? rand_resonance_vz(rng, ph.xfreq, a_cell, cnt.reject) : 0.0)
-                                            : rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, a_cell, cnt.reject);
-    if (!active) continue;
-    // ---- the rest of the photon record and of the cell record
-    {
+    double uz_w = 0.0;
+    if (SERIAL) { if (resonant) uz_w = rand_resonance_vz(rng, ph.xfreq, a_cell, cnt.reject); }  // ablation: per-lane rejection loops
+    else uz_w = rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, a_cell, cnt.reject);
+    // ---- the rest of the photon record and of the cell record (lanes without a photon stay for the warp collectives)
+    if (active) {
       const double *f = pl.f + s;
       ph.x = f[F_X * S]; ph.y = f[F_Y * S]; ph.z = f[F_Z * S];
       ph.kx = f[F_KX * S]; ph.ky = f[F_KY * S]; ph.kz = f[F_KZ * S];
@@ -939,7 +939,7 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
         cs.rhokap = c0.x; cs.voigt_a = c0.y; cs.Dfreq = c1.x; cs.vfx = c1.y; cs.vfy = c2.x; cs.vfz = c2.y; cs.rhokapD = 0.0;
       }
     }
-    const double wgt_in = ph.wgt;
+    const double wgt_in = active ? ph.wgt : 0.0;
     bool peeled = false;
     // With local steps the ray toward observer 0 stays in registers: most of them end inside the
     // photon's own cell (tau cap) and never reach the queue.
@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
       }
     };
     auto drop = [&](const PeelRay &pr) { return bound && peel_certainly_capped(P, vtab, cs, pr); };
-    if (DUST && to_dust) {
+    if (DUST && active && to_dust) {
       scatter_dust(P, ph, rng, cs, cnt, [&]() {
         peeled = true;
         for (int k = 0; k < P.nobs; ++k) {
@@ -965,10 +965,10 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
         }
       });
       if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
-    } else {
-      // do_resonance1 — line_mod.f90:108-139
-      scatter_resonance_core<false, STOKES ? 1 : 0>(P, ph, rng, cs, cnt, uz_w, ph.xfreq - uz_w, 1.0,
-                                                    [&](double xa, double ux, double uy, double uz) {
+    }
+    {
+      // do_resonance1 — line_mod.f90:108-139; then scatter_resonance_stokes / _nostokes with peel-off in between
+      auto peel = [&](double xa, double ux, double uy, double uz) {
         peeled = true;
         for (int k = 0; k < P.nobs; ++k) {
           PeelRay pr;
@@ -976,8 +976,14 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
                                   : peel_resonance_nostokes_prepare2(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr, drop);
           emit_ray(k, code, pr);
         }
-      });
+      };
+      if (SERIAL) {
+        if (resonant) scatter_resonance_core<false, STOKES ? 1 : 0>(P, ph, rng, cs, cnt, uz_w, ph.xfreq - uz_w, 1.0, peel);
+      } else {
+        scatter_resonance_warp<STOKES>(sh, resonant, P, ph, rng, cs, cnt, uz_w, ph.xfreq - uz_w, peel);
+      }
     }
+    if (!active) continue;
     if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
     // ---- bounded runs: the photon is abandoned after max_events scatterings, recorded as it stands
     if (P.max_events > 0 && (ph.flags & PH_ALIVE)) {
@@ -2406,18 +2412,20 @@ int drain_peel_only(lart_gpu_handle h);
 void launch_scatter(lart_gpu_handle h, lart_gpu_ctx::Group &g) {
   const int nb = (g.pool.n + kScatBlock - 1) / kScatBlock;
   const int grid = std::max(1, std::min(nb, h->nsm * LART_SCATTER_MINBLOCKS));
-  const int v = (h->P.use_stokes ? 4 : 0) | (h->P.dust ? 2 : 0) | (h->P.local_steps ? 1 : 0);
-#define LART_SC(ST, DU, LO) k_wf_scatter<ST, DU, LO><<<grid, kScatBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q)
+  const int v = (h->P.use_stokes ? 8 : 0) | (h->P.dust ? 4 : 0) | (h->P.local_steps ? 2 : 0) | (h->P.flags_serial_vz ? 1 : 0);
+#define LART_SC(ST, DU, LO, SE) k_wf_scatter<ST, DU, LO, SE><<<grid, kScatBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q)
+#define LART_SC2(ST, DU, n)                                   \
+  case n + 0: LART_SC(ST, DU, false, false); break;           \
+  case n + 1: LART_SC(ST, DU, false, true); break;            \
+  case n + 2: LART_SC(ST, DU, true, false); break;            \
+  case n + 3: LART_SC(ST, DU, true, true); break;
   switch (v) {
-    case 0: LART_SC(false, false, false); break;
-    case 1: LART_SC(false, false, true); break;
-    case 2: LART_SC(false, true, false); break;
-    case 3: LART_SC(false, true, true); break;
-    case 4: LART_SC(true, false, false); break;
-    case 5: LART_SC(true, false, true); break;
-    case 6: LART_SC(true, true, false); break;
-    default: LART_SC(true, true, true); break;
+    LART_SC2(false, false, 0)
+    LART_SC2(false, true, 4)
+    LART_SC2(true, false, 8)
+    LART_SC2(true, true, 12)
   }
+#undef LART_SC2
 #undef LART_SC
 }
 // sticky device error word -> error return

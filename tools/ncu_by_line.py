@@ -26,6 +26,9 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capt
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 short = re.search(r"(k_\w+)", kname).group(1)
+targs = re.search(r"<([0-9, ]+)>", kname.replace("(bool)", ""))  # template instantiation, e.g. k_wf_scatter<1, 0, 0> -> k_wf_scatterILb1ELb0ELb0E
+if targs:
+    short += "I" + "".join("Lb%sE" % a.strip() for a in targs.group(1).split(","))
 start = next(i for i, l in enumerate(dis) if l.startswith("_Z") and short in l and l.rstrip().endswith(":"))
 cur = "?"
 agg = collections.defaultdict(lambda: [0, 0, 0])

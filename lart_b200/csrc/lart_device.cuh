@@ -530,7 +530,7 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
 // ---------------------------------------------------------------------------
 // photon_type — define.f90:80-111 (I == 1 always; E1,E2,E3 are line constants)
 // ---------------------------------------------------------------------------
-enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8, PH_TAUPEND = 16, PH_INFLIGHT = 64 };
+enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8, PH_TAUPEND = 16, PH_DUSTEV = 32, PH_INFLIGHT = 64 };
 struct Photon {
   long long id;
   double x, y, z, kx, ky, kz, mx, my, mz, nx, ny, nz;
@@ -1337,36 +1337,46 @@ LART_DEV void gauss_pair_warp(VzWarpShared &sh, bool mine, Rng &r, ctr_t &nrej, 
   g_first = v2 * f;
 }
 
-// scatter_resonance_stokes (:331-486) / _nostokes (:660-827) for a whole warp: the same statements as
-// scatter_resonance_core in the same order of draws, with the two rejection loops served cooperatively.  Lanes
-// without a photon (`active` false) only take part in the collectives.  `peel` as in scatter_resonance_core.
-template <bool STOKES, class PeelFn>
-LART_DEV void scatter_resonance_warp(VzWarpShared &sh, bool active, const DevParams &P, Photon &ph, Rng &r, const CellData &cs,
-                                     Counters &cnt, double uz, double xfreq_atom, PeelFn &&peel) {
-  double cost = 0.0, sint = 0.0, cosp = 1.0, sinp = 0.0;
-  double S22 = 1.0, S11 = 1.0, S12 = 0.0, S33 = 0.0, S44 = 0.0;
+// A resonance scattering in two halves, so that each can be its own kernel (lart_engine.cu: k_wf_draw / k_wf_apply):
+//
+//   draw_resonance_warp   every random variate of the event, in the reference's order of draws — u_par
+//                         (rand_resonance_vz), cos(theta) (rand_resonance), the azimuth (rejection, Stokes) and the
+//                         perpendicular atom velocity (two rand_gauss, or the core-skip / no-Stokes form) — with the
+//                         three rejection loops served warp-cooperatively.  Needs the frequency, the cell's Voigt
+//                         parameter, the photon's Q and U and (core-skip only) its position: few registers, so many
+//                         warps are resident to hide the latency of the Philox and libm chains.
+//   apply_resonance       the deterministic rest of scatter_resonance_stokes (:331-486) / _nostokes (:660-827): new
+//                         frequency, recoil, peel-off (`peel` is invoked where the reference calls it, :446 / :788),
+//                         Stokes vector and triad.  Straight-line FP64 code.
+struct ScatterVariates {
+  double uz, cost, cosp, sinp, ux, uy;
+};
+// Must be called by all 32 lanes of a converged warp; `active` = this lane has a resonance scattering to draw.
+// x, a: frequency and Voigt parameter (do_resonance1, line_mod.f90:108-139); Q, U: Stokes parameters (read only with
+// STOKES); xc, xc2: core-skip threshold of this photon (0 = no skip), computed by the caller.
+template <bool STOKES>
+LART_DEV void draw_resonance_warp(VzWarpShared &sh, bool active, const DevParams &P, Rng &r, double x, double a, double Q,
+                                  double U, double xc, double xc2, Counters &cnt, ScatterVariates &v) {
+  v.uz = rand_resonance_vz_warp(sh, active, r, x, a, cnt.reject);
+  double S12overS11 = 0.0;
+  v.cost = 0.0; v.cosp = 1.0; v.sinp = 0.0; v.ux = 0.0; v.uy = 0.0;
   if (active) {
-    ph.nsg += ph.wgt;
-    cost = rand_resonance_fast(r, P);
-    sint = sqrt(1.0 - cost * cost);
-    const double cost2 = cost * cost;
-    S22 = 0.75 * P.E1 * (cost2 + 1.0); S11 = S22 + P.E2; S12 = 0.75 * P.E1 * (cost2 - 1.0);
-    S33 = 1.5 * P.E1 * cost; S44 = 1.5 * P.E3 * cost;
+    v.cost = rand_resonance_fast(r, P);
+    const double cost2 = v.cost * v.cost;
+    const double S22 = 0.75 * P.E1 * (cost2 + 1.0);
+    S12overS11 = 0.75 * P.E1 * (cost2 - 1.0) / (S22 + P.E2);
   }
-  if (STOKES) sample_phi_stokes_warp(sh, active, r, active ? ph.Q : 0.0, active ? ph.U : 0.0, S12 / S11, cnt.reject, cosp, sinp);
-  else if (active) sincospi(2.0 * r.uniform(), &sinp, &cosp);
-  double xc = 0.0, xc2 = 0.0;
-  if (active && P.core_skip) car_xcrit_local(P, ph.ic, ph.jc, ph.kc, ph.x, ph.y, ph.z, cs.voigt_a, cs.rhokap, xc, xc2);
-  const bool skip = active && P.core_skip && fabs(ph.xfreq) < xc;
-  double ux = 0.0, uy = 0.0;
+  if (STOKES) sample_phi_stokes_warp(sh, active, r, Q, U, S12overS11, cnt.reject, v.cosp, v.sinp);
+  else if (active) sincospi(2.0 * r.uniform(), &v.sinp, &v.cosp);
+  const bool skip = active && P.core_skip && fabs(x) < xc;
   if (STOKES) {  // :413-414: two rand_gauss calls = the stored spare (if any) and one polar pair
     const bool need = active && !skip;
     double g_first, g_spare;
     gauss_pair_warp(sh, need, r, cnt.reject, g_first, g_spare);
     if (need) {
       const double one_over_sqrt2 = 1.0 / 1.4142135623730951;
-      if (r.gauss_stored) { ux = r.gset * one_over_sqrt2; uy = g_first * one_over_sqrt2; r.gset = g_spare; }
-      else { ux = g_first * one_over_sqrt2; uy = g_spare * one_over_sqrt2; }
+      if (r.gauss_stored) { v.ux = r.gset * one_over_sqrt2; v.uy = g_first * one_over_sqrt2; r.gset = g_spare; }
+      else { v.ux = g_first * one_over_sqrt2; v.uy = g_spare * one_over_sqrt2; }
     }
   }
   if (active && (!STOKES || skip)) {  // :397-401 / :749-752
@@ -1375,12 +1385,21 @@ LART_DEV void scatter_resonance_warp(VzWarpShared &sh, bool active, const DevPar
     const double uxy = skip ? sqrt(xc2 - log(u2)) : sqrt(-log(u2));
     double s2, c2;
     sincospi(2.0 * u1, &s2, &c2);
-    ux = uxy * c2; uy = uxy * s2;
+    v.ux = uxy * c2; v.uy = uxy * s2;
   }
-  if (!active) return;
-  ph.xfreq = xfreq_atom + uz * cost + (ux * cosp + uy * sinp) * sint;
+}
+template <bool STOKES, class PeelFn>
+LART_DEV void apply_resonance(const DevParams &P, Photon &ph, const CellData &cs, const ScatterVariates &v, PeelFn &&peel) {
+  ph.nsg += ph.wgt;
+  const double cost = v.cost, cosp = v.cosp, sinp = v.sinp;
+  const double sint = sqrt(1.0 - cost * cost);
+  const double cost2 = cost * cost;
+  const double S22 = 0.75 * P.E1 * (cost2 + 1.0), S11 = S22 + P.E2, S12 = 0.75 * P.E1 * (cost2 - 1.0);
+  const double S33 = 1.5 * P.E1 * cost, S44 = 1.5 * P.E3 * cost;
+  const double xfreq_atom = ph.xfreq - v.uz;  // do_resonance1 — line_mod.f90:108-139
+  ph.xfreq = xfreq_atom + v.uz * cost + (v.ux * cosp + v.uy * sinp) * sint;
   if (P.recoil) ph.xfreq -= (P.g_recoil0 / cs.Dfreq) * (1.0 - cost);
-  if (P.save_peeloff) peel(xfreq_atom, ux, uy, uz);
+  if (P.save_peeloff) peel(xfreq_atom, v.ux, v.uy, v.uz);
   if (STOKES) {
     const double cos2p = 2.0 * cosp * cosp - 1.0, sin2p = 2.0 * sinp * cosp;
     const double Q0 = cos2p * ph.Q + sin2p * ph.U, U0 = -sin2p * ph.Q + cos2p * ph.U;

@@ -82,6 +82,7 @@ struct Pool {
   double *rs;                  // [10][S] DDA state of a flight suspended at its per-wave step budget
   int *rc;                     // [3][S]  ... and its current cell
   int *nev;                    // [S] scatterings of the slot's photon so far (bounded runs, lart_config::max_events)
+  double *var;                 // [6][S] variates of the slot's pending scattering: uz, cos(theta), cos(phi), sin(phi), ux, uy
   int S;                       // slots (= SoA stride)
   int s0, n;                   // the partition [s0, s0+n) this kernel launch works on
 };
@@ -761,39 +762,33 @@ __global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ 
   flush_counters(P, cnt, nrng);
 }
 
-// stage 3: scattering for every photon flagged by the trace stage; writes the peel-ray descriptors of its slot.
+// stage 3: scattering for every photon flagged by the trace stage, in two kernels:
 //
-// * Compile-time variants <STOKES, DUST, LOCAL>: the instantiation a run uses carries only its own physics (no
-//   Mueller/alias/HG code in a dust-free run, one peel-off routine instead of four) — smaller code, fewer registers.
-// * Block-level regrouping (dust-free runs): the atom-velocity sampler has two branches, |x| <= 1 (84 % of the
-//   scatterings of an optically thick run) and the wing majorant, whose set-up and trials are ~5x more expensive.  With
-//   slots in pool order nearly every warp holds a few wing photons and runs both branches at a fraction of its lanes.
-//   Each block therefore sorts its active slots by branch first (stable partition through shared memory: ballot ranks +
-//   per-warp counts), so that all but one warp of a block execute a single branch with full lanes; a lane then works on
-//   slot base + perm[lane].  Photon physics does not notice: every photon owns its Philox stream.
-// * Only what the sampler needs (frequency, Voigt parameter, stream position) is loaded before it; position, direction,
-//   triad and Stokes columns follow afterwards (L1-prefetched meanwhile), and only the columns a scattering changes are
-//   written back (position, cell, weight and id stay as they are).
-// * A peel ray whose first cell alone is deeper than the cap ends there with a contribution of exactly zero
-//   (raytrace_car.f90:432,497: tau >= 745.2).  The path inside the cell is at least the distance L to the nearest face
-//   (|k| <= 1), and rounding is monotonic, so kappa*L >= 745.2 proves it without the DDA set-up and its three divides:
-//   such a ray is counted (one peel ray, one cell step, as the walk would; reported as n_peel_bound) and never written
-//   to the queue — the test runs as soon as the ray's frequency is known, before the Stokes algebra.  On a face L = 0.
-#ifndef LART_SCATTER_BLOCK
-#define LART_SCATTER_BLOCK 256
+//   k_wf_draw   every random variate of the event (atom velocity, scattering angles), written to six pool columns.
+//               The Philox rounds and the libm chains of the rejection samplers are long dependent instruction
+//               sequences; as one kernel with the rest of the scattering (128 registers, 16 warps per SM) the stage
+//               issued on 45 % of the cycles with "wait" and "no instruction" as top stalls (profiles/r2_*): it is
+//               latency bound.  Alone, the samplers need few registers, so twice as many warps are resident.  All
+//               three rejection loops are warp-cooperative (lart_device.cuh).
+//   k_wf_apply  the deterministic rest: new frequency, peel-ray descriptors (one per observer), Stokes vector and
+//               triad; dust events (rare) are scattered here serially.  Compile-time variants <STOKES, DUST, LOCAL>:
+//               the instantiation a run uses carries only its own physics.  Only the columns a scattering changes are
+//               written back (position, cell, weight and id stay as they are).
+//
+// A peel ray whose first cell alone is deeper than the cap ends there with a contribution of exactly zero
+// (raytrace_car.f90:432,497: tau >= 745.2).  The path inside the cell is at least the distance L to the nearest face
+// (|k| <= 1), and rounding is monotonic, so kappa*L >= 745.2 proves it without the DDA set-up and its three divides:
+// such a ray is counted (one peel ray, one cell step, as the walk would; reported as n_peel_bound) and never written
+// to the queue — the test runs as soon as the ray's frequency is known, before the Stokes algebra.  On a face L = 0.
+#ifndef LART_DRAW_MINBLOCKS
+#define LART_DRAW_MINBLOCKS 3
 #endif
-#ifndef LART_SCATTER_MINBLOCKS
-#define LART_SCATTER_MINBLOCKS 2
+#ifndef LART_APPLY_MINBLOCKS
+#define LART_APPLY_MINBLOCKS 2
 #endif
 #ifndef LART_PEEL_BOUND
 #define LART_PEEL_BOUND 1
 #endif
-#ifndef LART_REGROUP
-#define LART_REGROUP 0
-#endif
-constexpr int kScatBlock = LART_SCATTER_BLOCK;
-constexpr int kWingCap = 1536;  // listed wing photons per block (a block owns ~1400 slots of a default partition, ~16 % of them wing)
-static_assert(kScatBlock % 32 == 0 && kScatBlock <= kBlock, "scatter block: whole warps, at most kBlock threads");
 
 __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const double *vtab, const CellData &cs, const PeelRay &pr) {
   double L = fmin(DSUB(pr.z, __ldg(P.zface + pr.kc - 1)), DSUB(__ldg(P.zface + pr.kc), pr.z));
@@ -810,136 +805,134 @@ __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const 
   return DMUL(kap, L) >= kTauHuge;
 }
 
-template <bool STOKES, bool DUST, bool LOCAL, bool SERIAL>
-__global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatter(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+// SERIAL (LART_FLAG_SERIAL_REJECTION): per-lane rejection loops, the ablation arm of the cooperative samplers.
+template <bool STOKES, bool DUST, bool SERIAL>
+__global__ void __launch_bounds__(kBlock, LART_DRAW_MINBLOCKS) k_wf_draw(const __grid_constant__ DevParams P, Pool pl) {
+  __shared__ double vtab[DUST ? kVoigtTabN : 1];
+  __shared__ VzWarpShared vzsh[kBlock / 32];
+  if (DUST) load_vtab(P, vtab);
+  VzWarpShared &sh = vzsh[threadIdx.x >> 5];
+  Counters cnt;
+  ctr_t nrng = 0;
+  const int lane = threadIdx.x & 31;
+  const size_t S = pl.S;
+  const int end = pl.s0 + pl.n, stride = gridDim.x * blockDim.x;
+  for (int base = pl.s0 + blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < end; base += stride) {  // warp-uniform
+    const int s = base + lane;
+    const int fl0 = s < end ? pl.flags[s] : 0;
+    const bool active = (fl0 & PH_SCATTER) != 0;
+    if (!__any_sync(0xffffffffu, active)) continue;
+    Rng rng;
+    double x = 0.0, a = 1.0, Q = 0.0, U = 0.0, xc = 0.0, xc2 = 0.0;
+    int fl = fl0;
+    bool to_dust = false;
+    if (active) {
+      const double *f = pl.f + s;
+      x = f[F_XFREQ * S];
+      load_rng(P, pl, s, pl.id[s], fl0, rng);
+      if (STOKES) { Q = f[F_Q * S]; U = f[F_U * S]; }
+      const int ic = pl.ic[s], jc = pl.jc[s], kc = pl.kc[s];
+      double rhokap = 0.0;
+      if (DUST || P.soa) {
+        CellData cs;
+        load_cell(P, ic, jc, kc, cs);
+        a = cs.voigt_a; rhokap = cs.rhokap;
+        if (DUST) {  // scattering_car.f90:106-118
+          const double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, x, cs.voigt_a) + cs.rhokapD);
+          to_dust = rng.uniform() <= pd;
+        }
+      } else {
+        const double2 c0 = __ldg(reinterpret_cast<const double2 *>(P.cells + cell_slot(P, ic, jc, kc)));
+        rhokap = c0.x; a = c0.y;
+      }
+      if (P.core_skip && !to_dust) car_xcrit_local(P, ic, jc, kc, f[F_X * S], f[F_Y * S], f[F_Z * S], a, rhokap, xc, xc2);
+    } else {
+      rng.start(P.seed, 0ULL);
+    }
+    const bool resonant = active && !to_dust;
+    ScatterVariates v;
+    if (SERIAL) {
+      if (resonant) {  // the statements of scatter_resonance_core, draws only
+        v.uz = rand_resonance_vz(rng, x, a, cnt.reject);
+        v.cost = rand_resonance_fast(rng, P);
+        const double cost2 = v.cost * v.cost, S22 = 0.75 * P.E1 * (cost2 + 1.0);
+        if (STOKES) {
+          Photon tmp;
+          tmp.Q = Q; tmp.U = U;
+          sample_phi_stokes(rng, tmp, 0.75 * P.E1 * (cost2 - 1.0) / (S22 + P.E2), cnt.reject, v.cosp, v.sinp);
+        } else {
+          sincospi(2.0 * rng.uniform(), &v.sinp, &v.cosp);
+        }
+        const bool skip = P.core_skip && fabs(x) < xc;
+        if (STOKES && !skip) {
+          const double one_over_sqrt2 = 1.0 / 1.4142135623730951;
+          v.ux = rng.gauss(cnt.reject) * one_over_sqrt2;
+          v.uy = rng.gauss(cnt.reject) * one_over_sqrt2;
+        } else {
+          double u1, u2;
+          rng.uniform2(u1, u2);
+          const double uxy = skip ? sqrt(xc2 - log(u2)) : sqrt(-log(u2));
+          double s2, c2;
+          sincospi(2.0 * u1, &s2, &c2);
+          v.ux = uxy * c2; v.uy = uxy * s2;
+        }
+      }
+    } else {
+      draw_resonance_warp<STOKES>(sh, resonant, P, rng, x, a, Q, U, xc, xc2, cnt, v);
+    }
+    if (!active) continue;
+    if (resonant) {
+      double *o = pl.var + s;
+      o[0 * S] = v.uz; o[1 * S] = v.cost; o[2 * S] = v.cosp; o[3 * S] = v.sinp; o[4 * S] = v.ux; o[5 * S] = v.uy;
+    } else {
+      fl |= PH_DUSTEV;  // k_wf_apply runs scatter_dust from here on the same stream
+    }
+    store_rng(pl, s, rng, fl);
+    if (fl != fl0) pl.flags[s] = fl;
+    nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+template <bool STOKES, bool DUST, bool LOCAL>
+__global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
   __shared__ double vtab[kVoigtTabN];
-  __shared__ VzWarpShared vzsh[kScatBlock / 32];
-  __shared__ int wing_list[kWingCap];
-  __shared__ int n_wing;
   const bool bound = LART_PEEL_BOUND && !LOCAL && P.save_peeloff;
   if (LOCAL || DUST || bound) load_vtab(P, vtab);
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
-  VzWarpShared &sh = vzsh[warp];
   Counters cnt;
   ctr_t nrng = 0;
   const size_t S = pl.S;
   const int end = pl.s0 + pl.n;
-  // Pass 0 walks this warp's share of the partition in pool order and scatters the |x| <= 1 photons; wing photons are
-  // only listed.  Pass 1 (after one block barrier) scatters the listed photons, 32 per warp.  No barrier inside a pass.
-  const bool two_pass = LART_REGROUP && !DUST && !SERIAL;
-  if (threadIdx.x == 0) n_wing = 0;
-  for (int i = threadIdx.x; i < kWingCap; i += kScatBlock) wing_list[i] = -1;  // (entries a full list could not take stay -1)
-  __syncthreads();
-  int pass = 0;
-  int base = pl.s0 + blockIdx.x * kScatBlock + warp * 32;
-  const int stride = gridDim.x * kScatBlock;
-  for (;;) {
-    int s = 0;
-    bool active = false;
-    double xf0 = 0.0;
-    if (pass == 0) {
-      if (base >= end) {  // every warp of the block passes here exactly once
-        pass = 1;
-        __syncthreads();
-        base = warp * 32;
-        continue;
-      }
-      s = base + lane;
-      base += stride;
-      const bool inb = s < end;
-      const int fl0 = inb ? pl.flags[s] : 0;
-      active = (fl0 & PH_SCATTER) != 0;
-      if (inb && !active)
-        for (int k = 0; k < P.nobs; ++k) q.rays[(size_t)s * P.nobs + k].kind = -1;
-      if (!__any_sync(FULL, active)) continue;
-      if (active) xf0 = pl.f[(size_t)F_XFREQ * S + s];
-      if (two_pass) {
-        const bool wing = active && !(fabs(xf0) <= 1.0);
-        const unsigned mw = __ballot_sync(FULL, wing);
-        if (mw) {
-          int at = 0;
-          if (lane == 0) at = atomicAdd(&n_wing, __popc(mw));
-          at = __shfl_sync(FULL, at, 0);
-          if (at + __popc(mw) <= kWingCap) {  // (a full list: these photons are scattered here, in mixed company)
-            if (wing) { wing_list[at + __popc(mw & lt)] = s; active = false; }
-            if (!__any_sync(FULL, active)) continue;
-          }
-        }
-      }
-    } else {
-      const int nw = min(n_wing, kWingCap);
-      if (base >= nw) break;
-      s = base + lane < nw ? wing_list[base + lane] : -1;
-      active = s >= 0;
-      if (active) xf0 = pl.f[(size_t)F_XFREQ * S + s];
-      else s = 0;
-      base += kScatBlock;
+  for (int s = pl.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < end; s += gridDim.x * blockDim.x) {
+    const int fl0 = pl.flags[s];
+    PeelRay *myrays = q.rays + (size_t)s * P.nobs;
+    if (!(fl0 & PH_SCATTER)) {
+      for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
+      continue;
     }
-    PeelRay *myrays = q.rays + (size_t)(active ? s : 0) * P.nobs;
     Photon ph;
-    Rng rng;
     CellData cs;
-    bool to_dust = false;
-    double a_cell = 1.0;
-    const Cell *cellp = nullptr;
-    if (active) {
-      ph.flags = pl.flags[s] & ~PH_SCATTER;
-      ph.id = pl.id[s];
-      ph.ic = pl.ic[s]; ph.jc = pl.jc[s]; ph.kc = pl.kc[s];
-      ph.xfreq = xf0;
-      {  // everything else is needed only after the sampler: warm L1 now
-        const double *f = pl.f + s;
-#pragma unroll
-        for (int c = F_X; c <= F_NZ; ++c) prefetch_l1(f + (size_t)c * S);
-        prefetch_l1(f + (size_t)F_WGT * S);
-        prefetch_l1(f + (size_t)F_NSG * S);
-        if (STOKES) { prefetch_l1(f + (size_t)F_Q * S); prefetch_l1(f + (size_t)F_U * S); prefetch_l1(f + (size_t)F_V * S); }
-        if (ph.flags & PH_GAUSS) prefetch_l1(f + (size_t)F_GSET * S);
-      }
-      load_rng(P, pl, s, ph.id, ph.flags, rng);
-      cnt.scatter += 1;
-      if (DUST || P.soa) {
-        load_cell(P, ph.ic, ph.jc, ph.kc, cs);
-        a_cell = cs.voigt_a;
-        if (DUST) {
-          double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, ph.xfreq, cs.voigt_a) + cs.rhokapD);
-          to_dust = rng.uniform() <= pd;
-        }
-      } else {  // only the Voigt parameter now; the record is re-read (from L1) after the sampler
-        cellp = P.cells + cell_slot(P, ph.ic, ph.jc, ph.kc);
-        a_cell = __ldg(&cellp->voigt_a);
-      }
-    } else {
-      ph.xfreq = 0.0; rng.start(P.seed, 0ULL);
+    const double *f = pl.f + s;
+    ph.flags = fl0 & ~(PH_SCATTER | PH_DUSTEV);
+    ph.id = pl.id[s];
+    ph.ic = pl.ic[s]; ph.jc = pl.jc[s]; ph.kc = pl.kc[s];
+    load_cell(P, ph.ic, ph.jc, ph.kc, cs);
+    ph.x = f[F_X * S]; ph.y = f[F_Y * S]; ph.z = f[F_Z * S];
+    ph.kx = f[F_KX * S]; ph.ky = f[F_KY * S]; ph.kz = f[F_KZ * S];
+    ph.xfreq = f[F_XFREQ * S]; ph.wgt = f[F_WGT * S]; ph.nsg = f[F_NSG * S];
+    ph.nsd = DUST ? f[F_NSD * S] : 0.0;
+    ph.xfreq_ref = 0.0;
+    if (STOKES) {
+      ph.mx = f[F_MX * S]; ph.my = f[F_MY * S]; ph.mz = f[F_MZ * S];
+      ph.nx = f[F_NX * S]; ph.ny = f[F_NY * S]; ph.nz = f[F_NZ * S];
+      ph.Q = f[F_Q * S]; ph.U = f[F_U * S]; ph.V = f[F_V * S];
+    } else {  // no triad and no Stokes vector in this variant (record_final reads them only with par%use_stokes)
+      ph.mx = ph.my = ph.mz = ph.nx = ph.ny = ph.nz = 0.0; ph.Q = ph.U = ph.V = 0.0;
     }
-    const bool resonant = active && !to_dust;
-    double uz_w = 0.0;
-    if (SERIAL) { if (resonant) uz_w = rand_resonance_vz(rng, ph.xfreq, a_cell, cnt.reject); }  // ablation: per-lane rejection loops
-    else uz_w = rand_resonance_vz_warp(sh, resonant, rng, ph.xfreq, a_cell, cnt.reject);
-    // ---- the rest of the photon record and of the cell record (lanes without a photon stay for the warp collectives)
-    if (active) {
-      const double *f = pl.f + s;
-      ph.x = f[F_X * S]; ph.y = f[F_Y * S]; ph.z = f[F_Z * S];
-      ph.kx = f[F_KX * S]; ph.ky = f[F_KY * S]; ph.kz = f[F_KZ * S];
-      ph.wgt = f[F_WGT * S]; ph.nsg = f[F_NSG * S];
-      ph.nsd = DUST ? f[F_NSD * S] : 0.0;
-      ph.xfreq_ref = 0.0;
-      if (STOKES) {
-        ph.mx = f[F_MX * S]; ph.my = f[F_MY * S]; ph.mz = f[F_MZ * S];
-        ph.nx = f[F_NX * S]; ph.ny = f[F_NY * S]; ph.nz = f[F_NZ * S];
-        ph.Q = f[F_Q * S]; ph.U = f[F_U * S]; ph.V = f[F_V * S];
-      } else {  // no triad and no Stokes vector in this variant (record_final reads them only with par%use_stokes)
-        ph.mx = ph.my = ph.mz = ph.nx = ph.ny = ph.nz = 0.0; ph.Q = ph.U = ph.V = 0.0;
-      }
-      if (!(DUST || P.soa)) {
-        const double2 *qc = reinterpret_cast<const double2 *>(cellp);
-        const double2 c0 = __ldg(qc), c1 = __ldg(qc + 1), c2 = __ldg(qc + 2);
-        cs.rhokap = c0.x; cs.voigt_a = c0.y; cs.Dfreq = c1.x; cs.vfx = c1.y; cs.vfy = c2.x; cs.vfz = c2.y; cs.rhokapD = 0.0;
-      }
-    }
-    const double wgt_in = active ? ph.wgt : 0.0;
+    const double wgt_in = ph.wgt;
+    cnt.scatter += 1;
+    Rng rng;
+    bool have_rng = false;
     bool peeled = false;
     // With local steps the ray toward observer 0 stays in registers: most of them end inside the
     // photon's own cell (tau cap) and never reach the queue.
@@ -954,7 +947,9 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
       }
     };
     auto drop = [&](const PeelRay &pr) { return bound && peel_certainly_capped(P, vtab, cs, pr); };
-    if (DUST && active && to_dust) {
+    if (DUST && (fl0 & PH_DUSTEV)) {
+      load_rng(P, pl, s, ph.id, ph.flags, rng);
+      have_rng = true;
       scatter_dust(P, ph, rng, cs, cnt, [&]() {
         peeled = true;
         for (int k = 0; k < P.nobs; ++k) {
@@ -965,10 +960,11 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
         }
       });
       if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
-    }
-    {
-      // do_resonance1 — line_mod.f90:108-139; then scatter_resonance_stokes / _nostokes with peel-off in between
-      auto peel = [&](double xa, double ux, double uy, double uz) {
+    } else {
+      const double *vi = pl.var + s;
+      ScatterVariates v;
+      v.uz = vi[0 * S]; v.cost = vi[1 * S]; v.cosp = vi[2 * S]; v.sinp = vi[3 * S]; v.ux = vi[4 * S]; v.uy = vi[5 * S];
+      apply_resonance<STOKES>(P, ph, cs, v, [&](double xa, double ux, double uy, double uz) {
         peeled = true;
         for (int k = 0; k < P.nobs; ++k) {
           PeelRay pr;
@@ -976,14 +972,8 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
                                   : peel_resonance_nostokes_prepare2(P, P.obs[k], k, ph, cs, xa, ux, uy, uz, pr, drop);
           emit_ray(k, code, pr);
         }
-      };
-      if (SERIAL) {
-        if (resonant) scatter_resonance_core<false, STOKES ? 1 : 0>(P, ph, rng, cs, cnt, uz_w, ph.xfreq - uz_w, 1.0, peel);
-      } else {
-        scatter_resonance_warp<STOKES>(sh, resonant, P, ph, rng, cs, cnt, uz_w, ph.xfreq - uz_w, peel);
-      }
+      });
     }
-    if (!active) continue;
     if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
     // ---- bounded runs: the photon is abandoned after max_events scatterings, recorded as it stands
     if (P.max_events > 0 && (ph.flags & PH_ALIVE)) {
@@ -1009,11 +999,12 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
       }
       // ---- first cell step of the next flight (raytrace_to_tau): most flights end inside the cell
       if (ph.flags & PH_ALIVE) {
+        if (!have_rng) { load_rng(P, pl, s, ph.id, ph.flags, rng); have_rng = true; }
         const double tau_in = -log(rng.uniform());
         Ray r;
         if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true, &cs)) {
           ph.flags &= ~PH_ALIVE;  // already leaving: dead without tally (raytrace_car.f90:1469-1472)
-            retire_photon(P, ph, false, job, cnt);
+          retire_photon(P, ph, false, job, cnt);
         } else {
           double xp, yp, zp;
           const int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
@@ -1025,7 +1016,7 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
             cnt.cellsteps += r.nsteps;
             moved = true;
           } else if (st == 2) {
-                cnt.cellsteps += finish_escape(P, ph, r);
+            cnt.cellsteps += finish_escape(P, ph, r);
             retire_photon(P, ph, true, job, cnt);
             moved = true;
           } else {  // crossed into the next cell: the trace stage walks it (from its start) with this tau
@@ -1038,24 +1029,24 @@ __global__ void __launch_bounds__(kScatBlock, LART_SCATTER_MINBLOCKS) k_wf_scatt
     // ---- write back what a scattering changes
     {
       int fl = ph.flags;
-      store_rng(pl, s, rng, fl);
+      if (have_rng) { store_rng(pl, s, rng, fl); nrng += rng.nrng; }
+      else fl |= fl0 & PH_GAUSS;  // the spare deviate k_wf_draw left stays
       pl.flags[s] = fl;
-      double *f = pl.f + s;
-      f[F_XFREQ * S] = ph.xfreq;
-      f[F_KX * S] = ph.kx; f[F_KY * S] = ph.ky; f[F_KZ * S] = ph.kz;
-      f[F_NSG * S] = ph.nsg;
+      double *o = pl.f + s;
+      o[F_XFREQ * S] = ph.xfreq;
+      o[F_KX * S] = ph.kx; o[F_KY * S] = ph.ky; o[F_KZ * S] = ph.kz;
+      o[F_NSG * S] = ph.nsg;
       if (STOKES) {
-        f[F_MX * S] = ph.mx; f[F_MY * S] = ph.my; f[F_MZ * S] = ph.mz;
-        f[F_NX * S] = ph.nx; f[F_NY * S] = ph.ny; f[F_NZ * S] = ph.nz;
-        f[F_Q * S] = ph.Q; f[F_U * S] = ph.U; f[F_V * S] = ph.V;
+        o[F_MX * S] = ph.mx; o[F_MY * S] = ph.my; o[F_MZ * S] = ph.mz;
+        o[F_NX * S] = ph.nx; o[F_NY * S] = ph.ny; o[F_NZ * S] = ph.nz;
+        o[F_Q * S] = ph.Q; o[F_U * S] = ph.U; o[F_V * S] = ph.V;
       }
-      if (DUST) { f[F_NSD * S] = ph.nsd; if (ph.wgt != wgt_in) f[F_WGT * S] = ph.wgt; }
+      if (DUST) { o[F_NSD * S] = ph.nsd; if (ph.wgt != wgt_in) o[F_WGT * S] = ph.wgt; }
       if (LOCAL && moved) {
-        f[F_X * S] = ph.x; f[F_Y * S] = ph.y; f[F_Z * S] = ph.z; f[F_XREF * S] = ph.xfreq_ref;
+        o[F_X * S] = ph.x; o[F_Y * S] = ph.y; o[F_Z * S] = ph.z; o[F_XREF * S] = ph.xfreq_ref;
         pl.ic[s] = ph.ic; pl.jc[s] = ph.jc; pl.kc[s] = ph.kc;
       }
     }
-    nrng += rng.nrng;
   }
   flush_counters(P, cnt, nrng);
 }
@@ -2310,6 +2301,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   rc = rc ? rc : dalloc(h, &h->pool.rs, (size_t)10 * S);
   rc = rc ? rc : dalloc(h, &h->pool.rc, (size_t)3 * S);
   rc = rc ? rc : dalloc(h, &h->pool.nev, S);
+  if (!mono) rc = rc ? rc : dalloc(h, &h->pool.var, (size_t)6 * S);
   rc = rc ? rc : dalloc(h, &h->job, 1);
   if (!rc) P.err = &h->job->err;
   P.max_events = cfg->max_events > 0 ? cfg->max_events : 0;
@@ -2408,25 +2400,24 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
 
 namespace {
 int drain_peel_only(lart_gpu_handle h);
-// the scatter-stage instantiation of this run: <use_stokes, dust, local steps>
+// the scatter-stage instantiations of this run: k_wf_draw<use_stokes, dust, serial rejection>, k_wf_apply<use_stokes, dust, local steps>
 void launch_scatter(lart_gpu_handle h, lart_gpu_ctx::Group &g) {
-  const int nb = (g.pool.n + kScatBlock - 1) / kScatBlock;
-  const int grid = std::max(1, std::min(nb, h->nsm * LART_SCATTER_MINBLOCKS));
-  const int v = (h->P.use_stokes ? 8 : 0) | (h->P.dust ? 4 : 0) | (h->P.local_steps ? 2 : 0) | (h->P.flags_serial_vz ? 1 : 0);
-#define LART_SC(ST, DU, LO, SE) k_wf_scatter<ST, DU, LO, SE><<<grid, kScatBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q)
-#define LART_SC2(ST, DU, n)                                   \
-  case n + 0: LART_SC(ST, DU, false, false); break;           \
-  case n + 1: LART_SC(ST, DU, false, true); break;            \
-  case n + 2: LART_SC(ST, DU, true, false); break;            \
-  case n + 3: LART_SC(ST, DU, true, true); break;
-  switch (v) {
-    LART_SC2(false, false, 0)
-    LART_SC2(false, true, 4)
-    LART_SC2(true, false, 8)
-    LART_SC2(true, true, 12)
+  const int nb = (g.pool.n + kBlock - 1) / kBlock;
+  const int gd = std::max(1, std::min(nb, h->nsm * LART_DRAW_MINBLOCKS)), ga = std::max(1, std::min(nb, h->nsm * LART_APPLY_MINBLOCKS));
+  const int st = h->P.use_stokes ? 4 : 0, du = h->P.dust ? 2 : 0;
+#define LART_DR(ST, DU, SE) k_wf_draw<ST, DU, SE><<<gd, kBlock, 0, g.stream>>>(h->P, g.pool)
+#define LART_AP(ST, DU, LO) k_wf_apply<ST, DU, LO><<<ga, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q)
+#define LART_8(M, v)                                                                                              \
+  switch (v) {                                                                                                    \
+    case 0: M(false, false, false); break; case 1: M(false, false, true); break; case 2: M(false, true, false); break; \
+    case 3: M(false, true, true); break;   case 4: M(true, false, false); break; case 5: M(true, false, true); break;  \
+    case 6: M(true, true, false); break;   default: M(true, true, true); break;                                    \
   }
-#undef LART_SC2
-#undef LART_SC
+  LART_8(LART_DR, st | du | (h->P.flags_serial_vz ? 1 : 0))
+  LART_8(LART_AP, st | du | (h->P.local_steps ? 1 : 0))
+#undef LART_8
+#undef LART_AP
+#undef LART_DR
 }
 // sticky device error word -> error return
 int check_device_error(unsigned int err) {
@@ -2519,7 +2510,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
       }
       CUDA_OK(cudaGraphLaunch(it->second, h->stream));
     }
-    h->launches += (h->P.nobs == 0 ? 4LL : 5LL) * G * qn;
+    h->launches += (h->P.nobs == 0 ? 5LL : 6LL) * G * qn;
     h->pending_rays = true;
   }
   CUDA_OK(cudaEventRecord(h->ev1, h->stream));

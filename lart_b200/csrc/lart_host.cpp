@@ -90,6 +90,8 @@ struct Par {
   std::string distance_unit, source_geometry = "point", spectral_type = "voigt";
   bool use_reduced_wgt = false, use_stokes = false;
   bool save_Jin = true, save_Jabs = true, save_Jmu = false;
+  bool continuum_normalize = true;  // define.f90:314
+  double f_line = 0.0;              // define.f90:320 (internal: line fraction of 'continuum+gaussian', not on this path)
   int nmu = 11;
   double mu_min = -1.0, dmu = 0.0;
   bool save_direc0 = false, save_all_photons = false;
@@ -211,7 +213,7 @@ int set_key(lart_host_model *m, std::string key, const std::string &value) {
   REAL(velocity_min) REAL(velocity_max) INT(nvelocity)
   REAL(distance2cm) REAL(gaussian_sigma_vel) REAL(gaussian_FWHM_vel)
   STR(distance_unit) STR(source_geometry) STR(spectral_type)
-  BOOL(use_reduced_wgt) BOOL(use_stokes) BOOL(save_Jin) BOOL(save_Jabs) BOOL(save_Jmu) INT(nmu)
+  BOOL(use_reduced_wgt) BOOL(use_stokes) BOOL(save_Jin) BOOL(save_Jabs) BOOL(save_Jmu) BOOL(continuum_normalize) INT(nmu)
   BOOL(save_direc0) BOOL(save_all_photons) BOOL(save_peeloff) BOOL(save_peeloff_2D) BOOL(save_peeloff_3D)
   INT(intensity_unit)
   REAL(hgg) REAL(albedo) REAL(cext_dust) REAL(DGR) STR(scatt_mat_file)
@@ -1073,6 +1075,21 @@ int lart_host_normalize(lart_host_model *m) {
     if (t.Jabs) t.Jabs[i] /= den;
   }
   if (t.Jmu) for (size_t i = 0; i < nxf * p.nmu; ++i) t.Jmu[i] = t.Jmu[i] * p.nmu / den;
+  // continuum runs are expressed in units of the input continuum level — output_sum_rect.f90:252-273
+  // (par%continuum_normalize defaults to .true., define.f90:314; the reference aborts without save_Jin)
+  if (p.spectral_type == "continuum" && p.continuum_normalize) {
+    if (!t.Jin) { g_err = "ERROR: continuum_normalize=T requires save_Jin=T"; return 1; }
+    double mean = 0.0;
+    for (size_t i = 0; i < nxf; ++i) mean += t.Jin[i];
+    mean /= static_cast<double>(nxf);
+    const double scale = (p.f_line > 0.0 && p.f_line < 1.0) ? mean * (1.0 - p.f_line) : mean;
+    for (size_t i = 0; i < nxf; ++i) {
+      t.Jout[i] /= scale;
+      t.Jin[i] /= scale;
+      if (t.Jabs) t.Jabs[i] /= scale;
+    }
+    if (t.Jmu) for (size_t i = 0; i < nxf * p.nmu; ++i) t.Jmu[i] /= scale;
+  }
   for (size_t k = 0; k < m->obs_out.size(); ++k) {  // :405-450
     lart_observer_out &oo = m->obs_out[k];
     const size_t n2 = static_cast<size_t>(p.nxim) * p.nyim, n3 = n2 * nxf;

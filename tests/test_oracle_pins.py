@@ -197,3 +197,27 @@ def test_rand_resonance_phase_function():
     assert abs(mu.mean() - g) < 5e-3
     z = oracle.sample(1, 3, np.arange(100000)).ravel()
     assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.02
+
+
+def test_continuum_runs_are_normalised_to_the_input_continuum_level():
+    """output_normalize_outside, continuum branch (output_sum_rect.f90:252-273; par%continuum_normalize defaults to
+    .true., define.f90:314): every spectrum is divided by mean(Jin), so the injected continuum sits at 1; without
+    save_Jin the reference aborts."""
+    from lart_b200 import LartError, Model
+    kw = dict(no_photons=4000, temperature=1e4, taumax=5.0, nx=11, ny=11, nz=11, rmax=1.0, spectral_type="continuum",
+              nxfreq=40, xfreq_min=-20.0, xfreq_max=20.0, save_Jmu=True, nmu=3, iseed=3)
+    m = Model(**kw).setup()
+    oracle.run(m, rng_mode=1, nthreads=2)
+    m.output_normalize()
+    assert m.spectrum("Jin").mean() == pytest.approx(1.0, rel=1e-12)
+    assert m.spectrum("Jout").mean() == pytest.approx(1.0, rel=0.05)  # no dust: what goes in comes out
+    assert m.spectrum("Jmu").sum(1).mean() / 3 == pytest.approx(m.spectrum("Jout").mean(), rel=1e-9)
+    raw = Model(continuum_normalize=False, **kw).setup()
+    oracle.run(raw, rng_mode=1, nthreads=2)
+    raw.output_normalize()
+    assert raw.spectrum("Jin").mean() != pytest.approx(1.0, rel=0.5)
+    assert np.allclose(raw.spectrum("Jout") / raw.spectrum("Jin").mean(), m.spectrum("Jout"), rtol=1e-12)
+    bad = Model(save_Jin=False, **kw).setup()
+    oracle.run(bad, rng_mode=1, nthreads=2)
+    with pytest.raises(LartError, match="save_Jin"):
+        bad.output_normalize()

@@ -79,6 +79,10 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true", help="device-resident arm only (profiling runs)")
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--streams", type=int, default=0, help="wave pipelines (pool partitions on separate streams); 0 = auto")
+    ap.add_argument("--complete-workload", default="sphere_peel_tau1e4", choices=sorted(WORKLOADS),
+                    help="workload of the `complete_run` record: every photon to its escape through lart_gpu_run")
+    ap.add_argument("--complete-photons", type=float, default=1e6,
+                    help="photons of the complete run, TOTAL over all GPUs (strong scaling under --gpus N); 0 = skip")
     return ap.parse_args()
 
 
@@ -128,15 +132,32 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_model(args, nphotons):
+def build_model(args, nphotons, workload=None):
     from lart_b200 import Model
-    return Model(no_photons=nphotons, iseed=args.seed, **WORKLOADS[args.workload]).setup()
+    return Model(no_photons=nphotons, iseed=args.seed, **WORKLOADS[workload or args.workload]).setup()
+
+
+def workload_config(args, model):
+    """`config` of the JSON line: names the workload and nothing else, so that both arms print the same object."""
+    cfg = model.config.contents
+    g = cfg.grid
+    ncell = g.nx * g.ny * g.nz
+    return {"workload": args.workload, "grid": [g.nx, g.ny, g.nz], "tau0": WORKLOADS[args.workload].get("taumax"),
+            "peel_cube": [g.nxfreq, cfg.observers[0].nxim, cfg.observers[0].nyim] if cfg.par.nobs else None,
+            "quantum": args.quantum, "seed": args.seed,
+            "step": "every photon in flight advances by `quantum` scatterings (bounded sample of the workload: a photon needs "
+                    "~1e7 scatterings to leave the tau0 = 1e7 medium); value = scatterings/s",
+            "l2": "working set (grid %.0f MB as the host's SoA arrays, %.0f MB packed on the device, + photon pool + ray queue + cubes) "
+                  "larger than the 126 MB L2; no flush" % (48.0 * ncell / 1e6, 64.0 * ncell / 1e6),
+            "parallelism": "photon ids strided over the ranks / host threads (run_simulation_mod.f90:150); grid replicated; "
+                           "tallies summed once at the end"}
 
 
 def cpu_sample(args, events_per_photon, seconds, threads=None):
     """Time the CPU restatement (oracle, MT19937-64 like the reference) on a bounded sample of the
     same workload: the first `events_per_photon` scatterings of n photons, n sized for ~`seconds`."""
     from oracle import oracle
+    flags = oracle.use_native()
     threads = threads or oracle.hardware_threads()
     m = build_model(args, 10 ** 6)
     n = 4000 * threads  # calibration pass, long enough to amortise thread start-up
@@ -153,9 +174,29 @@ def cpu_sample(args, events_per_photon, seconds, threads=None):
     c = m.counters
     return {"value": c["n_scatter"] / dt, "unit": "scatterings/s", "cores": threads, "kind": "port",
             "sample": "%s: first %d scatterings of %d photons on %d threads, %.1f s (C++ restatement of the reference loop, "
-                      "g++ -O3 -ffp-contract=off, MT19937-64; the Fortran+MPI build is impossible in this image)"
-                      % (args.workload, events_per_photon, n, threads, dt),
-            "cellsteps_per_s": c["n_cellsteps"] / dt, "seconds": dt, "photons": n}
+                      "%s built on this host, MT19937-64; the Fortran+MPI build is impossible in this image)"
+                      % (args.workload, events_per_photon, n, threads, dt, flags),
+            "compiler": flags, "cellsteps_per_s": c["n_cellsteps"] / dt, "seconds": dt, "photons": n, "_model": m}
+
+
+def cpu_complete(args, seconds, threads=None):
+    """The CPU port on a bounded sample of the complete-run workload: n photons from emission to escape."""
+    from oracle import oracle
+    flags = oracle.use_native()
+    threads = threads or oracle.hardware_threads()
+    m = build_model(args, 10 ** 6, args.complete_workload)
+    n = 8 * threads
+    t0 = time.perf_counter()
+    oracle.run(m, rng_mode=0, nthreads=threads, first_id=1, count=n, seed=args.seed)
+    dt = time.perf_counter() - t0
+    n = int(max(threads, min(10 ** 6, n * seconds / max(dt, 1e-3)))) // threads * threads
+    m.zero_tallies()
+    t0 = time.perf_counter()
+    oracle.run(m, rng_mode=0, nthreads=threads, first_id=1, count=n, seed=args.seed)
+    dt = time.perf_counter() - t0
+    c = m.counters
+    return {"photons": n, "wall_s": dt, "photons_per_s": n / dt, "scatterings_per_s": c["n_scatter"] / dt,
+            "mean_nscatt": c["n_scatter"] / n, "cores": threads, "kind": "port", "compiler": flags}
 
 
 def run_reference(args):
@@ -174,20 +215,25 @@ def run_reference(args):
         tot_t += last["seconds"]
     v = tot_s / tot_t
     cb = dict(last)
+    model = cb.pop("_model")
     cb["value"] = v
-    print(json.dumps({
+    out = {
         "impl": "reference", "metric": "scatterings_per_s", "value": v, "unit": "scatterings/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "quantum": args.quantum, "note": "CPU port of the reference loop; bounded sample per step"},
+        "config": workload_config(args, model),
         "cpu_baseline": cb, "e2e": {"value": v, "unit": "scatterings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0}
+    if args.complete_photons > 0:
+        out["complete_run"] = dict(cpu_complete(args, 20.0), workload=args.complete_workload)
+    print(json.dumps(out))
 
 
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from lart_b200 import Simulation, capi, measure_fp64
+    from lart_b200.host import comm_init_torch, comm_finalize, photon_partition
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +243,7 @@ def run_gpu(args):
         os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm_init_torch(local)  # the engine's own NCCL communicator (lart_gpu_reduce); torch only carries the 128-byte id
 
     def barrier():
         if world > 1:
@@ -205,7 +252,6 @@ def run_gpu(args):
 
     S_auto = args.pool_slots or 148 * 16384
     total_steps = args.warmup + args.steps
-    import lart_b200  # noqa: F401
     nph = S_auto * world * 4  # far more ids than slots: the queue never runs dry, nobody finishes tau0 = 1e7 anyway
     model = build_model(args, nph)
     cfg = model.config.contents
@@ -242,68 +288,87 @@ def run_gpu(args):
         return ms_, launches_, stage_, c_, S_, wall_, clk_
 
     dev_ms, launches, _, c, S, wall, clk = device_arm(args.flags, args.warmup, args.steps, args.streams)
-    t = torch.tensor([dev_ms, c["n_scatter"], c["n_cellsteps"], c["n_peel"], c["n_photons_done"], c["n_rng"], float(launches)],
-                     dtype=torch.float64, device="cuda")
+    keys = ["n_scatter", "n_cellsteps", "n_peel", "n_photons_done", "n_rng", "n_peel_bound", "n_cellsteps_bound"]
+    t = torch.tensor([dev_ms] + [c[k] for k in keys] + [float(launches)], dtype=torch.float64, device="cuda")
     tmax = t.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     max_ms = float(tmax[0])
-    n_scatter, n_cell, n_peel, n_done, n_rng, n_launch = (float(t[i]) for i in range(1, 7))
-    value = n_scatter / (max_ms * 1e-3)
+    tot = {k: float(t[1 + i]) for i, k in enumerate(keys)}
+    n_launch = float(t[-1])
+    value = tot["n_scatter"] / (max_ms * 1e-3)
     # a second, short pass with CUDA events around every stage kernel feeds the roofline: plain launches on ONE
     # stream, so that every kernel is timed alone (in the value arm the partitions' kernels overlap)
     dev_ms, _, stage, c, _, _, _ = device_arm(args.flags | capi.FLAG_STAGE_TIMING, max(args.warmup, 3), min(args.steps, 4), 1)
 
-    # ------------------------- FP64 issue peak + roofline of the dominant kernel (rank 0)
+    # ------------------------- roofline (rank 0's numbers), SURVEY.md section 8(d)
     hbm_peak, peak_src = measured_peaks()
     fp64_peak = measure_fp64(local)
-    dom = max(stage, key=lambda k: stage[k][0])
-    tot_stage = max(sum(v[0] for v in stage.values()), 1e-30)
-    walk_ms = stage["trace"][0] + stage["peel"][0]
-    walk_n = stage["trace"][1] + stage["peel"][1]
-    steps_local = c["n_cellsteps"]
-    flops = 50.0 * steps_local + 300.0 * c["n_scatter"]
     mono = bool(args.flags & 4)
-    # Dominant kernel = the scatter stage.  Its algorithmic HBM bytes per scattering: the photon
-    # record is read and written once (22 f64 + id + block counter + 4 i32 = 208 B each way) and one 144-B peel-ray
-    # descriptor is written per observer.
-    nobs = max(int(cfg.par.nobs), 0)
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")  # dram__bytes_read+write per launch from `ncu --set full`
-    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    # ... per QUEUED ray: on this workload the scatter stage drops the rays that provably end in their own cell; the
-    # fraction it still writes comes from the ncu capture (1.0 when there is none, and for other workloads' geometry)
-    qf = tj.get("queued_ray_fraction", 1.0) if args.workload == "sphere_peel_tau1e7" and not (args.flags & 4) else 1.0
-    bytes_per_scatter = 2 * 208 + 144 * nobs * qf
-    sc_ms, sc_n = stage["scatter"] if not mono else stage["trace"]
-    ach = bytes_per_scatter * c["n_scatter"] / (sc_ms * 1e-3) / 1e9 if sc_ms > 0 else 0.0
-    traffic = None
-    if tj and not mono and args.workload == "sphere_peel_tau1e7":
-        # profiled at tj["pool_slots"] scatterings per launch; scale to this run's launch
-        traffic = tj["k_wf_scatter_bytes_per_launch"] / tj["pool_slots"] * (c["n_scatter"] / max(sc_n, 1))
     clump = bool(cfg.par.use_clump_medium)
-    roof = {"bound": "hbm", "kernel": ("k_cl_scatter" if clump else "k_wf_scatter") if not mono else ("k_mono_clump" if clump else "k_mono"),
-            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-            "peak_source": peak_src, "bytes_per_scattering": bytes_per_scatter,
-            "scatterings_per_launch": c["n_scatter"] / max(sc_n, 1), "avg_launch_ms": sc_ms / max(sc_n, 1),
-            "note": "the path is FP64-issue/latency bound, not HBM bound: see `fp64` (issue-rate roofline) and `dda_walk`",
-            "stage_ms_per_wave": {k: stage[k][0] / max(stage[k][1], 1) for k in stage},
-            "stage_share": {k: stage[k][0] / tot_stage for k in stage},
-            "dominant_stage": dom,
-            # Cartesian: one 48-B share of a cell record per step; clump medium: a CSR cell = 8 B of offsets + ~1.5
-            # registrations of 36 B (index + centre/r^2) = 62 B
-            "dda_walk": {"kernels": "k_cl_flight+k_cl_peel" if clump else "k_wf_trace+k_wf_peel",
-                         "bytes_per_cellstep": 62 if clump else 48,
-                         "achieved_GBps": (62.0 if clump else 48.0) * steps_local / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0,
-                         "cellsteps_per_launch": steps_local / max(walk_n, 1), "avg_launch_ms": walk_ms / max(walk_n, 1)},
-            "fp64": {"achieved_tflops": flops / (dev_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
-                     "frac": flops / (dev_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
-                     "model": "50 flop/cell step + 300 flop/scattering (SURVEY.md 8d; libm calls and the RNG not counted)",
-                     "peak_source": "measured DFMA loop (lart_gpu_measure_fp64)"}}
+    names = {"emit": "k_cl_emit" if clump else "k_wf_emit", "trace": "k_cl_flight" if clump else "k_wf_trace",
+             "draw": "k_cl_scatter" if clump else "k_wf_draw", "apply": "k_wf_apply", "peel": "k_cl_peel" if clump else "k_wf_peel"}
+    if mono:
+        names["trace"] = "k_mono_clump" if clump else "k_mono"
+    tot_stage = max(sum(v[0] for v in stage.values()), 1e-30)
+    dom = max(stage, key=lambda k: stage[k][0])
+    walked = c["n_cellsteps"] - c["n_cellsteps_bound"]  # steps a walker kernel actually took
+    bcs = 62.0 if clump else (56.0 if cfg.par.DGR > 0 else 48.0)  # algorithmic bytes per cell step (8d)
+    walk_ms = stage["trace"][0] + stage["peel"][0]
+    walk_n = max(stage["trace"][1], 1)
+    nobs = max(int(cfg.par.nobs), 0)
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")  # dram__bytes_read+write per launch from `ncu --set full`
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    same_wl = bool(tj) and tj.get("workload") == args.workload and not mono
+    per_kernel = {}
+    for k in stage:
+        ms_k, n_k = stage[k]
+        ent = {"kernel": names[k], "ms_per_launch": ms_k / max(n_k, 1), "share_of_wave": ms_k / tot_stage}
+        if same_wl and names[k] in tj.get("dram_bytes_per_scattering", {}):
+            ent["dram_bytes_per_scattering_ncu"] = tj["dram_bytes_per_scattering"][names[k]]
+        per_kernel[k] = ent
+    wave_ms = tot_stage / walk_n  # one wave = one launch of each stage kernel (serial sum)
+    scat_per_wave = c["n_scatter"] / walk_n
+    alg_bytes_wave = bcs * walked / walk_n
+    ach = alg_bytes_wave / (wave_ms * 1e-3) / 1e9
+    traffic = None
+    if same_wl:
+        traffic = sum(tj["dram_bytes_per_scattering"].values()) * scat_per_wave
+    flops = 50.0 * walked + 300.0 * c["n_scatter"]
+    roof = {
+        # the contract's figure: algorithmic grid bytes of the cell walk (48 B per WALKED cell step) over the duration of one wave
+        # (one launch of each stage kernel, timed alone with CUDA events) against the measured HBM copy rate
+        "bound": "hbm", "kernel": "one wave: " + " + ".join(names[k] for k in stage if stage[k][0] > 0),
+        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+        "peak_source": peak_src, "bytes_per_cellstep": bcs, "walked_cellsteps_per_wave": walked / walk_n,
+        "scatterings_per_wave": scat_per_wave, "avg_launch_ms": wave_ms,
+        "traffic_over_algorithmic": (traffic / alg_bytes_wave) if traffic else None,
+        "note": "this path is bound by FP64/integer instruction issue and latency, not by HBM: at tau0 = 1e7 a scattering walks ~1 cell "
+                "(48 B) but costs ~300 flop + 6 libm calls + ~16 Philox blocks; `traffic` is dominated by the wavefront's photon records "
+                "(read+written once per stage), see `dram_traffic`",
+        "dominant_stage": dom, "per_kernel": per_kernel,
+        "hbm_algorithmic": {"bytes_per_cellstep": bcs, "walked_cellsteps_per_s": walked / (dev_ms * 1e-3),
+                            "GBps": bcs * walked / (dev_ms * 1e-3) / 1e9, "frac_of_hbm_peak": bcs * walked / (dev_ms * 1e-3) / 1e9 / hbm_peak},
+        "dda_walk": {"kernels": names["trace"] + "+" + names["peel"], "bytes_per_cellstep": bcs,
+                     "walked_cellsteps": walked, "bound_skipped_cellsteps": c["n_cellsteps_bound"],
+                     "achieved_GBps": bcs * walked / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else 0.0,
+                     "frac_of_hbm_peak": bcs * walked / (walk_ms * 1e-3) / 1e9 / hbm_peak if walk_ms > 0 else 0.0,
+                     "walked_cellsteps_per_launch": walked / walk_n, "avg_launch_ms": walk_ms / walk_n},
+        "fp64_model": {"achieved_tflops": flops / (dev_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+                       "frac": flops / (dev_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                       "model": "50 flop per walked cell step + 300 flop per scattering (SURVEY.md 8d; libm calls and the RNG not counted)",
+                       "peak_source": "measured DFMA loop (lart_gpu_measure_fp64)"},
+        "dram_traffic": ({"source": "profiles/r2_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                          "bytes_per_scattering": tj["dram_bytes_per_scattering"],
+                          "total_bytes_per_scattering": sum(tj["dram_bytes_per_scattering"].values()),
+                          "algorithmic_bytes_per_scattering": bcs * walked / max(c["n_scatter"], 1)} if same_wl else None),
+    }
 
     # ------------------------- end-to-end arm through the public API with HOST buffers: `e2e`
-    # timed: lart_gpu_create (H2D of the host grid arrays) + begin + steps (each followed by the D2H read of
-    # its result: photons in flight) + output_reduce (NCCL reduce of the tally buffer + D2H into the host tallies).
+    # timed: lart_gpu_create (H2D of the host grid arrays; a cold handle: the library's memory pool was trimmed when the
+    # last handle closed) + begin + steps (each followed by the D2H read of its result: photons in flight) +
+    # output_reduce (ONE ncclReduce of the tally buffer inside the C ABI + D2H into the host tallies).
     model.zero_tallies()
     barrier()
     t0 = time.perf_counter()
@@ -332,43 +397,79 @@ def run_gpu(args):
     ns = torch.tensor([model.counters["n_scatter"] if rank == 0 else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_scatter = float(ns[0])  # rank 0 holds the reduced counters of all ranks
-    if world > 1:
-        dist.broadcast(ns, src=0)
-        e2e_scatter = float(ns[0])
-    e2e_value = e2e_scatter / float(te[0])
+        dist.broadcast(ns, src=0)  # rank 0 holds the reduced counters of all ranks
+    e2e_value = float(ns[0]) / float(te[0])
+
+    # ------------------------- complete run: a fixed number of photons, every one to its escape, through lart_gpu_run
+    # (BASELINE's other unit, photons/s).  The TOTAL is fixed: under --gpus N it is split over the ranks = strong scaling.
+    complete = None
+    if args.complete_photons > 0 and not args.skip_e2e:
+        ntot = int(args.complete_photons)
+        cm = build_model(args, ntot, args.complete_workload)
+        barrier()
+        t0 = time.perf_counter()
+        sim = Simulation(cm, device=local, pool_slots=args.pool_slots, flags=args.flags & ~capi.FLAG_STAGE_TIMING, streams=args.streams)
+        sim.run_simulation(rank, world, ntot)
+        t_run = time.perf_counter() - t0
+        sim.output_reduce(dst=0)
+        barrier()
+        t_all = time.perf_counter() - t0
+        dms, _ = sim.kernel_ms()
+        sim.close()
+        tt = torch.tensor([t_all, t_run, dms * 1e-3], dtype=torch.float64, device="cuda")
+        tmin = tt.clone()
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            cc = cm.counters
+            cm.output_normalize()
+            sm_ = cm.summary
+            flux = None
+            if cm.config.contents.par.nobs:
+                omega = sm_.dxim * sm_.dyim * (np.pi / 180) ** 2
+                flux = float((cm.observer_cube("scatt").sum() + cm.observer_cube("direc").sum()) * 4 * np.pi * omega
+                             * sm_.distance ** 2 * sm_.dxfreq)
+            complete = {"workload": args.complete_workload, "photons": ntot, "n_gpus": world, "scaling": "strong",
+                        "wall_s": float(tt[0]), "photons_per_s": ntot / float(tt[0]), "scatterings_per_s": cc["n_scatter"] / float(tt[0]),
+                        "mean_nscatt": cc["n_scatter"] / ntot, "run_s_max_rank": float(tt[1]), "run_s_min_rank": float(tmin[1]),
+                        "device_s_max_rank": float(tt[2]), "flux_check": flux,
+                        "region": "lart_gpu_create (H2D grid) + lart_gpu_run to the last photon (ids rank+1 : N : nranks) + "
+                                  "lart_gpu_reduce (NCCL) + lart_gpu_fetch into host arrays; wall = max over ranks"}
 
     if rank == 0:
         out = {
             "metric": "scatterings_per_s", "value": value, "unit": "scatterings/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "grid": [g.nx, g.ny, g.nz], "tau0": WORKLOADS[args.workload].get("taumax"),
-                       "peel_cube": [g.nxfreq, cfg.observers[0].nxim, cfg.observers[0].nyim] if cfg.par.nobs else None,
-                       "photons_in_flight_per_gpu": S, "quantum": args.quantum,
-                       "step": "every photon slot advances by `quantum` scatterings (waves of emit/trace/scatter/peel kernels)",
-                       "driver": "monolithic" if mono else "wavefront",
-                       "l2": "working set (cells %.0f MB + photon pool + ray queue + cubes) larger than the 126 MB L2; no flush"
-                             % (64.0 * ncell / 1e6),
-                       "parallelism": "photon ids strided over %d GPU(s); grid replicated; one NCCL reduce of the tally buffer" % world,
-                       "seed": args.seed},
-            "cellsteps_per_s": n_cell / (max_ms * 1e-3), "peel_rays_per_s": n_peel / (max_ms * 1e-3),
-            "photons_done": n_done, "uniforms_per_s": n_rng / (max_ms * 1e-3), "wall_s": wall,
+            "config": workload_config(args, model),
+            "engine": {"photons_in_flight_per_gpu": S, "driver": "monolithic" if mono else "wavefront",
+                       "wave": "emit / trace / draw / apply / peel stage kernels over the photon pool; steps are CUDA-graph launches"},
+            "cellsteps_per_s": (tot["n_cellsteps"] - tot["n_cellsteps_bound"]) / (max_ms * 1e-3),
+            "cellsteps_bound_skipped_per_s": tot["n_cellsteps_bound"] / (max_ms * 1e-3),
+            "peel_rays_per_s": tot["n_peel"] / (max_ms * 1e-3), "peel_rays_bound_skipped_per_s": tot["n_peel_bound"] / (max_ms * 1e-3),
+            "photons_done": tot["n_photons_done"], "uniforms_per_s": tot["n_rng"] / (max_ms * 1e-3), "wall_s": wall,
             "gpu_launches": int(n_launch), "roofline": roof,
             "e2e": {"value": e2e_value, "unit": "scatterings/s", "h2d_bytes_per_step": grid_bytes / total_steps,
                     "d2h_bytes_per_step": (8 * buf_n + 8 * total_steps) / total_steps, "seconds": float(te[0]),
                     "phases_rank0": phases,
-                    "region": "lart_gpu_create(H2D host grid) + begin + %d steps (+D2H of each step's in-flight count) + "
-                              "NCCL reduce + D2H of the tally buffer into host arrays (lart_gpu_destroy not timed); handle memory comes from "
-                              "the CUDA stream-ordered pool, so this second handle of the process reuses cached device memory "
-                              "(a process's first lart_gpu_create measured 0.06-0.17 s)" % total_steps},
+                    "region": "lart_gpu_create (cold handle: device allocations + H2D of the host grid) + begin + %d steps (+D2H of each "
+                              "step's in-flight count) + lart_gpu_reduce (NCCL) + D2H of the tally buffer into host arrays "
+                              "(lart_gpu_destroy not timed)" % total_steps},
             "clocks": clk.summary(),
         }
+        if complete:
+            out["complete_run"] = complete
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_sample(args, args.quantum, args.cpu_seconds)
+            cb = cpu_sample(args, args.quantum, args.cpu_seconds)
+            cb.pop("_model")
+            out["cpu_baseline"] = cb
+            if complete:
+                out["complete_run"]["cpu"] = cpu_complete(args, 10.0)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
+        comm_finalize()
         dist.destroy_process_group()
 
 

@@ -199,7 +199,8 @@ enum {
 };
 
 /* stage kernels of one wave, in launch order (index into lart_gpu_stage_ms) */
-enum { LART_STAGE_EMIT = 0, LART_STAGE_TRACE = 1, LART_STAGE_SCATTER = 2, LART_STAGE_PEEL = 3, LART_STAGE_COUNT = 4 };
+enum { LART_STAGE_EMIT = 0, LART_STAGE_TRACE = 1, LART_STAGE_DRAW = 2 /* k_wf_draw; the whole scatter stage of the clump driver */,
+       LART_STAGE_APPLY = 3, LART_STAGE_PEEL = 4, LART_STAGE_COUNT = 5 };
 
 /* per-observer output cubes (src/define.f90:561-600); frequency fastest:
  * cube(ixf,ix,iy) at [(ixf-1) + nxfreq*((ix-1) + nxim*(iy-1))]. NULL = skip. */

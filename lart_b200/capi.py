@@ -29,7 +29,7 @@ FLAG_STAGE_TIMING = 8
 FLAG_SERIAL_REJECTION = 16
 FLAG_LOCAL_STEPS = 32
 FLAG_DEBUG_TINY_QUEUES = 64
-STAGES = ["emit", "trace", "scatter", "peel"]
+STAGES = ["emit", "trace", "draw", "apply", "peel"]
 
 
 class Grid(C.Structure):

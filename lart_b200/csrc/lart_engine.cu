@@ -1932,8 +1932,8 @@ struct lart_gpu_ctx {
   bool begun = false;
   double *pinned[2] = {nullptr, nullptr};  // pinned staging of lart_gpu_fetch
   std::vector<cudaEvent_t> tev;  // stage-timing events of one step (monolithic driver)
-  double stage_ms[LART_STAGE_COUNT] = {0, 0, 0, 0};
-  long long stage_n[LART_STAGE_COUNT] = {0, 0, 0, 0};
+  double stage_ms[LART_STAGE_COUNT] = {};
+  long long stage_n[LART_STAGE_COUNT] = {};
 };
 
 namespace {
@@ -2401,7 +2401,8 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
 namespace {
 int drain_peel_only(lart_gpu_handle h);
 // the scatter-stage instantiations of this run: k_wf_draw<use_stokes, dust, serial rejection>, k_wf_apply<use_stokes, dust, local steps>
-void launch_scatter(lart_gpu_handle h, lart_gpu_ctx::Group &g) {
+template <class Mark>
+int launch_scatter(lart_gpu_handle h, lart_gpu_ctx::Group &g, Mark between) {
   const int nb = (g.pool.n + kBlock - 1) / kBlock;
   const int gd = std::max(1, std::min(nb, h->nsm * LART_DRAW_MINBLOCKS)), ga = std::max(1, std::min(nb, h->nsm * LART_APPLY_MINBLOCKS));
   const int st = h->P.use_stokes ? 4 : 0, du = h->P.dust ? 2 : 0;
@@ -2414,10 +2415,12 @@ void launch_scatter(lart_gpu_handle h, lart_gpu_ctx::Group &g) {
     case 6: M(true, true, false); break;   default: M(true, true, true); break;                                    \
   }
   LART_8(LART_DR, st | du | (h->P.flags_serial_vz ? 1 : 0))
+  if (int rc = between()) return rc;
   LART_8(LART_AP, st | du | (h->P.local_steps ? 1 : 0))
 #undef LART_8
 #undef LART_AP
 #undef LART_DR
+  return 0;
 }
 // sticky device error word -> error return
 int check_device_error(unsigned int err) {
@@ -2470,8 +2473,11 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           if (h->P.clump) k_cl_flight<<<std::max(1, std::min(nb, h->nsm * 3)), kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           else k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
-          if (h->P.clump) k_cl_scatter<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
-          else launch_scatter(h, g);
+          auto between = [&]() -> int { return with_marks ? mark(g.tev, ne[gi], g.stream) : 0; };
+          if (h->P.clump) {
+            k_cl_scatter<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
+            if (int rc = between()) return rc;
+          } else if (int rc = launch_scatter(h, g, between)) return rc;
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.nobs == 0) {}  // no observers: nothing to peel (xyz_symmetry, plain slabs)
           else if (h->P.clump) k_cl_peel<<<std::max(1, std::min(nb, h->nsm * 4)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
@@ -2532,7 +2538,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
         for (int w = 0; w < qn; ++w)
           for (int k = 0; k < LART_STAGE_COUNT; ++k) {
             float t = 0.f;
-            CUDA_OK(cudaEventElapsedTime(&t, g.tev[5 * w + k], g.tev[5 * w + k + 1]));
+            CUDA_OK(cudaEventElapsedTime(&t, g.tev[(LART_STAGE_COUNT + 1) * w + k], g.tev[(LART_STAGE_COUNT + 1) * w + k + 1]));
             h->stage_ms[k] += t;
             h->stage_n[k] += 1;
           }

@@ -230,10 +230,10 @@ class Simulation:
 
     def stage_ms(self):
         """{stage: (summed ms, launches)} — needs flags & FLAG_STAGE_TIMING."""
-        ms = (C.c_double * 4)()
-        n = (C.c_int64 * 4)()
+        ms = (C.c_double * len(capi.STAGES))()
+        n = (C.c_int64 * len(capi.STAGES))()
         self._check(self._lib.lart_gpu_stage_ms(self._h, ms, n))
-        return {capi.STAGES[k]: (ms[k], n[k]) for k in range(4)}
+        return {capi.STAGES[k]: (ms[k], n[k]) for k in range(len(capi.STAGES))}
 
     @property
     def pool_slots(self):

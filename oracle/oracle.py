@@ -15,10 +15,41 @@ from lart_b200 import capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_NATIVE = False
+PORTABLE_FLAGS = "g++ -O3 -march=x86-64-v3 -ffp-contract=off"
+NATIVE_FLAGS = "g++ -O3 -march=native"
 
 
 def lib_path():
+    if _NATIVE:
+        return os.path.join(_HERE, "_native", _cpu_tag(), "liblart_oracle_native.so")
     return os.path.join(_HERE, "liblart_oracle.so")
+
+
+def _cpu_tag():
+    """A -march=native build is only valid on the CPU it was made on: key it by the CPU's model and flag list."""
+    import hashlib
+    try:
+        lines = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        lines = []
+    return hashlib.sha1("".join(lines).encode()).hexdigest()[:12]
+
+
+def use_native():
+    """Timing legs only (bench.py): switch to a build made ON this machine with -march=native and FMA contraction
+    allowed.  Returns the compiler flags in use; falls back to the portable build (the
+    parity build: -march=x86-64-v3 -ffp-contract=off) when the compile fails.  Call before the first load()."""
+    global _NATIVE, _LIB
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native", "NATIVEDIR=_native/" + _cpu_tag()],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _NATIVE, _LIB = True, None
+        load()
+        return NATIVE_FLAGS
+    except Exception:
+        _NATIVE, _LIB = False, None
+        return PORTABLE_FLAGS
 
 
 def build(force=False):

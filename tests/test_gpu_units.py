@@ -292,13 +292,14 @@ def test_peel_bound_implies_capped_walk(name):
     ic = rng.integers(1, nn + 1, (n, 3)).astype(np.int32)
     u = rng.uniform(0, 1, (n, 3))
     q = n // 8
-    u[:q, rng.integers(0, 3)] = 0.0                  # exactly on a lower face: L = 0
+    zonly = g.nx == 1 and g.ny == 1
+    u[:q, 2 if zonly else rng.integers(0, 3)] = 0.0  # exactly on a lower face: L = 0 (a z-only slab has z faces only)
     u[q:2 * q] = rng.choice([1e-12, 1e-9, 1e-6, 1e-3], (q, 3))  # a hair inside
     u[2 * q:3 * q, 2] = 1.0                          # on the upper z face of the cell
     faces = [m.grid_array(a) for a in ("xface", "yface", "zface")]
     p = np.stack([faces[a][ic[:, a] - 1] + u[:, a] * (faces[a][ic[:, a]] - faces[a][ic[:, a] - 1]) for a in range(3)], axis=1)
     p[2 * q:3 * q, 2] = faces[2][ic[2 * q:3 * q, 2]]
-    if g.nx == 1 and g.ny == 1:
+    if zonly:
         p[:, 0] = 0.0; p[:, 1] = 0.0
     k = rng.normal(size=(n, 3))
     k /= np.linalg.norm(k, axis=1)[:, None]

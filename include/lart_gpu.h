@@ -188,11 +188,15 @@ enum {
   LART_FLAG_MONOLITHIC = 4,  /* one thread per photon slot, no stage compaction
                                 (the "before" arm of the warp-efficiency evidence) */
   LART_FLAG_STAGE_TIMING = 8, /* CUDA-event timing of every stage kernel (bench/roofline) */
-  LART_FLAG_SERIAL_REJECTION = 16, /* per-lane rejection loops instead of the warp-cooperative
-                                      atom-velocity sampler (ablation; same results) */
+  LART_FLAG_SERIAL_REJECTION = 16, /* per-lane rejection loops in the scatter stage: every warp waits for its
+                                      slowest lane (ablation; same results) */
   LART_FLAG_LOCAL_STEPS = 32,      /* the scatter stage takes the first cell step of the peel ray and
                                       of the next flight itself; only longer rays reach the queues
                                       (experimental; same results) */
+  LART_FLAG_SPECULATIVE_REJECTION = 128, /* round-2 first version of the scatter stage's samplers: the photons of a
+                                      warp that still wait for an accepted trial share its 32 lanes, 32/np
+                                      speculative trials each (ablation; same results).  Default: rejection loops
+                                      compacted with per-lane refill over a chunk of slots per warp (k_wf_draw2) */
   LART_FLAG_DEBUG_TINY_QUEUES = 64 /* tests only: one direct-peel entry per pool partition, so that the
                                       queue-overflow error path (sticky device error word -> error
                                       return of lart_gpu_step / _sync / _fetch) can be exercised */

@@ -29,6 +29,7 @@ FLAG_STAGE_TIMING = 8
 FLAG_SERIAL_REJECTION = 16
 FLAG_LOCAL_STEPS = 32
 FLAG_DEBUG_TINY_QUEUES = 64
+FLAG_SPECULATIVE_REJECTION = 128
 STAGES = ["emit", "trace", "draw", "apply", "peel"]
 
 

@@ -83,6 +83,8 @@ struct Pool {
   int *rc;                     // [3][S]  ... and its current cell
   int *nev;                    // [S] scatterings of the slot's photon so far (bounded runs, lart_config::max_events)
   double *var;                 // [6][S] variates of the slot's pending scattering: uz, cos(theta), cos(phi), sin(phi), ux, uy
+  double *wtab;                // [12][S] scratch of k_wf_draw2: wing majorant tables (10), core-skip threshold, polar-pair r^2
+  int *lst;                    // [S] scratch of k_wf_draw2: per warp chunk, core photons from the front, wing photons from the back
   int S;                       // slots (= SoA stride)
   int s0, n;                   // the partition [s0, s0+n) this kernel launch works on
 };
@@ -890,6 +892,326 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW_MINBLOCKS) k_wf_draw(const _
     store_rng(pl, s, rng, fl);
     if (fl != fl0) pl.flags[s] = fl;
     nrng += rng.nrng;
+  }
+  flush_counters(P, cnt, nrng);
+}
+
+// ---- k_wf_draw2 (default): the same variates with the rejection loops COMPACTED instead of shared -----------------------
+// ncu on k_wf_draw (profiles/r2_ncu_draw_split.txt): 3670 warp instructions per scattering, of which the wing sampler takes 910
+// although only one photon in six is in the wings (its set-up runs with 5 of 32 lanes, its trial rounds evaluate six speculative
+// trials per pending photon), and 9 Philox blocks are computed where the serial algorithm consumes 5.9.  Speculative trials buy
+// latency with instructions, and this stage is issue bound (56 % of the issue slots, top stall: instruction fetch).
+// Here every warp owns a contiguous CHUNK of pool slots and takes it through the event pass by pass; a pass is either straight-line
+// code over the chunk (32 photons at a time) or a rejection loop with per-lane refill: a lane whose trial was accepted stores its
+// result and takes the next photon of the pass's list, so every issued trial is a needed one and (almost) every lane runs one.
+//   pass 0   classify: dust coin (DUST), core-skip threshold, lists of line-core (|x| <= 1) and wing photons of the chunk
+//   pass A   core photons: Lorentzian proposal + exp(-u^2) acceptance                      (refill loop)
+//   pass B   wing photons: majorant table (straight) / trials (refill loop) / u = x + a tan(..) (straight)
+//   pass C   cos(theta) (rand_resonance); Stokes: S12/S11 and the azimuth envelope; no Stokes: the azimuth
+//   pass D   Stokes: azimuth rejection                                                     (refill loop)
+//   pass E   Stokes, no core skip: Marsaglia polar pair                                    (refill loop)
+//   pass F   perpendicular atom velocity from the pair (or the core-skip / no-Stokes form)
+// Each photon's trials are evaluated one after the other in the order of its own Philox stream, so the variates are those of the
+// serial loops bit for bit (and the oracle's).  Intermediate values travel through the pool's scratch columns (var, wtab, lst):
+// a chunk's few hundred slots stay in L1/L2.
+#ifndef LART_DRAW2_MINBLOCKS
+#define LART_DRAW2_MINBLOCKS 3
+#endif
+constexpr int kDrawChunkMax = 512;
+
+// Rejection loop over `count` work items owned by this warp.  load(i) sets the lane up for item i (false: nothing to do for it);
+// trial() runs one trial of the lane's item and returns true when the item is finished (result stored).
+template <class Load, class Trial>
+__device__ __forceinline__ void warp_refill_loop(int count, Load &&load, Trial &&trial) {
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  int cursor = 0;  // warp-uniform
+  bool have = false;
+  for (;;) {
+    const unsigned nm = __ballot_sync(FULL, !have);
+    if (cursor < count && (__popc(nm) >= kRefillMin || nm == FULL)) {
+      const int idx = cursor + __popc(nm & lt);
+      if (!have && idx < count) have = load(idx);
+      cursor += __popc(nm);
+    }
+    if (!__any_sync(FULL, have)) {
+      if (cursor >= count) break;
+      continue;
+    }
+    if (have && trial()) have = false;
+  }
+}
+
+template <bool STOKES, bool DUST>
+__global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const __grid_constant__ DevParams P, Pool pl, int chunk) {
+  __shared__ double vtab[DUST ? kVoigtTabN : 1];
+  if (DUST) load_vtab(P, vtab);
+  const unsigned FULL = 0xffffffffu;
+  Counters cnt;
+  ctr_t nrng = 0;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const size_t S = pl.S;
+  const long long w = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  const int end = pl.s0 + pl.n;
+  const int c0 = (int)min((long long)end, pl.s0 + w * chunk), c1 = min(end, c0 + chunk);
+  double *const var0 = pl.var, *const var1 = pl.var + S, *const var2 = pl.var + 2 * S, *const var3 = pl.var + 3 * S,
+               *const var4 = pl.var + 4 * S, *const var5 = pl.var + 5 * S;
+  double *const w_xc = pl.wtab + 10 * S, *const w_rsq = pl.wtab + 11 * S;
+  const double *const f = pl.f;
+  const unsigned long long seed = P.seed;
+  int nA = 0, nB = 0;  // warp-uniform
+  // ---------------- pass 0: classify
+  for (int base = c0; base < c1; base += 32) {
+    const int s = base + lane;
+    const int fl0 = s < c1 ? pl.flags[s] : 0;
+    const bool active = (fl0 & PH_SCATTER) != 0;
+    if (!__any_sync(FULL, active)) continue;
+    double x = 0.0;
+    bool to_dust = false;
+    if (active) {
+      x = f[F_XFREQ * S + s];
+      const int ic = pl.ic[s], jc = pl.jc[s], kc = pl.kc[s];
+      double a, rhokap;
+      if (DUST || P.soa) {
+        CellData cs;
+        load_cell(P, ic, jc, kc, cs);
+        a = cs.voigt_a; rhokap = cs.rhokap;
+        if (DUST) {  // scattering_car.f90:106-118
+          const double pd = cs.rhokapD / (cs.rhokap * voigt_seon2(vtab, x, cs.voigt_a) + cs.rhokapD);
+          double u, dummy;
+          const unsigned long long nb = pl.ndraw[s];
+          philox_uniform2(seed, (unsigned long long)pl.id[s], nb, u, dummy);
+          pl.ndraw[s] = nb + 1;
+          nrng += 1;
+          to_dust = u <= pd;
+          if (to_dust) pl.flags[s] = fl0 | PH_DUSTEV;  // k_wf_apply runs scatter_dust from here on the same stream
+        }
+      } else {
+        const double2 cc = __ldg(reinterpret_cast<const double2 *>(P.cells + cell_slot(P, ic, jc, kc)));
+        rhokap = cc.x; a = cc.y;
+      }
+      if (!to_dust) {
+        var1[s] = a;
+        if (P.core_skip) {
+          double xc, xc2;
+          car_xcrit_local(P, ic, jc, kc, f[F_X * S + s], f[F_Y * S + s], f[F_Z * S + s], a, rhokap, xc, xc2);
+          w_xc[s] = xc;
+        }
+      }
+    }
+    const bool res = active && !to_dust, core = res && fabs(x) <= 1.0, wing = res && !core;
+    const unsigned mA = __ballot_sync(FULL, core), mB = __ballot_sync(FULL, wing);
+    if (core) pl.lst[c0 + nA + __popc(mA & lt)] = s;
+    if (wing) pl.lst[c1 - 1 - (nB + __popc(mB & lt))] = s;
+    nA += __popc(mA); nB += __popc(mB);
+  }
+  __syncwarp();
+  // ---------------- pass A: |x| <= 1 (random_mt.f90:2579-2585)
+  {
+    int slot = 0, ntr = 0;
+    double x = 0.0, x0 = 0.0, a = 1.0;
+    unsigned long long id = 0, nb = 0;
+    warp_refill_loop(nA,
+      [&](int i) { slot = pl.lst[c0 + i]; x = f[F_XFREQ * S + slot]; x0 = fabs(x); a = var1[slot]; id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot]; return true; },
+      [&]() {
+        double u1, u2;
+        philox_uniform2(seed, id, nb, u1, u2);
+        ++nb; ++ntr;
+        const double v = x0 + a * tan(kPi * (u1 - 0.5));
+        if (!(u2 <= exp(-v * v))) return false;
+        var0[slot] = (x < 0.0) ? -v : v;
+        pl.ndraw[slot] = nb;
+        return true;
+      });
+    cnt.reject += ntr; nrng += 2 * ntr;
+  }
+  // ---------------- pass B: wings, piecewise-constant majorant in beta (:2605-2690)
+  if (nB > 0) {
+    for (int i0 = 0; i0 < nB; i0 += 32) {  // B0: the majorant table of every wing photon (the expressions of rand_resonance_vz)
+      const int i = i0 + lane;
+      if (i >= nB) continue;
+      const int pos = c1 - 1 - i, slot = pl.lst[pos];
+      const double x0 = fabs(f[F_XFREQ * S + slot]), a = var1[slot];
+      const double xc = 1.0 + 1.4142135623730951, two_over_PI = 2.0 / kPi;
+      double T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      int mode;
+      const double x0sq = x0 * x0;
+      const double beta0 = exp(-x0sq / 2.0);
+      const double h0_two = beta0 / a, h0 = h0_two / 2.0;
+      const double h2 = 0.3861 / (x0sq - 1.373);
+      T[0] = beta0;
+      if (x0 < xc || !(h0 < h2)) {
+        const double dbeta = sqrt(two_over_PI * a * (1.0 - beta0) * beta0 * x0);
+        const double beta1 = beta0 + dbeta, one_b1 = 1.0 - beta1;
+        const double pb1 = sqrt(-2.0 * log(beta1));
+        const double h1 = two_over_PI * beta1 * pb1 / (x0sq - pb1 * pb1);
+        const double hm = (x0 < xc) ? h1 : ((h1 > h2) ? h1 : h2);
+        const double S0 = beta0 * h0, S1 = dbeta * h0, S2 = one_b1 * hm, Stot = S0 + S1 + S2;
+        mode = 2; T[1] = S0 / Stot; T[2] = 1.0 - S2 / Stot;
+        T[3] = beta0; T[4] = dbeta; T[5] = h0; T[6] = beta1; T[7] = one_b1; T[8] = hm;
+      } else if (h0_two < h2) {
+        mode = 0; T[3] = 0.0; T[4] = 1.0; T[5] = h2;
+      } else {
+        const double S0 = beta0 * h0, one_b0 = 1.0 - beta0, S1 = one_b0 * h2, Stot = S0 + S1;
+        mode = 1; T[1] = S0 / Stot; T[3] = beta0; T[4] = one_b0; T[5] = h2;
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) pl.wtab[(size_t)q * S + pos] = T[q];
+      pl.wtab[(size_t)9 * S + pos] = (double)mode;
+    }
+    __syncwarp();
+    {  // B1: trials
+      int slot = 0, ntr = 0, mode = 0, nu = 0;
+      double x0 = 0.0, a = 1.0, T[9];
+      unsigned long long id = 0, nb = 0;
+      warp_refill_loop(nB,
+        [&](int i) {
+          const int pos = c1 - 1 - i;
+          slot = pl.lst[pos]; x0 = fabs(f[F_XFREQ * S + slot]); a = var1[slot]; id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) T[q] = pl.wtab[(size_t)q * S + pos];
+          mode = (int)pl.wtab[(size_t)9 * S + pos];
+          return true;
+        },
+        [&]() {
+          double ua, ub, uacc, beta, Cb;
+          philox_uniform2(seed, id, nb, ua, ub);
+          ++nb; ++ntr;
+          if (mode == 0) { beta = T[3] + T[4] * ua; Cb = T[5]; uacc = ub; nu += 2; }
+          else {
+            if (ua < T[1]) { beta = T[0] * sqrt(ub); Cb = beta / a; }
+            else if (mode == 1 || ua < T[2]) { beta = T[3] + T[4] * ub; Cb = T[5]; }
+            else { beta = T[6] + T[7] * ub; Cb = T[8]; }
+            double dummy;
+            philox_uniform2(seed, id, nb, uacc, dummy);
+            ++nb; nu += 3;
+          }
+          const double pb = sqrt(-2.0 * log(beta));
+          const double t2 = atan((pb - x0) / a), t1 = atan((-pb - x0) / a), delt = t2 - t1;
+          if (!(uacc * Cb < (beta / (a * kPi)) * delt)) return false;
+          var0[slot] = t1; var2[slot] = delt;
+          pl.ndraw[slot] = nb;
+          return true;
+        });
+      cnt.reject += ntr; nrng += nu;
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < nB; i0 += 32) {  // B2: u = x + a tan(delt xi + t1)  (:2693)
+      const int i = i0 + lane;
+      if (i >= nB) continue;
+      const int slot = pl.lst[c1 - 1 - i];
+      const double x = f[F_XFREQ * S + slot], a = var1[slot];
+      const unsigned long long nb = pl.ndraw[slot];
+      double u, dummy;
+      philox_uniform2(seed, (unsigned long long)pl.id[slot], nb, u, dummy);
+      const double vz = fabs(x) + a * tan(var2[slot] * u + var0[slot]);
+      var0[slot] = (x < 0.0) ? -vz : vz;
+      pl.ndraw[slot] = nb + 1;
+      nrng += 1;
+    }
+  }
+  __syncwarp();
+  // ---------------- pass C: cos(theta) (rand_resonance, random_mt.f90:2974-2993)
+  for (int base = c0; base < c1; base += 32) {
+    const int s = base + lane;
+    const int fl = s < c1 ? pl.flags[s] : 0;
+    if (!((fl & PH_SCATTER) && !(fl & PH_DUSTEV))) continue;
+    Rng r;
+    r.start(seed, (unsigned long long)pl.id[s], pl.ndraw[s]);
+    const double cost = rand_resonance_fast(r, P);
+    var1[s] = cost;
+    if (STOKES) {
+      const double cost2 = cost * cost, S22 = 0.75 * P.E1 * (cost2 + 1.0);
+      const double S12overS11 = 0.75 * P.E1 * (cost2 - 1.0) / (S22 + P.E2);
+      const double Q = f[F_Q * S + s], U = f[F_U * S + s];
+      var2[s] = S12overS11;
+      var3[s] = 1.0 + fabs(S12overS11) * sqrt(Q * Q + U * U);
+    } else {
+      double sinp, cosp;
+      sincospi(2.0 * r.uniform(), &sinp, &cosp);
+      var2[s] = cosp; var3[s] = sinp;
+    }
+    pl.ndraw[s] = r.nblk;
+    nrng += r.nrng;
+  }
+  __syncwarp();
+  const int nR = nA + nB;
+  auto res_slot = [&](int i) { return pl.lst[i < nA ? c0 + i : c1 - 1 - (i - nA)]; };
+  if (STOKES) {
+    // ---------------- pass D: azimuth by rejection (scattering_car.f90:364-371)
+    {
+      int slot = 0, ntr = 0;
+      double Q = 0.0, U = 0.0, s12 = 0.0, env = 1.0;
+      unsigned long long id = 0, nb = 0;
+      warp_refill_loop(nR,
+        [&](int i) { slot = res_slot(i); Q = f[F_Q * S + slot]; U = f[F_U * S + slot]; s12 = var2[slot]; env = var3[slot]; id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot]; return true; },
+        [&]() {
+          double u1, u2, sinp, cosp;
+          philox_uniform2(seed, id, nb, u1, u2);
+          ++nb; ++ntr;
+          sincospi(2.0 * u1, &sinp, &cosp);
+          const double c2 = 2.0 * cosp * cosp - 1.0, s2 = 2.0 * sinp * cosp;
+          if (!(env * u2 <= 1.0 + s12 * (Q * c2 + U * s2))) return false;
+          var2[slot] = cosp; var3[slot] = sinp;
+          pl.ndraw[slot] = nb;
+          return true;
+        });
+      cnt.reject += ntr; nrng += 2 * ntr;
+    }
+    __syncwarp();
+    // ---------------- pass E: one Marsaglia polar pair per photon that is not core-skipped (:413-414; random_mt.f90:964-988)
+    {
+      int slot = 0, ntr = 0;
+      unsigned long long id = 0, nb = 0;
+      warp_refill_loop(nR,
+        [&](int i) {
+          slot = res_slot(i);
+          if (P.core_skip && fabs(f[F_XFREQ * S + slot]) < w_xc[slot]) return false;
+          id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot];
+          return true;
+        },
+        [&]() {
+          double v1, v2;
+          philox_uniform2(seed, id, nb, v1, v2);
+          ++nb; ++ntr;
+          v1 = 2.0 * v1 - 1.0; v2 = 2.0 * v2 - 1.0;
+          const double rsq = v1 * v1 + v2 * v2;
+          if (!(rsq > 0.0 && rsq < 1.0)) return false;
+          var4[slot] = v1; var5[slot] = v2; w_rsq[slot] = rsq;
+          pl.ndraw[slot] = nb;
+          return true;
+        });
+      cnt.reject += ntr; nrng += 2 * ntr;
+    }
+    __syncwarp();
+  }
+  // ---------------- pass F: perpendicular atom velocity
+  for (int base = c0; base < c1; base += 32) {
+    const int s = base + lane;
+    const int fl = s < c1 ? pl.flags[s] : 0;
+    if (!((fl & PH_SCATTER) && !(fl & PH_DUSTEV))) continue;
+    double xc = 0.0;
+    const bool skip = P.core_skip && fabs(f[F_XFREQ * S + s]) < (xc = w_xc[s]);
+    double ux, uy;
+    if (STOKES && !skip) {  // two rand_gauss calls = the stored spare (if any) and the pair of pass E
+      const double one_over_sqrt2 = 1.0 / 1.4142135623730951;
+      const double rsq = w_rsq[s];
+      const double g = sqrt(-2.0 * log(rsq) / rsq), g_spare = var4[s] * g, g_first = var5[s] * g;
+      if (fl & PH_GAUSS) { ux = pl.f[(size_t)F_GSET * S + s] * one_over_sqrt2; uy = g_first * one_over_sqrt2; pl.f[(size_t)F_GSET * S + s] = g_spare; }
+      else { ux = g_first * one_over_sqrt2; uy = g_spare * one_over_sqrt2; }
+    } else {  // :397-401 / :749-752
+      const double xc2 = P.core_skip_global ? P.xcrit2 : xc * xc;
+      double u1, u2, s2, c2;
+      const unsigned long long nb = pl.ndraw[s];
+      philox_uniform2(seed, (unsigned long long)pl.id[s], nb, u1, u2);
+      pl.ndraw[s] = nb + 1;
+      nrng += 2;
+      const double uxy = skip ? sqrt(xc2 - log(u2)) : sqrt(-log(u2));
+      sincospi(2.0 * u1, &s2, &c2);
+      ux = uxy * c2; uy = uxy * s2;
+    }
+    var4[s] = ux; var5[s] = uy;
   }
   flush_counters(P, cnt, nrng);
 }
@@ -1932,6 +2254,8 @@ struct lart_gpu_ctx {
   bool begun = false;
   double *pinned[2] = {nullptr, nullptr};  // pinned staging of lart_gpu_fetch
   std::vector<cudaEvent_t> tev;  // stage-timing events of one step (monolithic driver)
+  int draw_mode = 0;    // 0: k_wf_draw2 (compacted rejection loops), 1: serial per-lane loops, 2: warp-cooperative speculative trials
+  int draw_chunk = 1024; // slots per warp of k_wf_draw2 (upper bound; LART_GPU_DRAW_CHUNK)
   double stage_ms[LART_STAGE_COUNT] = {};
   long long stage_n[LART_STAGE_COUNT] = {};
 };
@@ -2151,6 +2475,8 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   P.soa = (cfg->flags & LART_FLAG_SOA_GRID) ? 1 : 0;
   P.warp_agg = (cfg->flags & LART_FLAG_NO_WARP_AGG) ? 0 : 1;
   P.flags_serial_vz = (cfg->flags & LART_FLAG_SERIAL_REJECTION) ? 1 : 0;
+  h->draw_mode = (cfg->flags & LART_FLAG_SERIAL_REJECTION) ? 1 : ((cfg->flags & LART_FLAG_SPECULATIVE_REJECTION) ? 2 : 0);
+  if (const char *e = getenv("LART_GPU_DRAW_CHUNK")) h->draw_chunk = std::max(32, atoi(e) / 32 * 32);
   // which ray tracers the reference would bind (setup.f90:952-976)
   const bool zonly_grid = p.xy_periodic && g.nx == 1 && g.ny == 1;
   P.sym = p.xyz_symmetry ? 1 : 0; P.i0 = g.i0; P.j0 = g.j0; P.k0 = g.k0;
@@ -2302,6 +2628,8 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   rc = rc ? rc : dalloc(h, &h->pool.rc, (size_t)3 * S);
   rc = rc ? rc : dalloc(h, &h->pool.nev, S);
   if (!mono) rc = rc ? rc : dalloc(h, &h->pool.var, (size_t)6 * S);
+  if (!mono) rc = rc ? rc : dalloc(h, &h->pool.wtab, (size_t)12 * S);
+  if (!mono) rc = rc ? rc : dalloc(h, &h->pool.lst, S);
   rc = rc ? rc : dalloc(h, &h->job, 1);
   if (!rc) P.err = &h->job->err;
   P.max_events = cfg->max_events > 0 ? cfg->max_events : 0;
@@ -2414,7 +2742,23 @@ int launch_scatter(lart_gpu_handle h, lart_gpu_ctx::Group &g, Mark between) {
     case 3: M(false, true, true); break;   case 4: M(true, false, false); break; case 5: M(true, false, true); break;  \
     case 6: M(true, true, false); break;   default: M(true, true, true); break;                                    \
   }
-  LART_8(LART_DR, st | du | (h->P.flags_serial_vz ? 1 : 0))
+  if (h->draw_mode == 0) {
+    // One chunk of slots per warp: as long as the partitions together offer fewer warps than the device holds, chunks stay
+    // small (latency); beyond that they grow to kDrawChunkMax, so that the refill loops have many photons per lane.
+    const long long G = (long long)h->groups.size(), warps_dev = (long long)h->nsm * LART_DRAW2_MINBLOCKS * (kBlock / 32);
+    long long chunk = ((long long)g.pool.n * G / warps_dev + 31) / 32 * 32;
+    chunk = std::max<long long>(32, std::min<long long>(chunk, h->draw_chunk));
+    const long long warps = (g.pool.n + chunk - 1) / chunk;
+    const int gd2 = (int)std::max<long long>(1, (warps + kBlock / 32 - 1) / (kBlock / 32));
+    switch (st | du) {
+      case 0: k_wf_draw2<false, false><<<gd2, kBlock, 0, g.stream>>>(h->P, g.pool, (int)chunk); break;
+      case 2: k_wf_draw2<false, true><<<gd2, kBlock, 0, g.stream>>>(h->P, g.pool, (int)chunk); break;
+      case 4: k_wf_draw2<true, false><<<gd2, kBlock, 0, g.stream>>>(h->P, g.pool, (int)chunk); break;
+      default: k_wf_draw2<true, true><<<gd2, kBlock, 0, g.stream>>>(h->P, g.pool, (int)chunk); break;
+    }
+  } else {
+    LART_8(LART_DR, st | du | (h->draw_mode == 1 ? 1 : 0))
+  }
   if (int rc = between()) return rc;
   LART_8(LART_AP, st | du | (h->P.local_steps ? 1 : 0))
 #undef LART_8

@@ -915,16 +915,18 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW_MINBLOCKS) k_wf_draw(const _
 // serial loops bit for bit (and the oracle's).  Intermediate values travel through the pool's scratch columns (var, wtab, lst):
 // a chunk's few hundred slots stay in L1/L2.
 #ifndef LART_DRAW2_MINBLOCKS
-#define LART_DRAW2_MINBLOCKS 3
+#define LART_DRAW2_MINBLOCKS 4
 #endif
-constexpr int kDrawChunkMax = 512;
 
 // Rejection loop over `count` work items owned by this warp.  load(i) sets the lane up for item i (false: nothing to do for it);
 // trial() runs one trial of the lane's item and returns true when the item is finished (result stored).
-template <class Load, class Trial>
-__device__ __forceinline__ void warp_refill_loop(int count, Load &&load, Trial &&trial) {
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+struct NoPrefetch { __device__ __forceinline__ void operator()(int) const {} };
+template <class Load, class Trial, class Pre = NoPrefetch>
+__device__ __forceinline__ void warp_refill_loop(int count, Load &&load, Trial &&trial, Pre &&pre = Pre()) {
   const unsigned FULL = 0xffffffffu;
-  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   int cursor = 0;  // warp-uniform
   bool have = false;
   for (;;) {
@@ -933,6 +935,7 @@ __device__ __forceinline__ void warp_refill_loop(int count, Load &&load, Trial &
       const int idx = cursor + __popc(nm & lt);
       if (!have && idx < count) have = load(idx);
       cursor += __popc(nm);
+      if (cursor + lane < count) pre(cursor + lane);  // the window the next refills will take their items from
     }
     if (!__any_sync(FULL, have)) {
       if (cursor >= count) break;
@@ -960,7 +963,9 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
   double *const w_xc = pl.wtab + 10 * S, *const w_rsq = pl.wtab + 11 * S;
   const double *const f = pl.f;
   const unsigned long long seed = P.seed;
-  int nA = 0, nB = 0;  // warp-uniform
+  int nB = 0;  // wing photons of the chunk (warp-uniform)
+  const int nC = c1 - c0;
+  auto resonant = [](int fl) { return (fl & (PH_SCATTER | PH_DUSTEV)) == PH_SCATTER; };
   // ---------------- pass 0: classify
   for (int base = c0; base < c1; base += 32) {
     const int s = base + lane;
@@ -1000,11 +1005,10 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
         }
       }
     }
-    const bool res = active && !to_dust, core = res && fabs(x) <= 1.0, wing = res && !core;
-    const unsigned mA = __ballot_sync(FULL, core), mB = __ballot_sync(FULL, wing);
-    if (core) pl.lst[c0 + nA + __popc(mA & lt)] = s;
+    const bool wing = active && !to_dust && !(fabs(x) <= 1.0);
+    const unsigned mB = __ballot_sync(FULL, wing);
     if (wing) pl.lst[c1 - 1 - (nB + __popc(mB & lt))] = s;
-    nA += __popc(mA); nB += __popc(mB);
+    nB += __popc(mB);
   }
   __syncwarp();
   // ---------------- pass A: |x| <= 1 (random_mt.f90:2579-2585)
@@ -1012,8 +1016,14 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
     int slot = 0, ntr = 0;
     double x = 0.0, x0 = 0.0, a = 1.0;
     unsigned long long id = 0, nb = 0;
-    warp_refill_loop(nA,
-      [&](int i) { slot = pl.lst[c0 + i]; x = f[F_XFREQ * S + slot]; x0 = fabs(x); a = var1[slot]; id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot]; return true; },
+    warp_refill_loop(nC,
+      [&](int i) {
+        slot = c0 + i;
+        const int fl = pl.flags[slot];
+        x = f[F_XFREQ * S + slot]; a = var1[slot]; id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot];
+        x0 = fabs(x);
+        return resonant(fl) && x0 <= 1.0;
+      },
       [&]() {
         double u1, u2;
         philox_uniform2(seed, id, nb, u1, u2);
@@ -1023,7 +1033,8 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
         var0[slot] = (x < 0.0) ? -v : v;
         pl.ndraw[slot] = nb;
         return true;
-      });
+      },
+      [&](int i) { const int sp = c0 + i; prefetch_l1(pl.flags + sp); prefetch_l1(f + F_XFREQ * S + sp); prefetch_l1(var1 + sp); prefetch_l1(pl.id + sp); prefetch_l1(pl.ndraw + sp); });
     cnt.reject += ntr; nrng += 2 * ntr;
   }
   // ---------------- pass B: wings, piecewise-constant majorant in beta (:2605-2690)
@@ -1116,7 +1127,7 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
   for (int base = c0; base < c1; base += 32) {
     const int s = base + lane;
     const int fl = s < c1 ? pl.flags[s] : 0;
-    if (!((fl & PH_SCATTER) && !(fl & PH_DUSTEV))) continue;
+    if (!resonant(fl)) continue;
     Rng r;
     r.start(seed, (unsigned long long)pl.id[s], pl.ndraw[s]);
     const double cost = rand_resonance_fast(r, P);
@@ -1136,16 +1147,19 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
     nrng += r.nrng;
   }
   __syncwarp();
-  const int nR = nA + nB;
-  auto res_slot = [&](int i) { return pl.lst[i < nA ? c0 + i : c1 - 1 - (i - nA)]; };
   if (STOKES) {
     // ---------------- pass D: azimuth by rejection (scattering_car.f90:364-371)
     {
       int slot = 0, ntr = 0;
       double Q = 0.0, U = 0.0, s12 = 0.0, env = 1.0;
       unsigned long long id = 0, nb = 0;
-      warp_refill_loop(nR,
-        [&](int i) { slot = res_slot(i); Q = f[F_Q * S + slot]; U = f[F_U * S + slot]; s12 = var2[slot]; env = var3[slot]; id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot]; return true; },
+      warp_refill_loop(nC,
+        [&](int i) {
+          slot = c0 + i;
+          const int fl = pl.flags[slot];
+          Q = f[F_Q * S + slot]; U = f[F_U * S + slot]; s12 = var2[slot]; env = var3[slot]; id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot];
+          return resonant(fl);
+        },
         [&]() {
           double u1, u2, sinp, cosp;
           philox_uniform2(seed, id, nb, u1, u2);
@@ -1156,7 +1170,8 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
           var2[slot] = cosp; var3[slot] = sinp;
           pl.ndraw[slot] = nb;
           return true;
-        });
+        },
+        [&](int i) { const int sp = c0 + i; prefetch_l1(pl.flags + sp); prefetch_l1(f + F_Q * S + sp); prefetch_l1(f + F_U * S + sp); prefetch_l1(var2 + sp); prefetch_l1(var3 + sp); prefetch_l1(pl.id + sp); prefetch_l1(pl.ndraw + sp); });
       cnt.reject += ntr; nrng += 2 * ntr;
     }
     __syncwarp();
@@ -1164,12 +1179,13 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
     {
       int slot = 0, ntr = 0;
       unsigned long long id = 0, nb = 0;
-      warp_refill_loop(nR,
+      warp_refill_loop(nC,
         [&](int i) {
-          slot = res_slot(i);
-          if (P.core_skip && fabs(f[F_XFREQ * S + slot]) < w_xc[slot]) return false;
+          slot = c0 + i;
+          const int fl = pl.flags[slot];
           id = (unsigned long long)pl.id[slot]; nb = pl.ndraw[slot];
-          return true;
+          if (P.core_skip && fabs(f[F_XFREQ * S + slot]) < w_xc[slot]) return false;
+          return resonant(fl);
         },
         [&]() {
           double v1, v2;
@@ -1181,7 +1197,8 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
           var4[slot] = v1; var5[slot] = v2; w_rsq[slot] = rsq;
           pl.ndraw[slot] = nb;
           return true;
-        });
+        },
+        [&](int i) { const int sp = c0 + i; prefetch_l1(pl.flags + sp); prefetch_l1(pl.id + sp); prefetch_l1(pl.ndraw + sp); });
       cnt.reject += ntr; nrng += 2 * ntr;
     }
     __syncwarp();
@@ -1190,7 +1207,7 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW2_MINBLOCKS) k_wf_draw2(const
   for (int base = c0; base < c1; base += 32) {
     const int s = base + lane;
     const int fl = s < c1 ? pl.flags[s] : 0;
-    if (!((fl & PH_SCATTER) && !(fl & PH_DUSTEV))) continue;
+    if (!resonant(fl)) continue;
     double xc = 0.0;
     const bool skip = P.core_skip && fabs(f[F_XFREQ * S + s]) < (xc = w_xc[s]);
     double ux, uy;

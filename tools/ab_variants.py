@@ -14,13 +14,14 @@ for name in args:
     env = dict(os.environ)
     if name != "default":
         env["LART_GPU_LIB"] = os.path.join(ROOT, "lart_b200", "variants", "liblart_gpu_%s.so" % name)
-    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--skip-e2e", "--no-cpu-baseline", "--steps", "10", "--warmup", "3"] + extra
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--skip-e2e", "--no-cpu-baseline", "--complete-photons", "0", "--steps", "10", "--warmup", "3"] + extra
     p = subprocess.run(cmd, env=env, capture_output=True, text=True)
     try:
         j = json.loads(p.stdout.strip().splitlines()[-1])
         r = j["roofline"]
-        res[name] = {"value": j["value"], "stage_ms_per_wave": r["stage_ms_per_wave"], "cellsteps_per_s": j.get("cellsteps_per_s")}
-        print("%-14s value %.4g  stages %s" % (name, j["value"], {k: round(v, 4) for k, v in r["stage_ms_per_wave"].items()}), flush=True)
+        st = {k: v["ms_per_launch"] for k, v in r["per_kernel"].items()}
+        res[name] = {"value": j["value"], "stage_ms_per_wave": st, "cellsteps_per_s": j.get("cellsteps_per_s")}
+        print("%-14s value %.4g  stages %s" % (name, j["value"], {k: round(v, 4) for k, v in st.items()}), flush=True)
     except Exception as e:
         res[name] = {"error": str(e), "stderr": p.stderr[-2000:]}
         print(name, "FAILED", p.stderr[-1500:], flush=True)

@@ -26,6 +26,7 @@
 // stream (seed, photon id) and its draw counter travels with the photon, so both
 // drivers — and the CPU oracle in Philox mode — produce the same photon histories.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library is opened at run time (lart_gpu_comm_init), never linked
 
@@ -571,9 +572,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
 }
 
 // ------------------------------ wavefront driver ----------------------------
-// Work items are pool slots (trace, scatter) and ray-queue entries (peel); the ray
-// of slot s toward observer k lives at rays[s*nobs + k] (kind = -1: no ray this
-// wave), direct-peel rays of freshly emitted photons are appended behind them.
+// Work items are pool slots (trace, scatter) and ray-queue entries (peel).  Every partition owns a region of
+// 2 * n * nobs entries of the ray array (a slot can emit a photon AND scatter it in one wave); the emit and
+// scatter stages append to it with warp-aggregated atomics (ray_append), the peel stage reads what was appended:
+// rays that were proved dead (peel bound) or never existed cost no write and no read.  (The clump driver keeps
+// the round-1 layout: the ray of slot s toward observer k at rays[s*nobs + k], kind = -1 = none, direct rays behind.)
 constexpr int kRefillMin = 8;  // refill a warp when at least this many lanes are idle
 
 // warp-aggregated reservation from a converged point: lanes with `want` get
@@ -588,6 +591,17 @@ __device__ __forceinline__ unsigned reserve(unsigned int *ctr, bool want) {
     base = __shfl_sync(0xffffffffu, base, lead);
   }
   return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// Append a peel ray to the partition's queue.  The lanes that reach this point together (whatever subset of the warp)
+// reserve consecutive entries with ONE atomic; an entry is written only by its owner, the peel stage reads [0, n_direct).
+__device__ __forceinline__ void ray_append(const DevParams &P, const Queues &q, const PeelRay &pr) {
+  auto g = cooperative_groups::coalesced_threads();
+  unsigned base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(q.n_direct, (unsigned)g.size());
+  const unsigned at = g.shfl(base, 0) + g.thread_rank();
+  if (at < q.direct_cap) ray_store(q.rays + q.direct_base + at, pr);
+  else atomicOr(P.err, (unsigned)ERR_DIRECT_QUEUE);  // cannot happen by sizing; never drop a ray silently
 }
 
 // stage 1: refill dead slots from the job queue
@@ -610,9 +624,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
       for (int i = 0; i < P.nobs; ++i) {
         PeelRay pr;
         if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
-        unsigned at = atomicAdd(q.n_direct, 1u);
-        if (at < q.direct_cap) ray_store(q.rays + q.direct_base + at, pr);
-        else atomicOr(P.err, (unsigned)ERR_DIRECT_QUEUE);  // cannot happen by sizing; never drop a ray silently
+        ray_append(P, q, pr);
       }
     }
     int fl = ph.flags;
@@ -1244,11 +1256,7 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
   const int end = pl.s0 + pl.n;
   for (int s = pl.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < end; s += gridDim.x * blockDim.x) {
     const int fl0 = pl.flags[s];
-    PeelRay *myrays = q.rays + (size_t)s * P.nobs;
-    if (!(fl0 & PH_SCATTER)) {
-      for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
-      continue;
-    }
+    if (!(fl0 & PH_SCATTER)) continue;
     Photon ph;
     CellData cs;
     const double *f = pl.f + s;
@@ -1278,12 +1286,9 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
     PeelRay pr0;
     bool have_pr0 = false;
     auto emit_ray = [&](int k, int code, const PeelRay &pr) {  // code: 0 = no ray, 1 = descriptor ready, 2 = proved dead
-      if (LOCAL && k == 0) { have_pr0 = code == 1; if (have_pr0) pr0 = pr; else myrays[0].kind = -1; }
-      else if (code == 1) ray_store(myrays + k, pr);
-      else {
-        if (code == 2) { cnt.peel += 1; cnt.cellsteps += 1; cnt.peel_bound += 1; }
-        myrays[k].kind = -1;
-      }
+      if (LOCAL && k == 0) { have_pr0 = code == 1; if (have_pr0) pr0 = pr; }
+      else if (code == 1) ray_append(P, q, pr);
+      if (code == 2) { cnt.peel += 1; cnt.cellsteps += 1; cnt.peel_bound += 1; }
     };
     auto drop = [&](const PeelRay &pr) { return bound && peel_certainly_capped(P, vtab, cs, pr); };
     if (DUST && (fl0 & PH_DUSTEV)) {
@@ -1313,7 +1318,6 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
         }
       });
     }
-    if (!peeled) for (int k = 0; k < P.nobs; ++k) myrays[k].kind = -1;
     // ---- bounded runs: the photon is abandoned after max_events scatterings, recorded as it stands
     if (P.max_events > 0 && (ph.flags & PH_ALIVE)) {
       const int ne = pl.nev[s] + 1;
@@ -1333,8 +1337,8 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
         double tau = 0.0;
         if (ray_setup(P, r, pr0.x, pr0.y, pr0.z, pr0.kx, pr0.ky, pr0.kz, pr0.ic, pr0.jc, pr0.kc, pr0.xfreq, false, &cs)) resolved = true;
         else if (edge_step(P, vtab, r)) { resolved = true; tau = r.tau; cnt.cellsteps += r.nsteps; }
-        if (resolved) { cnt.peel += 1; peel_deposit(P, pr0, tau, 0u, false); myrays[0].kind = -1; }
-        else ray_store(myrays, pr0);  // the peel stage walks it (from its start)
+        if (resolved) { cnt.peel += 1; peel_deposit(P, pr0, tau, 0u, false); }
+        else ray_append(P, q, pr0);  // the peel stage walks it (from its start)
       }
       // ---- first cell step of the next flight (raytrace_to_tau): most flights end inside the cell
       if (ph.flags & PH_ALIVE) {
@@ -1391,18 +1395,23 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
 }
 
 // stage 4: raytrace_to_edge for every queued peel ray, per-lane refill, deposit
-__global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ DevParams P, Pool pl, Queues q, int budget, int cont_only) {
+#ifndef LART_PEEL_MINBLOCKS
+#define LART_PEEL_MINBLOCKS 2
+#endif
+#ifndef LART_PEEL_REFILL
+#define LART_PEEL_REFILL kRefillMin
+#endif
+__global__ void __launch_bounds__(kBlock, LART_PEEL_MINBLOCKS) k_wf_peel(const __grid_constant__ DevParams P, Pool pl, Queues q, int budget, int cont_only) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
   Counters cnt;
-  // work items of this partition: rays suspended in the previous wave, then its slot rays, then its direct rays
+  // work items of this partition: rays suspended in the previous wave, then the rays this wave's emit and scatter stages queued
   const unsigned par = *q.wave & 1u;
   const PeelCont *cin = q.cont[par];
   PeelCont *cout = q.cont[par ^ 1u];
   const unsigned ncont = min(q.n_cont[par], q.cont_cap);
-  const unsigned nslot = cont_only ? 0u : (unsigned)pl.n * (unsigned)P.nobs, slot_lo = (unsigned)pl.s0 * (unsigned)P.nobs;
-  const unsigned n = ncont + nslot + (cont_only ? 0u : min(*q.n_direct, q.direct_cap));
+  const unsigned n = ncont + (cont_only ? 0u : min(*q.n_direct, q.direct_cap));
   Ray r;
   PeelRay pr;
   bool have = false, exhausted = false;
@@ -1410,7 +1419,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ D
     bool zero_tau = false;
     bool need = !have && !exhausted;
     unsigned nm = __ballot_sync(FULL, need), hm = __ballot_sync(FULL, have);
-    if (nm && (__popc(nm) >= kRefillMin || !hm)) {
+    if (nm && (__popc(nm) >= LART_PEEL_REFILL || !hm)) {
       unsigned idx = reserve(q.head_peel, need);
       if (need) {
         if (idx >= n) exhausted = true;
@@ -1421,14 +1430,10 @@ __global__ void __launch_bounds__(kBlock, 3) k_wf_peel(const __grid_constant__ D
                      c.xfreq, c.u1, c.ic, c.jc, c.kc);
           have = true;
         } else {
-          idx -= ncont;
-          const PeelRay *src = q.rays + (idx < nslot ? slot_lo + idx : q.direct_base + (idx - nslot));
-          if (src->kind >= 0) {
-            ray_load(pr, src);
-            cnt.peel += 1;
-            if (ray_setup(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
-            else have = true;
-          }
+          ray_load(pr, q.rays + q.direct_base + (idx - ncont));
+          cnt.peel += 1;
+          if (ray_setup(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
+          else have = true;
         }
       }
     }
@@ -2677,8 +2682,13 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
       gr.q.rays = h->rays;
       gr.q.n_direct = ctr + 8 * g; gr.q.head_trace = ctr + 8 * g + 1; gr.q.head_peel = ctr + 8 * g + 2;
       gr.q.n_cont = ctr + 8 * g + 3; gr.q.wave = ctr + 8 * g + 5;
-      gr.q.direct_base = (unsigned)((long long)S * nobs + (long long)gr.pool.s0 * nobs);
-      gr.q.direct_cap = (unsigned)std::min<long long>((long long)gr.pool.n * nobs, ray_cap - gr.q.direct_base);
+      if (P.clump) {
+        gr.q.direct_base = (unsigned)((long long)S * nobs + (long long)gr.pool.s0 * nobs);
+        gr.q.direct_cap = (unsigned)std::min<long long>((long long)gr.pool.n * nobs, ray_cap - gr.q.direct_base);
+      } else {
+        gr.q.direct_base = (unsigned)(2LL * gr.pool.s0 * nobs);
+        gr.q.direct_cap = (unsigned)std::min<long long>(2LL * gr.pool.n * nobs, ray_cap - gr.q.direct_base);
+      }
       if (cfg->flags & LART_FLAG_DEBUG_TINY_QUEUES) gr.q.direct_cap = std::min(gr.q.direct_cap, 1u);  // tests of the error path
       gr.q.cont_cap = (unsigned)((long long)gr.pool.n * std::max<long long>(nobs, 1) * 2 + 32);
       gr.q.cont[0] = cont + 2LL * ((long long)gr.pool.s0 * std::max<long long>(nobs, 1) * 2 + 64LL * g);
@@ -2842,7 +2852,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.nobs == 0) {}  // no observers: nothing to peel (xyz_symmetry, plain slabs)
           else if (h->P.clump) k_cl_peel<<<std::max(1, std::min(nb, h->nsm * 4)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
-          else k_wf_peel<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
+          else k_wf_peel<<<std::max(1, std::min(nb, h->nsm * LART_PEEL_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
         }
       }
@@ -2920,6 +2930,13 @@ void partition_pool(lart_gpu_handle h, int n) {
     Pool &p = h->groups[g].pool;
     p.s0 = std::min(g * per, n);
     p.n = std::min(per, n - p.s0);
+    if (!h->P.clump) {  // the partition's region of the ray queue moves with it (between waves the queue is empty)
+      Queues &q = h->groups[g].q;
+      const long long nobs = h->P.nobs;
+      const bool tiny = (h->flags & LART_FLAG_DEBUG_TINY_QUEUES) != 0;
+      q.direct_base = (unsigned)(2LL * p.s0 * nobs);
+      q.direct_cap = tiny ? 1u : (unsigned)(2LL * p.n * nobs);
+    }
   }
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);  // kernel arguments changed: re-capture
   h->graphs.clear();

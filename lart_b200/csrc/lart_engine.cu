@@ -31,6 +31,7 @@
 #include <nccl.h>  // types and prototypes only: the library is opened at run time (lart_gpu_comm_init), never linked
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <thread>
 #include <cmath>
@@ -2274,7 +2275,7 @@ struct lart_gpu_ctx {
   double kernel_ms = 0.0;
   long long launches = 0;
   bool begun = false;
-  double *pinned[2] = {nullptr, nullptr};  // pinned staging of lart_gpu_fetch
+  double *pinned[2] = {nullptr, nullptr};  // pinned staging of lart_gpu_fetch / the grid upload (process-wide buffers, see host_staging)
   std::vector<cudaEvent_t> tev;  // stage-timing events of one step (monolithic driver)
   int draw_mode = 0;    // 0: k_wf_draw2 (compacted rejection loops), 1: serial per-lane loops, 2: warp-cooperative speculative trials
   int draw_chunk = 1024; // slots per warp of k_wf_draw2 (upper bound; LART_GPU_DRAW_CHUNK)
@@ -2286,12 +2287,73 @@ namespace {
 void partition_pool(lart_gpu_handle h, int n);
 int create_impl(const lart_config *cfg, lart_gpu_ctx *h);
 
+// Two 32-MB page-locked staging buffers, allocated at the first use in the process and kept (page-locking costs
+// ~10 ms per buffer; every handle of the process — one per run of the host program — reuses them).
+std::mutex g_stage_mu;
+double *g_stage[2] = {nullptr, nullptr};
+int host_staging(lart_gpu_ctx *h) {
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  for (int k = 0; k < 2; ++k) {
+    if (!g_stage[k]) CUDA_OK(cudaHostAlloc((void **)&g_stage[k], kStageDoubles * sizeof(double), cudaHostAllocPortable));
+    h->pinned[k] = g_stage[k];
+  }
+  return 0;
+}
+
+// Host arrays -> device through the staging buffers: T host threads, each its own pipeline (copy a piece into its share
+// of a staging buffer, async H2D on its own stream, two pieces in flight).  A pageable cudaMemcpy of the six 65-MB grid
+// arrays of a 201^3 run moves ~10 GB/s; this keeps the DMA engine fed from page-locked memory.
+struct UpJob { double *dev; const double *src; size_t n; };
+int upload_pipelined(lart_gpu_ctx *h, const std::vector<UpJob> &jobs) {
+  size_t total = 0;
+  for (const UpJob &j : jobs) total += j.n;
+  if (total < (size_t)(1 << 20)) {  // small grids: the plain copy is faster than starting threads
+    for (const UpJob &j : jobs) if (j.n) CUDA_OK(cudaMemcpy(j.dev, j.src, j.n * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+  }
+  if (int rc = host_staging(h)) return rc;
+  const int T = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  const size_t sub = kStageDoubles / T;
+  std::vector<UpJob> pieces;
+  for (const UpJob &j : jobs)
+    for (size_t c = 0; c < j.n; c += sub) pieces.push_back({j.dev + c, j.src + c, std::min(sub, j.n - c)});
+  std::atomic<size_t> next{0};
+  std::atomic<int> bad{0};
+  const int dev = h->device;
+  auto worker = [&](int t) {
+    if (cudaSetDevice(dev) != cudaSuccess) { bad = 1; return; }
+    cudaStream_t st;
+    cudaEvent_t ev[2];
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { bad = 1; return; }
+    for (int k = 0; k < 2; ++k) cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    bool used[2] = {false, false};
+    int b = 0;
+    for (size_t i; (i = next.fetch_add(1)) < pieces.size() && !bad; b ^= 1) {
+      const UpJob &pc = pieces[i];
+      double *stage = h->pinned[b] + (size_t)t * sub;
+      if (used[b] && cudaEventSynchronize(ev[b]) != cudaSuccess) { bad = 1; break; }
+      memcpy(stage, pc.src, pc.n * sizeof(double));
+      if (cudaMemcpyAsync(pc.dev, stage, pc.n * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) { bad = 1; break; }
+      cudaEventRecord(ev[b], st);
+      used[b] = true;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) bad = 1;
+    for (int k = 0; k < 2; ++k) cudaEventDestroy(ev[k]);
+    cudaStreamDestroy(st);
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(worker, t);
+  worker(0);
+  for (auto &x : th) x.join();
+  if (bad) return fail(std::string("lart_gpu_create: host-to-device copy of the grid failed: ") + cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
 int add_device_to_host(lart_gpu_ctx *h, const double *dev, long long total, const std::vector<Seg> &segs_in) {
   if (total <= 0 || segs_in.empty()) return 0;
   std::vector<Seg> segs = segs_in;
   std::sort(segs.begin(), segs.end(), [](const Seg &a, const Seg &b) { return a.off < b.off; });
-  for (int k = 0; k < 2; ++k)
-    if (!h->pinned[k]) CUDA_OK(cudaMallocHost(&h->pinned[k], kStageDoubles * sizeof(double)));
+  if (int rc = host_staging(h)) return rc;
   const long long lo = segs.front().off, hi = segs.back().off + segs.back().n;
   const int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   cudaEvent_t ev[2];
@@ -2461,6 +2523,15 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out) {
 namespace {
 int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   auto bail = [&](int rc) { return rc; };
+  const bool timing = getenv("LART_GPU_TIMING") != nullptr;  // phases of lart_gpu_create on stderr
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "lart_gpu_create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
   h->nsm = prop.multiProcessorCount;
@@ -2482,13 +2553,22 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   rc = rc ? rc : dupload(h, &P.xface, g.xface, g.nx + 1);
   rc = rc ? rc : dupload(h, &P.yface, g.yface, g.ny + 1);
   rc = rc ? rc : dupload(h, &P.zface, g.zface, g.nz + 1);
-  rc = rc ? rc : dupload(h, &P.rhokap, g.rhokap, nc);
-  rc = rc ? rc : dupload(h, &P.voigt_a, g.voigt_a, nc);
-  rc = rc ? rc : dupload(h, &P.Dfreq, g.Dfreq, nc);
-  rc = rc ? rc : dupload(h, &P.vfx, g.vfx, nc);
-  rc = rc ? rc : dupload(h, &P.vfy, g.vfy, nc);
-  rc = rc ? rc : dupload(h, &P.vfz, g.vfz, nc);
-  if (!rc && P.dust) rc = dupload(h, &P.rhokapD, g.rhokapD, nc);
+  {
+    const double *src[7] = {g.rhokap, g.voigt_a, g.Dfreq, g.vfx, g.vfy, g.vfz, P.dust ? g.rhokapD : nullptr};
+    const double **dst[7] = {&P.rhokap, &P.voigt_a, &P.Dfreq, &P.vfx, &P.vfy, &P.vfz, &P.rhokapD};
+    std::vector<UpJob> jobs;
+    for (int k = 0; k < 7 && !rc; ++k) {
+      *dst[k] = nullptr;
+      if (!src[k]) continue;
+      double *d = nullptr;
+      rc = dalloc(h, &d, nc, false);
+      *dst[k] = d;
+      jobs.push_back({d, src[k], nc});
+    }
+    lap("grid allocations");
+    rc = rc ? rc : upload_pipelined(h, jobs);
+    lap("grid H2D");
+  }
   if (rc) return bail(rc);
   double *vt = nullptr;
   if ((rc = dalloc(h, &vt, kVoigtTabN))) return bail(rc);
@@ -2613,6 +2693,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   }
   L.scalars = take(true, 2);
   L.counters = take(true, C_COUNT);
+  lap("pack cells, clumps, observers");
   L.total = off;
   if ((rc = dalloc(h, &P.tally, (size_t)L.total))) return bail(rc);
   // ---- allph: one slot per photon id
@@ -2626,6 +2707,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     if ((rc = dalloc(h, &h->allph_buf, (size_t)h->allph_n))) return bail(rc);
     for (int k = 0; k < 10; ++k) if (on[k]) P.allph[k] = h->allph_buf + (long long)h->allph_slot[k] * p.nphotons;
   }
+  lap("tally + allph buffers");
   // ---- photon pool
   h->flags = cfg->flags;
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
@@ -2698,6 +2780,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     }
   }
   if (rc) return bail(rc);
+  lap("photon pool + queues");
   h->quantum = cfg->quantum > 0 ? cfg->quantum : (mono ? 32 : 8);
   h->budget = cfg->ray_budget > 0 ? cfg->ray_budget : 32;
   CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -2727,7 +2810,6 @@ int lart_gpu_destroy(lart_gpu_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
-  for (int k = 0; k < 2; ++k) if (h->pinned[k]) cudaFreeHost(h->pinned[k]);
   cudaStreamSynchronize(0);  // the cudaFreeAsync calls above are ordered on the legacy stream
   pool_release(h->device);
   delete h;

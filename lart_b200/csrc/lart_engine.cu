@@ -68,7 +68,7 @@ int fail(const std::string &msg) {
 
 constexpr int kVoigtTabN = 202 * 4;
 constexpr int kBlock = 256;
-constexpr int64_t kTailPhotons = 65536;  // lart_gpu_run: below this many photons left, finish with k_mono
+constexpr int64_t kTailPhotons = 131072;  // lart_gpu_run: below this many photons left, finish with k_mono (+ deferred peel rays)
 constexpr int kTailQuantum = 256;
 
 // ------------------------------- photon pool -------------------------------
@@ -274,7 +274,13 @@ __device__ __forceinline__ void clamp_cell_for_read(const DevParams &P, const Ph
 }
 
 // ------------------------------ monolithic driver ---------------------------
-__global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevParams P, Pool pl, Job *job, int quantum) {
+__device__ __forceinline__ void ray_append(const DevParams &P, const Queues &q, const PeelRay &pr);
+// DEFER (the tail of lart_gpu_run): peel rays are appended to the ray queue q and walked by k_wf_peel after this launch.
+// A photon's next scattering does not depend on its peel rays, but walked inline they are most of the time between two
+// scatterings of a thread (tau0 = 1e4 sphere: ~17 cells per ray, 97 us per event with 8 k photons left) — and in the
+// tail that latency, times the scatterings the longest-lived photon still needs, is the run time.
+template <bool DEFER>
+__global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevParams P, Pool pl, Job *job, int quantum, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -314,6 +320,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
             for (int i = 0; i < P.nobs; ++i) {
               PeelRay pr;
               if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
+              if (DEFER) { ray_append(P, q, pr); continue; }
               int ns;
               double tau = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns);
               cnt.cellsteps += ns; cnt.peel += 1;
@@ -355,6 +362,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
         to_dust = rng.uniform() <= pd;
       }
       auto trace_and_deposit = [&](PeelRay &pr) {
+        if (DEFER) { ray_append(P, q, pr); return; }
         int ns2;
         double t = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns2);
         cnt.cellsteps += ns2; cnt.peel += 1;
@@ -639,7 +647,10 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
 }
 
 // stage 2: raytrace_to_tau for every live photon, per-lane refill
-__global__ void __launch_bounds__(kBlock, 2) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q, int budget) {
+#ifndef LART_TRACE_MINBLOCKS
+#define LART_TRACE_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q, int budget) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
   const unsigned FULL = 0xffffffffu;
@@ -933,6 +944,9 @@ __global__ void __launch_bounds__(kBlock, LART_DRAW_MINBLOCKS) k_wf_draw(const _
 
 // Rejection loop over `count` work items owned by this warp.  load(i) sets the lane up for item i (false: nothing to do for it);
 // trial() runs one trial of the lane's item and returns true when the item is finished (result stored).
+#ifndef LART_DRAW_REFILL
+#define LART_DRAW_REFILL kRefillMin
+#endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 struct NoPrefetch { __device__ __forceinline__ void operator()(int) const {} };
 template <class Load, class Trial, class Pre = NoPrefetch>
@@ -944,7 +958,7 @@ __device__ __forceinline__ void warp_refill_loop(int count, Load &&load, Trial &
   bool have = false;
   for (;;) {
     const unsigned nm = __ballot_sync(FULL, !have);
-    if (cursor < count && (__popc(nm) >= kRefillMin || nm == FULL)) {
+    if (cursor < count && (__popc(nm) >= LART_DRAW_REFILL || nm == FULL)) {
       const int idx = cursor + __popc(nm & lt);
       if (!have && idx < count) have = load(idx);
       cursor += __popc(nm);
@@ -2277,6 +2291,7 @@ struct lart_gpu_ctx {
   bool begun = false;
   double *pinned[2] = {nullptr, nullptr};  // pinned staging of lart_gpu_fetch / the grid upload (process-wide buffers, see host_staging)
   std::vector<cudaEvent_t> tev;  // stage-timing events of one step (monolithic driver)
+  long long ray_cap = 0;  // entries of the ray array
   int draw_mode = 0;    // 0: k_wf_draw2 (compacted rejection loops), 1: serial per-lane loops, 2: warp-cooperative speculative trials
   int draw_chunk = 1024; // slots per warp of k_wf_draw2 (upper bound; LART_GPU_DRAW_CHUNK)
   double stage_ms[LART_STAGE_COUNT] = {};
@@ -2747,6 +2762,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     const long long nobs = P.nobs;
     const long long ray_cap = std::min<long long>((long long)S * std::max<long long>(nobs, 1) * 2, 0x7fffffffLL);
     rc = rc ? rc : dalloc(h, &h->rays, (size_t)ray_cap, true);
+    h->ray_cap = ray_cap;
     unsigned int *ctr = nullptr;
     rc = rc ? rc : dalloc(h, &ctr, 8 * (size_t)G);
     h->ctr = ctr; h->ctr_n = 8 * (size_t)G;
@@ -2886,7 +2902,7 @@ int check_device_error(unsigned int err) {
 }
 // One step with an explicit driver choice (both drivers share the pool layout, and no
 // slot is left mid-wave between steps, so they can alternate freely).
-int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
+int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight, bool defer_peel = false) {
   const bool timing = (h->flags & LART_FLAG_STAGE_TIMING) != 0;
   auto mark = [&](std::vector<cudaEvent_t> &tev, size_t &ne, cudaStream_t st) -> int {  // one event between stage kernels
     if (!timing) return 0;
@@ -2903,7 +2919,16 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
     size_t ne = 0;
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
     if (h->P.clump) k_mono_clump<<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
-    else k_mono<<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn);
+    else if (defer_peel) {
+      // tail of a run: the ray queue is empty (drained) and all of it belongs to this launch
+      Queues q = h->groups[0].q;
+      q.direct_base = 0;
+      q.direct_cap = (unsigned)h->ray_cap;
+      k_wf_reset<<<1, 1, 0, h->stream>>>(q);
+      k_mono<true><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, q);
+      k_wf_peel<<<std::max(1, h->nsm * LART_PEEL_MINBLOCKS), kBlock, 0, h->stream>>>(h->P, h->pool, q, 0x7fffffff, 0);
+      h->launches += 2;
+    } else k_mono<false><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, Queues{});
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
     h->launches += 1;
   } else {
@@ -2924,7 +2949,7 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight) {
           else k_wf_emit<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.clump) k_cl_flight<<<std::max(1, std::min(nb, h->nsm * 3)), kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
-          else k_wf_trace<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
+          else k_wf_trace<<<std::max(1, std::min(nb, h->nsm * LART_TRACE_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           auto between = [&]() -> int { return with_marks ? mark(g.tev, ne[gi], g.stream) : 0; };
           if (h->P.clump) {
@@ -3094,17 +3119,26 @@ int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t str
   if (int rc = lart_gpu_begin(h, first_id, count, stride)) return rc;
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int64_t left = count;
-  const bool progress = getenv("LART_GPU_PROGRESS") != nullptr;
+  long long tail_photons = kTailPhotons;
+  if (const char *e = getenv("LART_GPU_TAIL_PHOTONS")) tail_photons = atoll(e);
+  const char *pe = getenv("LART_GPU_PROGRESS");  // LART_GPU_PROGRESS=n: a line every n steps (default 64)
+  const bool progress = pe != nullptr;
+  const int pevery = pe && atoi(pe) > 0 ? atoi(pe) : 64;
   long long nstep = 0;
   while (left > 0) {
     // Heavy tail: once the queue is empty the pool thins out; keep it dense (compaction), and below
     // kTailPhotons let one thread per photon run `quantum` scatterings per launch — a wave is then bound by
     // launch latency (one scattering per ~5 launches), not by throughput.
     if (!mono) if (int rc = maybe_compact(h, left)) return rc;
-    const bool tail = !mono && left < kTailPhotons && h->job_next >= (unsigned long long)count;
+    const bool tail = !mono && left < tail_photons && h->job_next >= (unsigned long long)count;
     if (tail) if (int rc = drain(h, true)) return rc;  // the monolithic kernel cannot resume parked walks
-    if (int rc = step_impl(h, tail ? kTailQuantum : h->quantum, mono || tail, &left)) return rc;
-    if (progress && (++nstep % 64 == 0 || left == 0))  // LART_GPU_PROGRESS=1: like the reference's nprint lines
+    // tail steps: one thread per photon runs `tq` scatterings and queues their peel rays, the peel stage walks them afterwards;
+    // tq is what the ray queue holds (one ray per scattering and observer)
+    int tq = kTailQuantum;
+    const bool defer = tail && !h->P.clump && h->P.nobs > 0 && h->ray_cap > 0 && !getenv("LART_GPU_TAIL_INLINE");
+    if (defer) tq = (int)std::max<long long>(1, std::min<long long>(kTailQuantum, h->ray_cap / ((long long)std::max(h->pool.n, 1) * h->P.nobs)));
+    if (int rc = step_impl(h, tail ? tq : h->quantum, mono || tail, &left, defer)) return rc;
+    if (progress && (++nstep % pevery == 0 || left == 0))  // LART_GPU_PROGRESS=1: like the reference's nprint lines
       fprintf(stderr, "lart_gpu_run: %lld of %lld photons left, pool range %d, driver %s, device time %.3f s\n", (long long)left,
               (long long)count, h->pool.n, (mono || tail) ? "monolithic" : "wavefront", h->kernel_ms * 1e-3);
   }

@@ -102,7 +102,8 @@ def test_photon_histories_match_oracle(case, flags):
     # In a velocity field thousands of scatterings amplify last-bit differences of the geometric state
     # (direction, Stokes) to ~1e-6..1e-3 while scattering counts and frequencies still agree to 1e-12.
     same = histories_equal(mg, mo, geom_rtol=5e-3 if "hubble" in case else 1e-8)
-    tallies_close(mg, mo, same.mean() if "hubble" not in case else min(same.mean(), 0.999))
+    # (one photon in 2000 taking a different branch somewhere moves the signed Q and U cubes by ~1 % of their absolute sum)
+    tallies_close(mg, mo, same.mean() if "hubble" not in case else min(same.mean(), 0.998))
     n = mo.config.contents.par.nphotons
     assert mg.nscatt_gas == pytest.approx(mo.nscatt_gas, rel=4 * (1 - same.mean()) + 1e-9)
     assert mg.counters["n_photons_done"] == n

@@ -2644,6 +2644,17 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     if ((rc = dalloc(h, &cells, (size_t)P.nsbx * P.nsby * P.nsbz * 32768, false))) return bail(rc);
     k_pack_cells<<<h->nsm * 8, 256, 0, h->stream>>>(P, cells, nc);
     P.cells = cells;
+    // the SoA copies have served: give their memory back to the pool, the photon pool allocated below reuses it
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    const double **soa[7] = {&P.rhokap, &P.voigt_a, &P.Dfreq, &P.vfx, &P.vfy, &P.vfz, &P.rhokapD};
+    for (auto pp : soa) {
+      if (!*pp) continue;
+      void *q = (void *)*pp;
+      h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), q), h->owned.end());
+      dev_free(q);
+      *pp = nullptr;
+    }
+    CUDA_OK(cudaStreamSynchronize(0));
   }
   P.seed = p.seed; P.xfreq0 = p.xfreq0; P.xs = p.xs_point; P.ys = p.ys_point; P.zs = p.zs_point;
   P.source_rmax = p.source_rmax; P.albedo = p.albedo; P.hgg = p.hgg; P.voigt_a0 = p.voigt_a0; P.Dfreq0 = p.Dfreq0;
@@ -2766,11 +2777,21 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     unsigned int *ctr = nullptr;
     rc = rc ? rc : dalloc(h, &ctr, 8 * (size_t)G);
     h->ctr = ctr; h->ctr_n = 8 * (size_t)G;
-    // suspended peel rays: two buffers per partition, each large enough for every ray of a wave plus the carry-over
-    const long long cont_total = 2LL * ((long long)S * std::max<long long>(nobs, 1) * 2 + 64LL * G);
+    // suspended peel rays (walks longer than the per-wave step budget): room for half of a wave's rays per buffer; a ray that
+    // finds its queue full simply keeps walking in this wave (k_wf_peel), so the size is a performance knob, not a limit
+    auto cont_cap_of = [&](long long n) { return std::max<long long>(1024, n * std::max<long long>(nobs, 1) / 2) + 32; };
+    long long cont_total = 0;
+    {
+      const int per0 = ((S / G) + 31) / 32 * 32;
+      for (int g = 0; g < G; ++g) {
+        const int s0 = std::min(g * per0, S), n = (g == G - 1) ? S - s0 : std::min(per0, S - s0);
+        cont_total += 2 * cont_cap_of(n);
+      }
+    }
     PeelCont *cont = nullptr;
     rc = rc ? rc : dalloc(h, &cont, (size_t)cont_total, false);
     h->groups.resize(G);
+    long long cont_off = 0;
     int per = ((S / G) + 31) / 32 * 32;
     for (int g = 0; g < G && !rc; ++g) {
       lart_gpu_ctx::Group &gr = h->groups[g];
@@ -2788,9 +2809,10 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
         gr.q.direct_cap = (unsigned)std::min<long long>(2LL * gr.pool.n * nobs, ray_cap - gr.q.direct_base);
       }
       if (cfg->flags & LART_FLAG_DEBUG_TINY_QUEUES) gr.q.direct_cap = std::min(gr.q.direct_cap, 1u);  // tests of the error path
-      gr.q.cont_cap = (unsigned)((long long)gr.pool.n * std::max<long long>(nobs, 1) * 2 + 32);
-      gr.q.cont[0] = cont + 2LL * ((long long)gr.pool.s0 * std::max<long long>(nobs, 1) * 2 + 64LL * g);
+      gr.q.cont_cap = (unsigned)cont_cap_of(gr.pool.n);
+      gr.q.cont[0] = cont + cont_off;
       gr.q.cont[1] = gr.q.cont[0] + gr.q.cont_cap;
+      cont_off += 2LL * gr.q.cont_cap;
       CUDA_OK(cudaStreamCreateWithFlags(&gr.stream, cudaStreamNonBlocking));
       CUDA_OK(cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming));
     }
@@ -3293,6 +3315,21 @@ int lart_gpu_comm_init(int32_t device, int32_t nranks, int32_t rank, const void 
   memcpy(&id, id128, sizeof(id));
   NCCL_OK(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
   g_comm_rank = rank; g_comm_size = nranks; g_comm_device = device;
+  // NCCL connects its channels at the first collective of each kind (seconds on an NVSwitch box): do that here, in the
+  // MPI_INIT of the GPU path, with a latency-sized and a bandwidth-sized reduce, not inside the first output_reduce.
+  if (nranks > 1) {
+    double *buf = nullptr;
+    const size_t big = (size_t)4 << 20;
+    CUDA_OK(cudaMalloc(&buf, big * sizeof(double)));
+    CUDA_OK(cudaMemset(buf, 0, big * sizeof(double)));
+    cudaStream_t st;
+    CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    NCCL_OK(g_nccl.Reduce(buf, buf, 8, ncclDouble, ncclSum, 0, g_comm, st));
+    NCCL_OK(g_nccl.Reduce(buf, buf, big, ncclDouble, ncclSum, 0, g_comm, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    cudaFree(buf);
+  }
   return 0;
 }
 

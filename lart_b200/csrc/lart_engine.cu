@@ -98,6 +98,7 @@ struct Job {  // photon ids = first_id + j*stride, j in [0,count)
 struct Queues {  // one per pool partition (pipeline)
   PeelRay *rays;      // [ray_cap]: S*nobs slot rays, then per partition the direct rays of this wave's emits
   unsigned int *n_direct, *head_trace, *head_peel;
+  unsigned int *n_dead;   // dead slots of the partition (the emit stage returns at once when there is none)
   unsigned int direct_base, direct_cap;  // direct-ray region of this partition
   PeelCont *cont[2];  // peel rays suspended at their step budget: read from [wave&1], appended to [(wave&1)^1]
   unsigned int *n_cont;   // [2]
@@ -615,6 +616,8 @@ __device__ __forceinline__ void ray_append(const DevParams &P, const Queues &q, 
 
 // stage 1: refill dead slots from the job queue
 __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
+  // nothing to do in most waves of an optically thick run (no photon died, or no photon is left to start): skip the scan
+  if (*q.n_dead == 0u || job->next >= job->count) return;
   Counters cnt;
   ctr_t nrng = 0;
   for (int s = pl.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < pl.s0 + pl.n; s += gridDim.x * blockDim.x) {
@@ -622,6 +625,10 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
     if (job->next >= job->count) continue;
     unsigned long long j = atomicAdd(&job->next, 1ULL);
     if (j >= job->count) continue;
+    {
+      auto cg = cooperative_groups::coalesced_threads();
+      if (cg.thread_rank() == 0) atomicSub(q.n_dead, (unsigned)cg.size());
+    }
     Photon ph;
     Rng rng;
     CellData cs;
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
             if (leaving) {  // dead without tally (raytrace_car.f90:1469-1472)
               ph.flags &= ~PH_ALIVE;
               load_rest(pl, slot, ph);
-              retire_photon(P, ph, false, job, cnt);
+              { retire_photon(P, ph, false, job, cnt); atomicAdd(q.n_dead, 1u); }
               pl.flags[slot] = ph.flags;
               nrng += rng.nrng;
             } else {
@@ -737,7 +744,7 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
           if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
             ph.flags &= ~PH_ALIVE;
             load_rest(pl, slot, ph);
-            retire_photon(P, ph, false, job, cnt);
+            { retire_photon(P, ph, false, job, cnt); atomicAdd(q.n_dead, 1u); }
             store_trace_part(pl, slot, ph);
             nrng += rng.nrng;
             have = false;
@@ -760,7 +767,7 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
         } else if (st == 2) {
           load_rest(pl, slot, ph);  // before finish_escape: it writes ph.xfreq_ref
           cnt.cellsteps += finish_escape(P, ph, r);
-          retire_photon(P, ph, true, job, cnt);
+          { retire_photon(P, ph, true, job, cnt); atomicAdd(q.n_dead, 1u); }
           store_trace_part(pl, slot, ph);
           nrng += rng.nrng;
           have = false;
@@ -1318,7 +1325,7 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
           emit_ray(k, (ok && drop(pr)) ? 2 : (ok ? 1 : 0), pr);
         }
       });
-      if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
+      if (!(ph.flags & PH_ALIVE)) { retire_photon(P, ph, false, job, cnt); atomicAdd(q.n_dead, 1u); }
     } else {
       const double *vi = pl.var + s;
       ScatterVariates v;
@@ -1340,7 +1347,7 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
       if (ne >= P.max_events) {
         ph.flags &= ~PH_ALIVE;
         ph.xfreq_ref = ph.xfreq;
-        retire_photon(P, ph, false, job, cnt);
+        { retire_photon(P, ph, false, job, cnt); atomicAdd(q.n_dead, 1u); }
       }
     }
     bool moved = false;  // position / cell changed (local steps only)
@@ -1362,7 +1369,7 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
         Ray r;
         if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true, &cs)) {
           ph.flags &= ~PH_ALIVE;  // already leaving: dead without tally (raytrace_car.f90:1469-1472)
-          retire_photon(P, ph, false, job, cnt);
+          { retire_photon(P, ph, false, job, cnt); atomicAdd(q.n_dead, 1u); }
         } else {
           double xp, yp, zp;
           const int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
@@ -1375,7 +1382,7 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
             moved = true;
           } else if (st == 2) {
             cnt.cellsteps += finish_escape(P, ph, r);
-            retire_photon(P, ph, true, job, cnt);
+            { retire_photon(P, ph, true, job, cnt); atomicAdd(q.n_dead, 1u); }
             moved = true;
           } else {  // crossed into the next cell: the trace stage walks it (from its start) with this tau
             pl.f[(size_t)F_TAU * S + s] = tau_in;
@@ -2800,7 +2807,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
       gr.pool.n = (g == G - 1) ? S - gr.pool.s0 : std::min(per, S - gr.pool.s0);
       gr.q.rays = h->rays;
       gr.q.n_direct = ctr + 8 * g; gr.q.head_trace = ctr + 8 * g + 1; gr.q.head_peel = ctr + 8 * g + 2;
-      gr.q.n_cont = ctr + 8 * g + 3; gr.q.wave = ctr + 8 * g + 5;
+      gr.q.n_cont = ctr + 8 * g + 3; gr.q.wave = ctr + 8 * g + 5; gr.q.n_dead = ctr + 8 * g + 6;
       if (P.clump) {
         gr.q.direct_base = (unsigned)((long long)S * nobs + (long long)gr.pool.s0 * nobs);
         gr.q.direct_cap = (unsigned)std::min<long long>((long long)gr.pool.n * nobs, ray_cap - gr.q.direct_base);
@@ -2864,6 +2871,10 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
   if (h->ctr) CUDA_OK(cudaMemsetAsync(h->ctr, 0, sizeof(unsigned int) * h->ctr_n, h->stream));  // ... and parked rays
   h->pending_rays = false;
   if (!h->groups.empty() && h->pool.n != h->pool.S) partition_pool(h, h->pool.S);
+  for (auto &g : h->groups) {  // every slot is dead now
+    const unsigned nd = (unsigned)g.pool.n;
+    CUDA_OK(cudaMemcpyAsync(g.q.n_dead, &nd, sizeof(nd), cudaMemcpyHostToDevice, h->stream));
+  }
   h->job_next = 0;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->count = count;

@@ -24,7 +24,69 @@ def grab(path, first, last, pattern, cast=float):
     raise SystemExit("pattern %r not found in %s:%d-%d" % (pattern, path, first, last))
 
 
+def pdf_text(path):
+    """Text of a (LaTeX-made) PDF under docs/: inflate the content streams and join the TJ/Tj string operands."""
+    import zlib
+    data = open(os.path.join(ref, "docs", path), "rb").read()
+    pages = []
+    for m in re.finditer(rb"stream\r?\n", data):
+        raw = data[m.end():data.find(b"endstream", m.end())]
+        try:
+            txt = zlib.decompress(raw)
+        except Exception:
+            continue
+        if b"TJ" not in txt and b"Tj" not in txt:
+            continue
+        out = []
+        for mm in re.finditer(rb"\[(.*?)\]\s*TJ|\((.*?)\)\s*Tj", txt, re.S):
+            if mm.group(1) is not None:
+                for a, b in re.findall(rb"\(((?:\\.|[^\\)])*)\)|(-?\d+\.?\d*)", mm.group(1)):
+                    out.append(b" " if (b and float(b) < -200) else a)
+            else:
+                out.append(mm.group(2))
+        pages.append(b"".join(out).decode("latin1"))
+    return " ".join(pages)
+
+
+def grab_doc(text, pattern, source, cast=float):
+    m = re.search(pattern, text)
+    if not m:
+        raise SystemExit("pattern %r not found in %s" % (pattern, source))
+    return {"value": cast(m.group(1).replace(" ", "").replace(":", ".")), "source": source, "text": m.group(0).strip()}
+
+
+_doc = pdf_text("LaRT_AMR_description.pdf")
+_d = r"(\d+:\d+)"  # a decimal number as the PDF holds it: '7:402'
+_src = "docs/LaRT_AMR_description.pdf section 11 (validation table: 101^3 Cartesian sphere, T = 1e4 K, central point source, 1e6 photons)"
+_row2 = r"102\d+:\d+\\00210-3" + _d + r"\\00210-30\.970\\006" + _d + "kms"   # tau0 = 1e2: J_AMR, J_CAR, ratio, peak velocity
+_row4 = r"104\d+:\d+\\00210-3" + _d + r"\\00210-30\.965\\006" + _d + "kms"   # tau0 = 1e4
+
+
+def grab_doc2(text, pattern, group, source, cast=float):
+    m = re.search(pattern, text)
+    if not m:
+        raise SystemExit("pattern %r not found in %s" % (pattern, source))
+    return {"value": cast(m.group(group).replace(":", ".")), "source": source, "text": m.group(0)}
+
+
 out = {
+    # Known answers of the Cartesian runs the reference documents beside its AMR runs: peak of the normalised J_out(x) and
+    # the velocity of the peak bin (the default 121-bin grid on [-9, 9])
+    "doc_car_sphere_101": {
+        "Jout_max_tau1e2": grab_doc2(_doc, _row2, 1, _src, lambda t: float(t) * 1e-3),
+        "Jout_max_tau1e4": grab_doc2(_doc, _row4, 1, _src, lambda t: float(t) * 1e-3),
+        "peak_kms_tau1e2": grab_doc2(_doc, _row2, 2, _src),
+        "peak_kms_tau1e4": grab_doc2(_doc, _row4, 2, _src),
+    },
+    "amr_sphere_generic_amr_1M": {  # log_amr_1M.txt: the octree twin (178 480 leaves) of the 64^3 sphere below
+        "nleaf": grab("amr_sphere_generic/log_amr_1M.txt", 1, 40, r"AMR nleaf\s*:\s*" + num, int),
+        "voigt_a": grab("amr_sphere_generic/log_amr_1M.txt", 1, 40, r"AMR voigt_a\s*:\s*" + num),
+        "N_HI_pole": grab("amr_sphere_generic/log_amr_1M.txt", 1, 40, r"AMR N\(HI\)_pole\s*:\s*" + num),
+        "tau_pole": grab("amr_sphere_generic/log_amr_1M.txt", 1, 40, r"AMR tau_pole\s*:\s*" + num),
+        "nphotons": grab("amr_sphere_generic/log_amr_1M.txt", 1, 40, r"Total number of photons\s*:\s*" + num),
+        "mean_nscatt": grab("amr_sphere_generic/log_amr_1M.txt", 1, 60, r"Average Number of scattering\s*:\s*" + num),
+        "wall_minutes": grab("amr_sphere_generic/log_amr_1M.txt", 1, 60, r"Total Excution Time\s*:\s*" + num),
+    },
     "sphere_peel_t1tau3": {  # examples/sphere_peel/out.txt, input t1tau3.in: T = 10 K, tau0 = 1e3, 201^3, 1e7 photons
         "voigt_a": grab("sphere_peel/out.txt", 1, 40, r"voigt_a\s*:\s*" + num),
         "N_HI_pole": grab("sphere_peel/out.txt", 1, 40, r"N\(H  I\)_pole\s*:\s*" + num),

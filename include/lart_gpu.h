@@ -107,6 +107,7 @@ typedef struct lart_params {
                                 wrap around in x and y (setup.f90:958-976; raytrace_car.f90:971-1136,
                                 2252-2517).  Shear-periodic boxes (par%Omega /= 0) are not on the GPU path */
   int32_t nobs;
+  int32_t use_amr_grid;      /* the octree ray tracers (raytrace_amr.f90:77-351) and leaf-indexed physics; needs cfg.amr */
 } lart_params;
 
 /* line_type members — src/define.f90:639-656; values from
@@ -160,12 +161,30 @@ typedef struct lart_clumps {
   const int32_t *cg_list;           /* 1-based clump indices                                        */
 } lart_clumps;
 
+/* ---- next row: the octree AMR grid — amr_grid_type, src/octree_mod.f90:19-138 ------------------
+ * The host owns the flat, 1-indexed tree (amr_build_tree, :470-575), its face-neighbour table (amr_build_neighbors,
+ * :619-683) and the leaf physics (grid_create_amr, src/grid_mod_amr.f90:34-526); the library only reads them.
+ * With par.use_amr_grid the photon's cell is a LEAF index (photon%icell_amr), lart_grid supplies the box
+ * (xmin..zmax), Dfreq_ref, the frequency grid and xcrit; its nx, ny, nz and cell arrays are not read.
+ * Not on the GPU path: periodic / mirror boundaries of the octree, band-2 (Ly-beta) photons, H2, CALCJ/CALCP. */
+typedef struct lart_amr {
+  int32_t ncells, nleaf;            /* all cells (internal + leaf), leaves                                   */
+  const int32_t *children;          /* (8,ncells) child cell or 0; octant = 1 + ix + 2*iy + 4*iz             */
+  const int32_t *ileaf;             /* (ncells)   leaf index of a leaf cell, 0 for an internal cell          */
+  const int32_t *icell_of_leaf;     /* (nleaf)    cell index of a leaf                                       */
+  const int32_t *neighbor;          /* (6,ncells) same-level face neighbour (+x,-x,+y,-y,+z,-z) or 0         */
+  const double *cx, *cy, *cz, *ch;  /* (ncells)   cell centres and half-widths                               */
+  const double *rhokap, *voigt_a, *Dfreq, *vfx, *vfy, *vfz; /* (nleaf) as lart_grid's cell arrays            */
+  const double *rhokapD;            /* (nleaf) or NULL when DGR = 0                                          */
+} lart_amr;
+
 typedef struct lart_config {
   lart_grid grid;
   lart_params par;
   lart_line line;
   lart_scatt_mat scatt_mat;        /* nPDF = 0 when unused                  */
   lart_clumps clumps;              /* n = 0 when unused                     */
+  lart_amr amr;                    /* nleaf = 0 when unused                 */
   const lart_observer *observers;  /* par.nobs entries                      */
   int32_t device;                  /* CUDA device ordinal                   */
   int32_t pool_slots;              /* photons in flight; 0 = auto           */
@@ -384,6 +403,13 @@ int lart_gpu_clump_tau_batch(lart_gpu_handle h, int64_t n,
 /* active_set_at_point (src/clump_mod.f90:1595-1634), first hit: the clump a point lies in, or 0 */
 int lart_gpu_clump_locate_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z,
                                 int32_t *icl);
+
+/* ---- octree AMR, unit level.  On a handle created with par.use_amr_grid the batch entry points above
+ * take the LEAF index in icell (jcell = kcell = 1; icell <= 0: the leaf is located first, as raytrace_amr.f90:98-104 does):
+ * lart_gpu_raytrace_edge_batch = raytrace_to_edge_amr (src/raytrace_amr.f90:265-351), lart_gpu_raytrace_tau_batch =
+ * raytrace_to_tau_amr (:77-259), lart_gpu_xcrit_batch = amr_xcrit_local (src/octree_mod.f90:248-284).
+ * lart_gpu_amr_locate_batch = amr_find_leaf (src/octree_mod.f90:149-171): leaf index of every point, 0 = none. */
+int lart_gpu_amr_locate_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z, int32_t *il);
 
 /* ---- next row: sight-line maps, a pure reuse of the edge walk -------------
  * make_sightline_tau_outside (src/sightline_tau_rect.f90:11-190): for every observer and detector pixel the

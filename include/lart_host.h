@@ -43,6 +43,15 @@ int lart_host_read_input(lart_host_model *m, const char *path);
 /* read_input's derived defaults (setup.f90:42-562) + setup_resonance_line
  * (line_mod.f90:1241-1270) + grid_create (grid_mod_car.f90:11-1238) +
  * observer_create_outside (observer_rect.f90:10-300). */
+/* Leaf cells of an octree in the reference's generic AMR format, as generic_amr_read returns them
+ * (src/read_generic_amr.f90:52-346: centre, level (root = 0, its children = 1), nH [cm^-3], T [K], bulk velocity
+ * [km/s]; box length and lower corner in code units).  Sets par%use_amr_grid; lart_host_setup then builds the tree,
+ * the neighbour table and the leaf physics as grid_create_amr does (src/grid_mod_amr.f90:34-526).  The file reader
+ * itself stays the reference's.  vx, vy, vz may be NULL (static medium). */
+int lart_host_set_amr_leaves(lart_host_model *m, int64_t n, const double *x, const double *y, const double *z, const int32_t *level,
+                             const double *nH, const double *T, const double *vx, const double *vy, const double *vz,
+                             double boxlen, double origin_x, double origin_y, double origin_z);
+
 int lart_host_setup(lart_host_model *m);
 
 const lart_config *lart_host_config(const lart_host_model *m);

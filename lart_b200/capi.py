@@ -62,7 +62,7 @@ class Params(C.Structure):
         ("save_peeloff", C.c_int32), ("save_peeloff_2D", C.c_int32), ("save_peeloff_3D", C.c_int32),
         ("save_direc0", C.c_int32), ("save_all_photons", C.c_int32), ("xyz_symmetry", C.c_int32), ("xy_symmetry", C.c_int32),
         ("use_clump_medium", C.c_int32), ("xy_periodic", C.c_int32),
-        ("nobs", C.c_int32),
+        ("nobs", C.c_int32), ("use_amr_grid", C.c_int32),
     ]
 
 
@@ -94,8 +94,16 @@ class Clumps(C.Structure):
                 ("cg_start", c_int32_p), ("cg_list", c_int32_p)]
 
 
+class Amr(C.Structure):
+    _fields_ = [("ncells", C.c_int32), ("nleaf", C.c_int32), ("children", c_int32_p), ("ileaf", c_int32_p),
+                ("icell_of_leaf", c_int32_p), ("neighbor", c_int32_p),
+                ("cx", c_double_p), ("cy", c_double_p), ("cz", c_double_p), ("ch", c_double_p),
+                ("rhokap", c_double_p), ("voigt_a", c_double_p), ("Dfreq", c_double_p),
+                ("vfx", c_double_p), ("vfy", c_double_p), ("vfz", c_double_p), ("rhokapD", c_double_p)]
+
+
 class Config(C.Structure):
-    _fields_ = [("grid", Grid), ("par", Params), ("line", Line), ("scatt_mat", ScattMat), ("clumps", Clumps),
+    _fields_ = [("grid", Grid), ("par", Params), ("line", Line), ("scatt_mat", ScattMat), ("clumps", Clumps), ("amr", Amr),
                 ("observers", C.POINTER(Observer)), ("device", C.c_int32), ("pool_slots", C.c_int32),
                 ("quantum", C.c_int32), ("flags", C.c_int32), ("streams", C.c_int32), ("ray_budget", C.c_int32),
                 ("max_events", C.c_int32), ("pad_", C.c_int32)]
@@ -147,13 +155,13 @@ GPU_SYMBOLS = [
     "lart_gpu_raytrace_edge_batch", "lart_gpu_raytrace_tau_batch", "lart_gpu_sample_batch",
     "lart_gpu_xcrit_batch", "lart_gpu_version", "lart_gpu_stage_ms", "lart_gpu_pool_slots", "lart_gpu_measure_fp64",
     "lart_gpu_sightline_tau", "lart_gpu_sightline_stats",
-    "lart_gpu_clump_edge_batch", "lart_gpu_clump_tau_batch", "lart_gpu_clump_locate_batch", "lart_gpu_peel_bound_batch",
+    "lart_gpu_clump_edge_batch", "lart_gpu_clump_tau_batch", "lart_gpu_clump_locate_batch", "lart_gpu_peel_bound_batch", "lart_gpu_amr_locate_batch",
     "lart_gpu_comm_unique_id", "lart_gpu_comm_init", "lart_gpu_comm_info", "lart_gpu_comm_finalize", "lart_gpu_reduce",
 ]
 HOST_SYMBOLS = [
     "lart_host_new", "lart_host_free", "lart_host_set", "lart_host_read_input", "lart_host_setup",
     "lart_host_config", "lart_host_get_summary", "lart_host_tallies", "lart_host_zero_tallies",
-    "lart_host_normalize", "lart_host_last_error",
+    "lart_host_normalize", "lart_host_last_error", "lart_host_set_amr_leaves",
 ]
 
 _host = None
@@ -186,6 +194,8 @@ def load_host():
         lib.lart_host_zero_tallies.argtypes = [C.c_void_p]
         lib.lart_host_normalize.argtypes = [C.c_void_p]
         lib.lart_host_last_error.restype = C.c_char_p
+        lib.lart_host_set_amr_leaves.argtypes = [C.c_void_p, C.c_int64] + [c_double_p] * 3 + [c_int32_p] + [c_double_p] * 5 + \
+                                               [C.c_double] * 4
         _host = lib
     return _host
 
@@ -236,6 +246,8 @@ def load_gpu():
             lib.lart_gpu_comm_init.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
             lib.lart_gpu_comm_info.argtypes = [c_int32_p, c_int32_p]
             lib.lart_gpu_reduce.argtypes = [H, C.c_int32]
+        if hasattr(lib, "lart_gpu_amr_locate_batch"):
+            lib.lart_gpu_amr_locate_batch.argtypes = [H, C.c_int64] + [c_double_p] * 3 + [c_int32_p]
         if hasattr(lib, "lart_gpu_peel_bound_batch"):  # (absent from older A/B builds selected through LART_GPU_LIB)
             lib.lart_gpu_peel_bound_batch.argtypes = [H, C.c_int64] + [c_double_p] * 4 + [c_int32_p] * 4
         _gpu = lib

@@ -69,6 +69,17 @@ struct DevClumps {
   double xmin, ymin, zmin, dx, dy, dz, inv_dx, inv_dy, inv_dz;
 };
 
+// octree AMR: one 64-byte geometry record per LEAF (centre, half-width, the six face neighbours of its cell) —
+// what a ray needs to leave the leaf — and one 64-byte record per CELL for the descent into a finer neighbour
+// (octree_mod.f90:19-138).  The leaf physics sits in the packed `cells` array, indexed by leaf.
+struct __align__(16) AmrGeo { double cx, cy, cz, h; int nb[6]; int icell, pad_; };
+struct __align__(16) AmrCell { double cx, cy, cz; int child[8]; int ileaf, pad_; };
+struct DevAmr {
+  int on, ncells, nleaf, pad_;
+  const AmrGeo *geo;    // [nleaf]
+  const AmrCell *cell;  // [ncells]
+};
+
 struct DevParams {
   // grid
   int nx, ny, nz, nxfreq;
@@ -79,6 +90,7 @@ struct DevParams {
   // sym = par%xyz_symmetry (source fold, |kz| in Jmu); i0,j0,k0 = cell entered on reflection (grid_mod_car.f90:85-134)
   int sym, bcxy, bcz, i0, j0, k0;
   int clump;      // par%use_clump_medium: the ray tracers of lart_clump.cuh, photons carry their clump index
+  DevAmr amr;     // par%use_amr_grid: photons carry a leaf index in `ic` (jc = kc = 1); nx = nleaf, ny = nz = 1
   DevClumps cl;
   double Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax;
   const double *xface, *yface, *zface;
@@ -268,6 +280,7 @@ LART_DEV unsigned part1by2_5(unsigned v) {  // spread the low 5 bits: ...edcba -
   return v;
 }
 LART_DEV size_t cell_slot(const DevParams &P, int ic, int jc, int kc) {  // 1-based in
+  if (P.amr.on) return (size_t)(ic - 1);  // leaf-indexed records
   const unsigned i = (unsigned)(ic - 1), j = (unsigned)(jc - 1), k = (unsigned)(kc - 1);
   const size_t sb = (size_t)(i >> 5) + (size_t)P.nsbx * ((size_t)(j >> 5) + (size_t)P.nsby * (size_t)(k >> 5));
   const unsigned m = part1by2_5(i & 31u) | (part1by2_5(j & 31u) << 1) | (part1by2_5(k & 31u) << 2);
@@ -284,6 +297,10 @@ LART_DEV void load_cell(const DevParams &P, int ic, int jc, int kc, CellData &o)
     o.vfx = __ldg(P.vfx + c); o.vfy = __ldg(P.vfy + c); o.vfz = __ldg(P.vfz + c);
     o.rhokapD = P.dust ? __ldg(P.rhokapD + c) : 0.0;
   }
+}
+LART_DEV double4 ldg_d4(const void *p) {  // four doubles through the read-only path (two 16-byte loads)
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
 }
 LART_DEV double vdotk(const CellData &c, double kx, double ky, double kz) {
   return DADD(DADD(DMUL(c.vfx, kx), DMUL(c.vfy, ky)), DMUL(c.vfz, kz));
@@ -361,11 +378,141 @@ LART_DEV bool axis_setup_bc(double &k, double &p, int &cell, int n, const double
 
 // `here` (optional) = record of the start cell when the caller already holds it; it is used
 // unless the on-face rule moved the start into a neighbouring cell.
+// ---------------------------------------------------------------------------
+// Octree AMR ray tracers — raytrace_amr.f90:77-351 over octree_mod.f90.  A Ray on the octree keeps its RUNNING position in
+// (tx,ty,tz) (the reference advances x,y,z at every face: x = x + t_exit*kx), the current leaf in `ic` and the leaf's
+// physics in `cell`; the DDA members are unused.  Every expression is written in the reference's order with explicit
+// roundings, so optical depths, positions, frequencies and leaf sequences are those of the CPU oracle bit for bit.
+// Open boundaries only (periodic / mirror octrees stay with the Fortran host).
+// ---------------------------------------------------------------------------
+// amr_find_leaf — octree_mod.f90:149-171
+LART_DEV int amr_find_leaf(const DevParams &P, double x, double y, double z) {
+  if (x < P.xmin || x > P.xmax || y < P.ymin || y > P.ymax || z < P.zmin || z > P.zmax) return 0;
+  int icell = 1;
+  for (;;) {
+    const AmrCell *c = P.amr.cell + (icell - 1);
+    const int il = __ldg(&c->ileaf);
+    if (il > 0) return il;
+    int ioct = 0;
+    if (x >= __ldg(&c->cx)) ioct += 1;
+    if (y >= __ldg(&c->cy)) ioct += 2;
+    if (z >= __ldg(&c->cz)) ioct += 4;
+    icell = __ldg(&c->child[ioct]);
+    if (icell == 0) return 0;
+  }
+}
+LART_DEV bool amr_ray_setup(const DevParams &P, Ray &r, const CellData *here) {
+  r.tx = r.x0; r.ty = r.y0; r.tz = r.z0;
+  r.delx = r.dely = r.delz = 0.0;
+  r.istep = r.jstep = r.kstep = 0;
+  r.jc = 1; r.kc = 1;
+  if (r.ic <= 0) {  // raytrace_amr.f90:98-104
+    r.ic = amr_find_leaf(P, r.x0, r.y0, r.z0);
+    if (r.ic <= 0) return true;
+    here = nullptr;
+  }
+  if (here) r.cell = *here;
+  else load_cell(P, r.ic, 1, 1, r.cell);
+  r.u1 = vdotk(r.cell, r.kx, r.ky, r.kz);
+  return false;
+}
+// amr_cell_exit — octree_mod.f90:412-458; face 1=+x 2=-x 3=+y 4=-y 5=+z 6=-z, minloc = the first minimum
+LART_DEV void amr_cell_exit(const double4 g, double x, double y, double z, double kx, double ky, double kz, double &t_exit, int &iface) {
+  double t1 = kHugest, t2 = kHugest, t3 = kHugest, t4 = kHugest, t5 = kHugest, t6 = kHugest;
+  if (kx > 0.0) t1 = DSUB(DADD(g.x, g.w), x) / kx; else if (kx < 0.0) t2 = DSUB(DSUB(g.x, g.w), x) / kx;
+  if (ky > 0.0) t3 = DSUB(DADD(g.y, g.w), y) / ky; else if (ky < 0.0) t4 = DSUB(DSUB(g.y, g.w), y) / ky;
+  if (kz > 0.0) t5 = DSUB(DADD(g.z, g.w), z) / kz; else if (kz < 0.0) t6 = DSUB(DSUB(g.z, g.w), z) / kz;
+  iface = 1; t_exit = t1;
+  if (t2 < t_exit) { t_exit = t2; iface = 2; }
+  if (t3 < t_exit) { t_exit = t3; iface = 3; }
+  if (t4 < t_exit) { t_exit = t4; iface = 4; }
+  if (t5 < t_exit) { t_exit = t5; iface = 5; }
+  if (t6 < t_exit) { t_exit = t6; iface = 6; }
+}
+// amr_next_leaf — octree_mod.f90:717-757: the neighbour of the leaf's cell across `iface`, then the descent into its
+// children; the octant bit along the face normal is set from iface, the two others from the position on the face
+LART_DEV int amr_next_leaf(const DevParams &P, int ineigh, int iface, double x, double y, double z) {
+  if (ineigh == 0) return 0;
+  for (;;) {
+    const AmrCell *c = P.amr.cell + (ineigh - 1);
+    const int il = __ldg(&c->ileaf);
+    if (il != 0) return il;
+    const bool bx = x >= __ldg(&c->cx), by = y >= __ldg(&c->cy), bz = z >= __ldg(&c->cz);
+    int ioct;
+    switch (iface) {
+      case 1: ioct = (by ? 2 : 0) + (bz ? 4 : 0); break;
+      case 2: ioct = 1 + (by ? 2 : 0) + (bz ? 4 : 0); break;
+      case 3: ioct = (bx ? 1 : 0) + (bz ? 4 : 0); break;
+      case 4: ioct = (bx ? 1 : 0) + 2 + (bz ? 4 : 0); break;
+      case 5: ioct = (bx ? 1 : 0) + (by ? 2 : 0); break;
+      default: ioct = (bx ? 1 : 0) + (by ? 2 : 0) + 4; break;
+    }
+    const int child = __ldg(&c->child[ioct]);
+    if (child == 0) return 0;  // a gap: no leaf there (ileaf of an internal cell is 0), the ray leaves
+    ineigh = child;
+  }
+}
+// leave the current leaf: running position to the face, next leaf, frequency into its frame (:162-216 / :302-348).
+// false = the ray left the grid
+LART_DEV bool amr_cross(const DevParams &P, Ray &r, const AmrGeo *g, double t_exit, int iface) {
+  r.tx = DADD(r.tx, DMUL(t_exit, r.kx));
+  r.ty = DADD(r.ty, DMUL(t_exit, r.ky));
+  r.tz = DADD(r.tz, DMUL(t_exit, r.kz));
+  const int il_new = amr_next_leaf(P, __ldg(&g->nb[iface - 1]), iface, r.tx, r.ty, r.tz);
+  if (il_new <= 0) return false;
+  const double Dold = r.cell.Dfreq;
+  load_cell(P, il_new, 1, 1, r.cell);
+  const double u2 = vdotk(r.cell, r.kx, r.ky, r.kz);
+  r.xfreq = DSUB(DMUL(DADD(r.xfreq, r.u1), Dold) / r.cell.Dfreq, u2);
+  r.u1 = u2;
+  r.ic = il_new;
+  return true;
+}
+LART_DEV double amr_opacity(const DevParams &P, const double *vtab, const Ray &r) {
+  double k = DMUL(r.cell.rhokap, voigt_seon2(vtab, r.xfreq, r.cell.voigt_a));
+  if (P.dust) k = DADD(k, r.cell.rhokapD);
+  return k;
+}
+// one leaf of raytrace_to_edge_amr (:302-348); true when the walk is finished
+LART_DEV bool amr_edge_step(const DevParams &P, const double *vtab, Ray &r) {
+  const AmrGeo *g = P.amr.geo + (r.ic - 1);
+  const double4 gc = ldg_d4(g);
+  double t_exit;
+  int iface;
+  amr_cell_exit(gc, r.tx, r.ty, r.tz, r.kx, r.ky, r.kz, t_exit, iface);
+  const double kap = amr_opacity(P, vtab, r);
+  r.tau = DADD(r.tau, DMUL(t_exit, kap));
+  ++r.nsteps;
+  if (r.tau >= kTauHuge) return true;
+  return !amr_cross(P, r, g, t_exit, iface);
+}
+// one leaf of raytrace_to_tau_amr (:107-216): 0 = keep walking, 1 = reached tau_in (position in xp,yp,zp), 2 = left the grid
+LART_DEV int amr_tau_step(const DevParams &P, const double *vtab, Ray &r, double tau_in, double &xp, double &yp, double &zp) {
+  const AmrGeo *g = P.amr.geo + (r.ic - 1);
+  const double4 gc = ldg_d4(g);
+  double t_exit;
+  int iface;
+  amr_cell_exit(gc, r.tx, r.ty, r.tz, r.kx, r.ky, r.kz, t_exit, iface);
+  const double kap = amr_opacity(P, vtab, r);
+  ++r.nsteps;
+  const double tnext = DADD(r.tau, DMUL(t_exit, kap));
+  if (tnext >= tau_in) {
+    const double d_step = (kap > 0.0) ? DSUB(tau_in, r.tau) / kap : t_exit;
+    xp = DADD(r.tx, DMUL(d_step, r.kx));
+    yp = DADD(r.ty, DMUL(d_step, r.ky));
+    zp = DADD(r.tz, DMUL(d_step, r.kz));
+    return 1;
+  }
+  r.tau = tnext;
+  return amr_cross(P, r, g, t_exit, iface) ? 0 : 2;
+}
+
 LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
                         int ic, int jc, int kc, double xfreq, bool zonly_eq, const CellData *here = nullptr) {
   r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
   r.ic = ic; r.jc = jc; r.kc = kc;
   r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0; r.flip = 0;
+  if (P.amr.on) return amr_ray_setup(P, r, here);
   if (P.bcxy) {  // folded / periodic grids; their to_tau variants test `== xp` (:1681, :1993, :2293), to_edge `<= xp`
     bool mx, my, mz;
     if (axis_setup_bc(r.kx, r.x0, r.ic, P.nx, P.xface, r.istep, r.tx, r.delx, zonly_eq, P.bcxy, P.i0, mx)) return true;
@@ -489,6 +636,7 @@ LART_DEV void ray_shift(const DevParams &P, Ray &r) {
 
 // One cell step of raytrace_to_edge.  Returns true when the walk is finished.
 LART_DEV bool edge_step(const DevParams &P, const double *vtab, Ray &r) {
+  if (P.amr.on) return amr_edge_step(P, vtab, r);
   double kap = ray_opacity(P, vtab, r);
   ++r.nsteps;
   int ax = ray_axis(P, r);
@@ -504,6 +652,7 @@ LART_DEV bool edge_step(const DevParams &P, const double *vtab, Ray &r) {
 // One cell step of raytrace_to_tau.  status: 0 = keep walking, 1 = reached tau_in
 // (position in xp,yp,zp), 2 = left the grid.
 LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau_in, double &xp, double &yp, double &zp) {
+  if (P.amr.on) return amr_tau_step(P, vtab, r, tau_in, xp, yp, zp);
   double kap = ray_opacity(P, vtab, r);
   ++r.nsteps;
   int ax = ray_axis(P, r);
@@ -823,6 +972,14 @@ LART_DEV void car_xcrit_local(const DevParams &P, int i, int j, int k, double x,
   if (P.core_skip_global) { xc = P.xcrit; xc2 = P.xcrit2; return; }
   xc = 0.0; xc2 = 0.0;
   if (i < 1 || j < 1 || k < 1) return;
+  if (P.amr.on) {  // amr_xcrit_local — octree_mod.f90:248-284
+    const double4 g = ldg_d4(P.amr.geo + (i - 1));
+    const double dla = fmin(g.w - fabs(x - g.x), fmin(g.w - fabs(y - g.y), g.w - fabs(z - g.z)));
+    if (dla <= 0.0) return;
+    const double at = voigt_a * rhokap * dla;
+    if (at > 1.0) { xc = cbrt(at) / 5.0; xc2 = xc * xc; }
+    return;
+  }
   double dlx = fmin(x - __ldg(P.xface + i - 1), __ldg(P.xface + i) - x);
   double dly = fmin(y - __ldg(P.yface + j - 1), __ldg(P.yface + j) - y);
   double dlz = fmin(z - __ldg(P.zface + k - 1), __ldg(P.zface + k) - z);
@@ -1563,12 +1720,16 @@ LART_DEV void generate_photon(const DevParams &P, Photon &ph, Rng &r, Counters &
   ph.ic = (int)floor((ph.x - P.xmin) / P.dx) + 1;
   ph.jc = (int)floor((ph.y - P.ymin) / P.dy) + 1;
   ph.kc = (int)floor((ph.z - P.zmin) / P.dz) + 1;
-  if (ph.kx < 0.0 && ph.ic == P.nx + 1) ph.ic = P.nx;
-  if (ph.ky < 0.0 && ph.jc == P.ny + 1) ph.jc = P.ny;
-  if (ph.kz < 0.0 && ph.kc == P.nz + 1) ph.kc = P.nz;
-  if (ph.kx > 0.0 && ph.ic < 1) ph.ic = 1;
-  if (ph.ky > 0.0 && ph.jc < 1) ph.jc = 1;
-  if (ph.kz > 0.0 && ph.kc < 1) ph.kc = 1;
+  if (P.amr.on) {  // generate_photon.f90:375-376
+    ph.ic = amr_find_leaf(P, ph.x, ph.y, ph.z); ph.jc = 1; ph.kc = 1;
+  } else {
+    if (ph.kx < 0.0 && ph.ic == P.nx + 1) ph.ic = P.nx;
+    if (ph.ky < 0.0 && ph.jc == P.ny + 1) ph.jc = P.ny;
+    if (ph.kz < 0.0 && ph.kc == P.nz + 1) ph.kc = P.nz;
+    if (ph.kx > 0.0 && ph.ic < 1) ph.ic = 1;
+    if (ph.ky > 0.0 && ph.jc < 1) ph.jc = 1;
+    if (ph.kz > 0.0 && ph.kc < 1) ph.kc = 1;
+  }
   ph.mx = cost * cosp; ph.my = cost * sinp; ph.mz = -sint;
   ph.nx = -sinp; ph.ny = cosp; ph.nz = 0.0;
   ph.Q = 0.0; ph.U = 0.0; ph.V = 0.0;

@@ -211,6 +211,7 @@ __device__ __forceinline__ int finish_escape(const DevParams &P, Photon &ph, con
   ph.xfreq = DADD(r.xfreq, r.u1);
   ph.xfreq_ref = DMUL(ph.xfreq, r.cell.Dfreq / P.Dfreq_ref);
   ph.x = r.x0; ph.y = r.y0; ph.z = r.z0;
+  if (P.amr.on) { ph.x = r.tx; ph.y = r.ty; ph.z = r.tz; }  // the running position at the last face (raytrace_amr.f90:219-222)
   if (P.bcxy == BC_MIRROR) {  // raytrace_car.f90:1934-1943: the end point and the reflected direction are stored even on escape
     ray_endpoint_bc(P, r, ph.x, ph.y, ph.z);
     ph.kx = r.kx; ph.ky = r.ky; ph.kz = r.kz;
@@ -824,6 +825,16 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
 #endif
 
 __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const double *vtab, const CellData &cs, const PeelRay &pr) {
+  if (P.amr.on) {  // the same bound with the leaf's faces: L = min over the axes of h - |p - c|
+    if (pr.ic <= 0) return false;
+    const double4 g = ldg_d4(P.amr.geo + (pr.ic - 1));
+    const double La = fmin(DSUB(g.w, fabs(DSUB(pr.x, g.x))), fmin(DSUB(g.w, fabs(DSUB(pr.y, g.y))), DSUB(g.w, fabs(DSUB(pr.z, g.z)))));
+    if (!(La > 0.0)) return false;
+    if (!(DMUL(DADD(cs.rhokap, P.dust ? cs.rhokapD : 0.0), La) >= kTauHuge)) return false;
+    double kapa = DMUL(cs.rhokap, voigt_seon2(vtab, pr.xfreq, cs.voigt_a));
+    if (P.dust) kapa = DADD(kapa, cs.rhokapD);
+    return DMUL(kapa, La) >= kTauHuge;
+  }
   double L = fmin(DSUB(pr.z, __ldg(P.zface + pr.kc - 1)), DSUB(__ldg(P.zface + pr.kc), pr.z));
   if (!P.zonly) {
     L = fmin(L, fmin(DSUB(pr.x, __ldg(P.xface + pr.ic - 1)), DSUB(__ldg(P.xface + pr.ic), pr.x)));
@@ -1996,6 +2007,11 @@ __global__ void k_clump_locate_batch(const __grid_constant__ DevParams P, long l
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     icl[i] = clump_at_point(P.cl, x[i], y[i], z[i]);
 }
+__global__ void k_amr_locate_batch(const __grid_constant__ DevParams P, long long n, const double *x, const double *y,
+                                   const double *z, int *il) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    il[i] = amr_find_leaf(P, x[i], y[i], z[i]);
+}
 // host arrays -> device records (geometry: centre + radius^2; physics: 64 bytes)
 __global__ void k_clump_geo_reg(long long nreg, const int *cg_list, const double4 *geo, double4 *geo_reg) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nreg; i += (long long)gridDim.x * blockDim.x)
@@ -2467,11 +2483,32 @@ inline int grid_for(long long n, int nsm) { return (int)std::max<long long>(1, s
 int validate(const lart_config *c) {
   const lart_grid &g = c->grid;
   const lart_params &p = c->par;
+  if (p.use_amr_grid) {  // octree: the box, Dfreq_ref and the frequency grid come from lart_grid, everything else from lart_amr
+    const lart_amr &a = c->amr;
+    if (a.nleaf < 1 || a.ncells < a.nleaf) return fail("lart_gpu_create: use_amr_grid needs amr.nleaf >= 1 and ncells >= nleaf");
+    if (!a.children || !a.ileaf || !a.icell_of_leaf || !a.neighbor || !a.cx || !a.cy || !a.cz || !a.ch || !a.rhokap || !a.voigt_a ||
+        !a.Dfreq || !a.vfx || !a.vfy || !a.vfz)
+      return fail("lart_gpu_create: NULL octree array");
+    if (p.DGR > 0.0 && !a.rhokapD) return fail("lart_gpu_create: DGR > 0 but amr.rhokapD is NULL");
+    if (p.use_clump_medium || p.xy_periodic || p.xyz_symmetry || p.xy_symmetry)
+      return fail("lart_gpu_create: clump media, periodic and mirror boundaries on an octree stay with the Fortran host");
+    if (c->flags & (LART_FLAG_SOA_GRID | LART_FLAG_LOCAL_STEPS)) return fail("lart_gpu_create: LART_FLAG_SOA_GRID / LOCAL_STEPS do not apply to an octree");
+    if (g.nxfreq < 1 || !(g.xmax > g.xmin)) return fail("lart_gpu_create: octree box / frequency grid missing in lart_grid");
+    for (int64_t i = 0; i < (int64_t)a.ncells; ++i) {
+      if (a.ileaf[i] < 0 || a.ileaf[i] > a.nleaf) return fail("lart_gpu_create: amr.ileaf out of range");
+      for (int q = 0; q < 8; ++q) if (a.children[8 * i + q] < 0 || a.children[8 * i + q] > a.ncells) return fail("lart_gpu_create: amr.children out of range");
+      for (int q = 0; q < 6; ++q) if (a.neighbor[6 * i + q] < 0 || a.neighbor[6 * i + q] > a.ncells) return fail("lart_gpu_create: amr.neighbor out of range");
+    }
+    for (int64_t i = 0; i < (int64_t)a.nleaf; ++i)
+      if (a.icell_of_leaf[i] < 1 || a.icell_of_leaf[i] > a.ncells || a.ileaf[a.icell_of_leaf[i] - 1] != i + 1)
+        return fail("lart_gpu_create: amr.icell_of_leaf / ileaf are not inverse to each other");
+  } else {
   if (g.nx < 1 || g.ny < 1 || g.nz < 1 || g.nxfreq < 1) return fail("lart_gpu_create: grid dimensions must be >= 1");
   if (!g.xface || !g.yface || !g.zface || !g.rhokap || !g.voigt_a || !g.Dfreq || !g.vfx || !g.vfy || !g.vfz)
     return fail("lart_gpu_create: NULL grid array");
+  }
   if (c->line.line_type != 1) return fail("lart_gpu_create: only line_type 1 (Ly-alpha singlet) is on the GPU path");
-  if (p.DGR > 0.0 && !g.rhokapD) return fail("lart_gpu_create: DGR > 0 but rhokapD is NULL");
+  if (p.DGR > 0.0 && !p.use_amr_grid && !g.rhokapD) return fail("lart_gpu_create: DGR > 0 but rhokapD is NULL");
   if (p.DGR > 0.0 && p.use_stokes && c->scatt_mat.nPDF < 2) return fail("lart_gpu_create: dust + Stokes needs scatt_mat");
   if (p.nobs < 0 || p.nobs > LART_MAX_OBSERVERS) return fail("lart_gpu_create: nobs out of range");
   if (p.save_peeloff && p.nobs > 0 && !c->observers) return fail("lart_gpu_create: observers is NULL");
@@ -2572,6 +2609,51 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   const size_t nc = (size_t)g.nx * g.ny * g.nz;
   P.dust = p.DGR > 0.0 ? 1 : 0;
   int rc = 0;
+  P.amr = DevAmr{};
+  const bool amr_on = p.use_amr_grid != 0;
+  if (amr_on) {
+    // octree: leaf physics as packed 64-byte records indexed by leaf, a 64-byte geometry record per leaf
+    // (centre, half-width, face neighbours of its cell) and a 64-byte record per cell for descents
+    const lart_amr &a = cfg->amr;
+    P.nx = a.nleaf; P.ny = 1; P.nz = 1;
+    P.dx = g.xmax - g.xmin; P.dy = g.ymax - g.ymin; P.dz = g.zmax - g.zmin;
+    const double faces[6] = {g.xmin, g.xmax, g.ymin, g.ymax, g.zmin, g.zmax};
+    rc = rc ? rc : dupload(h, &P.xface, faces, 2);
+    rc = rc ? rc : dupload(h, &P.yface, faces + 2, 2);
+    rc = rc ? rc : dupload(h, &P.zface, faces + 4, 2);
+    static_assert(sizeof(Cell) == 64 && sizeof(AmrGeo) == 64 && sizeof(AmrCell) == 64, "octree records are 64 bytes");
+    std::vector<Cell> hc(a.nleaf);
+    std::vector<AmrGeo> hg(a.nleaf);
+    std::vector<AmrCell> hx(a.ncells);
+    for (int il = 0; il < a.nleaf; ++il) {
+      Cell &c = hc[il];
+      c.rhokap = a.rhokap[il]; c.voigt_a = a.voigt_a[il]; c.Dfreq = a.Dfreq[il];
+      c.vfx = a.vfx[il]; c.vfy = a.vfy[il]; c.vfz = a.vfz[il]; c.rhokapD = P.dust ? a.rhokapD[il] : 0.0; c.pad = 0.0;
+      const int ic = a.icell_of_leaf[il];
+      AmrGeo &q = hg[il];
+      q.cx = a.cx[ic - 1]; q.cy = a.cy[ic - 1]; q.cz = a.cz[ic - 1]; q.h = a.ch[ic - 1];
+      for (int f = 0; f < 6; ++f) q.nb[f] = a.neighbor[6 * (size_t)(ic - 1) + f];
+      q.icell = ic; q.pad_ = 0;
+    }
+    for (int ic = 0; ic < a.ncells; ++ic) {
+      AmrCell &c = hx[ic];
+      c.cx = a.cx[ic]; c.cy = a.cy[ic]; c.cz = a.cz[ic];
+      for (int q = 0; q < 8; ++q) c.child[q] = a.children[8 * (size_t)ic + q];
+      c.ileaf = a.ileaf[ic]; c.pad_ = 0;
+    }
+    Cell *dc = nullptr; AmrGeo *dg = nullptr; AmrCell *dx = nullptr;
+    rc = rc ? rc : dalloc(h, &dc, (size_t)a.nleaf, false);
+    rc = rc ? rc : dalloc(h, &dg, (size_t)a.nleaf, false);
+    rc = rc ? rc : dalloc(h, &dx, (size_t)a.ncells, false);
+    lap("octree allocations");
+    if (!rc) rc = upload_pipelined(h, {{(double *)dc, (const double *)hc.data(), (size_t)a.nleaf * 8},
+                                       {(double *)dg, (const double *)hg.data(), (size_t)a.nleaf * 8},
+                                       {(double *)dx, (const double *)hx.data(), (size_t)a.ncells * 8}});
+    lap("octree H2D");
+    P.cells = dc;
+    P.amr.on = 1; P.amr.ncells = a.ncells; P.amr.nleaf = a.nleaf; P.amr.geo = dg; P.amr.cell = dx;
+    P.rhokap = P.voigt_a = P.Dfreq = P.vfx = P.vfy = P.vfz = P.rhokapD = nullptr;
+  } else {
   rc = rc ? rc : dupload(h, &P.xface, g.xface, g.nx + 1);
   rc = rc ? rc : dupload(h, &P.yface, g.yface, g.ny + 1);
   rc = rc ? rc : dupload(h, &P.zface, g.zface, g.nz + 1);
@@ -2590,6 +2672,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     lap("grid allocations");
     rc = rc ? rc : upload_pipelined(h, jobs);
     lap("grid H2D");
+  }
   }
   if (rc) return bail(rc);
   double *vt = nullptr;
@@ -2646,7 +2729,7 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     }
   }
   P.nsbx = (g.nx + 31) / 32; P.nsby = (g.ny + 31) / 32; P.nsbz = (g.nz + 31) / 32;
-  if (!P.soa) {
+  if (!P.soa && !amr_on) {
     Cell *cells = nullptr;
     if ((rc = dalloc(h, &cells, (size_t)P.nsbx * P.nsby * P.nsbz * 32768, false))) return bail(rc);
     k_pack_cells<<<h->nsm * 8, 256, 0, h->stream>>>(P, cells, nc);
@@ -3585,6 +3668,25 @@ int lart_gpu_clump_locate_batch(lart_gpu_handle h, int64_t n, const double *x, c
   return 0;
 }
 
+int lart_gpu_amr_locate_batch(lart_gpu_handle h, int64_t n, const double *x, const double *y, const double *z, int32_t *il) {
+  if (!h) return fail("lart_gpu_amr_locate_batch: NULL handle");
+  if (!h->P.amr.on) return fail("lart_gpu_amr_locate_batch: the handle has no octree");
+  if (n < 0 || (n > 0 && (!x || !y || !z || !il))) return fail("lart_gpu_amr_locate_batch: bad argument");
+  if (n == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  Scratch s;
+  double *dx, *dy, *dz;
+  int *dil;
+  int rc = 0;
+  rc = rc ? rc : s.in(&dx, x, n); rc = rc ? rc : s.in(&dy, y, n); rc = rc ? rc : s.in(&dz, z, n); rc = rc ? rc : s.outbuf(&dil, n);
+  if (rc) return rc;
+  k_amr_locate_batch<<<grid_for(n, h->nsm), kBlock, 0, h->stream>>>(h->P, n, dx, dy, dz, dil);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  D2H(il, dil, n);
+  return 0;
+}
+
 int lart_gpu_sample_batch(int32_t kind, uint64_t seed, int64_t n, const int64_t *ids, const double *p0, const double *p1,
                           int32_t ndraw, double *out) {
   if (kind < 0 || kind > 6) return fail("lart_gpu_sample_batch: unknown kind");
@@ -3671,6 +3773,7 @@ extern "C" {
 int lart_gpu_sightline_tau(lart_gpu_handle h, double cross0, lart_sightline_out *out) {
   if (!h || !out) return fail("lart_gpu_sightline_tau: NULL argument");
   if (h->obs_host.empty()) return fail("lart_gpu_sightline_tau: the handle has no observers (par%save_peeloff, par%nobs)");
+  if (h->P.amr.on) return fail("lart_gpu_sightline_tau: sight-line maps of an octree stay with the Fortran host");
   if (h->P.zonly) return fail("lart_gpu_sightline_tau: not defined for the xy-periodic slab");
   if (h->P.bcxy) return fail("lart_gpu_sightline_tau: not defined for folded or periodic grids");
   if (!(cross0 > 0.0)) return fail("lart_gpu_sightline_tau: cross0 must be > 0");

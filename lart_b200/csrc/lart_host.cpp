@@ -71,6 +71,7 @@ struct Par {
   double atau3 = 0.0;
   double Vexp = 0.0, Vx = 0.0, Vy = 0.0, Vz = 0.0, rpeak = 0.0, Vrot = 0.0, rinner = 0.0;
   // clump medium — define.f90:326-352
+  bool use_amr_grid = false;  // define.f90: par%use_amr_grid (leaf data handed over with lart_host_set_amr_leaves)
   bool use_clump_medium = false, clump_fully_inside = true, clump_allow_overlap = false;
   double clump_radius = -1.0, clump_N_clumps = -1.0, clump_f_vol = -1.0, clump_f_cov = -1.0, clump_tau0 = -1.0,
          clump_NHI = -1.0, clump_sigma_v = 0.0;
@@ -130,6 +131,12 @@ struct lart_host_model {
   std::vector<double> cl_x, cl_y, cl_z, cl_vx, cl_vy, cl_vz, cl_radius, cl_rhokap, cl_rhokapD, cl_voigt_a, cl_Dfreq;
   std::vector<int32_t> cg_start, cg_list;
   std::vector<double> steradian_pix;
+  // octree (octree_mod.f90:19-138): leaf input as the generic reader returns it, then the flat tree + leaf physics
+  std::vector<double> in_x, in_y, in_z, in_nH, in_T, in_vx, in_vy, in_vz;
+  std::vector<int32_t> in_level;
+  double amr_boxlen = 0.0, amr_ox = 0.0, amr_oy = 0.0, amr_oz = 0.0;
+  std::vector<int32_t> a_parent, a_children, a_level, a_ileaf, a_icell_of_leaf, a_neighbor;
+  std::vector<double> a_cx, a_cy, a_cz, a_ch, a_rhokap, a_voigt_a, a_Dfreq, a_vfx, a_vfy, a_vfz, a_rhokapD;
   lart_config cfg{};
   lart_host_summary sum{};
   double dwave = 0.0;
@@ -782,6 +789,231 @@ int grid_create(lart_host_model *m) {
 }
 
 // observer_create_outside — observer_rect.f90:10-300
+// ---------------------------------------------------------------------------
+// grid_create_amr — grid_mod_amr.f90:34-526 for leaf data in the generic format (the file reader itself,
+// read_generic_amr.f90, stays the reference's: the leaves arrive through lart_host_set_amr_leaves).
+//   amr_build_tree      octree_mod.f90:470-575   insertion of the leaves in input order, internal nodes created on demand
+//   amr_build_neighbors octree_mod.f90:619-683   same-level face neighbours, ancestors struck out
+//   leaf physics        grid_mod_amr.f90:198-300 (full_neutral / global_dgr defaults, analytic velocity types refused)
+//   tau normalisation   grid_mod_amr.f90:343-430 (pole traversal from the root centre along +z)
+//   frequency grid      grid_mod_amr.f90:726-790 ;  global core-skip :462-473
+// ---------------------------------------------------------------------------
+int amr_find_cell_at_level(const lart_host_model *m, double x, double y, double z, int target_level, double xmin, double xmax,
+                           double ymin, double ymax, double zmin, double zmax) {  // octree_mod.f90:833-853
+  if (x < xmin || x > xmax || y < ymin || y > ymax || z < zmin || z > zmax) return 0;
+  int icell = 1;
+  for (;;) {
+    if (m->a_level[icell - 1] >= target_level) return icell;
+    if (m->a_ileaf[icell - 1] > 0) return icell;
+    int ioct = 1;
+    if (x >= m->a_cx[icell - 1]) ioct += 1;
+    if (y >= m->a_cy[icell - 1]) ioct += 2;
+    if (z >= m->a_cz[icell - 1]) ioct += 4;
+    int child = m->a_children[8 * (size_t)(icell - 1) + ioct - 1];
+    if (child == 0) return icell;
+    icell = child;
+  }
+}
+int amr_find_leaf_host(const lart_host_model *m, double x, double y, double z, const lart_grid &g) {  // octree_mod.f90:149-171
+  if (x < g.xmin || x > g.xmax || y < g.ymin || y > g.ymax || z < g.zmin || z > g.zmax) return 0;
+  int icell = 1;
+  for (;;) {
+    if (m->a_ileaf[icell - 1] > 0) return m->a_ileaf[icell - 1];
+    int ioct = 1;
+    if (x >= m->a_cx[icell - 1]) ioct += 1;
+    if (y >= m->a_cy[icell - 1]) ioct += 2;
+    if (z >= m->a_cz[icell - 1]) ioct += 4;
+    icell = m->a_children[8 * (size_t)(icell - 1) + ioct - 1];
+    if (icell == 0) return 0;
+  }
+}
+
+int amr_create(lart_host_model *m) {
+  Par &p = m->par;
+  const Line &ln = m->line;
+  const size_t nleaf = m->in_x.size();
+  if (nleaf == 0) { g_err = "par%use_amr_grid: no leaf data (lart_host_set_amr_leaves)"; return 1; }
+  if (p.xy_periodic || p.xyz_symmetry || p.xy_symmetry) { g_err = "AMR: periodic / mirror boundaries stay with the Fortran host"; return 1; }
+  if (!p.velocity_type.empty()) { g_err = "AMR: analytic velocity types stay with the Fortran host (velocities come with the leaves)"; return 1; }
+  if (!(p.distance2cm > 0.0)) { p.distance_unit = ""; p.distance2cm = 1.0; }  // no par%distance_unit: code units
+  const double L = m->amr_boxlen;
+  const double xmin = m->amr_ox, xmax = m->amr_ox + L, ymin = m->amr_oy, ymax = m->amr_oy + L, zmin = m->amr_oz, zmax = m->amr_oz + L;
+  // ---- amr_build_tree
+  auto &par_ = m->a_parent; auto &chi = m->a_children; auto &lev = m->a_level; auto &ile = m->a_ileaf;
+  auto &cx = m->a_cx; auto &cy = m->a_cy; auto &cz = m->a_cz; auto &ch = m->a_ch;
+  par_.assign(1, 0); chi.assign(8, 0); lev.assign(1, 0); ile.assign(1, 0);
+  cx.assign(1, (xmin + xmax) * 0.5); cy.assign(1, (ymin + ymax) * 0.5); cz.assign(1, (zmin + zmax) * 0.5); ch.assign(1, (xmax - xmin) * 0.5);
+  m->a_icell_of_leaf.assign(nleaf, 0);
+  for (size_t il = 0; il < nleaf; ++il) {
+    int icell = 1;
+    for (int l = 0; l <= m->in_level[il] - 1; ++l) {
+      int ioct = 1;
+      if (m->in_x[il] >= cx[icell - 1]) ioct += 1;
+      if (m->in_y[il] >= cy[icell - 1]) ioct += 2;
+      if (m->in_z[il] >= cz[icell - 1]) ioct += 4;
+      if (chi[8 * (size_t)(icell - 1) + ioct - 1] == 0) {
+        const int nc = (int)par_.size() + 1;
+        par_.push_back(icell); lev.push_back(l + 1); ile.push_back(0);
+        for (int q = 0; q < 8; ++q) chi.push_back(0);
+        const double h = ch[icell - 1] * 0.5;
+        ch.push_back(h);
+        const int ix = (ioct - 1) % 2, iy = ((ioct - 1) / 2) % 2, iz = (ioct - 1) / 4;
+        cx.push_back(cx[icell - 1] + (double)(2 * ix - 1) * h);
+        cy.push_back(cy[icell - 1] + (double)(2 * iy - 1) * h);
+        cz.push_back(cz[icell - 1] + (double)(2 * iz - 1) * h);
+        chi[8 * (size_t)(icell - 1) + ioct - 1] = nc;
+      }
+      icell = chi[8 * (size_t)(icell - 1) + ioct - 1];
+    }
+    if (ile[icell - 1] != 0 || [&] { for (int q = 0; q < 8; ++q) if (chi[8 * (size_t)(icell - 1) + q]) return true; return false; }()) {
+      g_err = "AMR leaf data: two leaves share a cell, or a leaf sits on an internal cell"; return 1;
+    }
+    ile[icell - 1] = (int32_t)il + 1;
+    m->a_icell_of_leaf[il] = icell;
+  }
+  const int ncells = (int)par_.size();
+  // ---- amr_build_neighbors
+  m->a_neighbor.assign(6 * (size_t)ncells, 0);
+  auto is_ancestor = [&](int anc, int desc) { for (int c = desc; c > 0;) { c = par_[c - 1]; if (c == anc) return true; } return false; };
+  for (int ic = 1; ic <= ncells; ++ic) {
+    const double x = cx[ic - 1], y = cy[ic - 1], z = cz[ic - 1], hp = 2.0 * ch[ic - 1];
+    const int l = lev[ic - 1];
+    int32_t *nb = &m->a_neighbor[6 * (size_t)(ic - 1)];
+    auto at = [&](double qx, double qy, double qz) { return amr_find_cell_at_level(m, qx, qy, qz, l, xmin, xmax, ymin, ymax, zmin, zmax); };
+    if (x + hp <= xmax) nb[0] = at(x + hp, y, z);
+    if (x - hp >= xmin) nb[1] = at(x - hp, y, z);
+    if (y + hp <= ymax) nb[2] = at(x, y + hp, z);
+    if (y - hp >= ymin) nb[3] = at(x, y - hp, z);
+    if (z + hp <= zmax) nb[4] = at(x, y, z + hp);
+    if (z - hp >= zmin) nb[5] = at(x, y, z - hp);
+    for (int f = 0; f < 6; ++f) if (nb[f] > 0 && nb[f] != ic && is_ancestor(nb[f], ic)) nb[f] = 0;
+  }
+  // ---- leaf physics
+  const double Dfreq_ref = m->vtherm_total(p.temperature) / (ln.wavelength0 * kUm2Km);
+  const double voigt_amean = (ln.damping / kFourPi) / Dfreq_ref;
+  const bool dust = p.DGR > 0.0;
+  m->a_rhokap.assign(nleaf, 0.0); m->a_voigt_a.assign(nleaf, 0.0); m->a_Dfreq.assign(nleaf, 0.0);
+  m->a_vfx.assign(nleaf, 0.0); m->a_vfy.assign(nleaf, 0.0); m->a_vfz.assign(nleaf, 0.0);
+  if (dust) m->a_rhokapD.assign(nleaf, 0.0); else m->a_rhokapD.clear();
+  for (size_t il = 0; il < nleaf; ++il) {
+    const double T = std::max(m->in_T[il], 10.0);
+    const double vth = m->vtherm_total(T);
+    m->a_Dfreq[il] = vth / (ln.wavelength0 * kUm2Km);
+    m->a_voigt_a[il] = (ln.damping / kFourPi) / m->a_Dfreq[il];
+    m->a_rhokap[il] = m->in_nH[il] * ln.cross0 / m->a_Dfreq[il] * p.distance2cm;  // full_neutral: nHI_frac = 1
+    if (dust) m->a_rhokapD[il] = m->in_nH[il] * p.cext_dust * p.DGR * p.distance2cm;
+    m->a_vfx[il] = m->in_vx[il] / vth; m->a_vfy[il] = m->in_vy[il] / vth; m->a_vfz[il] = m->in_vz[il] / vth;
+  }
+  lart_grid &g = m->cfg.grid;
+  g = lart_grid{};
+  g.xmin = xmin; g.xmax = xmax; g.ymin = ymin; g.ymax = ymax; g.zmin = zmin; g.zmax = zmax;
+  // ---- tauhomo and the pole traversal (from the root centre along +z; gaps are crossed with the gap cell's geometry)
+  auto voigt0 = [](double a) { return 1.0 + a * (-1.1283791671e+00 + a * 1.0); };  // voigt(0,a), as in grid_create
+  double opacity_sum = 0.0, nopac = 0.0;
+  for (size_t il = 0; il < nleaf; ++il) { opacity_sum += m->a_rhokap[il] * voigt0(m->a_voigt_a[il]); if (m->a_rhokap[il] > 0.0) nopac += 1.0; }
+  const double opac_length = L / 2.0;
+  double tauhomo = nopac > 0.0 ? (opacity_sum / nopac) * opac_length : 0.0;
+  double NHI_pole_raw = 0.0, tau_raw_half = 0.0;
+  {
+    double xc = cx[0], yc = cy[0], zc = cz[0];
+    for (long niter = 0; niter < 10000000 && zc < zmax; ++niter) {
+      const int il = amr_find_leaf_host(m, xc, yc, zc, g);
+      int icell;
+      if (il > 0) icell = m->a_icell_of_leaf[il - 1];
+      else {  // amr_find_enclosing_cell, octree_mod.f90:211-237
+        if (xc < xmin || xc > xmax || yc < ymin || yc > ymax || zc < zmin || zc > zmax) break;
+        icell = 1;
+        for (;;) {
+          if (ile[icell - 1] > 0) break;
+          int ioct = 1;
+          if (xc >= cx[icell - 1]) ioct += 1;
+          if (yc >= cy[icell - 1]) ioct += 2;
+          if (zc >= cz[icell - 1]) ioct += 4;
+          const int child = chi[8 * (size_t)(icell - 1) + ioct - 1];
+          if (child == 0) break;
+          icell = child;
+        }
+      }
+      const double t_exit = (cz[icell - 1] + ch[icell - 1] - zc) / 1.0;  // amr_cell_exit / amr_gap_exit with k = (0,0,1)
+      if (il > 0) {
+        tau_raw_half += m->a_rhokap[il - 1] * voigt0(m->a_voigt_a[il - 1]) * t_exit;
+        NHI_pole_raw += m->a_rhokap[il - 1] * m->a_Dfreq[il - 1] / ln.cross0 * t_exit;
+      }
+      zc = zc + t_exit;
+    }
+  }
+  double taupole = tau_raw_half > 0.0 ? tau_raw_half : tauhomo;
+  double opac_norm = 1.0;
+  if (p.taumax > 0.0) { if (taupole > 0.0) opac_norm = p.taumax / taupole; }
+  else if (p.N_HImax > 0.0) { if (NHI_pole_raw > 0.0) opac_norm = p.N_HImax / NHI_pole_raw; }
+  else if (p.N_gasmax > 0.0) { if (NHI_pole_raw > 0.0) opac_norm = p.N_gasmax / NHI_pole_raw; }
+  if (opac_norm != 1.0) {
+    for (auto &v : m->a_rhokap) v *= opac_norm;
+    for (auto &v : m->a_rhokapD) v *= opac_norm;
+  }
+  opacity_sum = 0.0;
+  for (size_t il = 0; il < nleaf; ++il) opacity_sum += m->a_rhokap[il] * voigt0(m->a_voigt_a[il]);
+  if (nopac > 0.0) tauhomo = (opacity_sum / nopac) * opac_length;
+  taupole = p.taumax > 0.0 ? p.taumax : tauhomo;
+  const double N_HIpole = NHI_pole_raw * opac_norm;
+  if (p.N_HImax <= 0.0) p.N_HImax = N_HIpole;
+  if (p.N_gasmax <= 0.0) p.N_gasmax = N_HIpole;
+  p.tauhomo = tauhomo; p.taumax = taupole;
+  // ---- global core skip (:462-473) and the frequency grid (amr_setup_freq_grid)
+  const double atau0 = voigt_amean * p.tauhomo;
+  const double atau0_cell = atau0 / (L / (2.0 * ch[0]));
+  double xcrit = 0.0, xcrit2 = 0.0;
+  if (atau0_cell > 1.0) {
+    const double xi = atau0_cell <= 60.0 ? 0.6 : 1.4, chi_ = atau0_cell <= 60.0 ? 1.2 : 0.6;
+    xcrit = 0.02 * std::exp(xi * std::pow(std::log(atau0_cell), chi_));
+    xcrit2 = xcrit * xcrit;
+  }
+  const double vtherm = m->vtherm_total(p.temperature);
+  if (isfin(p.velocity_min) && isfin(p.velocity_max)) {
+    if (p.nvelocity == 0 && p.nxfreq > 0) p.nvelocity = p.nxfreq;
+    if (p.nvelocity > 0) p.nxfreq = p.nvelocity;
+    p.xfreq_min = -p.velocity_max / vtherm; p.xfreq_max = -p.velocity_min / vtherm;
+  }
+  const double atau1 = std::pow(voigt_amean * p.tauhomo, 1.0 / 3.0);
+  p.atau3 = atau1;
+  if (!(isfin(p.xfreq_max) && isfin(p.xfreq_min))) {
+    double xscale = (p.taumax <= 5e1) ? 25.0 : (p.taumax <= 5e2) ? 14.0 : (p.taumax <= 5e3) ? 10.0 : 5.0;
+    const double hk = ln.DnuHK_Hz / Dfreq_ref;
+    if (p.Vexp == 0.0) { p.xfreq_max = std::floor(xscale * atau1) + 1.0; p.xfreq_min = -(std::floor(xscale * atau1 + hk) + 1.0); }
+    else if (p.Vexp > 0.0) { p.xfreq_max = std::floor(xscale * atau1) + 1.0; p.xfreq_min = -(std::floor(xscale * atau1 + std::fabs(p.Vexp) / vtherm + hk) + 1.0); }
+    else { p.xfreq_max = std::floor(xscale * atau1 + std::fabs(p.Vexp) / vtherm) + 1.0; p.xfreq_min = -(std::floor(xscale * atau1 + hk) + 1.0); }
+    if (p.spectral_type == "continuum") {
+      xscale = 4.0 * xscale;
+      p.xfreq_max = std::floor(xscale * atau1 + std::fabs(p.Vexp) / vtherm) + 1.0;
+      p.xfreq_min = -(std::floor(xscale * atau1 + std::fabs(p.Vexp) / vtherm + hk) + 1.0);
+    }
+  }
+  const double dxfreq = (p.xfreq_max - p.xfreq_min) / p.nxfreq;
+  m->dwave = vtherm / kSpeedC * (ln.wavelength0 * 1e4) * dxfreq;
+  // 'sphere' geometry: rmax = L_box/2 (:177-180); the host's box members follow the octree (amr_sync_to_grid, :1017-1058)
+  if (p.geometry == "sphere" || p.rmax > 0.0) p.rmax = L * 0.5;
+  p.xmax = xmax; p.ymax = ymax; p.zmax = zmax;
+  g.nx = g.ny = g.nz = 1; g.nxfreq = p.nxfreq;
+  g.dx = g.dy = g.dz = L;
+  g.Dfreq_ref = Dfreq_ref; g.xfreq_min = p.xfreq_min; g.xfreq_max = p.xfreq_max; g.dxfreq = dxfreq;
+  g.xcrit = xcrit; g.xcrit2 = xcrit2; g.rmax = p.rmax;
+  lart_amr &a = m->cfg.amr;
+  a.ncells = ncells; a.nleaf = (int32_t)nleaf;
+  a.children = chi.data(); a.ileaf = ile.data(); a.icell_of_leaf = m->a_icell_of_leaf.data(); a.neighbor = m->a_neighbor.data();
+  a.cx = cx.data(); a.cy = cy.data(); a.cz = cz.data(); a.ch = ch.data();
+  a.rhokap = m->a_rhokap.data(); a.voigt_a = m->a_voigt_a.data(); a.Dfreq = m->a_Dfreq.data();
+  a.vfx = m->a_vfx.data(); a.vfy = m->a_vfy.data(); a.vfz = m->a_vfz.data();
+  a.rhokapD = dust ? m->a_rhokapD.data() : nullptr;
+  lart_host_summary &su = m->sum;
+  su.voigt_a = voigt_amean; su.temperature = p.temperature; su.N_gaspole = N_HIpole; su.N_gashomo = N_HIpole;
+  su.taupole = taupole; su.tauhomo = tauhomo; su.taupole_dust = 0.0; su.tauhomo_dust = 0.0;
+  su.Dfreq_ref = Dfreq_ref; su.vtherm = vtherm; su.cross0 = ln.cross0; su.atau3 = atau1;
+  su.xfreq_min = p.xfreq_min; su.xfreq_max = p.xfreq_max; su.dxfreq = dxfreq;
+  su.nx = su.ny = su.nz = 1; su.nxfreq = p.nxfreq; su.nphotons = p.nphotons; su.zonly = 0;
+  su.nclumps = 0;
+  return 0;
+}
+
 int observer_create(lart_host_model *m) {
   Par &p = m->par;
   if (!isfin(p.rotation_center_x)) p.rotation_center_x = 0.0;
@@ -972,11 +1204,32 @@ int lart_host_read_input(lart_host_model *m, const char *path) {
   return 0;
 }
 
+int lart_host_set_amr_leaves(lart_host_model *m, int64_t n, const double *x, const double *y, const double *z, const int32_t *level,
+                             const double *nH, const double *T, const double *vx, const double *vy, const double *vz,
+                             double boxlen, double origin_x, double origin_y, double origin_z) {
+  if (!m || n < 1 || !x || !y || !z || !level || !nH || !T || !(boxlen > 0.0)) { g_err = "lart_host_set_amr_leaves: bad argument"; return 1; }
+  m->is_setup = false;
+  m->in_x.assign(x, x + n); m->in_y.assign(y, y + n); m->in_z.assign(z, z + n); m->in_level.assign(level, level + n);
+  m->in_nH.assign(nH, nH + n); m->in_T.assign(T, T + n);
+  if (vx && vy && vz) { m->in_vx.assign(vx, vx + n); m->in_vy.assign(vy, vy + n); m->in_vz.assign(vz, vz + n); }
+  else { m->in_vx.assign(n, 0.0); m->in_vy.assign(n, 0.0); m->in_vz.assign(n, 0.0); }
+  m->amr_boxlen = boxlen; m->amr_ox = origin_x; m->amr_oy = origin_y; m->amr_oz = origin_z;
+  m->par.use_amr_grid = true;
+  return 0;
+}
+
 int lart_host_setup(lart_host_model *m) {
   if (!m) { g_err = "lart_host_setup: null model"; return 1; }
   if (int rc = derive(m)) return rc;
-  if (int rc = clumps_create(m)) return rc;  // grid_create_clump: the population first (grid_mod_clump.f90:60-80)
-  if (int rc = grid_create(m)) return rc;
+  m->cfg.amr = lart_amr{};
+  if (m->par.use_amr_grid) {
+    if (m->par.use_clump_medium) { g_err = "use_amr_grid and use_clump_medium exclude each other"; return 1; }
+    m->cfg.clumps = lart_clumps{};
+    if (int rc = amr_create(m)) return rc;
+  } else {
+    if (int rc = clumps_create(m)) return rc;  // grid_create_clump: the population first (grid_mod_clump.f90:60-80)
+    if (int rc = grid_create(m)) return rc;
+  }
   Par &p = m->par;
   if (p.use_clump_medium) {  // :93-101 — the box carries no opacity, no bulk velocity, the clumps' Doppler width
     std::fill(m->rhokap.begin(), m->rhokap.end(), 0.0);
@@ -1016,7 +1269,7 @@ int lart_host_setup(lart_host_model *m) {
   q.use_stokes = p.use_stokes; q.use_reduced_wgt = p.use_reduced_wgt;
   q.save_Jin = p.save_Jin; q.save_Jabs = p.save_Jabs; q.save_Jmu = p.save_Jmu;
   q.save_peeloff = p.save_peeloff; q.save_peeloff_2D = p.save_peeloff_2D; q.save_peeloff_3D = p.save_peeloff_3D; q.save_direc0 = p.save_direc0;
-  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.xy_symmetry = p.xy_symmetry; q.use_clump_medium = p.use_clump_medium; q.nobs = p.nobs;
+  q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.xy_symmetry = p.xy_symmetry; q.use_clump_medium = p.use_clump_medium; q.nobs = p.nobs; q.use_amr_grid = p.use_amr_grid;
   const Line &ln = m->line;
   c.line.line_type = ln.line_type; c.line.E1 = ln.E1; c.line.E2 = ln.E2; c.line.E3 = ln.E3;
   c.line.g_recoil0 = ln.g_recoil0; c.line.DnuHK_Hz = ln.DnuHK_Hz;

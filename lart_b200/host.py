@@ -78,6 +78,22 @@ class Model:
         self._check(self._lib.lart_host_read_input(self._m, str(path).encode()))
         return self
 
+    def set_amr_leaves(self, x, y, z, level, nH, T, vx=None, vy=None, vz=None, boxlen=2.0, origin=None):
+        """Leaf cells of an octree in the reference's generic AMR format (what generic_amr_read returns,
+        read_generic_amr.f90:52-346); sets par%use_amr_grid.  origin = lower corner (default: box centred on 0)."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x, y, z, nH = f(x), f(y), f(z), f(nH)
+        T = f(np.broadcast_to(T, x.shape))
+        level = np.ascontiguousarray(level, dtype=np.int32)
+        v = [None if a is None else f(a) for a in (vx, vy, vz)]
+        dp = lambda a: None if a is None else a.ctypes.data_as(capi.c_double_p)
+        o = (-boxlen / 2.0,) * 3 if origin is None else origin
+        self._setup = False
+        self._check(self._lib.lart_host_set_amr_leaves(self._m, x.size, dp(x), dp(y), dp(z), level.ctypes.data_as(capi.c_int32_p),
+                                                       dp(nH), dp(T), dp(v[0]), dp(v[1]), dp(v[2]), float(boxlen),
+                                                       float(o[0]), float(o[1]), float(o[2])))
+        return self
+
     def setup(self):
         self._check(self._lib.lart_host_setup(self._m))
         self._setup = True
@@ -355,6 +371,15 @@ class Simulation:
         self._check(self._lib.lart_gpu_clump_locate_batch(self._h, x.size, dp(x), dp(y), dp(z),
                                                           icl.ctypes.data_as(capi.c_int32_p)))
         return icl
+
+    def amr_locate(self, x, y, z):
+        """amr_find_leaf (octree_mod.f90:149-171): leaf index of every point, 0 = not covered."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x, y, z = map(f, (x, y, z))
+        il = np.zeros(x.size, dtype=np.int32)
+        dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+        self._check(self._lib.lart_gpu_amr_locate_batch(self._h, x.size, dp(x), dp(y), dp(z), il.ctypes.data_as(capi.c_int32_p)))
+        return il
 
     def batch_stats(self):
         """(cells or cell steps walked, kernel ms) of the last sight-line or clump-edge batch call."""

@@ -251,15 +251,18 @@ struct World {
   bool sym = false;  // par%xyz_symmetry: mirror planes at the lower faces (raytrace_car.f90:584-760, 1650-1949)
   int bcxy = 0, bcz = 0;  // BC_* of the x/y axes and of the z axis (setup.f90:952-976)
   const lart_clumps *cl = nullptr;  // par%use_clump_medium (clump_mod.f90)
+  const lart_amr *amr = nullptr;    // par%use_amr_grid (octree_mod.f90): the photon's icell is a LEAF index, jcell = kcell = 1
   inline size_t idx(int i, int j, int k) const {
+    if (amr) return static_cast<size_t>(i > 0 ? i - 1 : 0);  // (a photon outside the octree reads leaf 1, never used)
     return static_cast<size_t>(i - 1) + static_cast<size_t>(g->nx) * (static_cast<size_t>(j - 1) + static_cast<size_t>(g->ny) * static_cast<size_t>(k - 1));
   }
-  inline double rhokap(int i, int j, int k) const { return g->rhokap[idx(i, j, k)]; }
-  inline double rhokapD(int i, int j, int k) const { return g->rhokapD[idx(i, j, k)]; }
-  inline double voigt_a(int i, int j, int k) const { return g->voigt_a[idx(i, j, k)]; }
-  inline double Dfreq(int i, int j, int k) const { return g->Dfreq[idx(i, j, k)]; }
+  inline double rhokap(int i, int j, int k) const { return amr ? amr->rhokap[idx(i, j, k)] : g->rhokap[idx(i, j, k)]; }
+  inline double rhokapD(int i, int j, int k) const { return amr ? amr->rhokapD[idx(i, j, k)] : g->rhokapD[idx(i, j, k)]; }
+  inline double voigt_a(int i, int j, int k) const { return amr ? amr->voigt_a[idx(i, j, k)] : g->voigt_a[idx(i, j, k)]; }
+  inline double Dfreq(int i, int j, int k) const { return amr ? amr->Dfreq[idx(i, j, k)] : g->Dfreq[idx(i, j, k)]; }
   inline double vdotk(int i, int j, int k, double kx, double ky, double kz) const {
     size_t c = idx(i, j, k);
+    if (amr) return amr->vfx[c] * kx + amr->vfy[c] * ky + amr->vfz[c] * kz;
     return g->vfx[c] * kx + g->vfy[c] * ky + g->vfz[c] * kz;
   }
   inline double xface(int i) const { return g->xface[i - 1]; }
@@ -914,11 +917,172 @@ void raytrace_to_tau_clump_overlap(const World &w, Photon &ph, double tau_in, Rn
 }
 
 // the ray tracers the procedure pointers select (setup.f90:806-815; peel_raytrace_to_edge, peelingoff_rect.f90:894-906)
+// ---------------------------------------------------------------------------
+// Octree AMR — octree_mod.f90 / raytrace_amr.f90.  Cells and leaves are 1-based as upstream;
+// face index: 1=+x 2=-x 3=+y 4=-y 5=+z 6=-z.
+// ---------------------------------------------------------------------------
+// amr_find_leaf — octree_mod.f90:149-171
+int amr_find_leaf(const World &w, double x, double y, double z) {
+  const lart_amr &a = *w.amr;
+  const lart_grid &g = *w.g;
+  if (x < g.xmin || x > g.xmax || y < g.ymin || y > g.ymax || z < g.zmin || z > g.zmax) return 0;
+  int icell = 1;
+  for (;;) {
+    if (a.ileaf[icell - 1] > 0) return a.ileaf[icell - 1];
+    int ioct = 1;
+    if (x >= a.cx[icell - 1]) ioct += 1;
+    if (y >= a.cy[icell - 1]) ioct += 2;
+    if (z >= a.cz[icell - 1]) ioct += 4;
+    icell = a.children[8 * static_cast<size_t>(icell - 1) + ioct - 1];
+    if (icell == 0) return 0;
+  }
+}
+// amr_cell_exit — octree_mod.f90:412-458 (minloc: the first minimum wins)
+inline void amr_cell_exit(const lart_amr &a, int icell, double x, double y, double z, double kx, double ky, double kz,
+                          double &t_exit, int &iface) {
+  const double cx = a.cx[icell - 1], cy = a.cy[icell - 1], cz = a.cz[icell - 1], h = a.ch[icell - 1];
+  double t[6] = {kHugest, kHugest, kHugest, kHugest, kHugest, kHugest};
+  if (kx > 0.0) t[0] = (cx + h - x) / kx; else if (kx < 0.0) t[1] = (cx - h - x) / kx;
+  if (ky > 0.0) t[2] = (cy + h - y) / ky; else if (ky < 0.0) t[3] = (cy - h - y) / ky;
+  if (kz > 0.0) t[4] = (cz + h - z) / kz; else if (kz < 0.0) t[5] = (cz - h - z) / kz;
+  iface = 1;
+  for (int q = 1; q < 6; ++q) if (t[q] < t[iface - 1]) iface = q + 1;
+  t_exit = t[iface - 1];
+}
+// amr_next_leaf — octree_mod.f90:717-757: neighbour table, then descent with the face-normal octant bit set topologically
+inline int amr_next_leaf(const lart_amr &a, int icell, int iface, double x, double y, double z) {
+  int ineigh = a.neighbor[6 * static_cast<size_t>(icell - 1) + iface - 1];
+  if (ineigh == 0) return 0;
+  while (a.ileaf[ineigh - 1] == 0) {
+    int ioct = 1;
+    const bool bx = x >= a.cx[ineigh - 1], by = y >= a.cy[ineigh - 1], bz = z >= a.cz[ineigh - 1];
+    switch (iface) {
+      case 1: if (by) ioct += 2; if (bz) ioct += 4; break;
+      case 2: ioct += 1; if (by) ioct += 2; if (bz) ioct += 4; break;
+      case 3: if (bx) ioct += 1; if (bz) ioct += 4; break;
+      case 4: if (bx) ioct += 1; ioct += 2; if (bz) ioct += 4; break;
+      case 5: if (bx) ioct += 1; if (by) ioct += 2; break;
+      default: if (bx) ioct += 1; if (by) ioct += 2; ioct += 4; break;
+    }
+    const int child = a.children[8 * static_cast<size_t>(ineigh - 1) + ioct - 1];
+    if (child == 0) break;
+    ineigh = child;
+  }
+  return a.ileaf[ineigh - 1];
+}
+// opacity of leaf il at frequency x (raytrace_amr.f90:114-121, band 1, no H2)
+inline double amr_opacity(const World &w, int il, double xfreq) {
+  double k = w.amr->rhokap[il - 1] * voigt_seon2(xfreq, w.amr->voigt_a[il - 1]);
+  if (w.dust() && w.amr->rhokapD) k = k + w.amr->rhokapD[il - 1];
+  return k;
+}
+// raytrace_to_edge_amr — raytrace_amr.f90:265-351 (open boundaries)
+double raytrace_to_edge_amr(const World &w, const Photon &p0, Counters *cnt, int *nsteps_out = nullptr) {
+  const lart_amr &a = *w.amr;
+  double x = p0.x, y = p0.y, z = p0.z;
+  const double kx = p0.kx, ky = p0.ky, kz = p0.kz;
+  int il = p0.icell, ns = 0;
+  double tau = 0.0;
+  if (nsteps_out) *nsteps_out = 0;
+  if (il <= 0) { il = amr_find_leaf(w, x, y, z); if (il <= 0) return tau; }
+  double u1 = a.vfx[il - 1] * kx + a.vfy[il - 1] * ky + a.vfz[il - 1] * kz;
+  double xfreq_loc = p0.xfreq;
+  for (;;) {
+    const int icell = a.icell_of_leaf[il - 1];
+    double t_exit; int iface;
+    amr_cell_exit(a, icell, x, y, z, kx, ky, kz, t_exit, iface);
+    const double rhokap = amr_opacity(w, il, xfreq_loc);
+    tau = tau + t_exit * rhokap;
+    ++ns;
+    if (tau >= kTauHuge) break;
+    x = x + t_exit * kx; y = y + t_exit * ky; z = z + t_exit * kz;
+    const int il_new = amr_next_leaf(a, icell, iface, x, y, z);
+    if (il_new <= 0) break;
+    const double Df_old = a.Dfreq[il - 1], Df_new = a.Dfreq[il_new - 1];
+    const double u2 = a.vfx[il_new - 1] * kx + a.vfy[il_new - 1] * ky + a.vfz[il_new - 1] * kz;
+    xfreq_loc = (xfreq_loc + u1) * Df_old / Df_new - u2;
+    u1 = u2;
+    il = il_new;
+  }
+  if (cnt) cnt->n_cellsteps += ns;
+  if (nsteps_out) *nsteps_out = ns;
+  return tau;
+}
+// raytrace_to_tau_amr — raytrace_amr.f90:77-259 (band 1, open boundaries)
+void raytrace_to_tau_amr(const World &w, Photon &ph, double tau_in, Tally *tl, Counters *cnt, int *nsteps_out = nullptr) {
+  const lart_amr &a = *w.amr;
+  const lart_grid &g = *w.g;
+  double x = ph.x, y = ph.y, z = ph.z;
+  const double kx = ph.kx, ky = ph.ky, kz = ph.kz;
+  int il = ph.icell, ns = 0;
+  if (nsteps_out) *nsteps_out = 0;
+  if (il <= 0) {
+    il = amr_find_leaf(w, x, y, z);
+    if (il <= 0) { ph.inside = false; return; }
+  }
+  double tau = 0.0;
+  double u1 = a.vfx[il - 1] * kx + a.vfy[il - 1] * ky + a.vfz[il - 1] * kz;
+  while (ph.inside) {
+    const int icell = a.icell_of_leaf[il - 1];
+    double t_exit; int iface;
+    amr_cell_exit(a, icell, x, y, z, kx, ky, kz, t_exit, iface);
+    const double rhokap = amr_opacity(w, il, ph.xfreq);
+    ++ns;
+    if (tau + t_exit * rhokap >= tau_in) {
+      const double d_step = (rhokap > 0.0) ? (tau_in - tau) / rhokap : t_exit;
+      x = x + d_step * kx; y = y + d_step * ky; z = z + d_step * kz;
+      tau = tau_in;
+      break;
+    }
+    tau = tau + t_exit * rhokap;
+    x = x + t_exit * kx; y = y + t_exit * ky; z = z + t_exit * kz;
+    const int il_new = amr_next_leaf(a, icell, iface, x, y, z);
+    if (il_new <= 0) { ph.inside = false; break; }
+    const double Df_old = a.Dfreq[il - 1], Df_new = a.Dfreq[il_new - 1];
+    const double u2 = a.vfx[il_new - 1] * kx + a.vfy[il_new - 1] * ky + a.vfz[il_new - 1] * kz;
+    ph.xfreq = (ph.xfreq + u1) * Df_old / Df_new - u2;
+    u1 = u2;
+    il = il_new;
+  }
+  ph.x = x; ph.y = y; ph.z = z;
+  ph.icell = il; ph.jcell = 1; ph.kcell = 1;
+  if (cnt) cnt->n_cellsteps += ns;
+  if (nsteps_out) *nsteps_out = ns;
+  if (!ph.inside) {  // :226-237 — lab frame, reference Doppler units, Jout (+ Jmu)
+    u1 = a.vfx[il - 1] * kx + a.vfy[il - 1] * ky + a.vfz[il - 1] * kz;
+    ph.xfreq = ph.xfreq + u1;
+    const double xfreq_ref = ph.xfreq * (a.Dfreq[il - 1] / g.Dfreq_ref);
+    ph.xfreq_ref = xfreq_ref;
+    if (tl) {
+      const int ix = static_cast<int>(std::floor((xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
+      if (ix >= 1 && ix <= g.nxfreq) {
+        tl->Jout[ix - 1] += ph.wgt;
+        if (w.par->save_Jmu) tl->Jmu[(ix - 1) + static_cast<size_t>(g.nxfreq) * (jmu_bin(*w.par, ph.kz) - 1)] += ph.wgt;
+      }
+    }
+  }
+}
+// amr_xcrit_local — octree_mod.f90:248-284
+void amr_xcrit_local(const World &w, int il, double x, double y, double z, double &xc, double &xc2) {
+  if (w.par->core_skip_global) { xc = w.g->xcrit; xc2 = w.g->xcrit2; return; }
+  xc = 0.0; xc2 = 0.0;
+  if (il <= 0) return;
+  const lart_amr &a = *w.amr;
+  const int icell = a.icell_of_leaf[il - 1];
+  const double h = a.ch[icell - 1];
+  const double dl = std::min(h - std::fabs(x - a.cx[icell - 1]), std::min(h - std::fabs(y - a.cy[icell - 1]), h - std::fabs(z - a.cz[icell - 1])));
+  if (dl <= 0.0) return;
+  const double atau = a.voigt_a[il - 1] * a.rhokap[il - 1] * dl;
+  if (atau > 1.0) { xc = std::pow(atau, 1.0 / 3.0) / 5.0; xc2 = xc * xc; }
+}
+
 inline double edge_tau(const World &w, const Photon &p, Counters *cnt) {
+  if (w.amr) return raytrace_to_edge_amr(w, p, cnt);
   if (w.cl) return w.cl->has_overlap ? raytrace_to_edge_clump_overlap(w, p, -1.0, cnt) : raytrace_to_edge_clump(w, p, -1.0, cnt);
   return raytrace_to_edge(w, p, cnt);
 }
 inline double peel_tau(const World &w, const Photon &p, Counters *cnt) {
+  if (w.amr) return raytrace_to_edge_amr(w, p, cnt);
   if (w.cl) return w.cl->has_overlap ? raytrace_to_edge_clump_overlap(w, p, kTauHugeClump, cnt)
                                      : raytrace_to_edge_clump(w, p, kTauHugeClump, cnt);
   return raytrace_to_edge(w, p, cnt);
@@ -1055,6 +1219,7 @@ double interp_eq(const double *x, const double *y, int n, double xnew) {
 
 // car_xcrit_local — grid_mod_car.f90:1598-1629
 void car_xcrit_local(const World &w, int i, int j, int k, double x, double y, double z, double &xc, double &xc2) {
+  if (w.amr) { amr_xcrit_local(w, i, x, y, z, xc, xc2); return; }
   const lart_grid &g = *w.g;
   if (w.par->core_skip_global) {
     xc = g.xcrit;
@@ -1588,6 +1753,9 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
   double phi = kTwoPi * up;
   double cosp = std::cos(phi), sinp = std::sin(phi);
   ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
+  if (w.amr) {  // generate_photon.f90:375-376
+    ph.icell = amr_find_leaf(w, ph.x, ph.y, ph.z); ph.jcell = 1; ph.kcell = 1;
+  } else {
   ph.icell = static_cast<int>(std::floor((ph.x - g.xmin) / g.dx)) + 1;
   ph.jcell = static_cast<int>(std::floor((ph.y - g.ymin) / g.dy)) + 1;
   ph.kcell = static_cast<int>(std::floor((ph.z - g.zmin) / g.dz)) + 1;
@@ -1597,6 +1765,7 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
   if (ph.kx > 0.0 && ph.icell < 1) ph.icell = 1;
   if (ph.ky > 0.0 && ph.jcell < 1) ph.jcell = 1;
   if (ph.kz > 0.0 && ph.kcell < 1) ph.kcell = 1;
+  }
   if (par.use_stokes) {
     ph.mx = cost * cosp; ph.my = cost * sinp; ph.mz = -sint;
     ph.nx = -sinp; ph.ny = cosp; ph.nz = 0.0;
@@ -1728,6 +1897,7 @@ void run_photon(const World &w, int64_t id, Rng &r, Tally &tl, int64_t max_event
     }
     if (w.cl && w.cl->has_overlap) raytrace_to_tau_clump_overlap(w, ph, tau, r, &tl, &tl.cnt);
     else if (w.cl) raytrace_to_tau_clump(w, ph, tau, &tl, &tl.cnt);
+    else if (w.amr) raytrace_to_tau_amr(w, ph, tau, &tl, &tl.cnt);
     else raytrace_to_tau(w, ph, tau, &tl, &tl.cnt);
     if (ph.inside) {
       scattering(w, ph, r, tl);
@@ -1863,6 +2033,7 @@ World make_world(const lart_config *cfg) {
   else if (cfg->par.xy_symmetry) w.bcxy = 1;                                  // :955-957
   else if (cfg->par.xy_periodic && !w.zonly) w.bcxy = 2;                      // :966-975 (no shear)
   if (cfg->par.use_clump_medium && cfg->clumps.n > 0) w.cl = &cfg->clumps;    // :806-860
+  if (cfg->par.use_amr_grid && cfg->amr.nleaf > 0) w.amr = &cfg->amr;         // the octree ray tracers and leaf physics
   return w;
 }
 
@@ -1948,6 +2119,43 @@ int oracle_clump_locate(const lart_config *cfg, int64_t n, const double *x, cons
   World w = make_world(cfg);
   if (!w.cl) { g_err = "oracle_clump_locate: no clump medium"; return 1; }
   for (int64_t i = 0; i < n; ++i) icl[i] = static_cast<int32_t>(clump_at_point(*w.cl, x[i], y[i], z[i]));
+  return 0;
+}
+
+// octree: raytrace_to_edge_amr / raytrace_to_tau_amr / amr_find_leaf on arrays (il = leaf index, <= 0: locate first)
+int oracle_amr_edge(const lart_config *cfg, int64_t n, const double *x, const double *y, const double *z, const double *kx,
+                    const double *ky, const double *kz, const double *xfreq, const int32_t *il, double *tau, int32_t *nsteps) {
+  World w = make_world(cfg);
+  if (!w.amr) { g_err = "oracle_amr_edge: no octree in the configuration"; return 1; }
+  for (int64_t i = 0; i < n; ++i) {
+    Photon p;
+    p.x = x[i]; p.y = y[i]; p.z = z[i]; p.kx = kx[i]; p.ky = ky[i]; p.kz = kz[i]; p.xfreq = xfreq[i]; p.icell = il[i];
+    int ns = 0;
+    tau[i] = raytrace_to_edge_amr(w, p, nullptr, &ns);
+    if (nsteps) nsteps[i] = ns;
+  }
+  return 0;
+}
+int oracle_amr_tau(const lart_config *cfg, int64_t n, double *x, double *y, double *z, const double *kx, const double *ky,
+                   const double *kz, double *xfreq, int32_t *il, const double *tau_in, int32_t *inside, double *xfreq_ref,
+                   int32_t *nsteps) {
+  World w = make_world(cfg);
+  if (!w.amr) { g_err = "oracle_amr_tau: no octree in the configuration"; return 1; }
+  for (int64_t i = 0; i < n; ++i) {
+    Photon p;
+    p.x = x[i]; p.y = y[i]; p.z = z[i]; p.kx = kx[i]; p.ky = ky[i]; p.kz = kz[i]; p.xfreq = xfreq[i]; p.icell = il[i];
+    int ns = 0;
+    raytrace_to_tau_amr(w, p, tau_in[i], nullptr, nullptr, &ns);
+    x[i] = p.x; y[i] = p.y; z[i] = p.z; xfreq[i] = p.xfreq; il[i] = p.icell; inside[i] = p.inside ? 1 : 0;
+    if (xfreq_ref) xfreq_ref[i] = p.xfreq_ref;
+    if (nsteps) nsteps[i] = ns;
+  }
+  return 0;
+}
+int oracle_amr_locate(const lart_config *cfg, int64_t n, const double *x, const double *y, const double *z, int32_t *il) {
+  World w = make_world(cfg);
+  if (!w.amr) { g_err = "oracle_amr_locate: no octree in the configuration"; return 1; }
+  for (int64_t i = 0; i < n; ++i) il[i] = amr_find_leaf(w, x[i], y[i], z[i]);
   return 0;
 }
 

@@ -82,6 +82,9 @@ def load():
         lib.oracle_clump_edge.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip, C.c_double, dp, ip]
         lib.oracle_clump_tau.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip, dp, ip]
         lib.oracle_clump_locate.argtypes = [cfgp, C.c_int64] + [dp] * 3 + [ip]
+        lib.oracle_amr_edge.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip, dp, ip]
+        lib.oracle_amr_tau.argtypes = [cfgp, C.c_int64] + [dp] * 7 + [ip, dp, ip, dp, ip]
+        lib.oracle_amr_locate.argtypes = [cfgp, C.c_int64] + [dp] * 3 + [ip]
         _LIB = lib
     return _LIB
 
@@ -240,3 +243,34 @@ def sightline_tau(model):
     steps = C.c_double()
     _check(load().oracle_sightline_tau(model.config, model.summary.cross0, outs, C.byref(steps)))
     return maps, steps.value
+
+
+# ---- octree AMR, unit level (raytrace_amr.f90 / octree_mod.f90) ----------------------------------------------------
+def amr_edge(cfg, x, y, z, kx, ky, kz, xfreq, il):
+    """raytrace_to_edge_amr; returns (tau, cells crossed)."""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x, y, z, kx, ky, kz, xfreq = map(f, (x, y, z, kx, ky, kz, xfreq))
+    il = np.ascontiguousarray(il, dtype=np.int32)
+    tau, ns = np.zeros(x.size), np.zeros(x.size, dtype=np.int32)
+    _check(load().oracle_amr_edge(cfg, x.size, _d(x), _d(y), _d(z), _d(kx), _d(ky), _d(kz), _d(xfreq), _i(il), _d(tau), _i(ns)))
+    return tau, ns
+
+
+def amr_tau(cfg, x, y, z, kx, ky, kz, xfreq, il, tau_in):
+    """raytrace_to_tau_amr on copies; returns the updated photon state."""
+    f = lambda a: np.array(a, dtype=np.float64, copy=True)
+    x, y, z, kx, ky, kz, xfreq, tau_in = map(f, (x, y, z, kx, ky, kz, xfreq, tau_in))
+    il = np.array(il, dtype=np.int32, copy=True)
+    n = x.size
+    inside, ns, xref = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros(n)
+    _check(load().oracle_amr_tau(cfg, n, _d(x), _d(y), _d(z), _d(kx), _d(ky), _d(kz), _d(xfreq), _i(il), _d(tau_in), _i(inside),
+                                 _d(xref), _i(ns)))
+    return dict(x=x, y=y, z=z, xfreq=xfreq, il=il, inside=inside, xfreq_ref=xref, nsteps=ns)
+
+
+def amr_locate(cfg, x, y, z):
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x, y, z = map(f, (x, y, z))
+    il = np.zeros(x.size, dtype=np.int32)
+    _check(load().oracle_amr_locate(cfg, x.size, _d(x), _d(y), _d(z), _i(il)))
+    return il

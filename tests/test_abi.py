@@ -38,7 +38,7 @@ def test_struct_sizes_match_the_header():
 #include <stdio.h>
 #include "lart_gpu.h"
 #include "lart_host.h"
-int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(lart_clumps), sizeof(lart_grid), sizeof(lart_params), sizeof(lart_line),
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(lart_amr), sizeof(lart_clumps), sizeof(lart_grid), sizeof(lart_params), sizeof(lart_line),
   sizeof(lart_observer), sizeof(lart_scatt_mat), sizeof(lart_config), sizeof(lart_observer_out), sizeof(lart_allph_out),
   sizeof(lart_counters), sizeof(lart_tallies), sizeof(lart_host_summary)); return 0; }
 '''
@@ -48,7 +48,7 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", size
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
         sizes = list(map(int, subprocess.check_output([exe]).split()))
-    mirrors = [capi.Clumps, capi.Grid, capi.Params, capi.Line, capi.Observer, capi.ScattMat, capi.Config, capi.ObserverOut,
+    mirrors = [capi.Amr, capi.Clumps, capi.Grid, capi.Params, capi.Line, capi.Observer, capi.ScattMat, capi.Config, capi.ObserverOut,
                capi.AllphOut, capi.Counters, capi.Tallies, capi.HostSummary]
     assert sizes == [ctypes.sizeof(t) for t in mirrors]
 

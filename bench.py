@@ -59,6 +59,13 @@ WORKLOADS = {
                                geometry="sphere", velocity_type="rotating_galaxy_halo", Vrot=300.0, rinner=0.1, nxfreq=500,
                                velocity_min=-1000.0, velocity_max=1000.0, nx=11, ny=11, nz=11, save_Jmu=True, nmu=101,
                                nxim=129, nyim=129, distance=1e4),
+    # BASELINE configs[4]: examples/amr_sphere_generic (sphere_amr_inside_test1M.in / log_amr_1M.txt): octree sphere of 178 480
+    # leaves (levels 3-7, the leaf list written by the reference's own generator: tests/golden/amr_sphere_l37.npz), T = 1e4 K,
+    # tau_pole = 1e4, with an outside observer's peel cube instead of the HEALPix inside observer
+    "amr_sphere_tau1e4": dict(amr="amr_sphere_l37", temperature=1e4, taumax=1e4, geometry="sphere", use_stokes=True, nxfreq=121,
+                              nxim=100, nyim=100, distance=1e2),
+    "amr_sphere_tau1e7": dict(amr="amr_sphere_l37", temperature=1e4, taumax=1e7, geometry="sphere", use_stokes=True, nxfreq=201,
+                              nxim=129, nyim=129, distance=1e2),
     # small case for smoke-testing the bench itself
     "tiny": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=61, nxim=33, nyim=33),
 }
@@ -134,15 +141,25 @@ def measured_peaks():
 
 def build_model(args, nphotons, workload=None):
     from lart_b200 import Model
-    return Model(no_photons=nphotons, iseed=args.seed, **WORKLOADS[workload or args.workload]).setup()
+    kw = dict(WORKLOADS[workload or args.workload])
+    fixture = kw.pop("amr", None)
+    m = Model(no_photons=nphotons, iseed=args.seed, **kw)
+    if fixture:  # octree leaves in the reference's generic format (tools/make_amr_fixtures.py)
+        d = np.load(os.path.join(ROOT, "tests", "golden", fixture + ".npz"))
+        lev = d["level"].astype(np.int32)
+        xyz = [-1.0 + (2.0 * d[k] + 1.0) / 2.0 ** lev for k in ("ix", "iy", "iz")]
+        m.set_amr_leaves(xyz[0], xyz[1], xyz[2], lev, d["dens"].astype(np.float64), kw.get("temperature", 1e4), boxlen=float(d["boxlen"]))
+    return m.setup()
 
 
 def workload_config(args, model):
     """`config` of the JSON line: names the workload and nothing else, so that both arms print the same object."""
     cfg = model.config.contents
     g = cfg.grid
-    ncell = g.nx * g.ny * g.nz
-    return {"workload": args.workload, "grid": [g.nx, g.ny, g.nz], "tau0": WORKLOADS[args.workload].get("taumax"),
+    ncell = cfg.amr.nleaf if cfg.par.use_amr_grid else g.nx * g.ny * g.nz
+    amr = cfg.amr
+    return {"workload": args.workload, "grid": [g.nx, g.ny, g.nz] if not cfg.par.use_amr_grid else {"octree_leaves": amr.nleaf, "cells": amr.ncells},
+            "tau0": WORKLOADS[args.workload].get("taumax"),
             "peel_cube": [g.nxfreq, cfg.observers[0].nxim, cfg.observers[0].nyim] if cfg.par.nobs else None,
             "quantum": args.quantum, "seed": args.seed,
             "step": "every photon in flight advances by `quantum` scatterings (bounded sample of the workload: a photon needs "
@@ -256,8 +273,9 @@ def run_gpu(args):
     model = build_model(args, nph)
     cfg = model.config.contents
     g = cfg.grid
-    ncell = g.nx * g.ny * g.nz
-    grid_bytes = 8 * (6 * ncell + (g.nx + g.ny + g.nz + 3))
+    ncell = cfg.amr.nleaf if cfg.par.use_amr_grid else g.nx * g.ny * g.nz
+    grid_bytes = 8 * (6 * ncell + (g.nx + g.ny + g.nz + 3)) if not cfg.par.use_amr_grid else \
+        8 * 6 * cfg.amr.nleaf + cfg.amr.ncells * (4 * 8 + 4 * 15) + 4 * cfg.amr.nleaf
 
     # ------------------------- device-resident arm: `value`  (CUDA-graph launches, no per-stage events)
     first, count, stride = rank + 1, nph // world, world  # run_simulation_mod.f90:150 partition

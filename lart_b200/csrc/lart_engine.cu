@@ -617,8 +617,13 @@ __device__ __forceinline__ void ray_append(const DevParams &P, const Queues &q, 
 
 // stage 1: refill dead slots from the job queue
 __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q) {
-  // nothing to do in most waves of an optically thick run (no photon died, or no photon is left to start): skip the scan
-  if (*q.n_dead == 0u || job->next >= job->count) return;
+  // nothing to do in most waves of an optically thick run (no photon died, or no photon is left to start): skip the scan.
+  // The decision is taken once per block (other blocks change both words while this one reads them, and a block whose warps
+  // disagreed would sum work counters of warps that never wrote them)
+  __shared__ int go;
+  if (threadIdx.x == 0) go = !(*q.n_dead == 0u || job->next >= job->count);
+  __syncthreads();
+  if (!go) return;
   Counters cnt;
   ctr_t nrng = 0;
   for (int s = pl.s0 + blockIdx.x * blockDim.x + threadIdx.x; s < pl.s0 + pl.n; s += gridDim.x * blockDim.x) {

@@ -31,6 +31,7 @@ module lart_gpu_shim
   use clump_mod, only: N_clumps, sphere_R, cl_Dfreq_ref, cl_x, cl_y, cl_z, cl_vx, cl_vy, cl_vz, cl_radius, cl_rhokap, &
                        cl_rhokapD, cl_voigt_a, cl_Dfreq, cgx, cgy, cgz, cg_xmin, cg_ymin, cg_zmin, cg_dx, cg_dy, cg_dz, &
                        cg_start, cg_list, has_overlap
+  use octree_mod, only: amr_grid
   implicit none
   private
   public :: run_gpu
@@ -51,6 +52,7 @@ module lart_gpu_shim
      integer(c_int32_t) :: core_skip, core_skip_global, use_stokes, use_reduced_wgt
      integer(c_int32_t) :: save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D
      integer(c_int32_t) :: save_direc0, save_all_photons, xyz_symmetry, xy_symmetry, use_clump_medium, xy_periodic, nobs
+     integer(c_int32_t) :: use_amr_grid
   end type
   type, bind(C) :: c_lart_line
      integer(c_int32_t) :: line_type, pad_
@@ -72,12 +74,19 @@ module lart_gpu_shim
      real(c_double)     :: cg_xmin, cg_ymin, cg_zmin, cg_dx, cg_dy, cg_dz
      type(c_ptr)        :: cg_start, cg_list
   end type
+  type, bind(C) :: c_lart_amr               ! amr_grid_type, src/octree_mod.f90:19-138
+     integer(c_int32_t) :: ncells, nleaf
+     type(c_ptr)        :: children, ileaf, icell_of_leaf, neighbor
+     type(c_ptr)        :: cx, cy, cz, ch
+     type(c_ptr)        :: rhokap, voigt_a, Dfreq, vfx, vfy, vfz, rhokapD
+  end type
   type, bind(C) :: c_lart_config
      type(c_lart_grid)      :: grid
      type(c_lart_params)    :: par
      type(c_lart_line)      :: line
      type(c_lart_scatt_mat) :: scatt_mat
      type(c_lart_clumps)    :: clumps
+     type(c_lart_amr)       :: amr
      type(c_ptr)            :: observers
      integer(c_int32_t)     :: device, pool_slots, quantum, flags, streams, ray_budget, max_events, pad_
   end type
@@ -237,6 +246,27 @@ contains
        cfg%clumps%cg_start = c_loc(cg_start); cfg%clumps%cg_list = c_loc(cg_list)
     endif
 
+    !--- octree (src/octree_mod.f90:19-138): `use octree_mod, only: amr_grid`; the box and the frequency grid travel in cfg%grid
+    !--- (grid_create_amr copies them into `grid`, src/grid_mod_amr.f90:1017-1058)
+    cfg%par%use_amr_grid = l2i(par%use_amr_grid)
+    cfg%amr%ncells = 0; cfg%amr%nleaf = 0
+    if (par%use_amr_grid) then
+       cfg%amr%ncells = amr_grid%ncells; cfg%amr%nleaf = amr_grid%nleaf
+       cfg%amr%children = c_loc(amr_grid%children); cfg%amr%ileaf = c_loc(amr_grid%ileaf)
+       cfg%amr%icell_of_leaf = c_loc(amr_grid%icell_of_leaf); cfg%amr%neighbor = c_loc(amr_grid%neighbor)
+       cfg%amr%cx = c_loc(amr_grid%cx); cfg%amr%cy = c_loc(amr_grid%cy); cfg%amr%cz = c_loc(amr_grid%cz); cfg%amr%ch = c_loc(amr_grid%ch)
+       cfg%amr%rhokap = c_loc(amr_grid%rhokap); cfg%amr%voigt_a = c_loc(amr_grid%voigt_a); cfg%amr%Dfreq = c_loc(amr_grid%Dfreq)
+       cfg%amr%vfx = c_loc(amr_grid%vfx); cfg%amr%vfy = c_loc(amr_grid%vfy); cfg%amr%vfz = c_loc(amr_grid%vfz)
+       cfg%amr%rhokapD = c_null_ptr
+       if (par%DGR > 0.0_wp .and. associated(amr_grid%rhokapD)) cfg%amr%rhokapD = c_loc(amr_grid%rhokapD)
+       cfg%grid%xmin = amr_grid%xmin; cfg%grid%xmax = amr_grid%xmax; cfg%grid%ymin = amr_grid%ymin; cfg%grid%ymax = amr_grid%ymax
+       cfg%grid%zmin = amr_grid%zmin; cfg%grid%zmax = amr_grid%zmax
+       cfg%grid%Dfreq_ref = amr_grid%Dfreq_ref; cfg%grid%nxfreq = amr_grid%nxfreq
+       cfg%grid%xfreq_min = amr_grid%xfreq_min; cfg%grid%xfreq_max = amr_grid%xfreq_max; cfg%grid%dxfreq = amr_grid%dxfreq
+       cfg%grid%xcrit = amr_grid%xcrit; cfg%grid%xcrit2 = amr_grid%xcrit2
+       ! tallies of an octree run live in amr_grid%Jout/Jin/Jabs/Jmu: lart_gpu_fetch is pointed at those (see fetch below)
+    endif
+
     !--- line_type (src/define.f90:639-656)
     cfg%line%line_type = line%line_type; cfg%line%pad_ = 0
     cfg%line%E1 = line%E1; cfg%line%E2 = line%E2; cfg%line%E3 = line%E3
@@ -289,6 +319,13 @@ contains
 
     !--- add the raw weighted sums into the host's arrays (then main.f90:46 output_reduce sums the ranks)
     tal%Jout = ploc(grid%Jout); tal%Jin = ploc(grid%Jin); tal%Jabs = ploc(grid%Jabs); tal%Jmu = ploc(grid%Jmu)
+    if (par%use_amr_grid) then  ! an octree run tallies into amr_grid (src/octree_mod.f90:84-88)
+       tal%Jout = c_null_ptr; tal%Jin = c_null_ptr; tal%Jabs = c_null_ptr; tal%Jmu = c_null_ptr
+       if (allocated(amr_grid%Jout)) tal%Jout = c_loc(amr_grid%Jout)
+       if (allocated(amr_grid%Jin))  tal%Jin  = c_loc(amr_grid%Jin)
+       if (allocated(amr_grid%Jabs)) tal%Jabs = c_loc(amr_grid%Jabs)
+       if (allocated(amr_grid%Jmu))  tal%Jmu  = c_loc(amr_grid%Jmu)
+    endif
     tal%obs  = c_loc(oout)
     tal%allph%rp0 = c_null_ptr; tal%allph%rp = c_null_ptr; tal%allph%xfreq1 = c_null_ptr; tal%allph%xfreq2 = c_null_ptr
     tal%allph%nscatt_gas = c_null_ptr; tal%allph%nscatt_dust = c_null_ptr

@@ -47,7 +47,19 @@ enum {
 enum {
   LART_SRC_POINT = 0,         /* default: (xs,ys,zs)_point                  */
   LART_SRC_UNIFORM = 1,       /* 'uniform': uniform in the box              */
-  LART_SRC_UNIFORM_SPHERE = 2 /* 'uniform_sphere'/'sphere': r<source_rmax   */
+  LART_SRC_UNIFORM_SPHERE = 2, /* 'uniform_sphere'/'sphere': r<source_rmax   */
+  LART_SRC_PLANE_ILLUMINATION = 3 /* 'plane_illumination': parallel beam onto an atmosphere, random_plane_illumination
+                                    (src/generate_photon.f90:729-812); needs par.atmosphere != 0 */
+};
+
+/* par%geometry of the exoplanet-atmosphere models (src/setup.f90:86-113, 959-987) */
+enum {
+  LART_ATM_NONE = 0,
+  LART_ATM_PLANE = 1,    /* 'plane_atmosphere': 1x1xnz, raytrace_to_tau_car_zonly_atmosphere (raytrace_car.f90:2956-3117):
+                            a photon that leaves through the bottom cell is absorbed into Jabs2 */
+  LART_ATM_SPHERICAL = 2 /* 'spherical_atmosphere': raytrace_to_tau_car_atmosphere / _xysym_atmosphere (:3119-3663),
+                            raytrace_to_edge_car_atmosphere (:3665-3770) and the two sight-line variants (:3772-3976):
+                            cells with grid%mask == -1 destroy the photon (Jabs2), rays through them have tau = +inf */
 };
 
 /* grid_type scalars + arrays — src/define.f90:117-148; built by
@@ -74,6 +86,14 @@ typedef struct lart_grid {
   const double *Dfreq;         /* (nx,ny,nz)                                */
   const double *vfx, *vfy, *vfz; /* (nx,ny,nz) bulk velocity / v_th(cell)   */
   const double *rhokapD;       /* (nx,ny,nz) dust extinction, or NULL if DGR==0 */
+  /* ---- next rows; all NULL / 0 when unused ---- */
+  const int8_t *mask;          /* (nx,ny,nz) grid%mask (grid_mod_car.f90:247-250, 320-330): -1 = the planet's molecular
+                                  layer; read only with par.atmosphere == LART_ATM_SPHERICAL */
+  int32_t geometry_JPa;        /* par%geometry_JPa of the CALCJ/CALCP/CALCPnew accumulators (grid_mod_car.f90:1242-1440):
+                                  3 = per cell, 2 = cylindrical (nr,nz), 1 = spherical (nr), -1 = plane parallel (nz) */
+  int32_t nr;                  /* grid%nr: radial bins of geometries 1 and 2                                  */
+  const int32_t *ind_sph;      /* (nx,ny,nz) grid%ind_sph, 1-based radial bin of a cell (geometry 1)          */
+  const int32_t *ind_cyl;      /* (nx,ny)    grid%ind_cyl (geometry 2)                                        */
 } lart_grid;
 
 /* the members of params_type the path reads — src/define.f90:209-544 */
@@ -105,9 +125,19 @@ typedef struct lart_params {
   int32_t use_clump_medium;  /* the clump ray tracers and do_resonance1_clump (setup.f90:806-860); needs cfg.clumps */
   int32_t xy_periodic;       /* nx==ny==1: the _zonly ray tracers; otherwise the _xyper ray tracers, photons
                                 wrap around in x and y (setup.f90:958-976; raytrace_car.f90:971-1136,
-                                2252-2517).  Shear-periodic boxes (par%Omega /= 0) are not on the GPU path */
+                                2252-2517); with par.Omega /= 0 the shearing-box variant (:2677-2954) */
   int32_t nobs;
   int32_t use_amr_grid;      /* the octree ray tracers (raytrace_amr.f90:77-351) and leaf-indexed physics; needs cfg.amr */
+  int32_t atmosphere;        /* LART_ATM_*                                                                    */
+  int32_t calc_J;            /* the reference's -DCALCJ build: mean intensity J(x, cell) from path lengths,
+                                add_to_J (raytrace_car.f90:3979-4011), called once per cell step of raytrace_to_tau */
+  int32_t calc_P;            /* -DCALCP: scattering rate per atom, add_to_Pa (scattering_car.f90:829-860), once per
+                                resonance scattering                                                          */
+  int32_t calc_Pnew;         /* -DCALCPnew: the same rate from path lengths, add_to_Pnew (raytrace_car.f90:4015-4045) */
+  double Omega;              /* par%Omega after grid_mod_car.f90:348-350 (q*Omega*xrange in thermal-velocity units of
+                                the reference frame): /= 0 with xy_periodic and nx,ny > 1 binds
+                                raytrace_to_tau_car_xyper_shear (raytrace_car.f90:2677-2954); raytrace_to_edge then stays
+                                the plain open-box routine, as upstream (setup.f90:967-969)                   */
 } lart_params;
 
 /* line_type members — src/define.f90:639-656; values from
@@ -118,6 +148,7 @@ typedef struct lart_line {
   double E1, E2, E3;
   double g_recoil0;
   double DnuHK_Hz;
+  double cross0;     /* line%cross0: rhokap*Dfreq/cross0 = number density x distance2cm (add_to_Pa, add_to_Pnew) */
 } lart_line;
 
 /* observer_type members — src/define.f90:547-560; rmatrix is the Fortran
@@ -166,7 +197,7 @@ typedef struct lart_clumps {
  * :619-683) and the leaf physics (grid_create_amr, src/grid_mod_amr.f90:34-526); the library only reads them.
  * With par.use_amr_grid the photon's cell is a LEAF index (photon%icell_amr), lart_grid supplies the box
  * (xmin..zmax), Dfreq_ref, the frequency grid and xcrit; its nx, ny, nz and cell arrays are not read.
- * Not on the GPU path: periodic / mirror boundaries of the octree, band-2 (Ly-beta) photons, H2, CALCJ/CALCP. */
+ * Not on the GPU path: periodic / mirror boundaries of the octree, band-2 (Ly-beta) photons, H2, CALCJ/CALCP on leaves. */
 typedef struct lart_amr {
   int32_t ncells, nleaf;            /* all cells (internal + leaf), leaves                                   */
   const int32_t *children;          /* (8,ncells) child cell or 0; octant = 1 + ix + 2*iy + 4*iz             */
@@ -257,6 +288,11 @@ typedef struct lart_tallies {
   lart_allph_out allph;      /* all NULL unless save_all_photons           */
   double nscatt_gas, nscatt_dust; /* par%nscatt_* : weighted sums, ADDED   */
   lart_counters counters;    /* ADDED                                      */
+  double *Jabs2;             /* (nxfreq) grid%Jabs2: photons destroyed by the atmosphere's molecular zone (NULL = skip) */
+  double *J;                 /* CALCJ:    (nxfreq, [nx,ny,nz | nr,nz | nr | nz]) by geometry_JPa 3 | 2 | 1 | -1 —
+                                grid%J / J2 / J1 (grid_mod_car.f90:1422-1434), raw sums of path length x weight  */
+  double *Pa;                /* CALCP:    ([nx,ny,nz | nr,nz | nr | nz]) grid%Pa / P2 / P1 (:1385-1395)          */
+  double *Pnew;              /* CALCPnew: the same shape, grid%Pa_new / P2_new / P1_new (:1410-1420)             */
 } lart_tallies;
 
 typedef struct lart_gpu_ctx *lart_gpu_handle;

@@ -21,7 +21,8 @@ c_int64_p = C.POINTER(C.c_int64)
 
 LART_MAX_OBSERVERS = 181
 SPEC_MONO, SPEC_VOIGT, SPEC_VOIGT0, SPEC_CONTINUUM, SPEC_GAUSSIAN = range(5)
-SRC_POINT, SRC_UNIFORM, SRC_UNIFORM_SPHERE = range(3)
+SRC_POINT, SRC_UNIFORM, SRC_UNIFORM_SPHERE, SRC_PLANE_ILLUMINATION = range(4)
+ATM_NONE, ATM_PLANE, ATM_SPHERICAL = range(3)
 FLAG_SOA_GRID = 1
 FLAG_NO_WARP_AGG = 2
 FLAG_MONOLITHIC = 4
@@ -45,6 +46,8 @@ class Grid(C.Structure):
         ("xface", c_double_p), ("yface", c_double_p), ("zface", c_double_p),
         ("rhokap", c_double_p), ("voigt_a", c_double_p), ("Dfreq", c_double_p),
         ("vfx", c_double_p), ("vfy", c_double_p), ("vfz", c_double_p), ("rhokapD", c_double_p),
+        ("mask", C.POINTER(C.c_int8)), ("geometry_JPa", C.c_int32), ("nr", C.c_int32),
+        ("ind_sph", c_int32_p), ("ind_cyl", c_int32_p),
     ]
 
 
@@ -63,12 +66,14 @@ class Params(C.Structure):
         ("save_direc0", C.c_int32), ("save_all_photons", C.c_int32), ("xyz_symmetry", C.c_int32), ("xy_symmetry", C.c_int32),
         ("use_clump_medium", C.c_int32), ("xy_periodic", C.c_int32),
         ("nobs", C.c_int32), ("use_amr_grid", C.c_int32),
+        ("atmosphere", C.c_int32), ("calc_J", C.c_int32), ("calc_P", C.c_int32), ("calc_Pnew", C.c_int32),
+        ("Omega", C.c_double),
     ]
 
 
 class Line(C.Structure):
     _fields_ = [("line_type", C.c_int32), ("pad_", C.c_int32), ("E1", C.c_double), ("E2", C.c_double),
-                ("E3", C.c_double), ("g_recoil0", C.c_double), ("DnuHK_Hz", C.c_double)]
+                ("E3", C.c_double), ("g_recoil0", C.c_double), ("DnuHK_Hz", C.c_double), ("cross0", C.c_double)]
 
 
 class Observer(C.Structure):
@@ -131,7 +136,8 @@ class Counters(C.Structure):
 class Tallies(C.Structure):
     _fields_ = [("Jout", c_double_p), ("Jin", c_double_p), ("Jabs", c_double_p), ("Jmu", c_double_p),
                 ("obs", C.POINTER(ObserverOut)), ("allph", AllphOut),
-                ("nscatt_gas", C.c_double), ("nscatt_dust", C.c_double), ("counters", Counters)]
+                ("nscatt_gas", C.c_double), ("nscatt_dust", C.c_double), ("counters", Counters),
+                ("Jabs2", c_double_p), ("J", c_double_p), ("Pa", c_double_p), ("Pnew", c_double_p)]
 
 
 class SightlineOut(C.Structure):

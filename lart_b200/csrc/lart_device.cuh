@@ -47,6 +47,7 @@ struct TallyLayout {
   long long img[7];                // the same, 2-D
   long long scalars;               // nscatt_gas, nscatt_dust
   long long counters;              // C_COUNT work counters
+  long long Jabs2, J, Pa, Pnew;    // atmosphere absorption spectrum; CALCJ / CALCP / CALCPnew accumulators (-1 = off)
   long long total;
 };
 enum { T_SCATT = 0, T_DIREC = 1, T_DIREC0 = 2, T_I = 3, T_Q = 4, T_U = 5, T_V = 6 };
@@ -80,6 +81,21 @@ struct DevAmr {
   const AmrCell *cell;  // [ncells]
 };
 
+// The less common bindings of the Cartesian ray tracers (setup.f90:959-987) and the mean-intensity /
+// scattering-rate accumulators (8f-4).  `any` = 0 on every other run: each hook below sits behind a warp-uniform branch.
+struct DevExtras {
+  int any;
+  int atm;            // LART_ATM_*: 1 = plane atmosphere (a photon leaving through the bottom cell goes to Jabs2),
+                      // 2 = spherical atmosphere (cells with mask == -1 destroy the photon; rays through them have tau = +inf)
+  int shear;          // shearing box: photon%vfy_shear changes by -+Omega at every x wrap (raytrace_car.f90:2842-2850)
+  int edge_open;      // shear or atm: raytrace_to_edge stays the plain open-box routine (setup.f90:947-950, 984)
+  int calc_J, calc_P, calc_Pnew, jp;  // jp = any of the three
+  int geometry_JPa, nr;
+  double Omega, cross0;
+  const signed char *mask;   // (nx,ny,nz) Fortran order
+  const int *ind_sph, *ind_cyl;
+};
+
 struct DevParams {
   // grid
   int nx, ny, nz, nxfreq;
@@ -92,6 +108,7 @@ struct DevParams {
   int clump;      // par%use_clump_medium: the ray tracers of lart_clump.cuh, photons carry their clump index
   DevAmr amr;     // par%use_amr_grid: photons carry a leaf index in `ic` (jc = kc = 1); nx = nleaf, ny = nz = 1
   DevClumps cl;
+  DevExtras x;
   double Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax;
   const double *xface, *yface, *zface;
   const Cell *cells;                                            // packed records (default walk)
@@ -319,8 +336,11 @@ struct Ray {
   int ic, jc, kc;                   // 1-based
   int istep, jstep, kstep;
   int nsteps;
-  int flip;                         // xyz symmetry: bit a set = direction component a reflected since the start
+  int flip;                         // xyz symmetry: bit a set = direction component a reflected since the start;
+                                    // bit 3 (kRayOpen): this walk ignores the periodic / z-only / mirror binding
+  double vshear;                    // shearing box: the photon's vfy_shear (touched only when P.x.shear)
 };
+constexpr int kRayOpen = 8;
 
 // One straight-line path for both signs of k (no divergent branch around the divide): the special cases of
 // raytrace_car.f90:27-44 — already outside (k>0), sitting on the lower face (k<0) — become predicates.
@@ -376,6 +396,13 @@ LART_DEV bool axis_setup_bc(double &k, double &p, int &cell, int n, const double
   return false;
 }
 
+// line-of-sight bulk velocity of the ray's current cell; the shearing box adds the photon's vfy_shear to vfy in the
+// to_tau walk (raytrace_car.f90:2809, 2905, 2932)
+LART_DEV double ray_ulos(const DevParams &P, const Ray &r) {
+  if (P.x.shear && !(r.flip & kRayOpen))
+    return DADD(DADD(DMUL(r.cell.vfx, r.kx), DMUL(DADD(r.cell.vfy, r.vshear), r.ky)), DMUL(r.cell.vfz, r.kz));
+  return vdotk(r.cell, r.kx, r.ky, r.kz);
+}
 // `here` (optional) = record of the start cell when the caller already holds it; it is used
 // unless the on-face rule moved the start into a neighbouring cell.
 // ---------------------------------------------------------------------------
@@ -513,17 +540,20 @@ LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z
   r.ic = ic; r.jc = jc; r.kc = kc;
   r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0; r.flip = 0;
   if (P.amr.on) return amr_ray_setup(P, r, here);
-  if (P.bcxy) {  // folded / periodic grids; their to_tau variants test `== xp` (:1681, :1993, :2293), to_edge `<= xp`
+  // shearing boxes and atmospheres: raytrace_to_edge is the plain open-box routine whatever raytrace_to_tau is bound to
+  const bool open = P.x.edge_open && !zonly_eq;
+  if (open) r.flip = kRayOpen;
+  if (P.bcxy && !open) {  // folded / periodic grids; their to_tau variants test `== xp` (:1681, :1993, :2293), to_edge `<= xp`
     bool mx, my, mz;
     if (axis_setup_bc(r.kx, r.x0, r.ic, P.nx, P.xface, r.istep, r.tx, r.delx, zonly_eq, P.bcxy, P.i0, mx)) return true;
     if (axis_setup_bc(r.ky, r.y0, r.jc, P.ny, P.yface, r.jstep, r.ty, r.dely, zonly_eq, P.bcxy, P.j0, my)) return true;
     if (axis_setup_bc(r.kz, r.z0, r.kc, P.nz, P.zface, r.kstep, r.tz, r.delz, zonly_eq, P.bcz, P.k0, mz)) return true;
     r.flip = (mx ? 1 : 0) | (my ? 2 : 0) | (mz ? 4 : 0);
     load_cell(P, r.ic, r.jc, r.kc, r.cell);
-    r.u1 = vdotk(r.cell, r.kx, r.ky, r.kz);
+    r.u1 = ray_ulos(P, r);
     return false;
   }
-  if (P.zonly) {
+  if (P.zonly && !open) {
     r.istep = r.jstep = 0; r.tx = r.ty = kHugest; r.delx = r.dely = kHugest;
     if (axis_setup(kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, zonly_eq)) return true;
   } else {
@@ -541,9 +571,12 @@ constexpr int kFlipShift = 28, kCellMask = (1 << kFlipShift) - 1;
 // Resume a suspended walk: start point and direction are the ray's own, the DDA state is what was saved.
 LART_DEV void ray_resume(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
                          double tx, double ty, double tz, double delx, double dely, double delz, double d, double tau,
-                         double xfreq, double u1, int ic, int jc, int kc_flip) {
-  const int kc = kc_flip & kCellMask, flip = kc_flip >> kFlipShift;  // see ray_save_state
-  if (P.bcxy == BC_PERIODIC) {  // the start point had been wrapped to the far side
+                         double xfreq, double u1, int ic, int jc, int kc_flip, bool open = false) {
+  const int kc = kc_flip & kCellMask;
+  int flip = kc_flip >> kFlipShift;  // see ray_save_state
+  if (open) {                   // an edge walk of a shearing box / an atmosphere: plain open box
+    flip = kRayOpen;
+  } else if (P.bcxy == BC_PERIODIC) {  // the start point had been wrapped to the far side
     if (flip & 1) x = __ldg(P.xface + (kx > 0.0 ? 0 : P.nx));
     if (flip & 2) y = __ldg(P.yface + (ky > 0.0 ? 0 : P.ny));
   } else {                      // reflected direction components
@@ -556,8 +589,9 @@ LART_DEV void ray_resume(const DevParams &P, Ray &r, double x, double y, double 
   r.tx = tx; r.ty = ty; r.tz = tz; r.delx = delx; r.dely = dely; r.delz = delz;
   r.d = d; r.tau = tau; r.xfreq = xfreq; r.u1 = u1;
   r.ic = ic; r.jc = jc; r.kc = kc; r.nsteps = 0;
-  r.istep = P.zonly ? 0 : (kx > 0.0 ? 1 : (kx < 0.0 ? -1 : 0));
-  r.jstep = P.zonly ? 0 : (ky > 0.0 ? 1 : (ky < 0.0 ? -1 : 0));
+  const bool zo = P.zonly && !open;
+  r.istep = zo ? 0 : (kx > 0.0 ? 1 : (kx < 0.0 ? -1 : 0));
+  r.jstep = zo ? 0 : (ky > 0.0 ? 1 : (ky < 0.0 ? -1 : 0));
   r.kstep = kz > 0.0 ? 1 : (kz < 0.0 ? -1 : 0);
   load_cell(P, ic, jc, kc, r.cell);
 }
@@ -571,7 +605,7 @@ LART_DEV double ray_opacity(const DevParams &P, const double *vtab, const Ray &r
 
 // minloc([tx,ty,tz]) — first minimum wins (:476,:1506); z-only walks z
 LART_DEV int ray_axis(const DevParams &P, const Ray &r) {
-  if (P.zonly) return 3;
+  if (P.zonly && !(r.flip & kRayOpen)) return 3;
   if (r.tx <= r.ty && r.tx <= r.tz) return 1;
   if (r.ty <= r.tz) return 2;
   return 3;
@@ -586,19 +620,24 @@ LART_DEV bool ray_leave_or_turn(int bc, int &cell, int &step, double &k, int n, 
   return true;
 }
 LART_DEV bool ray_advance(const DevParams &P, Ray &r, int axis) {
+  const bool open = (r.flip & kRayOpen) != 0;
+  const int bcxy = open ? (int)BC_OPEN : P.bcxy, bcz = open ? (int)BC_OPEN : P.bcz;
   if (axis == 1) {
     r.ic += r.istep;
-    if ((r.ic < 1 || r.ic > P.nx) && ray_leave_or_turn(P.bcxy, r.ic, r.istep, r.kx, P.nx, P.i0, r.flip, 1)) return false;
+    if (r.ic < 1 || r.ic > P.nx) {
+      if (P.x.shear && !open) r.vshear = (r.ic < 1) ? DSUB(r.vshear, P.x.Omega) : DADD(r.vshear, P.x.Omega);  // :2842-2850
+      if (ray_leave_or_turn(bcxy, r.ic, r.istep, r.kx, P.nx, P.i0, r.flip, 1)) return false;
+    }
     if (r.delx < 0.0) r.delx = P.dx / fabs(r.kx);
     r.tx = DADD(r.tx, r.delx);
   } else if (axis == 2) {
     r.jc += r.jstep;
-    if ((r.jc < 1 || r.jc > P.ny) && ray_leave_or_turn(P.bcxy, r.jc, r.jstep, r.ky, P.ny, P.j0, r.flip, 2)) return false;
+    if ((r.jc < 1 || r.jc > P.ny) && ray_leave_or_turn(bcxy, r.jc, r.jstep, r.ky, P.ny, P.j0, r.flip, 2)) return false;
     if (r.dely < 0.0) r.dely = P.dy / fabs(r.ky);
     r.ty = DADD(r.ty, r.dely);
   } else {
     r.kc += r.kstep;
-    if ((r.kc < 1 || r.kc > P.nz) && ray_leave_or_turn(P.bcz, r.kc, r.kstep, r.kz, P.nz, P.k0, r.flip, 4)) return false;
+    if ((r.kc < 1 || r.kc > P.nz) && ray_leave_or_turn(bcz, r.kc, r.kstep, r.kz, P.nz, P.k0, r.flip, 4)) return false;
     if (r.delz < 0.0) r.delz = P.dz / fabs(r.kz);
     r.tz = DADD(r.tz, r.delz);
   }
@@ -629,14 +668,57 @@ LART_DEV void fold_periodic(const DevParams &P, double &xp, double &yp) {
 LART_DEV void ray_shift(const DevParams &P, Ray &r) {
   double Dold = r.cell.Dfreq;
   load_cell(P, r.ic, r.jc, r.kc, r.cell);
-  double u2 = vdotk(r.cell, r.kx, r.ky, r.kz);
+  double u2 = ray_ulos(P, r);
   r.xfreq = DSUB(DMUL(DADD(r.xfreq, r.u1), Dold) / r.cell.Dfreq, u2);
   r.u1 = u2;
+}
+
+// spherical atmosphere: grid%mask == -1 marks the planet's molecular layer (grid_mod_car.f90:320-330)
+LART_DEV bool ray_masked(const DevParams &P, const Ray &r) {
+  return P.x.atm == 2 && P.x.mask[cell_index(P, r.ic, r.jc, r.kc)] == -1;
+}
+
+// CALCJ / CALCP / CALCPnew: the bin of cell (ic,jc,kc) in the P arrays by par%geometry_JPa — 3 the cell, 2 (ind_cyl, k),
+// 1 ind_sph, -1 k — or -1 when the cell takes no deposit (raytrace_car.f90:3989-3991, 3996; the reference does not
+// range-check ind_sph: a bin outside 1..nr is skipped instead of written out of bounds)
+LART_DEV long long jp_bin(const DevParams &P, int ic, int jc, int kc, double rhokap) {
+  if (!(ic > 0 && ic <= P.nx && jc > 0 && jc <= P.ny && kc > 0 && kc <= P.nz) || !(rhokap > 0.0)) return -1;
+  switch (P.x.geometry_JPa) {
+    case 3: return (long long)cell_index(P, ic, jc, kc);
+    case 2: {
+      const int ir = __ldg(P.x.ind_cyl + (ic - 1) + (size_t)P.nx * (jc - 1));
+      return (ir >= 1 && ir <= P.x.nr) ? (long long)(ir - 1) + (long long)P.x.nr * (kc - 1) : -1;
+    }
+    case 1: {
+      const int ir = __ldg(P.x.ind_sph + cell_index(P, ic, jc, kc));
+      return (ir >= 1 && ir <= P.x.nr) ? (long long)(ir - 1) : -1;
+    }
+    default: return kc - 1;
+  }
+}
+// add_to_J + add_to_Pnew (raytrace_car.f90:3979-4045) for one path segment of a to_tau walk: del = its length,
+// dtauH = its line optical depth, xfreq = the photon's frequency in the cell's frame
+__device__ __noinline__ void jp_deposit(const DevParams &P, int ic, int jc, int kc, double rhokap, double Dfreq, double xfreq,
+                                        double wgt, double del, double dtauH) {
+  const long long b = jp_bin(P, ic, jc, kc, rhokap);
+  if (b < 0) return;
+  if (P.x.calc_J) {
+    const double xref = DMUL(xfreq, Dfreq / P.Dfreq_ref);
+    const int ix = (int)floor(DSUB(xref, P.xfreq_min) / P.dxfreq) + 1;
+    if (ix > 0 && ix <= P.nxfreq) atomicAdd(P.tally + P.lay.J + (ix - 1) + (long long)P.nxfreq * b, DMUL(del, wgt));
+  }
+  if (P.x.calc_Pnew) atomicAdd(P.tally + P.lay.Pnew + b, DMUL(dtauH, wgt) / (DMUL(rhokap, Dfreq) / P.x.cross0));
+}
+// add_to_Pa (scattering_car.f90:829-860): one resonance scattering in cell (ic,jc,kc)
+__device__ __noinline__ void jp_add_Pa(const DevParams &P, int ic, int jc, int kc, double rhokap, double Dfreq, double wgt) {
+  const long long b = jp_bin(P, ic, jc, kc, rhokap);
+  if (b >= 0) atomicAdd(P.tally + P.lay.Pa + b, wgt / (DMUL(rhokap, Dfreq) / P.x.cross0));
 }
 
 // One cell step of raytrace_to_edge.  Returns true when the walk is finished.
 LART_DEV bool edge_step(const DevParams &P, const double *vtab, Ray &r) {
   if (P.amr.on) return amr_edge_step(P, vtab, r);
+  if (P.x.atm && ray_masked(P, r)) { r.tau = __longlong_as_double(0x7ff0000000000000LL); return true; }  // :3729-3733 tau = +inf
   double kap = ray_opacity(P, vtab, r);
   ++r.nsteps;
   int ax = ray_axis(P, r);
@@ -650,9 +732,40 @@ LART_DEV bool edge_step(const DevParams &P, const double *vtab, Ray &r) {
 }
 
 // One cell step of raytrace_to_tau.  status: 0 = keep walking, 1 = reached tau_in
-// (position in xp,yp,zp), 2 = left the grid.
-LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau_in, double &xp, double &yp, double &zp) {
+// (position in xp,yp,zp), 2 = left the grid, 3 = destroyed by the atmosphere mask (:3186-3190).
+// wgt = the photon's weight (only the CALCJ / CALCPnew deposits read it).
+LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau_in, double &xp, double &yp, double &zp,
+                      double wgt = 0.0) {
   if (P.amr.on) return amr_tau_step(P, vtab, r, tau_in, xp, yp, zp);
+  if (P.x.any) {  // the uncommon bindings: mask, path-length accumulators (one extra Voigt evaluation is not paid: kapH below)
+    if (P.x.atm && ray_masked(P, r)) return 3;
+    if (P.x.jp) {
+      const double kapH = DMUL(r.cell.rhokap, voigt_seon2(vtab, r.xfreq, r.cell.voigt_a));
+      const double kap = P.dust ? DADD(kapH, r.cell.rhokapD) : kapH;
+      ++r.nsteps;
+      const int ax = ray_axis(P, r);
+      const double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
+      double del = DSUB(tn, r.d);
+      r.tau = DADD(r.tau, DMUL(del, kap));
+      r.d = tn;
+      const bool reached = r.tau >= tau_in;
+      if (reached && kap > 0.0) {
+        const double over = DSUB(r.tau, tau_in) / kap;
+        r.d = DSUB(r.d, over);
+        del = DSUB(del, over);
+      }
+      // every segment is credited once to the cell it lies in (:1579-1584 in the loop, :1604-1609 for the last one)
+      jp_deposit(P, r.ic, r.jc, r.kc, r.cell.rhokap, r.cell.Dfreq, r.xfreq, wgt, del, DMUL(del, kapH));
+      if (reached) {
+        ray_endpoint_bc(P, r, xp, yp, zp);
+        if (P.bcxy == BC_PERIODIC) fold_periodic(P, xp, yp);
+        return 1;
+      }
+      if (!ray_advance(P, r, ax)) return 2;
+      ray_shift(P, r);
+      return 0;
+    }
+  }
   double kap = ray_opacity(P, vtab, r);
   ++r.nsteps;
   int ax = ray_axis(P, r);
@@ -679,8 +792,10 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
 // ---------------------------------------------------------------------------
 // photon_type — define.f90:80-111 (I == 1 always; E1,E2,E3 are line constants)
 // ---------------------------------------------------------------------------
-enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8, PH_TAUPEND = 16, PH_DUSTEV = 32, PH_INFLIGHT = 64 };
+enum { PH_ALIVE = 1, PH_FIRST = 2, PH_GAUSS = 4, PH_SCATTER = 8, PH_TAUPEND = 16, PH_DUSTEV = 32, PH_INFLIGHT = 64,
+       PH_ABS2 = 128 /* ended in the atmosphere's molecular zone: its weight goes to Jabs2, not Jout */ };
 struct Photon {
+  double vshear;  // photon%vfy_shear (define.f90:100), shearing boxes only
   long long id;
   double x, y, z, kx, ky, kz, mx, my, mz, nx, ny, nz;
   double xfreq, xfreq_ref, wgt, Q, U, V, nsg, nsd;
@@ -1045,7 +1160,7 @@ static_assert(sizeof(PeelCont) == 240, "PeelCont must be fifteen 16-byte chunks"
 LART_DEV void ray_save_state(const Ray &r, double *st10, int *c3) {
   st10[0] = r.tx; st10[1] = r.ty; st10[2] = r.tz; st10[3] = r.delx; st10[4] = r.dely; st10[5] = r.delz;
   st10[6] = r.d; st10[7] = r.tau; st10[8] = r.xfreq; st10[9] = r.u1;
-  c3[0] = r.ic; c3[1] = r.jc; c3[2] = r.kc | (r.flip << kFlipShift);
+  c3[0] = r.ic; c3[1] = r.jc; c3[2] = r.kc | ((r.flip & 7) << kFlipShift);
 }
 LART_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -1548,6 +1663,7 @@ LART_DEV void draw_resonance_warp(VzWarpShared &sh, bool active, const DevParams
 template <bool STOKES, class PeelFn>
 LART_DEV void apply_resonance(const DevParams &P, Photon &ph, const CellData &cs, const ScatterVariates &v, PeelFn &&peel) {
   ph.nsg += ph.wgt;
+  if (P.x.calc_P) jp_add_Pa(P, ph.ic, ph.jc, ph.kc, cs.rhokap, cs.Dfreq, ph.wgt);  // scattering_car.f90:356-358
   const double cost = v.cost, cosp = v.cosp, sinp = v.sinp;
   const double sint = sqrt(1.0 - cost * cost);
   const double cost2 = cost * cost;
@@ -1589,6 +1705,7 @@ LART_DEV void scatter_resonance_core(const DevParams &P, Photon &ph, Rng &r, con
                                      double xfreq_atom, double vth_ratio, PeelFn &&peel) {
   const bool stokes = STOKES < 0 ? (P.use_stokes != 0) : (STOKES != 0);
   ph.nsg += ph.wgt;
+  if (!CLUMP && P.x.calc_P) jp_add_Pa(P, ph.ic, ph.jc, ph.kc, cs.rhokap, cs.Dfreq, ph.wgt);  // scattering_car.f90:356-358, 691-693
   double cost = rand_resonance_fast(r, P);
   double sint = sqrt(1.0 - cost * cost);
   double cost2 = cost * cost;
@@ -1701,21 +1818,34 @@ LART_DEV void generate_photon(const DevParams &P, Photon &ph, Rng &r, Counters &
     ph.x = (P.xmax - P.xmin) * u1 + P.xmin;
     ph.y = (P.ymax - P.ymin) * u2 + P.ymin;
     ph.z = (P.zmax - P.zmin) * r.uniform() + P.zmin;
+  } else if (P.source_geometry == 3) {  // plane_illumination — random_plane_illumination :729-760
+    if (P.x.atm == 1) {
+      ph.x = 0.0; ph.y = 0.0; ph.z = P.zmax;
+    } else {
+      const double rp = P.rmax * sqrt(r.uniform());
+      const double phi = (P.bcxy == BC_MIRROR ? kHalfPi : kTwoPi) * r.uniform();
+      ph.x = rp * cos(phi); ph.y = rp * sin(phi); ph.z = P.zmin;
+    }
   } else {  // point :126-131
     ph.x = P.xs; ph.y = P.ys; ph.z = P.zs;
   }
   ph.wgt = 1.0;
+  ph.vshear = 0.0;  // :141
   if (P.sym) {  // sources are folded into the octant (:356-360)
     if (ph.x < P.xmin) ph.x = -ph.x;
     if (ph.y < P.ymin) ph.y = -ph.y;
     if (ph.z < P.zmin) ph.z = -ph.z;
   }
-  double uc, up;
-  r.uniform2(uc, up);
-  double cost = 2.0 * uc - 1.0;
-  double sint = sqrt(1.0 - cost * cost);
-  double cosp, sinp;
-  sincospi(2.0 * up, &sinp, &cosp);
+  double cost, sint, cosp, sinp;
+  if (P.source_geometry == 3) {  // :765-778 a parallel beam: down onto the slab, or up along +z
+    cost = (P.x.atm == 1) ? -1.0 : 1.0; sint = 0.0; cosp = 1.0; sinp = 0.0;
+  } else {
+    double uc, up;
+    r.uniform2(uc, up);
+    cost = 2.0 * uc - 1.0;
+    sint = sqrt(1.0 - cost * cost);
+    sincospi(2.0 * up, &sinp, &cosp);
+  }
   ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
   ph.ic = (int)floor((ph.x - P.xmin) / P.dx) + 1;
   ph.jc = (int)floor((ph.y - P.ymin) / P.dy) + 1;

@@ -74,7 +74,9 @@ constexpr int kTailQuantum = 256;
 // ------------------------------- photon pool -------------------------------
 enum {
   F_X, F_Y, F_Z, F_KX, F_KY, F_KZ, F_MX, F_MY, F_MZ, F_NX, F_NY, F_NZ,
-  F_XFREQ, F_XREF, F_WGT, F_Q, F_U, F_V, F_NSG, F_NSD, F_GSET, F_TAU, F_COUNT
+  F_XFREQ, F_XREF, F_WGT, F_Q, F_U, F_V, F_NSG, F_NSD, F_GSET, F_TAU,
+  F_SHEAR,  // photon%vfy_shear (shearing boxes only; the column is never touched otherwise)
+  F_COUNT
 };
 struct Pool {
   double *f;                   // [F_COUNT][S]
@@ -206,8 +208,12 @@ __device__ __forceinline__ double walk_edge(const DevParams &P, const double *vt
 // raytrace_to_tau on a photon; returns the number of cell steps.  On escape the
 // photon is flagged dead and carries the lab-frame xfreq_ref (raytrace_car.f90:1598-1623);
 // the Jout tally is the caller's.
-__device__ __forceinline__ int finish_escape(const DevParams &P, Photon &ph, const Ray &r) {
+// destroyed = the walk ended in a masked cell of a spherical atmosphere (:3316-3327: same binning, into Jabs2); a plane
+// atmosphere absorbs what leaves through its bottom cell (:3099-3107).
+__device__ __forceinline__ int finish_escape(const DevParams &P, Photon &ph, const Ray &r, bool destroyed = false) {
   ph.flags &= ~PH_ALIVE;
+  if (P.x.atm && (destroyed || (P.x.atm == 1 && !(r.kc > 1)))) ph.flags |= PH_ABS2;
+  if (P.x.shear) ph.vshear = r.vshear;
   ph.xfreq = DADD(r.xfreq, r.u1);
   ph.xfreq_ref = DMUL(ph.xfreq, r.cell.Dfreq / P.Dfreq_ref);
   ph.x = r.x0; ph.y = r.y0; ph.z = r.z0;
@@ -230,28 +236,37 @@ __device__ __forceinline__ void store_direction(const Pool &pl, int s, const Pho
 }
 __device__ __forceinline__ int walk_tau(const DevParams &P, const double *vtab, Photon &ph, double tau_in, CellData &cs) {
   Ray r;
+  if (P.x.shear) r.vshear = ph.vshear;
   if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
     ph.flags &= ~PH_ALIVE;  // raytrace_car.f90:1469-1472: returns before any update
     return -1;
   }
   for (;;) {
     double xp, yp, zp;
-    int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
+    int st = tau_step(P, vtab, r, tau_in, xp, yp, zp, ph.wgt);
     if (st == 1) {
       ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
       if (P.bcxy == BC_MIRROR) adopt_direction(r, ph);
       if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
       ph.kc = r.kc;
+      if (P.x.shear) ph.vshear = r.vshear;
       cs = r.cell;
       return r.nsteps;
     }
-    if (st == 2) return finish_escape(P, ph, r);
+    if (st >= 2) return finish_escape(P, ph, r, st == 3);
   }
 }
 
 // photon left the system: Jout (if it was walked), allph record, per-run sums
 __device__ __forceinline__ void retire_photon(const DevParams &P, const Photon &ph, bool tally_jout, Job *job, Counters &cnt) {
-  if (tally_jout) tally_Jout(P, ph.xfreq_ref, ph.kz, ph.wgt);
+  if (tally_jout) {
+    if (ph.flags & PH_ABS2) {  // absorbed by the atmosphere's molecular zone
+      const int ix = freq_bin(P, ph.xfreq_ref);
+      if (ix >= 1 && ix <= P.nxfreq) tally_add(P.tally + P.lay.Jabs2 + ix - 1, ph.wgt);
+    } else {
+      tally_Jout(P, ph.xfreq_ref, ph.kz, ph.wgt);
+    }
+  }
   if (ph.nsg != 0.0) atomicAdd(P.tally + P.lay.scalars + 0, ph.nsg);
   if (ph.nsd != 0.0) atomicAdd(P.tally + P.lay.scalars + 1, ph.nsd);
   if (P.save_all_photons) record_final(P, ph);
@@ -298,6 +313,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
       load_trace_part(pl, s, ph);
       load_rest(pl, s, ph);
       load_rng(P, pl, s, ph.id, ph.flags, rng);
+      if (P.x.shear) ph.vshear = pl.f[(size_t)F_SHEAR * pl.S + s];
       nev = pl.nev[s];
       rng_valid = true;
     }
@@ -402,6 +418,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
       if (fl & PH_ALIVE) store_rng(pl, s, rng, fl);
       ph.flags = fl;
       store_all(pl, s, ph);
+      if (P.x.shear) pl.f[(size_t)F_SHEAR * pl.S + s] = ph.vshear;
       pl.nev[s] = nev;
     }
     if (rng_valid) nrng += rng.nrng;
@@ -653,6 +670,7 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
     store_rng(pl, s, rng, fl);
     ph.flags = fl;
     store_all(pl, s, ph);
+    if (P.x.shear) pl.f[(size_t)F_SHEAR * pl.S + s] = 0.0;
     pl.nev[s] = 0;
     nrng += rng.nrng;
   }
@@ -700,7 +718,9 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
             mode = (ph.flags & PH_FIRST) ? 0 : 1;
             tau_in = pl.f[(size_t)F_TAU * S + slot];
             ray_resume(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, st[0 * S], st[1 * S], st[2 * S], st[3 * S], st[4 * S],
-                       st[5 * S], st[6 * S], st[7 * S], st[8 * S], st[9 * S], pl.rc[slot], pl.rc[S + slot], pl.rc[2 * S + slot]);
+                       st[5 * S], st[6 * S], st[7 * S], st[8 * S], st[9 * S], pl.rc[slot], pl.rc[S + slot], pl.rc[2 * S + slot],
+                       P.x.edge_open && mode == 0);
+            if (P.x.shear) r.vshear = pl.f[(size_t)F_SHEAR * S + slot];
             have = true;
           } else {
             bool leaving;
@@ -721,6 +741,7 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
               mode = 1;
               leaving = true;
             }
+            if (P.x.shear) r.vshear = pl.f[(size_t)F_SHEAR * S + slot];
             if (mode == 1 && leaving)
               leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true);
             if (leaving) {  // dead without tally (raytrace_car.f90:1469-1472)
@@ -758,7 +779,7 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
         }
       } else {
         double xp, yp, zp;
-        int st = tau_step(P, vtab, r, tau_in, xp, yp, zp);
+        int st = tau_step(P, vtab, r, tau_in, xp, yp, zp, ph.wgt);
         if (st == 1) {
           ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
           if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
@@ -766,13 +787,14 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
           ph.flags |= PH_SCATTER;
           cnt.cellsteps += r.nsteps;
           if (P.bcxy == BC_MIRROR && r.flip) { adopt_direction(r, ph); store_direction(pl, slot, ph); }
+          if (P.x.shear) pl.f[(size_t)F_SHEAR * S + slot] = r.vshear;
           store_trace_part(pl, slot, ph);
           pl.ndraw[slot] = rng.nblk;
           nrng += rng.nrng;
           have = false;
-        } else if (st == 2) {
+        } else if (st >= 2) {
           load_rest(pl, slot, ph);  // before finish_escape: it writes ph.xfreq_ref
-          cnt.cellsteps += finish_escape(P, ph, r);
+          cnt.cellsteps += finish_escape(P, ph, r, st == 3);
           { retire_photon(P, ph, true, job, cnt); atomicAdd(q.n_dead, 1u); }
           store_trace_part(pl, slot, ph);
           nrng += rng.nrng;
@@ -789,6 +811,7 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
         for (int k = 0; k < 10; ++k) st[(size_t)k * S] = st10[k];
         pl.rc[slot] = c3[0]; pl.rc[S + slot] = c3[1]; pl.rc[2 * S + slot] = c3[2];
         pl.f[(size_t)F_TAU * S + slot] = tau_in;
+        if (P.x.shear) pl.f[(size_t)F_SHEAR * S + slot] = r.vshear;
         ph.flags |= PH_INFLIGHT;
         store_trace_part(pl, slot, ph);  // weight and flags may have changed (forced first scattering)
         pl.ndraw[slot] = rng.nblk;
@@ -840,6 +863,7 @@ __device__ __forceinline__ bool peel_certainly_capped(const DevParams &P, const 
     if (P.dust) kapa = DADD(kapa, cs.rhokapD);
     return DMUL(kapa, La) >= kTauHuge;
   }
+  if (P.x.edge_open) return false;  // shearing boxes / atmospheres: the edge walk is not the one this bound reasons about
   double L = fmin(DSUB(pr.z, __ldg(P.zface + pr.kc - 1)), DSUB(__ldg(P.zface + pr.kc), pr.z));
   if (!P.zonly) {
     L = fmin(L, fmin(DSUB(pr.x, __ldg(P.xface + pr.ic - 1)), DSUB(__ldg(P.xface + pr.ic), pr.x)));
@@ -1465,7 +1489,7 @@ __global__ void __launch_bounds__(kBlock, LART_PEEL_MINBLOCKS) k_wf_peel(const _
           const PeelCont &c = cin[idx];
           ray_load(pr, &c.pr);
           ray_resume(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, c.tx, c.ty, c.tz, c.delx, c.dely, c.delz, c.d, c.tau,
-                     c.xfreq, c.u1, c.ic, c.jc, c.kc);
+                     c.xfreq, c.u1, c.ic, c.jc, c.kc, P.x.edge_open != 0);
           have = true;
         } else {
           ray_load(pr, q.rays + q.direct_base + (idx - ncont));
@@ -2119,6 +2143,7 @@ __global__ void __launch_bounds__(kBlock) k_sightline(const __grid_constant__ De
       double tau = 0.0;
       if (!ray_setup(P, r, s.x, s.y, s.z, s.kx, s.ky, s.kz, s.ic, s.jc, s.kc, x0, false)) {
         for (;;) {  // raytrace_to_edge_car_tau_gas: gas opacity only, no tau cap
+          if (P.x.atm && ray_masked(P, r)) { r.tau = __longlong_as_double(0x7ff0000000000000LL); break; }  // _atmosphere :3832-3836
           const double kap = DMUL(r.cell.rhokap, voigt_seon2(vtab, r.xfreq, r.cell.voigt_a));
           ++r.nsteps;
           const int ax = ray_axis(P, r);
@@ -2136,6 +2161,11 @@ __global__ void __launch_bounds__(kBlock) k_sightline(const __grid_constant__ De
       double N = 0.0, td = 0.0;
       if (!ray_setup(P, r, s.x, s.y, s.z, s.kx, s.ky, s.kz, s.ic, s.jc, s.kc, 0.0, false)) {
         for (;;) {  // raytrace_to_edge_car_column
+          if (P.x.atm && ray_masked(P, r)) {  // _column_atmosphere :3933-3938
+            N = __longlong_as_double(0x7ff0000000000000LL);
+            if (P.dust) td = N;
+            break;
+          }
           const double rho = DMUL(r.cell.rhokap, r.cell.Dfreq) / cross0;
           const int ax = ray_axis(P, r);
           const double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
@@ -2282,6 +2312,7 @@ int add_device_to_host(lart_gpu_ctx *h, const double *dev, long long total, cons
 }  // namespace
 
 struct lart_gpu_ctx {
+  long long jp_bins = 0;  // bins of the CALCP / CALCPnew arrays (CALCJ: nxfreq times as many)
   int device = 0;
   DevParams P{};
   Pool pool{};
@@ -2552,6 +2583,31 @@ int validate(const lart_config *c) {
     if (g.i0 < 1 || g.i0 > 2 || g.j0 < 1 || g.j0 > 2 || (p.xyz_symmetry && (g.k0 < 1 || g.k0 > 2)))
       return fail("lart_gpu_create: folded grids need grid.i0/j0(/k0) in {1,2} (grid_mod_car.f90:85-134)");
   }
+  // ---- atmospheres, shearing boxes, CALCJ / CALCP / CALCPnew
+  const bool extras = p.atmosphere || p.Omega != 0.0 || p.calc_J || p.calc_P || p.calc_Pnew;
+  if (extras && (p.use_clump_medium || p.use_amr_grid))
+    return fail("lart_gpu_create: atmospheres, shearing boxes and the CALCJ/CALCP accumulators are Cartesian-grid options");
+  if (p.atmosphere < 0 || p.atmosphere > LART_ATM_SPHERICAL) return fail("lart_gpu_create: par.atmosphere must be a LART_ATM_* value");
+  if (p.atmosphere == LART_ATM_PLANE && !(p.xy_periodic && g.nx == 1 && g.ny == 1))
+    return fail("lart_gpu_create: a plane atmosphere is a 1 x 1 x nz periodic column (setup.f90:86-94)");
+  if (p.atmosphere == LART_ATM_SPHERICAL) {
+    if (p.xy_periodic || p.xyz_symmetry) return fail("lart_gpu_create: a spherical atmosphere excludes xy_periodic and xyz_symmetry (setup.f90:95-98)");
+    if (!g.mask) return fail("lart_gpu_create: a spherical atmosphere needs grid.mask");
+  }
+  if (p.source_geometry == LART_SRC_PLANE_ILLUMINATION && !p.atmosphere)
+    return fail("lart_gpu_create: plane illumination needs an atmosphere geometry (generate_photon.f90:742-778)");
+  if (p.source_geometry < 0 || p.source_geometry > LART_SRC_PLANE_ILLUMINATION) return fail("lart_gpu_create: unknown source_geometry");
+  if (p.Omega != 0.0 && !(p.xy_periodic && g.nx > 1 && g.ny > 1))
+    return fail("lart_gpu_create: par.Omega (shearing box) needs xy_periodic with nx, ny > 1 (setup.f90:966-969)");
+  if (p.calc_J || p.calc_P || p.calc_Pnew) {
+    const int gj = g.geometry_JPa;
+    if (!(gj == 3 || gj == 2 || gj == 1 || gj == -1)) return fail("lart_gpu_create: grid.geometry_JPa must be 3, 2, 1 or -1");
+    if ((gj == 1 || gj == 2) && g.nr < 1) return fail("lart_gpu_create: grid.nr must be >= 1 for geometry_JPa 1 and 2");
+    if (gj == 1 && !g.ind_sph) return fail("lart_gpu_create: geometry_JPa = 1 needs grid.ind_sph");
+    if (gj == 2 && !g.ind_cyl) return fail("lart_gpu_create: geometry_JPa = 2 needs grid.ind_cyl");
+    if ((p.calc_P || p.calc_Pnew) && !(c->line.cross0 > 0.0)) return fail("lart_gpu_create: CALCP / CALCPnew need line.cross0 > 0");
+    if (c->flags & LART_FLAG_LOCAL_STEPS) return fail("lart_gpu_create: LART_FLAG_LOCAL_STEPS does not carry the CALCJ/CALCP accumulators");
+  }
   return 0;
 }
 }  // namespace
@@ -2694,7 +2750,23 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   P.sym = p.xyz_symmetry ? 1 : 0; P.i0 = g.i0; P.j0 = g.j0; P.k0 = g.k0;
   P.bcxy = P.sym ? BC_MIRROR : (p.xy_symmetry ? BC_MIRROR : ((p.xy_periodic && !zonly_grid) ? BC_PERIODIC : BC_OPEN));
   P.bcz = P.sym ? BC_MIRROR : BC_OPEN;
-  P.local_steps = ((cfg->flags & LART_FLAG_LOCAL_STEPS) && !P.bcxy) ? 1 : 0;  // the in-stage cell step knows no mirror planes or wrap-around
+  // ---- the less common bindings (setup.f90:959-987) and the CALCJ / CALCP / CALCPnew accumulators
+  DevExtras &X = P.x;
+  X = DevExtras{};
+  X.atm = p.atmosphere;
+  X.shear = (P.bcxy == BC_PERIODIC && p.Omega != 0.0) ? 1 : 0;  // :967-969
+  X.Omega = p.Omega;
+  X.edge_open = (X.atm || X.shear) ? 1 : 0;
+  X.calc_J = p.calc_J ? 1 : 0; X.calc_P = p.calc_P ? 1 : 0; X.calc_Pnew = p.calc_Pnew ? 1 : 0;
+  X.jp = (X.calc_J || X.calc_P || X.calc_Pnew) ? 1 : 0;
+  X.geometry_JPa = g.geometry_JPa; X.nr = g.nr; X.cross0 = cfg->line.cross0;
+  X.any = (X.atm || X.shear || X.jp) ? 1 : 0;
+  if (X.atm == LART_ATM_SPHERICAL) {
+    if ((rc = dupload(h, (const int8_t **)&X.mask, g.mask, nc))) return bail(rc);
+  }
+  if (X.jp && g.geometry_JPa == 1 && (rc = dupload(h, &X.ind_sph, g.ind_sph, nc))) return bail(rc);
+  if (X.jp && g.geometry_JPa == 2 && (rc = dupload(h, &X.ind_cyl, g.ind_cyl, (size_t)g.nx * g.ny))) return bail(rc);
+  P.local_steps = ((cfg->flags & LART_FLAG_LOCAL_STEPS) && !P.bcxy && !X.any) ? 1 : 0;  // the in-stage cell step knows no mirror planes or wrap-around
   // ---- clump medium: records packed on the device from the host's arrays (clump_mod.f90:30-118)
   P.clump = 0;
   P.cl = DevClumps{};
@@ -2814,6 +2886,15 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   }
   L.scalars = take(true, 2);
   L.counters = take(true, C_COUNT);
+  {  // behind everything else, so that the common layouts stay as they were
+    const long long nb = X.jp ? (g.geometry_JPa == 3 ? (long long)nc : g.geometry_JPa == 2 ? (long long)g.nr * g.nz
+                                 : g.geometry_JPa == 1 ? (long long)g.nr : (long long)g.nz) : 0;
+    h->jp_bins = nb;
+    L.Jabs2 = take(X.atm != 0, g.nxfreq);
+    L.J = take(X.calc_J != 0, (long long)g.nxfreq * nb);
+    L.Pa = take(X.calc_P != 0, nb);
+    L.Pnew = take(X.calc_Pnew != 0, nb);
+  }
   lap("pack cells, clumps, observers");
   L.total = off;
   if ((rc = dalloc(h, &P.tally, (size_t)L.total))) return bail(rc);
@@ -3369,6 +3450,10 @@ int lart_gpu_fetch(lart_gpu_handle h, lart_tallies *out) {
       if (L.img[q] >= 0) seg(c2[q], base + L.img[q], n2);
     }
   }
+  seg(out->Jabs2, L.Jabs2, P.nxfreq);
+  seg(out->J, L.J, (long long)P.nxfreq * h->jp_bins);
+  seg(out->Pa, L.Pa, h->jp_bins);
+  seg(out->Pnew, L.Pnew, h->jp_bins);
   double tail[2 + C_COUNT];
   segs.push_back({tail, L.scalars, 2 + C_COUNT});  // scalars and counters are adjacent in the layout
   for (double &v : tail) v = 0.0;

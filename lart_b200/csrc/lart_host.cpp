@@ -77,6 +77,10 @@ struct Par {
          clump_NHI = -1.0, clump_sigma_v = 0.0;
   bool comoving_source = true, recoil = false, core_skip = false, core_skip_global = false;
   bool xyz_symmetry = false, xy_symmetry = false, xy_periodic = false, z_symmetry = false;
+  double Omega = 0.0;  // define.f90:312 — taken as the value the ray tracer adds (after grid_mod_car.f90:348-350)
+  // the reference's compile-time options -DCALCJ / -DCALCP / -DCALCPnew as run-time keys of the mini-host
+  bool calc_J = false, calc_P = false, calc_Pnew = false, save_all = false;
+  int geometry_JPa = 2147483647;  // define.f90:269 huge(1)
   std::string geometry, velocity_type;
   int nx = 1, ny = 1, nz = 11, nr = -999;
   double xmax = 1.0, ymax = 1.0, zmax = 1.0, rmin = -999.0, rmax = -999.0, source_rmax = -999.0;
@@ -123,6 +127,10 @@ struct lart_host_model {
   bool is_setup = false;
   // grid arrays
   std::vector<double> xface, yface, zface, rhokap, voigt_a, Dfreq, vfx, vfy, vfz, rhokapD;
+  std::vector<int8_t> mask;                                  // grid%mask (spherical atmospheres)
+  std::vector<int32_t> ind_sph, ind_cyl, ncount;             // create_JPa_mem: radial bin of a cell, cells per output bin
+  int jp_nr = 0;
+  size_t jp_bins = 0;                                        // bins of Pa / Pnew; J has nxfreq times as many
   // scattering matrix
   std::vector<double> sm_coss, sm_S11, sm_S12, sm_S33, sm_S34, sm_pdf;
   std::vector<int32_t> sm_alias;
@@ -211,6 +219,7 @@ int set_key(lart_host_model *m, std::string key, const std::string &value) {
   REAL(clump_f_cov) REAL(clump_tau0) REAL(clump_NHI) REAL(clump_sigma_v)
   BOOL(comoving_source) BOOL(recoil) BOOL(core_skip) BOOL(core_skip_global)
   BOOL(xyz_symmetry) BOOL(xy_symmetry) BOOL(xy_periodic) BOOL(z_symmetry)
+  REAL(Omega) BOOL(calc_J) BOOL(calc_P) BOOL(calc_Pnew) BOOL(save_all) INT(geometry_JPa)
   STR(geometry) STR(velocity_type)
   INT(nx) INT(ny) INT(nz) INT(nr)
   REAL(xmax) REAL(ymax) REAL(zmax) REAL(rmin) REAL(rmax) REAL(source_rmax)
@@ -298,9 +307,26 @@ int derive(lart_host_model *m) {
   p.spectral_type = lower(p.spectral_type);
   if (p.geometry.empty()) p.geometry = "sphere";   // :70-75
   if (p.geometry == "box") p.geometry = "rectangle";
-  if (p.geometry != "sphere" && p.geometry != "rectangle" && p.geometry != "cylinder") {
+  if (p.geometry != "sphere" && p.geometry != "rectangle" && p.geometry != "cylinder" && p.geometry != "plane_atmosphere" &&
+      p.geometry != "spherical_atmosphere") {
     g_err = "geometry '" + p.geometry + "' stays with the Fortran host (not on the GPU path)"; return 1;
   }
+  // exoplanet atmospheres — setup.f90:86-113.  Upstream reads their density from a profile file (read_plane_data /
+  // read_spherical_data); this mini-host builds an exponential profile from density_zscale / density_rscale instead.
+  if (p.geometry == "plane_atmosphere") {
+    p.xy_periodic = true; p.xyz_symmetry = false; p.xy_symmetry = false;
+    p.xmax = p.zmax; p.ymax = p.zmax; p.nx = 1; p.ny = 1; p.rmax = -1.0;
+  } else if (p.geometry == "spherical_atmosphere") {
+    p.xy_periodic = false; p.xyz_symmetry = false;
+    if (p.xy_symmetry) {
+      p.nx = std::max(p.nx, p.ny); p.ny = p.nx; p.xmax = std::max(p.xmax, p.ymax); p.ymax = p.xmax;
+    } else {
+      p.nx = std::max({p.nx, p.ny, p.nz}); p.ny = p.nx; p.nz = p.nx;
+      p.xmax = std::max({p.xmax, p.ymax, p.zmax}); p.ymax = p.xmax; p.zmax = p.xmax;
+    }
+    if (p.rmax <= 0.0) p.rmax = p.xmax;
+  }
+  if (p.Omega != 0.0 && !(p.xy_periodic && p.nx > 1 && p.ny > 1)) { g_err = "par%Omega needs an xy_periodic box with nx, ny > 1"; return 1; }
   // setup_resonance_line, Ly-alpha branch — line_mod.f90:1241-1270
   if (lower(p.line_id) != "ly_alpha" || p.fine_structure) { g_err = "only line_id='ly_alpha' without fine structure (line_type 1) is on this path"; return 1; }
   {
@@ -349,7 +375,7 @@ int derive(lart_host_model *m) {
     for (double v : {p.rmax, p.xmax, p.ymax}) if (v > 0.0) r0 = std::max(r0, v);
     if (r0 > 0.0) { p.rmax = r0; p.xmax = r0; p.ymax = r0; }
     if (!p.xy_symmetry) { p.nx = std::max(p.nx, p.ny); p.ny = p.nx; }
-  } else {
+  } else if (p.geometry == "rectangle") {
     p.rmax = -1.0;
   }
   if (p.source_rmax < 0.0) p.source_rmax = p.rmax;  // :432
@@ -370,8 +396,28 @@ int derive(lart_host_model *m) {
     p.DGR = 0.0;
   }
   if (p.DGR == 0.0) p.save_Jabs = false;
-  if (p.source_geometry != "point" && p.source_geometry != "uniform" && p.source_geometry != "uniform_sphere" && p.source_geometry != "sphere") {
+  if (p.source_geometry != "point" && p.source_geometry != "uniform" && p.source_geometry != "uniform_sphere" && p.source_geometry != "sphere" &&
+      p.source_geometry != "plane_illumination") {
     g_err = "source_geometry '" + p.source_geometry + "' stays with the Fortran host"; return 1;
+  }
+  if (p.source_geometry == "plane_illumination" && p.geometry != "plane_atmosphere" && p.geometry != "spherical_atmosphere") {
+    g_err = "source_geometry 'plane_illumination' needs an atmosphere geometry (generate_photon.f90:742-778)"; return 1;
+  }
+  if (p.calc_J || p.calc_P || p.calc_Pnew) {  // setup.f90:438-455
+    if (p.use_clump_medium || p.use_amr_grid) { g_err = "CALCJ/CALCP accumulators: Cartesian grids only on this path"; return 1; }
+    if (p.rmax <= 0.0) p.geometry_JPa = 3;
+    if (p.geometry_JPa < -1 || p.geometry_JPa > 3) {
+      p.geometry_JPa = 1;
+      if (p.save_all) p.geometry_JPa = 3;
+      if (p.geometry_JPa != 3) {
+        if (p.xy_periodic) p.geometry_JPa = -1;
+        else if (p.xyz_symmetry) p.geometry_JPa = 1;
+        else if (p.xy_symmetry) p.geometry_JPa = 2;
+        else if (p.geometry == "cylinder") p.geometry_JPa = 2;
+        else if (p.geometry == "spherical_atmosphere") p.geometry_JPa = 2;
+      }
+    }
+    if (p.geometry_JPa == 0) { g_err = "par%geometry_JPa = 0 is not a geometry"; return 1; }
   }
   static const char *spec_ok[] = {"voigt", "voigt0", "continuum", "gaussian", "monochromatic", "mono", nullptr};
   bool ok = false;
@@ -767,7 +813,68 @@ int grid_create(lart_host_model *m) {
       xcrit2 = xcrit * xcrit;
     }
   }
+  // grid%mask — grid_mod_car.f90:247-250, 320-330: cells whose centre lies within rmin belong to the planet
+  m->mask.clear();
+  if (p.geometry == "spherical_atmosphere") {
+    m->mask.assign(nc, 0);
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i)
+      if (std::sqrt(xx[i] * xx[i] + yy[j] * yy[j] + zz[k] * zz[k]) <= p.rmin) m->mask[at(i, j, k)] = -1;
+  }
+  // create_JPa_mem — grid_mod_car.f90:1242-1440: radial bin of every cell and the number of cells per output bin
+  m->ind_sph.clear(); m->ind_cyl.clear(); m->ncount.clear(); m->jp_nr = 0; m->jp_bins = 0;
+  if (p.calc_J || p.calc_P || p.calc_Pnew) {
+    const int gj = p.geometry_JPa;
+    int nr = 0;
+    double rmaxJ = 0.0, dr = 0.0, roff = 0.0;
+    if (gj == 2 || gj == 1) {
+      nr = (gj == 2) ? std::max(nx, ny) : std::max({nx, ny, nz});
+      const bool folded = (gj == 2) ? p.xy_symmetry : p.xyz_symmetry;
+      if (!folded) nr = ((nr / 2) * 2 == nr) ? nr / 2 : (nr - 1) / 2 + 1;
+      rmaxJ = (gj == 2) ? std::min(p.xmax, p.ymax) : std::min({p.xmax, p.ymax, p.zmax});
+      if ((nr / 2) * 2 == nr) { dr = rmaxJ / nr; roff = 0.0; }   // :1281-1289 ("minor-bug fixed (2021.05.26)")
+      else { dr = rmaxJ / (nr - 0.5); roff = -dr / 2.0; }
+    }
+    auto nadd_of = [&](int i, int j, int k, bool with_z) {
+      int nadd = with_z ? 8 : 4;
+      if (i == 0 && (nx / 2) * 2 != nx) nadd /= 2;
+      if (j == 0 && (ny / 2) * 2 != ny) nadd /= 2;
+      if (with_z && k == 0 && (nz / 2) * 2 != nz) nadd /= 2;
+      return nadd;
+    };
+    if (gj == 1) {
+      m->ind_sph.assign(nc, 0); m->ncount.assign(nr, 0); m->jp_bins = nr;
+      for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+        const int ir = static_cast<int>(std::floor((std::sqrt(xx[i] * xx[i] + yy[j] * yy[j] + zz[k] * zz[k]) - roff) / dr)) + 1;
+        m->ind_sph[at(i, j, k)] = ir;
+        if (m->rhokap[at(i, j, k)] > 0.0 && ir >= 1 && ir <= nr) m->ncount[ir - 1] += p.xyz_symmetry ? nadd_of(i, j, k, true) : 1;
+      }
+    } else if (gj == 2) {
+      m->ind_cyl.assign(static_cast<size_t>(nx) * ny, 0); m->ncount.assign(static_cast<size_t>(nr) * nz, 0);
+      m->jp_bins = static_cast<size_t>(nr) * nz;
+      for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+        const int ir = static_cast<int>(std::floor((std::sqrt(xx[i] * xx[i] + yy[j] * yy[j]) - roff) / dr)) + 1;
+        m->ind_cyl[i + static_cast<size_t>(nx) * j] = ir;
+        if (m->rhokap[at(i, j, k)] > 0.0 && ir >= 1 && ir <= nr)
+          m->ncount[(ir - 1) + static_cast<size_t>(nr) * k] += p.xy_symmetry ? nadd_of(i, j, k, false) : 1;
+      }
+    } else if (gj == -1) {
+      m->ncount.assign(nz, 0); m->jp_bins = nz;
+      for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i)
+        if (m->rhokap[at(i, j, k)] > 0.0) m->ncount[k] += 1;
+    } else {
+      m->jp_bins = nc;
+      if (p.xyz_symmetry) {
+        m->ncount.assign(nc, 0);
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) m->ncount[at(i, j, k)] = nadd_of(i, j, k, true);
+      }
+    }
+    m->jp_nr = nr;
+  }
   lart_grid &g = m->cfg.grid;
+  g.mask = m->mask.empty() ? nullptr : m->mask.data();
+  g.geometry_JPa = (p.calc_J || p.calc_P || p.calc_Pnew) ? p.geometry_JPa : 0; g.nr = m->jp_nr;
+  g.ind_sph = m->ind_sph.empty() ? nullptr : m->ind_sph.data();
+  g.ind_cyl = m->ind_cyl.empty() ? nullptr : m->ind_cyl.data();
   g.nx = nx; g.ny = ny; g.nz = nz; g.nxfreq = p.nxfreq;
   g.xmin = xmin; g.ymin = ymin; g.zmin = zmin; g.xmax = p.xmax; g.ymax = p.ymax; g.zmax = p.zmax;
   g.dx = dx; g.dy = dy; g.dz = dz;
@@ -1144,6 +1251,10 @@ void alloc_tallies(lart_host_model *m) {
   m->tal.Jout = alloc(m, nxf);
   if (p.save_Jin) m->tal.Jin = alloc(m, nxf);
   if (p.DGR > 0.0 && p.save_Jabs) m->tal.Jabs = alloc(m, nxf);
+  if (p.geometry == "plane_atmosphere" || p.geometry == "spherical_atmosphere") m->tal.Jabs2 = alloc(m, nxf);  // grid_mod_car.f90:1179-1183
+  if (p.calc_J) m->tal.J = alloc(m, nxf * m->jp_bins);   // :1422-1434
+  if (p.calc_P) m->tal.Pa = alloc(m, m->jp_bins);        // :1385-1395
+  if (p.calc_Pnew) m->tal.Pnew = alloc(m, m->jp_bins);   // :1410-1420
   if (p.save_Jmu) m->tal.Jmu = alloc(m, nxf * p.nmu);
   m->obs_out.assign(p.save_peeloff ? p.nobs : 0, lart_observer_out{});
   for (auto &oo : m->obs_out) {  // observer_rect.f90:286-330
@@ -1269,10 +1380,13 @@ int lart_host_setup(lart_host_model *m) {
   q.use_stokes = p.use_stokes; q.use_reduced_wgt = p.use_reduced_wgt;
   q.save_Jin = p.save_Jin; q.save_Jabs = p.save_Jabs; q.save_Jmu = p.save_Jmu;
   q.save_peeloff = p.save_peeloff; q.save_peeloff_2D = p.save_peeloff_2D; q.save_peeloff_3D = p.save_peeloff_3D; q.save_direc0 = p.save_direc0;
+  if (p.source_geometry == "plane_illumination") q.source_geometry = LART_SRC_PLANE_ILLUMINATION;
+  q.atmosphere = (p.geometry == "plane_atmosphere") ? LART_ATM_PLANE : (p.geometry == "spherical_atmosphere") ? LART_ATM_SPHERICAL : LART_ATM_NONE;
+  q.calc_J = p.calc_J; q.calc_P = p.calc_P; q.calc_Pnew = p.calc_Pnew; q.Omega = p.Omega;
   q.save_all_photons = p.save_all_photons; q.xy_periodic = p.xy_periodic; q.xyz_symmetry = p.xyz_symmetry; q.xy_symmetry = p.xy_symmetry; q.use_clump_medium = p.use_clump_medium; q.nobs = p.nobs; q.use_amr_grid = p.use_amr_grid;
   const Line &ln = m->line;
   c.line.line_type = ln.line_type; c.line.E1 = ln.E1; c.line.E2 = ln.E2; c.line.E3 = ln.E3;
-  c.line.g_recoil0 = ln.g_recoil0; c.line.DnuHK_Hz = ln.DnuHK_Hz;
+  c.line.g_recoil0 = ln.g_recoil0; c.line.DnuHK_Hz = ln.DnuHK_Hz; c.line.cross0 = ln.cross0;
   lart_scatt_mat &sm = c.scatt_mat;
   sm = lart_scatt_mat{};
   if (!m->sm_coss.empty() && p.DGR > 0.0) {
@@ -1326,8 +1440,37 @@ int lart_host_normalize(lart_host_model *m) {
     t.Jout[i] /= den;
     if (t.Jin) t.Jin[i] /= den;
     if (t.Jabs) t.Jabs[i] /= den;
+    if (t.Jabs2) t.Jabs2[i] /= den;  // :238-248
   }
   if (t.Jmu) for (size_t i = 0; i < nxf * p.nmu; ++i) t.Jmu[i] = t.Jmu[i] * p.nmu / den;
+  // CALCJ / CALCP / CALCPnew — :275-400: per-bin cell counts, cell volume, and for periodic boxes the surface area
+  if (t.J || t.Pa || t.Pnew) {
+    const double d2 = p.distance2cm * p.distance2cm;
+    const double dVol = g.dx * g.dy * g.dz * d2;
+    const double slab_area = (g.xmax - g.xmin) * (g.ymax - g.ymin) * d2;  // :177
+    const int gj = p.geometry_JPa;
+    const size_t nb = m->jp_bins;
+    for (size_t b = 0; b < nb; ++b) {
+      double fJ, fP;  // multiplicative factors of J(:,b) and P(b)
+      const double cnt = m->ncount.empty() ? 1.0 : static_cast<double>(m->ncount[b]);
+      if (gj == 3) {
+        fJ = p.xy_periodic ? slab_area / (kFourPi * dVol * nph * bin_unit) : 1.0 / (kFourPi * dVol * nph * bin_unit);
+        fP = p.xy_periodic ? slab_area / (dVol * nph) : 1.0 / (dVol * nph);
+        if (p.xyz_symmetry) { fJ /= cnt; fP /= cnt; }
+      } else if (gj == -1) {
+        if (!(cnt > 0.0)) continue;
+        fJ = 1.0 / cnt * (slab_area / (kFourPi * dVol * nph * bin_unit));
+        fP = 1.0 / cnt * (slab_area / (dVol * nph));
+      } else {
+        if (!(cnt > 0.0)) continue;
+        fJ = 1.0 / cnt / (kFourPi * dVol * nph * bin_unit);
+        fP = 1.0 / cnt / (dVol * nph);
+      }
+      if (t.J) for (size_t i = 0; i < nxf; ++i) t.J[i + nxf * b] *= fJ;
+      if (t.Pa) t.Pa[b] *= fP;
+      if (t.Pnew) t.Pnew[b] *= fP;
+    }
+  }
   // continuum runs are expressed in units of the input continuum level — output_sum_rect.f90:252-273
   // (par%continuum_normalize defaults to .true., define.f90:314; the reference aborts without save_Jin)
   if (p.spectral_type == "continuum" && p.continuum_normalize) {
@@ -1340,6 +1483,7 @@ int lart_host_normalize(lart_host_model *m) {
       t.Jout[i] /= scale;
       t.Jin[i] /= scale;
       if (t.Jabs) t.Jabs[i] /= scale;
+      if (t.Jabs2) t.Jabs2[i] /= scale;
     }
     if (t.Jmu) for (size_t i = 0; i < nxf * p.nmu; ++i) t.Jmu[i] /= scale;
   }

@@ -140,6 +140,17 @@ class Model:
             return _np(t.Jmu, (g.nxfreq, self.config.contents.par.nmu))
         return _np(getattr(t, name), (g.nxfreq,))
 
+    def jp_array(self, name):
+        """CALCJ / CALCP / CALCPnew accumulators (grid%J|J2|J1, Pa|P2|P1, Pa_new|...; grid_mod_car.f90:1385-1434):
+        name 'J' -> (nxfreq, bins...), 'Pa' / 'Pnew' -> (bins...), bins by par%geometry_JPa: 3 (nx,ny,nz), 2 (nr,nz),
+        1 (nr,), -1 (nz,).  None when the accumulator is off."""
+        g = self.config.contents.grid
+        bins = {3: (g.nx, g.ny, g.nz), 2: (g.nr, g.nz), 1: (g.nr,), -1: (g.nz,)}.get(g.geometry_JPa)
+        ptr = getattr(self.tallies.contents, name)
+        if not ptr or bins is None:
+            return None
+        return _np(ptr, ((g.nxfreq,) + bins) if name == "J" else bins)
+
     def xfreq(self):
         """bin centres, grid%xfreq (grid_mod_car.f90:1505)."""
         g = self.config.contents.grid

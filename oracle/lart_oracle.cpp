@@ -31,6 +31,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <thread>
 #include <vector>
@@ -235,6 +236,7 @@ struct Photon {
   int icell = 1, jcell = 1, kcell = 1;  // 1-based like the reference
   int icl = 0;                          // icell_clump: 0 = vacuum, > 0 = current clump (clump medium only)
   double xfreq = 0, xfreq_ref = 0, wgt = 1;
+  double vfy_shear = 0;                 // photon%vfy_shear (define.f90:100): shearing-box velocity offset picked up at x wraps
   bool inside = true;
   double I = 1, Q = 0, U = 0, V = 0;
   double E1 = 1, E2 = 0, E3 = 1;
@@ -252,6 +254,11 @@ struct World {
   int bcxy = 0, bcz = 0;  // BC_* of the x/y axes and of the z axis (setup.f90:952-976)
   const lart_clumps *cl = nullptr;  // par%use_clump_medium (clump_mod.f90)
   const lart_amr *amr = nullptr;    // par%use_amr_grid (octree_mod.f90): the photon's icell is a LEAF index, jcell = kcell = 1
+  int atm = 0;         // LART_ATM_*: par%geometry = 'plane_atmosphere' / 'spherical_atmosphere' (setup.f90:959-987)
+  bool shear = false;  // raytrace_to_tau_car_xyper_shear bound (setup.f90:967-969)
+  bool jp = false;     // any of the CALCJ / CALCP / CALCPnew accumulators
+  // spherical atmosphere: grid%mask == -1 marks the planet's molecular layer (grid_mod_car.f90:320-330)
+  inline bool masked(int i, int j, int k) const { return atm == LART_ATM_SPHERICAL && g->mask && g->mask[idx(i, j, k)] == -1; }
   inline size_t idx(int i, int j, int k) const {
     if (amr) return static_cast<size_t>(i > 0 ? i - 1 : 0);  // (a photon outside the octree reads leaf 1, never used)
     return static_cast<size_t>(i - 1) + static_cast<size_t>(g->nx) * (static_cast<size_t>(j - 1) + static_cast<size_t>(g->ny) * static_cast<size_t>(k - 1));
@@ -286,7 +293,7 @@ inline void atomic_add(double *p, double v) {
 }
 
 struct Tally {
-  std::vector<double> Jout, Jin, Jabs, Jmu;
+  std::vector<double> Jout, Jin, Jabs, Jmu, Jabs2;
   double nscatt_gas = 0, nscatt_dust = 0;
   Counters cnt;
   lart_tallies *shared;  // cubes + allph written straight into the caller's buffers
@@ -376,8 +383,17 @@ inline int minloc3(double tx, double ty, double tz) {
 // raytrace_to_edge_car — raytrace_car.f90:410-508; _zonly :1138-1234.
 // Optional trace of visited cells (0-based linear index) for parity tests.
 // ---------------------------------------------------------------------------
-double raytrace_to_edge(const World &w, const Photon &p0, Counters *cnt, int *nsteps_out = nullptr,
+// With a shearing box or an atmosphere model the reference leaves raytrace_to_edge bound to the plain open-box routine
+// (setup.f90:947-950 is not overridden at :959-969; spherical atmospheres bind raytrace_to_edge_car_atmosphere, :984, even
+// with xy_symmetry): the walk then ignores the periodic / z-only / mirror binding of the to_tau routine.
+inline World edge_world(const World &w0) {
+  World w = w0;
+  if (w.shear || w.atm) { w.zonly = false; w.bcxy = 0; w.bcz = 0; }
+  return w;
+}
+double raytrace_to_edge(const World &w0, const Photon &p0, Counters *cnt, int *nsteps_out = nullptr,
                         int trace_cap = 0, int32_t *trace = nullptr) {
+  const World w = edge_world(w0);
   const lart_grid &g = *w.g;
   double xp = p0.x, yp = p0.y, zp = p0.z, kx = p0.kx, ky = p0.ky, kz = p0.kz;
   int ic = p0.icell, jc = p0.jcell, kc = p0.kcell;
@@ -392,6 +408,7 @@ double raytrace_to_edge(const World &w, const Photon &p0, Counters *cnt, int *ns
   double u1 = w.vdotk(io, jo, ko, kx, ky, kz);
   double xfreq = p0.xfreq;
   for (;;) {
+    if (w.masked(ic, jc, kc)) { tau = std::numeric_limits<double>::infinity(); break; }  // raytrace_car.f90:3729-3733
     double rhokap = w.rhokap(ic, jc, kc) * w.calc_voigt(xfreq, ic, jc, kc);
     if (w.dust()) rhokap += w.rhokapD(ic, jc, kc);
     if (trace && nsteps < trace_cap) trace[nsteps] = static_cast<int32_t>(w.idx(ic, jc, kc));
@@ -435,8 +452,61 @@ inline int jmu_bin(const lart_params &par, double kz) {
 }
 
 // ---------------------------------------------------------------------------
-// raytrace_to_tau_car — raytrace_car.f90:1425-1648; _zonly :2519-2675.
-// `tl` may be null (unit-level batch calls: no Jout tally).
+// CALCJ / CALCP / CALCPnew accumulators (compile-time options of the reference, run-time flags here).
+// jp_bin: the bin of cell (i,j,k) in the P arrays by par%geometry_JPa — 3: the cell, 2: (ind_cyl(i,j), k), 1: ind_sph(i,j,k),
+// -1: k; -1 when the cell takes no deposit (guards of raytrace_car.f90:3989-3991, :3996).  The reference does not range-check
+// ind_sph; a bin outside 1..nr is skipped here instead of written out of bounds.
+// ---------------------------------------------------------------------------
+inline long long jp_bin(const World &w, int i, int j, int k) {
+  const lart_grid &g = *w.g;
+  if (!(i > 0 && i <= g.nx && j > 0 && j <= g.ny && k > 0 && k <= g.nz)) return -1;
+  if (!(w.rhokap(i, j, k) > 0.0)) return -1;
+  switch (g.geometry_JPa) {
+    case 3: return static_cast<long long>(w.idx(i, j, k));
+    case 2: {
+      const int ir = g.ind_cyl[(i - 1) + static_cast<size_t>(g.nx) * (j - 1)];
+      return (ir >= 1 && ir <= g.nr) ? (ir - 1) + static_cast<long long>(g.nr) * (k - 1) : -1;
+    }
+    case 1: {
+      const int ir = g.ind_sph[w.idx(i, j, k)];
+      return (ir >= 1 && ir <= g.nr) ? ir - 1 : -1;
+    }
+    default: return k - 1;
+  }
+}
+// add_to_J — raytrace_car.f90:3979-4011
+inline void add_to_J(const World &w, const Photon &ph, Tally *tl, int i, int j, int k, double del) {
+  if (!w.par->calc_J || !tl || !tl->shared->J) return;
+  const lart_grid &g = *w.g;
+  if (!(i > 0 && i <= g.nx && j > 0 && j <= g.ny && k > 0 && k <= g.nz)) return;
+  const double xref = ph.xfreq * (w.Dfreq(i, j, k) / g.Dfreq_ref);
+  const int ix = static_cast<int>(std::floor((xref - g.xfreq_min) / g.dxfreq)) + 1;
+  if (!(ix > 0 && ix <= g.nxfreq)) return;
+  const long long b = jp_bin(w, i, j, k);
+  if (b >= 0) atomic_add(tl->shared->J + (ix - 1) + static_cast<size_t>(g.nxfreq) * b, del * ph.wgt);
+}
+// add_to_Pnew — raytrace_car.f90:4015-4045
+inline void add_to_Pnew(const World &w, const Photon &ph, Tally *tl, int i, int j, int k, double dtauH) {
+  if (!w.par->calc_Pnew || !tl || !tl->shared->Pnew) return;
+  const long long b = jp_bin(w, i, j, k);
+  if (b < 0) return;
+  const double rhokap = w.rhokap(i, j, k) * w.Dfreq(i, j, k) / w.line->cross0;
+  atomic_add(tl->shared->Pnew + b, dtauH * ph.wgt / rhokap);
+}
+// add_to_Pa — scattering_car.f90:829-860
+inline void add_to_Pa(const World &w, const Photon &ph, Tally &tl) {
+  if (!w.par->calc_P || !tl.shared->Pa) return;
+  const int i = ph.icell, j = ph.jcell, k = ph.kcell;
+  const long long b = jp_bin(w, i, j, k);
+  if (b < 0) return;
+  const double rhokap = w.rhokap(i, j, k) * w.Dfreq(i, j, k) / w.line->cross0;
+  atomic_add(tl.shared->Pa + b, ph.wgt / rhokap);
+}
+
+// ---------------------------------------------------------------------------
+// raytrace_to_tau_car — raytrace_car.f90:1425-1648; _zonly :2519-2675; the shearing box _xyper_shear :2677-2954; the
+// atmosphere models _zonly_atmosphere :2956-3117, _atmosphere :3119-3338, _xysym_atmosphere :3340-3663.
+// `tl` may be null (unit-level batch calls: no tallies).
 // ---------------------------------------------------------------------------
 void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Counters *cnt, int *nsteps_out = nullptr) {
   const lart_grid &g = *w.g;
@@ -449,22 +519,34 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
     if (nsteps_out) *nsteps_out = 0;
     return;
   }
-  double tau = 0.0, d = 0.0;
+  double tau = 0.0, d = 0.0, del = 0.0, dtauH = 0.0;
   int io = ic, jo = jc, ko = kc;
-  double u1 = w.vdotk(io, jo, ko, kx, ky, kz);
+  // the shearing box adds photon%vfy_shear to the cell's vfy in every line-of-sight velocity (:2809, :2905, :2932)
+  auto ulos = [&](int i, int j, int k) {
+    if (!w.shear) return w.vdotk(i, j, k, kx, ky, kz);
+    const size_t c = w.idx(i, j, k);
+    return g.vfx[c] * kx + (g.vfy[c] + ph.vfy_shear) * ky + g.vfz[c] * kz;
+  };
+  double u1 = ulos(io, jo, ko);
+  bool destroyed = false;
   while (ph.inside) {
-    double rhokap = w.rhokap(ic, jc, kc) * w.calc_voigt(ph.xfreq, ic, jc, kc);
+    if (w.masked(ic, jc, kc)) { destroyed = true; break; }  // :3186-3190 the planet's molecular layer destroys the photon
+    double rhokapH = w.rhokap(ic, jc, kc) * w.calc_voigt(ph.xfreq, ic, jc, kc);
+    double rhokap = rhokapH;
     if (w.dust()) rhokap += w.rhokapD(ic, jc, kc);
     ++nsteps;
     int m = w.zonly ? 3 : minloc3(t.tx, t.ty, t.tz);
     double tnext = (m == 1) ? t.tx : (m == 2) ? t.ty : t.tz;
-    double del = tnext - d;
+    del = tnext - d;
     tau += del * rhokap;
+    dtauH = del * rhokapH;
     d = tnext;
     if (tau >= tau_in) {  // :1513-1524
       if (rhokap > 0.0) {
         double d_overshoot = (tau - tau_in) / rhokap;
         d = d - d_overshoot;
+        del = del - d_overshoot;
+        dtauH = del * rhokapH;
       }
       // the ORIGINAL direction even after a reflection; the point is mirrored back below (:1936-1941)
       xp = xp + d * ph.kx;
@@ -473,7 +555,12 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
       break;
     }
     if (m == 1) {
+      const int before = ic + t.istep;
       if (!advance_axis(w.bcxy, ic, t.istep, kx, g.nx, g.i0)) { ph.inside = false; break; }
+      if (w.shear) {  // :2842-2850 the photon re-enters through the opposite x face of the sheared neighbour box
+        if (before < 1) ph.vfy_shear = ph.vfy_shear - w.par->Omega;
+        if (before > g.nx) ph.vfy_shear = ph.vfy_shear + w.par->Omega;
+      }
       t.tx += t.delx;
     } else if (m == 2) {
       if (!advance_axis(w.bcxy, jc, t.jstep, ky, g.ny, g.j0)) { ph.inside = false; break; }
@@ -482,24 +569,41 @@ void raytrace_to_tau(const World &w, Photon &ph, double tau_in, Tally *tl, Count
       if (!advance_axis(w.bcz, kc, t.kstep, kz, g.nz, g.k0)) { ph.inside = false; break; }
       t.tz += t.delz;
     }
-    double u2 = w.vdotk(ic, jc, kc, kx, ky, kz);
+    if (w.jp) {  // :1579-1584
+      add_to_J(w, ph, tl, io, jo, ko, del);
+      add_to_Pnew(w, ph, tl, io, jo, ko, dtauH);
+    }
+    double u2 = ulos(ic, jc, kc);
     ph.xfreq = (ph.xfreq + u1) * w.Dfreq(io, jo, ko) / w.Dfreq(ic, jc, kc) - u2;  // :1586-1589
     io = ic; jo = jc; ko = kc;
     u1 = u2;
   }
-  if (!ph.inside) {  // :1598-1602
-    ic = io; jc = jo; kc = ko;
-    // :1613-1623 — fluid frame -> lab frame, reference Doppler units, Jout bin
-    double ue = w.vdotk(ic, jc, kc, kx, ky, kz);
+  if (!ph.inside) { ic = io; jc = jo; kc = ko; }  // :1598-1602
+  // :1604-1609 the last segment.  Deviation: for a photon destroyed by the mask the reference calls add_to_J / add_to_Pnew
+  // once more with the PREVIOUS segment's del and dtauH, now credited to the masked cell (:3296-3301; the variables are
+  // undefined when the first cell is masked) — a stale-variable slip that neither side of the parity tests reproduces.
+  if (w.jp && !destroyed) {
+    add_to_J(w, ph, tl, ic, jc, kc, del);
+    add_to_Pnew(w, ph, tl, ic, jc, kc, dtauH);
+  }
+  if (!ph.inside || destroyed) {
+    // :1613-1623 — fluid frame -> lab frame, reference Doppler units, Jout bin; a destroyed photon is binned the same way
+    // into Jabs2 (:3316-3327), and so is one that leaves a plane atmosphere through its bottom cell (:3099-3107)
+    double ue = ulos(ic, jc, kc);
     ph.xfreq = ph.xfreq + ue;
     ph.xfreq_ref = ph.xfreq * (w.Dfreq(ic, jc, kc) / g.Dfreq_ref);
     if (tl) {
       int ix = static_cast<int>(std::floor((ph.xfreq_ref - g.xfreq_min) / g.dxfreq)) + 1;
       if (ix >= 1 && ix <= g.nxfreq) {
-        tl->Jout[ix - 1] += ph.wgt;
-        if (w.par->save_Jmu) tl->Jmu[(ix - 1) + static_cast<size_t>(g.nxfreq) * (jmu_bin(*w.par, ph.kz) - 1)] += ph.wgt;
+        if (destroyed || (w.atm == LART_ATM_PLANE && !(kc > 1))) {
+          tl->Jabs2[ix - 1] += ph.wgt;
+        } else {
+          tl->Jout[ix - 1] += ph.wgt;
+          if (w.par->save_Jmu) tl->Jmu[(ix - 1) + static_cast<size_t>(g.nxfreq) * (jmu_bin(*w.par, ph.kz) - 1)] += ph.wgt;
+        }
       }
     }
+    ph.inside = false;
   }
   if (w.bcxy == BC_MIRROR) {  // :1936-1947, :2236-2245 (d is the whole path when the photon left the grid)
     if (!ph.inside) { xp = ph.x + d * ph.kx; yp = ph.y + d * ph.ky; zp = ph.z + d * ph.kz; }
@@ -1559,6 +1663,7 @@ inline double sample_phi_stokes(Rng &r, const Photon &ph, double S12overS11) {
 void scatter_resonance_stokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
   const lart_params &par = *w.par;
   ph.nscatt_gas += ph.wgt;
+  add_to_Pa(w, ph, tl);  // :356-358
   double uz, xfreq_atom, cost, sint;
   do_resonance1(w, ph, r, uz, xfreq_atom, cost, sint);
   double cost2 = cost * cost;
@@ -1599,6 +1704,7 @@ void scatter_resonance_stokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
 void scatter_resonance_nostokes(const World &w, Photon &ph, Rng &r, Tally &tl) {
   const lart_params &par = *w.par;
   ph.nscatt_gas += ph.wgt;
+  add_to_Pa(w, ph, tl);  // :691-693
   double uz, xfreq_atom, cost, sint;
   do_resonance1(w, ph, r, uz, xfreq_atom, cost, sint);
   double phi = kTwoPi * r.uniform();
@@ -1736,6 +1842,15 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
       ph.z = (g.zmax - g.zmin) * r.uniform() + g.zmin;
     }
       break;
+    case LART_SRC_PLANE_ILLUMINATION:  // random_plane_illumination :729-760
+      if (w.atm == LART_ATM_PLANE) {
+        ph.x = 0.0; ph.y = 0.0; ph.z = g.zmax;  // par%zmax
+      } else {
+        double rp = g.rmax * std::sqrt(r.uniform());
+        double phi = (par.xy_symmetry ? kHalfPi : kTwoPi) * r.uniform();
+        ph.x = rp * std::cos(phi); ph.y = rp * std::sin(phi); ph.z = g.zmin;
+      }
+      break;
     default:  // :126-131
       ph.x = par.xs_point; ph.y = par.ys_point; ph.z = par.zs_point;
   }
@@ -1746,12 +1861,18 @@ void generate_photon(const World &w, Photon &ph, Rng &r, Tally &tl) {
     if (ph.y < g.ymin) ph.y = -ph.y;
     if (ph.z < g.zmin) ph.z = -ph.z;
   }
-  double uc, up;
-  r.uniform2(uc, up);
-  double cost = 2.0 * uc - 1.0;
-  double sint = std::sqrt(1.0 - cost * cost);
-  double phi = kTwoPi * up;
-  double cosp = std::cos(phi), sinp = std::sin(phi);
+  double cost, sint, cosp, sinp;
+  if (par.source_geometry == LART_SRC_PLANE_ILLUMINATION) {  // :765-778 a parallel beam, down onto the slab or up along +z
+    cost = (w.atm == LART_ATM_PLANE) ? -1.0 : 1.0;
+    sint = 0.0; cosp = 1.0; sinp = 0.0;
+  } else {
+    double uc, up;
+    r.uniform2(uc, up);
+    cost = 2.0 * uc - 1.0;
+    sint = std::sqrt(1.0 - cost * cost);
+    double phi = kTwoPi * up;
+    cosp = std::cos(phi); sinp = std::sin(phi);
+  }
   ph.kx = sint * cosp; ph.ky = sint * sinp; ph.kz = cost;
   if (w.amr) {  // generate_photon.f90:375-376
     ph.icell = amr_find_leaf(w, ph.x, ph.y, ph.z); ph.jcell = 1; ph.kcell = 1;
@@ -1923,6 +2044,7 @@ double raytrace_to_edge_tau_gas(const World &w, const Photon &p0, long long *nst
   double u1 = w.vdotk(io, jo, ko, kx, ky, kz);
   double xfreq = p0.xfreq;
   for (;;) {
+    if (w.masked(ic, jc, kc)) return std::numeric_limits<double>::infinity();  // _tau_gas_atmosphere, :3832-3836
     double rhokap = w.rhokap(ic, jc, kc) * w.calc_voigt(xfreq, ic, jc, kc);
     if (nsteps) ++*nsteps;
     int m = w.zonly ? 3 : minloc3(t.tx, t.ty, t.tz);
@@ -1947,6 +2069,11 @@ void raytrace_to_edge_column(const World &w, const Photon &p0, double cross0, do
   Trav t;
   if (setup_traversal(w, xp, yp, zp, kx, ky, kz, ic, jc, kc, t, false)) return;
   for (;;) {
+    if (w.masked(ic, jc, kc)) {  // _column_atmosphere, :3933-3938
+      N_gas = std::numeric_limits<double>::infinity();
+      if (w.dust()) tau_dust = std::numeric_limits<double>::infinity();
+      return;
+    }
     double rho = w.rhokap(ic, jc, kc) * w.Dfreq(ic, jc, kc) / cross0;
     double rkD = w.dust() ? w.rhokapD(ic, jc, kc) : 0.0;
     if (nsteps) ++*nsteps;
@@ -2034,6 +2161,9 @@ World make_world(const lart_config *cfg) {
   else if (cfg->par.xy_periodic && !w.zonly) w.bcxy = 2;                      // :966-975 (no shear)
   if (cfg->par.use_clump_medium && cfg->clumps.n > 0) w.cl = &cfg->clumps;    // :806-860
   if (cfg->par.use_amr_grid && cfg->amr.nleaf > 0) w.amr = &cfg->amr;         // the octree ray tracers and leaf physics
+  w.shear = w.bcxy == 2 && cfg->par.Omega != 0.0;                             // :967-969
+  w.atm = cfg->par.atmosphere;                                                // :959-962, :977-987
+  w.jp = cfg->par.calc_J || cfg->par.calc_P || cfg->par.calc_Pnew;
   return w;
 }
 
@@ -2235,6 +2365,7 @@ int oracle_run(const lart_config *cfg, int32_t rng_mode, int32_t nthreads, int64
     tl.Jout.assign(nxf, 0.0);
     tl.Jin.assign(nxf, 0.0);
     tl.Jabs.assign(nxf, 0.0);
+    tl.Jabs2.assign(nxf, 0.0);
     tl.Jmu.assign(static_cast<size_t>(nxf) * (cfg->par.save_Jmu ? cfg->par.nmu : 0), 0.0);
     tl.shared = out;
     th.emplace_back([&, t]() {
@@ -2253,6 +2384,7 @@ int oracle_run(const lart_config *cfg, int32_t rng_mode, int32_t nthreads, int64
       if (out->Jout) out->Jout[i] += tl.Jout[i];
       if (out->Jin) out->Jin[i] += tl.Jin[i];
       if (out->Jabs) out->Jabs[i] += tl.Jabs[i];
+      if (out->Jabs2) out->Jabs2[i] += tl.Jabs2[i];
     }
     if (out->Jmu) for (size_t i = 0; i < tl.Jmu.size(); ++i) out->Jmu[i] += tl.Jmu[i];
     out->nscatt_gas += tl.nscatt_gas;

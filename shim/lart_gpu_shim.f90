@@ -20,10 +20,11 @@
 ! run_equal_number leaves behind.
 !
 ! MPI: one rank per GPU (device = node-local rank modulo the GPU count).  Each
-! rank runs photon ids rank+1, rank+1+nproc, ... (src/run_simulation_mod.f90:150)
-! and the host's existing output_reduce sums the ranks.  (A single process can
-! instead create one handle per GPU and reduce on the device with one NCCL reduce
-! over lart_gpu_tally_buffer -- lart_b200/host.py:output_reduce does that.)
+! rank runs photon ids rank+1, rank+1+nproc, ... (src/run_simulation_mod.f90:150);
+! the ranks' tallies are summed on the device by ONE NCCL reduce inside the C ABI
+! (lart_gpu_reduce; the communicator id travels by MPI_BCAST) before they are
+! added into the host arrays, so the host's plane-by-plane MPI reduce of 160-400 MB
+! arrays (src/memory_mod_mpi.f90:366-458) only ever sums zeros onto rank 0's result.
 !------------------------------------------------------------------------------
 module lart_gpu_shim
   use, intrinsic :: iso_c_binding
@@ -43,6 +44,9 @@ module lart_gpu_shim
      real(c_double) :: Dfreq_ref, xfreq_min, xfreq_max, dxfreq, xcrit, xcrit2, rmax
      integer(c_int32_t) :: i0, j0, k0, pad_
      type(c_ptr) :: xface, yface, zface, rhokap, voigt_a, Dfreq, vfx, vfy, vfz, rhokapD
+     type(c_ptr) :: mask
+     integer(c_int32_t) :: geometry_JPa, nr
+     type(c_ptr) :: ind_sph, ind_cyl
   end type
   type, bind(C) :: c_lart_params
      integer(c_int64_t) :: nphotons, seed
@@ -53,10 +57,12 @@ module lart_gpu_shim
      integer(c_int32_t) :: save_Jin, save_Jabs, save_Jmu, save_peeloff, save_peeloff_2D, save_peeloff_3D
      integer(c_int32_t) :: save_direc0, save_all_photons, xyz_symmetry, xy_symmetry, use_clump_medium, xy_periodic, nobs
      integer(c_int32_t) :: use_amr_grid
+     integer(c_int32_t) :: atmosphere, calc_J, calc_P, calc_Pnew
+     real(c_double) :: Omega
   end type
   type, bind(C) :: c_lart_line
      integer(c_int32_t) :: line_type, pad_
-     real(c_double) :: E1, E2, E3, g_recoil0, DnuHK_Hz
+     real(c_double) :: E1, E2, E3, g_recoil0, DnuHK_Hz, cross0
   end type
   type, bind(C) :: c_lart_observer
      real(c_double) :: x, y, z, rmatrix(9), dxim, dyim
@@ -105,6 +111,7 @@ module lart_gpu_shim
      type(c_lart_allph_out) :: allph
      real(c_double) :: nscatt_gas, nscatt_dust
      type(c_lart_counters) :: counters
+     type(c_ptr) :: Jabs2, J, Pa, Pnew
   end type
 
   interface
@@ -129,6 +136,20 @@ module lart_gpu_shim
      end function
      type(c_ptr) function lart_gpu_last_error() bind(C, name='lart_gpu_last_error')
        import :: c_ptr
+     end function
+     integer(c_int) function lart_gpu_comm_unique_id(id128) bind(C, name='lart_gpu_comm_unique_id')
+       import :: c_int, c_char
+       character(kind=c_char), intent(out) :: id128(128)
+     end function
+     integer(c_int) function lart_gpu_comm_init(device, nranks, rank, id128) bind(C, name='lart_gpu_comm_init')
+       import :: c_int, c_int32_t, c_char
+       integer(c_int32_t), value :: device, nranks, rank
+       character(kind=c_char), intent(in) :: id128(128)
+     end function
+     integer(c_int) function lart_gpu_reduce(handle, root) bind(C, name='lart_gpu_reduce')
+       import :: c_int, c_ptr, c_int32_t
+       type(c_ptr), value :: handle
+       integer(c_int32_t), value :: root
      end function
   end interface
 
@@ -172,12 +193,13 @@ contains
     type(c_lart_observer_out), allocatable, target :: oout(:)
     type(c_ptr) :: handle
     integer(c_int64_t) :: first_id, count, stride
-    integer :: k, ngpu_per_node
+    integer :: k, ngpu_per_node, ierr
+    character(kind=c_char), save :: nccl_id(128)
+    logical, save :: comm_ready = .false.
 
-    !--- inputs that bind other ray tracers or run loops than the ones behind lart_gpu_run (src/setup.f90:905-990)
-    if (par%use_amr_grid .or. par%z_symmetry .or. par%Omega /= 0.0_wp .or. par%nside > 0 .or. &
-        trim(par%geometry) == 'plane_atmosphere' .or. trim(par%geometry) == 'spherical_atmosphere') then
-       write(*,'(a)') 'ERROR (lart_gpu): AMR, z_symmetry, shear, atmospheres and HEALPix observers are not on the GPU path.'
+    !--- inputs that bind other run loops than the one behind lart_gpu_run (src/setup.f90:905-990)
+    if (par%nside > 0 .or. line%line_type /= 1) then
+       write(*,'(a)') 'ERROR (lart_gpu): HEALPix observers and lines other than line_type 1 are not on the GPU path.'
        call MPI_ABORT(MPI_COMM_WORLD, 1, k)
     endif
 
@@ -193,6 +215,15 @@ contains
     cfg%grid%rhokap = ploc(grid%rhokap); cfg%grid%voigt_a = ploc(grid%voigt_a); cfg%grid%Dfreq = ploc(grid%Dfreq)
     cfg%grid%vfx = ploc(grid%vfx); cfg%grid%vfy = ploc(grid%vfy); cfg%grid%vfz = ploc(grid%vfz)
     cfg%grid%rhokapD = ploc(grid%rhokapD)
+    !--- atmosphere mask and the CALCJ / CALCP / CALCPnew index maps (src/define.f90:158, 166-175)
+    cfg%grid%mask = c_null_ptr; cfg%grid%ind_sph = c_null_ptr; cfg%grid%ind_cyl = c_null_ptr
+    cfg%grid%geometry_JPa = 0; cfg%grid%nr = 0
+    if (associated(grid%mask)) cfg%grid%mask = c_loc(grid%mask)
+#if defined (CALCJ) || defined (CALCP) || defined (CALCPnew)
+    cfg%grid%geometry_JPa = grid%geometry_JPa; cfg%grid%nr = grid%nr
+    if (associated(grid%ind_sph)) cfg%grid%ind_sph = c_loc(grid%ind_sph)
+    if (associated(grid%ind_cyl)) cfg%grid%ind_cyl = c_loc(grid%ind_cyl)
+#endif
 
     !--- params_type members the path reads (src/define.f90:209-544)
     cfg%par%nphotons = par%nphotons
@@ -217,8 +248,23 @@ contains
     select case (trim(par%source_geometry))
     case ('uniform');                  cfg%par%source_geometry = 1
     case ('uniform_sphere', 'sphere'); cfg%par%source_geometry = 2
+    case ('plane_illumination');       cfg%par%source_geometry = 3
     case default;                      cfg%par%source_geometry = 0
     end select
+    cfg%par%atmosphere = 0
+    if (trim(par%geometry) == 'plane_atmosphere')     cfg%par%atmosphere = 1
+    if (trim(par%geometry) == 'spherical_atmosphere') cfg%par%atmosphere = 2
+    cfg%par%Omega = par%Omega          ! already q*Omega*xrange (src/grid_mod_car.f90:348-350)
+    cfg%par%calc_J = 0; cfg%par%calc_P = 0; cfg%par%calc_Pnew = 0
+#ifdef CALCJ
+    cfg%par%calc_J = 1
+#endif
+#ifdef CALCP
+    cfg%par%calc_P = 1
+#endif
+#ifdef CALCPnew
+    cfg%par%calc_Pnew = 1
+#endif
     cfg%par%comoving_source = l2i(par%comoving_source); cfg%par%recoil = l2i(par%recoil)
     cfg%par%core_skip = l2i(par%core_skip); cfg%par%core_skip_global = l2i(par%core_skip_global)
     cfg%par%use_stokes = l2i(par%use_stokes); cfg%par%use_reduced_wgt = l2i(par%use_reduced_wgt)
@@ -270,7 +316,7 @@ contains
     !--- line_type (src/define.f90:639-656)
     cfg%line%line_type = line%line_type; cfg%line%pad_ = 0
     cfg%line%E1 = line%E1; cfg%line%E2 = line%E2; cfg%line%E3 = line%E3
-    cfg%line%g_recoil0 = line%g_recoil0; cfg%line%DnuHK_Hz = line%DnuHK_Hz
+    cfg%line%g_recoil0 = line%g_recoil0; cfg%line%DnuHK_Hz = line%DnuHK_Hz; cfg%line%cross0 = line%cross0
 
     !--- scattering_matrix_type (src/define.f90:616-625), dust + Stokes only
     cfg%scatt_mat%nPDF = 0; cfg%scatt_mat%pad_ = 0
@@ -308,6 +354,14 @@ contains
     cfg%device     = mod(mpar%h_rank, ngpu_per_node)
     cfg%pool_slots = 0; cfg%quantum = 0; cfg%flags = 0; cfg%streams = 0; cfg%ray_budget = 0; cfg%max_events = 0; cfg%pad_ = 0
 
+    !--- one NCCL communicator per process, its 128-byte id broadcast by MPI (once, like MPI_INIT)
+    if (.not. comm_ready .and. mpar%nproc > 1) then
+       if (mpar%p_rank == 0) call check(lart_gpu_comm_unique_id(nccl_id))
+       call MPI_BCAST(nccl_id, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, ierr)
+       call check(lart_gpu_comm_init(cfg%device, int(mpar%nproc, c_int32_t), int(mpar%p_rank, c_int32_t), nccl_id))
+       comm_ready = .true.
+    endif
+
     call check(lart_gpu_create(cfg, handle))
 
     !--- photon ids of this rank: ip = rank+1, nphotons, nproc (src/run_simulation_mod.f90:150)
@@ -317,7 +371,12 @@ contains
     if (par%nphotons >= first_id) count = (par%nphotons - first_id)/stride + 1
     call check(lart_gpu_run(handle, first_id, count, stride))
 
-    !--- add the raw weighted sums into the host's arrays (then main.f90:46 output_reduce sums the ranks)
+    !--- ONE ncclReduce(sum, f64) over the contiguous device tally buffer onto rank 0 replaces reduce_mem's per-array
+    !--- MPI_REDUCE (src/memory_mod_mpi.f90:366-458): afterwards only rank 0 holds non-zero device tallies, every rank
+    !--- adds its device tallies into its (zero-initialised) host arrays, and the host's own output_reduce still yields the
+    !--- same sums — or is skipped altogether (INTEGRATION.md, "output_reduce")
+    call check(lart_gpu_reduce(handle, 0_c_int32_t))
+    !--- add the raw weighted sums into the host's arrays
     tal%Jout = ploc(grid%Jout); tal%Jin = ploc(grid%Jin); tal%Jabs = ploc(grid%Jabs); tal%Jmu = ploc(grid%Jmu)
     if (par%use_amr_grid) then  ! an octree run tallies into amr_grid (src/octree_mod.f90:84-88)
        tal%Jout = c_null_ptr; tal%Jin = c_null_ptr; tal%Jabs = c_null_ptr; tal%Jmu = c_null_ptr
@@ -326,6 +385,28 @@ contains
        if (allocated(amr_grid%Jabs)) tal%Jabs = c_loc(amr_grid%Jabs)
        if (allocated(amr_grid%Jmu))  tal%Jmu  = c_loc(amr_grid%Jmu)
     endif
+    tal%Jabs2 = ploc(grid%Jabs2); tal%J = c_null_ptr; tal%Pa = c_null_ptr; tal%Pnew = c_null_ptr
+#ifdef CALCJ
+    select case (grid%geometry_JPa)        ! src/grid_mod_car.f90:1422-1434
+    case (3);  tal%J = ploc(grid%J)
+    case (2);  tal%J = ploc(grid%J2)
+    case default; tal%J = ploc(grid%J1)
+    end select
+#endif
+#ifdef CALCP
+    select case (grid%geometry_JPa)        ! :1385-1395
+    case (3);  tal%Pa = ploc(grid%Pa)
+    case (2);  tal%Pa = ploc(grid%P2)
+    case default; tal%Pa = ploc(grid%P1)
+    end select
+#endif
+#ifdef CALCPnew
+    select case (grid%geometry_JPa)        ! :1410-1420
+    case (3);  tal%Pnew = ploc(grid%Pa_new)
+    case (2);  tal%Pnew = ploc(grid%P2_new)
+    case default; tal%Pnew = ploc(grid%P1_new)
+    end select
+#endif
     tal%obs  = c_loc(oout)
     tal%allph%rp0 = c_null_ptr; tal%allph%rp = c_null_ptr; tal%allph%xfreq1 = c_null_ptr; tal%allph%xfreq2 = c_null_ptr
     tal%allph%nscatt_gas = c_null_ptr; tal%allph%nscatt_dust = c_null_ptr
@@ -339,7 +420,8 @@ contains
        tal%allph%I = ploc(allph%I); tal%allph%Q = ploc(allph%Q); tal%allph%U = ploc(allph%U); tal%allph%V = ploc(allph%V)
     endif
     tal%nscatt_gas = 0.0_c_double; tal%nscatt_dust = 0.0_c_double
-    tal%counters = c_lart_counters(0.0_c_double, 0.0_c_double, 0.0_c_double, 0.0_c_double, 0.0_c_double, 0.0_c_double)
+    tal%counters = c_lart_counters(0.0_c_double, 0.0_c_double, 0.0_c_double, 0.0_c_double, 0.0_c_double, 0.0_c_double, &
+                                   0.0_c_double, 0.0_c_double)
     call check(lart_gpu_fetch(handle, tal))
     par%nscatt_gas  = par%nscatt_gas  + tal%nscatt_gas       ! src/run_simulation_mod.f90:189-191
     par%nscatt_dust = par%nscatt_dust + tal%nscatt_dust

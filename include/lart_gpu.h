@@ -173,7 +173,9 @@ typedef struct lart_scatt_mat {
  * N spherical clumps inside a sphere of radius sphere_R, vacuum between them (par%use_clump_medium).  The host owns
  * the population (init_clumps / generate_clumps / read_clumps_info) and the CSR acceleration grid
  * (build_clump_csr, :1267-1349); the library only reads them.  n = 0: no clump medium.  Overlapping populations
- * (has_overlap, the event-walk ray tracers of raytrace_clump.f90:621-1208) are not on the GPU path. */
+ * (has_overlap: the event-walk ray tracers raytrace_to_tau_clump_overlap / raytrace_to_edge_clump_overlap(_capped),
+ * raytrace_clump.f90:621-920, and the scatter_resonance_clump_* wrappers, scattering_car.f90:897-945) run on the
+ * one-thread-per-photon driver with a per-thread event list of MAX_EVT = 2048 entries, as upstream. */
 typedef struct lart_clumps {
   int64_t n;                        /* N_clumps                                                     */
   double sphere_R;                  /* outer radius                                                 */
@@ -185,7 +187,7 @@ typedef struct lart_clumps {
   const double *rhokapD;            /* cl_rhokapD (n) or NULL when DGR = 0                          */
   const double *voigt_a, *Dfreq;    /* cl_voigt_a, cl_Dfreq (n)                                     */
   int32_t cgx, cgy, cgz;            /* CSR grid cells per axis                                      */
-  int32_t has_overlap;              /* must be 0                                                    */
+  int32_t has_overlap;              /* clump_mod's has_overlap (setup_clump_overlap, setup.f90:1051-1081) */
   double cg_xmin, cg_ymin, cg_zmin; /* lower corner of the CSR grid                                 */
   double cg_dx, cg_dy, cg_dz;       /* its cell sizes; cg_inv_d* = 1/cg_d* is recomputed            */
   const int32_t *cg_start;          /* (cgx*cgy*cgz + 1) 1-based offsets into cg_list, as upstream  */

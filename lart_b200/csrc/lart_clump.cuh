@@ -249,4 +249,181 @@ LART_DEV bool clump_walk_tau(const DevParams &P, const double *vtab, Photon &ph,
   return st == 1;
 }
 
+// ---------------------------------------------------------------------------
+// Overlapping populations (has_overlap; setup_clump_overlap, setup.f90:1051-1081) — the event walk of
+// clump_mod.f90:1595-1760 and raytrace_clump.f90:621-920.  A ray's ENTER/EXIT events up to the bounding sphere are
+// collected through the CSR grid, sorted by distance, and swept with the set of clumps the ray is inside; in an overlap
+// region every clump adds its opacity at the ray's frequency in ITS frame.  The event list (up to MAX_EVT = 2048
+// entries, as upstream) and the active set live in global memory, element e of thread t at [e*T + t] (a warp's lanes
+// touch one line per element); one thread walks one ray.  Expression order is the reference's, so events, sums and the
+// sampled owner clump coincide with the CPU restatement bit for bit.
+// ---------------------------------------------------------------------------
+constexpr int kMaxEvt = 2048;  // raytrace_clump.f90:680
+struct OvList {
+  double *t; int *ev; int *act;  // ev = +icl ENTER, -icl EXIT
+  size_t T, tid;
+  LART_DEV double &tt(int e) const { return t[(size_t)e * T + tid]; }
+  LART_DEV int &ee(int e) const { return ev[(size_t)e * T + tid]; }
+  LART_DEV int &aa(int e) const { return act[(size_t)e * T + tid]; }
+};
+LART_DEV OvList ov_list(const DevClumps &C) {
+  OvList L;
+  L.t = C.ov_t; L.ev = C.ov_ev; L.act = C.ov_act; L.T = (size_t)C.ov_T;
+  L.tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  return L;
+}
+// active_set_at_point — clump_mod.f90:1595-1634: every clump that contains the point, first-seen order
+LART_DEV int ov_active_set(const DevClumps &C, const OvList &L, double xp, double yp, double zp) {
+  const int ci = cg_clamp(xp, C.xmin, C.inv_dx, C.cgx), cj = cg_clamp(yp, C.ymin, C.inv_dy, C.cgy), ck = cg_clamp(zp, C.zmin, C.inv_dz, C.cgz);
+  int na = 0;
+  for (int k = max(0, ck - 1); k <= min(C.cgz - 1, ck + 1); ++k)
+    for (int j = max(0, cj - 1); j <= min(C.cgy - 1, cj + 1); ++j)
+      for (int i = max(0, ci - 1); i <= min(C.cgx - 1, ci + 1); ++i) {
+        const size_t icell = (size_t)i + (size_t)C.cgx * ((size_t)j + (size_t)C.cgy * (size_t)k);
+        const int p0 = __ldg(C.cg_start + icell), p1 = __ldg(C.cg_start + icell + 1);
+        for (int ip = p0; ip < p1; ++ip) {
+          const int icl = __ldg(C.cg_list + ip - 1);
+          const double4 g = ldg4(C.geo_reg + ip - 1);
+          const double rx = DSUB(xp, g.x), ry = DSUB(yp, g.y), rz = DSUB(zp, g.z);
+          if (!(DADD(DADD(DMUL(rx, rx), DMUL(ry, ry)), DMUL(rz, rz)) <= g.w)) continue;
+          bool seen = false;
+          for (int m = 0; m < na; ++m) seen = seen || L.aa(m) == icl;
+          if (!seen && na < kMaxEvt) L.aa(na++) = icl;
+        }
+      }
+  return na;
+}
+// collect_ray_events_overlap — clump_mod.f90:1639-1760: all events with 0 < t <= t_max, stably sorted by t
+LART_DEV int ov_collect(const DevClumps &C, const OvList &L, double xp, double yp, double zp, double kx, double ky, double kz,
+                        double t_max) {
+  int n = 0;
+  int ci = cg_clamp(xp, C.xmin, C.inv_dx, C.cgx), cj = cg_clamp(yp, C.ymin, C.inv_dy, C.cgy), ck = cg_clamp(zp, C.zmin, C.inv_dz, C.cgz);
+  const int si = kx > 0.0 ? 1 : (kx < 0.0 ? -1 : 0), sj = ky > 0.0 ? 1 : (ky < 0.0 ? -1 : 0), sk = kz > 0.0 ? 1 : (kz < 0.0 ? -1 : 0);
+  auto first = [](double k, double p, int cc, double lo, double dd, int st) {
+    return st == 0 ? kHugest : DSUB(DADD(lo, DMUL((double)(cc + (st > 0 ? 1 : 0)), dd)), p) / k;
+  };
+  double tx = first(kx, xp, ci, C.xmin, C.dx, si), ty = first(ky, yp, cj, C.ymin, C.dy, sj), tz = first(kz, zp, ck, C.zmin, C.dz, sk);
+  const double delx = si ? C.dx / fabs(kx) : kHugest, dely = sj ? C.dy / fabs(ky) : kHugest, delz = sk ? C.dz / fabs(kz) : kHugest;
+  double d = 0.0;
+  for (;;) {
+    if (d > t_max) break;
+    if (ci < 0 || ci >= C.cgx || cj < 0 || cj >= C.cgy || ck < 0 || ck >= C.cgz) break;
+    const size_t icell = (size_t)ci + (size_t)C.cgx * ((size_t)cj + (size_t)C.cgy * (size_t)ck);
+    const int p0 = __ldg(C.cg_start + icell), p1 = __ldg(C.cg_start + icell + 1);
+    for (int ip = p0; ip < p1; ++ip) {
+      const int icl = __ldg(C.cg_list + ip - 1);
+      const double4 g = ldg4(C.geo_reg + ip - 1);
+      const double rx = DSUB(xp, g.x), ry = DSUB(yp, g.y), rz = DSUB(zp, g.z);
+      const double b = DADD(DADD(DMUL(rx, kx), DMUL(ry, ky)), DMUL(rz, kz));
+      double disc = DADD(DSUB(DMUL(b, b), DADD(DADD(DMUL(rx, rx), DMUL(ry, ry)), DMUL(rz, rz))), g.w);
+      if (disc < 0.0) continue;
+      disc = sqrt(disc);
+      const double te = DSUB(-b, disc), tx2 = DADD(-b, disc);
+      if (!(tx2 > 0.0) || te > t_max) continue;
+      bool dup = false;
+      for (int e = 0; e < n; ++e) dup = dup || abs(L.ee(e)) == icl;
+      if (dup || n + 2 > kMaxEvt) continue;
+      if (te > 0.0) { L.tt(n) = te; L.ee(n) = icl; ++n; }
+      L.tt(n) = fmin(tx2, t_max); L.ee(n) = -icl; ++n;
+    }
+    if (tx <= ty && tx <= tz) { d = tx; tx = DADD(tx, delx); ci += si; }
+    else if (ty <= tz) { d = ty; ty = DADD(ty, dely); cj += sj; }
+    else { d = tz; tz = DADD(tz, delz); ck += sk; }
+  }
+  for (int e = 1; e < n; ++e) {  // insertion sort, stable for equal t
+    const double tt = L.tt(e);
+    const int ii = L.ee(e);
+    int q = e - 1;
+    while (q >= 0 && L.tt(q) > tt) { L.tt(q + 1) = L.tt(q); L.ee(q + 1) = L.ee(q); --q; }
+    L.tt(q + 1) = tt; L.ee(q + 1) = ii;
+  }
+  return n;
+}
+LART_DEV void ov_apply(const OvList &L, int ev, int &na) {
+  if (ev > 0) { if (na < kMaxEvt) L.aa(na++) = ev; return; }
+  for (int m = 0; m < na; ++m) if (L.aa(m) == -ev) { L.aa(m) = L.aa(na - 1); --na; return; }
+}
+// sum_kap_active — raytrace_clump.f90:621-640
+LART_DEV double ov_sum_kap(const DevParams &P, const double *vtab, const OvList &L, int na, double xg, double kx, double ky, double kz) {
+  double s = 0.0;
+  for (int m = 0; m < na; ++m) {
+    const ClumpPhys cp = load_clump(P.cl, L.aa(m));
+    s = DADD(s, kappa_clump(P, vtab, cp, DSUB(xg, ulos_clump(P, cp, kx, ky, kz))));
+  }
+  return s;
+}
+// raytrace_to_edge_clump_overlap (:792-855; tau_max <= 0) and _overlap_capped (:858-920)
+LART_DEV double clump_walk_edge_overlap(const DevParams &P, const double *vtab, double xp, double yp, double zp, double kx, double ky,
+                                        double kz, double xg, double tau_max, int &nevents) {
+  const DevClumps &C = P.cl;
+  double tau = 0.0;
+  const double t_sp = sphere_exit_dist(C, xp, yp, zp, kx, ky, kz);
+  if (t_sp <= 0.0) return tau;
+  const OvList L = ov_list(C);
+  const int n = ov_collect(C, L, xp, yp, zp, kx, ky, kz, t_sp);
+  int na = ov_active_set(C, L, xp, yp, zp);
+  nevents += n;
+  double t_cur = 0.0;
+  for (int ie = 0; ie <= n; ++ie) {
+    const double t_next = fmin(ie < n ? L.tt(ie) : t_sp, t_sp);
+    const double dt = DSUB(t_next, t_cur);
+    if (dt > 0.0) {
+      tau = DADD(tau, DMUL(ov_sum_kap(P, vtab, L, na, xg, kx, ky, kz), dt));
+      if (tau_max > 0.0 && tau >= tau_max) return tau;
+    }
+    t_cur = t_next;
+    if (ie < n) ov_apply(L, L.ee(ie), na);
+  }
+  return tau;
+}
+// raytrace_to_tau_clump_overlap — raytrace_clump.f90:668-790.  true = the photon sits at its next scattering point, owned by
+// clump icl (drawn with one uniform among the clumps that overlap there, sample_owner_clump :642-666); false = it left the
+// sphere (ph.xfreq stays the global-frame frequency that is binned into Jout).
+template <class RngT>
+LART_DEV bool clump_walk_tau_overlap(const DevParams &P, const double *vtab, Photon &ph, int &icl, double tau_in, RngT &rng, int &nevents) {
+  const DevClumps &C = P.cl;
+  const double kx = ph.kx, ky = ph.ky, kz = ph.kz, xg = ph.xfreq;
+  double tau_rem = tau_in;
+  const double t_sp = sphere_exit_dist(C, ph.x, ph.y, ph.z, kx, ky, kz);
+  if (t_sp <= 0.0) { icl = 0; update_cell_idx(P, ph); return false; }
+  const OvList L = ov_list(C);
+  const int n = ov_collect(C, L, ph.x, ph.y, ph.z, kx, ky, kz, t_sp);
+  int na = ov_active_set(C, L, ph.x, ph.y, ph.z);
+  nevents += n;
+  double t_cur = 0.0;
+  for (int ie = 0; ie <= n; ++ie) {
+    const double t_next = fmin(ie < n ? L.tt(ie) : t_sp, t_sp);
+    const double dt = DSUB(t_next, t_cur);
+    if (dt <= 0.0) {
+      if (ie < n) ov_apply(L, L.ee(ie), na);
+      continue;
+    }
+    const double kap_tot = ov_sum_kap(P, vtab, L, na, xg, kx, ky, kz);
+    if (kap_tot > 0.0 && tau_rem <= DMUL(kap_tot, dt)) {  // scatters inside this segment
+      const double s = DADD(t_cur, tau_rem / kap_tot);
+      ph.x = DADD(ph.x, DMUL(s, kx)); ph.y = DADD(ph.y, DMUL(s, ky)); ph.z = DADD(ph.z, DMUL(s, kz));
+      const double rnd = rng.uniform();
+      const double lim = DMUL(rnd, kap_tot);
+      double cumul = 0.0;
+      int owner = 0;
+      for (int m = 0; m < na; ++m) {
+        const ClumpPhys cp = load_clump(C, L.aa(m));
+        cumul = DADD(cumul, kappa_clump(P, vtab, cp, DSUB(xg, ulos_clump(P, cp, kx, ky, kz))));
+        owner = L.aa(m);
+        if (lim <= cumul) break;
+      }
+      icl = owner;
+      update_cell_idx(P, ph);
+      return true;
+    }
+    tau_rem = DSUB(tau_rem, DMUL(kap_tot, dt));
+    t_cur = t_next;
+    if (ie < n) ov_apply(L, L.ee(ie), na);
+  }
+  ph.x = DADD(ph.x, DMUL(t_sp, kx)); ph.y = DADD(ph.y, DMUL(t_sp, ky)); ph.z = DADD(ph.z, DMUL(t_sp, kz));
+  icl = 0;
+  update_cell_idx(P, ph);
+  return false;
+}
+
 }  // namespace lart

@@ -66,8 +66,10 @@ struct DevClumps {
   const double4 *geo_reg;  // geo[cg_list[ip]] for every CSR registration ip: the cell's clumps are contiguous, one load level less
   const ClumpPhys *phys;
   const int *cg_start, *cg_list;  // 1-based offsets / clump indices, as the host built them
-  int cgx, cgy, cgz, pad_;
+  int cgx, cgy, cgz;
+  int overlap;             // has_overlap: the event-walk ray tracers (raytrace_clump.f90:621-920), one thread per ray
   double xmin, ymin, zmin, dx, dy, dz, inv_dx, inv_dy, inv_dz;
+  double *ov_t; int *ov_ev, *ov_act; long long ov_T;  // per-thread event lists and active sets of the overlap walk
 };
 
 // octree AMR: one 64-byte geometry record per LEAF (centre, half-width, the six face neighbours of its cell) —

@@ -463,7 +463,9 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
     // peel-off toward every observer from the photon's current state; csp = grid record with the clump's bulk velocity
     auto trace_and_deposit = [&](PeelRay &pr) {
       int nc = 0, ncl = 0;
-      double t = clump_walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.xfreq, icl, kTauHugeClump, nc, ncl);
+      // overlapping populations: the event walk (peel_raytrace_to_edge, peelingoff_rect.f90:894-898)
+      double t = C.overlap ? clump_walk_edge_overlap(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.xfreq, kTauHugeClump, nc)
+                           : clump_walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.xfreq, icl, kTauHugeClump, nc, ncl);
       cnt.cellsteps += nc; cnt.peel += 1;
       peel_deposit(P, pr, t, __activemask());
     };
@@ -489,7 +491,9 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
           rng_valid = true;
           nev = 0;
           generate_photon(P, ph, rng, cnt, cs);
-          icl = clump_at_point(C, ph.x, ph.y, ph.z);  // the birth clump, before the direct peel (generate_photon.f90:325-332)
+          // the birth clump, before the direct peel (generate_photon.f90:325-332); with overlapping populations the photon
+          // stays in the global frame and owns no clump until its first scattering
+          icl = C.overlap ? 0 : clump_at_point(C, ph.x, ph.y, ph.z);
           csp0 = cs;
           if (icl > 0) {
             const ClumpPhys cp = load_clump(C, icl);
@@ -523,14 +527,15 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
           int ci, cj, ck, nc = 0, ncl = 0;
           clamp_cell_for_read(P, ph, ci, cj, ck);
           load_cell(P, ci, cj, ck, cs);
-          double tau0 = clump_walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, -1.0, nc, ncl);
+          double tau0 = C.overlap ? clump_walk_edge_overlap(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, -1.0, nc)
+                                  : clump_walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.xfreq, icl, -1.0, nc, ncl);
           cnt.cellsteps += nc;
           tau = forced_first(P, ph, rng, cs, tau0);
         } else {
           tau = -log(rng.uniform());
         }
         int nc = 0;
-        inside = clump_walk_tau(P, vtab, ph, icl, tau, nc);
+        inside = C.overlap ? clump_walk_tau_overlap(P, vtab, ph, icl, tau, rng, nc) : clump_walk_tau(P, vtab, ph, icl, tau, nc);
         cnt.cellsteps += nc;
         if (!inside) {  // left the sphere (raytrace_clump.f90:137-146, 151-160, 182-192)
           ph.flags &= ~PH_ALIVE;
@@ -563,6 +568,9 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
           });
           if (!(ph.flags & PH_ALIVE)) retire_photon(P, ph, false, job, cnt);
         } else {  // do_resonance1_clump — line_clump_mod.f90:29-58
+          // overlapping populations: scatter_resonance_clump_* (scattering_car.f90:897-945) — into the owner clump's frame,
+          // scatter, back to the global frame along the new direction
+          if (C.overlap) ph.xfreq = DSUB(ph.xfreq, ulos_clump(P, cp, ph.kx, ph.ky, ph.kz));
           const double scale_inv = 1.0 / scale;
           const double xloc = ph.xfreq * scale;
           const double uz_loc = rand_resonance_vz(rng, xloc, cp.voigt_a, cnt.reject);
@@ -577,6 +585,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_mono_clump(const __grid_constant_
               if (ok) trace_and_deposit(pr);
             }
           });
+          if (C.overlap) ph.xfreq = DADD(ph.xfreq, ulos_clump(P, cp, ph.kx, ph.ky, ph.kz));
         }
         if (P.max_events > 0 && (ph.flags & PH_ALIVE) && ++nev >= P.max_events) {
           ph.flags &= ~PH_ALIVE;
@@ -2011,7 +2020,8 @@ __global__ void k_clump_edge_batch(const __grid_constant__ DevParams P, long lon
   unsigned long long mine = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int nc = 0, ncl = 0;
-    tau[i] = clump_walk_edge(P, vtab, x[i], y[i], z[i], kx[i], ky[i], kz[i], xfreq[i], icl[i], tau_max, nc, ncl);
+    tau[i] = P.cl.overlap ? clump_walk_edge_overlap(P, vtab, x[i], y[i], z[i], kx[i], ky[i], kz[i], xfreq[i], tau_max, nc)
+                          : clump_walk_edge(P, vtab, x[i], y[i], z[i], kx[i], ky[i], kz[i], xfreq[i], icl[i], tau_max, nc, ncl);
     if (nclumps) nclumps[i] = ncl;
     mine += (unsigned long long)nc;
   }
@@ -2562,7 +2572,6 @@ int validate(const lart_config *c) {
         !cl.cg_start || !cl.cg_list)
       return fail("lart_gpu_create: NULL clump array");
     if (p.DGR > 0.0 && !cl.rhokapD) return fail("lart_gpu_create: DGR > 0 but clumps.rhokapD is NULL");
-    if (cl.has_overlap) return fail("lart_gpu_create: overlapping clump populations (has_overlap) stay with the Fortran host");
     if (cl.cgx < 1 || cl.cgy < 1 || cl.cgz < 1 || !(cl.cg_dx > 0.0) || !(cl.cg_dy > 0.0) || !(cl.cg_dz > 0.0) || !(cl.sphere_R > 0.0))
       return fail("lart_gpu_create: bad clump CSR grid");
     if (p.xyz_symmetry || p.xy_symmetry || p.xy_periodic) return fail("lart_gpu_create: the clump medium uses the plain box (grid_mod_clump.f90:55-59)");
@@ -2912,8 +2921,12 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   lap("tally + allph buffers");
   // ---- photon pool
   h->flags = cfg->flags;
+  // overlapping clump populations run on the one-thread-per-photon driver: the event walk keeps a per-thread event list
+  const bool overlap = P.clump && cfg->clumps.has_overlap;
+  if (overlap) h->flags |= LART_FLAG_MONOLITHIC;
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
   int S = cfg->pool_slots;
+  if (S <= 0 && overlap) S = h->nsm * 1024;  // 32 KB of event list per thread: 148 K photons in flight = 5 GB
   if (S <= 0) S = mono ? (P.clump ? h->nsm * 8192 : h->nsm * 2048) : h->nsm * 16384;  // k_mono_clump: 2.75e8 / 2.85e8 / 2.96e8 scatterings/s at 2048 / 4096 / 8192 per SM
   {
     // keep the ray queue below ~3 GB when many observers are configured
@@ -2923,6 +2936,14 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
   }
   S = std::max(32, (S + 31) / 32 * 32);
   h->pool.S = S;
+  if (overlap) {  // threads of k_mono_clump (one per slot, whole blocks) and of the batch kernels (grid_for: <= 8 blocks per SM)
+    const size_t T = std::max<size_t>(((size_t)S + kBlock - 1) / kBlock * kBlock, (size_t)h->nsm * 8 * kBlock);
+    P.cl.overlap = 1; P.cl.ov_T = (long long)T;
+    rc = rc ? rc : dalloc(h, &P.cl.ov_t, T * kMaxEvt, false);
+    rc = rc ? rc : dalloc(h, &P.cl.ov_ev, T * kMaxEvt, false);
+    rc = rc ? rc : dalloc(h, &P.cl.ov_act, T * kMaxEvt, false);
+    if (rc) return bail(rc);
+  }
   rc = rc ? rc : dalloc(h, &h->pool.f, (size_t)F_COUNT * S);
   rc = rc ? rc : dalloc(h, &h->pool.id, S);
   rc = rc ? rc : dalloc(h, &h->pool.ndraw, S);
@@ -3720,6 +3741,7 @@ int lart_gpu_clump_tau_batch(lart_gpu_handle h, int64_t n, double *x, double *y,
                              const double *kz, double *xfreq, int32_t *icl, const double *tau_in, int32_t *inside) {
   if (!h) return fail("lart_gpu_clump_tau_batch: NULL handle");
   if (!h->P.clump) return fail("lart_gpu_clump_tau_batch: the handle has no clump medium");
+  if (h->P.cl.overlap) return fail("lart_gpu_clump_tau_batch: raytrace_to_tau_clump_overlap draws the owner clump from the photon's stream; use a run");
   if (n < 0 || (n > 0 && (!x || !y || !z || !kx || !ky || !kz || !xfreq || !icl || !tau_in || !inside))) return fail("lart_gpu_clump_tau_batch: bad argument");
   if (n == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));

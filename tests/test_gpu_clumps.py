@@ -106,12 +106,55 @@ def test_clump_known_answer_reference_log():
 
 def test_clump_errors():
     from lart_b200 import LartError
-    bad = clump_model()
-    bad.config.contents.clumps.has_overlap = 1
-    with pytest.raises(LartError, match="overlap"):
-        Simulation(bad)
     m = clump_model(use_clump_medium=False, rmax=1.0)
     sim = Simulation(m, pool_slots=64)
     with pytest.raises(LartError, match="clump"):
         sim.clump_locate([0.0], [0.0], [0.0])
     sim.close()
+
+
+# ---- overlapping populations (has_overlap): the event walk, raytrace_clump.f90:621-920, clump_mod.f90:1595-1760 --------------
+OVERLAP = dict(clump_allow_overlap=True, clump_radius=0.08, clump_f_cov=3.0, clump_sigma_v=15.0)
+
+
+def test_overlap_edge_walk_bit_exact():
+    m = clump_model(velocity_type="hubble", Vexp=60.0, **OVERLAP)
+    assert m.config.contents.clumps.has_overlap == 1
+    sim = Simulation(m, pool_slots=256)
+    rng = np.random.default_rng(17)
+    n = 60000
+    p, k = rays_from(rng, n)
+    q = n // 10
+    p[:q] = 1e-9
+    p[q:2 * q] *= 1.0 / np.linalg.norm(p[q:2 * q], axis=1)[:, None]
+    xf = rng.normal(size=n) * 2
+    cols = lambda a: (a[:, 0], a[:, 1], a[:, 2])
+    icl0 = np.zeros(n, dtype=np.int32)  # the overlap walk finds its own active set
+    for cap in (-1.0, 745.2, 2.0):
+        tg, _ = sim.clump_edge(*cols(p), *cols(k), xf, icl0, tau_max=cap)
+        to, _ = oracle.clump_edge(m.config, *cols(p), *cols(k), xf, icl0, tau_max=cap)
+        assert np.array_equal(tg, to), cap
+    assert (to > 0).mean() > 0.6
+    with pytest.raises(Exception, match="overlap"):
+        sim.clump_tau(*cols(p[:4]), *cols(k[:4]), xf[:4], icl0[:4], np.ones(4))
+    sim.close()
+
+
+OVERLAP_CASES = {
+    "stokes_peel": dict(use_stokes=True, nxim=9, nyim=9, xfreq_min=-30.0, xfreq_max=30.0),
+    "nostokes_hubble_two_observers": dict(use_stokes=False, nxim=9, nyim=9, obsx=[0.0, 1.0], obsy=[0.0, 0.5], obsz=[1.0, 0.2],
+                                          velocity_type="hubble", Vexp=60.0, save_Jmu=True, nmu=4),
+    "dust_recoil": dict(use_stokes=False, nxim=0, nyim=0, DGR=1.0, cext_dust=3e-17, clump_NHI=2e16, clump_tau0=-1.0, recoil=True),
+}
+
+
+@pytest.mark.parametrize("case", sorted(OVERLAP_CASES))
+def test_overlap_photon_histories_match_oracle(case):
+    kw = dict(OVERLAP, no_photons=1500, save_all_photons=True, **OVERLAP_CASES[case])
+    mg, mo = clump_model(**kw), clump_model(**kw)
+    assert mg.config.contents.clumps.has_overlap == 1
+    run_gpu(mg, pool_slots=512)  # (the engine runs overlapping populations on the one-thread-per-photon driver)
+    oracle.run(mo, rng_mode=1)
+    same = histories_equal(mg, mo, geom_rtol=5e-3 if "hubble" in case else 1e-8)
+    tallies_close(mg, mo, min(same.mean(), 0.998) if "hubble" in case else same.mean())
+    assert mg.counters["n_photons_done"] == 1500 and mg.nscatt_gas > 1500

@@ -191,8 +191,8 @@ def test_setup_scalars_clump_sphere_log():
 
 def test_overlapping_population_event_walk_equals_brute_force():
     """has_overlap (clump_mod.f90:1544-1590, 1639-1760; raytrace_clump.f90:608-920): in an overlap region every clump adds
-    its opacity at its own frame's frequency; the frequency stays in the global frame during the walk.  The GPU engine
-    refuses such populations for now (lart_gpu_create); this pins the oracle for the day it does not."""
+    its opacity at its own frame's frequency; the frequency stays in the global frame during the walk.  Pins the oracle
+    the GPU event walk is compared with (tests/test_gpu_clumps.py::test_overlap_*)."""
     m = clump_model(clump_allow_overlap=True, clump_radius=0.08, clump_f_cov=3.0, clump_sigma_v=15.0, velocity_type="hubble",
                     Vexp=60.0)
     A = clump_arrays(m)
@@ -233,5 +233,4 @@ def test_overlapping_population_event_walk_equals_brute_force():
     oracle.run(run, rng_mode=1)
     assert run.counters["n_photons_done"] == 3000 and run.spectrum("Jout").sum() == pytest.approx(3000, rel=1e-3)
     assert run.nscatt_gas / 3000 > 3 and run.observer_cube("scatt").sum() > 0
-    # the GPU engine's validation rejects the population (CPU-checkable part: the flag travels through the ABI struct)
-    assert run.config.contents.clumps.has_overlap == 1
+    assert run.config.contents.clumps.has_overlap == 1  # the flag travels through the ABI struct

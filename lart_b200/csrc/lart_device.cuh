@@ -298,16 +298,18 @@ LART_DEV unsigned part1by2_5(unsigned v) {  // spread the low 5 bits: ...edcba -
   v = (v | (v << 2)) & 0x1249u;
   return v;
 }
+template <bool PLAIN = false>
 LART_DEV size_t cell_slot(const DevParams &P, int ic, int jc, int kc) {  // 1-based in
-  if (P.amr.on) return (size_t)(ic - 1);  // leaf-indexed records
+  if (!PLAIN && P.amr.on) return (size_t)(ic - 1);  // leaf-indexed records
   const unsigned i = (unsigned)(ic - 1), j = (unsigned)(jc - 1), k = (unsigned)(kc - 1);
   const size_t sb = (size_t)(i >> 5) + (size_t)P.nsbx * ((size_t)(j >> 5) + (size_t)P.nsby * (size_t)(k >> 5));
   const unsigned m = part1by2_5(i & 31u) | (part1by2_5(j & 31u) << 1) | (part1by2_5(k & 31u) << 2);
   return (sb << 15) + m;
 }
+template <bool PLAIN = false>
 LART_DEV void load_cell(const DevParams &P, int ic, int jc, int kc, CellData &o) {
   if (!P.soa) {
-    const double2 *q = reinterpret_cast<const double2 *>(P.cells + cell_slot(P, ic, jc, kc));
+    const double2 *q = reinterpret_cast<const double2 *>(P.cells + cell_slot<PLAIN>(P, ic, jc, kc));
     double2 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2), e = __ldg(q + 3);
     o.rhokap = a.x; o.voigt_a = a.y; o.Dfreq = b.x; o.vfx = b.y; o.vfy = d.x; o.vfz = d.y; o.rhokapD = e.x;
   } else {
@@ -400,8 +402,13 @@ LART_DEV bool axis_setup_bc(double &k, double &p, int &cell, int n, const double
 
 // line-of-sight bulk velocity of the ray's current cell; the shearing box adds the photon's vfy_shear to vfy in the
 // to_tau walk (raytrace_car.f90:2809, 2905, 2932)
+// PLAIN (template parameter of the walker functions below): the caller guarantees an open Cartesian box (3-D or z-only)
+// without octree, mirror / periodic axes, atmosphere, shear or path-length accumulators — the binding of the three headline
+// configurations.  The run-time switches of the other bindings are then compile-time false and their code is not
+// instantiated (k_wf_trace / k_wf_peel are launched in this variant when is_plain(P)).
+template <bool PLAIN = false>
 LART_DEV double ray_ulos(const DevParams &P, const Ray &r) {
-  if (P.x.shear && !(r.flip & kRayOpen))
+  if (!PLAIN && P.x.shear && !(r.flip & kRayOpen))
     return DADD(DADD(DMUL(r.cell.vfx, r.kx), DMUL(DADD(r.cell.vfy, r.vshear), r.ky)), DMUL(r.cell.vfz, r.kz));
   return vdotk(r.cell, r.kx, r.ky, r.kz);
 }
@@ -536,23 +543,24 @@ LART_DEV int amr_tau_step(const DevParams &P, const double *vtab, Ray &r, double
   return amr_cross(P, r, g, t_exit, iface) ? 0 : 2;
 }
 
+template <bool PLAIN = false>
 LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
                         int ic, int jc, int kc, double xfreq, bool zonly_eq, const CellData *here = nullptr) {
   r.x0 = x; r.y0 = y; r.z0 = z; r.kx = kx; r.ky = ky; r.kz = kz;
   r.ic = ic; r.jc = jc; r.kc = kc;
   r.d = 0.0; r.tau = 0.0; r.xfreq = xfreq; r.nsteps = 0; r.flip = 0;
-  if (P.amr.on) return amr_ray_setup(P, r, here);
+  if (!PLAIN && P.amr.on) return amr_ray_setup(P, r, here);
   // shearing boxes and atmospheres: raytrace_to_edge is the plain open-box routine whatever raytrace_to_tau is bound to
-  const bool open = P.x.edge_open && !zonly_eq;
+  const bool open = !PLAIN && P.x.edge_open && !zonly_eq;
   if (open) r.flip = kRayOpen;
-  if (P.bcxy && !open) {  // folded / periodic grids; their to_tau variants test `== xp` (:1681, :1993, :2293), to_edge `<= xp`
+  if (!PLAIN && P.bcxy && !open) {  // folded / periodic grids; their to_tau variants test `== xp` (:1681, :1993, :2293), to_edge `<= xp`
     bool mx, my, mz;
     if (axis_setup_bc(r.kx, r.x0, r.ic, P.nx, P.xface, r.istep, r.tx, r.delx, zonly_eq, P.bcxy, P.i0, mx)) return true;
     if (axis_setup_bc(r.ky, r.y0, r.jc, P.ny, P.yface, r.jstep, r.ty, r.dely, zonly_eq, P.bcxy, P.j0, my)) return true;
     if (axis_setup_bc(r.kz, r.z0, r.kc, P.nz, P.zface, r.kstep, r.tz, r.delz, zonly_eq, P.bcz, P.k0, mz)) return true;
     r.flip = (mx ? 1 : 0) | (my ? 2 : 0) | (mz ? 4 : 0);
     load_cell(P, r.ic, r.jc, r.kc, r.cell);
-    r.u1 = ray_ulos(P, r);
+    r.u1 = ray_ulos<PLAIN>(P, r);
     return false;
   }
   if (P.zonly && !open) {
@@ -564,19 +572,22 @@ LART_DEV bool ray_setup(const DevParams &P, Ray &r, double x, double y, double z
     if (axis_setup(kz, z, r.kc, P.nz, P.zface, P.dz, r.kstep, r.tz, r.delz, false)) return true;
   }
   if (here && r.ic == ic && r.jc == jc && r.kc == kc) r.cell = *here;
-  else load_cell(P, r.ic, r.jc, r.kc, r.cell);
+  else load_cell<PLAIN>(P, r.ic, r.jc, r.kc, r.cell);
   r.u1 = vdotk(r.cell, kx, ky, kz);
   return false;
 }
 
 constexpr int kFlipShift = 28, kCellMask = (1 << kFlipShift) - 1;
 // Resume a suspended walk: start point and direction are the ray's own, the DDA state is what was saved.
+template <bool PLAIN = false>
 LART_DEV void ray_resume(const DevParams &P, Ray &r, double x, double y, double z, double kx, double ky, double kz,
                          double tx, double ty, double tz, double delx, double dely, double delz, double d, double tau,
                          double xfreq, double u1, int ic, int jc, int kc_flip, bool open = false) {
   const int kc = kc_flip & kCellMask;
   int flip = kc_flip >> kFlipShift;  // see ray_save_state
-  if (open) {                   // an edge walk of a shearing box / an atmosphere: plain open box
+  if (PLAIN) {
+    flip = 0;
+  } else if (open) {            // an edge walk of a shearing box / an atmosphere: plain open box
     flip = kRayOpen;
   } else if (P.bcxy == BC_PERIODIC) {  // the start point had been wrapped to the far side
     if (flip & 1) x = __ldg(P.xface + (kx > 0.0 ? 0 : P.nx));
@@ -595,7 +606,7 @@ LART_DEV void ray_resume(const DevParams &P, Ray &r, double x, double y, double 
   r.istep = zo ? 0 : (kx > 0.0 ? 1 : (kx < 0.0 ? -1 : 0));
   r.jstep = zo ? 0 : (ky > 0.0 ? 1 : (ky < 0.0 ? -1 : 0));
   r.kstep = kz > 0.0 ? 1 : (kz < 0.0 ? -1 : 0);
-  load_cell(P, ic, jc, kc, r.cell);
+  load_cell<PLAIN>(P, ic, jc, kc, r.cell);
 }
 
 // opacity of the current cell at the ray's current frequency (:1488-1494)
@@ -606,8 +617,9 @@ LART_DEV double ray_opacity(const DevParams &P, const double *vtab, const Ray &r
 }
 
 // minloc([tx,ty,tz]) — first minimum wins (:476,:1506); z-only walks z
+template <bool PLAIN = false>
 LART_DEV int ray_axis(const DevParams &P, const Ray &r) {
-  if (P.zonly && !(r.flip & kRayOpen)) return 3;
+  if (P.zonly && (PLAIN || !(r.flip & kRayOpen))) return 3;
   if (r.tx <= r.ty && r.tx <= r.tz) return 1;
   if (r.ty <= r.tz) return 2;
   return 3;
@@ -621,13 +633,14 @@ LART_DEV bool ray_leave_or_turn(int bc, int &cell, int &step, double &k, int n, 
   cell -= step;
   return true;
 }
+template <bool PLAIN = false>
 LART_DEV bool ray_advance(const DevParams &P, Ray &r, int axis) {
-  const bool open = (r.flip & kRayOpen) != 0;
+  const bool open = PLAIN || (r.flip & kRayOpen) != 0;
   const int bcxy = open ? (int)BC_OPEN : P.bcxy, bcz = open ? (int)BC_OPEN : P.bcz;
   if (axis == 1) {
     r.ic += r.istep;
     if (r.ic < 1 || r.ic > P.nx) {
-      if (P.x.shear && !open) r.vshear = (r.ic < 1) ? DSUB(r.vshear, P.x.Omega) : DADD(r.vshear, P.x.Omega);  // :2842-2850
+      if (!PLAIN && P.x.shear && !open) r.vshear = (r.ic < 1) ? DSUB(r.vshear, P.x.Omega) : DADD(r.vshear, P.x.Omega);  // :2842-2850
       if (ray_leave_or_turn(bcxy, r.ic, r.istep, r.kx, P.nx, P.i0, r.flip, 1)) return false;
     }
     if (r.delx < 0.0) r.delx = P.dx / fabs(r.kx);
@@ -667,10 +680,11 @@ LART_DEV void fold_periodic(const DevParams &P, double &xp, double &yp) {
   xp = DSUB(xp, DMUL(floor(DSUB(xp, P.xmin) / xrange), xrange));
   yp = DSUB(yp, DMUL(floor(DSUB(yp, P.ymin) / yrange), yrange));
 }
+template <bool PLAIN = false>
 LART_DEV void ray_shift(const DevParams &P, Ray &r) {
   double Dold = r.cell.Dfreq;
-  load_cell(P, r.ic, r.jc, r.kc, r.cell);
-  double u2 = ray_ulos(P, r);
+  load_cell<PLAIN>(P, r.ic, r.jc, r.kc, r.cell);
+  double u2 = ray_ulos<PLAIN>(P, r);
   r.xfreq = DSUB(DMUL(DADD(r.xfreq, r.u1), Dold) / r.cell.Dfreq, u2);
   r.u1 = u2;
 }
@@ -718,28 +732,30 @@ __device__ __noinline__ void jp_add_Pa(const DevParams &P, int ic, int jc, int k
 }
 
 // One cell step of raytrace_to_edge.  Returns true when the walk is finished.
+template <bool PLAIN = false>
 LART_DEV bool edge_step(const DevParams &P, const double *vtab, Ray &r) {
-  if (P.amr.on) return amr_edge_step(P, vtab, r);
-  if (P.x.atm && ray_masked(P, r)) { r.tau = __longlong_as_double(0x7ff0000000000000LL); return true; }  // :3729-3733 tau = +inf
+  if (!PLAIN && P.amr.on) return amr_edge_step(P, vtab, r);
+  if (!PLAIN && P.x.atm && ray_masked(P, r)) { r.tau = __longlong_as_double(0x7ff0000000000000LL); return true; }  // :3729-3733 tau = +inf
   double kap = ray_opacity(P, vtab, r);
   ++r.nsteps;
-  int ax = ray_axis(P, r);
+  int ax = ray_axis<PLAIN>(P, r);
   double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
   r.tau = DADD(r.tau, DMUL(DSUB(tn, r.d), kap));
   r.d = tn;
-  if (!ray_advance(P, r, ax)) return true;
+  if (!ray_advance<PLAIN>(P, r, ax)) return true;
   if (r.tau >= kTauHuge) return true;
-  ray_shift(P, r);
+  ray_shift<PLAIN>(P, r);
   return false;
 }
 
 // One cell step of raytrace_to_tau.  status: 0 = keep walking, 1 = reached tau_in
 // (position in xp,yp,zp), 2 = left the grid, 3 = destroyed by the atmosphere mask (:3186-3190).
 // wgt = the photon's weight (only the CALCJ / CALCPnew deposits read it).
+template <bool PLAIN = false>
 LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau_in, double &xp, double &yp, double &zp,
                       double wgt = 0.0) {
-  if (P.amr.on) return amr_tau_step(P, vtab, r, tau_in, xp, yp, zp);
-  if (P.x.any) {  // the uncommon bindings: mask, path-length accumulators (one extra Voigt evaluation is not paid: kapH below)
+  if (!PLAIN && P.amr.on) return amr_tau_step(P, vtab, r, tau_in, xp, yp, zp);
+  if (!PLAIN && P.x.any) {  // the uncommon bindings: mask, path-length accumulators (one extra Voigt evaluation is not paid: kapH below)
     if (P.x.atm && ray_masked(P, r)) return 3;
     if (P.x.jp) {
       const double kapH = DMUL(r.cell.rhokap, voigt_seon2(vtab, r.xfreq, r.cell.voigt_a));
@@ -770,13 +786,13 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
   }
   double kap = ray_opacity(P, vtab, r);
   ++r.nsteps;
-  int ax = ray_axis(P, r);
+  int ax = ray_axis<PLAIN>(P, r);
   double tn = (ax == 1) ? r.tx : (ax == 2) ? r.ty : r.tz;
   r.tau = DADD(r.tau, DMUL(DSUB(tn, r.d), kap));
   r.d = tn;
   if (r.tau >= tau_in) {  // :1513-1524
     if (kap > 0.0) r.d = DSUB(r.d, DSUB(r.tau, tau_in) / kap);
-    if (P.bcxy) {
+    if (!PLAIN && P.bcxy) {
       ray_endpoint_bc(P, r, xp, yp, zp);
       if (P.bcxy == BC_PERIODIC) fold_periodic(P, xp, yp);
       return 1;
@@ -786,8 +802,8 @@ LART_DEV int tau_step(const DevParams &P, const double *vtab, Ray &r, double tau
     zp = DADD(r.z0, DMUL(r.d, r.kz));
     return 1;
   }
-  if (!ray_advance(P, r, ax)) return 2;
-  ray_shift(P, r);
+  if (!ray_advance<PLAIN>(P, r, ax)) return 2;
+  ray_shift<PLAIN>(P, r);
   return 0;
 }
 

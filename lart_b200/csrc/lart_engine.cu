@@ -210,13 +210,19 @@ __device__ __forceinline__ double walk_edge(const DevParams &P, const double *vt
 // the Jout tally is the caller's.
 // destroyed = the walk ended in a masked cell of a spherical atmosphere (:3316-3327: same binning, into Jabs2); a plane
 // atmosphere absorbs what leaves through its bottom cell (:3099-3107).
+template <bool PLAIN = false>
 __device__ __forceinline__ int finish_escape(const DevParams &P, Photon &ph, const Ray &r, bool destroyed = false) {
   ph.flags &= ~PH_ALIVE;
-  if (P.x.atm && (destroyed || (P.x.atm == 1 && !(r.kc > 1)))) ph.flags |= PH_ABS2;
-  if (P.x.shear) ph.vshear = r.vshear;
   ph.xfreq = DADD(r.xfreq, r.u1);
   ph.xfreq_ref = DMUL(ph.xfreq, r.cell.Dfreq / P.Dfreq_ref);
   ph.x = r.x0; ph.y = r.y0; ph.z = r.z0;
+  if (PLAIN) {
+    if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
+    ph.kc = r.kc;
+    return r.nsteps;
+  }
+  if (P.x.atm && (destroyed || (P.x.atm == 1 && !(r.kc > 1)))) ph.flags |= PH_ABS2;
+  if (P.x.shear) ph.vshear = r.vshear;
   if (P.amr.on) { ph.x = r.tx; ph.y = r.ty; ph.z = r.tz; }  // the running position at the last face (raytrace_amr.f90:219-222)
   if (P.bcxy == BC_MIRROR) {  // raytrace_car.f90:1934-1943: the end point and the reflected direction are stored even on escape
     ray_endpoint_bc(P, r, ph.x, ph.y, ph.z);
@@ -686,10 +692,14 @@ __global__ void __launch_bounds__(kBlock) k_wf_emit(const __grid_constant__ DevP
   flush_counters(P, cnt, nrng);
 }
 
+// the open-box walker instantiation applies (DevParams as created; clump runs have their own stages)
+inline bool is_plain(const DevParams &P) { return !P.amr.on && !P.bcxy && !P.bcz && !P.sym && !P.x.any && !P.clump; }
 // stage 2: raytrace_to_tau for every live photon, per-lane refill
 #ifndef LART_TRACE_MINBLOCKS
 #define LART_TRACE_MINBLOCKS 2
 #endif
+// PLAIN: see lart_device.cuh (ray_ulos) — the open-box instantiation of the walker
+template <bool PLAIN>
 __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const __grid_constant__ DevParams P, Pool pl, Job *job, Queues q, int budget) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
@@ -719,23 +729,23 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
           if (ph.flags & PH_FIRST) {
             int ci, cj, ck;
             clamp_cell_for_read(P, ph, ci, cj, ck);
-            load_cell(P, ci, cj, ck, cs0);
+            load_cell<PLAIN>(P, ci, cj, ck, cs0);
           }
           if (ph.flags & PH_INFLIGHT) {  // a walk suspended at its step budget in an earlier wave: resume it exactly
             const double *st = pl.rs + slot;
             ph.flags &= ~PH_INFLIGHT;
             mode = (ph.flags & PH_FIRST) ? 0 : 1;
             tau_in = pl.f[(size_t)F_TAU * S + slot];
-            ray_resume(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, st[0 * S], st[1 * S], st[2 * S], st[3 * S], st[4 * S],
+            ray_resume<PLAIN>(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, st[0 * S], st[1 * S], st[2 * S], st[3 * S], st[4 * S],
                        st[5 * S], st[6 * S], st[7 * S], st[8 * S], st[9 * S], pl.rc[slot], pl.rc[S + slot], pl.rc[2 * S + slot],
-                       P.x.edge_open && mode == 0);
-            if (P.x.shear) r.vshear = pl.f[(size_t)F_SHEAR * S + slot];
+                       !PLAIN && P.x.edge_open && mode == 0);
+            if (!PLAIN && P.x.shear) r.vshear = pl.f[(size_t)F_SHEAR * S + slot];
             have = true;
           } else {
             bool leaving;
             if (ph.flags & PH_FIRST) {
               mode = 0;
-              leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, false);
+              leaving = ray_setup<PLAIN>(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, false);
               if (leaving) {  // tau0 = 0 (raytrace_to_edge returns at once)
                 tau_in = forced_first(P, ph, rng, cs0, 0.0);
                 mode = 1;
@@ -750,9 +760,9 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
               mode = 1;
               leaving = true;
             }
-            if (P.x.shear) r.vshear = pl.f[(size_t)F_SHEAR * S + slot];
+            if (!PLAIN && P.x.shear) r.vshear = pl.f[(size_t)F_SHEAR * S + slot];
             if (mode == 1 && leaving)
-              leaving = ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true);
+              leaving = ray_setup<PLAIN>(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true);
             if (leaving) {  // dead without tally (raytrace_car.f90:1469-1472)
               ph.flags &= ~PH_ALIVE;
               load_rest(pl, slot, ph);
@@ -773,11 +783,11 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
     // ---- one cell step for every lane that has a ray
     if (have) {
       if (mode == 0) {
-        if (edge_step(P, vtab, r)) {
+        if (edge_step<PLAIN>(P, vtab, r)) {
           cnt.cellsteps += r.nsteps;
           tau_in = forced_first(P, ph, rng, cs0, r.tau);
           mode = 1;
-          if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
+          if (ray_setup<PLAIN>(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
             ph.flags &= ~PH_ALIVE;
             load_rest(pl, slot, ph);
             { retire_photon(P, ph, false, job, cnt); atomicAdd(q.n_dead, 1u); }
@@ -788,22 +798,22 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
         }
       } else {
         double xp, yp, zp;
-        int st = tau_step(P, vtab, r, tau_in, xp, yp, zp, ph.wgt);
+        int st = tau_step<PLAIN>(P, vtab, r, tau_in, xp, yp, zp, ph.wgt);
         if (st == 1) {
           ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
           if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
           ph.kc = r.kc;
           ph.flags |= PH_SCATTER;
           cnt.cellsteps += r.nsteps;
-          if (P.bcxy == BC_MIRROR && r.flip) { adopt_direction(r, ph); store_direction(pl, slot, ph); }
-          if (P.x.shear) pl.f[(size_t)F_SHEAR * S + slot] = r.vshear;
+          if (!PLAIN && P.bcxy == BC_MIRROR && r.flip) { adopt_direction(r, ph); store_direction(pl, slot, ph); }
+          if (!PLAIN && P.x.shear) pl.f[(size_t)F_SHEAR * S + slot] = r.vshear;
           store_trace_part(pl, slot, ph);
           pl.ndraw[slot] = rng.nblk;
           nrng += rng.nrng;
           have = false;
         } else if (st >= 2) {
           load_rest(pl, slot, ph);  // before finish_escape: it writes ph.xfreq_ref
-          cnt.cellsteps += finish_escape(P, ph, r, st == 3);
+          cnt.cellsteps += finish_escape<PLAIN>(P, ph, r, st == 3);
           { retire_photon(P, ph, true, job, cnt); atomicAdd(q.n_dead, 1u); }
           store_trace_part(pl, slot, ph);
           nrng += rng.nrng;
@@ -820,7 +830,7 @@ __global__ void __launch_bounds__(kBlock, LART_TRACE_MINBLOCKS) k_wf_trace(const
         for (int k = 0; k < 10; ++k) st[(size_t)k * S] = st10[k];
         pl.rc[slot] = c3[0]; pl.rc[S + slot] = c3[1]; pl.rc[2 * S + slot] = c3[2];
         pl.f[(size_t)F_TAU * S + slot] = tau_in;
-        if (P.x.shear) pl.f[(size_t)F_SHEAR * S + slot] = r.vshear;
+        if (!PLAIN && P.x.shear) pl.f[(size_t)F_SHEAR * S + slot] = r.vshear;
         ph.flags |= PH_INFLIGHT;
         store_trace_part(pl, slot, ph);  // weight and flags may have changed (forced first scattering)
         pl.ndraw[slot] = rng.nblk;
@@ -1472,6 +1482,7 @@ __global__ void __launch_bounds__(kBlock, LART_APPLY_MINBLOCKS) k_wf_apply(const
 #ifndef LART_PEEL_REFILL
 #define LART_PEEL_REFILL kRefillMin
 #endif
+template <bool PLAIN>
 __global__ void __launch_bounds__(kBlock, LART_PEEL_MINBLOCKS) k_wf_peel(const __grid_constant__ DevParams P, Pool pl, Queues q, int budget, int cont_only) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
@@ -1497,19 +1508,19 @@ __global__ void __launch_bounds__(kBlock, LART_PEEL_MINBLOCKS) k_wf_peel(const _
         else if (idx < ncont) {  // resume a suspended ray
           const PeelCont &c = cin[idx];
           ray_load(pr, &c.pr);
-          ray_resume(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, c.tx, c.ty, c.tz, c.delx, c.dely, c.delz, c.d, c.tau,
-                     c.xfreq, c.u1, c.ic, c.jc, c.kc, P.x.edge_open != 0);
+          ray_resume<PLAIN>(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, c.tx, c.ty, c.tz, c.delx, c.dely, c.delz, c.d, c.tau,
+                     c.xfreq, c.u1, c.ic, c.jc, c.kc, !PLAIN && P.x.edge_open != 0);
           have = true;
         } else {
           ray_load(pr, q.rays + q.direct_base + (idx - ncont));
           cnt.peel += 1;
-          if (ray_setup(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
+          if (ray_setup<PLAIN>(P, r, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, false)) zero_tau = true;
           else have = true;
         }
       }
     }
     bool fin = zero_tau;
-    if (have && edge_step(P, vtab, r)) { fin = true; have = false; cnt.cellsteps += r.nsteps; }
+    if (have && edge_step<PLAIN>(P, vtab, r)) { fin = true; have = false; cnt.cellsteps += r.nsteps; }
     unsigned fm = __ballot_sync(FULL, fin);
     if (fin) peel_deposit(P, pr, zero_tau ? 0.0 : r.tau, fm);
     if (have && r.nsteps >= budget) {  // park the ray: the next wave continues it
@@ -1518,7 +1529,7 @@ __global__ void __launch_bounds__(kBlock, LART_PEEL_MINBLOCKS) k_wf_peel(const _
         PeelCont &c = cout[at];
         ray_store(&c.pr, pr);
         c.tx = r.tx; c.ty = r.ty; c.tz = r.tz; c.delx = r.delx; c.dely = r.dely; c.delz = r.delz;
-        c.d = r.d; c.tau = r.tau; c.xfreq = r.xfreq; c.u1 = r.u1; c.ic = r.ic; c.jc = r.jc; c.kc = r.kc | (r.flip << kFlipShift);
+        c.d = r.d; c.tau = r.tau; c.xfreq = r.xfreq; c.u1 = r.u1; c.ic = r.ic; c.jc = r.jc; c.kc = r.kc | ((r.flip & 7) << kFlipShift);
         cnt.cellsteps += r.nsteps;
         have = false;
       } else {
@@ -3149,7 +3160,8 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight, bool def
       q.direct_cap = (unsigned)h->ray_cap;
       k_wf_reset<<<1, 1, 0, h->stream>>>(q);
       k_mono<true><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, q);
-      k_wf_peel<<<std::max(1, h->nsm * LART_PEEL_MINBLOCKS), kBlock, 0, h->stream>>>(h->P, h->pool, q, 0x7fffffff, 0);
+      if (is_plain(h->P)) k_wf_peel<true><<<std::max(1, h->nsm * LART_PEEL_MINBLOCKS), kBlock, 0, h->stream>>>(h->P, h->pool, q, 0x7fffffff, 0);
+      else k_wf_peel<false><<<std::max(1, h->nsm * LART_PEEL_MINBLOCKS), kBlock, 0, h->stream>>>(h->P, h->pool, q, 0x7fffffff, 0);
       h->launches += 2;
     } else k_mono<false><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, Queues{});
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
@@ -3172,7 +3184,8 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight, bool def
           else k_wf_emit<<<grid, kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.clump) k_cl_flight<<<std::max(1, std::min(nb, h->nsm * 3)), kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q);
-          else k_wf_trace<<<std::max(1, std::min(nb, h->nsm * LART_TRACE_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
+          else if (is_plain(h->P)) k_wf_trace<true><<<std::max(1, std::min(nb, h->nsm * LART_TRACE_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
+          else k_wf_trace<false><<<std::max(1, std::min(nb, h->nsm * LART_TRACE_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, h->job, g.q, h->budget);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           auto between = [&]() -> int { return with_marks ? mark(g.tev, ne[gi], g.stream) : 0; };
           if (h->P.clump) {
@@ -3182,7 +3195,8 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight, bool def
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
           if (h->P.nobs == 0) {}  // no observers: nothing to peel (xyz_symmetry, plain slabs)
           else if (h->P.clump) k_cl_peel<<<std::max(1, std::min(nb, h->nsm * 4)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q);
-          else k_wf_peel<<<std::max(1, std::min(nb, h->nsm * LART_PEEL_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
+          else if (is_plain(h->P)) k_wf_peel<true><<<std::max(1, std::min(nb, h->nsm * LART_PEEL_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
+          else k_wf_peel<false><<<std::max(1, std::min(nb, h->nsm * LART_PEEL_MINBLOCKS)), kBlock, 0, g.stream>>>(h->P, g.pool, g.q, h->budget, 0);
           if (with_marks) if (int rc = mark(g.tev, ne[gi], g.stream)) return rc;
         }
       }
@@ -3315,8 +3329,12 @@ int drain(lart_gpu_handle h, bool flights) {
     const int nb = (g.pool.n + kBlock - 1) / kBlock;
     const int grid = std::max(1, std::min(nb, h->nsm * 2));
     k_wf_reset<<<1, 1, 0, h->stream>>>(g.q);
-    if (flights) k_wf_trace<<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, h->job, g.q, big);
-    k_wf_peel<<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, g.q, big, 1);
+    if (flights) {
+      if (is_plain(h->P)) k_wf_trace<true><<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, h->job, g.q, big);
+      else k_wf_trace<false><<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, h->job, g.q, big);
+    }
+    if (is_plain(h->P)) k_wf_peel<true><<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, g.q, big, 1);
+    else k_wf_peel<false><<<grid, kBlock, 0, h->stream>>>(h->P, g.pool, g.q, big, 1);
     h->launches += flights ? 3 : 2;
   }
   CUDA_OK(cudaGetLastError());

@@ -312,6 +312,21 @@ int lart_gpu_create(const lart_config *cfg, lart_gpu_handle *out);
  * (src/run_simulation_mod.f90:150-202; partition rule :150). */
 int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride);
 
+/* ---- dynamic photon dealing on one node: the GPU analogue of the reference's master/worker loop -------------------------
+ * (src/run_simulation_mod.f90:31-128: workers ask the master for batches of par%num_send_at_once photons).  The processes
+ * of a node (one per GPU) share ONE 64-bit counter in POSIX shared memory, `name` ('/lart_...'); a process whose job queue
+ * runs dry claims the next `batch` photon ids with an atomic fetch-add — no master rank, no messages — and keeps its
+ * photons in flight while the new ids are emitted.  Photon streams are keyed by id, so tallies summed over the processes
+ * equal the statically partitioned run (lart_gpu_run) up to summation order.
+ *   one rank:   lart_gpu_deal_open(name, 1, &d)   creates and zeroes the counter; then a host barrier (MPI_BARRIER)
+ *   the others: lart_gpu_deal_open(name, 0, &d)
+ *   every rank: lart_gpu_run_dealt(h, d, par%nphotons, batch, &mine)   mine = photons this process ran
+ *   every rank: lart_gpu_deal_close(d, unlink)     unlink != 0 on one rank removes the name */
+typedef struct lart_gpu_deal *lart_gpu_deal_handle;
+int lart_gpu_deal_open(const char *name, int32_t reset, lart_gpu_deal_handle *out);
+int lart_gpu_deal_close(lart_gpu_deal_handle d, int32_t unlink_name);
+int lart_gpu_run_dealt(lart_gpu_handle h, lart_gpu_deal_handle d, int64_t nphotons, int64_t batch, int64_t *nclaimed);
+
 /* Bounded-work variant of the same loop (used for benchmarking heavy-tailed
  * cases): begin() queues the photon ids, each step() advances every pool slot by
  * at most `quantum` scattering events (`quantum` waves of the emit/trace/scatter/

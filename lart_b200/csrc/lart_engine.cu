@@ -28,6 +28,9 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <nccl.h>  // types and prototypes only: the library is opened at run time (lart_gpu_comm_init), never linked
 
 #include <algorithm>
@@ -39,6 +42,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cerrno>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -2363,6 +2368,8 @@ struct lart_gpu_ctx {
   int *cmp_src = nullptr, *cmp_dst = nullptr;  // compaction work lists
   unsigned int *cmp_n = nullptr;
   unsigned long long job_next = 0;  // job queue head after the last step
+  long long job_count = 0;          // ids in the job queue's current range (h->count = all ids handed to this handle so far)
+  bool more_to_claim = false;       // lart_gpu_run_dealt: the node's shared counter still has photons to deal
   std::vector<DevObserver> obs_host;  // host copy of the observers (sight-line maps)
   double sight_steps = 0.0, sight_ms = 0.0;
   long long count = 0;
@@ -3079,6 +3086,8 @@ int lart_gpu_begin(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t s
   h->job_next = 0;
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->count = count;
+  h->job_count = count;
+  h->more_to_claim = false;
   h->begun = true;
   return 0;
 }
@@ -3288,7 +3297,7 @@ void partition_pool(lart_gpu_handle h, int n) {
 
 // Compact the live photons into [0, alive) when the queue is empty and the pool is less than half full.
 int maybe_compact(lart_gpu_handle h, int64_t alive) {
-  if (h->groups.empty() || h->job_next < (unsigned long long)h->count) return 0;
+  if (h->groups.empty() || h->job_next < (unsigned long long)h->job_count || h->more_to_claim) return 0;
   if (alive * 2 > h->pool.n || h->pool.n <= 4096) return 0;
   if (int rc = drain_peel_only(h)) return rc;
   const int n_keep = (int)std::max<int64_t>(1024, (alive + 31) / 32 * 32);
@@ -3356,22 +3365,45 @@ int lart_gpu_sync(lart_gpu_handle h) {
   return check_device_error(err);
 }
 
-int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride) {
-  if (int rc = lart_gpu_begin(h, first_id, count, stride)) return rc;
+}  // extern "C"
+namespace {
+// the job queue's range is used up: hand the device the next range of photon ids; photons in flight are untouched
+int extend_job(lart_gpu_handle h, int64_t first_id, int64_t count) {
+  const unsigned long long head[2] = {0ULL, (unsigned long long)count};  // Job::next, Job::count
+  const long long first = (long long)first_id, stride = 1;
+  CUDA_OK(cudaMemcpyAsync(h->job, head, sizeof(head), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(&h->job->first_id, &first, sizeof(first), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(&h->job->stride, &stride, sizeof(stride), cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->job_next = 0;
+  h->job_count = count;
+  h->count += count;
+  return 0;
+}
+// claim(first_id, count): the next range of photon ids for this handle, false when the node has none left (dynamic dealing);
+// null: the ids queued by lart_gpu_begin are all there is
+int run_to_end(lart_gpu_handle h, int64_t left, const std::function<bool(int64_t &, int64_t &)> &claim) {
   const bool mono = (h->flags & LART_FLAG_MONOLITHIC) != 0;
-  int64_t left = count;
   long long tail_photons = kTailPhotons;
   if (const char *e = getenv("LART_GPU_TAIL_PHOTONS")) tail_photons = atoll(e);
   const char *pe = getenv("LART_GPU_PROGRESS");  // LART_GPU_PROGRESS=n: a line every n steps (default 64)
   const bool progress = pe != nullptr;
   const int pevery = pe && atoi(pe) > 0 ? atoi(pe) : 64;
   long long nstep = 0;
-  while (left > 0) {
+  h->more_to_claim = claim != nullptr;
+  while (left > 0 || h->more_to_claim) {
+    if (h->more_to_claim && h->job_next >= (unsigned long long)h->job_count) {  // the queue ran dry: ask for more work
+      int64_t first = 0, cnt = 0;
+      if (claim(first, cnt)) { if (int rc = extend_job(h, first, cnt)) return rc; left += cnt; }
+      else h->more_to_claim = false;
+      if (left <= 0) continue;
+    }
+    const bool dry = h->job_next >= (unsigned long long)h->job_count && !h->more_to_claim;
     // Heavy tail: once the queue is empty the pool thins out; keep it dense (compaction), and below
     // kTailPhotons let one thread per photon run `quantum` scatterings per launch — a wave is then bound by
     // launch latency (one scattering per ~5 launches), not by throughput.
     if (!mono) if (int rc = maybe_compact(h, left)) return rc;
-    const bool tail = !mono && left < tail_photons && h->job_next >= (unsigned long long)count;
+    const bool tail = !mono && left < tail_photons && dry;
     if (tail) if (int rc = drain(h, true)) return rc;  // the monolithic kernel cannot resume parked walks
     // tail steps: one thread per photon runs `tq` scatterings and queues their peel rays, the peel stage walks them afterwards;
     // tq is what the ray queue holds (one ray per scattering and observer)
@@ -3381,9 +3413,65 @@ int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t str
     if (int rc = step_impl(h, tail ? tq : h->quantum, mono || tail, &left, defer)) return rc;
     if (progress && (++nstep % pevery == 0 || left == 0))  // LART_GPU_PROGRESS=1: like the reference's nprint lines
       fprintf(stderr, "lart_gpu_run: %lld of %lld photons left, pool range %d, driver %s, device time %.3f s\n", (long long)left,
-              (long long)count, h->pool.n, (mono || tail) ? "monolithic" : "wavefront", h->kernel_ms * 1e-3);
+              (long long)h->count, h->pool.n, (mono || tail) ? "monolithic" : "wavefront", h->kernel_ms * 1e-3);
   }
   return lart_gpu_sync(h);
+}
+}  // namespace
+extern "C" {
+
+int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t stride) {
+  if (int rc = lart_gpu_begin(h, first_id, count, stride)) return rc;
+  return run_to_end(h, count, nullptr);
+}
+
+/* ---- dynamic photon dealing on one node (src/run_simulation_mod.f90:31-128: master/worker, batches of num_send_at_once) ----
+ * The node's processes share ONE 64-bit counter in POSIX shared memory; a process whose job queue runs dry claims the next
+ * `batch` photon ids with an atomic fetch-add — no master rank, no messages.  Streams are keyed by photon id, so the sum over
+ * the processes does not depend on who ran which photon. */
+struct lart_gpu_deal {
+  int fd = -1;
+  volatile long long *next = nullptr;
+  std::string name;
+};
+int lart_gpu_deal_open(const char *name, int32_t reset, lart_gpu_deal_handle *out) {
+  if (!name || !out || name[0] != '/') return fail("lart_gpu_deal_open: name must be a POSIX shared-memory name ('/...')");
+  *out = nullptr;
+  int fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+  if (fd < 0) return fail(std::string("lart_gpu_deal_open: shm_open failed: ") + strerror(errno));
+  if (ftruncate(fd, 64) != 0) { close(fd); return fail("lart_gpu_deal_open: ftruncate failed"); }
+  void *p = mmap(nullptr, 64, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  if (p == MAP_FAILED) { close(fd); return fail("lart_gpu_deal_open: mmap failed"); }
+  lart_gpu_deal *d = new lart_gpu_deal();
+  d->fd = fd; d->next = (volatile long long *)p; d->name = name;
+  if (reset) __atomic_store_n(d->next, 0LL, __ATOMIC_SEQ_CST);
+  *out = d;
+  return 0;
+}
+int lart_gpu_deal_close(lart_gpu_deal_handle d, int32_t unlink_name) {
+  if (!d) return 0;
+  if (d->next) munmap((void *)d->next, 64);
+  if (d->fd >= 0) close(d->fd);
+  if (unlink_name) shm_unlink(d->name.c_str());
+  delete d;
+  return 0;
+}
+int lart_gpu_run_dealt(lart_gpu_handle h, lart_gpu_deal_handle d, int64_t nphotons, int64_t batch, int64_t *nclaimed) {
+  if (!h || !d) return fail("lart_gpu_run_dealt: NULL argument");
+  if (nphotons < 0 || batch < 1) return fail("lart_gpu_run_dealt: nphotons must be >= 0 and batch >= 1");
+  int64_t mine = 0;
+  auto claim = [&](int64_t &first, int64_t &cnt) {
+    const long long a = __atomic_fetch_add(d->next, (long long)batch, __ATOMIC_SEQ_CST);
+    if (a >= nphotons) return false;
+    first = a + 1;  // photon ids are 1-based
+    cnt = std::min<int64_t>(batch, nphotons - a);
+    mine += cnt;
+    return true;
+  };
+  if (int rc = lart_gpu_begin(h, 1, 0, 1)) return rc;  // an empty queue: the first claim fills it
+  const int rc = run_to_end(h, 0, claim);
+  if (nclaimed) *nclaimed = mine;
+  return rc;
 }
 
 int lart_gpu_reset_tallies(lart_gpu_handle h) {

@@ -236,6 +236,20 @@ class Simulation:
         first, count, stride = photon_partition(n, rank, nproc)
         self._check(self._lib.lart_gpu_run(self._h, first, count, stride))
 
+    def run_simulation_dealt(self, deal_name, nphotons=None, batch=65536, create=False):
+        """Master/worker mode (run_simulation_mod.f90:31-128) without a master: the node's processes claim batches of
+        photon ids from one shared counter (POSIX shared memory `deal_name`, '/...') whenever their queue runs dry.
+        create=True on exactly one process, before the others open it (host barrier).  Returns the photons this
+        process ran."""
+        n = int(self.model.config.contents.par.nphotons if nphotons is None else nphotons)
+        d, mine = C.c_void_p(), C.c_int64()
+        self._check(self._lib.lart_gpu_deal_open(deal_name.encode(), 1 if create else 0, C.byref(d)))
+        try:
+            self._check(self._lib.lart_gpu_run_dealt(self._h, d, n, int(batch), C.byref(mine)))
+        finally:
+            self._lib.lart_gpu_deal_close(d, 0)
+        return mine.value
+
     def begin(self, first_id, count, stride=1):
         self._check(self._lib.lart_gpu_begin(self._h, first_id, count, stride))
 

@@ -63,3 +63,16 @@ def test_no_product_code_touches_the_oracle():
                 if re.search(r"(^|\n)\s*(from|import)\s+oracle|liblart_oracle|oracle/", text):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_deal_counter_is_shared_memory_and_needs_no_gpu():
+    """lart_gpu_deal_open/close (the node-wide photon counter of lart_gpu_run_dealt) are host-only calls."""
+    lib = capi.load_gpu()
+    name = ("/lart_abi_deal_%d" % os.getpid()).encode()
+    a, b = ctypes.c_void_p(), ctypes.c_void_p()
+    assert lib.lart_gpu_deal_open(name, 1, ctypes.byref(a)) == 0 and a.value
+    assert lib.lart_gpu_deal_open(name, 0, ctypes.byref(b)) == 0 and b.value
+    assert os.path.exists("/dev/shm" + name.decode())
+    assert lib.lart_gpu_deal_close(b, 0) == 0 and lib.lart_gpu_deal_close(a, 1) == 0
+    assert not os.path.exists("/dev/shm" + name.decode())
+    assert lib.lart_gpu_deal_open(b"no_leading_slash", 1, ctypes.byref(a)) != 0

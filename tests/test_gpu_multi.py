@@ -79,3 +79,58 @@ def test_two_gpu_reduce_inside_the_abi_equals_one_rank():
     assert np.abs(Q - Q1).sum() <= 1e-10 * np.abs(Q1).sum()
     assert nsg == pytest.approx(m.nscatt_gas, rel=1e-12)
     assert done_twice == 2 * n
+
+
+# ---- dynamic photon dealing (run_simulation_mod.f90:31-128 without a master): processes of one node claim batches ------
+def _dealt_worker(rank, name, batch, q):
+    sys.path.insert(0, ROOT)
+    from lart_b200 import Model, Simulation
+    m = Model(**PAR).setup()
+    ndev = _ndev()
+    sim = Simulation(m, device=rank % max(ndev, 1), pool_slots=512, quantum=4)
+    mine = sim.run_simulation_dealt(name, batch=batch)
+    sim.output_reduce()  # no communicator in this process: a plain fetch into its own host arrays
+    sim.close()
+    q.put((rank, mine, m.spectrum("Jout").copy(), m.observer_cube("scatt").copy(), m.allph("nscatt_gas").copy(), m.nscatt_gas,
+           m.counters["n_photons_done"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [100, 700])
+def test_dynamically_dealt_photons_sum_to_the_single_run(batch):
+    """Two processes share the node's photon counter (both on GPU 0 when the box has one): every photon id is run exactly once,
+    by whichever process claimed its batch, and the summed tallies are those of one statically partitioned run."""
+    import ctypes as C
+    import torch.multiprocessing as mp
+    from lart_b200 import Model, Simulation, capi
+    lib = capi.load_gpu()
+    name = "/lart_test_deal_%d_%d" % (os.getpid(), batch)
+    d = C.c_void_p()
+    assert lib.lart_gpu_deal_open(name.encode(), 1, C.byref(d)) == 0  # created and zeroed before the workers start
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_dealt_worker, args=(r, name, batch, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = sorted(q.get(timeout=300) for _ in procs)
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        lib.lart_gpu_deal_close(d, 1)
+    n = PAR["no_photons"]
+    (_, mine0, j0, s0, a0, g0, d0), (_, mine1, j1, s1, a1, g1, d1) = res
+    assert mine0 + mine1 == n and d0 + d1 == n and mine0 == d0 and mine1 == d1
+    assert mine0 > 0 and mine1 > 0 and mine0 % batch in (0, n % batch) or mine1 % batch in (0, n % batch)
+    m = Model(**PAR).setup()
+    sim = Simulation(m, device=0, pool_slots=2048)
+    sim.run_simulation()
+    sim.output_reduce()
+    sim.close()
+    ref = m.allph("nscatt_gas")
+    assert np.all((a0 == 0) | (a1 == 0))                 # no photon was run twice ...
+    assert np.array_equal(a0 + a1, ref)                  # ... and every one was run, with the history of the single run
+    assert np.allclose(j0 + j1, m.spectrum("Jout"), rtol=1e-12, atol=1e-300)
+    assert np.allclose(s0 + s1, m.observer_cube("scatt"), rtol=1e-10, atol=1e-300)
+    assert g0 + g1 == pytest.approx(m.nscatt_gas, rel=1e-12)

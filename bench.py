@@ -88,6 +88,10 @@ def parse():
     ap.add_argument("--streams", type=int, default=0, help="wave pipelines (pool partitions on separate streams); 0 = auto")
     ap.add_argument("--complete-workload", default="sphere_peel_tau1e4", choices=sorted(WORKLOADS),
                     help="workload of the `complete_run` record: every photon to its escape through lart_gpu_run")
+    ap.add_argument("--deal-batch", type=int, default=0,
+                    help="complete run under --gpus N: 0 = static photon partition (ids rank+1 : N : nranks, run_simulation_mod.f90:150); "
+                         "> 0 = dynamic dealing, ranks claim batches of this many ids from a shared-memory counter (lart_gpu_run_dealt, "
+                         "the master/worker mode of run_simulation_mod.f90:31-128)")
     ap.add_argument("--complete-photons", type=float, default=1e6,
                     help="photons of the complete run, TOTAL over all GPUs (strong scaling under --gpus N); 0 = skip")
     return ap.parse_args()
@@ -427,11 +431,21 @@ def run_gpu(args):
         barrier()
         t0 = time.perf_counter()
         sim = Simulation(cm, device=local, pool_slots=args.pool_slots, flags=args.flags & ~capi.FLAG_STAGE_TIMING, streams=args.streams)
-        sim.run_simulation(rank, world, ntot)
+        dealt = None
+        if args.deal_batch > 0 and world > 1:
+            deal_name = "/lart_bench_deal_%s" % os.environ.get("MASTER_PORT", "0")
+            if rank == 0:  # create and zero the node's counter before anybody claims from it
+                sim.open_deal(deal_name, create=True)
+            barrier()
+            dealt = sim.run_simulation_dealt(deal_name, ntot, batch=args.deal_batch)
+        else:
+            sim.run_simulation(rank, world, ntot)
         t_run = time.perf_counter() - t0
         sim.output_reduce(dst=0)
         barrier()
         t_all = time.perf_counter() - t0
+        if dealt is not None and rank == 0:
+            sim.unlink_deal(deal_name)
         dms, _ = sim.kernel_ms()
         sim.close()
         tt = torch.tensor([t_all, t_run, dms * 1e-3], dtype=torch.float64, device="cuda")
@@ -452,6 +466,8 @@ def run_gpu(args):
                         "wall_s": float(tt[0]), "photons_per_s": ntot / float(tt[0]), "scatterings_per_s": cc["n_scatter"] / float(tt[0]),
                         "mean_nscatt": cc["n_scatter"] / ntot, "run_s_max_rank": float(tt[1]), "run_s_min_rank": float(tmin[1]),
                         "device_s_max_rank": float(tt[2]), "flux_check": flux,
+                        "photon_partition": ("dynamic: batches of %d ids claimed from a shared counter (lart_gpu_run_dealt)" % args.deal_batch)
+                        if dealt is not None else "static: ids rank+1 : N : nranks",
                         "region": "lart_gpu_create (H2D grid) + lart_gpu_run to the last photon (ids rank+1 : N : nranks) + "
                                   "lart_gpu_reduce (NCCL) + lart_gpu_fetch into host arrays; wall = max over ranks"}
 

@@ -236,6 +236,18 @@ class Simulation:
         first, count, stride = photon_partition(n, rank, nproc)
         self._check(self._lib.lart_gpu_run(self._h, first, count, stride))
 
+    def open_deal(self, deal_name, create=False):
+        """Create (and zero) or just touch the node's shared photon counter; the handle is closed again at once —
+        the name persists until unlink_deal."""
+        d = C.c_void_p()
+        self._check(self._lib.lart_gpu_deal_open(deal_name.encode(), 1 if create else 0, C.byref(d)))
+        self._lib.lart_gpu_deal_close(d, 0)
+
+    def unlink_deal(self, deal_name):
+        d = C.c_void_p()
+        self._check(self._lib.lart_gpu_deal_open(deal_name.encode(), 0, C.byref(d)))
+        self._lib.lart_gpu_deal_close(d, 1)
+
     def run_simulation_dealt(self, deal_name, nphotons=None, batch=65536, create=False):
         """Master/worker mode (run_simulation_mod.f90:31-128) without a master: the node's processes claim batches of
         photon ids from one shared counter (POSIX shared memory `deal_name`, '/...') whenever their queue runs dry.

@@ -66,6 +66,26 @@ WORKLOADS = {
                               nxim=100, nyim=100, distance=1e2),
     "amr_sphere_tau1e7": dict(amr="amr_sphere_l37", temperature=1e4, taumax=1e7, geometry="sphere", use_stokes=True, nxfreq=201,
                               nxim=129, nyim=129, distance=1e2),
+    # ---- SURVEY 8f-1 remainder / 8f-3 / 8f-4 (round 2): the same engine behind the less common bindings
+    # overlapping clump population (has_overlap): the event walk of raytrace_clump.f90:621-920 on the one-thread-per-photon driver
+    "clump_overlap_fcov3": dict(use_clump_medium=True, clump_allow_overlap=True, rmax=1.0, clump_radius=0.02, clump_f_cov=3.0,
+                                N_HImax=1e18, temperature=1e4, clump_sigma_v=15.0, geometry="sphere", nxfreq=201, nx=11, ny=11, nz=11,
+                                velocity_min=-600.0, velocity_max=600.0, nxim=129, nyim=129, distance=1e2),
+    # configs[1] with the reference's -DCALCJ -DCALCP -DCALCPnew build: J(x, r), Pa(r), Pnew(r) in 101 radial shells
+    "sphere_tau1e7_calcJP_radial": dict(temperature=1e4, taumax=1e7, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0, nxfreq=201,
+                                        nxim=129, nyim=129, distance=1e2, calc_J=True, calc_P=True, calc_Pnew=True, geometry_JPa=1),
+    # ... and per cell: J(nxfreq, nx, ny, nz) = 3.3 GB in HBM at 51 frequency bins (13 GB at the input's 201)
+    "sphere_tau1e7_calcJP_cells": dict(temperature=1e4, taumax=1e7, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0, nxfreq=51,
+                                       nxim=129, nyim=129, distance=1e2, calc_J=True, calc_P=True, calc_Pnew=True, geometry_JPa=3),
+    # shearing box: configs[0]'s slab as a periodic 64 x 64 x 201 box with par%Omega (raytrace_to_tau_car_xyper_shear)
+    "box_shear_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xy_periodic=True, geometry="rectangle", nx=64, ny=64, nz=201,
+                             xmax=0.32, ymax=0.32, zmax=1.0, Omega=2.0),
+    # exoplanet atmospheres (exponential profiles; plane-parallel illumination)
+    "plane_atmosphere_tau1e6": dict(geometry="plane_atmosphere", source_geometry="plane_illumination", temperature=1e4, taumax=1e6,
+                                    nz=201, zmax=1.0, density_zscale=0.3, use_stokes=True, nxfreq=201),
+    "spherical_atmosphere_tau1e6": dict(geometry="spherical_atmosphere", source_geometry="plane_illumination", temperature=1e4, taumax=1e6,
+                                        nx=201, ny=201, nz=201, rmax=1.0, rmin=0.4, density_rscale=0.3, use_stokes=True, nxfreq=201,
+                                        nxim=129, nyim=129, distance=1e2),
     # small case for smoke-testing the bench itself
     "tiny": dict(temperature=1e4, taumax=1e5, use_stokes=True, nx=41, ny=41, nz=41, rmax=1.0, nxfreq=61, nxim=33, nyim=33),
 }

@@ -712,6 +712,15 @@ LART_DEV long long jp_bin(const DevParams &P, int ic, int jc, int kc, double rho
     default: return kc - 1;
   }
 }
+// One atomic per distinct address among the lanes that arrive together (north-star part 5 for the path-length tallies):
+// early in a run every photon sits in the source's cell — and in a few frequency bins — so 2.4 M plain atomics per wave
+// would serialise on a handful of L2 lines (measured on the tau0 = 1e7 sphere: 3.4e8 scatterings/s with plain atomics).
+LART_DEV void atomic_add_grouped(double *addr, double v) {
+  const unsigned m = __match_any_sync(__activemask(), (unsigned long long)addr);
+  double sum = 0.0;
+  for (unsigned mm = m; mm; mm &= mm - 1) sum += __shfl_sync(m, v, __ffs(mm) - 1);  // every lane of the group, same order
+  if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(addr, sum);
+}
 // add_to_J + add_to_Pnew (raytrace_car.f90:3979-4045) for one path segment of a to_tau walk: del = its length,
 // dtauH = its line optical depth, xfreq = the photon's frequency in the cell's frame
 __device__ __noinline__ void jp_deposit(const DevParams &P, int ic, int jc, int kc, double rhokap, double Dfreq, double xfreq,
@@ -721,14 +730,14 @@ __device__ __noinline__ void jp_deposit(const DevParams &P, int ic, int jc, int 
   if (P.x.calc_J) {
     const double xref = DMUL(xfreq, Dfreq / P.Dfreq_ref);
     const int ix = (int)floor(DSUB(xref, P.xfreq_min) / P.dxfreq) + 1;
-    if (ix > 0 && ix <= P.nxfreq) atomicAdd(P.tally + P.lay.J + (ix - 1) + (long long)P.nxfreq * b, DMUL(del, wgt));
+    if (ix > 0 && ix <= P.nxfreq) atomic_add_grouped(P.tally + P.lay.J + (ix - 1) + (long long)P.nxfreq * b, DMUL(del, wgt));
   }
-  if (P.x.calc_Pnew) atomicAdd(P.tally + P.lay.Pnew + b, DMUL(dtauH, wgt) / (DMUL(rhokap, Dfreq) / P.x.cross0));
+  if (P.x.calc_Pnew) atomic_add_grouped(P.tally + P.lay.Pnew + b, DMUL(dtauH, wgt) / (DMUL(rhokap, Dfreq) / P.x.cross0));
 }
 // add_to_Pa (scattering_car.f90:829-860): one resonance scattering in cell (ic,jc,kc)
 __device__ __noinline__ void jp_add_Pa(const DevParams &P, int ic, int jc, int kc, double rhokap, double Dfreq, double wgt) {
   const long long b = jp_bin(P, ic, jc, kc, rhokap);
-  if (b >= 0) atomicAdd(P.tally + P.lay.Pa + b, wgt / (DMUL(rhokap, Dfreq) / P.x.cross0));
+  if (b >= 0) atomic_add_grouped(P.tally + P.lay.Pa + b, wgt / (DMUL(rhokap, Dfreq) / P.x.cross0));
 }
 
 // One cell step of raytrace_to_edge.  Returns true when the walk is finished.

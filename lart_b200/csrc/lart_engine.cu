@@ -196,15 +196,16 @@ __device__ void flush_counters(const DevParams &P, Counters &c, ctr_t nrng) {
 }
 
 // full walks (monolithic driver, batch API)
+template <bool PLAIN = false>
 __device__ __forceinline__ double walk_edge(const DevParams &P, const double *vtab, double x, double y, double z,
                                             double kx, double ky, double kz, int ic, int jc, int kc, double xfreq,
                                             int &nsteps, int trace_cap = 0, int *trace = nullptr) {
   Ray r;
   nsteps = 0;
-  if (ray_setup(P, r, x, y, z, kx, ky, kz, ic, jc, kc, xfreq, false)) return 0.0;
+  if (ray_setup<PLAIN>(P, r, x, y, z, kx, ky, kz, ic, jc, kc, xfreq, false)) return 0.0;
   for (;;) {
     if (trace && r.nsteps < trace_cap) trace[r.nsteps] = (int)cell_index(P, r.ic, r.jc, r.kc);
-    if (edge_step(P, vtab, r)) break;
+    if (edge_step<PLAIN>(P, vtab, r)) break;
   }
   nsteps = r.nsteps;
   return r.tau;
@@ -245,26 +246,27 @@ __device__ __forceinline__ void adopt_direction(const Ray &r, Photon &ph) { ph.k
 __device__ __forceinline__ void store_direction(const Pool &pl, int s, const Photon &ph) {
   pl.f[F_KX * pl.S + s] = ph.kx; pl.f[F_KY * pl.S + s] = ph.ky; pl.f[F_KZ * pl.S + s] = ph.kz;
 }
+template <bool PLAIN = false>
 __device__ __forceinline__ int walk_tau(const DevParams &P, const double *vtab, Photon &ph, double tau_in, CellData &cs) {
   Ray r;
-  if (P.x.shear) r.vshear = ph.vshear;
-  if (ray_setup(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
+  if (!PLAIN && P.x.shear) r.vshear = ph.vshear;
+  if (ray_setup<PLAIN>(P, r, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, true)) {
     ph.flags &= ~PH_ALIVE;  // raytrace_car.f90:1469-1472: returns before any update
     return -1;
   }
   for (;;) {
     double xp, yp, zp;
-    int st = tau_step(P, vtab, r, tau_in, xp, yp, zp, ph.wgt);
+    int st = tau_step<PLAIN>(P, vtab, r, tau_in, xp, yp, zp, ph.wgt);
     if (st == 1) {
       ph.x = xp; ph.y = yp; ph.z = zp; ph.xfreq = r.xfreq;
-      if (P.bcxy == BC_MIRROR) adopt_direction(r, ph);
+      if (!PLAIN && P.bcxy == BC_MIRROR) adopt_direction(r, ph);
       if (!P.zonly) { ph.ic = r.ic; ph.jc = r.jc; }
       ph.kc = r.kc;
-      if (P.x.shear) ph.vshear = r.vshear;
+      if (!PLAIN && P.x.shear) ph.vshear = r.vshear;
       cs = r.cell;
       return r.nsteps;
     }
-    if (st >= 2) return finish_escape(P, ph, r, st == 3);
+    if (st >= 2) return finish_escape<PLAIN>(P, ph, r, st == 3);
   }
 }
 
@@ -307,7 +309,7 @@ __device__ __forceinline__ void ray_append(const DevParams &P, const Queues &q, 
 // A photon's next scattering does not depend on its peel rays, but walked inline they are most of the time between two
 // scatterings of a thread (tau0 = 1e4 sphere: ~17 cells per ray, 97 us per event with 8 k photons left) — and in the
 // tail that latency, times the scatterings the longest-lived photon still needs, is the run time.
-template <bool DEFER>
+template <bool DEFER, bool PLAIN>
 __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevParams P, Pool pl, Job *job, int quantum, Queues q) {
   __shared__ double vtab[kVoigtTabN];
   load_vtab(P, vtab);
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
       load_trace_part(pl, s, ph);
       load_rest(pl, s, ph);
       load_rng(P, pl, s, ph.id, ph.flags, rng);
-      if (P.x.shear) ph.vshear = pl.f[(size_t)F_SHEAR * pl.S + s];
+      if (!PLAIN && P.x.shear) ph.vshear = pl.f[(size_t)F_SHEAR * pl.S + s];
       nev = pl.nev[s];
       rng_valid = true;
     }
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
               if (!peel_direct_prepare(P, P.obs[i], i, ph, cs, pr)) continue;
               if (DEFER) { ray_append(P, q, pr); continue; }
               int ns;
-              double tau = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns);
+              double tau = walk_edge<PLAIN>(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns);
               cnt.cellsteps += ns; cnt.peel += 1;
               peel_deposit(P, pr, tau, __activemask());
             }
@@ -362,8 +364,8 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
         if (ph.flags & PH_FIRST) {
           int ci, cj, ck, ns;
           clamp_cell_for_read(P, ph, ci, cj, ck);
-          load_cell(P, ci, cj, ck, cs);
-          double tau0 = walk_edge(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, ns);
+          load_cell<PLAIN>(P, ci, cj, ck, cs);
+          double tau0 = walk_edge<PLAIN>(P, vtab, ph.x, ph.y, ph.z, ph.kx, ph.ky, ph.kz, ph.ic, ph.jc, ph.kc, ph.xfreq, ns);
           cnt.cellsteps += ns;
           tau = forced_first(P, ph, rng, cs, tau0);
         } else if (ph.flags & PH_TAUPEND) {  // drawn by the wavefront scatter stage before a driver switch
@@ -372,14 +374,14 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
         } else {
           tau = -log(rng.uniform());
         }
-        int ns = walk_tau(P, vtab, ph, tau, cs);
+        int ns = walk_tau<PLAIN>(P, vtab, ph, tau, cs);
         if (ns > 0) cnt.cellsteps += ns;
         if (!(ph.flags & PH_ALIVE)) {
           retire_photon(P, ph, ns >= 0, job, cnt);
           continue;
         }
       } else {  // the wavefront scatter stage already flew this photon to its next scattering point
-        load_cell(P, ph.ic, ph.jc, ph.kc, cs);
+        load_cell<PLAIN>(P, ph.ic, ph.jc, ph.kc, cs);
         at_scatter = false;
         touched = true;
       }
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
       auto trace_and_deposit = [&](PeelRay &pr) {
         if (DEFER) { ray_append(P, q, pr); return; }
         int ns2;
-        double t = walk_edge(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns2);
+        double t = walk_edge<PLAIN>(P, vtab, pr.x, pr.y, pr.z, pr.kx, pr.ky, pr.kz, pr.ic, pr.jc, pr.kc, pr.xfreq, ns2);
         cnt.cellsteps += ns2; cnt.peel += 1;
         peel_deposit(P, pr, t, __activemask());
       };
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kBlock) k_mono(const __grid_constant__ DevPara
       if (fl & PH_ALIVE) store_rng(pl, s, rng, fl);
       ph.flags = fl;
       store_all(pl, s, ph);
-      if (P.x.shear) pl.f[(size_t)F_SHEAR * pl.S + s] = ph.vshear;
+      if (!PLAIN && P.x.shear) pl.f[(size_t)F_SHEAR * pl.S + s] = ph.vshear;
       pl.nev[s] = nev;
     }
     if (rng_valid) nrng += rng.nrng;
@@ -3168,11 +3170,13 @@ int step_impl(lart_gpu_handle h, int qn, bool mono, int64_t *in_flight, bool def
       q.direct_base = 0;
       q.direct_cap = (unsigned)h->ray_cap;
       k_wf_reset<<<1, 1, 0, h->stream>>>(q);
-      k_mono<true><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, q);
+      if (is_plain(h->P)) k_mono<true, true><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, q);
+      else k_mono<true, false><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, q);
       if (is_plain(h->P)) k_wf_peel<true><<<std::max(1, h->nsm * LART_PEEL_MINBLOCKS), kBlock, 0, h->stream>>>(h->P, h->pool, q, 0x7fffffff, 0);
       else k_wf_peel<false><<<std::max(1, h->nsm * LART_PEEL_MINBLOCKS), kBlock, 0, h->stream>>>(h->P, h->pool, q, 0x7fffffff, 0);
       h->launches += 2;
-    } else k_mono<false><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, Queues{});
+    } else if (is_plain(h->P)) k_mono<false, true><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, Queues{});
+    else k_mono<false, false><<<(h->pool.n + kBlock - 1) / kBlock, kBlock, 0, h->stream>>>(h->P, h->pool, h->job, qn, Queues{});
     if (int rc = mark(h->tev, ne, h->stream)) return rc;
     h->launches += 1;
   } else {

@@ -46,6 +46,7 @@
 #include <functional>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/lart_gpu.h"
@@ -2340,6 +2341,7 @@ int add_device_to_host(lart_gpu_ctx *h, const double *dev, long long total, cons
 }  // namespace
 
 struct lart_gpu_ctx {
+  double *soa_slab = nullptr;  // the host's SoA grid arrays on the device (one allocation; freed after packing unless LART_FLAG_SOA_GRID)
   long long jp_bins = 0;  // bins of the CALCP / CALCPnew arrays (CALCJ: nxfreq times as many)
   int device = 0;
   DevParams P{};
@@ -2751,11 +2753,16 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     const double *src[7] = {g.rhokap, g.voigt_a, g.Dfreq, g.vfx, g.vfy, g.vfz, P.dust ? g.rhokapD : nullptr};
     const double **dst[7] = {&P.rhokap, &P.voigt_a, &P.Dfreq, &P.vfx, &P.vfy, &P.vfz, &P.rhokapD};
     std::vector<UpJob> jobs;
-    for (int k = 0; k < 7 && !rc; ++k) {
+    int narr = 0;
+    for (int k = 0; k < 7; ++k) narr += src[k] ? 1 : 0;
+    const size_t nc_al = (nc + 31) / 32 * 32;  // 256-byte aligned arrays inside one allocation (one driver call, not seven)
+    double *slab = nullptr;
+    rc = rc ? rc : dalloc(h, &slab, nc_al * narr, false);
+    h->soa_slab = slab;
+    for (int k = 0, at = 0; k < 7 && !rc; ++k) {
       *dst[k] = nullptr;
       if (!src[k]) continue;
-      double *d = nullptr;
-      rc = dalloc(h, &d, nc, false);
+      double *d = slab + nc_al * (size_t)at++;
       *dst[k] = d;
       jobs.push_back({d, src[k], nc});
     }
@@ -2843,12 +2850,12 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     // the SoA copies have served: give their memory back to the pool, the photon pool allocated below reuses it
     CUDA_OK(cudaStreamSynchronize(h->stream));
     const double **soa[7] = {&P.rhokap, &P.voigt_a, &P.Dfreq, &P.vfx, &P.vfy, &P.vfz, &P.rhokapD};
-    for (auto pp : soa) {
-      if (!*pp) continue;
-      void *q = (void *)*pp;
+    for (auto pp : soa) *pp = nullptr;
+    if (h->soa_slab) {
+      void *q = (void *)h->soa_slab;
       h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), q), h->owned.end());
       dev_free(q);
-      *pp = nullptr;
+      h->soa_slab = nullptr;
     }
     CUDA_OK(cudaStreamSynchronize(0));
   }
@@ -2964,49 +2971,73 @@ int create_impl(const lart_config *cfg, lart_gpu_ctx *h) {
     rc = rc ? rc : dalloc(h, &P.cl.ov_act, T * kMaxEvt, false);
     if (rc) return bail(rc);
   }
-  rc = rc ? rc : dalloc(h, &h->pool.f, (size_t)F_COUNT * S);
-  rc = rc ? rc : dalloc(h, &h->pool.id, S);
-  rc = rc ? rc : dalloc(h, &h->pool.ndraw, S);
-  rc = rc ? rc : dalloc(h, &h->pool.ic, S);
-  rc = rc ? rc : dalloc(h, &h->pool.jc, S);
-  rc = rc ? rc : dalloc(h, &h->pool.kc, S);
-  rc = rc ? rc : dalloc(h, &h->pool.flags, S);
-  rc = rc ? rc : dalloc(h, &h->pool.rs, (size_t)10 * S);
-  rc = rc ? rc : dalloc(h, &h->pool.rc, (size_t)3 * S);
-  rc = rc ? rc : dalloc(h, &h->pool.nev, S);
-  if (!mono) rc = rc ? rc : dalloc(h, &h->pool.var, (size_t)6 * S);
-  if (!mono) rc = rc ? rc : dalloc(h, &h->pool.wtab, (size_t)12 * S);
-  if (!mono) rc = rc ? rc : dalloc(h, &h->pool.lst, S);
-  rc = rc ? rc : dalloc(h, &h->job, 1);
-  if (!rc) P.err = &h->job->err;
+  // The pool columns, the ray queue and the continuation queues are carved from ONE device allocation: a cold handle
+  // pays the driver's per-allocation cost (physical memory creation + mapping, a few ms each) once instead of 25 times —
+  // this phase was 99 ms of a cold lart_gpu_create.
   P.max_events = cfg->max_events > 0 ? cfg->max_events : 0;
-  rc = rc ? rc : dalloc(h, &h->cmp_src, S);
-  rc = rc ? rc : dalloc(h, &h->cmp_dst, S);
-  rc = rc ? rc : dalloc(h, &h->cmp_n, 2);
   h->pool.s0 = 0; h->pool.n = S;
-  if (!mono && !rc) {
-    int G = cfg->streams > 0 ? cfg->streams : 6;
-    G = std::max(1, std::min(G, std::min(16, S / 1024 > 0 ? S / 1024 : 1)));
-    const long long nobs = P.nobs;
-    const long long ray_cap = std::min<long long>((long long)S * std::max<long long>(nobs, 1) * 2, 0x7fffffffLL);
-    rc = rc ? rc : dalloc(h, &h->rays, (size_t)ray_cap, true);
-    h->ray_cap = ray_cap;
-    unsigned int *ctr = nullptr;
-    rc = rc ? rc : dalloc(h, &ctr, 8 * (size_t)G);
-    h->ctr = ctr; h->ctr_n = 8 * (size_t)G;
-    // suspended peel rays (walks longer than the per-wave step budget): room for half of a wave's rays per buffer; a ray that
-    // finds its queue full simply keeps walking in this wave (k_wf_peel), so the size is a performance knob, not a limit
-    auto cont_cap_of = [&](long long n) { return std::max<long long>(1024, n * std::max<long long>(nobs, 1) / 2) + 32; };
-    long long cont_total = 0;
-    {
-      const int per0 = ((S / G) + 31) / 32 * 32;
-      for (int g = 0; g < G; ++g) {
-        const int s0 = std::min(g * per0, S), n = (g == G - 1) ? S - s0 : std::min(per0, S - s0);
-        cont_total += 2 * cont_cap_of(n);
-      }
+  int G = cfg->streams > 0 ? cfg->streams : 6;
+  G = std::max(1, std::min(G, std::min(16, S / 1024 > 0 ? S / 1024 : 1)));
+  const long long nobs = P.nobs;
+  const long long ray_cap = mono ? 0 : std::min<long long>((long long)S * std::max<long long>(nobs, 1) * 2, 0x7fffffffLL);
+  // suspended peel rays (walks longer than the per-wave step budget): room for half of a wave's rays per buffer; a ray that
+  // finds its queue full simply keeps walking in this wave (k_wf_peel), so the size is a performance knob, not a limit
+  auto cont_cap_of = [&](long long n) { return std::max<long long>(1024, n * std::max<long long>(nobs, 1) / 2) + 32; };
+  long long cont_total = 0;
+  if (!mono) {
+    const int per0 = ((S / G) + 31) / 32 * 32;
+    for (int g = 0; g < G; ++g) {
+      const int s0 = std::min(g * per0, S), n = (g == G - 1) ? S - s0 : std::min(per0, S - s0);
+      cont_total += 2 * cont_cap_of(n);
     }
-    PeelCont *cont = nullptr;
-    rc = rc ? rc : dalloc(h, &cont, (size_t)cont_total, false);
+  }
+  unsigned int *ctr = nullptr;
+  PeelCont *cont = nullptr;
+  auto layout = [&](char *base) -> size_t {  // base = nullptr: sizes only
+    size_t off = 0;
+    auto carve = [&](auto **p, size_t n) {
+      using T = std::remove_pointer_t<std::remove_pointer_t<decltype(p)>>;
+      *p = reinterpret_cast<T *>(base + off);
+      off += (std::max<size_t>(n, 1) * sizeof(T) + 255) / 256 * 256;
+    };
+    carve(&h->pool.f, (size_t)F_COUNT * S);
+    carve(&h->pool.id, (size_t)S);
+    carve(&h->pool.ndraw, (size_t)S);
+    carve(&h->pool.ic, (size_t)S);
+    carve(&h->pool.jc, (size_t)S);
+    carve(&h->pool.kc, (size_t)S);
+    carve(&h->pool.flags, (size_t)S);
+    carve(&h->pool.rs, (size_t)10 * S);
+    carve(&h->pool.rc, (size_t)3 * S);
+    carve(&h->pool.nev, (size_t)S);
+    if (!mono) {
+      carve(&h->pool.var, (size_t)6 * S);
+      carve(&h->pool.wtab, (size_t)12 * S);
+      carve(&h->pool.lst, (size_t)S);
+    }
+    carve(&h->job, (size_t)1);
+    carve(&h->cmp_src, (size_t)S);
+    carve(&h->cmp_dst, (size_t)S);
+    carve(&h->cmp_n, (size_t)2);
+    if (!mono) {
+      carve(&h->rays, (size_t)ray_cap);
+      carve(&ctr, 8 * (size_t)G);
+      carve(&cont, (size_t)cont_total);
+    }
+    return off;
+  };
+  {
+    const size_t total = layout(nullptr);
+    char *slab = nullptr;
+    if ((rc = dalloc(h, &slab, total, false))) return bail(rc);
+    CUDA_OK(cudaMemsetAsync(slab, 0, total, h->stream));  // ~1 ms per 3 GB; flags = 0 marks every slot dead
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    layout(slab);
+  }
+  P.err = &h->job->err;
+  if (!mono) {
+    h->ray_cap = ray_cap;
+    h->ctr = ctr; h->ctr_n = 8 * (size_t)G;
     h->groups.resize(G);
     long long cont_off = 0;
     int per = ((S / G) + 31) / 32 * 32;

@@ -350,7 +350,8 @@ def run_gpu(args):
     mono = bool(args.flags & 4)
     clump = bool(cfg.par.use_clump_medium)
     names = {"emit": "k_cl_emit" if clump else "k_wf_emit", "trace": "k_cl_flight" if clump else "k_wf_trace",
-             "draw": "k_cl_scatter" if clump else "k_wf_draw", "apply": "k_wf_apply", "peel": "k_cl_peel" if clump else "k_wf_peel"}
+             "draw": "k_cl_scatter" if clump else ("k_wf_draw" if args.flags & (16 | 128) else "k_wf_draw2"), "apply": "k_wf_apply",
+             "peel": "k_cl_peel" if clump else "k_wf_peel"}
     if mono:
         names["trace"] = "k_mono_clump" if clump else "k_mono"
     tot_stage = max(sum(v[0] for v in stage.values()), 1e-30)

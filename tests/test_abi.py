@@ -76,3 +76,43 @@ def test_deal_counter_is_shared_memory_and_needs_no_gpu():
     assert lib.lart_gpu_deal_close(b, 0) == 0 and lib.lart_gpu_deal_close(a, 1) == 0
     assert not os.path.exists("/dev/shm" + name.decode())
     assert lib.lart_gpu_deal_open(b"no_leading_slash", 1, ctypes.byref(a)) != 0
+
+
+def test_fortran_shim_mirrors_the_header_member_for_member():
+    """shim/lart_gpu_shim.f90 cannot be compiled here (no Fortran compiler in the image), so its bind(C) types are checked
+    textually: every `c_lart_X` type must list the members of `lart_X` in include/lart_gpu.h in the same order, and every
+    entry point it binds must be declared in the header."""
+    hdr = open(os.path.join(ROOT, "include", "lart_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    shim = open(os.path.join(ROOT, "shim", "lart_gpu_shim.f90")).read()
+    shim = re.sub(r"!.*", "", shim)
+    shim = re.sub(r"&\s*\n\s*", " ", shim)
+
+    def c_members(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(unsigned\s+)?[A-Za-z_0-9]+\s+", "", decl)  # drop the type
+            for m in decl.split(","):
+                m = re.sub(r"\[.*?\]", "", m).replace("*", "").replace("const", "").strip()
+                out.append(m.lower())
+        return out
+
+    def f_members(name):
+        body = re.search(r"type, bind\(C\) :: c_%s\b(.*?)end type" % name, shim, re.S | re.I).group(1)
+        out = []
+        for line in body.splitlines():
+            if "::" not in line:
+                continue
+            for m in line.split("::", 1)[1].split(","):
+                out.append(re.sub(r"\(.*?\)", "", m).strip().lower())
+        return [m for m in out if m]
+
+    for name in ("lart_grid", "lart_params", "lart_line", "lart_observer", "lart_scatt_mat", "lart_clumps", "lart_amr",
+                 "lart_config", "lart_observer_out", "lart_allph_out", "lart_counters", "lart_tallies"):
+        assert f_members(name) == c_members(name), name
+    for fn in re.findall(r"bind\(C, name='(\w+)'\)", shim):
+        assert re.search(r"\b%s\s*\(" % fn, hdr), fn

@@ -325,6 +325,9 @@ int lart_gpu_run(lart_gpu_handle h, int64_t first_id, int64_t count, int64_t str
 typedef struct lart_gpu_deal *lart_gpu_deal_handle;
 int lart_gpu_deal_open(const char *name, int32_t reset, lart_gpu_deal_handle *out);
 int lart_gpu_deal_close(lart_gpu_deal_handle d, int32_t unlink_name);
+/* one claim: the next `batch` photon ids, first_id .. first_id+count-1 (count = 0: none left).  Host-only (no GPU needed);
+ * lart_gpu_run_dealt makes exactly this call whenever its job queue runs dry. */
+int lart_gpu_deal_claim(lart_gpu_deal_handle d, int64_t nphotons, int64_t batch, int64_t *first_id, int64_t *count);
 int lart_gpu_run_dealt(lart_gpu_handle h, lart_gpu_deal_handle d, int64_t nphotons, int64_t batch, int64_t *nclaimed);
 
 /* Bounded-work variant of the same loop (used for benchmarking heavy-tailed

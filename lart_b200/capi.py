@@ -163,7 +163,7 @@ GPU_SYMBOLS = [
     "lart_gpu_sightline_tau", "lart_gpu_sightline_stats",
     "lart_gpu_clump_edge_batch", "lart_gpu_clump_tau_batch", "lart_gpu_clump_locate_batch", "lart_gpu_peel_bound_batch", "lart_gpu_amr_locate_batch",
     "lart_gpu_comm_unique_id", "lart_gpu_comm_init", "lart_gpu_comm_info", "lart_gpu_comm_finalize", "lart_gpu_reduce",
-    "lart_gpu_deal_open", "lart_gpu_deal_close", "lart_gpu_run_dealt",
+    "lart_gpu_deal_open", "lart_gpu_deal_close", "lart_gpu_run_dealt", "lart_gpu_deal_claim",
 ]
 HOST_SYMBOLS = [
     "lart_host_new", "lart_host_free", "lart_host_set", "lart_host_read_input", "lart_host_setup",
@@ -257,6 +257,7 @@ def load_gpu():
             lib.lart_gpu_deal_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
             lib.lart_gpu_deal_close.argtypes = [C.c_void_p, C.c_int32]
             lib.lart_gpu_run_dealt.argtypes = [H, C.c_void_p, C.c_int64, C.c_int64, c_int64_p]
+            lib.lart_gpu_deal_claim.argtypes = [C.c_void_p, C.c_int64, C.c_int64, c_int64_p, c_int64_p]
         if hasattr(lib, "lart_gpu_amr_locate_batch"):
             lib.lart_gpu_amr_locate_batch.argtypes = [H, C.c_int64] + [c_double_p] * 3 + [c_int32_p]
         if hasattr(lib, "lart_gpu_peel_bound_batch"):  # (absent from older A/B builds selected through LART_GPU_LIB)

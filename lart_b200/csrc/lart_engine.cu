@@ -3503,15 +3503,20 @@ int lart_gpu_deal_close(lart_gpu_deal_handle d, int32_t unlink_name) {
   delete d;
   return 0;
 }
+int lart_gpu_deal_claim(lart_gpu_deal_handle d, int64_t nphotons, int64_t batch, int64_t *first_id, int64_t *count) {
+  if (!d || !first_id || !count) return fail("lart_gpu_deal_claim: NULL argument");
+  if (nphotons < 0 || batch < 1) return fail("lart_gpu_deal_claim: nphotons must be >= 0 and batch >= 1");
+  const long long a = __atomic_fetch_add(d->next, (long long)batch, __ATOMIC_SEQ_CST);
+  *first_id = a + 1;  // photon ids are 1-based
+  *count = a >= nphotons ? 0 : std::min<int64_t>(batch, nphotons - a);
+  return 0;
+}
 int lart_gpu_run_dealt(lart_gpu_handle h, lart_gpu_deal_handle d, int64_t nphotons, int64_t batch, int64_t *nclaimed) {
   if (!h || !d) return fail("lart_gpu_run_dealt: NULL argument");
   if (nphotons < 0 || batch < 1) return fail("lart_gpu_run_dealt: nphotons must be >= 0 and batch >= 1");
   int64_t mine = 0;
   auto claim = [&](int64_t &first, int64_t &cnt) {
-    const long long a = __atomic_fetch_add(d->next, (long long)batch, __ATOMIC_SEQ_CST);
-    if (a >= nphotons) return false;
-    first = a + 1;  // photon ids are 1-based
-    cnt = std::min<int64_t>(batch, nphotons - a);
+    if (lart_gpu_deal_claim(d, nphotons, batch, &first, &cnt) != 0 || cnt == 0) return false;
     mine += cnt;
     return true;
   };

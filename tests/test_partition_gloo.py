@@ -68,3 +68,62 @@ def test_two_rank_partition_and_reduce_equals_one_rank(medium):
     ref = np.concatenate([m.spectrum("Jout"), m.spectrum("Jin"), [m.nscatt_gas, m.counters["n_photons_done"]]])
     assert got[-1] == 301
     assert np.allclose(got, ref, rtol=1e-12, atol=0)
+
+
+# ---- dynamic dealing (run_simulation_mod.f90:31-128 without a master): the node's shared photon counter, on CPU -------------
+def _deal_worker(rank, world, port, q, name, nphotons, batch):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    from lart_b200 import capi
+    from lart_b200.host import Model
+    from oracle import oracle
+    lib = capi.load_gpu()  # the claim is a host-only entry point of the engine library: no GPU is touched
+    d = C.c_void_p()
+    if rank == 0:
+        assert lib.lart_gpu_deal_open(name.encode(), 1, C.byref(d)) == 0   # creates and zeroes the counter ...
+    dist.barrier()                                                         # ... before anybody claims
+    if rank != 0:
+        assert lib.lart_gpu_deal_open(name.encode(), 0, C.byref(d)) == 0
+    m = Model(**MEDIA["cartesian"]).setup()
+    first, count, mine = C.c_int64(), C.c_int64(), []
+    while True:
+        assert lib.lart_gpu_deal_claim(d, nphotons, batch, C.byref(first), C.byref(count)) == 0
+        if count.value == 0:
+            break
+        mine += list(range(first.value, first.value + count.value))
+        oracle.run(m, rng_mode=1, nthreads=1, first_id=first.value, count=count.value, stride=1)
+    t = torch.from_numpy(np.concatenate([m.spectrum("Jout"), m.spectrum("Jin"), [m.nscatt_gas, m.counters["n_photons_done"]]]))
+    dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+    ids = [None] * world
+    dist.all_gather_object(ids, mine)
+    if rank == 0:
+        q.put((t.numpy().copy(), ids))
+    dist.barrier()
+    lib.lart_gpu_deal_close(d, 1 if rank == 0 else 0)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [7, 100])
+def test_two_ranks_claiming_from_the_shared_counter_cover_every_photon_once(batch):
+    from lart_b200.host import Model
+    from oracle import oracle
+    n = 301
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 13 * batch) % 2000
+    name = "/lart_gloo_deal_%d_%d" % (os.getpid(), batch)
+    procs = [ctx.Process(target=_deal_worker, args=(r, 2, port, q, name, n, batch)) for r in range(2)]
+    for p in procs:
+        p.start()
+    summed, ids = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert sorted(ids[0] + ids[1]) == list(range(1, n + 1))   # every id exactly once, whoever claimed it
+    assert all(len(x) % batch in (0, n % batch) for x in ids)
+    m = Model(**MEDIA["cartesian"]).setup()
+    oracle.run(m, rng_mode=1, nthreads=1)
+    one = np.concatenate([m.spectrum("Jout"), m.spectrum("Jin"), [m.nscatt_gas, m.counters["n_photons_done"]]])
+    assert np.allclose(summed, one, rtol=1e-12, atol=1e-12)

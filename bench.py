@@ -31,10 +31,15 @@ WORKLOADS = {
     # the cell-by-cell core-skip variant of the same input
     "sphere_peel_tau1e7_coreskip": dict(temperature=1e4, taumax=1e7, use_stokes=True, nx=201, ny=201, nz=201, rmax=1.0,
                                         nxfreq=201, nxim=129, nyim=129, distance=1e2, core_skip=True),
-    # BASELINE configs[2]: examples/vel_effect_peel/t4NHI2_20_V0200.in
+    # BASELINE configs[2]: examples/vel_effect_peel/t4NHI2_20_V0200.in "with cell-by-cell core-skip" (the shipped input
+    # does not set par%core_skip; BASELINE's variant adds it — SURVEY 8, config sizes) ...
     "vel_effect_peel": dict(temperature=1e4, N_HI=2e20, Vexp=200.0, velocity_type="hubble", xfreq_min=-200.0,
                             xfreq_max=40.0, nxfreq=500, use_stokes=True, comoving_source=False, nx=201, ny=201, nz=201,
-                            rmax=1.0, nxim=129, nyim=129),
+                            rmax=1.0, nxim=129, nyim=129, core_skip=True),
+    # ... and the input as shipped
+    "vel_effect_peel_as_shipped": dict(temperature=1e4, N_HI=2e20, Vexp=200.0, velocity_type="hubble", xfreq_min=-200.0,
+                                       xfreq_max=40.0, nxfreq=500, use_stokes=True, comoving_source=False, nx=201, ny=201, nz=201,
+                                       rmax=1.0, nxim=129, nyim=129),
     # BASELINE configs[0]: examples/slab/t4tau7.in
     "slab_tau1e7": dict(temperature=1e4, taumax=1e7, use_stokes=True, xy_periodic=True, nx=1, ny=1, nz=201),
     # optically thinner variants of configs[1] (peel rays cross many cells: the DDA walk dominates)

@@ -355,7 +355,7 @@ def headline_model(workload, n, **extra):
 
 
 @pytest.mark.parametrize("workload,extra", [("sphere_peel_tau1e7", {}), ("sphere_peel_tau1e7_coreskip", {}),
-                                            ("vel_effect_peel", dict(core_skip=True)), ("slab_tau1e7", {}),
+                                            ("vel_effect_peel", {}), ("slab_tau1e7", {}),
                                             ("sphere_quadrant_tau1e7", {})],
                          ids=["sphere_peel_tau1e7", "coreskip", "vel_effect_peel_coreskip", "slab_tau1e7", "quadrant"])
 def test_headline_workloads_bounded_run_matches_oracle(workload, extra):

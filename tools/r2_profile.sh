@@ -4,7 +4,7 @@
 set -u
 O=gpurun_out
 python bench.py --steps 20 --warmup 5 > $O/r2_bench_n1.json 2> $O/r2_bench_n1.err
-for w in sphere_peel_tau1e7_coreskip vel_effect_peel slab_tau1e7 sphere_peel_tau1e4 sphere_octant_tau1e7 sphere_quadrant_tau1e7 box_periodic_tau1e7 clump_sphere_fcov5 amr_sphere_tau1e4 amr_sphere_tau1e7 clump_overlap_fcov3 sphere_tau1e7_calcJP_radial sphere_tau1e7_calcJP_cells box_shear_tau1e7 plane_atmosphere_tau1e6 spherical_atmosphere_tau1e6; do
+for w in sphere_peel_tau1e7_coreskip vel_effect_peel vel_effect_peel_as_shipped slab_tau1e7 sphere_peel_tau1e4 sphere_octant_tau1e7 sphere_quadrant_tau1e7 box_periodic_tau1e7 clump_sphere_fcov5 amr_sphere_tau1e4 amr_sphere_tau1e7 clump_overlap_fcov3 sphere_tau1e7_calcJP_radial sphere_tau1e7_calcJP_cells box_shear_tau1e7 plane_atmosphere_tau1e6 spherical_atmosphere_tau1e6; do
   timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --cpu-seconds 5 --complete-photons 0 > $O/r2_bench_$w.json 2> $O/r2_bench_$w.err
 done
 timeout 200 python bench.py --steps 10 --warmup 3 --flags 4 --skip-e2e --no-cpu-baseline --complete-photons 0 > $O/r2_bench_mono.json 2>/dev/null

@@ -2035,6 +2035,8 @@ __global__ void k_tau_batch(const __grid_constant__ DevParams P, long long n, do
     Photon ph;
     ph.x = x[i]; ph.y = y[i]; ph.z = z[i]; ph.kx = kx[i]; ph.ky = ky[i]; ph.kz = kz[i];
     ph.xfreq = xfreq[i]; ph.ic = ic[i]; ph.jc = jc[i]; ph.kc = kc[i]; ph.flags = PH_ALIVE; ph.xfreq_ref = 0.0;
+    ph.vshear = 0.0;  // a fresh photon (generate_photon.f90:141); shearing-box batches start without an offset
+    ph.wgt = 0.0;     // batch walks make no tallies: with CALCJ / CALCPnew on, their deposits are exact zeros
     CellData cs;
     int ns = walk_tau(P, vtab, ph, tau_in[i], cs);
     x[i] = ph.x; y[i] = ph.y; z[i] = ph.z; xfreq[i] = ph.xfreq; ic[i] = ph.ic; jc[i] = ph.jc; kc[i] = ph.kc;

@@ -112,3 +112,32 @@ def test_extras_are_refused_where_the_reference_has_no_such_binding():
     m.config.contents.par.xy_periodic = 0
     with pytest.raises(LartError):
         Simulation(m)
+
+
+def test_tau_walks_of_the_extra_bindings_are_bit_exact_and_leave_no_tally():
+    """raytrace_to_tau through the batch API under the shear / atmosphere / accumulator bindings: photon state after the walk
+    bit-identical to the oracle (a fresh photon carries vfy_shear = 0), masked cells end the walk, and a batch call leaves
+    the handle's tallies — the accumulators included — untouched."""
+    rng = np.random.default_rng(11)
+    cases = (SHEAR, ATM_PLANE, dict(ATM_SPH, nxim=0, nyim=0), dict(ATM_SPH, xy_symmetry=True, nx=12, ny=12, nz=23, nxim=0, nyim=0))
+    for kw in cases:
+        m = Model(**dict(kw, calc_J=True, calc_Pnew=True)).setup()
+        g = m.config.contents.grid
+        n = 20000
+        x = rng.uniform(g.xmin, g.xmax, n); y = rng.uniform(g.ymin, g.ymax, n); z = rng.uniform(g.zmin, g.zmax, n)
+        mu = rng.uniform(-1, 1, n); ph = rng.uniform(0, 2 * np.pi, n)
+        kx, ky, kz = np.sqrt(1 - mu * mu) * np.cos(ph), np.sqrt(1 - mu * mu) * np.sin(ph), mu
+        ic = np.floor((x - g.xmin) / g.dx).astype(np.int32) + 1
+        jc = np.floor((y - g.ymin) / g.dy).astype(np.int32) + 1
+        kc = np.floor((z - g.zmin) / g.dz).astype(np.int32) + 1
+        xf = rng.normal(0, 2, n)
+        tau_in = rng.exponential(size=n) * 5.0
+        sim = Simulation(m)
+        a = sim.raytrace_to_tau(x, y, z, kx, ky, kz, xf, ic, jc, kc, tau_in)
+        b = oracle.raytrace_to_tau(m.config, x, y, z, kx, ky, kz, xf, ic, jc, kc, tau_in)
+        for key in ("inside", "icell", "jcell", "kcell", "nsteps", "x", "y", "z", "xfreq"):
+            np.testing.assert_array_equal(a[key], b[key], err_msg=key)
+        assert 0.02 < a["inside"].mean() < 0.98
+        sim.output_reduce()   # fetch: nothing was tallied by the batch
+        sim.close()
+        assert m.jp_array("J").sum() == 0.0 and m.jp_array("Pnew").sum() == 0.0 and m.spectrum("Jout").sum() == 0.0

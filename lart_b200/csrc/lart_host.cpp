@@ -84,6 +84,7 @@ struct Par {
   std::string geometry, velocity_type;
   int nx = 1, ny = 1, nz = 11, nr = -999;
   double xmax = 1.0, ymax = 1.0, zmax = 1.0, rmin = -999.0, rmax = -999.0, source_rmax = -999.0;
+  double zmin = kNaN;  // define.f90: par%zmin, read by the plane-atmosphere geometry only
   double density_rscale = -999.9, density_zscale = -999.9, density_alpha = 0.0, velocity_alpha = 1.0;
   double xs_point = 0.0, ys_point = 0.0, zs_point = 0.0;
   double xfreq0 = 0.0, xfreq_min = kNaN, xfreq_max = kNaN;
@@ -222,7 +223,7 @@ int set_key(lart_host_model *m, std::string key, const std::string &value) {
   REAL(Omega) BOOL(calc_J) BOOL(calc_P) BOOL(calc_Pnew) BOOL(save_all) INT(geometry_JPa)
   STR(geometry) STR(velocity_type)
   INT(nx) INT(ny) INT(nz) INT(nr)
-  REAL(xmax) REAL(ymax) REAL(zmax) REAL(rmin) REAL(rmax) REAL(source_rmax)
+  REAL(xmax) REAL(ymax) REAL(zmax) REAL(zmin) REAL(rmin) REAL(rmax) REAL(source_rmax)
   REAL(density_rscale) REAL(density_zscale) REAL(density_alpha) REAL(velocity_alpha)
   REAL(xs_point) REAL(ys_point) REAL(zs_point)
   REAL(xfreq0) REAL(xfreq_min) REAL(xfreq_max) INT(nxfreq)
@@ -342,7 +343,9 @@ int derive(lart_host_model *m) {
   if (p.temperature0 <= 0.0) p.temperature0 = p.temperature;       // :127
   if (p.temperature <= 0.0 && p.bturb <= 0.0) { g_err = "par%temperature must be > 0 K (or set par%bturb > 0)"; return 1; }
   if (p.nx == 1 || p.ny == 1 || p.nz == 1) p.xyz_symmetry = false;  // :167
-  if (p.z_symmetry) { g_err = "z_symmetry grids stay with the Fortran host (xyz_symmetry and xy_symmetry are supported)"; return 1; }
+  // par%z_symmetry only changes the grid geometry (grid_mod_car.f90:135-150: z from 0, or from -dz/2, to zmax); setup.f90
+  // binds no ray tracer for it, so the plain open-box routines run on the half box — here too
+  if (p.z_symmetry && (p.xyz_symmetry || p.xy_symmetry)) p.z_symmetry = false;  // (the if / else-if chain of grid_mod_car.f90:92-135)
   if (p.xyz_symmetry) p.xy_symmetry = false;  // setup.f90:952-957: the xyz variant wins
   if ((p.xyz_symmetry || p.xy_symmetry) && p.xy_periodic) { g_err = "symmetry-folded and xy_periodic grids exclude each other"; return 1; }
   if (p.xy_symmetry && (p.nx == 1 || p.ny == 1)) { g_err = "xy_symmetry needs nx, ny > 1"; return 1; }
@@ -628,6 +631,13 @@ int grid_create(lart_host_model *m) {
   } else if (p.xy_symmetry) {  // :113-134 — a quadrant in x,y; the full height in z
     axis(nx, p.xmax, dx, xmin, i0); axis(ny, p.ymax, dy, ymin, j0);
     dz = 2.0 * p.zmax / nz; zmin = -p.zmax; k0 = 0;
+  } else if (p.z_symmetry) {  // :135-150 — the upper half in z, the full extent in x and y; k0 is set but never read
+    dx = 2.0 * p.xmax / nx; dy = 2.0 * p.ymax / ny; xmin = -p.xmax; ymin = -p.ymax;
+    axis(nz, p.zmax, dz, zmin, k0);
+  } else if (p.geometry == "plane_atmosphere") {  // :151-166 — the column runs from par%zmin (default 0) to zmax
+    dx = 2.0 * p.xmax / nx; dy = 2.0 * p.ymax / ny; xmin = -p.xmax; ymin = -p.ymax;
+    zmin = isfin(p.zmin) ? p.zmin : 0.0;
+    dz = (p.zmax - zmin) / nz;
   } else {
     dx = 2.0 * p.xmax / nx; dy = 2.0 * p.ymax / ny; dz = 2.0 * p.zmax / nz;
     xmin = -p.xmax; ymin = -p.ymax; zmin = -p.zmax;

@@ -33,6 +33,10 @@ CASES = {
     "plane_atmosphere_stokes_calc": (Model, dict(ATM_PLANE, use_stokes=True, calc_J=True, calc_P=True, calc_Pnew=True, **ALLPH)),
     "spherical_atmosphere_peel": (Model, dict(ATM_SPH, nxim=9, nyim=9, use_stokes=True, **ALLPH)),
     "spherical_atmosphere_xysym_calc": (Model, dict(ATM_SPH, xy_symmetry=True, nx=12, ny=12, nz=23, calc_Pnew=True, calc_J=True, **ALLPH)),
+    # par%z_symmetry: grid geometry only (grid_mod_car.f90:135-150), the plain open-box routines run on the upper half
+    "z_symmetry_half_box_even": (small_sphere, dict(z_symmetry=True, nx=16, ny=16, nz=16, zs_point=0.3, taumax=30.0, no_photons=800)),
+    "z_symmetry_half_box_odd_source_on_the_cut": (small_sphere, dict(z_symmetry=True, nx=15, ny=15, nz=15, taumax=30.0, no_photons=800,
+                                                                    use_stokes=False)),
     # shearing box
     "shear_box": (Model, dict(SHEAR, no_photons=1200, **ALLPH)),
     "shear_box_peel_velocity": (Model, dict(SHEAR, no_photons=800, nxim=9, nyim=9, velocity_type="parallel_velocity", Vy=15.0, Vx=5.0,

@@ -116,3 +116,20 @@ def test_shear_box_changes_frequencies_only_through_x_wraps():
     assert np.abs(a.spectrum("Jout") - b.spectrum("Jout")).sum() > 10.0  # the shear does move the spectrum
     with pytest.raises(LartError):
         Model(**dict(SHEAR, nx=1, ny=1)).setup()
+
+
+def test_z_symmetry_is_geometry_only():
+    """par%z_symmetry halves the grid in z (grid_mod_car.f90:135-150) and binds no ray tracer of its own (setup.f90:947-987):
+    zmin = 0 for an even nz, -dz/2 for an odd one; photons that reach the cut plane leave the grid."""
+    even = small_sphere(z_symmetry=True, nx=16, ny=16, nz=16, zs_point=0.3, nxim=0, nyim=0, no_photons=500)
+    odd = small_sphere(z_symmetry=True, nx=15, ny=15, nz=15, nxim=0, nyim=0, no_photons=500)
+    ge, go = even.config.contents.grid, odd.config.contents.grid
+    assert ge.zmin == 0.0 and ge.dz == pytest.approx(1.0 / 16) and ge.k0 == 1 and ge.xmin == -1.0 and ge.i0 == 0
+    assert go.dz == pytest.approx(1.0 / 14.5) and go.zmin == pytest.approx(-go.dz / 2) and go.k0 == 2
+    for m in (even, odd):
+        c = m.config.contents.par
+        assert c.xyz_symmetry == 0 and c.xy_symmetry == 0 and c.xy_periodic == 0
+        oracle.run(m, rng_mode=1, nthreads=4)
+        assert m.counters["n_photons_done"] == 500
+    # the odd grid's source sits inside the straddling first cell: half of the first flights leave through the cut at once
+    assert 0.2 * 500 < odd.spectrum("Jout").sum() <= 500.0

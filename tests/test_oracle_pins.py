@@ -106,7 +106,8 @@ def test_namelist_file_roundtrip(tmp_path):
     with pytest.raises(LartError):
         Model(no_such_key=1.0)
     with pytest.raises(LartError):
-        Model(z_symmetry=True, nx=3, ny=3).setup()  # stays with the Fortran host
+        Model(geometry="healpix_shell").setup()  # stays with the Fortran host
+    assert Model(z_symmetry=True, nx=4, ny=4, nz=4).setup().config.contents.grid.zmin == 0.0  # geometry only, as upstream
     with pytest.raises(LartError):
         Model(xy_symmetry=True, xy_periodic=True, nx=3, ny=3).setup()
     box = Model(xy_periodic=True, nx=3, ny=3, geometry="rectangle").setup()  # 3-D periodic box: the _xyper ray tracers

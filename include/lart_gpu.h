@@ -1,7 +1,8 @@
-/* lart_gpu.h — C ABI of the B200-native Cartesian photon-transport engine.
+/* lart_gpu.h — C ABI of the B200-native photon-transport engine.
  *
- * This is the drop-in boundary for ONE path of LaRT v2.00: the Cartesian-grid
- * Monte-Carlo photon loop.  Every entry point below is what a Fortran
+ * This is the drop-in boundary for ONE path of LaRT v2.00: the Monte-Carlo photon
+ * loop on the Cartesian grid (every binding of setup.f90:947-987), the clump medium
+ * and the octree.  Every entry point below is what a Fortran
  * ISO_C_BINDING interface block (shim/lart_gpu_shim.f90) binds;
  * each cites the reference interface it replaces (paths relative to the
  * reference tree, file:line).

@@ -1,8 +1,10 @@
 // lart_oracle.cpp — CPU ORACLE (test infrastructure, NOT product code).
 //
 // A scalar, one-photon-at-a-time FP64 restatement of the reference's Cartesian
-// photon loop (LaRT v2.00) — with its folded / periodic boundary variants, sight-line
-// maps and the clump medium — written to be read side by side with the Fortran.
+// photon loop (LaRT v2.00) — with its folded / periodic / shearing / atmosphere boundary
+// variants, sight-line maps, the CALCJ / CALCP / CALCPnew accumulators, the clump medium
+// (with and without overlapping clumps) and the octree — written to be read side by side
+// with the Fortran.
 // Every function cites the reference file:line it follows (paths relative to
 // the reference tree).  It exists so that the CUDA path has something to be
 // checked against: only tests/, __graft_entry__.smoke() and bench.py's
@@ -15,9 +17,12 @@
 // lines, (b) by the whole-run known answers the reference's logs hold
 // (<N_scatt> = 1.7898e3 / 2.8225e4, voigt_a, N(HI)_pole — tests/test_oracle_pins.py; for the clump medium the
 // population figures and <N_scatt> = 4.3454e3 of examples/clump_sphere/log_back — tests/test_oracle_clumps.py,
-// tests/test_gpu_clumps.py; all transcribed into tests/golden/reference_logs.json),
+// tests/test_gpu_clumps.py; for the octree nleaf = 178 480, N(HI)_pole and <N_scatt> = 2.8263e4 of
+// examples/amr_sphere_generic/log_amr_1M.txt — tests/test_oracle_amr.py; the documented J_out peaks of the 101^3 sphere —
+// tests/test_gpu_stats.py; all transcribed into tests/golden/reference_logs.json),
 // (c) by independent mathematics (Harris functions, scipy wofz, Neufeld/Dijkstra
-// analytic spectra, Philox and MT19937-64 known-answer vectors).
+// analytic spectra, Philox and MT19937-64 known-answer vectors, brute-force sums over all clumps for the overlap
+// event walk, binning identities and Pa ~ Pnew for the accumulators, photon conservation between Jout and Jabs2).
 //
 // The struct layouts come from the product's public header include/lart_gpu.h
 // (POD declarations only) so both sides consume identical host arrays.
